@@ -1,0 +1,305 @@
+"""ctypes bindings for oracle/libmcut_oracle.so (the plain-C restatement of the reference hot path)
+and, when present, oracle/_ref/libref_unit.so (doorways onto the unmodified reference).
+
+TEST INFRASTRUCTURE ONLY: importable from tests/, __graft_entry__.smoke() and bench.py's
+cpu_baseline / --impl reference legs.  The product package (mcut_b200/) never imports this module.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+from typing import Dict, Optional, Tuple
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB: Optional[C.CDLL] = None
+_REF: Optional[C.CDLL] = None
+
+c_dp = C.POINTER(C.c_double)
+c_u32p = C.POINTER(C.c_uint32)
+c_u64p = C.POINTER(C.c_uint64)
+
+
+class Soup(C.Structure):
+    _fields_ = [("nv", C.c_uint32), ("nf", C.c_uint32), ("ne", C.c_uint32), ("nh", C.c_uint32),
+                ("src_nv", C.c_uint32), ("src_nf", C.c_uint32),
+                ("xyz", c_dp), ("face_off", c_u32p), ("face_vtx", c_u32p), ("face_edge", c_u32p),
+                ("edge_v", c_u32p), ("edge_f", c_u32p)]
+
+
+class Test(C.Structure):
+    _fields_ = [("edge", C.c_uint32), ("face", C.c_uint32), ("type", C.c_char), ("pip", C.c_char),
+                ("sign_q", C.c_int8), ("sign_r", C.c_int8), ("exact_q", C.c_uint8), ("exact_r", C.c_uint8),
+                ("pad", C.c_uint8 * 2), ("point", C.c_double * 3)]
+
+
+class Record(C.Structure):
+    _fields_ = [("edge", C.c_uint32), ("face", C.c_uint32), ("point", C.c_double * 3)]
+
+
+class NarrowOut(C.Structure):
+    _fields_ = [("status", C.c_int), ("bad_face", C.c_uint32),
+                ("n_tests", C.c_size_t), ("n_records", C.c_size_t), ("n_edge_face_before_cull", C.c_size_t),
+                ("n_cand_faces", C.c_size_t),
+                ("tests", C.POINTER(Test)), ("records", C.POINTER(Record)),
+                ("cand_faces", c_u32p), ("cand_normal", c_dp), ("cand_d", c_dp), ("cand_maxcomp", C.POINTER(C.c_int32))]
+
+
+TEST_DTYPE = np.dtype([("edge", "<u4"), ("face", "<u4"), ("type", "S1"), ("pip", "S1"), ("sign_q", "i1"),
+                       ("sign_r", "i1"), ("exact_q", "u1"), ("exact_r", "u1"), ("pad", "u1", (2,)),
+                       ("point", "<f8", (3,))])
+RECORD_DTYPE = np.dtype([("edge", "<u4"), ("face", "<u4"), ("point", "<f8", (3,))])
+
+
+def build(force: bool = False) -> str:
+    """Compile oracle/libmcut_oracle.so (and oracle/_ref/* when /root/reference is present)."""
+    so = os.path.join(_HERE, "libmcut_oracle.so")
+    src = os.path.join(_HERE, "mcut_oracle.c")
+    if force or not os.path.exists(so) or os.path.getmtime(so) < os.path.getmtime(src):
+        subprocess.check_call(["make", "-C", _HERE, "oracle"], stdout=subprocess.DEVNULL)
+    return so
+
+
+def lib() -> C.CDLL:
+    global _LIB
+    if _LIB is None:
+        L = C.CDLL(build())
+        L.mco_vertex_parameters.argtypes = [C.c_int, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, c_dp, c_dp, c_dp, c_dp]
+        L.mco_vertex_parameters.restype = None
+        L.mco_transform_vertices.argtypes = [C.c_int, C.c_void_p, C.c_uint32, c_dp, c_dp, c_dp, c_dp]
+        L.mco_transform_vertices.restype = None
+        L.mco_cut_bbox_eps.argtypes = [c_dp, C.c_double, C.c_int]
+        L.mco_cut_bbox_eps.restype = C.c_double
+        L.mco_face_bboxes.argtypes = [c_dp, c_u32p, c_u32p, C.c_uint32, C.c_double, c_dp, c_dp]
+        L.mco_face_bboxes.restype = None
+        L.mco_morton3D.argtypes = [C.c_float, C.c_float, C.c_float]
+        L.mco_morton3D.restype = C.c_uint32
+        L.mco_morton_codes.argtypes = [c_dp, C.c_uint32, c_dp, c_u32p]
+        L.mco_morton_codes.restype = None
+        L.mco_oibvh_size.argtypes = [C.c_int]
+        L.mco_oibvh_size.restype = C.c_int
+        L.mco_oibvh_pairs.argtypes = [c_dp, C.c_uint32, c_dp, C.c_uint32, C.POINTER(c_u64p), c_u64p]
+        L.mco_oibvh_pairs.restype = C.c_size_t
+        L.mco_grid_pairs.argtypes = [c_dp, C.c_uint32, c_dp, C.c_uint32, C.POINTER(c_u64p)]
+        L.mco_grid_pairs.restype = C.c_size_t
+        L.mco_free.argtypes = [C.c_void_p]
+        L.mco_free.restype = None
+        L.mco_soup_build.argtypes = [c_dp, C.c_uint32, c_u32p, c_u32p, C.c_uint32, c_dp, C.c_uint32, c_u32p, c_u32p,
+                                     C.c_uint32, C.POINTER(Soup)]
+        L.mco_soup_build.restype = C.c_int
+        L.mco_soup_free.argtypes = [C.POINTER(Soup)]
+        L.mco_soup_free.restype = None
+        L.mco_plane_coefficients.argtypes = [c_dp, C.c_int, c_dp, c_dp]
+        L.mco_plane_coefficients.restype = C.c_int
+        L.mco_orient3d.argtypes = [c_dp, c_dp, c_dp, c_dp]
+        L.mco_orient3d.restype = C.c_double
+        L.mco_orient3d_stageA.argtypes = [c_dp, c_dp, c_dp, c_dp, C.POINTER(C.c_int)]
+        L.mco_orient3d_stageA.restype = C.c_double
+        L.mco_orient2d.argtypes = [c_dp, c_dp, c_dp]
+        L.mco_orient2d.restype = C.c_double
+        L.mco_segment_plane_type.argtypes = [c_dp, c_dp, c_dp, C.c_int, c_dp, C.c_int, c_dp, c_dp]
+        L.mco_segment_plane_type.restype = C.c_char
+        L.mco_segment_plane_intersection.argtypes = [c_dp, c_dp, C.c_double, c_dp, c_dp]
+        L.mco_segment_plane_intersection.restype = C.c_char
+        L.mco_projection_matrix.argtypes = [c_dp, C.c_int, c_dp]
+        L.mco_projection_matrix.restype = None
+        L.mco_point_in_polygon.argtypes = [c_dp, c_dp, C.c_int, c_dp, C.c_int]
+        L.mco_point_in_polygon.restype = C.c_char
+        L.mco_narrowphase.argtypes = [C.POINTER(Soup), c_u64p, C.c_size_t, c_dp, c_dp, C.c_int, C.POINTER(NarrowOut)]
+        L.mco_narrowphase.restype = C.c_int
+        L.mco_narrow_free.argtypes = [C.POINTER(NarrowOut)]
+        L.mco_narrow_free.restype = None
+        _LIB = L
+    return _LIB
+
+
+def ref_available() -> bool:
+    return os.path.exists(os.path.join(_HERE, "_ref", "libref_unit.so"))
+
+
+def ref() -> C.CDLL:
+    """Doorways onto the unmodified reference (oracle/_ref/libref_unit.so)."""
+    global _REF
+    if _REF is None:
+        R = C.CDLL(os.path.join(_HERE, "_ref", "libref_unit.so"))
+        R.ref_morton3D.argtypes = [C.c_float, C.c_float, C.c_float]
+        R.ref_morton3D.restype = C.c_uint32
+        R.ref_oibvh_size.argtypes = [C.c_int]
+        R.ref_oibvh_size.restype = C.c_int
+        R.ref_orient3d.argtypes = [c_dp, c_dp, c_dp, c_dp]
+        R.ref_orient3d.restype = C.c_double
+        R.ref_orient2d.argtypes = [c_dp, c_dp, c_dp]
+        R.ref_orient2d.restype = C.c_double
+        R.ref_plane_coefficients.argtypes = [c_dp, C.c_int, c_dp, c_dp]
+        R.ref_plane_coefficients.restype = C.c_int
+        R.ref_segment_plane_type.argtypes = [c_dp, c_dp, c_dp, C.c_int, c_dp, C.c_int]
+        R.ref_segment_plane_type.restype = C.c_char
+        R.ref_segment_plane_intersection.argtypes = [c_dp, c_dp, C.c_double, c_dp, c_dp]
+        R.ref_segment_plane_intersection.restype = C.c_char
+        R.ref_point_in_polygon.argtypes = [c_dp, c_dp, C.c_int, c_dp, C.c_int]
+        R.ref_point_in_polygon.restype = C.c_char
+        R.ref_vertex_parameters.argtypes = [C.c_uint, C.c_void_p, C.c_uint, C.c_void_p, C.c_uint, c_dp, c_dp, c_dp, c_dp]
+        R.ref_vertex_parameters.restype = C.c_int
+        _REF = R
+    return _REF
+
+
+# ------------------------------------------------------------------------------------------------
+# numpy-level helpers
+# ------------------------------------------------------------------------------------------------
+def dp(a: np.ndarray):
+    assert a.dtype == np.float64 and a.flags.c_contiguous
+    return a.ctypes.data_as(c_dp)
+
+
+def u32p(a: np.ndarray):
+    assert a.dtype == np.uint32 and a.flags.c_contiguous
+    return a.ctypes.data_as(c_u32p)
+
+
+def face_offsets(faces: np.ndarray, sizes: Optional[np.ndarray]) -> np.ndarray:
+    if sizes is None:
+        return np.arange(0, faces.size + 1, 3, dtype=np.uint32)
+    off = np.zeros(sizes.size + 1, dtype=np.uint32)
+    np.cumsum(sizes, out=off[1:])
+    return off
+
+
+def vertex_parameters(src_xyz: np.ndarray, cut_xyz: np.ndarray):
+    is_float = src_xyz.dtype == np.float32
+    src = np.ascontiguousarray(src_xyz)
+    cut = np.ascontiguousarray(cut_xyz)
+    com = np.zeros(3)
+    shift = np.zeros(3)
+    sb = np.zeros(6)
+    cb = np.zeros(6)
+    lib().mco_vertex_parameters(int(is_float), src.ctypes.data, src.shape[0], cut.ctypes.data, cut.shape[0], dp(com),
+                                dp(shift), dp(sb), dp(cb))
+    return com, shift, sb, cb
+
+
+def transform_vertices(xyz: np.ndarray, com: np.ndarray, shift: np.ndarray, perturbation: Optional[np.ndarray] = None):
+    is_float = xyz.dtype == np.float32
+    a = np.ascontiguousarray(xyz)
+    out = np.zeros((a.shape[0], 3))
+    pert = None if perturbation is None else dp(np.ascontiguousarray(perturbation, dtype=np.float64))
+    lib().mco_transform_vertices(int(is_float), a.ctypes.data, a.shape[0], dp(com), dp(shift), pert, dp(out))
+    return out
+
+
+def face_bboxes(xyz: np.ndarray, off: np.ndarray, vtx: np.ndarray, eps: float):
+    nf = off.size - 1
+    bb = np.zeros((nf, 6))
+    root = np.zeros(6)
+    lib().mco_face_bboxes(dp(xyz), u32p(off), u32p(vtx), nf, float(eps), dp(bb), dp(root))
+    return bb, root
+
+
+def morton_codes(bb: np.ndarray, root: np.ndarray) -> np.ndarray:
+    codes = np.zeros(bb.shape[0], dtype=np.uint32)
+    lib().mco_morton_codes(dp(bb), bb.shape[0], dp(root), u32p(codes))
+    return codes
+
+
+def _take_pairs(n: int, ptr) -> np.ndarray:
+    out = np.ctypeslib.as_array(ptr, shape=(n,)).copy() if n else np.zeros(0, dtype=np.uint64)
+    lib().mco_free(ptr)
+    return out
+
+
+def oibvh_pairs(src_bb: np.ndarray, cut_bb: np.ndarray) -> Tuple[np.ndarray, int]:
+    ptr = c_u64p()
+    nt = C.c_uint64(0)
+    n = lib().mco_oibvh_pairs(dp(src_bb), src_bb.shape[0], dp(cut_bb), cut_bb.shape[0], C.byref(ptr), C.byref(nt))
+    return _take_pairs(n, ptr), int(nt.value)
+
+
+def grid_pairs(src_bb: np.ndarray, cut_bb: np.ndarray) -> np.ndarray:
+    ptr = c_u64p()
+    n = lib().mco_grid_pairs(dp(src_bb), src_bb.shape[0], dp(cut_bb), cut_bb.shape[0], C.byref(ptr))
+    return np.sort(_take_pairs(n, ptr))
+
+
+class SoupHandle:
+    """Owns an mco_soup_t and exposes its arrays as numpy views (copied)."""
+
+    def __init__(self, src_xyz, src_off, src_vtx, cut_xyz, cut_off, cut_vtx):
+        self.c = Soup()
+        rc = lib().mco_soup_build(dp(src_xyz), src_xyz.shape[0], u32p(src_off), u32p(src_vtx), src_off.size - 1,
+                                  dp(cut_xyz), cut_xyz.shape[0], u32p(cut_off), u32p(cut_vtx), cut_off.size - 1,
+                                  C.byref(self.c))
+        if rc != 0:
+            raise ValueError("soup build failed: non-manifold edge or inconsistent winding")
+        c = self.c
+        as_arr = np.ctypeslib.as_array
+        self.xyz = as_arr(c.xyz, shape=(c.nv, 3)).copy()
+        self.face_off = as_arr(c.face_off, shape=(c.nf + 1,)).copy()
+        self.face_vtx = as_arr(c.face_vtx, shape=(c.nh,)).copy()
+        self.face_edge = as_arr(c.face_edge, shape=(c.nh,)).copy()
+        self.edge_v = as_arr(c.edge_v, shape=(c.ne, 2)).copy()
+        self.edge_f = as_arr(c.edge_f, shape=(c.ne, 2)).copy()
+        self.nv, self.nf, self.ne, self.nh = c.nv, c.nf, c.ne, c.nh
+        self.src_nv, self.src_nf = c.src_nv, c.src_nf
+
+    def __del__(self):
+        try:
+            lib().mco_soup_free(C.byref(self.c))
+        except Exception:
+            pass
+
+
+def narrowphase(soup: SoupHandle, pairs: np.ndarray, src_bb: np.ndarray, cut_bb: np.ndarray, stop_on_gp: bool = True
+                ) -> Dict[str, object]:
+    out = NarrowOut()
+    pairs = np.ascontiguousarray(pairs, dtype=np.uint64)
+    lib().mco_narrowphase(C.byref(soup.c), pairs.ctypes.data_as(c_u64p), pairs.size, dp(src_bb), dp(cut_bb),
+                          int(stop_on_gp), C.byref(out))
+    res: Dict[str, object] = {"status": int(out.status), "bad_face": int(out.bad_face),
+                              "n_edge_face_before_cull": int(out.n_edge_face_before_cull)}
+    nt, nr, nc = out.n_tests, out.n_records, out.n_cand_faces
+    if nt:
+        buf = C.string_at(out.tests, nt * C.sizeof(Test))
+        res["tests"] = np.frombuffer(buf, dtype=TEST_DTYPE).copy()
+    else:
+        res["tests"] = np.zeros(0, dtype=TEST_DTYPE)
+    if nr:
+        buf = C.string_at(out.records, nr * C.sizeof(Record))
+        res["records"] = np.frombuffer(buf, dtype=RECORD_DTYPE).copy()
+    else:
+        res["records"] = np.zeros(0, dtype=RECORD_DTYPE)
+    if nc and out.status in (0, 1):
+        res["cand_faces"] = np.ctypeslib.as_array(out.cand_faces, shape=(nc,)).copy()
+        res["cand_normal"] = np.ctypeslib.as_array(out.cand_normal, shape=(nc, 3)).copy()
+        res["cand_d"] = np.ctypeslib.as_array(out.cand_d, shape=(nc,)).copy()
+        res["cand_maxcomp"] = np.ctypeslib.as_array(out.cand_maxcomp, shape=(nc,)).copy()
+    else:
+        res["cand_faces"] = np.zeros(0, dtype=np.uint32)
+        res["cand_normal"] = np.zeros((0, 3))
+        res["cand_d"] = np.zeros(0)
+        res["cand_maxcomp"] = np.zeros(0, dtype=np.int32)
+    lib().mco_narrow_free(C.byref(out))
+    return res
+
+
+def intersect_stage(src, cut, flags: int, gp_constant: float = 1e-4, perturbation=None) -> Dict[str, object]:
+    """The whole intersect stage of one kernel invocation on user arrays (the oracle's mcDispatch slice):
+    re-centring -> face boxes -> candidate pairs -> polygon soup -> narrowphase."""
+    from mcut_b200 import meshgen as mg  # flag constants only
+    sx, sf, ss = src
+    cx, cf, cs = cut
+    com, shift, sbb, cbb = vertex_parameters(sx, cx)
+    sxi = transform_vertices(sx, com, shift)
+    cxi0 = transform_vertices(cx, com, shift)
+    cxi = cxi0 if perturbation is None else transform_vertices(cx, com, shift, perturbation)
+    soff, coff = face_offsets(sf, ss), face_offsets(cf, cs)
+    eps = lib().mco_cut_bbox_eps(dp(cbb), gp_constant, int(bool(flags & mg.MC_DISPATCH_ENFORCE_GENERAL_POSITION_ABSOLUTE)))
+    sb, sroot = face_bboxes(sxi, soff, np.ascontiguousarray(sf), 0.0)
+    cb, croot = face_bboxes(cxi0, coff, np.ascontiguousarray(cf), eps)  # boxes come from the UNperturbed cut mesh
+    pairs, ntests = oibvh_pairs(sb, cb)
+    soup = SoupHandle(sxi, soff, np.ascontiguousarray(sf), cxi, coff, np.ascontiguousarray(cf))
+    nar = narrowphase(soup, pairs, sb, cb)
+    nar.update({"com": com, "shift": shift, "eps": eps, "src_bboxes": sb, "cut_bboxes": cb, "src_root": sroot,
+                "cut_root": croot, "pairs": pairs, "bvh_tests": ntests, "soup": soup, "src_xyz": sxi, "cut_xyz": cxi})
+    return nar
