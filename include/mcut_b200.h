@@ -1,0 +1,187 @@
+/* include/mcut_b200.h — C-ABI of the B200-native intersection-detection stage for MCUT.
+ *
+ * This is the drop-in boundary: plain C, pointers and sizes only, no C++/torch types, no exceptions.
+ * Everything behind it is hand-written CUDA for sm_100a (mcut_b200/csrc/).  There is NO CPU fallback:
+ * every entry point that computes returns MCB200_ERR_NO_DEVICE / a CUDA error when no B200 is usable.
+ *
+ * What each group replaces in the reference (cutdigital/mcut; paths relative to the reference root):
+ *
+ *   mcb200_vertex_parameters / mcb200_cut_bbox_eps      source/preproc.cpp:2124-2290, :2518, :2667-2675
+ *        (host, sequential on purpose: the centre of mass is an order-dependent sum — SURVEY §7 hard part 2)
+ *   mcb200_soup_ids                                     source/kernel.cpp:1593-1732 + hmesh.cpp:406-651,705-733
+ *        (host: polygon-soup face/edge numbering rules; input to the narrowphase, like `ps` is in the reference)
+ *   mcb200_mesh_create / mcb200_mesh_set_frame          source/preproc.cpp:91-185 (x' = (x - com) + shift [+ perturbation])
+ *   mcb200_bvh_build                                    build_oibvh(), include/mcut/internal/bvh.h:117-125,
+ *                                                       source/bvh.cpp:219-636   (face AABBs, root AABB, Morton, sort, tree, refit)
+ *   mcb200_bvh_intersect                                intersectOIBVHs(), bvh.h:127-133, source/bvh.cpp:638-783
+ *   mcb200_narrowphase                                  dispatch(), source/kernel.cpp:1779-3231 (edge/face tests,
+ *                                                       intersection points, registry), arithmetic of source/math.cpp
+ *                                                       :130-287,:391-427,:553-902 and source/shewchuk.c:1611-2410
+ *   mcb200_intersect_stage                              the three of them back to back without host round trips
+ *
+ * Conventions: every function returns 0 on success, a negative MCB200_ERR_* or a positive cudaError_t otherwise;
+ * mcb200_last_error() gives the text.  Host arrays are borrowed for the duration of the call only.  One
+ * context = one device + one stream; a context may be used by one host thread at a time, different contexts
+ * are independent (the MultipleContextsInParallel pattern maps one MCUT context to one mcb200_ctx).
+ * Ids: source faces keep their index, cut faces are reported cut-mesh-local in pairs and as Fs + id
+ * ("polygon-soup id", kernel.cpp:153-156) in narrowphase records; same for vertices and edges.
+ */
+#ifndef MCUT_B200_H_
+#define MCUT_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MCB200_NULL 0xFFFFFFFFu
+
+enum {
+    MCB200_OK = 0,
+    MCB200_ERR_NO_DEVICE = -1, /* no CUDA device / not an sm_100 part: the product never falls back to the CPU */
+    MCB200_ERR_INVALID = -2, /* bad argument (NULL, zero faces, face smaller than a triangle, ...) */
+    MCB200_ERR_NON_MANIFOLD = -3, /* mcb200_soup_ids: an edge is used twice in the same direction (hmesh.cpp:612-628) */
+    MCB200_ERR_CAPACITY = -4, /* caller-provided output array too small; required size is returned */
+    MCB200_ERR_INTERNAL = -5
+};
+
+/* narrowphase status, the values of status_t in include/mcut/internal/kernel.h that this stage can produce */
+enum {
+    MCB200_STATUS_SUCCESS = 0,
+    MCB200_STATUS_GENERAL_POSITION_VIOLATION = 1,
+    MCB200_STATUS_INVALID_SRC_MESH = 2,
+    MCB200_STATUS_INVALID_CUT_MESH = 3
+};
+
+typedef struct mcb200_ctx mcb200_ctx;
+typedef struct mcb200_mesh mcb200_mesh; /* device-resident mesh (+ its face AABBs and LBVH once built) */
+typedef struct mcb200_soup mcb200_soup; /* device-resident polygon-soup topology of a (source, cut) pair */
+typedef struct mcb200_result mcb200_result; /* device-resident outputs of traversal + narrowphase */
+
+/* ---------------------------------------------------------------- context ---------------------------------- */
+int mcb200_device_count(void);
+/* stream == NULL: the context creates its own non-blocking stream.  Otherwise `stream` is a cudaStream_t the
+ * caller owns (e.g. torch.cuda.current_stream().cuda_stream) and all work is enqueued on it. */
+int mcb200_ctx_create(int device, void* stream, mcb200_ctx** ctx);
+void mcb200_ctx_destroy(mcb200_ctx* ctx);
+const char* mcb200_last_error(const mcb200_ctx* ctx); /* ctx may be NULL: last error of ctx creation */
+int mcb200_ctx_sync(mcb200_ctx* ctx);
+/* number of kernels this context has launched so far (bench.py's gpu_launches) */
+uint64_t mcb200_ctx_launch_count(const mcb200_ctx* ctx);
+
+/* ---------------------------------------------------------------- host-side logic (no GPU) ----------------- */
+void mcb200_vertex_parameters(int is_float, const void* src_xyz, uint32_t nsv, const void* cut_xyz, uint32_t ncv,
+    double com[3], double shift[3], double src_bbox[6], double cut_bbox[6]);
+double mcb200_cut_bbox_eps(const double cut_bbox[6], double gp_constant, int absolute);
+/* Polygon-soup ids.  *_off are face offsets ([nf+1]); *_vtx the user's vertex lists.  Outputs (caller-allocated):
+ *   face_vtx[nh], face_edge[nh]  (nh = src_off[nsf] + cut_off[ncf]) in ps.get_vertices_around_face order,
+ *   edge_v[2*nh], edge_f[2*nh]   (first *ne rows valid): source(h0), target(h0) / face(h0), face(h1)|MCB200_NULL */
+int mcb200_soup_ids(uint32_t nsv, const uint32_t* src_off, const uint32_t* src_vtx, uint32_t nsf, const uint32_t* cut_off,
+    const uint32_t* cut_vtx, uint32_t ncf, uint32_t* face_vtx, uint32_t* face_edge, uint32_t* edge_v, uint32_t* edge_f,
+    uint32_t* ne);
+
+/* ---------------------------------------------------------------- meshes ----------------------------------- */
+/* Uploads the user's arrays as they are (float or double vertices; face_sizes == NULL means triangles,
+ * preproc.cpp:206).  No geometry is computed here. */
+int mcb200_mesh_create(mcb200_ctx* ctx, int is_float, const void* xyz, uint32_t nv, const uint32_t* face_vtx,
+    const uint32_t* face_sizes, uint32_t nf, mcb200_mesh** mesh);
+/* Same, from arrays that already live on this context's device (no copy is made of xyz/face_vtx; face_off may be
+ * NULL for triangles).  Used when inputs are resident in HBM. */
+int mcb200_mesh_adopt_device(mcb200_ctx* ctx, int is_float, const void* d_xyz, uint32_t nv, const uint32_t* d_face_vtx,
+    const uint32_t* d_face_off, uint32_t nf, uint32_t nh, mcb200_mesh** mesh);
+/* Frame of the internal coordinates: x' = (x - com) + shift (+ perturbation).  com == NULL: the vertices already
+ * are internal coordinates (double only).  The transform is applied on the fly by every kernel that reads a
+ * vertex (bit-identical to materialising it, and a perturbation retry costs nothing). */
+int mcb200_mesh_set_frame(mcb200_ctx* ctx, mcb200_mesh* mesh, const double com[3], const double shift[3],
+    const double perturbation[3] /* or NULL */);
+void mcb200_mesh_free(mcb200_ctx* ctx, mcb200_mesh* mesh);
+
+/* ---------------------------------------------------------------- (1) LBVH build --------------------------- */
+/* Face AABBs (enlarged by eps when eps > 0), mesh AABB, 30-bit Morton codes of the reference's formula, one-sweep
+ * radix sort, Karras tree, atomic bottom-up refit.  Asynchronous on the context's stream. */
+int mcb200_bvh_build(mcb200_ctx* ctx, mcb200_mesh* mesh, double eps);
+/* D2H of what build_oibvh() hands back to its caller: face_bboxes [nf*6] (min xyz, max xyz; may be NULL) and the
+ * mesh AABB (bvhAABBs[0]).  Synchronises the stream. */
+int mcb200_bvh_read(mcb200_ctx* ctx, const mcb200_mesh* mesh, double* face_bboxes, double root_bbox[6]);
+/* debugging / parity: Morton codes [nf] by face id and the sorted leaf order [nf] */
+int mcb200_bvh_read_morton(mcb200_ctx* ctx, const mcb200_mesh* mesh, uint32_t* codes_by_face, uint32_t* sorted_faces);
+
+/* ---------------------------------------------------------------- results ---------------------------------- */
+int mcb200_result_create(mcb200_ctx* ctx, mcb200_result** res);
+void mcb200_result_free(mcb200_ctx* ctx, mcb200_result* res);
+
+typedef struct mcb200_counts {
+    uint64_t n_pairs; /* candidate face pairs (closed-interval AABB overlap) */
+    uint64_t n_node_tests; /* AABB tests the traversal performed (tree nodes + leaf boxes) */
+    uint64_t n_tests; /* edge/face tests that survived ownership + AABB cull */
+    uint64_t n_exact; /* of those, how many needed the exact-expansion orient3d stage */
+    uint64_t n_records; /* intersection points registered */
+    uint64_t n_cand_faces; /* faces that appear in at least one pair */
+    int32_t status; /* MCB200_STATUS_* */
+    uint32_t bad_face; /* polygon-soup id of a degenerate candidate face when status is INVALID_* */
+} mcb200_counts;
+
+/* ---------------------------------------------------------------- (2) traversal ---------------------------- */
+/* Both meshes must have been built.  Leaves `n_pairs` pairs on the device, sorted ascending by
+ * (src_face << 32 | cut_face).  Asynchronous. */
+int mcb200_bvh_intersect(mcb200_ctx* ctx, const mcb200_mesh* src, const mcb200_mesh* cut, mcb200_result* res);
+/* Restrict the traversal to a slice of the query leaf range (multi-GPU sharding of one huge dispatch):
+ * chunks of `chunk` consecutive Morton-ordered leaves are dealt round-robin, this call handles the chunks with
+ * index % nparts == part.  nparts == 1 restores the full range. */
+int mcb200_result_set_shard(mcb200_ctx* ctx, mcb200_result* res, uint32_t part, uint32_t nparts, uint32_t chunk);
+
+/* ---------------------------------------------------------------- (3) narrowphase -------------------------- */
+int mcb200_soup_create(mcb200_ctx* ctx, uint32_t nsf, uint32_t ncf, uint32_t nh, uint32_t ne, const uint32_t* face_vtx,
+    const uint32_t* face_edge, const uint32_t* edge_f, mcb200_soup** soup);
+void mcb200_soup_free(mcb200_ctx* ctx, mcb200_soup* soup);
+/* Builds the soup ids on the host from the two meshes' face arrays and uploads them (mcb200_soup_ids + create). */
+int mcb200_soup_from_meshes(mcb200_ctx* ctx, const mcb200_mesh* src, const mcb200_mesh* cut, mcb200_soup** soup);
+
+#define MCB200_NARROW_LOG_TESTS 1u /* also keep one log entry per edge/face test (parity checks) */
+/* Consumes res's pairs; uses the face AABBs of the meshes' builds (cut ones enlarged) for the edge cull and the
+ * meshes' CURRENT frames for coordinates (so a perturbed cut frame is tested against unperturbed boxes, exactly
+ * like preproc.cpp:2562-2945).  Asynchronous. */
+int mcb200_narrowphase(mcb200_ctx* ctx, const mcb200_soup* soup, const mcb200_mesh* src, const mcb200_mesh* cut,
+    mcb200_result* res, uint32_t flags);
+
+/* build(src) + build(cut) + intersect + narrowphase, nothing but kernel launches in between */
+int mcb200_intersect_stage(mcb200_ctx* ctx, mcb200_mesh* src, mcb200_mesh* cut, double cut_eps, const mcb200_soup* soup,
+    mcb200_result* res, uint32_t flags);
+
+/* ---------------------------------------------------------------- reading results (D2H, synchronising) ----- */
+int mcb200_result_counts(mcb200_ctx* ctx, mcb200_result* res, mcb200_counts* out);
+int mcb200_result_read_pairs(mcb200_ctx* ctx, mcb200_result* res, uint64_t* pairs, size_t capacity);
+
+typedef struct mcb200_record {
+    uint32_t edge, face; /* polygon-soup ids: the tested edge and the face it pierces */
+    double point[3]; /* intersection point, the reference's q + t (r - q) */
+} mcb200_record;
+/* sorted by (edge, face): the canonical registry order */
+int mcb200_result_read_records(mcb200_ctx* ctx, mcb200_result* res, mcb200_record* records, size_t capacity);
+
+typedef struct mcb200_test {
+    uint32_t edge, face;
+    char type; /* '0' '1' 'p' 'q' 'r' (math.cpp:391-427) */
+    char pip; /* 'i' 'o' 'e' 'v' or 0 */
+    int8_t sign_q, sign_r; /* signs of the two orient3d determinants */
+    uint8_t exact; /* bit0/bit1: q / r needed the exact stage */
+    uint8_t pad[3];
+    double point[3];
+} mcb200_test;
+/* only when MCB200_NARROW_LOG_TESTS was passed; sorted by (edge, face) */
+int mcb200_result_read_tests(mcb200_ctx* ctx, mcb200_result* res, mcb200_test* tests, size_t capacity);
+/* plane data of the candidate faces (keys of ps_face_to_potentially_intersecting_others), ascending face id:
+ * faces[n], normal[n*3], d[n], max_comp[n] — kernel.cpp:2184-2356, consumed downstream by the host */
+int mcb200_result_read_planes(mcb200_ctx* ctx, mcb200_result* res, uint32_t* faces, double* normal, double* d,
+    int32_t* max_comp, size_t capacity);
+
+/* device pointers of the result buffers (for collectives that gather them, e.g. NCCL all-gather in bench.py):
+ * which: 0 pairs (u64), 1 records (mcb200_record).  *count is the element count (synchronises). */
+int mcb200_result_device_ptr(mcb200_ctx* ctx, mcb200_result* res, int which, void** dptr, uint64_t* count);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MCUT_B200_H_ */

@@ -1,0 +1,571 @@
+// mcut_b200/csrc/api.cu — the C-ABI of include/mcut_b200.h: handle management, H2D/D2H, stage launchers.
+// No computation happens on the host here except argument checking and the final ordering of the (few) candidate
+// faces' plane rows; there is no CPU fallback for any device stage.
+#include <algorithm>
+#include <cstddef>
+#include <mutex>
+#include <numeric>
+
+#include "internal.h"
+
+namespace {
+std::string g_create_error;
+std::mutex g_create_mutex;
+
+int fail(mcb200_ctx* ctx, int code, const char* msg, const char* file, int line)
+{
+    if (ctx) ctx->set_error(msg, file, line);
+    return code;
+}
+#define MCB_FAIL(ctx, code, msg) return fail((ctx), (code), (msg), __FILE__, __LINE__)
+
+int fetch_counters(mcb200_ctx* ctx, mcb200_result* res)
+{
+    if (res->h_valid) return 0;
+    if (!res->counters.p) MCB_FAIL(ctx, MCB200_ERR_INVALID, "result has not been produced yet");
+    MCB_TRY(ctx->pinned(sizeof(result_counters_t)));
+    MCB_CUDA(ctx, cudaMemcpyAsync(ctx->h_pinned, res->counters.p, sizeof(result_counters_t), cudaMemcpyDeviceToHost, ctx->stream));
+    MCB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    std::memcpy(&res->h, ctx->h_pinned, sizeof(result_counters_t));
+    res->h_valid = true;
+    return 0;
+}
+
+int upload(mcb200_ctx* ctx, dbuf& dst, const void* src, size_t bytes)
+{
+    MCB_TRY(ctx->reserve(dst, bytes ? bytes : 16));
+    if (bytes) MCB_CUDA(ctx, cudaMemcpyAsync(dst.p, src, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    return 0;
+}
+} // namespace
+
+extern "C" {
+
+int mcb200_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+    return n;
+}
+
+int mcb200_ctx_create(int device, void* stream, mcb200_ctx** out)
+{
+    std::lock_guard<std::mutex> lk(g_create_mutex);
+    if (!out) return MCB200_ERR_INVALID;
+    *out = nullptr;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0) {
+        g_create_error = std::string("no CUDA device: ") + (e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0")
+            + " — mcut_b200 has no CPU fallback";
+        return MCB200_ERR_NO_DEVICE;
+    }
+    if (device < 0 || device >= n) {
+        g_create_error = "device index out of range";
+        return MCB200_ERR_INVALID;
+    }
+    cudaDeviceProp prop;
+    if ((e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess) {
+        g_create_error = std::string("cudaGetDeviceProperties: ") + cudaGetErrorString(e);
+        return (int)e;
+    }
+    if (prop.major != 10) {
+        g_create_error = std::string("device '") + prop.name + "' is sm_" + std::to_string(prop.major) + std::to_string(prop.minor)
+            + "; this library carries sm_100a code only";
+        return MCB200_ERR_NO_DEVICE;
+    }
+    if ((e = cudaSetDevice(device)) != cudaSuccess) {
+        g_create_error = std::string("cudaSetDevice: ") + cudaGetErrorString(e);
+        return (int)e;
+    }
+    mcb200_ctx* ctx = new mcb200_ctx();
+    ctx->device = device;
+    ctx->num_sms = prop.multiProcessorCount;
+    if (stream) {
+        ctx->stream = reinterpret_cast<cudaStream_t>(stream);
+        ctx->owns_stream = false;
+    } else {
+        if ((e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess) {
+            g_create_error = std::string("cudaStreamCreate: ") + cudaGetErrorString(e);
+            delete ctx;
+            return (int)e;
+        }
+        ctx->owns_stream = true;
+    }
+    // keep freed blocks in the pool: repeated dispatches reuse them without going back to the driver
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+        uint64_t thr = UINT64_MAX;
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+    }
+    *out = ctx;
+    return 0;
+}
+
+void mcb200_ctx_destroy(mcb200_ctx* ctx)
+{
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    ctx->release(ctx->sort_keys_alt);
+    ctx->release(ctx->sort_vals_alt);
+    ctx->release(ctx->sort_hist);
+    ctx->release(ctx->sort_status);
+    ctx->release(ctx->sort_tilectr);
+    cudaStreamSynchronize(ctx->stream);
+    if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
+    if (ctx->owns_stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+const char* mcb200_last_error(const mcb200_ctx* ctx)
+{
+    if (!ctx) return g_create_error.c_str();
+    return ctx->error.c_str();
+}
+
+int mcb200_ctx_sync(mcb200_ctx* ctx)
+{
+    if (!ctx) return MCB200_ERR_INVALID;
+    MCB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+uint64_t mcb200_ctx_launch_count(const mcb200_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+// ---------------------------------------------------------------------------------------------------------- meshes
+
+static void identity_frame(frame_t& fr, int is_float)
+{
+    std::memset(&fr, 0, sizeof(fr));
+    fr.is_float = is_float;
+}
+
+int mcb200_mesh_create(mcb200_ctx* ctx, int is_float, const void* xyz, uint32_t nv, const uint32_t* face_vtx,
+    const uint32_t* face_sizes, uint32_t nf, mcb200_mesh** out)
+{
+    if (!ctx || !out) return MCB200_ERR_INVALID;
+    *out = nullptr;
+    if (!xyz || !face_vtx || nv == 0 || nf == 0) MCB_FAIL(ctx, MCB200_ERR_INVALID, "mesh_create: empty mesh or NULL array");
+    MCB_CUDA(ctx, cudaSetDevice(ctx->device));
+    mcb200_mesh* m = new mcb200_mesh();
+    m->nv = nv;
+    m->nf = nf;
+    m->is_float = is_float ? 1 : 0;
+    m->is_tri = 1;
+    m->h_face_off.resize((size_t)nf + 1);
+    if (face_sizes) {
+        uint32_t acc = 0;
+        for (uint32_t f = 0; f < nf; ++f) {
+            if (face_sizes[f] < 3) {
+                delete m;
+                MCB_FAIL(ctx, MCB200_ERR_INVALID, "mesh_create: a face has fewer than 3 vertices");
+            }
+            if (face_sizes[f] != 3) m->is_tri = 0;
+            m->h_face_off[f] = acc;
+            acc += face_sizes[f];
+        }
+        m->h_face_off[nf] = acc;
+    } else {
+        for (uint32_t f = 0; f <= nf; ++f) m->h_face_off[f] = 3u * f;
+    }
+    m->nh = m->h_face_off[nf];
+    m->h_face_vtx.assign(face_vtx, face_vtx + m->nh);
+    for (uint32_t h = 0; h < m->nh; ++h)
+        if (face_vtx[h] >= nv) {
+            delete m;
+            MCB_FAIL(ctx, MCB200_ERR_INVALID, "mesh_create: face index out of range");
+        }
+    identity_frame(m->frame, m->is_float);
+    const size_t vbytes = (size_t)nv * 3 * (is_float ? sizeof(float) : sizeof(double));
+    void* d_xyz = nullptr;
+    uint32_t* d_fv = nullptr;
+    uint32_t* d_fo = nullptr;
+    cudaError_t e = cudaMallocAsync(&d_xyz, vbytes, ctx->stream);
+    if (e == cudaSuccess) e = cudaMallocAsync((void**)&d_fv, sizeof(uint32_t) * (size_t)m->nh, ctx->stream);
+    if (e == cudaSuccess && !m->is_tri) e = cudaMallocAsync((void**)&d_fo, sizeof(uint32_t) * ((size_t)nf + 1), ctx->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_xyz, xyz, vbytes, cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_fv, face_vtx, sizeof(uint32_t) * (size_t)m->nh, cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess && d_fo)
+        e = cudaMemcpyAsync(d_fo, m->h_face_off.data(), sizeof(uint32_t) * ((size_t)nf + 1), cudaMemcpyHostToDevice, ctx->stream);
+    if (e != cudaSuccess) {
+        if (d_xyz) cudaFreeAsync(d_xyz, ctx->stream);
+        if (d_fv) cudaFreeAsync(d_fv, ctx->stream);
+        if (d_fo) cudaFreeAsync(d_fo, ctx->stream);
+        delete m;
+        ctx->set_error(std::string("mesh_create: ") + cudaGetErrorString(e), __FILE__, __LINE__);
+        return (int)e;
+    }
+    // the caller's arrays are only borrowed for the call
+    MCB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    m->d_xyz = d_xyz;
+    m->d_face_vtx = d_fv;
+    m->d_face_off = d_fo;
+    m->owns_arrays = true;
+    *out = m;
+    return 0;
+}
+
+int mcb200_mesh_adopt_device(mcb200_ctx* ctx, int is_float, const void* d_xyz, uint32_t nv, const uint32_t* d_face_vtx,
+    const uint32_t* d_face_off, uint32_t nf, uint32_t nh, mcb200_mesh** out)
+{
+    if (!ctx || !out) return MCB200_ERR_INVALID;
+    *out = nullptr;
+    if (!d_xyz || !d_face_vtx || nv == 0 || nf == 0) MCB_FAIL(ctx, MCB200_ERR_INVALID, "mesh_adopt_device: empty mesh or NULL array");
+    if (!d_face_off && nh != 3u * nf) MCB_FAIL(ctx, MCB200_ERR_INVALID, "mesh_adopt_device: triangle mesh needs nh == 3 nf");
+    mcb200_mesh* m = new mcb200_mesh();
+    m->nv = nv;
+    m->nf = nf;
+    m->nh = nh;
+    m->is_float = is_float ? 1 : 0;
+    m->is_tri = d_face_off ? 0 : 1;
+    m->d_xyz = d_xyz;
+    m->d_face_vtx = d_face_vtx;
+    m->d_face_off = d_face_off;
+    m->owns_arrays = false;
+    identity_frame(m->frame, m->is_float);
+    *out = m;
+    return 0;
+}
+
+int mcb200_mesh_set_frame(mcb200_ctx* ctx, mcb200_mesh* m, const double com[3], const double shift[3], const double pert[3])
+{
+    if (!ctx || !m) return MCB200_ERR_INVALID;
+    identity_frame(m->frame, m->is_float);
+    if (!com) {
+        if (m->is_float) MCB_FAIL(ctx, MCB200_ERR_INVALID, "set_frame: internal-coordinate meshes must be double");
+        if (pert) MCB_FAIL(ctx, MCB200_ERR_INVALID, "set_frame: a perturbation needs a frame");
+        return 0;
+    }
+    if (!shift) MCB_FAIL(ctx, MCB200_ERR_INVALID, "set_frame: shift is NULL");
+    m->frame.has_frame = 1;
+    for (int j = 0; j < 3; ++j) {
+        m->frame.com[j] = com[j];
+        m->frame.shift[j] = shift[j];
+        m->frame.fcom[j] = (float)com[j]; // preproc.cpp:124-129
+        m->frame.fshift[j] = (float)shift[j];
+        m->frame.pert[j] = pert ? pert[j] : 0.0;
+    }
+    m->frame.has_pert = pert ? 1 : 0;
+    return 0;
+}
+
+void mcb200_mesh_free(mcb200_ctx* ctx, mcb200_mesh* m)
+{
+    if (!ctx || !m) return;
+    cudaSetDevice(ctx->device);
+    if (m->owns_arrays) {
+        if (m->d_xyz) cudaFreeAsync(const_cast<void*>(m->d_xyz), ctx->stream);
+        if (m->d_face_vtx) cudaFreeAsync(const_cast<uint32_t*>(m->d_face_vtx), ctx->stream);
+        if (m->d_face_off) cudaFreeAsync(const_cast<uint32_t*>(m->d_face_off), ctx->stream);
+    }
+    ctx->release(m->face_bbox);
+    ctx->release(m->root);
+    ctx->release(m->codes);
+    ctx->release(m->sorted_codes);
+    ctx->release(m->sorted_faces);
+    ctx->release(m->nodes);
+    ctx->release(m->parent);
+    ctx->release(m->flags);
+    delete m;
+}
+
+// ---------------------------------------------------------------------------------------------------------- (1) build
+
+int mcb200_bvh_build(mcb200_ctx* ctx, mcb200_mesh* m, double eps)
+{
+    if (!ctx || !m) return MCB200_ERR_INVALID;
+    MCB_CUDA(ctx, cudaSetDevice(ctx->device));
+    return lbvh_build(ctx, m, eps);
+}
+
+int mcb200_bvh_read(mcb200_ctx* ctx, const mcb200_mesh* m, double* face_bboxes, double root_bbox[6])
+{
+    if (!ctx || !m) return MCB200_ERR_INVALID;
+    if (!m->built) MCB_FAIL(ctx, MCB200_ERR_INVALID, "bvh_read: mesh has not been built");
+    if (face_bboxes)
+        MCB_CUDA(ctx, cudaMemcpyAsync(face_bboxes, m->face_bbox.p, sizeof(double) * 6 * (size_t)m->nf, cudaMemcpyDeviceToHost, ctx->stream));
+    if (root_bbox) {
+        const double* dec = reinterpret_cast<const double*>(m->root.as<unsigned long long>() + 6);
+        MCB_CUDA(ctx, cudaMemcpyAsync(root_bbox, dec, sizeof(double) * 6, cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    MCB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+int mcb200_bvh_read_morton(mcb200_ctx* ctx, const mcb200_mesh* m, uint32_t* codes_by_face, uint32_t* sorted_faces)
+{
+    if (!ctx || !m) return MCB200_ERR_INVALID;
+    if (!m->built) MCB_FAIL(ctx, MCB200_ERR_INVALID, "bvh_read_morton: mesh has not been built");
+    if (codes_by_face)
+        MCB_CUDA(ctx, cudaMemcpyAsync(codes_by_face, m->codes.p, sizeof(uint32_t) * (size_t)m->nf, cudaMemcpyDeviceToHost, ctx->stream));
+    if (sorted_faces)
+        MCB_CUDA(ctx, cudaMemcpyAsync(sorted_faces, m->sorted_faces.p, sizeof(uint32_t) * (size_t)m->nf, cudaMemcpyDeviceToHost, ctx->stream));
+    MCB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------- results
+
+int mcb200_result_create(mcb200_ctx* ctx, mcb200_result** out)
+{
+    if (!ctx || !out) return MCB200_ERR_INVALID;
+    *out = new mcb200_result();
+    return 0;
+}
+
+void mcb200_result_free(mcb200_ctx* ctx, mcb200_result* r)
+{
+    if (!ctx || !r) return;
+    cudaSetDevice(ctx->device);
+    dbuf* all[] = { &r->counters, &r->pairs, &r->cand_flag, &r->plane, &r->plane_mc, &r->exact_queue, &r->records, &r->rec_keys,
+        &r->rec_idx, &r->records_sorted, &r->tests, &r->tests_sorted, &r->test_keys, &r->test_idx };
+    for (dbuf* b : all) ctx->release(*b);
+    delete r;
+}
+
+int mcb200_result_set_shard(mcb200_ctx* ctx, mcb200_result* res, uint32_t part, uint32_t nparts, uint32_t chunk)
+{
+    if (!ctx || !res) return MCB200_ERR_INVALID;
+    if (nparts == 0 || part >= nparts || chunk == 0 || (chunk % 32u) != 0u)
+        MCB_FAIL(ctx, MCB200_ERR_INVALID, "set_shard: need part < nparts and a chunk that is a positive multiple of 32");
+    res->shard_part = part;
+    res->shard_nparts = nparts;
+    res->shard_chunk = chunk;
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------- (2) traversal
+
+int mcb200_bvh_intersect(mcb200_ctx* ctx, const mcb200_mesh* src, const mcb200_mesh* cut, mcb200_result* res)
+{
+    if (!ctx || !src || !cut || !res) return MCB200_ERR_INVALID;
+    MCB_CUDA(ctx, cudaSetDevice(ctx->device));
+    for (int attempt = 0; attempt < 2; ++attempt) {
+        MCB_TRY(traverse_pairs(ctx, src, cut, res));
+        if (attempt == 1) break;
+        // The only host round trip of the stage: did the pair buffer hold everything?  (One 128-byte read; skipped by
+        // mcb200_intersect_stage, which checks after the fact.)
+        MCB_TRY(fetch_counters(ctx, res));
+        if (!res->h.pair_overflow) break;
+        const size_t want = (size_t)res->h.n_pairs + (size_t)res->h.n_pairs / 8 + 1024;
+        MCB_TRY(ctx->reserve(res->pairs, sizeof(unsigned long long) * want));
+        res->cap_pairs = want;
+    }
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------- (3) narrowphase
+
+int mcb200_soup_create(mcb200_ctx* ctx, uint32_t nsf, uint32_t ncf, uint32_t nh, uint32_t ne, const uint32_t* face_vtx,
+    const uint32_t* face_edge, const uint32_t* edge_f, mcb200_soup** out)
+{
+    if (!ctx || !out) return MCB200_ERR_INVALID;
+    *out = nullptr;
+    if (!face_vtx || !face_edge || !edge_f || nsf == 0 || ncf == 0) MCB_FAIL(ctx, MCB200_ERR_INVALID, "soup_create: NULL array or empty mesh");
+    MCB_CUDA(ctx, cudaSetDevice(ctx->device));
+    mcb200_soup* s = new mcb200_soup();
+    s->nsf = nsf;
+    s->ncf = ncf;
+    s->nh = nh;
+    s->ne = ne;
+    s->all_tri = (nh == 3u * (nsf + ncf)) ? 1 : 0; // callers with polygons go through mcb200_soup_from_meshes
+    int rc = upload(ctx, s->face_vtx, face_vtx, sizeof(uint32_t) * (size_t)nh);
+    if (!rc) rc = upload(ctx, s->face_edge, face_edge, sizeof(uint32_t) * (size_t)nh);
+    if (!rc) rc = upload(ctx, s->edge_f, edge_f, sizeof(uint32_t) * 2 * (size_t)ne);
+    if (!rc) {
+        cudaError_t e = cudaStreamSynchronize(ctx->stream);
+        if (e != cudaSuccess) rc = (int)e;
+    }
+    if (rc) {
+        mcb200_soup_free(ctx, s);
+        return rc;
+    }
+    *out = s;
+    return 0;
+}
+
+void mcb200_soup_free(mcb200_ctx* ctx, mcb200_soup* s)
+{
+    if (!ctx || !s) return;
+    cudaSetDevice(ctx->device);
+    ctx->release(s->face_vtx);
+    ctx->release(s->face_edge);
+    ctx->release(s->face_off);
+    ctx->release(s->edge_f);
+    delete s;
+}
+
+int mcb200_soup_from_meshes(mcb200_ctx* ctx, const mcb200_mesh* src, const mcb200_mesh* cut, mcb200_soup** out)
+{
+    if (!ctx || !src || !cut || !out) return MCB200_ERR_INVALID;
+    *out = nullptr;
+    if (src->h_face_vtx.empty() || cut->h_face_vtx.empty())
+        MCB_FAIL(ctx, MCB200_ERR_INVALID, "soup_from_meshes: meshes adopted from device memory carry no host face arrays");
+    const uint32_t nh = src->nh + cut->nh;
+    std::vector<uint32_t> fv(nh), fe(nh), ev(2 * (size_t)nh), ef(2 * (size_t)nh);
+    uint32_t ne = 0;
+    const int rc = host_soup_ids(src->nv, src->h_face_off.data(), src->h_face_vtx.data(), src->nf, cut->h_face_off.data(),
+        cut->h_face_vtx.data(), cut->nf, fv.data(), fe.data(), ev.data(), ef.data(), &ne);
+    if (rc == MCB200_ERR_NON_MANIFOLD) MCB_FAIL(ctx, rc, "soup_from_meshes: non-manifold edge or inconsistent winding");
+    if (rc) MCB_FAIL(ctx, rc, "soup_from_meshes: invalid face");
+    MCB_TRY(mcb200_soup_create(ctx, src->nf, cut->nf, nh, ne, fv.data(), fe.data(), ef.data(), out));
+    mcb200_soup* s = *out;
+    s->all_tri = (src->is_tri && cut->is_tri) ? 1 : 0;
+    if (!s->all_tri) {
+        std::vector<uint32_t> off((size_t)src->nf + cut->nf + 1);
+        for (uint32_t f = 0; f <= src->nf; ++f) off[f] = src->h_face_off[f];
+        for (uint32_t f = 0; f <= cut->nf; ++f) off[src->nf + f] = src->nh + cut->h_face_off[f];
+        MCB_TRY(upload(ctx, s->face_off, off.data(), sizeof(uint32_t) * off.size()));
+        MCB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    }
+    return 0;
+}
+
+int mcb200_narrowphase(mcb200_ctx* ctx, const mcb200_soup* soup, const mcb200_mesh* src, const mcb200_mesh* cut,
+    mcb200_result* res, uint32_t flags)
+{
+    if (!ctx || !soup || !src || !cut || !res) return MCB200_ERR_INVALID;
+    MCB_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (!soup->all_tri && !soup->face_off.p) MCB_FAIL(ctx, MCB200_ERR_INVALID, "narrowphase: polygon soup without face offsets");
+    return narrowphase_run(ctx, soup, src, cut, res, flags);
+}
+
+int mcb200_intersect_stage(mcb200_ctx* ctx, mcb200_mesh* src, mcb200_mesh* cut, double cut_eps, const mcb200_soup* soup,
+    mcb200_result* res, uint32_t flags)
+{
+    if (!ctx || !src || !cut || !soup || !res) return MCB200_ERR_INVALID;
+    MCB_CUDA(ctx, cudaSetDevice(ctx->device));
+    // The cut boxes always come from the UNPERTURBED cut frame (the reference builds the cut BVH on the first pass only,
+    // preproc.cpp:2676-2698); a perturbation only affects the narrowphase coordinates.
+    frame_t cut_frame = cut->frame;
+    if (cut_frame.has_pert) {
+        cut->frame.has_pert = 0;
+        for (int j = 0; j < 3; ++j) cut->frame.pert[j] = 0.0;
+    }
+    int rc = lbvh_build(ctx, src, 0.0);
+    if (!rc) rc = lbvh_build(ctx, cut, cut_eps);
+    cut->frame = cut_frame;
+    if (rc) return rc;
+    MCB_TRY(traverse_pairs(ctx, src, cut, res));
+    MCB_TRY(narrowphase_run(ctx, soup, src, cut, res, flags));
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------- reads
+
+int mcb200_result_counts(mcb200_ctx* ctx, mcb200_result* res, mcb200_counts* out)
+{
+    if (!ctx || !res || !out) return MCB200_ERR_INVALID;
+    MCB_TRY(fetch_counters(ctx, res));
+    const result_counters_t& h = res->h;
+    out->n_pairs = h.n_pairs;
+    out->n_node_tests = h.n_node_tests;
+    out->n_tests = h.n_tests;
+    out->n_exact = h.n_exact;
+    out->n_records = h.n_records;
+    out->n_cand_faces = h.n_cand_faces;
+    out->bad_face = h.bad_face;
+    // status precedence follows dispatch(): the degenerate-face check returns before any edge/face test runs
+    // (kernel.cpp:2301-2312); note the reference's `>` when naming the mesh (kernel.cpp:2304)
+    if (res->have_narrow && h.bad_face != MCB200_NULL)
+        out->status = (h.bad_face > res->nsf) ? MCB200_STATUS_INVALID_CUT_MESH : MCB200_STATUS_INVALID_SRC_MESH;
+    else if (res->have_narrow && h.gp_violation)
+        out->status = MCB200_STATUS_GENERAL_POSITION_VIOLATION;
+    else
+        out->status = MCB200_STATUS_SUCCESS;
+    if (h.pair_overflow) MCB_FAIL(ctx, MCB200_ERR_CAPACITY, "pair buffer overflow: call mcb200_bvh_intersect (it regrows and retries)");
+    return 0;
+}
+
+int mcb200_result_read_pairs(mcb200_ctx* ctx, mcb200_result* res, uint64_t* pairs, size_t capacity)
+{
+    if (!ctx || !res) return MCB200_ERR_INVALID;
+    MCB_TRY(fetch_counters(ctx, res));
+    const size_t n = (size_t)res->h.n_pairs;
+    if (n > res->cap_pairs) MCB_FAIL(ctx, MCB200_ERR_CAPACITY, "pair buffer overflowed on the device");
+    if (n > capacity || (n && !pairs)) MCB_FAIL(ctx, MCB200_ERR_CAPACITY, "read_pairs: output array too small");
+    if (n) MCB_CUDA(ctx, cudaMemcpyAsync(pairs, res->pairs.p, sizeof(uint64_t) * n, cudaMemcpyDeviceToHost, ctx->stream));
+    MCB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+int mcb200_result_read_records(mcb200_ctx* ctx, mcb200_result* res, mcb200_record* records, size_t capacity)
+{
+    if (!ctx || !res) return MCB200_ERR_INVALID;
+    if (!res->have_narrow) MCB_FAIL(ctx, MCB200_ERR_INVALID, "read_records: narrowphase has not run");
+    MCB_TRY(fetch_counters(ctx, res));
+    const size_t n = (size_t)res->h.n_records;
+    if (n > res->cap_records) MCB_FAIL(ctx, MCB200_ERR_CAPACITY, "record buffer overflowed on the device");
+    if (n > capacity || (n && !records)) MCB_FAIL(ctx, MCB200_ERR_CAPACITY, "read_records: output array too small");
+    if (n) MCB_CUDA(ctx, cudaMemcpyAsync(records, res->records_sorted.p, sizeof(mcb200_record) * n, cudaMemcpyDeviceToHost, ctx->stream));
+    MCB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+int mcb200_result_read_tests(mcb200_ctx* ctx, mcb200_result* res, mcb200_test* tests, size_t capacity)
+{
+    if (!ctx || !res) return MCB200_ERR_INVALID;
+    if (!res->have_narrow || !res->logged_tests) MCB_FAIL(ctx, MCB200_ERR_INVALID, "read_tests: run the narrowphase with MCB200_NARROW_LOG_TESTS");
+    MCB_TRY(fetch_counters(ctx, res));
+    const size_t n = (size_t)res->h.n_log;
+    if (n > res->cap_tests) MCB_FAIL(ctx, MCB200_ERR_CAPACITY, "test log overflowed on the device");
+    if (n > capacity || (n && !tests)) MCB_FAIL(ctx, MCB200_ERR_CAPACITY, "read_tests: output array too small");
+    if (n) MCB_CUDA(ctx, cudaMemcpyAsync(tests, res->tests_sorted.p, sizeof(mcb200_test) * n, cudaMemcpyDeviceToHost, ctx->stream));
+    MCB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+int mcb200_result_read_planes(mcb200_ctx* ctx, mcb200_result* res, uint32_t* faces, double* normal, double* d, int32_t* max_comp,
+    size_t capacity)
+{
+    if (!ctx || !res) return MCB200_ERR_INVALID;
+    if (!res->have_narrow) MCB_FAIL(ctx, MCB200_ERR_INVALID, "read_planes: narrowphase has not run");
+    MCB_TRY(fetch_counters(ctx, res));
+    const size_t n = (size_t)res->h.n_cand_faces;
+    if (n > capacity) MCB_FAIL(ctx, MCB200_ERR_CAPACITY, "read_planes: output arrays too small");
+    if (n == 0) return 0;
+    std::vector<double> pl(4 * n);
+    std::vector<int32_t> mc(n);
+    std::vector<uint32_t> fc(n);
+    MCB_CUDA(ctx, cudaMemcpyAsync(pl.data(), res->plane.p, sizeof(double) * 4 * n, cudaMemcpyDeviceToHost, ctx->stream));
+    MCB_CUDA(ctx, cudaMemcpyAsync(mc.data(), res->plane_mc.p, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, ctx->stream));
+    MCB_CUDA(ctx, cudaMemcpyAsync(fc.data(), res->plane_mc.as<int32_t>() + res->nf_ps, sizeof(uint32_t) * n, cudaMemcpyDeviceToHost,
+        ctx->stream));
+    MCB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    // rows were appended in scheduling order; hand them back by ascending face id
+    std::vector<uint32_t> order(n);
+    std::iota(order.begin(), order.end(), 0u);
+    std::sort(order.begin(), order.end(), [&](uint32_t x, uint32_t y) { return fc[x] < fc[y]; });
+    for (size_t i = 0; i < n; ++i) {
+        const uint32_t k = order[i];
+        if (faces) faces[i] = fc[k];
+        if (normal) {
+            normal[3 * i] = pl[4 * (size_t)k];
+            normal[3 * i + 1] = pl[4 * (size_t)k + 1];
+            normal[3 * i + 2] = pl[4 * (size_t)k + 2];
+        }
+        if (d) d[i] = pl[4 * (size_t)k + 3];
+        if (max_comp) max_comp[i] = mc[k];
+    }
+    return 0;
+}
+
+int mcb200_result_device_ptr(mcb200_ctx* ctx, mcb200_result* res, int which, void** dptr, uint64_t* count)
+{
+    if (!ctx || !res || !dptr || !count) return MCB200_ERR_INVALID;
+    MCB_TRY(fetch_counters(ctx, res));
+    if (which == 0) {
+        *dptr = res->pairs.p;
+        *count = res->h.n_pairs;
+    } else if (which == 1) {
+        if (!res->have_narrow) MCB_FAIL(ctx, MCB200_ERR_INVALID, "device_ptr: narrowphase has not run");
+        *dptr = res->records_sorted.p;
+        *count = res->h.n_records;
+    } else {
+        MCB_FAIL(ctx, MCB200_ERR_INVALID, "device_ptr: unknown buffer");
+    }
+    return 0;
+}
+
+} // extern "C"

@@ -1,0 +1,282 @@
+// mcut_b200/csrc/common.cuh — context, device buffers and small device helpers shared by every kernel file.
+// sm_100a only; compiled with -fmad=false so no a*b+c is ever contracted (the reference build has no FMA,
+// SURVEY §8-c) — the only fused operations in the product are the explicit ones in predicates.cuh.
+#pragma once
+
+#include <cuda_runtime.h>
+
+#include <cfloat>
+#include <cmath>
+
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/mcut_b200.h"
+
+#define MCB_NUM_SMS_DEFAULT 148
+
+#define MCB_CUDA(ctx, expr)                                                                              \
+    do {                                                                                                 \
+        cudaError_t err__ = (expr);                                                                      \
+        if (err__ != cudaSuccess) {                                                                      \
+            (ctx)->set_error(std::string(#expr) + ": " + cudaGetErrorString(err__), __FILE__, __LINE__); \
+            return (int)err__;                                                                           \
+        }                                                                                                \
+    } while (0)
+
+#define MCB_TRY(expr)            \
+    do {                         \
+        int rc__ = (expr);       \
+        if (rc__ != 0) return rc__; \
+    } while (0)
+
+// A grow-only device allocation.
+struct dbuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    template <typename T> T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+struct mcb200_ctx {
+    int device = 0;
+    int num_sms = MCB_NUM_SMS_DEFAULT;
+    cudaStream_t stream = nullptr;
+    bool owns_stream = false;
+    std::string error;
+    uint64_t launches = 0;
+    // pinned staging for small D2H reads (counters)
+    void* h_pinned = nullptr;
+    size_t h_pinned_cap = 0;
+    // scratch shared by all stages of this context (sort double-buffers, histograms, tile status)
+    dbuf sort_keys_alt, sort_vals_alt, sort_hist, sort_status, sort_tilectr;
+
+    void set_error(const std::string& msg, const char* file, int line)
+    {
+        error = msg + " (" + file + ":" + std::to_string(line) + ")";
+    }
+    int reserve(dbuf& b, size_t bytes)
+    {
+        if (bytes <= b.cap) return 0;
+        // grow geometrically so repeated dispatches of growing size do not reallocate every time
+        size_t want = bytes + bytes / 4 + 256;
+        if (b.p) {
+            cudaError_t e = cudaFreeAsync(b.p, stream);
+            if (e != cudaSuccess) {
+                set_error(std::string("cudaFreeAsync: ") + cudaGetErrorString(e), __FILE__, __LINE__);
+                return (int)e;
+            }
+            b.p = nullptr;
+            b.cap = 0;
+        }
+        cudaError_t e = cudaMallocAsync(&b.p, want, stream);
+        if (e != cudaSuccess) {
+            set_error(std::string("cudaMallocAsync(") + std::to_string(want) + "): " + cudaGetErrorString(e), __FILE__, __LINE__);
+            return (int)e;
+        }
+        b.cap = want;
+        return 0;
+    }
+    void release(dbuf& b)
+    {
+        if (b.p) cudaFreeAsync(b.p, stream);
+        b.p = nullptr;
+        b.cap = 0;
+    }
+    int pinned(size_t bytes)
+    {
+        if (bytes <= h_pinned_cap) return 0;
+        if (h_pinned) cudaFreeHost(h_pinned);
+        h_pinned = nullptr;
+        h_pinned_cap = 0;
+        cudaError_t e = cudaMallocHost(&h_pinned, bytes);
+        if (e != cudaSuccess) {
+            set_error(std::string("cudaMallocHost: ") + cudaGetErrorString(e), __FILE__, __LINE__);
+            return (int)e;
+        }
+        h_pinned_cap = bytes;
+        return 0;
+    }
+};
+
+// The frame of the internal coordinates (preproc.cpp:91-185), applied on the fly.
+struct frame_t {
+    double com[3];
+    double shift[3];
+    double pert[3];
+    float fcom[3];
+    float fshift[3];
+    int has_frame; // 0: vertices already are internal coordinates
+    int has_pert;
+    int is_float;
+};
+
+struct mcb200_mesh {
+    uint32_t nv = 0, nf = 0, nh = 0;
+    int is_float = 0;
+    int is_tri = 1;
+    bool owns_arrays = true;
+    const void* d_xyz = nullptr; // user-frame vertices, float3 or double3
+    const uint32_t* d_face_vtx = nullptr; // [nh]
+    const uint32_t* d_face_off = nullptr; // [nf+1] or nullptr for triangles
+    frame_t frame;
+    // host copies of the face arrays (needed by mcb200_soup_from_meshes)
+    std::vector<uint32_t> h_face_vtx, h_face_off;
+    // build products
+    bool built = false;
+    double eps = 0.0;
+    dbuf face_bbox; // [nf][6] double
+    dbuf root; // 6 x u64 (order-preserving encoding) + 6 double (decoded)
+    dbuf codes; // [nf] u32 Morton code by face (kept for parity reads)
+    dbuf sorted_codes; // [nf] u32
+    dbuf sorted_faces; // [nf] u32 (leaf -> face)
+    dbuf nodes; // [max(nf-1,1)] bvh_node_t (128 B)
+    dbuf parent; // [2nf-1] u32 parent of internal node i / leaf (nf-1+j)
+    dbuf flags; // [nf-1] u32 refit arrival counters
+};
+
+// One LBVH node: both children's boxes live in the parent so one 128-byte line feeds a traversal step.
+struct __align__(128) bvh_node_t {
+    double lbox[6]; // min xyz, max xyz of the left child
+    double rbox[6];
+    uint32_t left, right; // child ids; bit31 set => leaf, low bits = sorted leaf index
+    uint32_t first, last; // leaf range covered (Karras)
+    uint32_t pad[4];
+};
+static_assert(sizeof(bvh_node_t) == 128, "bvh_node_t must be one 128-byte line");
+
+#define MCB_LEAF_BIT 0x80000000u
+
+struct mcb200_soup {
+    uint32_t nsf = 0, ncf = 0, nh = 0, ne = 0;
+    dbuf face_vtx; // [nh] ps vertex ids in ps.get_vertices_around_face order
+    dbuf face_edge; // [nh]
+    dbuf face_off; // [nf+1] (always materialised for the soup)
+    dbuf edge_f; // [ne][2]
+    int all_tri = 1;
+};
+
+// device-side counters of one result (one 128-byte block, zeroed per run)
+struct result_counters_t {
+    unsigned long long n_pairs;
+    unsigned long long n_node_tests;
+    unsigned long long n_tests;
+    unsigned long long n_exact;
+    unsigned long long n_records;
+    unsigned long long n_cand_faces;
+    unsigned long long n_log;
+    unsigned int gp_violation;
+    unsigned int bad_face; // min polygon-soup id of a degenerate candidate face, 0xFFFFFFFF if none
+    unsigned int pair_overflow;
+    unsigned int work_counter; // dynamic work distribution (traversal groups)
+    unsigned int work_counter2;
+    unsigned int pad[7];
+};
+
+struct mcb200_result {
+    dbuf counters; // result_counters_t
+    dbuf pairs; // u64 [cap_pairs]
+    size_t cap_pairs = 0;
+    dbuf cand_flag; // u8 [nf_ps]
+    dbuf plane; // per ps face: normal[3], d  (4 doubles) ; maxcomp in separate int array
+    dbuf plane_mc; // i32 per ps face
+    dbuf exact_queue; // u64 test keys needing the exact stage
+    size_t cap_exact = 0;
+    dbuf records; // mcb200_record [cap_records]
+    dbuf rec_keys; // u64
+    dbuf rec_idx; // u32
+    dbuf records_sorted;
+    size_t cap_records = 0;
+    dbuf tests; // mcb200_test log
+    dbuf tests_sorted;
+    dbuf test_keys;
+    dbuf test_idx;
+    size_t cap_tests = 0;
+    uint32_t shard_part = 0, shard_nparts = 1, shard_chunk = 4096;
+    uint32_t nf_ps = 0, nsf = 0, ne_ps = 0;
+    bool have_pairs = false, have_narrow = false, logged_tests = false;
+    bool records_sorted_valid = false, tests_sorted_valid = false;
+    result_counters_t h; // last host copy
+    bool h_valid = false;
+};
+
+// ------------------------------------------------------------------------------------------------------------
+// device helpers
+// ------------------------------------------------------------------------------------------------------------
+
+__device__ __forceinline__ unsigned lane_id() { return threadIdx.x & 31u; }
+__device__ __forceinline__ unsigned lanemask_lt()
+{
+    unsigned m;
+    asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m));
+    return m;
+}
+
+// order-preserving map double <-> u64 so mesh-AABB min/max can use integer atomics
+__device__ __forceinline__ unsigned long long dbl_to_ordered(double d)
+{
+    unsigned long long u = (unsigned long long)__double_as_longlong(d);
+    return (u & 0x8000000000000000ull) ? ~u : (u | 0x8000000000000000ull);
+}
+__device__ __forceinline__ double ordered_to_dbl(unsigned long long u)
+{
+    u = (u & 0x8000000000000000ull) ? (u & 0x7FFFFFFFFFFFFFFFull) : ~u;
+    return __longlong_as_double((long long)u);
+}
+
+// the reference's min/max (math.h:590-600): min(a,b) = (b < a) ? b : a ; max(a,b) = (a < b) ? b : a
+__device__ __forceinline__ double ref_min(double a, double b) { return (b < a) ? b : a; }
+__device__ __forceinline__ double ref_max(double a, double b) { return (a < b) ? b : a; }
+
+// closed-interval AABB overlap (math.h:931-941); boxes as min xyz, max xyz
+__device__ __forceinline__ bool overlap6(const double* a, const double* b)
+{
+    return (a[0] <= b[3] && a[3] >= b[0]) && (a[1] <= b[4] && a[4] >= b[1]) && (a[2] <= b[5] && a[5] >= b[2]);
+}
+
+// internal coordinate of vertex v: x' = (x - com) + shift (+ perturbation); float input does the first two
+// operations in float with (float)com, (float)shift and widens afterwards (preproc.cpp:124-134, :166-176)
+__device__ __forceinline__ void load_vertex(const void* __restrict__ xyz, const frame_t& fr, uint32_t v, double out[3])
+{
+    if (fr.is_float) {
+        const float* p = reinterpret_cast<const float*>(xyz) + 3 * (size_t)v;
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+            float x = __ldg(p + j);
+            if (fr.has_frame) {
+                x = __fsub_rn(x, fr.fcom[j]);
+                x = __fadd_rn(x, fr.fshift[j]);
+            }
+            double d = (double)x;
+            if (fr.has_frame) d = __dadd_rn(d, fr.has_pert ? fr.pert[j] : 0.0);
+            out[j] = d;
+        }
+    } else {
+        const double* p = reinterpret_cast<const double*>(xyz) + 3 * (size_t)v;
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+            double x = __ldg(p + j);
+            if (fr.has_frame) {
+                x = __dadd_rn(__dsub_rn(x, fr.com[j]), fr.shift[j]);
+                x = __dadd_rn(x, fr.has_pert ? fr.pert[j] : 0.0);
+            }
+            out[j] = x;
+        }
+    }
+}
+
+static inline unsigned div_up(size_t a, size_t b) { return (unsigned)((a + b - 1) / b); }
+
+// launch accounting: every kernel launch of the product goes through this macro
+#define MCB_LAUNCH(ctx, kernel, grid, block, smem, ...)                          \
+    do {                                                                         \
+        kernel<<<(grid), (block), (smem), (ctx)->stream>>>(__VA_ARGS__);         \
+        (ctx)->launches++;                                                       \
+        cudaError_t le__ = cudaPeekAtLastError();                                \
+        if (le__ != cudaSuccess) {                                               \
+            (ctx)->set_error(std::string(#kernel) + " launch: " + cudaGetErrorString(le__), __FILE__, __LINE__); \
+            return (int)le__;                                                    \
+        }                                                                        \
+    } while (0)

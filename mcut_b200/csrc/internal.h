@@ -1,0 +1,18 @@
+// mcut_b200/csrc/internal.h — launchers shared between the kernel files and the C-ABI (api.cu).
+#pragma once
+
+#include "common.cuh"
+
+// lbvh.cu
+int lbvh_build(mcb200_ctx* ctx, mcb200_mesh* mesh, double eps);
+// traverse.cu
+int traverse_pairs(mcb200_ctx* ctx, const mcb200_mesh* src, const mcb200_mesh* cut, mcb200_result* res);
+// narrowphase.cu
+int narrowphase_run(mcb200_ctx* ctx, const mcb200_soup* soup, const mcb200_mesh* src, const mcb200_mesh* cut,
+    mcb200_result* res, uint32_t flags);
+int narrowphase_sort_records(mcb200_ctx* ctx, mcb200_result* res);
+int narrowphase_sort_tests(mcb200_ctx* ctx, mcb200_result* res);
+// host_logic.cpp
+int host_soup_ids(uint32_t nsv, const uint32_t* src_off, const uint32_t* src_vtx, uint32_t nsf, const uint32_t* cut_off,
+    const uint32_t* cut_vtx, uint32_t ncf, uint32_t* face_vtx, uint32_t* face_edge, uint32_t* edge_v, uint32_t* edge_f,
+    uint32_t* ne);

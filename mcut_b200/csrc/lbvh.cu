@@ -1,0 +1,314 @@
+// mcut_b200/csrc/lbvh.cu — (1) LBVH construction on the device.
+//
+// Replaces build_oibvh() (include/mcut/internal/bvh.h:117-125, source/bvh.cpp:219-636):
+//   K_aabb    face AABBs (+eps enlargement) and the mesh AABB            bvh.cpp:242-368, math.h:866-928
+//   K_morton  30-bit Morton codes, the reference's float formula          bvh.cpp:196-217, :373-433
+//   sort      one-sweep radix sort of (code, face)                        bvh.cpp:437-442 (std::sort there)
+//   K_karras  radix tree over the sorted codes (Karras 2012)              replaces the implicit OIBVH layout :444-493
+//   K_refit   atomic bottom-up AABB refit                                 bvh.cpp:498-635 (one parallel_for per level there)
+// Only face AABBs, the mesh AABB and the leaf-pair SET escape this stage, and every internal box is the exact
+// min/max union of its leaves, so the tree shape is free: an LBVH yields the same pairs.
+#include "internal.h"
+#include "radix_sort.cuh"
+
+namespace {
+
+constexpr int BLOCK = 256;
+
+__device__ __forceinline__ unsigned spread10(unsigned v)
+{
+    v = (v * 0x00010001u) & 0xFF0000FFu;
+    v = (v * 0x00000101u) & 0x0F00F00Fu;
+    v = (v * 0x00000011u) & 0xC30C30C3u;
+    v = (v * 0x00000005u) & 0x49249249u;
+    return v;
+}
+
+__device__ __forceinline__ unsigned morton3D(float x, float y, float z)
+{
+    // bvh.cpp:206-217; fminf/fmaxf have std::fmin/std::fmax semantics (NaN -> the other operand)
+    x = fminf(fmaxf(__fmul_rn(x, 1024.0f), 0.0f), 1023.0f);
+    y = fminf(fmaxf(__fmul_rn(y, 1024.0f), 0.0f), 1023.0f);
+    z = fminf(fmaxf(__fmul_rn(z, 1024.0f), 0.0f), 1023.0f);
+    return spread10((unsigned)x) * 4u + spread10((unsigned)y) * 2u + spread10((unsigned)z);
+}
+
+// ---- K_aabb -----------------------------------------------------------------------------------------------------
+// One thread per face, grid-stride; the block's union goes to the mesh AABB through 6 ordered-integer atomics.
+template <bool TRI>
+__global__ void __launch_bounds__(BLOCK) k_face_bbox(const void* __restrict__ xyz, frame_t fr,
+    const uint32_t* __restrict__ face_vtx, const uint32_t* __restrict__ face_off, uint32_t nf, double eps,
+    double* __restrict__ face_bbox, unsigned long long* __restrict__ root_ordered)
+{
+    double bmin[3] = { DBL_MAX, DBL_MAX, DBL_MAX }, bmax[3] = { -DBL_MAX, -DBL_MAX, -DBL_MAX };
+    for (uint32_t f = blockIdx.x * BLOCK + threadIdx.x; f < nf; f += gridDim.x * BLOCK) {
+        const uint32_t h0 = TRI ? 3u * f : face_off[f];
+        const uint32_t h1 = TRI ? h0 + 3u : face_off[f + 1];
+        double mn[3] = { DBL_MAX, DBL_MAX, DBL_MAX }, mx[3] = { -DBL_MAX, -DBL_MAX, -DBL_MAX };
+        for (uint32_t h = h0; h < h1; ++h) {
+            double p[3];
+            load_vertex(xyz, fr, __ldg(face_vtx + h), p);
+#pragma unroll
+            for (int j = 0; j < 3; ++j) {
+                mx[j] = ref_max(mx[j], p[j]);
+                mn[j] = ref_min(mn[j], p[j]);
+            }
+        }
+        if (eps > 0.0) {
+#pragma unroll
+            for (int j = 0; j < 3; ++j) {
+                mx[j] = __dadd_rn(mx[j], eps);
+                mn[j] = __dsub_rn(mn[j], eps);
+            }
+        }
+        double* out = face_bbox + 6 * (size_t)f;
+        // 48-byte rows: three 16-byte stores
+        reinterpret_cast<double2*>(out)[0] = make_double2(mn[0], mn[1]);
+        reinterpret_cast<double2*>(out)[1] = make_double2(mn[2], mx[0]);
+        reinterpret_cast<double2*>(out)[2] = make_double2(mx[1], mx[2]);
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+            bmax[j] = ref_max(bmax[j], mx[j]);
+            bmin[j] = ref_min(bmin[j], mn[j]);
+        }
+    }
+    // warp reduce, then one lane per warp hits the 6 global words (persistent grid => few atomics)
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            bmin[j] = fmin(bmin[j], __shfl_xor_sync(0xffffffffu, bmin[j], o));
+            bmax[j] = fmax(bmax[j], __shfl_xor_sync(0xffffffffu, bmax[j], o));
+        }
+    }
+    __shared__ double s_min[BLOCK / 32][3], s_max[BLOCK / 32][3];
+    const unsigned w = threadIdx.x >> 5;
+    if (lane_id() == 0) {
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+            s_min[w][j] = bmin[j];
+            s_max[w][j] = bmax[j];
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x < 6) {
+        const int j = threadIdx.x % 3;
+        if (threadIdx.x < 3) {
+            double v = s_min[0][j];
+            for (int i = 1; i < BLOCK / 32; ++i) v = fmin(v, s_min[i][j]);
+            if (v != DBL_MAX) atomicMin(root_ordered + j, dbl_to_ordered(v));
+        } else {
+            double v = s_max[0][j];
+            for (int i = 1; i < BLOCK / 32; ++i) v = fmax(v, s_max[i][j]);
+            if (v != -DBL_MAX) atomicMax(root_ordered + 3 + j, dbl_to_ordered(v));
+        }
+    }
+}
+
+// ---- K_morton ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(BLOCK) k_morton(const double* __restrict__ face_bbox, uint32_t nf,
+    const unsigned long long* __restrict__ root_ordered, double* __restrict__ root_decoded, uint32_t* __restrict__ codes,
+    uint32_t* __restrict__ sort_keys)
+{
+    double rmin[3], dims[3];
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+        rmin[j] = ordered_to_dbl(root_ordered[j]);
+        dims[j] = __dsub_rn(ordered_to_dbl(root_ordered[3 + j]), rmin[j]);
+    }
+    if (blockIdx.x == 0 && threadIdx.x < 6) root_decoded[threadIdx.x] = ordered_to_dbl(root_ordered[threadIdx.x]);
+    for (uint32_t f = blockIdx.x * BLOCK + threadIdx.x; f < nf; f += gridDim.x * BLOCK) {
+        const double2* in = reinterpret_cast<const double2*>(face_bbox + 6 * (size_t)f);
+        const double2 a = in[0], b = in[1], c = in[2];
+        const double mn[3] = { a.x, a.y, b.x }, mx[3] = { b.y, c.x, c.y };
+        float nrm[3];
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+            const double centre = __dadd_rn(mn[j], mx[j]) / 2; // bvh.cpp:275
+            const double off = __dsub_rn(centre, rmin[j]); // bvh.cpp:382
+            nrm[j] = (float)(off / dims[j]); // bvh.cpp:399-402
+        }
+        const uint32_t code = morton3D(nrm[0], nrm[1], nrm[2]);
+        codes[f] = code;
+        sort_keys[f] = code;
+    }
+}
+
+// ---- K_karras ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ int delta(const uint32_t* __restrict__ codes, int n, int i, uint32_t ci, int j)
+{
+    if (j < 0 || j >= n) return -1;
+    const uint32_t cj = __ldg(codes + j);
+    if (ci == cj) return 32 + __clz((unsigned)i ^ (unsigned)j); // duplicate codes: tie-break on the index
+    return __clz(ci ^ cj);
+}
+
+__global__ void __launch_bounds__(BLOCK) k_karras(const uint32_t* __restrict__ codes, uint32_t nf, bvh_node_t* __restrict__ nodes,
+    uint32_t* __restrict__ parent)
+{
+    const int n = (int)nf;
+    for (int i = blockIdx.x * BLOCK + threadIdx.x; i < n - 1; i += gridDim.x * BLOCK) {
+        const uint32_t ci = __ldg(codes + i);
+        const int d = (delta(codes, n, i, ci, i + 1) - delta(codes, n, i, ci, i - 1)) >= 0 ? 1 : -1;
+        const int dmin = delta(codes, n, i, ci, i - d);
+        int lmax = 2;
+        while (delta(codes, n, i, ci, i + lmax * d) > dmin) lmax <<= 1;
+        int l = 0;
+        for (int t = lmax >> 1; t >= 1; t >>= 1)
+            if (delta(codes, n, i, ci, i + (l + t) * d) > dmin) l += t;
+        const int j = i + l * d;
+        const int dnode = delta(codes, n, i, ci, j);
+        int s = 0;
+        int t = l;
+        do {
+            t = (t + 1) >> 1;
+            if (delta(codes, n, i, ci, i + (s + t) * d) > dnode) s += t;
+        } while (t > 1);
+        const int gamma = i + s * d + (d < 0 ? -1 : 0);
+        const int lo = i < j ? i : j, hi = i < j ? j : i;
+        const uint32_t left = (lo == gamma) ? (MCB_LEAF_BIT | (uint32_t)gamma) : (uint32_t)gamma;
+        const uint32_t right = (hi == gamma + 1) ? (MCB_LEAF_BIT | (uint32_t)(gamma + 1)) : (uint32_t)(gamma + 1);
+        bvh_node_t* nd = nodes + i;
+        nd->left = left;
+        nd->right = right;
+        nd->first = (uint32_t)lo;
+        nd->last = (uint32_t)hi;
+        parent[(left & MCB_LEAF_BIT) ? (nf - 1 + (left & ~MCB_LEAF_BIT)) : left] = (uint32_t)i;
+        parent[(right & MCB_LEAF_BIT) ? (nf - 1 + (right & ~MCB_LEAF_BIT)) : right] = (uint32_t)i;
+        if (i == 0) parent[0] = MCB200_NULL;
+    }
+}
+
+// ---- K_refit ----------------------------------------------------------------------------------------------------
+// One thread per leaf carries its box up; the first thread to reach a node parks its box in the node and leaves,
+// the second one merges and continues (atomic arrival counter per internal node).
+__device__ __forceinline__ void store_box(double* dst, const double* b)
+{
+    reinterpret_cast<double2*>(dst)[0] = make_double2(b[0], b[1]);
+    reinterpret_cast<double2*>(dst)[1] = make_double2(b[2], b[3]);
+    reinterpret_cast<double2*>(dst)[2] = make_double2(b[4], b[5]);
+}
+__device__ __forceinline__ void load_box_cg(const double* src, double* b)
+{
+    // written by another SM moments ago: read through L2
+    const double2 a = __ldcg(reinterpret_cast<const double2*>(src));
+    const double2 c = __ldcg(reinterpret_cast<const double2*>(src) + 1);
+    const double2 e = __ldcg(reinterpret_cast<const double2*>(src) + 2);
+    b[0] = a.x;
+    b[1] = a.y;
+    b[2] = c.x;
+    b[3] = c.y;
+    b[4] = e.x;
+    b[5] = e.y;
+}
+
+__global__ void __launch_bounds__(BLOCK) k_refit(const double* __restrict__ face_bbox, const uint32_t* __restrict__ sorted_faces,
+    uint32_t nf, bvh_node_t* nodes, const uint32_t* __restrict__ parent, unsigned* flags)
+{
+    if (nf == 1) {
+        // a single leaf (e.g. the planar-section triangle): pseudo-root whose right child can never be hit
+        if (blockIdx.x == 0 && threadIdx.x == 0) {
+            double b[6];
+            const double* src = face_bbox + 6 * (size_t)sorted_faces[0];
+            for (int k = 0; k < 6; ++k) b[k] = src[k];
+            store_box(nodes[0].lbox, b);
+            const double e[6] = { DBL_MAX, DBL_MAX, DBL_MAX, -DBL_MAX, -DBL_MAX, -DBL_MAX };
+            store_box(nodes[0].rbox, e);
+            nodes[0].left = MCB_LEAF_BIT | 0u;
+            nodes[0].right = MCB200_NULL;
+            nodes[0].first = 0;
+            nodes[0].last = 0;
+        }
+        return;
+    }
+    for (uint32_t j = blockIdx.x * BLOCK + threadIdx.x; j < nf; j += gridDim.x * BLOCK) {
+        double box[6];
+        {
+            const double2* in = reinterpret_cast<const double2*>(face_bbox + 6 * (size_t)__ldg(sorted_faces + j));
+            const double2 a = in[0], b = in[1], c = in[2];
+            box[0] = a.x;
+            box[1] = a.y;
+            box[2] = b.x;
+            box[3] = b.y;
+            box[4] = c.x;
+            box[5] = c.y;
+        }
+        uint32_t child = MCB_LEAF_BIT | j;
+        uint32_t p = __ldg(parent + (nf - 1 + j));
+        for (;;) {
+            bvh_node_t* nd = nodes + p;
+            const bool is_left = (nd->left == child);
+            store_box(is_left ? nd->lbox : nd->rbox, box);
+            __threadfence();
+            const unsigned arrived = atomicAdd(flags + p, 1u);
+            if (arrived == 0) break; // sibling subtree not finished yet; its thread will continue from here
+            double sib[6];
+            load_box_cg(is_left ? nd->rbox : nd->lbox, sib);
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                box[k] = ref_min(box[k], sib[k]);
+                box[3 + k] = ref_max(box[3 + k], sib[3 + k]);
+            }
+            if (p == 0) break; // root merged; the mesh AABB itself comes from K_aabb's reduction
+            child = p;
+            p = __ldg(parent + p);
+        }
+    }
+}
+
+} // namespace
+
+int lbvh_build(mcb200_ctx* ctx, mcb200_mesh* m, double eps)
+{
+    if (m->nf == 0) {
+        ctx->set_error("bvh_build: mesh has no faces", __FILE__, __LINE__);
+        return MCB200_ERR_INVALID;
+    }
+    const uint32_t nf = m->nf;
+    MCB_TRY(ctx->reserve(m->face_bbox, sizeof(double) * 6 * (size_t)nf));
+    MCB_TRY(ctx->reserve(m->root, sizeof(unsigned long long) * 6 + sizeof(double) * 6));
+    MCB_TRY(ctx->reserve(m->codes, sizeof(uint32_t) * (size_t)nf));
+    MCB_TRY(ctx->reserve(m->sorted_codes, sizeof(uint32_t) * (size_t)nf));
+    MCB_TRY(ctx->reserve(m->sorted_faces, sizeof(uint32_t) * (size_t)nf));
+    MCB_TRY(ctx->reserve(m->nodes, sizeof(bvh_node_t) * (size_t)(nf > 1 ? nf - 1 : 1)));
+    MCB_TRY(ctx->reserve(m->parent, sizeof(uint32_t) * (2 * (size_t)nf)));
+    MCB_TRY(ctx->reserve(m->flags, sizeof(unsigned) * (size_t)nf));
+    MCB_TRY(ctx->reserve(ctx->sort_keys_alt, sizeof(uint32_t) * (size_t)nf));
+    MCB_TRY(ctx->reserve(ctx->sort_vals_alt, sizeof(uint32_t) * (size_t)nf));
+
+    unsigned long long* root_ord = m->root.as<unsigned long long>();
+    double* root_dec = reinterpret_cast<double*>(root_ord + 6);
+    MCB_CUDA(ctx, cudaMemsetAsync(root_ord, 0xFF, sizeof(unsigned long long) * 3, ctx->stream));
+    MCB_CUDA(ctx, cudaMemsetAsync(root_ord + 3, 0x00, sizeof(unsigned long long) * 3, ctx->stream));
+    MCB_CUDA(ctx, cudaMemsetAsync(m->flags.p, 0, sizeof(unsigned) * (size_t)nf, ctx->stream));
+
+    const unsigned max_grid = (unsigned)ctx->num_sms * 8u;
+    const unsigned grid = div_up(nf, BLOCK) < max_grid ? div_up(nf, BLOCK) : max_grid;
+    if (m->is_tri)
+        MCB_LAUNCH(ctx, k_face_bbox<true>, grid, BLOCK, 0, m->d_xyz, m->frame, m->d_face_vtx, m->d_face_off, nf, eps,
+            m->face_bbox.as<double>(), root_ord);
+    else
+        MCB_LAUNCH(ctx, k_face_bbox<false>, grid, BLOCK, 0, m->d_xyz, m->frame, m->d_face_vtx, m->d_face_off, nf, eps,
+            m->face_bbox.as<double>(), root_ord);
+    MCB_LAUNCH(ctx, k_morton, grid, BLOCK, 0, m->face_bbox.as<double>(), nf, root_ord, root_dec, m->codes.as<uint32_t>(),
+        m->sorted_codes.as<uint32_t>());
+
+    bool in_alt = false;
+    const rsort::pass_desc pd = rsort::make_passes(0, 32);
+    MCB_TRY((rsort::sort<uint32_t, uint32_t, true>(ctx, m->sorted_codes.as<uint32_t>(), ctx->sort_keys_alt.as<uint32_t>(),
+        m->sorted_faces.as<uint32_t>(), ctx->sort_vals_alt.as<uint32_t>(), /*vals_are_iota=*/true, nullptr, nf, pd, &in_alt)));
+    if (in_alt) {
+        ctx->set_error("internal: Morton sort must use an even number of passes", __FILE__, __LINE__);
+        return MCB200_ERR_INTERNAL;
+    }
+    if (nf > 1) {
+        const unsigned g2 = div_up(nf - 1, BLOCK) < max_grid ? div_up(nf - 1, BLOCK) : max_grid;
+        MCB_LAUNCH(ctx, k_karras, g2, BLOCK, 0, m->sorted_codes.as<uint32_t>(), nf, m->nodes.as<bvh_node_t>(),
+            m->parent.as<uint32_t>());
+    }
+    MCB_LAUNCH(ctx, k_refit, grid, BLOCK, 0, m->face_bbox.as<double>(), m->sorted_faces.as<uint32_t>(), nf,
+        m->nodes.as<bvh_node_t>(), m->parent.as<uint32_t>(), m->flags.as<unsigned>());
+    m->built = true;
+    m->eps = eps;
+    return 0;
+}

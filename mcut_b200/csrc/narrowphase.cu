@@ -1,0 +1,639 @@
+// mcut_b200/csrc/narrowphase.cu — (3) exact edge/face narrowphase.
+//
+// Replaces the inline narrowphase of dispatch() (source/kernel.cpp:1779-3231):
+//   "Prepare edge-to-face pairs"  :1781-1983   edge e is tested against the union of the candidate lists of its
+//                                              incident faces.  Here: a candidate pair (f, g) generates the test
+//                                              (e, g) for every halfedge slot e of f; the same (e, g) reached from the
+//                                              face on the other side of e is dropped by an OWNERSHIP rule instead of a
+//                                              sort/unique: the face of halfedge h0 owns the test, the h1 face runs it
+//                                              only when (face(h0), g) is not a candidate pair — decidable locally
+//                                              because the candidate set IS the closed AABB overlap set.
+//   "Build edge bounding boxes" / "Cull"  :1989-2177   edge box vs the BVH-build box of the tested face
+//   "Compute intersecting face properties" :2184-2356  k_planes (also the degenerate-face -> INVALID_*_MESH rule)
+//   "Calculate intersection points"  :2415-3231
+//        k_filter  : Shewchuk stage-A orient3d x2 (error-bound filter), plane point, point-in-polygon, registry
+//                    record; tests whose filter fails are compacted into a queue ...
+//        k_exact   : ... and re-evaluated with the exact expansion arithmetic (orient3dadapt), then the same tail.
+// Registry order: records are sorted by (edge, face) — the canonical order of SURVEY §8-a15; the reference's own order
+// depends on unordered_map iteration and on its thread count.
+#include "internal.h"
+#include "predicates.cuh"
+#include "radix_sort.cuh"
+
+namespace {
+
+constexpr int NBLOCK = 128;
+
+struct narrow_args_t {
+    // geometry
+    const void* src_xyz;
+    const void* cut_xyz;
+    frame_t src_frame, cut_frame;
+    uint32_t src_nv;
+    const double* src_bbox; // [nsf][6]
+    const double* cut_bbox; // [ncf][6] (enlarged, from the unperturbed build)
+    // polygon-soup topology
+    const uint32_t* face_off; // [nf+1]
+    const uint32_t* face_vtx; // [nh] ps vertex ids
+    const uint32_t* face_edge; // [nh]
+    const uint32_t* edge_f; // [ne][2]
+    uint32_t nsf, nf;
+    // work
+    const unsigned long long* pairs;
+    unsigned long long cap_pairs;
+    result_counters_t* counters;
+    // outputs
+    uint8_t* cand_flag;
+    mcb200_record* records;
+    unsigned long long cap_records;
+    unsigned long long* exact_queue; // (pair index << 8 | slot)
+    unsigned long long cap_exact;
+    mcb200_test* tests; // optional log
+    unsigned long long cap_tests;
+};
+
+__device__ __forceinline__ void load_ps_vertex(const narrow_args_t& a, uint32_t v, double* out)
+{
+    if (v < a.src_nv) load_vertex(a.src_xyz, a.src_frame, v, out);
+    else load_vertex(a.cut_xyz, a.cut_frame, v - a.src_nv, out);
+}
+
+__device__ __forceinline__ void load_box(const double* p, double* b)
+{
+    const double2* in = reinterpret_cast<const double2*>(p);
+    const double2 x = __ldg(in), y = __ldg(in + 1), z = __ldg(in + 2);
+    b[0] = x.x;
+    b[1] = x.y;
+    b[2] = y.x;
+    b[3] = y.y;
+    b[4] = z.x;
+    b[5] = z.y;
+}
+
+__device__ __forceinline__ const double* face_box_ptr(const narrow_args_t& a, uint32_t ps_face)
+{
+    return ps_face < a.nsf ? a.src_bbox + 6 * (size_t)ps_face : a.cut_bbox + 6 * (size_t)(ps_face - a.nsf);
+}
+
+// A face whose vertices are fetched on demand (any polygon size).
+struct face_view {
+    const narrow_args_t* a;
+    uint32_t h0, n;
+    __device__ __forceinline__ void vert(uint32_t i, double* out) const { load_ps_vertex(*a, __ldg(a->face_vtx + h0 + i), out); }
+};
+
+// warp-aggregated slot allocation for threads that happen to be in the same branch
+__device__ __forceinline__ unsigned long long alloc_slot(unsigned long long* counter)
+{
+    const unsigned m = __activemask();
+    const int leader = __ffs(m) - 1;
+    unsigned long long base = 0;
+    if ((int)lane_id() == leader) base = atomicAdd(counter, (unsigned long long)__popc(m));
+    base = __shfl_sync(m, base, leader);
+    return base + __popc(m & lanemask_lt());
+}
+
+struct test_out_t {
+    char type, pip;
+    int8_t sq, sr;
+    uint8_t exact;
+    double p[3];
+};
+
+__device__ __forceinline__ int sgn(double x) { return (x > 0.0) - (x < 0.0); }
+
+// plane of face G (math.cpp:130-239); returns max_comp
+template <bool TRI> __device__ __forceinline__ int face_plane(const face_view& G, const double (*gv)[3], double* normal, double& d)
+{
+    if (TRI) return pred::plane_tri(gv[0], gv[1], gv[2], normal, d);
+    normal[0] = normal[1] = normal[2] = 0.0;
+    double first[3], cur[3], nxt[3];
+    G.vert(0, first);
+    for (int k = 0; k < 3; ++k) cur[k] = first[k];
+    for (uint32_t i = 0; i < G.n; ++i) {
+        if (i + 1 < G.n) G.vert(i + 1, nxt);
+        else
+            for (int k = 0; k < 3; ++k) nxt[k] = first[k];
+        pred::newell_step(normal, cur, nxt);
+        for (int k = 0; k < 3; ++k) cur[k] = nxt[k];
+    }
+    return pred::plane_finish(normal, first, d);
+}
+
+// point in polygon (math.cpp:851-902 -> :553-704)
+template <bool TRI>
+__device__ __forceinline__ char face_pip(const face_view& G, const double (*gv)[3], const double* p, const double* normal, int mc)
+{
+    if (TRI) return pred::point_in_triangle(p, gv[0], gv[1], gv[2], normal, mc);
+    double P[6], pp[2];
+    pred::projection_matrix(normal, mc, P);
+    pred::project2(P, p, pp);
+    int rcross = 0, lcross = 0;
+    double v3[3], prev[2], cur[2];
+    G.vert(G.n - 1, v3);
+    pred::project2(P, v3, prev);
+    prev[0] = pred::sub(prev[0], pp[0]);
+    prev[1] = pred::sub(prev[1], pp[1]);
+    for (uint32_t i = 0; i < G.n; ++i) {
+        G.vert(i, v3);
+        pred::project2(P, v3, cur);
+        cur[0] = pred::sub(cur[0], pp[0]);
+        cur[1] = pred::sub(cur[1], pp[1]);
+        if (cur[0] == 0.0 && cur[1] == 0.0) return 'v';
+        const bool rstrad = (cur[1] > 0.0) != (prev[1] > 0.0);
+        const bool lstrad = (cur[1] < 0.0) != (prev[1] < 0.0);
+        if (rstrad || lstrad) {
+            const double x = pred::sub(pred::mul(cur[0], prev[1]), pred::mul(prev[0], cur[1])) / pred::sub(prev[1], cur[1]);
+            if (rstrad && x > 0.0) rcross++;
+            if (lstrad && x < 0.0) lcross++;
+        }
+        prev[0] = cur[0];
+        prev[1] = cur[1];
+    }
+    if ((rcross & 1) != (lcross & 1)) return 'e';
+    return (rcross & 1) ? 'i' : 'o';
+}
+
+// math.cpp:289-389 for faces with more than three vertices: the triple (i<j<k) with the largest |orient2d| of the
+// projected vertices; first maximal one in enumeration order (libstdc++ insertion sort is stable for <= 16 triples).
+__device__ __noinline__ bool best_triple(const face_view& G, const double* normal, int mc, int* ijk)
+{
+    double P[6];
+    pred::projection_matrix(normal, mc, P);
+    double best = -1.0;
+    bool found = false;
+    double vi[3], vj[3], vk[3], xi[2], xj[2], xk[2];
+    for (uint32_t i = 0; i < G.n; ++i) {
+        G.vert(i, vi);
+        pred::project2(P, vi, xi);
+        for (uint32_t j = i + 1; j < G.n; ++j) {
+            G.vert(j, vj);
+            pred::project2(P, vj, xj);
+            for (uint32_t k = j + 1; k < G.n; ++k) {
+                G.vert(k, vk);
+                pred::project2(P, vk, xk);
+                const double r = pred::orient2d(xi, xj, xk);
+                if (r == 0.0) continue;
+                if (fabs(r) > best) {
+                    best = fabs(r);
+                    ijk[0] = (int)i;
+                    ijk[1] = (int)j;
+                    ijk[2] = (int)k;
+                    found = true;
+                }
+            }
+        }
+    }
+    return found;
+}
+
+// One edge/face test (kernel.cpp:2483-2656).  Returns false when the stage-A filter failed and EXACT is off
+// (the caller queues the test for k_exact); otherwise fills `o`.
+template <bool TRI, bool EXACT>
+__device__ __forceinline__ bool eval_test(const face_view& G, const double (*gv)[3], const double* q, const double* r,
+    test_out_t& o, unsigned& gp_violation)
+{
+    double normal[3], d = 0.0;
+    int mc = 0;
+    bool have_plane = false;
+    double A[3], B[3], C[3];
+    if (TRI) {
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            A[k] = gv[0][k];
+            B[k] = gv[1][k];
+            C[k] = gv[2][k];
+        }
+    } else {
+        int ijk[3] = { 0, 1, 2 };
+        if (G.n > 3) {
+            mc = face_plane<false>(G, gv, normal, d);
+            have_plane = true;
+            if (!best_triple(G, normal, mc, ijk)) { // all vertices collinear (math.cpp:408-410)
+                o.type = '0';
+                o.pip = 0;
+                o.sq = o.sr = 0;
+                o.exact = 0;
+                o.p[0] = o.p[1] = o.p[2] = 0.0;
+                return true;
+            }
+        }
+        G.vert((uint32_t)ijk[0], A);
+        G.vert((uint32_t)ijk[1], B);
+        G.vert((uint32_t)ijk[2], C);
+    }
+    bool cq, cr;
+    double permq, permr;
+    double detq = pred::orient3d_stageA(A, B, C, q, cq, permq);
+    double detr = pred::orient3d_stageA(A, B, C, r, cr, permr);
+    o.exact = (uint8_t)((cq ? 0 : 1) | (cr ? 0 : 2));
+    if (!cq || !cr) {
+        if (!EXACT) return false;
+        if (!cq) detq = pred::orient3d_adapt(A, B, C, q, permq);
+        if (!cr) detr = pred::orient3d_adapt(A, B, C, r, permr);
+    }
+    o.sq = (int8_t)sgn(detq);
+    o.sr = (int8_t)sgn(detr);
+    o.pip = 0;
+    o.p[0] = o.p[1] = o.p[2] = 0.0;
+    // math.cpp:416-426
+    if (detq == 0.0 && detr == 0.0) o.type = 'p';
+    else if (detq == 0.0) o.type = 'q';
+    else if (detr == 0.0) o.type = 'r';
+    else if ((detr < 0.0 && detq < 0.0) || (detr > 0.0 && detq > 0.0)) o.type = '0';
+    else o.type = '1';
+    if (o.type == '0') return true;
+    if (!have_plane) mc = face_plane<TRI>(G, gv, normal, d);
+    if (o.type == '1') {
+        pred::segment_plane_point(o.p, normal, d, q, r); // kernel.cpp:2559-2564
+        o.pip = face_pip<TRI>(G, gv, o.p, normal, mc); // :2566-2575
+        if (o.pip == 'v' || o.pip == 'e') gp_violation = 1u; // :2588-2597
+    } else { // 'p' 'q' 'r': an endpoint touches the plane (kernel.cpp:2518-2557)
+        const bool test_q = (o.type != 'r'), test_r = (o.type != 'q');
+        bool stop = false;
+        if (test_q) {
+            o.pip = face_pip<TRI>(G, gv, q, normal, mc);
+            stop = (o.pip == 'i' || o.pip == 'v' || o.pip == 'e');
+        }
+        if (!stop && test_r) {
+            o.pip = face_pip<TRI>(G, gv, r, normal, mc);
+            stop = (o.pip == 'i' || o.pip == 'v' || o.pip == 'e');
+        }
+        if (stop) gp_violation = 1u;
+    }
+    return true;
+}
+
+__device__ __forceinline__ void emit(const narrow_args_t& a, uint32_t edge, uint32_t face, const test_out_t& o)
+{
+    if (o.type == '1' && o.pip == 'i') {
+        const unsigned long long slot = alloc_slot(&a.counters->n_records);
+        if (slot < a.cap_records) {
+            mcb200_record rec;
+            rec.edge = edge;
+            rec.face = face;
+            rec.point[0] = o.p[0];
+            rec.point[1] = o.p[1];
+            rec.point[2] = o.p[2];
+            a.records[slot] = rec;
+        }
+    }
+}
+
+__device__ __forceinline__ void log_test(const narrow_args_t& a, uint32_t edge, uint32_t face, const test_out_t& o)
+{
+    if (!a.tests) return;
+    const unsigned long long slot = alloc_slot(&a.counters->n_log);
+    if (slot < a.cap_tests) {
+        mcb200_test t;
+        t.edge = edge;
+        t.face = face;
+        t.type = o.type;
+        t.pip = o.pip;
+        t.sign_q = o.sq;
+        t.sign_r = o.sr;
+        t.exact = o.exact;
+        t.pad[0] = t.pad[1] = t.pad[2] = 0;
+        t.point[0] = o.p[0];
+        t.point[1] = o.p[1];
+        t.point[2] = o.p[2];
+        a.tests[slot] = t;
+    }
+}
+
+// Decode halfedge slot `slot` of pair (s, c): slots [0, ns) are the halfedges of the source face tested against the
+// cut face, slots [ns, ns+nc) those of the cut face tested against the source face.  Applies ownership + AABB cull.
+// Returns false when the test must not run.  On success q, r are source(h0), target(h0) (kernel.cpp:2466-2474).
+template <bool TRI>
+__device__ __forceinline__ bool setup_test(const narrow_args_t& a, uint32_t s, uint32_t c, uint32_t slot, uint32_t hs,
+    uint32_t ns, uint32_t hc, uint32_t nc, const double (*sv)[3], const double (*cv)[3], const double* sbox,
+    const double* cbox, uint32_t& edge, uint32_t& tested_face, bool& edge_from_src, double* q, double* r)
+{
+    edge_from_src = slot < ns;
+    const uint32_t i = edge_from_src ? slot : slot - ns;
+    const uint32_t n = edge_from_src ? ns : nc;
+    const uint32_t hbase = edge_from_src ? hs : hc;
+    const uint32_t own_face = edge_from_src ? s : a.nsf + c;
+    tested_face = edge_from_src ? a.nsf + c : s;
+    edge = __ldg(a.face_edge + hbase + i);
+    const uint2 ef = __ldg(reinterpret_cast<const uint2*>(a.edge_f) + edge);
+    const bool is_h0 = (ef.x == own_face);
+    const double* tbox = edge_from_src ? cbox : sbox; // box of the tested face
+    if (!is_h0) {
+        // the face of h0 owns this test whenever it is paired with the tested face too
+        double ob[6];
+        load_box(face_box_ptr(a, ef.x), ob);
+        if (overlap6(ob, tbox)) return false;
+    }
+    // halfedge i of a face runs from its vertex i-1 to its vertex i (hmesh.cpp:705-733: vertices are halfedge targets)
+    const uint32_t ip = (i + n - 1) % n;
+    double from[3], to[3];
+    if (TRI) {
+        const double(*fv)[3] = edge_from_src ? sv : cv;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            from[k] = fv[ip][k];
+            to[k] = fv[i][k];
+        }
+    } else {
+        load_ps_vertex(a, __ldg(a.face_vtx + hbase + ip), from);
+        load_ps_vertex(a, __ldg(a.face_vtx + hbase + i), to);
+    }
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        q[k] = is_h0 ? from[k] : to[k];
+        r[k] = is_h0 ? to[k] : from[k];
+    }
+    // edge box vs the tested face's box (kernel.cpp:2004-2027, :2086-2115)
+    double eb[6];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        eb[k] = ref_min(q[k], r[k]);
+        eb[3 + k] = ref_max(q[k], r[k]);
+    }
+    return overlap6(eb, tbox);
+}
+
+template <bool TRI, bool EXACT> __global__ void __launch_bounds__(NBLOCK) k_tests(narrow_args_t a)
+{
+    unsigned long long n_items;
+    if (EXACT) {
+        n_items = a.counters->n_exact < a.cap_exact ? a.counters->n_exact : a.cap_exact;
+    } else {
+        n_items = a.counters->n_pairs < a.cap_pairs ? a.counters->n_pairs : a.cap_pairs;
+    }
+    unsigned n_tests_local = 0, gp = 0;
+    for (unsigned long long it = (unsigned long long)blockIdx.x * NBLOCK + threadIdx.x; it < n_items;
+         it += (unsigned long long)gridDim.x * NBLOCK) {
+        unsigned long long pair_index = it;
+        uint32_t only_slot = 0xFFFFFFFFu;
+        if (EXACT) {
+            const unsigned long long e = a.exact_queue[it];
+            pair_index = e >> 8;
+            only_slot = (uint32_t)(e & 0xFFu);
+        }
+        const unsigned long long pr = a.pairs[pair_index];
+        const uint32_t s = (uint32_t)(pr >> 32), c = (uint32_t)(pr & 0xFFFFFFFFu);
+        const uint32_t hs = TRI ? 3u * s : __ldg(a.face_off + s);
+        const uint32_t ns = TRI ? 3u : __ldg(a.face_off + s + 1) - hs;
+        const uint32_t hc = TRI ? 3u * (a.nsf + c) : __ldg(a.face_off + a.nsf + c);
+        const uint32_t nc = TRI ? 3u : __ldg(a.face_off + a.nsf + c + 1) - hc;
+        if (!EXACT) {
+            a.cand_flag[s] = 1;
+            a.cand_flag[a.nsf + c] = 1;
+        }
+        double sv[3][3], cv[3][3];
+        if (TRI) {
+#pragma unroll
+            for (int i = 0; i < 3; ++i) {
+                load_ps_vertex(a, __ldg(a.face_vtx + hs + i), sv[i]);
+                load_ps_vertex(a, __ldg(a.face_vtx + hc + i), cv[i]);
+            }
+        }
+        double sbox[6], cbox[6];
+        load_box(a.src_bbox + 6 * (size_t)s, sbox);
+        load_box(a.cut_bbox + 6 * (size_t)c, cbox);
+        const face_view SF { &a, hs, ns }, CF { &a, hc, nc };
+        const uint32_t nslots = ns + nc;
+        for (uint32_t slot = EXACT ? only_slot : 0u; slot < (EXACT ? only_slot + 1u : nslots); ++slot) {
+            uint32_t edge, tested_face;
+            bool from_src;
+            double q[3], r[3];
+            if (!setup_test<TRI>(a, s, c, slot, hs, ns, hc, nc, sv, cv, sbox, cbox, edge, tested_face, from_src, q, r)) continue;
+            test_out_t o;
+            const bool done = from_src ? eval_test<TRI, EXACT>(CF, cv, q, r, o, gp) : eval_test<TRI, EXACT>(SF, sv, q, r, o, gp);
+            if (!EXACT) n_tests_local++;
+            if (!done) {
+                // slot index fits 8 bits only for faces with < 128 vertices each; larger faces are evaluated in place
+                if (nslots <= 255u) {
+                    const unsigned long long qs = alloc_slot(&a.counters->n_exact);
+                    if (qs < a.cap_exact) a.exact_queue[qs] = (pair_index << 8) | slot;
+                    continue;
+                }
+                if (from_src) eval_test<TRI, true>(CF, cv, q, r, o, gp);
+                else eval_test<TRI, true>(SF, sv, q, r, o, gp);
+            }
+            emit(a, edge, tested_face, o);
+            log_test(a, edge, tested_face, o);
+        }
+    }
+    // counters: one atomic per warp
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        n_tests_local += __shfl_xor_sync(0xffffffffu, n_tests_local, o);
+        gp |= __shfl_xor_sync(0xffffffffu, gp, o);
+    }
+    if (lane_id() == 0) {
+        if (n_tests_local) atomicAdd(&a.counters->n_tests, (unsigned long long)n_tests_local);
+        if (gp) atomicOr(&a.counters->gp_violation, 1u);
+    }
+}
+
+// ---- per-candidate-face plane data + degenerate-face rule (kernel.cpp:2184-2356) ----------------------------------------
+struct plane_args_t {
+    narrow_args_t n;
+    double* plane; // [cap][4] normal, d   (compacted, unordered; the face id travels in plane_face)
+    int32_t* plane_mc;
+    uint32_t* plane_face;
+};
+
+template <bool TRI> __global__ void __launch_bounds__(NBLOCK) k_planes(plane_args_t pa)
+{
+    const narrow_args_t& a = pa.n;
+    for (uint32_t f = blockIdx.x * NBLOCK + threadIdx.x; f < a.nf; f += gridDim.x * NBLOCK) {
+        if (!a.cand_flag[f]) continue;
+        const uint32_t h0 = TRI ? 3u * f : __ldg(a.face_off + f);
+        const uint32_t n = TRI ? 3u : __ldg(a.face_off + f + 1) - h0;
+        double gv[3][3];
+        if (TRI)
+#pragma unroll
+            for (int i = 0; i < 3; ++i) load_ps_vertex(a, __ldg(a.face_vtx + h0 + i), gv[i]);
+        const face_view G { &a, h0, n };
+        double normal[3], d;
+        const int mc = face_plane<TRI>(G, gv, normal, d);
+        // kernel.cpp:2237-2244: squared_length(normal) == 0 or NaN -> the mesh is invalid
+        if (pred::dot3(normal, normal) == 0.0 || isnan(normal[0]) || isnan(normal[1]) || isnan(normal[2]))
+            atomicMin(&a.counters->bad_face, f);
+        const unsigned long long slot = alloc_slot(&a.counters->n_cand_faces);
+        pa.plane[4 * slot + 0] = normal[0];
+        pa.plane[4 * slot + 1] = normal[1];
+        pa.plane[4 * slot + 2] = normal[2];
+        pa.plane[4 * slot + 3] = d;
+        pa.plane_mc[slot] = mc;
+        pa.plane_face[slot] = f;
+    }
+}
+
+// ---- canonical ordering of records / logged tests -----------------------------------------------------------------------
+template <typename T> __global__ void __launch_bounds__(256) k_make_keys(const T* items, const unsigned long long* d_n,
+    unsigned long long cap, unsigned long long* keys)
+{
+    const unsigned long long n = *d_n < cap ? *d_n : cap;
+    for (unsigned long long i = (unsigned long long)blockIdx.x * 256 + threadIdx.x; i < n; i += (unsigned long long)gridDim.x * 256)
+        keys[i] = ((unsigned long long)items[i].edge << 32) | items[i].face;
+}
+
+template <typename T> __global__ void __launch_bounds__(256) k_gather(const T* items, const uint32_t* idx,
+    const unsigned long long* d_n, unsigned long long cap, T* out)
+{
+    const unsigned long long n = *d_n < cap ? *d_n : cap;
+    for (unsigned long long i = (unsigned long long)blockIdx.x * 256 + threadIdx.x; i < n; i += (unsigned long long)gridDim.x * 256)
+        out[i] = items[idx[i]];
+}
+
+static int bits_for(uint32_t n)
+{
+    int b = 1;
+    while (b < 32 && (1ull << b) < (unsigned long long)n) ++b;
+    return b;
+}
+
+template <typename T>
+int sort_items(mcb200_ctx* ctx, const mcb200_result* res, const T* items, T* items_sorted, dbuf& keys, dbuf& idx,
+    const unsigned long long* d_n, size_t cap, uint32_t nfaces, uint32_t nedges_bound)
+{
+    if (cap == 0) return 0;
+    (void)res;
+    MCB_TRY(ctx->reserve(keys, sizeof(unsigned long long) * cap));
+    MCB_TRY(ctx->reserve(idx, sizeof(uint32_t) * cap));
+    MCB_TRY(ctx->reserve(ctx->sort_keys_alt, sizeof(unsigned long long) * cap));
+    MCB_TRY(ctx->reserve(ctx->sort_vals_alt, sizeof(uint32_t) * cap));
+    const unsigned grid = (unsigned)ctx->num_sms * 2u;
+    MCB_LAUNCH(ctx, (k_make_keys<T>), grid, 256, 0, items, d_n, (unsigned long long)cap, keys.as<unsigned long long>());
+    rsort::pass_desc pd = rsort::make_passes(0, bits_for(nfaces), 32, 32 + bits_for(nedges_bound));
+    if (pd.npasses & 1) {
+        pd.shift[pd.npasses] = 0;
+        pd.bits[pd.npasses] = 0;
+        pd.npasses++;
+    }
+    bool in_alt = false;
+    MCB_TRY((rsort::sort<unsigned long long, uint32_t, true>(ctx, keys.as<unsigned long long>(),
+        ctx->sort_keys_alt.as<unsigned long long>(), idx.as<uint32_t>(), ctx->sort_vals_alt.as<uint32_t>(), true, d_n, cap, pd,
+        &in_alt)));
+    MCB_LAUNCH(ctx, (k_gather<T>), grid, 256, 0, items, idx.as<uint32_t>(), d_n, (unsigned long long)cap, items_sorted);
+    return 0;
+}
+
+} // namespace
+
+int narrowphase_run(mcb200_ctx* ctx, const mcb200_soup* soup, const mcb200_mesh* src, const mcb200_mesh* cut,
+    mcb200_result* res, uint32_t flags)
+{
+    if (!res->have_pairs) {
+        ctx->set_error("narrowphase: run mcb200_bvh_intersect first", __FILE__, __LINE__);
+        return MCB200_ERR_INVALID;
+    }
+    if (soup->nsf != src->nf || soup->ncf != cut->nf) {
+        ctx->set_error("narrowphase: soup does not match the meshes", __FILE__, __LINE__);
+        return MCB200_ERR_INVALID;
+    }
+    const uint32_t nf = soup->nsf + soup->ncf;
+    const bool tri = soup->all_tri != 0;
+    const bool want_log = (flags & MCB200_NARROW_LOG_TESTS) != 0;
+
+    // capacities: a pair yields at most ns + nc tests; records <= tests.  Sized from the pair CAPACITY so no host
+    // round trip is needed between traversal and narrowphase; grown on overflow by the caller-visible retry below.
+    const size_t avg_slots = tri ? 6 : (size_t)((soup->nh + nf - 1) / nf) * 2 + 2;
+    size_t cap_rec = res->cap_pairs * 2;
+    size_t cap_exact = res->cap_pairs * avg_slots;
+    if (cap_exact > (size_t)1 << 28) cap_exact = (size_t)1 << 28;
+    MCB_TRY(ctx->reserve(res->records, sizeof(mcb200_record) * cap_rec));
+    MCB_TRY(ctx->reserve(res->records_sorted, sizeof(mcb200_record) * cap_rec));
+    res->cap_records = cap_rec;
+    MCB_TRY(ctx->reserve(res->exact_queue, sizeof(unsigned long long) * cap_exact));
+    res->cap_exact = cap_exact;
+    MCB_TRY(ctx->reserve(res->cand_flag, (size_t)nf));
+    MCB_CUDA(ctx, cudaMemsetAsync(res->cand_flag.p, 0, (size_t)nf, ctx->stream));
+    MCB_TRY(ctx->reserve(res->plane, sizeof(double) * 4 * (size_t)nf));
+    MCB_TRY(ctx->reserve(res->plane_mc, sizeof(int32_t) * 2 * (size_t)nf));
+    size_t cap_tests = 0;
+    if (want_log) {
+        cap_tests = res->cap_pairs * avg_slots;
+        if (cap_tests > (size_t)1 << 26) cap_tests = (size_t)1 << 26;
+        MCB_TRY(ctx->reserve(res->tests, sizeof(mcb200_test) * cap_tests));
+        MCB_TRY(ctx->reserve(res->tests_sorted, sizeof(mcb200_test) * cap_tests));
+    }
+    res->cap_tests = cap_tests;
+    res->logged_tests = want_log;
+    res->ne_ps = soup->ne;
+
+    // reset the narrowphase counters only (pairs / node tests stay)
+    {
+        result_counters_t* c = res->counters.as<result_counters_t>();
+        MCB_CUDA(ctx, cudaMemsetAsync(&c->n_tests, 0, sizeof(unsigned long long) * 5, ctx->stream)); // n_tests..n_log
+        MCB_CUDA(ctx, cudaMemsetAsync(&c->gp_violation, 0, sizeof(unsigned), ctx->stream));
+        MCB_CUDA(ctx, cudaMemsetAsync(&c->bad_face, 0xFF, sizeof(unsigned), ctx->stream));
+    }
+
+    narrow_args_t a;
+    a.src_xyz = src->d_xyz;
+    a.cut_xyz = cut->d_xyz;
+    a.src_frame = src->frame;
+    a.cut_frame = cut->frame;
+    a.src_nv = src->nv;
+    a.src_bbox = src->face_bbox.as<double>();
+    a.cut_bbox = cut->face_bbox.as<double>();
+    a.face_off = soup->face_off.as<uint32_t>();
+    a.face_vtx = soup->face_vtx.as<uint32_t>();
+    a.face_edge = soup->face_edge.as<uint32_t>();
+    a.edge_f = soup->edge_f.as<uint32_t>();
+    a.nsf = soup->nsf;
+    a.nf = nf;
+    a.pairs = res->pairs.as<unsigned long long>();
+    a.cap_pairs = res->cap_pairs;
+    a.counters = res->counters.as<result_counters_t>();
+    a.cand_flag = res->cand_flag.as<uint8_t>();
+    a.records = res->records.as<mcb200_record>();
+    a.cap_records = cap_rec;
+    a.exact_queue = res->exact_queue.as<unsigned long long>();
+    a.cap_exact = cap_exact;
+    a.tests = want_log ? res->tests.as<mcb200_test>() : nullptr;
+    a.cap_tests = cap_tests;
+
+    const unsigned grid = (unsigned)ctx->num_sms * 8u;
+    if (tri) MCB_LAUNCH(ctx, (k_tests<true, false>), grid, NBLOCK, 0, a);
+    else MCB_LAUNCH(ctx, (k_tests<false, false>), grid, NBLOCK, 0, a);
+
+    plane_args_t pa;
+    pa.n = a;
+    pa.plane = res->plane.as<double>();
+    pa.plane_mc = res->plane_mc.as<int32_t>();
+    pa.plane_face = reinterpret_cast<uint32_t*>(res->plane_mc.as<int32_t>() + nf);
+    const unsigned pgrid = div_up(nf, NBLOCK) < grid ? div_up(nf, NBLOCK) : grid;
+    if (tri) MCB_LAUNCH(ctx, k_planes<true>, pgrid, NBLOCK, 0, pa);
+    else MCB_LAUNCH(ctx, k_planes<false>, pgrid, NBLOCK, 0, pa);
+
+    // exact-expansion pass over the compacted filter failures (own kernel: its local-memory footprint and divergence
+    // stay out of the filter kernel)
+    const unsigned egrid = (unsigned)ctx->num_sms * 4u;
+    if (tri) MCB_LAUNCH(ctx, (k_tests<true, true>), egrid, NBLOCK, 0, a);
+    else MCB_LAUNCH(ctx, (k_tests<false, true>), egrid, NBLOCK, 0, a);
+
+    res->have_narrow = true;
+    res->h_valid = false;
+    res->records_sorted_valid = false;
+    res->tests_sorted_valid = false;
+    MCB_TRY(narrowphase_sort_records(ctx, res));
+    if (want_log) MCB_TRY(narrowphase_sort_tests(ctx, res));
+    return 0;
+}
+
+int narrowphase_sort_records(mcb200_ctx* ctx, mcb200_result* res)
+{
+    if (res->records_sorted_valid) return 0;
+    result_counters_t* c = res->counters.as<result_counters_t>();
+    MCB_TRY(sort_items<mcb200_record>(ctx, res, res->records.as<mcb200_record>(), res->records_sorted.as<mcb200_record>(),
+        res->rec_keys, res->rec_idx, &c->n_records, res->cap_records, res->nf_ps, res->ne_ps));
+    res->records_sorted_valid = true;
+    return 0;
+}
+
+int narrowphase_sort_tests(mcb200_ctx* ctx, mcb200_result* res)
+{
+    if (res->tests_sorted_valid || !res->logged_tests) return 0;
+    result_counters_t* c = res->counters.as<result_counters_t>();
+    MCB_TRY(sort_items<mcb200_test>(ctx, res, res->tests.as<mcb200_test>(), res->tests_sorted.as<mcb200_test>(), res->test_keys,
+        res->test_idx, &c->n_log, res->cap_tests, res->nf_ps, res->ne_ps));
+    res->tests_sorted_valid = true;
+    return 0;
+}

@@ -1,0 +1,306 @@
+// mcut_b200/csrc/radix_sort.cuh — hand-written one-sweep LSD radix sort (no CUB/Thrust).
+//
+// Replaces the reference's single-threaded std::sort of (face, Morton code) pairs (source/bvh.cpp:437-442)
+// and provides the canonical ordering of candidate pairs and registry records.
+//
+// Structure ("onesweep"): ONE histogram kernel reads the keys once and produces the digit histograms of
+// every pass; each pass is then a single sweep: a persistent grid takes 256-thread tiles by ticket, ranks
+// the tile's keys per digit with warp match/ballot, publishes the tile's digit counts and resolves its
+// global offsets by decoupled look-back over the previous tiles (no second read of the keys, no separate
+// scan kernel), reorders the tile through shared memory and writes coalesced runs.
+// The sort is stable, so LSD passes compose.  Element counts may live on the device (d_n), so a sort can
+// follow the kernel that produced its input without a host round trip.
+#pragma once
+
+#include "common.cuh"
+
+namespace rsort {
+
+constexpr int RADIX_BITS = 8;
+constexpr int RADIX = 1 << RADIX_BITS;
+constexpr int THREADS = 256;
+constexpr int WARPS = THREADS / 32;
+constexpr int MAX_PASSES = 8;
+
+constexpr unsigned FLAG_MASK = 0xC0000000u;
+constexpr unsigned FLAG_AGG = 0x40000000u;
+constexpr unsigned FLAG_INCL = 0x80000000u;
+constexpr unsigned VALUE_MASK = 0x3FFFFFFFu;
+
+struct pass_desc {
+    int shift[MAX_PASSES];
+    int bits[MAX_PASSES];
+    int npasses;
+};
+
+// 8-bit chunks over the bit ranges [lo0, hi0) and [lo1, hi1) (second range optional: hi1 <= lo1)
+static inline pass_desc make_passes(int lo0, int hi0, int lo1 = 0, int hi1 = 0)
+{
+    pass_desc p;
+    p.npasses = 0;
+    for (int b = lo0; b < hi0 && p.npasses < MAX_PASSES; b += RADIX_BITS) {
+        p.shift[p.npasses] = b;
+        p.bits[p.npasses] = (hi0 - b < RADIX_BITS) ? hi0 - b : RADIX_BITS;
+        p.npasses++;
+    }
+    for (int b = lo1; b < hi1 && p.npasses < MAX_PASSES; b += RADIX_BITS) {
+        p.shift[p.npasses] = b;
+        p.bits[p.npasses] = (hi1 - b < RADIX_BITS) ? hi1 - b : RADIX_BITS;
+        p.npasses++;
+    }
+    for (int i = p.npasses; i < MAX_PASSES; ++i) {
+        p.shift[i] = 0;
+        p.bits[i] = 0;
+    }
+    return p;
+}
+
+template <typename KeyT> __device__ __forceinline__ unsigned digit_of(KeyT k, int shift, int bits)
+{
+    return (unsigned)(k >> shift) & ((1u << bits) - 1u);
+}
+
+__device__ __forceinline__ size_t resolve_n(const unsigned long long* d_n, size_t n_max)
+{
+    if (!d_n) return n_max;
+    const unsigned long long v = *d_n;
+    return v < n_max ? (size_t)v : n_max;
+}
+
+// ---- histogram of every pass in one read of the keys -------------------------------------------------------------
+// Also clears the look-back status words of the tiles that will exist (a function of the LIVE count, which may
+// only be known on the device), so no capacity-sized memset is needed.
+template <typename KeyT>
+__global__ void __launch_bounds__(THREADS) k_histogram(const KeyT* __restrict__ keys, const unsigned long long* d_n,
+    size_t n_max, pass_desc pd, int tile_items, unsigned* __restrict__ hist /* [npasses][RADIX] */,
+    unsigned* __restrict__ status)
+{
+    __shared__ unsigned s_hist[MAX_PASSES * RADIX];
+    for (int i = threadIdx.x; i < pd.npasses * RADIX; i += THREADS) s_hist[i] = 0;
+    __syncthreads();
+    const size_t n = resolve_n(d_n, n_max);
+    {
+        const size_t tiles = (n + tile_items - 1) / tile_items;
+        const size_t words = tiles * RADIX * (size_t)pd.npasses;
+        for (size_t i = (size_t)blockIdx.x * THREADS + threadIdx.x; i < words; i += (size_t)gridDim.x * THREADS) status[i] = 0u;
+    }
+    for (size_t i = (size_t)blockIdx.x * THREADS + threadIdx.x; i < n; i += (size_t)gridDim.x * THREADS) {
+        const KeyT k = keys[i];
+        for (int p = 0; p < pd.npasses; ++p) atomicAdd(&s_hist[p * RADIX + digit_of(k, pd.shift[p], pd.bits[p])], 1u);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < pd.npasses * RADIX; i += THREADS) {
+        const unsigned c = s_hist[i];
+        if (c) atomicAdd(&hist[i], c);
+    }
+}
+
+// block-wide exclusive scan of one value per thread (256 threads)
+__device__ __forceinline__ unsigned block_exclusive_scan(unsigned v, unsigned* s_warp /* [WARPS] */, unsigned* total)
+{
+    const unsigned lane = threadIdx.x & 31u, w = threadIdx.x >> 5;
+    unsigned inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const unsigned t = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= (unsigned)o) inc += t;
+    }
+    if (lane == 31) s_warp[w] = inc;
+    __syncthreads();
+    unsigned base = 0, tot = 0;
+#pragma unroll
+    for (int i = 0; i < WARPS; ++i) {
+        const unsigned c = s_warp[i];
+        if ((unsigned)i < w) base += c;
+        tot += c;
+    }
+    __syncthreads();
+    if (total) *total = tot;
+    return base + inc - v;
+}
+
+// ---- one pass ------------------------------------------------------------------------------------------------
+// vals_in == nullptr with HAS_VALS: the value of element i is i (saves materialising an iota array).
+template <typename KeyT, typename ValT, bool HAS_VALS, int ITEMS>
+__global__ void __launch_bounds__(THREADS) k_onesweep_pass(const KeyT* __restrict__ keys_in, KeyT* __restrict__ keys_out,
+    const ValT* __restrict__ vals_in, ValT* __restrict__ vals_out, const unsigned long long* d_n, size_t n_max, int shift,
+    int bits, int pass_index, const unsigned* __restrict__ hist /* [RADIX] of this pass */,
+    unsigned* status_all /* [npasses][tiles(n)][RADIX] */, unsigned* tile_counter)
+{
+    constexpr int TILE = THREADS * ITEMS;
+    __shared__ unsigned s_warp_hist[WARPS][RADIX];
+    __shared__ unsigned s_tile_excl[RADIX];
+    __shared__ unsigned s_global_off[RADIX];
+    __shared__ unsigned s_scan[WARPS];
+    __shared__ unsigned s_tile;
+    __shared__ KeyT s_keys[TILE];
+    __shared__ ValT s_vals[HAS_VALS ? TILE : 1];
+
+    const size_t n = resolve_n(d_n, n_max);
+    const unsigned num_tiles = (unsigned)((n + TILE - 1) / TILE);
+    unsigned* status = status_all + (size_t)pass_index * num_tiles * RADIX;
+    const unsigned lane = threadIdx.x & 31u, w = threadIdx.x >> 5;
+    const unsigned lt = lanemask_lt();
+
+    // exclusive scan of the pass histogram: where each digit's bucket starts in the output
+    unsigned my_bucket_base = block_exclusive_scan(hist[threadIdx.x], s_scan, nullptr);
+
+    for (;;) {
+        if (threadIdx.x == 0) s_tile = atomicAdd(tile_counter, 1u);
+        for (int i = threadIdx.x; i < WARPS * RADIX; i += THREADS) (&s_warp_hist[0][0])[i] = 0;
+        __syncthreads();
+        const unsigned tile = s_tile;
+        if (tile >= num_tiles) break;
+        const size_t tile_base = (size_t)tile * TILE;
+        const unsigned tile_n = (unsigned)((n - tile_base < (size_t)TILE) ? (n - tile_base) : (size_t)TILE);
+
+        // ---- load (warp-striped inside each warp's contiguous chunk) and rank ----
+        KeyT key[ITEMS];
+        ValT val[HAS_VALS ? ITEMS : 1];
+        unsigned short rank[ITEMS];
+#pragma unroll
+        for (int j = 0; j < ITEMS; ++j) {
+            const unsigned local = w * (32 * ITEMS) + j * 32 + lane;
+            const bool valid = local < tile_n;
+            key[j] = valid ? keys_in[tile_base + local] : (KeyT)0;
+            if (HAS_VALS) val[j] = valid ? (vals_in ? vals_in[tile_base + local] : (ValT)(tile_base + local)) : (ValT)0;
+        }
+#pragma unroll
+        for (int j = 0; j < ITEMS; ++j) {
+            const unsigned local = w * (32 * ITEMS) + j * 32 + lane;
+            const bool valid = local < tile_n;
+            const unsigned vmask = __ballot_sync(0xffffffffu, valid);
+            unsigned r = 0;
+            if (valid) {
+                const unsigned d = digit_of(key[j], shift, bits);
+                const unsigned peers = __match_any_sync(vmask, d);
+                const int leader = __ffs(peers) - 1;
+                unsigned old = 0;
+                if ((int)lane == leader) {
+                    old = s_warp_hist[w][d];
+                    s_warp_hist[w][d] = old + __popc(peers);
+                }
+                old = __shfl_sync(peers, old, leader);
+                r = old + __popc(peers & lt);
+            }
+            rank[j] = (unsigned short)r;
+            __syncwarp();
+        }
+        __syncthreads();
+
+        // ---- per-digit: warp counts -> exclusive warp offsets, tile total ----
+        unsigned total = 0;
+        {
+            const unsigned d = threadIdx.x;
+#pragma unroll
+            for (int i = 0; i < WARPS; ++i) {
+                const unsigned c = s_warp_hist[i][d];
+                s_warp_hist[i][d] = total;
+                total += c;
+            }
+        }
+        // publish the tile's digit count as early as possible so successors can look back
+        {
+            const unsigned d = threadIdx.x;
+            volatile unsigned* st = status + (size_t)tile * RADIX + d;
+            *st = (tile == 0) ? (FLAG_INCL | total) : (FLAG_AGG | total);
+        }
+        const unsigned excl_in_tile = block_exclusive_scan(total, s_scan, nullptr);
+        s_tile_excl[threadIdx.x] = excl_in_tile;
+
+        // ---- decoupled look-back: sum of this digit's counts over all previous tiles ----
+        {
+            const unsigned d = threadIdx.x;
+            unsigned prefix = 0;
+            if (tile > 0) {
+                int t = (int)tile - 1;
+                while (t >= 0) {
+                    volatile unsigned* st = status + (size_t)t * RADIX + d;
+                    unsigned s;
+                    do {
+                        s = *st;
+                    } while ((s & FLAG_MASK) == 0);
+                    prefix += s & VALUE_MASK;
+                    if (s & FLAG_INCL) break;
+                    --t;
+                }
+                volatile unsigned* me = status + (size_t)tile * RADIX + d;
+                *me = FLAG_INCL | (prefix + total);
+            }
+            s_global_off[d] = my_bucket_base + prefix;
+        }
+        __syncthreads();
+
+        // ---- reorder the tile through shared memory ----
+#pragma unroll
+        for (int j = 0; j < ITEMS; ++j) {
+            const unsigned local = w * (32 * ITEMS) + j * 32 + lane;
+            if (local < tile_n) {
+                const unsigned d = digit_of(key[j], shift, bits);
+                const unsigned pos = s_tile_excl[d] + s_warp_hist[w][d] + rank[j];
+                s_keys[pos] = key[j];
+                if (HAS_VALS) s_vals[pos] = val[j];
+            }
+        }
+        __syncthreads();
+        // ---- coalesced runs out ----
+        for (unsigned i = threadIdx.x; i < tile_n; i += THREADS) {
+            const KeyT k = s_keys[i];
+            const unsigned d = digit_of(k, shift, bits);
+            const size_t dst = (size_t)s_global_off[d] + (i - s_tile_excl[d]);
+            keys_out[dst] = k;
+            if (HAS_VALS) vals_out[dst] = s_vals[i];
+        }
+        __syncthreads();
+    }
+}
+
+template <typename KeyT> struct items_for {
+    static constexpr int value = sizeof(KeyT) == 4 ? 16 : 8;
+};
+
+// Sort n (or *d_n) keys [and values].  keys/vals are the in/out arrays, alt_* the ping-pong buffers.  Returns in
+// *result_in_alt whether the sorted data ended up in the alt buffers (odd number of passes).
+// scratch: hist [MAX_PASSES*RADIX] u32, status [npasses * tiles * RADIX] u32, tilectr [MAX_PASSES] u32.
+template <typename KeyT, typename ValT, bool HAS_VALS>
+int sort(mcb200_ctx* ctx, KeyT* keys, KeyT* alt_keys, ValT* vals, ValT* alt_vals, bool vals_are_iota,
+    const unsigned long long* d_n, size_t n_max, const pass_desc& pd, bool* result_in_alt)
+{
+    constexpr int ITEMS = items_for<KeyT>::value;
+    constexpr int TILE = THREADS * ITEMS;
+    *result_in_alt = false;
+    if (n_max == 0 || pd.npasses == 0) return 0;
+    const size_t tiles = (n_max + TILE - 1) / TILE;
+    MCB_TRY(ctx->reserve(ctx->sort_hist, sizeof(unsigned) * MAX_PASSES * RADIX));
+    MCB_TRY(ctx->reserve(ctx->sort_status, sizeof(unsigned) * (size_t)pd.npasses * tiles * RADIX));
+    MCB_TRY(ctx->reserve(ctx->sort_tilectr, sizeof(unsigned) * MAX_PASSES));
+    MCB_CUDA(ctx, cudaMemsetAsync(ctx->sort_hist.p, 0, sizeof(unsigned) * MAX_PASSES * RADIX, ctx->stream));
+    MCB_CUDA(ctx, cudaMemsetAsync(ctx->sort_tilectr.p, 0, sizeof(unsigned) * MAX_PASSES, ctx->stream));
+
+    const unsigned hgrid = (unsigned)((tiles < (size_t)ctx->num_sms * 4) ? tiles : (size_t)ctx->num_sms * 4);
+    MCB_LAUNCH(ctx, (k_histogram<KeyT>), hgrid, THREADS, 0, keys, d_n, n_max, pd, TILE, ctx->sort_hist.as<unsigned>(),
+        ctx->sort_status.as<unsigned>());
+
+    // persistent grid: enough resident blocks to fill the machine, never more than tiles
+    const unsigned pgrid = (unsigned)((tiles < (size_t)ctx->num_sms * 4) ? tiles : (size_t)ctx->num_sms * 4);
+    KeyT* kin = keys;
+    KeyT* kout = alt_keys;
+    ValT* vin = vals;
+    ValT* vout = alt_vals;
+    for (int p = 0; p < pd.npasses; ++p) {
+        const ValT* vsrc = (HAS_VALS && p == 0 && vals_are_iota) ? nullptr : vin;
+        MCB_LAUNCH(ctx, (k_onesweep_pass<KeyT, ValT, HAS_VALS, ITEMS>), pgrid, THREADS, 0, kin, kout, vsrc, vout, d_n, n_max,
+            pd.shift[p], pd.bits[p], p, ctx->sort_hist.as<unsigned>() + p * RADIX, ctx->sort_status.as<unsigned>(),
+            ctx->sort_tilectr.as<unsigned>() + p);
+        KeyT* tk = kin;
+        kin = kout;
+        kout = tk;
+        ValT* tv = vin;
+        vin = vout;
+        vout = tv;
+    }
+    *result_in_alt = (pd.npasses & 1) != 0;
+    return 0;
+}
+
+} // namespace rsort

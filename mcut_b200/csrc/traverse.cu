@@ -1,0 +1,295 @@
+// mcut_b200/csrc/traverse.cu — (2) BVH x BVH overlap traversal.
+//
+// Replaces intersectOIBVHs() (include/mcut/internal/bvh.h:127-133, source/bvh.cpp:638-783), a serial BFS over
+// node pairs feeding a std::map.  The emitted set is {(s, c) : face_bbox_src[s] overlaps face_bbox_cut[c]} with
+// closed intervals (math.h:931-941) whatever the trees look like, so the device walks its own LBVHs:
+//
+//   * the mesh with more faces is the QUERY side; its Morton-sorted leaves are cut into groups of 32;
+//   * one warp owns a group: lane l keeps leaf l's box in registers, the warp keeps the group's union box;
+//   * the warp walks the other mesh's tree with a stack in shared memory, up to 32 nodes per step — one node per
+//     lane, one 128-byte line per node carrying both children's boxes; surviving internal children are pushed with
+//     __ballot_sync/__popc slots, surviving leaves go to a shared candidate list;
+//   * candidates are then tested against the 32 lane-resident leaf boxes (box broadcast from shared memory) and hits
+//     are compacted with __ballot_sync/__popc into a per-warp buffer that is flushed to global memory with ONE
+//     atomicAdd per ~200 pairs.
+// Pairs come out as (src_face << 32 | cut_face) and are then put in ascending order by the one-sweep sort, which
+// makes the output independent of scheduling (and of how many GPUs produced it).
+#include "internal.h"
+#include "radix_sort.cuh"
+
+namespace {
+
+constexpr int WARPS_PER_BLOCK = 4;
+constexpr int TBLOCK = WARPS_PER_BLOCK * 32;
+constexpr int STACK_CAP = 1024;
+constexpr int CAND_CAP = 96;
+constexpr int OUT_CAP = 256;
+constexpr int GROUP_BATCH = 4;
+
+struct warp_scratch_t {
+    uint32_t stack[STACK_CAP];
+    double cand_box[CAND_CAP][6];
+    uint32_t cand_face[CAND_CAP];
+    unsigned long long out[OUT_CAP];
+};
+
+struct traverse_args_t {
+    // query side
+    const double* q_face_bbox;
+    const uint32_t* q_sorted_faces;
+    uint32_t q_nf;
+    // tree side
+    const bvh_node_t* t_nodes;
+    const uint32_t* t_sorted_faces;
+    uint32_t t_nf;
+    int query_is_cut; // emit (tree_face << 32 | query_face) instead
+    // sharding of the query leaf range
+    uint32_t shard_part, shard_nparts, shard_chunk;
+    // output
+    unsigned long long* pairs;
+    unsigned long long cap_pairs;
+    result_counters_t* counters;
+};
+
+__device__ __forceinline__ void flush_out(warp_scratch_t& ws, unsigned& nout, const traverse_args_t& a)
+{
+    if (nout == 0) return;
+    unsigned long long base = 0;
+    if (lane_id() == 0) base = atomicAdd(&a.counters->n_pairs, (unsigned long long)nout);
+    base = __shfl_sync(0xffffffffu, base, 0);
+    for (unsigned i = lane_id(); i < nout; i += 32) {
+        const unsigned long long dst = base + i;
+        if (dst < a.cap_pairs) a.pairs[dst] = ws.out[i];
+        else a.counters->pair_overflow = 1u;
+    }
+    __syncwarp();
+    nout = 0;
+}
+
+// test candidates [first, first+count) of the shared list against the 32 lane-resident query boxes
+__device__ __forceinline__ void drain_candidates(warp_scratch_t& ws, unsigned first, unsigned count, const double* mybox,
+    bool valid, uint32_t myface, unsigned& nout, unsigned long long& ntests, const traverse_args_t& a)
+{
+    const unsigned lt = lanemask_lt();
+    for (unsigned k = first; k < first + count; ++k) {
+        const double* cb = ws.cand_box[k];
+        const bool hit = valid && overlap6(mybox, cb);
+        const unsigned mask = __ballot_sync(0xffffffffu, hit);
+        if (mask) {
+            if (hit) {
+                const uint32_t tf = ws.cand_face[k];
+                const unsigned long long pair = a.query_is_cut ? (((unsigned long long)tf << 32) | myface)
+                                                               : (((unsigned long long)myface << 32) | tf);
+                ws.out[nout + __popc(mask & lt)] = pair;
+            }
+            nout += __popc(mask);
+            __syncwarp();
+            if (nout > OUT_CAP - 32) flush_out(ws, nout, a);
+        }
+    }
+    ntests += count;
+}
+
+__global__ void __launch_bounds__(TBLOCK) k_traverse(traverse_args_t a)
+{
+    __shared__ warp_scratch_t s_ws[WARPS_PER_BLOCK];
+    warp_scratch_t& ws = s_ws[threadIdx.x >> 5];
+    const unsigned lane = lane_id();
+    const unsigned lt = lanemask_lt();
+    const uint32_t ngroups = (a.q_nf + 31u) / 32u;
+    unsigned nout = 0;
+    unsigned long long ntests = 0;
+
+    for (;;) {
+        uint32_t g0 = 0;
+        if (lane == 0) g0 = atomicAdd(&a.counters->work_counter, (unsigned)GROUP_BATCH);
+        g0 = __shfl_sync(0xffffffffu, g0, 0);
+        if (g0 >= ngroups) break;
+        const uint32_t g1 = (g0 + GROUP_BATCH < ngroups) ? g0 + GROUP_BATCH : ngroups;
+        for (uint32_t g = g0; g < g1; ++g) {
+            if (a.shard_nparts > 1 && ((g * 32u) / a.shard_chunk) % a.shard_nparts != a.shard_part) continue;
+            // ---- lane-resident query leaf + the group's union box ----
+            const uint32_t q = g * 32u + lane;
+            const bool valid = q < a.q_nf;
+            uint32_t myface = 0;
+            double mybox[6] = { DBL_MAX, DBL_MAX, DBL_MAX, -DBL_MAX, -DBL_MAX, -DBL_MAX };
+            if (valid) {
+                myface = __ldg(a.q_sorted_faces + q);
+                const double2* in = reinterpret_cast<const double2*>(a.q_face_bbox + 6 * (size_t)myface);
+                const double2 x = __ldg(in), y = __ldg(in + 1), z = __ldg(in + 2);
+                mybox[0] = x.x;
+                mybox[1] = x.y;
+                mybox[2] = y.x;
+                mybox[3] = y.y;
+                mybox[4] = z.x;
+                mybox[5] = z.y;
+            }
+            double gbox[6];
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                double mn = mybox[k], mx = mybox[3 + k];
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                    mn = fmin(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+                    mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+                }
+                gbox[k] = mn;
+                gbox[3 + k] = mx;
+            }
+
+            // ---- walk the tree ----
+            unsigned size = 1, ncand = 0;
+            if (lane == 0) ws.stack[0] = 0u;
+            __syncwarp();
+            while (size > 0) {
+                if (ncand > 32) { // keep room for the up-to-64 leaves one step can add
+                    drain_candidates(ws, ncand - 32, 32, mybox, valid, myface, nout, ntests, a);
+                    ncand -= 32;
+                }
+                // wide steps while the stack has room; near the cap fall back to one node per step, whose growth is
+                // bounded by the tree depth (LIFO order keeps it a depth-first walk)
+                const unsigned width = (size <= STACK_CAP - 160) ? 32u : 1u;
+                const unsigned take = size < width ? size : width;
+                const bool active = lane < take;
+                bool hitL = false, hitR = false;
+                uint32_t left = 0, right = 0;
+                double lb[6], rb[6];
+                if (active) {
+                    const uint32_t node = ws.stack[size - 1 - lane];
+                    const double2* nd = reinterpret_cast<const double2*>(a.t_nodes + node);
+                    const double2 l0 = __ldg(nd), l1 = __ldg(nd + 1), l2 = __ldg(nd + 2);
+                    const double2 r0 = __ldg(nd + 3), r1 = __ldg(nd + 4), r2 = __ldg(nd + 5);
+                    const uint2 ch = __ldg(reinterpret_cast<const uint2*>(nd + 6));
+                    lb[0] = l0.x; lb[1] = l0.y; lb[2] = l1.x; lb[3] = l1.y; lb[4] = l2.x; lb[5] = l2.y;
+                    rb[0] = r0.x; rb[1] = r0.y; rb[2] = r1.x; rb[3] = r1.y; rb[4] = r2.x; rb[5] = r2.y;
+                    left = ch.x;
+                    right = ch.y;
+                    hitL = overlap6(gbox, lb);
+                    hitR = (right != MCB200_NULL) && overlap6(gbox, rb);
+                }
+                __syncwarp();
+                size -= take;
+                ntests += 2ull * take;
+                // internal children -> stack
+                {
+                    const bool pl = hitL && !(left & MCB_LEAF_BIT);
+                    const unsigned ml = __ballot_sync(0xffffffffu, pl);
+                    if (pl) ws.stack[size + __popc(ml & lt)] = left;
+                    size += __popc(ml);
+                    const bool pr = hitR && !(right & MCB_LEAF_BIT);
+                    const unsigned mr = __ballot_sync(0xffffffffu, pr);
+                    if (pr) ws.stack[size + __popc(mr & lt)] = right;
+                    size += __popc(mr);
+                }
+                // leaf children -> candidate list (box travels with it, no second fetch)
+                {
+                    const bool cl = hitL && (left & MCB_LEAF_BIT);
+                    const unsigned ml = __ballot_sync(0xffffffffu, cl);
+                    if (cl) {
+                        const unsigned slot = ncand + __popc(ml & lt);
+#pragma unroll
+                        for (int k = 0; k < 6; ++k) ws.cand_box[slot][k] = lb[k];
+                        ws.cand_face[slot] = __ldg(a.t_sorted_faces + (left & ~MCB_LEAF_BIT));
+                    }
+                    ncand += __popc(ml);
+                    const bool cr = hitR && (right & MCB_LEAF_BIT);
+                    const unsigned mr = __ballot_sync(0xffffffffu, cr);
+                    if (cr) {
+                        const unsigned slot = ncand + __popc(mr & lt);
+#pragma unroll
+                        for (int k = 0; k < 6; ++k) ws.cand_box[slot][k] = rb[k];
+                        ws.cand_face[slot] = __ldg(a.t_sorted_faces + (right & ~MCB_LEAF_BIT));
+                    }
+                    ncand += __popc(mr);
+                }
+                __syncwarp();
+            }
+            if (ncand) drain_candidates(ws, 0, ncand, mybox, valid, myface, nout, ntests, a);
+        }
+    }
+    flush_out(ws, nout, a);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) ntests += __shfl_xor_sync(0xffffffffu, ntests, o);
+    if (lane == 0 && ntests) atomicAdd(&a.counters->n_node_tests, ntests / 32ull);
+}
+
+static int bits_for(uint32_t n)
+{
+    int b = 1;
+    while (b < 32 && (1ull << b) < (unsigned long long)n) ++b;
+    return b;
+}
+
+} // namespace
+
+int traverse_pairs(mcb200_ctx* ctx, const mcb200_mesh* src, const mcb200_mesh* cut, mcb200_result* res)
+{
+    if (!src->built || !cut->built) {
+        ctx->set_error("bvh_intersect: both meshes need mcb200_bvh_build first", __FILE__, __LINE__);
+        return MCB200_ERR_INVALID;
+    }
+    const bool query_is_cut = cut->nf > src->nf;
+    const mcb200_mesh* q = query_is_cut ? cut : src;
+    const mcb200_mesh* t = query_is_cut ? src : cut;
+
+    if (res->cap_pairs == 0) {
+        size_t want = 4ull * ((size_t)src->nf + cut->nf);
+        if (want < (1u << 20)) want = 1u << 20;
+        MCB_TRY(ctx->reserve(res->pairs, sizeof(unsigned long long) * want));
+        res->cap_pairs = want;
+    }
+    MCB_TRY(ctx->reserve(res->counters, sizeof(result_counters_t)));
+    MCB_CUDA(ctx, cudaMemsetAsync(res->counters.p, 0, sizeof(result_counters_t), ctx->stream));
+    {
+        // bad_face starts at "none"
+        const size_t off = offsetof(result_counters_t, bad_face);
+        MCB_CUDA(ctx, cudaMemsetAsync(reinterpret_cast<char*>(res->counters.p) + off, 0xFF, sizeof(unsigned), ctx->stream));
+    }
+    res->nsf = src->nf;
+    res->nf_ps = src->nf + cut->nf;
+    res->h_valid = false;
+    res->have_narrow = false;
+    res->records_sorted_valid = false;
+    res->tests_sorted_valid = false;
+
+    traverse_args_t a;
+    a.q_face_bbox = q->face_bbox.as<double>();
+    a.q_sorted_faces = q->sorted_faces.as<uint32_t>();
+    a.q_nf = q->nf;
+    a.t_nodes = t->nodes.as<bvh_node_t>();
+    a.t_sorted_faces = t->sorted_faces.as<uint32_t>();
+    a.t_nf = t->nf;
+    a.query_is_cut = query_is_cut ? 1 : 0;
+    a.shard_part = res->shard_part;
+    a.shard_nparts = res->shard_nparts;
+    a.shard_chunk = res->shard_chunk ? res->shard_chunk : 4096u;
+    a.pairs = res->pairs.as<unsigned long long>();
+    a.cap_pairs = res->cap_pairs;
+    a.counters = res->counters.as<result_counters_t>();
+
+    const uint32_t ngroups = (q->nf + 31u) / 32u;
+    const unsigned want_blocks = div_up(div_up(ngroups, GROUP_BATCH), WARPS_PER_BLOCK);
+    const unsigned max_blocks = (unsigned)ctx->num_sms * 4u; // 4 x 44.5 KB of shared memory per SM
+    const unsigned grid = want_blocks < max_blocks ? (want_blocks ? want_blocks : 1u) : max_blocks;
+    MCB_LAUNCH(ctx, k_traverse, grid, TBLOCK, 0, a);
+
+    // ascending (src << 32 | cut): only the bits that can be set take part in the sort; an odd pass count gets a
+    // zero-bit (identity) pass appended so the result lands in res->pairs without a capacity-sized copy
+    rsort::pass_desc pd = rsort::make_passes(0, bits_for(cut->nf), 32, 32 + bits_for(src->nf));
+    if (pd.npasses & 1) {
+        pd.shift[pd.npasses] = 0;
+        pd.bits[pd.npasses] = 0;
+        pd.npasses++;
+    }
+    MCB_TRY(ctx->reserve(ctx->sort_keys_alt, sizeof(unsigned long long) * res->cap_pairs));
+    bool in_alt = false;
+    MCB_TRY((rsort::sort<unsigned long long, uint32_t, false>(ctx, res->pairs.as<unsigned long long>(),
+        ctx->sort_keys_alt.as<unsigned long long>(), nullptr, nullptr, false,
+        &res->counters.as<result_counters_t>()->n_pairs, res->cap_pairs, pd, &in_alt)));
+    if (in_alt) {
+        ctx->set_error("internal: pair sort ended in the alternate buffer", __FILE__, __LINE__);
+        return MCB200_ERR_INTERNAL;
+    }
+    res->have_pairs = true;
+    return 0;
+}

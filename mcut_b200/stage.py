@@ -1,0 +1,292 @@
+"""Host-side mirror of the reference's intersect stage over the C-ABI (include/mcut_b200.h).
+
+The names follow the reference: a `Context` is what mcCreateContext gives (one device, one stream), and
+`intersect_stage()` walks the same steps preproc() walks between "calculate_vertex_parameters" and the end of the
+kernel's "Calculate intersection points" (source/preproc.cpp:2292-2926, source/kernel.cpp:1779-3231):
+
+    frame (com/shift)            host, sequential            mcb200_vertex_parameters
+    build_oibvh(src), (cut)      device                      mcb200_bvh_build
+    intersectOIBVHs              device                      mcb200_bvh_intersect
+    polygon-soup ids             host, integer               mcb200_soup_from_meshes
+    edge/face narrowphase        device                      mcb200_narrowphase
+
+Everything that computes runs in the CUDA library; this module only moves arrays and raises on errors.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, Optional, Tuple
+
+import numpy as np
+
+from . import _lib
+from ._lib import Counts, Record, Test, c_dp, c_i32p, c_u32p, c_u64p
+
+MC_DISPATCH_VERTEX_ARRAY_FLOAT = 1 << 0
+MC_DISPATCH_VERTEX_ARRAY_DOUBLE = 1 << 1
+MC_DISPATCH_ENFORCE_GENERAL_POSITION = 1 << 15
+MC_DISPATCH_ENFORCE_GENERAL_POSITION_ABSOLUTE = 1 << 16
+
+NARROW_LOG_TESTS = 1
+
+STATUS_SUCCESS = 0
+STATUS_GENERAL_POSITION_VIOLATION = 1
+STATUS_INVALID_SRC_MESH = 2
+STATUS_INVALID_CUT_MESH = 3
+
+RECORD_DTYPE = np.dtype([("edge", "<u4"), ("face", "<u4"), ("point", "<f8", (3,))])
+TEST_DTYPE = np.dtype([("edge", "<u4"), ("face", "<u4"), ("type", "S1"), ("pip", "S1"), ("sign_q", "i1"), ("sign_r", "i1"),
+                       ("exact", "u1"), ("pad", "u1", (3,)), ("point", "<f8", (3,))])
+
+
+class Mcb200Error(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"mcut_b200 error {code}: {msg}")
+        self.code = code
+
+
+def _dp(a: Optional[np.ndarray]):
+    if a is None:
+        return None
+    assert a.dtype == np.float64 and a.flags.c_contiguous
+    return a.ctypes.data_as(c_dp)
+
+
+def _u32p(a: Optional[np.ndarray]):
+    if a is None:
+        return None
+    assert a.dtype == np.uint32 and a.flags.c_contiguous
+    return a.ctypes.data_as(c_u32p)
+
+
+def vertex_parameters(src_xyz: np.ndarray, cut_xyz: np.ndarray):
+    """com, shift, src_bbox, cut_bbox of source/preproc.cpp:2124-2290 (host; float or double arrays)."""
+    L = _lib.lib()
+    is_float = src_xyz.dtype == np.float32
+    if cut_xyz.dtype != src_xyz.dtype:
+        raise ValueError("both meshes must use the same vertex type (one MC_DISPATCH_VERTEX_ARRAY_* flag)")
+    s = np.ascontiguousarray(src_xyz)
+    c = np.ascontiguousarray(cut_xyz)
+    com, shift, sb, cb = np.zeros(3), np.zeros(3), np.zeros(6), np.zeros(6)
+    L.mcb200_vertex_parameters(int(is_float), s.ctypes.data, s.shape[0], c.ctypes.data, c.shape[0], _dp(com), _dp(shift), _dp(sb),
+                               _dp(cb))
+    return com, shift, sb, cb
+
+
+def cut_bbox_eps(cut_bbox: np.ndarray, gp_constant: float = 1e-4, absolute: bool = False) -> float:
+    return float(_lib.lib().mcb200_cut_bbox_eps(_dp(np.ascontiguousarray(cut_bbox)), gp_constant, int(absolute)))
+
+
+def soup_ids(nsv: int, src_off: np.ndarray, src_vtx: np.ndarray, cut_off: np.ndarray, cut_vtx: np.ndarray):
+    """Polygon-soup numbering (host).  Returns face_vtx, face_edge, edge_v[ne,2], edge_f[ne,2]."""
+    L = _lib.lib()
+    nh = int(src_off[-1]) + int(cut_off[-1])
+    fv = np.zeros(nh, dtype=np.uint32)
+    fe = np.zeros(nh, dtype=np.uint32)
+    ev = np.zeros(2 * nh, dtype=np.uint32)
+    ef = np.zeros(2 * nh, dtype=np.uint32)
+    ne = C.c_uint32(0)
+    rc = L.mcb200_soup_ids(nsv, _u32p(src_off), _u32p(src_vtx), src_off.size - 1, _u32p(cut_off), _u32p(cut_vtx), cut_off.size - 1,
+                           _u32p(fv), _u32p(fe), _u32p(ev), _u32p(ef), C.byref(ne))
+    if rc:
+        raise Mcb200Error(rc, "soup_ids: non-manifold edge, inconsistent winding or degenerate face")
+    n = ne.value
+    return fv, fe, ev[:2 * n].reshape(n, 2).copy(), ef[:2 * n].reshape(n, 2).copy()
+
+
+class Context:
+    """One device + one stream (what an MCUT context maps to)."""
+
+    def __init__(self, device: int = 0, stream: int = 0):
+        self.L = _lib.lib()
+        self.h = C.c_void_p()
+        rc = self.L.mcb200_ctx_create(device, C.c_void_p(stream) if stream else None, C.byref(self.h))
+        if rc:
+            raise Mcb200Error(rc, self.L.mcb200_last_error(None).decode())
+        self.device = device
+
+    def check(self, rc: int):
+        if rc:
+            raise Mcb200Error(rc, self.L.mcb200_last_error(self.h).decode())
+
+    def sync(self):
+        self.check(self.L.mcb200_ctx_sync(self.h))
+
+    @property
+    def launches(self) -> int:
+        return int(self.L.mcb200_ctx_launch_count(self.h))
+
+    def close(self):
+        if self.h:
+            self.L.mcb200_ctx_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class Mesh:
+    def __init__(self, ctx: Context, xyz: np.ndarray, faces: np.ndarray, sizes: Optional[np.ndarray] = None):
+        self.ctx = ctx
+        self.h = C.c_void_p()
+        if xyz.dtype not in (np.float32, np.float64):
+            raise TypeError("vertices must be float32 or float64")
+        self.is_float = xyz.dtype == np.float32
+        xyz = np.ascontiguousarray(xyz)
+        faces = np.ascontiguousarray(faces, dtype=np.uint32)
+        sizes = None if sizes is None else np.ascontiguousarray(sizes, dtype=np.uint32)
+        self.nv = int(xyz.shape[0])
+        self.nf = int(sizes.size) if sizes is not None else int(faces.size // 3)
+        ctx.check(ctx.L.mcb200_mesh_create(ctx.h, int(self.is_float), xyz.ctypes.data, self.nv, _u32p(faces), _u32p(sizes), self.nf,
+                                           C.byref(self.h)))
+
+    def set_frame(self, com=None, shift=None, perturbation=None):
+        f = lambda a: None if a is None else _dp(np.ascontiguousarray(a, dtype=np.float64))
+        self.ctx.check(self.ctx.L.mcb200_mesh_set_frame(self.ctx.h, self.h, f(com), f(shift), f(perturbation)))
+
+    def build(self, eps: float = 0.0):
+        self.ctx.check(self.ctx.L.mcb200_bvh_build(self.ctx.h, self.h, float(eps)))
+
+    def read_bvh(self, want_boxes: bool = True):
+        bb = np.zeros((self.nf, 6)) if want_boxes else None
+        root = np.zeros(6)
+        self.ctx.check(self.ctx.L.mcb200_bvh_read(self.ctx.h, self.h, _dp(bb), _dp(root)))
+        return bb, root
+
+    def read_morton(self):
+        codes = np.zeros(self.nf, dtype=np.uint32)
+        order = np.zeros(self.nf, dtype=np.uint32)
+        self.ctx.check(self.ctx.L.mcb200_bvh_read_morton(self.ctx.h, self.h, _u32p(codes), _u32p(order)))
+        return codes, order
+
+    def free(self):
+        if self.h:
+            self.ctx.L.mcb200_mesh_free(self.ctx.h, self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+class Soup:
+    def __init__(self, ctx: Context, src: Mesh, cut: Mesh):
+        self.ctx = ctx
+        self.h = C.c_void_p()
+        ctx.check(ctx.L.mcb200_soup_from_meshes(ctx.h, src.h, cut.h, C.byref(self.h)))
+
+    def free(self):
+        if self.h:
+            self.ctx.L.mcb200_soup_free(self.ctx.h, self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+class Result:
+    def __init__(self, ctx: Context):
+        self.ctx = ctx
+        self.h = C.c_void_p()
+        ctx.check(ctx.L.mcb200_result_create(ctx.h, C.byref(self.h)))
+
+    def set_shard(self, part: int, nparts: int, chunk: int = 4096):
+        self.ctx.check(self.ctx.L.mcb200_result_set_shard(self.ctx.h, self.h, part, nparts, chunk))
+
+    def counts(self) -> Counts:
+        c = Counts()
+        self.ctx.check(self.ctx.L.mcb200_result_counts(self.ctx.h, self.h, C.byref(c)))
+        return c
+
+    def pairs(self) -> np.ndarray:
+        n = int(self.counts().n_pairs)
+        out = np.zeros(n, dtype=np.uint64)
+        self.ctx.check(self.ctx.L.mcb200_result_read_pairs(self.ctx.h, self.h, out.ctypes.data_as(c_u64p), n))
+        return out
+
+    def records(self) -> np.ndarray:
+        n = int(self.counts().n_records)
+        out = np.zeros(n, dtype=RECORD_DTYPE)
+        self.ctx.check(self.ctx.L.mcb200_result_read_records(self.ctx.h, self.h, out.ctypes.data_as(C.POINTER(Record)), n))
+        return out
+
+    def tests(self) -> np.ndarray:
+        # the log count is not part of mcb200_counts; ask with a generous capacity = n_tests
+        n = int(self.counts().n_tests)
+        out = np.zeros(n, dtype=TEST_DTYPE)
+        self.ctx.check(self.ctx.L.mcb200_result_read_tests(self.ctx.h, self.h, out.ctypes.data_as(C.POINTER(Test)), n))
+        return out
+
+    def planes(self):
+        n = int(self.counts().n_cand_faces)
+        faces = np.zeros(n, dtype=np.uint32)
+        normal = np.zeros((n, 3))
+        d = np.zeros(n)
+        mc = np.zeros(n, dtype=np.int32)
+        self.ctx.check(self.ctx.L.mcb200_result_read_planes(self.ctx.h, self.h, _u32p(faces), _dp(normal), _dp(d),
+                                                            mc.ctypes.data_as(c_i32p), n))
+        return faces, normal, d, mc
+
+    def device_ptr(self, which: int) -> Tuple[int, int]:
+        p = C.c_void_p()
+        n = C.c_uint64(0)
+        self.ctx.check(self.ctx.L.mcb200_result_device_ptr(self.ctx.h, self.h, which, C.byref(p), C.byref(n)))
+        return int(p.value or 0), int(n.value)
+
+    def free(self):
+        if self.h:
+            self.ctx.L.mcb200_result_free(self.ctx.h, self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+def intersect_stage(ctx: Context, src, cut, flags: int, gp_constant: float = 1e-4, perturbation=None, log_tests: bool = False,
+                    want_boxes: bool = True) -> Dict[str, object]:
+    """One kernel invocation's intersect stage on user arrays, through the C-ABI with host buffers.
+    `src`/`cut` = (xyz[V,3] float32|float64, faces_flat uint32, sizes uint32|None)."""
+    sx, sf, ss = src
+    cx, cf, cs = cut
+    com, shift, sbb, cbb = vertex_parameters(sx, cx)
+    eps = cut_bbox_eps(cbb, gp_constant, bool(flags & MC_DISPATCH_ENFORCE_GENERAL_POSITION_ABSOLUTE))
+    ms = Mesh(ctx, sx, sf, ss)
+    mc = Mesh(ctx, cx, cf, cs)
+    ms.set_frame(com, shift)
+    mc.set_frame(com, shift)  # boxes/BVH of the cut mesh always come from the unperturbed frame
+    ms.build(0.0)
+    mc.build(eps)
+    res = Result(ctx)
+    ctx.check(ctx.L.mcb200_bvh_intersect(ctx.h, ms.h, mc.h, res.h))
+    soup = Soup(ctx, ms, mc)
+    if perturbation is not None:
+        mc.set_frame(com, shift, perturbation)
+    ctx.check(ctx.L.mcb200_narrowphase(ctx.h, soup.h, ms.h, mc.h, res.h, NARROW_LOG_TESTS if log_tests else 0))
+    c = res.counts()
+    out: Dict[str, object] = {
+        "com": com, "shift": shift, "eps": eps, "status": int(c.status), "bad_face": int(c.bad_face),
+        "n_pairs": int(c.n_pairs), "n_node_tests": int(c.n_node_tests), "n_tests": int(c.n_tests), "n_exact": int(c.n_exact),
+        "n_records": int(c.n_records), "n_cand_faces": int(c.n_cand_faces),
+        "pairs": res.pairs(), "records": res.records(),
+    }
+    if want_boxes:
+        out["src_bboxes"], out["src_root"] = ms.read_bvh()
+        out["cut_bboxes"], out["cut_root"] = mc.read_bvh()
+    faces, normal, d, mcmp = res.planes()
+    out.update({"cand_faces": faces, "cand_normal": normal, "cand_d": d, "cand_maxcomp": mcmp})
+    if log_tests:
+        out["tests"] = res.tests()
+    for o in (soup, res, ms, mc):
+        o.free()
+    return out
