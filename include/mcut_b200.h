@@ -70,6 +70,12 @@ const char* mcb200_last_error(const mcb200_ctx* ctx); /* ctx may be NULL: last e
 int mcb200_ctx_sync(mcb200_ctx* ctx);
 /* number of kernels this context has launched so far (bench.py's gpu_launches) */
 uint64_t mcb200_ctx_launch_count(const mcb200_ctx* ctx);
+/* Per-kernel device timing for bench.py's roofline figures: while on, every launch is bracketed by a CUDA event
+ * pair on the context's stream.  mcb200_ctx_profile_read synchronises, writes one line per kernel name
+ * ("<name> <launches> <total_ms>\n") into buf, resets the log and returns the number of bytes written
+ * (negative error code on failure).  Off by default; never on inside a timed region that is reported as `value`. */
+int mcb200_ctx_set_profiling(mcb200_ctx* ctx, int on);
+int mcb200_ctx_profile_read(mcb200_ctx* ctx, char* buf, size_t capacity);
 
 /* ---------------------------------------------------------------- host-side logic (no GPU) ----------------- */
 void mcb200_vertex_parameters(int is_float, const void* src_xyz, uint32_t nsv, const void* cut_xyz, uint32_t ncv,

@@ -42,6 +42,8 @@ SYMBOLS = {
     "mcb200_last_error": (C.c_char_p, [vp]),
     "mcb200_ctx_sync": (C.c_int, [vp]),
     "mcb200_ctx_launch_count": (C.c_uint64, [vp]),
+    "mcb200_ctx_set_profiling": (C.c_int, [vp, C.c_int]),
+    "mcb200_ctx_profile_read": (C.c_int, [vp, C.c_char_p, C.c_size_t]),
     "mcb200_vertex_parameters": (None, [C.c_int, vp, C.c_uint32, vp, C.c_uint32, c_dp, c_dp, c_dp, c_dp]),
     "mcb200_cut_bbox_eps": (C.c_double, [c_dp, C.c_double, C.c_int]),
     "mcb200_soup_ids": (C.c_int, [C.c_uint32, c_u32p, c_u32p, C.c_uint32, c_u32p, c_u32p, C.c_uint32, c_u32p, c_u32p, c_u32p,

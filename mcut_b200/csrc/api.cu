@@ -114,6 +114,11 @@ void mcb200_ctx_destroy(mcb200_ctx* ctx)
     ctx->release(ctx->sort_tilectr);
     cudaStreamSynchronize(ctx->stream);
     if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
+    for (auto& r : ctx->prof) {
+        cudaEventDestroy(r.a);
+        cudaEventDestroy(r.b);
+    }
+    for (cudaEvent_t e : ctx->prof_pool) cudaEventDestroy(e);
     if (ctx->owns_stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -132,6 +137,51 @@ int mcb200_ctx_sync(mcb200_ctx* ctx)
 }
 
 uint64_t mcb200_ctx_launch_count(const mcb200_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+int mcb200_ctx_set_profiling(mcb200_ctx* ctx, int on)
+{
+    if (!ctx) return MCB200_ERR_INVALID;
+    ctx->profiling = on != 0;
+    return 0;
+}
+
+int mcb200_ctx_profile_read(mcb200_ctx* ctx, char* buf, size_t capacity)
+{
+    if (!ctx || !buf || capacity == 0) return MCB200_ERR_INVALID;
+    MCB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    std::vector<std::string> names;
+    std::vector<double> total;
+    std::vector<unsigned> count;
+    for (const auto& r : ctx->prof) {
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, r.a, r.b);
+        size_t k = 0;
+        for (; k < names.size(); ++k)
+            if (names[k] == r.name) break;
+        if (k == names.size()) {
+            names.push_back(r.name);
+            total.push_back(0.0);
+            count.push_back(0);
+        }
+        total[k] += ms;
+        count[k] += 1;
+        ctx->prof_pool.push_back(r.a);
+        ctx->prof_pool.push_back(r.b);
+    }
+    ctx->prof.clear();
+    std::string out;
+    for (size_t k = 0; k < names.size(); ++k) {
+        std::string nm = names[k];
+        for (char& c : nm)
+            if (c == ' ') c = '_';
+        char line[512];
+        std::snprintf(line, sizeof(line), "%s %u %.6f\n", nm.c_str(), count[k], total[k]);
+        out += line;
+    }
+    if (out.size() + 1 > capacity) MCB_FAIL(ctx, MCB200_ERR_CAPACITY, "profile_read: buffer too small");
+    std::memcpy(buf, out.c_str(), out.size() + 1);
+    return (int)out.size();
+}
 
 // ---------------------------------------------------------------------------------------------------------- meshes
 

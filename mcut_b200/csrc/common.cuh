@@ -47,6 +47,25 @@ struct mcb200_ctx {
     bool owns_stream = false;
     std::string error;
     uint64_t launches = 0;
+    // optional per-kernel timing (mcb200_ctx_set_profiling): an event pair around every launch
+    bool profiling = false;
+    struct prof_rec {
+        const char* name;
+        cudaEvent_t a, b;
+    };
+    std::vector<prof_rec> prof;
+    std::vector<cudaEvent_t> prof_pool;
+    cudaEvent_t prof_event()
+    {
+        if (!prof_pool.empty()) {
+            cudaEvent_t e = prof_pool.back();
+            prof_pool.pop_back();
+            return e;
+        }
+        cudaEvent_t e;
+        cudaEventCreate(&e);
+        return e;
+    }
     // pinned staging for small D2H reads (counters)
     void* h_pinned = nullptr;
     size_t h_pinned_cap = 0;
@@ -272,7 +291,17 @@ static inline unsigned div_up(size_t a, size_t b) { return (unsigned)((a + b - 1
 // launch accounting: every kernel launch of the product goes through this macro
 #define MCB_LAUNCH(ctx, kernel, grid, block, smem, ...)                          \
     do {                                                                         \
+        mcb200_ctx::prof_rec pr__ { #kernel, nullptr, nullptr };                 \
+        if ((ctx)->profiling) {                                                  \
+            pr__.a = (ctx)->prof_event();                                        \
+            pr__.b = (ctx)->prof_event();                                        \
+            cudaEventRecord(pr__.a, (ctx)->stream);                              \
+        }                                                                        \
         kernel<<<(grid), (block), (smem), (ctx)->stream>>>(__VA_ARGS__);         \
+        if ((ctx)->profiling) {                                                  \
+            cudaEventRecord(pr__.b, (ctx)->stream);                              \
+            (ctx)->prof.push_back(pr__);                                         \
+        }                                                                        \
         (ctx)->launches++;                                                       \
         cudaError_t le__ = cudaPeekAtLastError();                                \
         if (le__ != cudaSuccess) {                                               \

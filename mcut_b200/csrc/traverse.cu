@@ -142,7 +142,7 @@ __global__ void __launch_bounds__(TBLOCK) k_traverse(traverse_args_t a)
             if (lane == 0) ws.stack[0] = 0u;
             __syncwarp();
             while (size > 0) {
-                if (ncand > 32) { // keep room for the up-to-64 leaves one step can add
+                while (ncand > 32) { // keep room for the up-to-64 leaves one step can add (CAND_CAP = 32 + 64)
                     drain_candidates(ws, ncand - 32, 32, mybox, valid, myface, nout, ntests, a);
                     ncand -= 32;
                 }

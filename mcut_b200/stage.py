@@ -112,6 +112,21 @@ class Context:
     def sync(self):
         self.check(self.L.mcb200_ctx_sync(self.h))
 
+    def set_profiling(self, on: bool):
+        self.check(self.L.mcb200_ctx_set_profiling(self.h, int(on)))
+
+    def profile_read(self) -> Dict[str, Tuple[int, float]]:
+        """{kernel name: (launches, total device ms)} since the last read; synchronises."""
+        buf = C.create_string_buffer(1 << 16)
+        n = self.L.mcb200_ctx_profile_read(self.h, buf, len(buf))
+        if n < 0:
+            self.check(n)
+        out: Dict[str, Tuple[int, float]] = {}
+        for line in buf.value.decode().splitlines():
+            name, cnt, ms = line.rsplit(" ", 2)
+            out[name] = (int(cnt), float(ms))
+        return out
+
     @property
     def launches(self) -> int:
         return int(self.L.mcb200_ctx_launch_count(self.h))

@@ -33,6 +33,11 @@ def spheres_k16():
     return mg.c2_two_spheres(k=16)
 
 
+def spheres_k64():
+    """49,152 triangles per mesh: several radix-sort tiles, deep trees, > 32 leaf candidates per traversal step."""
+    return mg.c2_two_spheres(k=64)
+
+
 def uv12():
     return mg.two_uv_spheres(12, 20.0)
 
@@ -102,6 +107,7 @@ ALL = {
     "hello": hello,
     "spheres_k8": spheres_k8,
     "spheres_k16": spheres_k16,
+    "spheres_k64": spheres_k64,
     "uv12": uv12,
     "ico_pair": ico_pair,
     "cube_cube_axis_aligned": cube_cube_axis_aligned,
