@@ -252,7 +252,12 @@ def run_ours(args):
     src_nv, src_nf = meshgen.mesh_counts(src)
     cut_nv, cut_nf = meshgen.mesh_counts(cut)
 
-    stream = torch.cuda.current_stream().cuda_stream
+    # torch's legacy default stream has handle 0, which the C-ABI reads as "make your own stream"; use an explicit
+    # stream for everything so torch.cuda.Event (which sees torch's CURRENT stream only) brackets our kernels
+    tstream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(tstream)
+    stream = tstream.cuda_stream
+    assert stream != 0
     ctx = stage.Context(local_rank, stream)
 
     # ---- host-side inputs of the stage (what `hmesh`/`ps` are to the reference's stage): frame + polygon-soup ids ----

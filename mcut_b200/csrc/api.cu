@@ -317,6 +317,7 @@ void mcb200_mesh_free(mcb200_ctx* ctx, mcb200_mesh* m)
     ctx->release(m->nodes);
     ctx->release(m->parent);
     ctx->release(m->flags);
+    ctx->release(m->groups);
     delete m;
 }
 

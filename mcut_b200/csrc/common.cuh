@@ -154,6 +154,8 @@ struct mcb200_mesh {
     dbuf nodes; // [max(nf-1,1)] bvh_node_t (128 B)
     dbuf parent; // [2nf-1] u32 parent of internal node i / leaf (nf-1+j)
     dbuf flags; // [nf-1] u32 refit arrival counters
+    dbuf groups; // [nf] uint2 query groups (first leaf, count) + u32 counter after them
+    bool groups_valid = false;
 };
 
 // One LBVH node: both children's boxes live in the parent so one 128-byte line feeds a traversal step.

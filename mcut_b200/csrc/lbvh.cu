@@ -309,6 +309,7 @@ int lbvh_build(mcb200_ctx* ctx, mcb200_mesh* m, double eps)
     MCB_LAUNCH(ctx, k_refit, grid, BLOCK, 0, m->face_bbox.as<double>(), m->sorted_faces.as<uint32_t>(), nf,
         m->nodes.as<bvh_node_t>(), m->parent.as<uint32_t>(), m->flags.as<unsigned>());
     m->built = true;
+    m->groups_valid = false;
     m->eps = eps;
     return 0;
 }

@@ -4,7 +4,9 @@
 // node pairs feeding a std::map.  The emitted set is {(s, c) : face_bbox_src[s] overlaps face_bbox_cut[c]} with
 // closed intervals (math.h:931-941) whatever the trees look like, so the device walks its own LBVHs:
 //
-//   * the mesh with more faces is the QUERY side; its Morton-sorted leaves are cut into groups of 32;
+//   * the mesh with more faces is the QUERY side; its leaves are grouped by the query mesh's OWN tree: a group is a
+//     maximal subtree with at most 32 leaves (k_groups).  Such treelets are spatially compact — cutting the Morton
+//     order into fixed runs of 32 is not: a run that straddles an octant boundary has a union box spanning the mesh;
 //   * one warp owns a group: lane l keeps leaf l's box in registers, the warp keeps the group's union box;
 //   * the warp walks the other mesh's tree with a stack in shared memory, up to 32 nodes per step — one node per
 //     lane, one 128-byte line per node carrying both children's boxes; surviving internal children are pushed with
@@ -21,10 +23,10 @@ namespace {
 
 constexpr int WARPS_PER_BLOCK = 4;
 constexpr int TBLOCK = WARPS_PER_BLOCK * 32;
-constexpr int STACK_CAP = 1024;
+constexpr int STACK_CAP = 512;
 constexpr int CAND_CAP = 96;
-constexpr int OUT_CAP = 256;
-constexpr int GROUP_BATCH = 4;
+constexpr int OUT_CAP = 128;
+constexpr int GROUP_BATCH = 2;
 
 struct warp_scratch_t {
     uint32_t stack[STACK_CAP];
@@ -38,6 +40,9 @@ struct traverse_args_t {
     const double* q_face_bbox;
     const uint32_t* q_sorted_faces;
     uint32_t q_nf;
+    const uint2* groups; // (first sorted leaf, leaf count <= 32)
+    const unsigned* n_groups;
+    const double* t_root; // mesh AABB of the tree side (6 doubles)
     // tree side
     const bvh_node_t* t_nodes;
     const uint32_t* t_sorted_faces;
@@ -90,13 +95,49 @@ __device__ __forceinline__ void drain_candidates(warp_scratch_t& ws, unsigned fi
     ntests += count;
 }
 
+// ---- query groups = maximal subtrees of the query mesh's LBVH with <= 32 leaves --------------------------------------
+__global__ void __launch_bounds__(256) k_groups(const bvh_node_t* __restrict__ nodes, const uint32_t* __restrict__ parent,
+    uint32_t nf, uint2* __restrict__ groups, unsigned* __restrict__ n_groups)
+{
+    // items [0, nf-1): internal nodes; items [nf-1, 2nf-1): leaves
+    const uint32_t total = 2u * nf - 1u;
+    for (uint32_t it = blockIdx.x * 256u + threadIdx.x; it < total; it += gridDim.x * 256u) {
+        uint32_t first, count;
+        if (it < nf - 1u) {
+            first = nodes[it].first;
+            count = nodes[it].last - first + 1u;
+        } else {
+            first = it - (nf - 1u);
+            count = 1u;
+        }
+        if (count > 32u) continue;
+        bool is_group_root = true;
+        const bool is_tree_root = (nf == 1u) || (it == 0u);
+        if (!is_tree_root) {
+            const uint32_t p = __ldg(parent + it);
+            const uint32_t pc = nodes[p].last - nodes[p].first + 1u;
+            is_group_root = pc > 32u;
+        }
+        if (!is_group_root) continue;
+        const unsigned m = __activemask();
+        const int leader = __ffs(m) - 1;
+        unsigned base = 0;
+        if ((int)lane_id() == leader) base = atomicAdd(n_groups, (unsigned)__popc(m));
+        base = __shfl_sync(m, base, leader);
+        groups[base + __popc(m & lanemask_lt())] = make_uint2(first, count);
+    }
+}
+
 __global__ void __launch_bounds__(TBLOCK) k_traverse(traverse_args_t a)
 {
     __shared__ warp_scratch_t s_ws[WARPS_PER_BLOCK];
     warp_scratch_t& ws = s_ws[threadIdx.x >> 5];
     const unsigned lane = lane_id();
     const unsigned lt = lanemask_lt();
-    const uint32_t ngroups = (a.q_nf + 31u) / 32u;
+    const uint32_t ngroups = *a.n_groups;
+    double troot[6];
+#pragma unroll
+    for (int k = 0; k < 6; ++k) troot[k] = __ldg(a.t_root + k);
     unsigned nout = 0;
     unsigned long long ntests = 0;
 
@@ -107,10 +148,11 @@ __global__ void __launch_bounds__(TBLOCK) k_traverse(traverse_args_t a)
         if (g0 >= ngroups) break;
         const uint32_t g1 = (g0 + GROUP_BATCH < ngroups) ? g0 + GROUP_BATCH : ngroups;
         for (uint32_t g = g0; g < g1; ++g) {
-            if (a.shard_nparts > 1 && ((g * 32u) / a.shard_chunk) % a.shard_nparts != a.shard_part) continue;
+            const uint2 grp = __ldg(a.groups + g);
+            if (a.shard_nparts > 1 && (grp.x / a.shard_chunk) % a.shard_nparts != a.shard_part) continue;
             // ---- lane-resident query leaf + the group's union box ----
-            const uint32_t q = g * 32u + lane;
-            const bool valid = q < a.q_nf;
+            const uint32_t q = grp.x + lane;
+            const bool valid = lane < grp.y;
             uint32_t myface = 0;
             double mybox[6] = { DBL_MAX, DBL_MAX, DBL_MAX, -DBL_MAX, -DBL_MAX, -DBL_MAX };
             if (valid) {
@@ -138,7 +180,7 @@ __global__ void __launch_bounds__(TBLOCK) k_traverse(traverse_args_t a)
             }
 
             // ---- walk the tree ----
-            unsigned size = 1, ncand = 0;
+            unsigned size = overlap6(gbox, troot) ? 1u : 0u, ncand = 0;
             if (lane == 0) ws.stack[0] = 0u;
             __syncwarp();
             while (size > 0) {
@@ -148,7 +190,7 @@ __global__ void __launch_bounds__(TBLOCK) k_traverse(traverse_args_t a)
                 }
                 // wide steps while the stack has room; near the cap fall back to one node per step, whose growth is
                 // bounded by the tree depth (LIFO order keeps it a depth-first walk)
-                const unsigned width = (size <= STACK_CAP - 160) ? 32u : 1u;
+                const unsigned width = (size <= STACK_CAP - 160) ? 32u : 1u; // 160 = 32 (wide growth) + 128 (depth bound)
                 const unsigned take = size < width ? size : width;
                 const bool active = lane < take;
                 bool hitL = false, hitR = false;
@@ -267,9 +309,24 @@ int traverse_pairs(mcb200_ctx* ctx, const mcb200_mesh* src, const mcb200_mesh* c
     a.cap_pairs = res->cap_pairs;
     a.counters = res->counters.as<result_counters_t>();
 
-    const uint32_t ngroups = (q->nf + 31u) / 32u;
-    const unsigned want_blocks = div_up(div_up(ngroups, GROUP_BATCH), WARPS_PER_BLOCK);
-    const unsigned max_blocks = (unsigned)ctx->num_sms * 4u; // 4 x 44.5 KB of shared memory per SM
+    // query groups from the query mesh's own tree (cached on the mesh: they only depend on its build)
+    mcb200_mesh* qm = const_cast<mcb200_mesh*>(q);
+    if (!qm->groups_valid) {
+        MCB_TRY(ctx->reserve(qm->groups, sizeof(uint2) * (size_t)q->nf + sizeof(unsigned) * 4));
+        unsigned* ng = reinterpret_cast<unsigned*>(qm->groups.as<uint2>() + q->nf);
+        MCB_CUDA(ctx, cudaMemsetAsync(ng, 0, sizeof(unsigned) * 4, ctx->stream));
+        const unsigned gg = div_up(2u * (size_t)q->nf, 256) < (unsigned)ctx->num_sms * 8u ? div_up(2u * (size_t)q->nf, 256)
+                                                                                         : (unsigned)ctx->num_sms * 8u;
+        MCB_LAUNCH(ctx, k_groups, gg, 256, 0, q->nodes.as<bvh_node_t>(), q->parent.as<uint32_t>(), q->nf, qm->groups.as<uint2>(), ng);
+        qm->groups_valid = true;
+    }
+    a.groups = q->groups.as<uint2>();
+    a.n_groups = reinterpret_cast<const unsigned*>(q->groups.as<uint2>() + q->nf);
+    a.t_root = reinterpret_cast<const double*>(t->root.as<unsigned long long>() + 6);
+
+    // a persistent grid sized for the machine; groups are handed out by an atomic ticket
+    const unsigned max_blocks = (unsigned)ctx->num_sms * 8u;
+    const unsigned want_blocks = div_up(div_up((size_t)q->nf / 8u + 1u, GROUP_BATCH), WARPS_PER_BLOCK);
     const unsigned grid = want_blocks < max_blocks ? (want_blocks ? want_blocks : 1u) : max_blocks;
     MCB_LAUNCH(ctx, k_traverse, grid, TBLOCK, 0, a);
 
