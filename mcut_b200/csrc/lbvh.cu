@@ -135,44 +135,69 @@ __global__ void __launch_bounds__(BLOCK) k_morton(const double* __restrict__ fac
 }
 
 // ---- K_karras ---------------------------------------------------------------------------------------------------
-__device__ __forceinline__ int delta(const uint32_t* __restrict__ codes, int n, int i, uint32_t ci, int j)
-{
-    if (j < 0 || j >= n) return -1;
-    const uint32_t cj = __ldg(codes + j);
-    if (ci == cj) return 32 + __clz((unsigned)i ^ (unsigned)j); // duplicate codes: tie-break on the index
-    return __clz(ci ^ cj);
-}
+// One thread per internal node (Karras 2012).  A block owns 256 consecutive nodes and stages the sorted codes of a
+// +-1024 window in shared memory: the range/split binary searches of almost every node stay inside that window, so
+// their ~40 dependent probes cost shared-memory latency instead of L2 latency.
+constexpr int KHALO = 1024;
+constexpr int KWIN = BLOCK + 2 * KHALO;
+
+struct code_window {
+    const uint32_t* codes;
+    const uint32_t* win; // shared copy of codes[base, base + KWIN)
+    int base, n;
+    __device__ __forceinline__ uint32_t get(int j) const
+    {
+        const int r = j - base;
+        return ((unsigned)r < (unsigned)KWIN) ? win[r] : __ldg(codes + j);
+    }
+    __device__ __forceinline__ int delta(int i, uint32_t ci, int j) const
+    {
+        if (j < 0 || j >= n) return -1;
+        const uint32_t cj = get(j);
+        if (ci == cj) return 32 + __clz((unsigned)i ^ (unsigned)j); // duplicate codes: tie-break on the index
+        return __clz(ci ^ cj);
+    }
+};
 
 __global__ void __launch_bounds__(BLOCK) k_karras(const uint32_t* __restrict__ codes, uint32_t nf, bvh_node_t* __restrict__ nodes,
-    uint32_t* __restrict__ parent)
+    uint4* __restrict__ meta, uint32_t* __restrict__ parent)
 {
+    __shared__ uint32_t s_win[KWIN];
     const int n = (int)nf;
-    for (int i = blockIdx.x * BLOCK + threadIdx.x; i < n - 1; i += gridDim.x * BLOCK) {
-        const uint32_t ci = __ldg(codes + i);
-        const int d = (delta(codes, n, i, ci, i + 1) - delta(codes, n, i, ci, i - 1)) >= 0 ? 1 : -1;
-        const int dmin = delta(codes, n, i, ci, i - d);
+    for (int i0 = blockIdx.x * BLOCK; i0 < n - 1; i0 += gridDim.x * BLOCK) {
+        const int base = i0 - KHALO;
+        __syncthreads();
+        for (int r = threadIdx.x; r < KWIN; r += BLOCK) {
+            const int j = base + r;
+            s_win[r] = (j >= 0 && j < n) ? __ldg(codes + j) : 0u;
+        }
+        __syncthreads();
+        const int i = i0 + (int)threadIdx.x;
+        if (i >= n - 1) continue;
+        const code_window cw { codes, s_win, base, n };
+        const uint32_t ci = cw.get(i);
+        const int d = (cw.delta(i, ci, i + 1) - cw.delta(i, ci, i - 1)) >= 0 ? 1 : -1;
+        const int dmin = cw.delta(i, ci, i - d);
         int lmax = 2;
-        while (delta(codes, n, i, ci, i + lmax * d) > dmin) lmax <<= 1;
+        while (cw.delta(i, ci, i + lmax * d) > dmin) lmax <<= 1;
         int l = 0;
         for (int t = lmax >> 1; t >= 1; t >>= 1)
-            if (delta(codes, n, i, ci, i + (l + t) * d) > dmin) l += t;
+            if (cw.delta(i, ci, i + (l + t) * d) > dmin) l += t;
         const int j = i + l * d;
-        const int dnode = delta(codes, n, i, ci, j);
+        const int dnode = cw.delta(i, ci, j);
         int s = 0;
         int t = l;
         do {
             t = (t + 1) >> 1;
-            if (delta(codes, n, i, ci, i + (s + t) * d) > dnode) s += t;
+            if (cw.delta(i, ci, i + (s + t) * d) > dnode) s += t;
         } while (t > 1);
         const int gamma = i + s * d + (d < 0 ? -1 : 0);
         const int lo = i < j ? i : j, hi = i < j ? j : i;
         const uint32_t left = (lo == gamma) ? (MCB_LEAF_BIT | (uint32_t)gamma) : (uint32_t)gamma;
         const uint32_t right = (hi == gamma + 1) ? (MCB_LEAF_BIT | (uint32_t)(gamma + 1)) : (uint32_t)(gamma + 1);
-        bvh_node_t* nd = nodes + i;
-        nd->left = left;
-        nd->right = right;
-        nd->first = (uint32_t)lo;
-        nd->last = (uint32_t)hi;
+        const uint4 m = make_uint4(left, right, (uint32_t)lo, (uint32_t)hi);
+        *reinterpret_cast<uint4*>(&nodes[i].left) = m; // inside the 128-byte record the traversal reads
+        meta[i] = m; // compact copy the refit reads coalesced
         parent[(left & MCB_LEAF_BIT) ? (nf - 1 + (left & ~MCB_LEAF_BIT)) : left] = (uint32_t)i;
         parent[(right & MCB_LEAF_BIT) ? (nf - 1 + (right & ~MCB_LEAF_BIT)) : right] = (uint32_t)i;
         if (i == 0) parent[0] = MCB200_NULL;
@@ -202,15 +227,49 @@ __device__ __forceinline__ void load_box_cg(const double* src, double* b)
     b[5] = e.y;
 }
 
-__global__ void __launch_bounds__(BLOCK) k_refit(const double* __restrict__ face_bbox, const uint32_t* __restrict__ sorted_faces,
-    uint32_t nf, bvh_node_t* nodes, const uint32_t* __restrict__ parent, unsigned* flags)
+__device__ __forceinline__ void load_face_box(const double* __restrict__ face_bbox, uint32_t face, double* b)
 {
+    const double2* in = reinterpret_cast<const double2*>(face_bbox + 6 * (size_t)face);
+    const double2 a = __ldg(in), c = __ldg(in + 1), e = __ldg(in + 2);
+    b[0] = a.x;
+    b[1] = a.y;
+    b[2] = c.x;
+    b[3] = c.y;
+    b[4] = e.x;
+    b[5] = e.y;
+}
+
+__device__ __forceinline__ void append_group(uint2* groups, unsigned* n_groups, uint32_t first, uint32_t count)
+{
+    const unsigned m = __activemask();
+    const int leader = __ffs(m) - 1;
+    unsigned base = 0;
+    if ((int)lane_id() == leader) base = atomicAdd(n_groups, (unsigned)__popc(m));
+    base = __shfl_sync(m, base, leader);
+    groups[base + __popc(m & lanemask_lt())] = make_uint2(first, count);
+}
+
+// Refit in two regimes, one kernel:
+//  * TREELETS: a node whose leaf range has at most 32 leaves gets both child boxes straight from the leaf boxes of its
+//    range (a Karras node knows its range and its split, so no other node's result is needed): no atomics, no fences.
+//    A block owns 256 consecutive node indices; since node i lies inside its own range, every such range falls inside
+//    the block's leaf window [i0-32, i0+288), which is gathered ONCE into shared memory with all loads in flight at once.
+//  * ABOVE THE TREELETS: the maximal treelets ("group roots", which are also the traversal's query groups) carry their
+//    box upwards with the classic arrival-counter scheme: the first thread to reach a node parks its box in the node and
+//    leaves, the second one merges and continues.  Only ~nf/16 nodes are refit this way.
+constexpr int RHALO = 32;
+constexpr int RWIN = BLOCK + 2 * RHALO;
+
+__global__ void __launch_bounds__(BLOCK) k_refit(const double* __restrict__ face_bbox, const uint32_t* __restrict__ sorted_faces,
+    uint32_t nf, bvh_node_t* nodes, const uint4* __restrict__ meta, const uint32_t* __restrict__ parent, unsigned* flags,
+    uint2* __restrict__ groups, unsigned* __restrict__ n_groups)
+{
+    __shared__ double s_box[RWIN][6];
     if (nf == 1) {
         // a single leaf (e.g. the planar-section triangle): pseudo-root whose right child can never be hit
         if (blockIdx.x == 0 && threadIdx.x == 0) {
             double b[6];
-            const double* src = face_bbox + 6 * (size_t)sorted_faces[0];
-            for (int k = 0; k < 6; ++k) b[k] = src[k];
+            load_face_box(face_bbox, sorted_faces[0], b);
             store_box(nodes[0].lbox, b);
             const double e[6] = { DBL_MAX, DBL_MAX, DBL_MAX, -DBL_MAX, -DBL_MAX, -DBL_MAX };
             store_box(nodes[0].rbox, e);
@@ -218,40 +277,98 @@ __global__ void __launch_bounds__(BLOCK) k_refit(const double* __restrict__ face
             nodes[0].right = MCB200_NULL;
             nodes[0].first = 0;
             nodes[0].last = 0;
+            groups[0] = make_uint2(0u, 1u);
+            *n_groups = 1u;
         }
         return;
     }
-    for (uint32_t j = blockIdx.x * BLOCK + threadIdx.x; j < nf; j += gridDim.x * BLOCK) {
-        double box[6];
-        {
-            const double2* in = reinterpret_cast<const double2*>(face_bbox + 6 * (size_t)__ldg(sorted_faces + j));
-            const double2 a = in[0], b = in[1], c = in[2];
-            box[0] = a.x;
-            box[1] = a.y;
-            box[2] = b.x;
-            box[3] = b.y;
-            box[4] = c.x;
-            box[5] = c.y;
-        }
-        uint32_t child = MCB_LEAF_BIT | j;
-        uint32_t p = __ldg(parent + (nf - 1 + j));
-        for (;;) {
-            bvh_node_t* nd = nodes + p;
-            const bool is_left = (nd->left == child);
-            store_box(is_left ? nd->lbox : nd->rbox, box);
-            __threadfence();
-            const unsigned arrived = atomicAdd(flags + p, 1u);
-            if (arrived == 0) break; // sibling subtree not finished yet; its thread will continue from here
-            double sib[6];
-            load_box_cg(is_left ? nd->rbox : nd->lbox, sib);
+    for (uint32_t i0 = blockIdx.x * BLOCK; i0 < nf; i0 += gridDim.x * BLOCK) {
+        __syncthreads();
+        for (int r = threadIdx.x; r < RWIN; r += BLOCK) {
+            const long long j = (long long)i0 - RHALO + r;
+            if (j >= 0 && j < (long long)nf) {
+                double b[6];
+                load_face_box(face_bbox, __ldg(sorted_faces + j), b);
 #pragma unroll
-            for (int k = 0; k < 3; ++k) {
-                box[k] = ref_min(box[k], sib[k]);
-                box[3 + k] = ref_max(box[3 + k], sib[3 + k]);
+                for (int k = 0; k < 6; ++k) s_box[r][k] = b[k];
             }
-            if (p == 0) break; // root merged; the mesh AABB itself comes from K_aabb's reduction
-            child = p;
-            p = __ldg(parent + p);
+        }
+        __syncthreads();
+        const uint32_t i = i0 + threadIdx.x;
+        const int wbase = (int)i0 - RHALO; // leaf j sits in s_box[j - wbase]
+        // two roles per thread: internal node i (if any) and leaf i (if any)
+#pragma unroll 1
+        for (int role = 0; role < 2; ++role) {
+            double box[6];
+            uint32_t child, p;
+            if (role == 0) {
+                if (i >= nf - 1u) continue;
+                const uint4 m = __ldg(meta + i);
+                const uint32_t first = m.z, last = m.w, count = last - first + 1u;
+                if (count > 32u) continue;
+                const uint32_t gamma = m.x & ~MCB_LEAF_BIT;
+                double rb[6];
+#pragma unroll
+                for (int k = 0; k < 6; ++k) {
+                    box[k] = s_box[(int)first - wbase][k];
+                    rb[k] = s_box[(int)gamma + 1 - wbase][k];
+                }
+                for (uint32_t j = first + 1u; j <= gamma; ++j)
+#pragma unroll
+                    for (int k = 0; k < 3; ++k) {
+                        box[k] = ref_min(box[k], s_box[(int)j - wbase][k]);
+                        box[3 + k] = ref_max(box[3 + k], s_box[(int)j - wbase][3 + k]);
+                    }
+                for (uint32_t j = gamma + 2u; j <= last; ++j)
+#pragma unroll
+                    for (int k = 0; k < 3; ++k) {
+                        rb[k] = ref_min(rb[k], s_box[(int)j - wbase][k]);
+                        rb[3 + k] = ref_max(rb[3 + k], s_box[(int)j - wbase][3 + k]);
+                    }
+                store_box(nodes[i].lbox, box);
+                store_box(nodes[i].rbox, rb);
+                if (i == 0u) { // the whole tree is one treelet
+                    append_group(groups, n_groups, first, count);
+                    continue;
+                }
+                p = __ldg(parent + i);
+                const uint4 pm = __ldg(meta + p);
+                if (pm.w - pm.z + 1u <= 32u) continue; // inside a bigger treelet
+                append_group(groups, n_groups, first, count);
+#pragma unroll
+                for (int k = 0; k < 3; ++k) {
+                    box[k] = ref_min(box[k], rb[k]);
+                    box[3 + k] = ref_max(box[3 + k], rb[3 + k]);
+                }
+                child = i;
+            } else {
+                if (i >= nf) continue;
+                p = __ldg(parent + (nf - 1u + i));
+                const uint4 pm = __ldg(meta + p);
+                if (pm.w - pm.z + 1u <= 32u) continue; // its parent's thread covers it
+                append_group(groups, n_groups, i, 1u);
+#pragma unroll
+                for (int k = 0; k < 6; ++k) box[k] = s_box[(int)i - wbase][k];
+                child = MCB_LEAF_BIT | i;
+            }
+            for (;;) {
+                bvh_node_t* nd = nodes + p;
+                const bool is_left = (__ldg(&meta[p].x) == child);
+                store_box(is_left ? nd->lbox : nd->rbox, box);
+                __threadfence();
+                const unsigned arrived = atomicAdd(flags + p, 1u);
+                if (arrived == 0) break; // sibling subtree not finished yet; its thread will continue from here
+                double sib[6];
+                load_box_cg(is_left ? nd->rbox : nd->lbox, sib);
+#pragma unroll
+                for (int k = 0; k < 3; ++k) {
+                    box[k] = ref_min(box[k], sib[k]);
+                    box[3 + k] = ref_max(box[3 + k], sib[3 + k]);
+                }
+                if (p == 0) break; // root merged; the mesh AABB itself comes from K_aabb's reduction
+                child = p;
+                p = __ldg(parent + p);
+            }
         }
     }
 }
@@ -272,7 +389,9 @@ int lbvh_build(mcb200_ctx* ctx, mcb200_mesh* m, double eps)
     MCB_TRY(ctx->reserve(m->sorted_faces, sizeof(uint32_t) * (size_t)nf));
     MCB_TRY(ctx->reserve(m->nodes, sizeof(bvh_node_t) * (size_t)(nf > 1 ? nf - 1 : 1)));
     MCB_TRY(ctx->reserve(m->parent, sizeof(uint32_t) * (2 * (size_t)nf)));
+    MCB_TRY(ctx->reserve(m->meta, sizeof(uint4) * (size_t)nf));
     MCB_TRY(ctx->reserve(m->flags, sizeof(unsigned) * (size_t)nf));
+    MCB_TRY(ctx->reserve(m->groups, sizeof(uint2) * (size_t)nf + sizeof(unsigned) * 4));
     MCB_TRY(ctx->reserve(ctx->sort_keys_alt, sizeof(uint32_t) * (size_t)nf));
     MCB_TRY(ctx->reserve(ctx->sort_vals_alt, sizeof(uint32_t) * (size_t)nf));
 
@@ -281,6 +400,8 @@ int lbvh_build(mcb200_ctx* ctx, mcb200_mesh* m, double eps)
     MCB_CUDA(ctx, cudaMemsetAsync(root_ord, 0xFF, sizeof(unsigned long long) * 3, ctx->stream));
     MCB_CUDA(ctx, cudaMemsetAsync(root_ord + 3, 0x00, sizeof(unsigned long long) * 3, ctx->stream));
     MCB_CUDA(ctx, cudaMemsetAsync(m->flags.p, 0, sizeof(unsigned) * (size_t)nf, ctx->stream));
+    unsigned* n_groups = reinterpret_cast<unsigned*>(m->groups.as<uint2>() + nf);
+    MCB_CUDA(ctx, cudaMemsetAsync(n_groups, 0, sizeof(unsigned) * 4, ctx->stream));
 
     const unsigned max_grid = (unsigned)ctx->num_sms * 8u;
     const unsigned grid = div_up(nf, BLOCK) < max_grid ? div_up(nf, BLOCK) : max_grid;
@@ -302,14 +423,15 @@ int lbvh_build(mcb200_ctx* ctx, mcb200_mesh* m, double eps)
         return MCB200_ERR_INTERNAL;
     }
     if (nf > 1) {
-        const unsigned g2 = div_up(nf - 1, BLOCK) < max_grid ? div_up(nf - 1, BLOCK) : max_grid;
-        MCB_LAUNCH(ctx, k_karras, g2, BLOCK, 0, m->sorted_codes.as<uint32_t>(), nf, m->nodes.as<bvh_node_t>(),
+        const unsigned g2 = div_up(nf - 1, BLOCK); // one 256-node window per block
+        MCB_LAUNCH(ctx, k_karras, g2, BLOCK, 0, m->sorted_codes.as<uint32_t>(), nf, m->nodes.as<bvh_node_t>(), m->meta.as<uint4>(),
             m->parent.as<uint32_t>());
     }
-    MCB_LAUNCH(ctx, k_refit, grid, BLOCK, 0, m->face_bbox.as<double>(), m->sorted_faces.as<uint32_t>(), nf,
-        m->nodes.as<bvh_node_t>(), m->parent.as<uint32_t>(), m->flags.as<unsigned>());
+    MCB_LAUNCH(ctx, k_refit, div_up(nf, BLOCK), BLOCK, 0, m->face_bbox.as<double>(), m->sorted_faces.as<uint32_t>(), nf,
+        m->nodes.as<bvh_node_t>(), m->meta.as<uint4>(), m->parent.as<uint32_t>(), m->flags.as<unsigned>(), m->groups.as<uint2>(),
+        n_groups);
     m->built = true;
-    m->groups_valid = false;
+    m->groups_valid = true;
     m->eps = eps;
     return 0;
 }

@@ -5,7 +5,7 @@
 // closed intervals (math.h:931-941) whatever the trees look like, so the device walks its own LBVHs:
 //
 //   * the mesh with more faces is the QUERY side; its leaves are grouped by the query mesh's OWN tree: a group is a
-//     maximal subtree with at most 32 leaves (k_groups).  Such treelets are spatially compact — cutting the Morton
+//     maximal subtree with at most 32 leaves (listed by lbvh.cu's k_refit).  Such treelets are spatially compact — cutting the Morton
 //     order into fixed runs of 32 is not: a run that straddles an octant boundary has a union box spanning the mesh;
 //   * one warp owns a group: lane l keeps leaf l's box in registers, the warp keeps the group's union box;
 //   * the warp walks the other mesh's tree with a stack in shared memory, up to 32 nodes per step — one node per
@@ -93,39 +93,6 @@ __device__ __forceinline__ void drain_candidates(warp_scratch_t& ws, unsigned fi
         }
     }
     ntests += count;
-}
-
-// ---- query groups = maximal subtrees of the query mesh's LBVH with <= 32 leaves --------------------------------------
-__global__ void __launch_bounds__(256) k_groups(const bvh_node_t* __restrict__ nodes, const uint32_t* __restrict__ parent,
-    uint32_t nf, uint2* __restrict__ groups, unsigned* __restrict__ n_groups)
-{
-    // items [0, nf-1): internal nodes; items [nf-1, 2nf-1): leaves
-    const uint32_t total = 2u * nf - 1u;
-    for (uint32_t it = blockIdx.x * 256u + threadIdx.x; it < total; it += gridDim.x * 256u) {
-        uint32_t first, count;
-        if (it < nf - 1u) {
-            first = nodes[it].first;
-            count = nodes[it].last - first + 1u;
-        } else {
-            first = it - (nf - 1u);
-            count = 1u;
-        }
-        if (count > 32u) continue;
-        bool is_group_root = true;
-        const bool is_tree_root = (nf == 1u) || (it == 0u);
-        if (!is_tree_root) {
-            const uint32_t p = __ldg(parent + it);
-            const uint32_t pc = nodes[p].last - nodes[p].first + 1u;
-            is_group_root = pc > 32u;
-        }
-        if (!is_group_root) continue;
-        const unsigned m = __activemask();
-        const int leader = __ffs(m) - 1;
-        unsigned base = 0;
-        if ((int)lane_id() == leader) base = atomicAdd(n_groups, (unsigned)__popc(m));
-        base = __shfl_sync(m, base, leader);
-        groups[base + __popc(m & lanemask_lt())] = make_uint2(first, count);
-    }
 }
 
 __global__ void __launch_bounds__(TBLOCK) k_traverse(traverse_args_t a)
@@ -309,17 +276,7 @@ int traverse_pairs(mcb200_ctx* ctx, const mcb200_mesh* src, const mcb200_mesh* c
     a.cap_pairs = res->cap_pairs;
     a.counters = res->counters.as<result_counters_t>();
 
-    // query groups from the query mesh's own tree (cached on the mesh: they only depend on its build)
-    mcb200_mesh* qm = const_cast<mcb200_mesh*>(q);
-    if (!qm->groups_valid) {
-        MCB_TRY(ctx->reserve(qm->groups, sizeof(uint2) * (size_t)q->nf + sizeof(unsigned) * 4));
-        unsigned* ng = reinterpret_cast<unsigned*>(qm->groups.as<uint2>() + q->nf);
-        MCB_CUDA(ctx, cudaMemsetAsync(ng, 0, sizeof(unsigned) * 4, ctx->stream));
-        const unsigned gg = div_up(2u * (size_t)q->nf, 256) < (unsigned)ctx->num_sms * 8u ? div_up(2u * (size_t)q->nf, 256)
-                                                                                         : (unsigned)ctx->num_sms * 8u;
-        MCB_LAUNCH(ctx, k_groups, gg, 256, 0, q->nodes.as<bvh_node_t>(), q->parent.as<uint32_t>(), q->nf, qm->groups.as<uint2>(), ng);
-        qm->groups_valid = true;
-    }
+    // query groups = the maximal <=32-leaf treelets of the query mesh's own tree, listed by its refit kernel
     a.groups = q->groups.as<uint2>();
     a.n_groups = reinterpret_cast<const unsigned*>(q->groups.as<uint2>() + q->nf);
     a.t_root = reinterpret_cast<const double*>(t->root.as<unsigned long long>() + 6);
