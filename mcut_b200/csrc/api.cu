@@ -92,6 +92,16 @@ int mcb200_ctx_create(int device, void* stream, mcb200_ctx** out)
         }
         ctx->owns_stream = true;
     }
+    if ((e = cudaStreamCreateWithFlags(&ctx->aux, cudaStreamNonBlocking)) != cudaSuccess) {
+        g_create_error = std::string("cudaStreamCreate(aux): ") + cudaGetErrorString(e);
+        delete ctx;
+        return (int)e;
+    }
+    cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&ctx->ev_fork2, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&ctx->ev_join2, cudaEventDisableTiming);
+    ctx->use_main();
     // keep freed blocks in the pool: repeated dispatches reuse them without going back to the driver
     cudaMemPool_t pool;
     if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
@@ -107,12 +117,20 @@ void mcb200_ctx_destroy(mcb200_ctx* ctx)
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
-    ctx->release(ctx->sort_keys_alt);
-    ctx->release(ctx->sort_vals_alt);
-    ctx->release(ctx->sort_hist);
-    ctx->release(ctx->sort_status);
-    ctx->release(ctx->sort_tilectr);
+    cudaStreamSynchronize(ctx->aux);
+    for (auto& sc : ctx->scratch) {
+        ctx->release(sc.keys_alt);
+        ctx->release(sc.vals_alt);
+        ctx->release(sc.hist);
+        ctx->release(sc.status);
+        ctx->release(sc.tilectr);
+    }
     cudaStreamSynchronize(ctx->stream);
+    cudaStreamDestroy(ctx->aux);
+    cudaEventDestroy(ctx->ev_fork);
+    cudaEventDestroy(ctx->ev_join);
+    cudaEventDestroy(ctx->ev_fork2);
+    cudaEventDestroy(ctx->ev_join2);
     if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
     for (auto& r : ctx->prof) {
         cudaEventDestroy(r.a);
@@ -328,6 +346,7 @@ int mcb200_bvh_build(mcb200_ctx* ctx, mcb200_mesh* m, double eps)
 {
     if (!ctx || !m) return MCB200_ERR_INVALID;
     MCB_CUDA(ctx, cudaSetDevice(ctx->device));
+    ctx->use_main();
     return lbvh_build(ctx, m, eps);
 }
 
@@ -370,7 +389,7 @@ void mcb200_result_free(mcb200_ctx* ctx, mcb200_result* r)
 {
     if (!ctx || !r) return;
     cudaSetDevice(ctx->device);
-    dbuf* all[] = { &r->counters, &r->pairs, &r->cand_flag, &r->plane, &r->plane_mc, &r->exact_queue, &r->records, &r->rec_keys,
+    dbuf* all[] = { &r->counters, &r->pairs, &r->pairs_a, &r->pairs_b, &r->cand_flag, &r->plane, &r->plane_mc, &r->exact_queue, &r->records, &r->rec_keys,
         &r->rec_idx, &r->records_sorted, &r->tests, &r->tests_sorted, &r->test_keys, &r->test_idx };
     for (dbuf* b : all) ctx->release(*b);
     delete r;
@@ -393,16 +412,16 @@ int mcb200_bvh_intersect(mcb200_ctx* ctx, const mcb200_mesh* src, const mcb200_m
 {
     if (!ctx || !src || !cut || !res) return MCB200_ERR_INVALID;
     MCB_CUDA(ctx, cudaSetDevice(ctx->device));
+    ctx->use_main();
     for (int attempt = 0; attempt < 2; ++attempt) {
         MCB_TRY(traverse_pairs(ctx, src, cut, res));
+        MCB_TRY(sort_pairs(ctx, src, cut, res));
         if (attempt == 1) break;
         // The only host round trip of the stage: did the pair buffer hold everything?  (One 128-byte read; skipped by
         // mcb200_intersect_stage, which checks after the fact.)
         MCB_TRY(fetch_counters(ctx, res));
         if (!res->h.pair_overflow) break;
-        const size_t want = (size_t)res->h.n_pairs + (size_t)res->h.n_pairs / 8 + 1024;
-        MCB_TRY(ctx->reserve(res->pairs, sizeof(unsigned long long) * want));
-        res->cap_pairs = want;
+        res->cap_pairs = (size_t)res->h.n_pairs + (size_t)res->h.n_pairs / 8 + 1024;
     }
     return 0;
 }
@@ -480,6 +499,7 @@ int mcb200_narrowphase(mcb200_ctx* ctx, const mcb200_soup* soup, const mcb200_me
     if (!ctx || !soup || !src || !cut || !res) return MCB200_ERR_INVALID;
     MCB_CUDA(ctx, cudaSetDevice(ctx->device));
     if (!soup->all_tri && !soup->face_off.p) MCB_FAIL(ctx, MCB200_ERR_INVALID, "narrowphase: polygon soup without face offsets");
+    ctx->use_main();
     return narrowphase_run(ctx, soup, src, cut, res, flags);
 }
 
@@ -495,13 +515,41 @@ int mcb200_intersect_stage(mcb200_ctx* ctx, mcb200_mesh* src, mcb200_mesh* cut, 
         cut->frame.has_pert = 0;
         for (int j = 0; j < 3; ++j) cut->frame.pert[j] = 0.0;
     }
-    int rc = lbvh_build(ctx, src, 0.0);
+    // ---- every allocation first, on the main lane (so the aux lane only ever sees memory that already exists) ----
+    ctx->use_main();
+    int rc = lbvh_reserve(ctx, src);
+    if (!rc) rc = traverse_reserve(ctx, src, cut, res);
+    if (!rc) rc = narrowphase_reserve(ctx, soup, res, flags);
+    ctx->use_aux();
+    if (!rc) rc = lbvh_reserve(ctx, cut);
+    if (!rc) rc = sort_pairs_reserve(ctx, src, cut, res);
+    ctx->use_main();
+    if (rc) {
+        cut->frame = cut_frame;
+        return rc;
+    }
+    // ---- the two LBVH builds side by side ----
+    MCB_CUDA(ctx, cudaEventRecord(ctx->ev_fork, ctx->stream));
+    MCB_CUDA(ctx, cudaStreamWaitEvent(ctx->aux, ctx->ev_fork, 0));
+    rc = lbvh_build(ctx, src, 0.0);
+    ctx->use_aux();
     if (!rc) rc = lbvh_build(ctx, cut, cut_eps);
+    cudaEventRecord(ctx->ev_join, ctx->aux);
+    ctx->use_main();
+    cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0);
     cut->frame = cut_frame;
     if (rc) return rc;
+    // ---- traversal, then the pair sort (aux lane) next to the narrowphase (main lane, reads the unsorted pairs) ----
     MCB_TRY(traverse_pairs(ctx, src, cut, res));
-    MCB_TRY(narrowphase_run(ctx, soup, src, cut, res, flags));
-    return 0;
+    MCB_CUDA(ctx, cudaEventRecord(ctx->ev_fork2, ctx->stream));
+    MCB_CUDA(ctx, cudaStreamWaitEvent(ctx->aux, ctx->ev_fork2, 0));
+    ctx->use_aux();
+    rc = sort_pairs(ctx, src, cut, res);
+    cudaEventRecord(ctx->ev_join2, ctx->aux);
+    ctx->use_main();
+    if (!rc) rc = narrowphase_run(ctx, soup, src, cut, res, flags);
+    cudaStreamWaitEvent(ctx->stream, ctx->ev_join2, 0);
+    return rc;
 }
 
 // ---------------------------------------------------------------------------------------------------------- reads
@@ -537,7 +585,8 @@ int mcb200_result_read_pairs(mcb200_ctx* ctx, mcb200_result* res, uint64_t* pair
     const size_t n = (size_t)res->h.n_pairs;
     if (n > res->cap_pairs) MCB_FAIL(ctx, MCB200_ERR_CAPACITY, "pair buffer overflowed on the device");
     if (n > capacity || (n && !pairs)) MCB_FAIL(ctx, MCB200_ERR_CAPACITY, "read_pairs: output array too small");
-    if (n) MCB_CUDA(ctx, cudaMemcpyAsync(pairs, res->pairs.p, sizeof(uint64_t) * n, cudaMemcpyDeviceToHost, ctx->stream));
+    if (n && !res->pairs_sorted) MCB_FAIL(ctx, MCB200_ERR_INTERNAL, "read_pairs: pairs were not sorted");
+    if (n) MCB_CUDA(ctx, cudaMemcpyAsync(pairs, res->pairs_sorted, sizeof(uint64_t) * n, cudaMemcpyDeviceToHost, ctx->stream));
     MCB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return 0;
 }
@@ -608,7 +657,7 @@ int mcb200_result_device_ptr(mcb200_ctx* ctx, mcb200_result* res, int which, voi
     if (!ctx || !res || !dptr || !count) return MCB200_ERR_INVALID;
     MCB_TRY(fetch_counters(ctx, res));
     if (which == 0) {
-        *dptr = res->pairs.p;
+        *dptr = res->pairs_sorted;
         *count = res->h.n_pairs;
     } else if (which == 1) {
         if (!res->have_narrow) MCB_FAIL(ctx, MCB200_ERR_INVALID, "device_ptr: narrowphase has not run");

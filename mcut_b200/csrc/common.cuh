@@ -69,8 +69,19 @@ struct mcb200_ctx {
     // pinned staging for small D2H reads (counters)
     void* h_pinned = nullptr;
     size_t h_pinned_cap = 0;
-    // scratch shared by all stages of this context (sort double-buffers, histograms, tile status)
-    dbuf sort_keys_alt, sort_vals_alt, sort_hist, sort_status, sort_tilectr;
+    // Two lanes of execution: `stream` (main) and `aux`.  Independent pieces of one intersect stage — the two meshes'
+    // LBVH builds, the pair sort next to the narrowphase — run side by side; `cur` is where launches currently go and
+    // `sci` selects the sort scratch set that belongs to that lane.
+    cudaStream_t aux = nullptr;
+    cudaStream_t cur = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_fork2 = nullptr, ev_join2 = nullptr;
+    int sci = 0;
+    struct sort_scratch_t {
+        dbuf keys_alt, vals_alt, hist, status, tilectr;
+    } scratch[2];
+    sort_scratch_t& sc() { return scratch[sci]; }
+    void use_main() { cur = stream; sci = 0; }
+    void use_aux() { cur = aux; sci = 1; }
 
     void set_error(const std::string& msg, const char* file, int line)
     {
@@ -199,7 +210,9 @@ struct result_counters_t {
 
 struct mcb200_result {
     dbuf counters; // result_counters_t
-    dbuf pairs; // u64 [cap_pairs]
+    dbuf pairs; // u64 [cap_pairs], in the order the traversal emitted them (what the narrowphase consumes)
+    dbuf pairs_a, pairs_b; // ping-pong buffers of the pair sort
+    unsigned long long* pairs_sorted = nullptr; // ascending (src << 32 | cut): points into pairs_a or pairs_b
     size_t cap_pairs = 0;
     dbuf cand_flag; // u8 [nf_ps]
     dbuf plane; // per ps face: normal[3], d  (4 doubles) ; maxcomp in separate int array
@@ -292,23 +305,25 @@ __device__ __forceinline__ void load_vertex(const void* __restrict__ xyz, const 
 static inline unsigned div_up(size_t a, size_t b) { return (unsigned)((a + b - 1) / b); }
 
 // launch accounting: every kernel launch of the product goes through this macro
-#define MCB_LAUNCH(ctx, kernel, grid, block, smem, ...)                          \
+#define MCB_LAUNCH(ctx, kernel, grid, block, smem, ...) MCB_LAUNCH_NAMED(ctx, #kernel, kernel, grid, block, smem, __VA_ARGS__)
+
+#define MCB_LAUNCH_NAMED(ctx, name, kernel, grid, block, smem, ...)              \
     do {                                                                         \
-        mcb200_ctx::prof_rec pr__ { #kernel, nullptr, nullptr };                 \
+        mcb200_ctx::prof_rec pr__ { name, nullptr, nullptr };                    \
         if ((ctx)->profiling) {                                                  \
             pr__.a = (ctx)->prof_event();                                        \
             pr__.b = (ctx)->prof_event();                                        \
-            cudaEventRecord(pr__.a, (ctx)->stream);                              \
+            cudaEventRecord(pr__.a, (ctx)->cur);                              \
         }                                                                        \
-        kernel<<<(grid), (block), (smem), (ctx)->stream>>>(__VA_ARGS__);         \
+        kernel<<<(grid), (block), (smem), (ctx)->cur>>>(__VA_ARGS__);         \
         if ((ctx)->profiling) {                                                  \
-            cudaEventRecord(pr__.b, (ctx)->stream);                              \
+            cudaEventRecord(pr__.b, (ctx)->cur);                              \
             (ctx)->prof.push_back(pr__);                                         \
         }                                                                        \
         (ctx)->launches++;                                                       \
         cudaError_t le__ = cudaPeekAtLastError();                                \
         if (le__ != cudaSuccess) {                                               \
-            (ctx)->set_error(std::string(#kernel) + " launch: " + cudaGetErrorString(le__), __FILE__, __LINE__); \
+            (ctx)->set_error(std::string(name) + " launch: " + cudaGetErrorString(le__), __FILE__, __LINE__); \
             return (int)le__;                                                    \
         }                                                                        \
     } while (0)

@@ -198,8 +198,11 @@ __global__ void __launch_bounds__(BLOCK) k_karras(const uint32_t* __restrict__ c
         const uint4 m = make_uint4(left, right, (uint32_t)lo, (uint32_t)hi);
         *reinterpret_cast<uint4*>(&nodes[i].left) = m; // inside the 128-byte record the traversal reads
         meta[i] = m; // compact copy the refit reads coalesced
-        parent[(left & MCB_LEAF_BIT) ? (nf - 1 + (left & ~MCB_LEAF_BIT)) : left] = (uint32_t)i;
-        parent[(right & MCB_LEAF_BIT) ? (nf - 1 + (right & ~MCB_LEAF_BIT)) : right] = (uint32_t)i;
+        // parent word of a child: (parent index << 2) | (parent covers more than 32 leaves) << 1 | (child is the right one)
+        // — everything the refit needs to know about the parent without touching the parent's record
+        const uint32_t pw = ((uint32_t)i << 2) | ((hi - lo + 1 > 32) ? 2u : 0u);
+        parent[(left & MCB_LEAF_BIT) ? (nf - 1 + (left & ~MCB_LEAF_BIT)) : left] = pw;
+        parent[(right & MCB_LEAF_BIT) ? (nf - 1 + (right & ~MCB_LEAF_BIT)) : right] = pw | 1u;
         if (i == 0) parent[0] = MCB200_NULL;
     }
 }
@@ -300,7 +303,7 @@ __global__ void __launch_bounds__(BLOCK) k_refit(const double* __restrict__ face
 #pragma unroll 1
         for (int role = 0; role < 2; ++role) {
             double box[6];
-            uint32_t child, p;
+            uint32_t pw;
             if (role == 0) {
                 if (i >= nf - 1u) continue;
                 const uint4 m = __ldg(meta + i);
@@ -331,29 +334,26 @@ __global__ void __launch_bounds__(BLOCK) k_refit(const double* __restrict__ face
                     append_group(groups, n_groups, first, count);
                     continue;
                 }
-                p = __ldg(parent + i);
-                const uint4 pm = __ldg(meta + p);
-                if (pm.w - pm.z + 1u <= 32u) continue; // inside a bigger treelet
+                pw = __ldg(parent + i);
+                if (!(pw & 2u)) continue; // inside a bigger treelet
                 append_group(groups, n_groups, first, count);
 #pragma unroll
                 for (int k = 0; k < 3; ++k) {
                     box[k] = ref_min(box[k], rb[k]);
                     box[3 + k] = ref_max(box[3 + k], rb[3 + k]);
                 }
-                child = i;
             } else {
                 if (i >= nf) continue;
-                p = __ldg(parent + (nf - 1u + i));
-                const uint4 pm = __ldg(meta + p);
-                if (pm.w - pm.z + 1u <= 32u) continue; // its parent's thread covers it
+                pw = __ldg(parent + (nf - 1u + i));
+                if (!(pw & 2u)) continue; // its parent's thread covers it
                 append_group(groups, n_groups, i, 1u);
 #pragma unroll
                 for (int k = 0; k < 6; ++k) box[k] = s_box[(int)i - wbase][k];
-                child = MCB_LEAF_BIT | i;
             }
             for (;;) {
+                const uint32_t p = pw >> 2;
                 bvh_node_t* nd = nodes + p;
-                const bool is_left = (__ldg(&meta[p].x) == child);
+                const bool is_left = !(pw & 1u);
                 store_box(is_left ? nd->lbox : nd->rbox, box);
                 __threadfence();
                 const unsigned arrived = atomicAdd(flags + p, 1u);
@@ -366,8 +366,7 @@ __global__ void __launch_bounds__(BLOCK) k_refit(const double* __restrict__ face
                     box[3 + k] = ref_max(box[3 + k], sib[3 + k]);
                 }
                 if (p == 0) break; // root merged; the mesh AABB itself comes from K_aabb's reduction
-                child = p;
-                p = __ldg(parent + p);
+                pw = __ldg(parent + p);
             }
         }
     }
@@ -375,7 +374,7 @@ __global__ void __launch_bounds__(BLOCK) k_refit(const double* __restrict__ face
 
 } // namespace
 
-int lbvh_build(mcb200_ctx* ctx, mcb200_mesh* m, double eps)
+int lbvh_reserve(mcb200_ctx* ctx, mcb200_mesh* m)
 {
     if (m->nf == 0) {
         ctx->set_error("bvh_build: mesh has no faces", __FILE__, __LINE__);
@@ -392,16 +391,24 @@ int lbvh_build(mcb200_ctx* ctx, mcb200_mesh* m, double eps)
     MCB_TRY(ctx->reserve(m->meta, sizeof(uint4) * (size_t)nf));
     MCB_TRY(ctx->reserve(m->flags, sizeof(unsigned) * (size_t)nf));
     MCB_TRY(ctx->reserve(m->groups, sizeof(uint2) * (size_t)nf + sizeof(unsigned) * 4));
-    MCB_TRY(ctx->reserve(ctx->sort_keys_alt, sizeof(uint32_t) * (size_t)nf));
-    MCB_TRY(ctx->reserve(ctx->sort_vals_alt, sizeof(uint32_t) * (size_t)nf));
+    MCB_TRY((rsort::reserve_scratch<uint32_t>(ctx, nf, 4, true, true)));
+    return 0;
+}
+
+// Everything is enqueued on ctx->cur (the caller picks the lane); all allocations happen in lbvh_reserve.
+int lbvh_build(mcb200_ctx* ctx, mcb200_mesh* m, double eps)
+{
+    MCB_TRY(lbvh_reserve(ctx, m));
+    const uint32_t nf = m->nf;
+    mcb200_ctx::sort_scratch_t& sc = ctx->sc();
 
     unsigned long long* root_ord = m->root.as<unsigned long long>();
     double* root_dec = reinterpret_cast<double*>(root_ord + 6);
-    MCB_CUDA(ctx, cudaMemsetAsync(root_ord, 0xFF, sizeof(unsigned long long) * 3, ctx->stream));
-    MCB_CUDA(ctx, cudaMemsetAsync(root_ord + 3, 0x00, sizeof(unsigned long long) * 3, ctx->stream));
-    MCB_CUDA(ctx, cudaMemsetAsync(m->flags.p, 0, sizeof(unsigned) * (size_t)nf, ctx->stream));
+    MCB_CUDA(ctx, cudaMemsetAsync(root_ord, 0xFF, sizeof(unsigned long long) * 3, ctx->cur));
+    MCB_CUDA(ctx, cudaMemsetAsync(root_ord + 3, 0x00, sizeof(unsigned long long) * 3, ctx->cur));
+    MCB_CUDA(ctx, cudaMemsetAsync(m->flags.p, 0, sizeof(unsigned) * (size_t)nf, ctx->cur));
     unsigned* n_groups = reinterpret_cast<unsigned*>(m->groups.as<uint2>() + nf);
-    MCB_CUDA(ctx, cudaMemsetAsync(n_groups, 0, sizeof(unsigned) * 4, ctx->stream));
+    MCB_CUDA(ctx, cudaMemsetAsync(n_groups, 0, sizeof(unsigned) * 4, ctx->cur));
 
     const unsigned max_grid = (unsigned)ctx->num_sms * 8u;
     const unsigned grid = div_up(nf, BLOCK) < max_grid ? div_up(nf, BLOCK) : max_grid;
@@ -414,11 +421,14 @@ int lbvh_build(mcb200_ctx* ctx, mcb200_mesh* m, double eps)
     MCB_LAUNCH(ctx, k_morton, grid, BLOCK, 0, m->face_bbox.as<double>(), nf, root_ord, root_dec, m->codes.as<uint32_t>(),
         m->sorted_codes.as<uint32_t>());
 
-    bool in_alt = false;
+    // (code, face) ascending by code: in = sorted_codes (values implicit 0..nf-1), ping-pong scratch <-> mesh arrays;
+    // four passes end in the mesh's own arrays
     const rsort::pass_desc pd = rsort::make_passes(0, 32);
-    MCB_TRY((rsort::sort<uint32_t, uint32_t, true>(ctx, m->sorted_codes.as<uint32_t>(), ctx->sort_keys_alt.as<uint32_t>(),
-        m->sorted_faces.as<uint32_t>(), ctx->sort_vals_alt.as<uint32_t>(), /*vals_are_iota=*/true, nullptr, nf, pd, &in_alt)));
-    if (in_alt) {
+    uint32_t *kout = nullptr, *vout = nullptr;
+    MCB_TRY((rsort::sort<uint32_t, uint32_t, true>(ctx, m->sorted_codes.as<uint32_t>(), sc.keys_alt.as<uint32_t>(),
+        m->sorted_codes.as<uint32_t>(), nullptr, sc.vals_alt.as<uint32_t>(), m->sorted_faces.as<uint32_t>(), nullptr, nf, pd, &kout,
+        &vout)));
+    if (kout != m->sorted_codes.as<uint32_t>() || vout != m->sorted_faces.as<uint32_t>()) {
         ctx->set_error("internal: Morton sort must use an even number of passes", __FILE__, __LINE__);
         return MCB200_ERR_INTERNAL;
     }

@@ -494,27 +494,62 @@ int sort_items(mcb200_ctx* ctx, const mcb200_result* res, const T* items, T* ite
 {
     if (cap == 0) return 0;
     (void)res;
+    const rsort::pass_desc pd = rsort::make_passes(0, bits_for(nfaces), 32, 32 + bits_for(nedges_bound));
     MCB_TRY(ctx->reserve(keys, sizeof(unsigned long long) * cap));
     MCB_TRY(ctx->reserve(idx, sizeof(uint32_t) * cap));
-    MCB_TRY(ctx->reserve(ctx->sort_keys_alt, sizeof(unsigned long long) * cap));
-    MCB_TRY(ctx->reserve(ctx->sort_vals_alt, sizeof(uint32_t) * cap));
+    MCB_TRY((rsort::reserve_scratch<unsigned long long>(ctx, cap, pd.npasses, true, true)));
+    mcb200_ctx::sort_scratch_t& sc = ctx->sc();
     const unsigned grid = (unsigned)ctx->num_sms * 2u;
-    MCB_LAUNCH(ctx, (k_make_keys<T>), grid, 256, 0, items, d_n, (unsigned long long)cap, keys.as<unsigned long long>());
-    rsort::pass_desc pd = rsort::make_passes(0, bits_for(nfaces), 32, 32 + bits_for(nedges_bound));
-    if (pd.npasses & 1) {
-        pd.shift[pd.npasses] = 0;
-        pd.bits[pd.npasses] = 0;
-        pd.npasses++;
-    }
-    bool in_alt = false;
-    MCB_TRY((rsort::sort<unsigned long long, uint32_t, true>(ctx, keys.as<unsigned long long>(),
-        ctx->sort_keys_alt.as<unsigned long long>(), idx.as<uint32_t>(), ctx->sort_vals_alt.as<uint32_t>(), true, d_n, cap, pd,
-        &in_alt)));
-    MCB_LAUNCH(ctx, (k_gather<T>), grid, 256, 0, items, idx.as<uint32_t>(), d_n, (unsigned long long)cap, items_sorted);
+    MCB_LAUNCH_NAMED(ctx, "k_make_keys", (k_make_keys<T>), grid, 256, 0, items, d_n, (unsigned long long)cap, keys.as<unsigned long long>());
+    unsigned long long* kout = nullptr;
+    uint32_t* vout = nullptr;
+    MCB_TRY((rsort::sort<unsigned long long, uint32_t, true>(ctx, keys.as<unsigned long long>(), sc.keys_alt.as<unsigned long long>(),
+        keys.as<unsigned long long>(), nullptr, sc.vals_alt.as<uint32_t>(), idx.as<uint32_t>(), d_n, cap, pd, &kout, &vout)));
+    MCB_LAUNCH_NAMED(ctx, "k_gather", (k_gather<T>), grid, 256, 0, items, vout, d_n, (unsigned long long)cap, items_sorted);
     return 0;
 }
 
 } // namespace
+
+// All allocations of the narrowphase (and of its record/test sorts, in the CURRENT scratch set).  Capacities are sized
+// from the pair CAPACITY, not the pair count, so nothing between traversal and narrowphase needs the host.
+int narrowphase_reserve(mcb200_ctx* ctx, const mcb200_soup* soup, mcb200_result* res, uint32_t flags)
+{
+    const uint32_t nf = soup->nsf + soup->ncf;
+    const bool tri = soup->all_tri != 0;
+    const bool want_log = (flags & MCB200_NARROW_LOG_TESTS) != 0;
+    // a pair yields at most ns + nc tests; records <= tests
+    const size_t avg_slots = tri ? 6 : (size_t)((soup->nh + nf - 1) / nf) * 2 + 2;
+    size_t cap_rec = res->cap_pairs * 2;
+    size_t cap_exact = res->cap_pairs * avg_slots;
+    if (cap_exact > (size_t)1 << 28) cap_exact = (size_t)1 << 28;
+    MCB_TRY(ctx->reserve(res->records, sizeof(mcb200_record) * cap_rec));
+    MCB_TRY(ctx->reserve(res->records_sorted, sizeof(mcb200_record) * cap_rec));
+    res->cap_records = cap_rec;
+    MCB_TRY(ctx->reserve(res->exact_queue, sizeof(unsigned long long) * cap_exact));
+    res->cap_exact = cap_exact;
+    MCB_TRY(ctx->reserve(res->cand_flag, (size_t)nf));
+    MCB_TRY(ctx->reserve(res->plane, sizeof(double) * 4 * (size_t)nf));
+    MCB_TRY(ctx->reserve(res->plane_mc, sizeof(int32_t) * 2 * (size_t)nf));
+    size_t cap_tests = 0;
+    if (want_log) {
+        cap_tests = res->cap_pairs * avg_slots;
+        if (cap_tests > (size_t)1 << 26) cap_tests = (size_t)1 << 26;
+        MCB_TRY(ctx->reserve(res->tests, sizeof(mcb200_test) * cap_tests));
+        MCB_TRY(ctx->reserve(res->tests_sorted, sizeof(mcb200_test) * cap_tests));
+        MCB_TRY(ctx->reserve(res->test_keys, sizeof(unsigned long long) * cap_tests));
+        MCB_TRY(ctx->reserve(res->test_idx, sizeof(uint32_t) * cap_tests));
+    }
+    res->cap_tests = cap_tests;
+    res->logged_tests = want_log;
+    res->ne_ps = soup->ne;
+    res->nf_ps = nf;
+    const size_t big = cap_tests > cap_rec ? cap_tests : cap_rec;
+    MCB_TRY(ctx->reserve(res->rec_keys, sizeof(unsigned long long) * cap_rec));
+    MCB_TRY(ctx->reserve(res->rec_idx, sizeof(uint32_t) * cap_rec));
+    MCB_TRY((rsort::reserve_scratch<unsigned long long>(ctx, big, rsort::MAX_PASSES, true, true)));
+    return 0;
+}
 
 int narrowphase_run(mcb200_ctx* ctx, const mcb200_soup* soup, const mcb200_mesh* src, const mcb200_mesh* cut,
     mcb200_result* res, uint32_t flags)
@@ -530,39 +565,16 @@ int narrowphase_run(mcb200_ctx* ctx, const mcb200_soup* soup, const mcb200_mesh*
     const uint32_t nf = soup->nsf + soup->ncf;
     const bool tri = soup->all_tri != 0;
     const bool want_log = (flags & MCB200_NARROW_LOG_TESTS) != 0;
-
-    // capacities: a pair yields at most ns + nc tests; records <= tests.  Sized from the pair CAPACITY so no host
-    // round trip is needed between traversal and narrowphase; grown on overflow by the caller-visible retry below.
-    const size_t avg_slots = tri ? 6 : (size_t)((soup->nh + nf - 1) / nf) * 2 + 2;
-    size_t cap_rec = res->cap_pairs * 2;
-    size_t cap_exact = res->cap_pairs * avg_slots;
-    if (cap_exact > (size_t)1 << 28) cap_exact = (size_t)1 << 28;
-    MCB_TRY(ctx->reserve(res->records, sizeof(mcb200_record) * cap_rec));
-    MCB_TRY(ctx->reserve(res->records_sorted, sizeof(mcb200_record) * cap_rec));
-    res->cap_records = cap_rec;
-    MCB_TRY(ctx->reserve(res->exact_queue, sizeof(unsigned long long) * cap_exact));
-    res->cap_exact = cap_exact;
-    MCB_TRY(ctx->reserve(res->cand_flag, (size_t)nf));
-    MCB_CUDA(ctx, cudaMemsetAsync(res->cand_flag.p, 0, (size_t)nf, ctx->stream));
-    MCB_TRY(ctx->reserve(res->plane, sizeof(double) * 4 * (size_t)nf));
-    MCB_TRY(ctx->reserve(res->plane_mc, sizeof(int32_t) * 2 * (size_t)nf));
-    size_t cap_tests = 0;
-    if (want_log) {
-        cap_tests = res->cap_pairs * avg_slots;
-        if (cap_tests > (size_t)1 << 26) cap_tests = (size_t)1 << 26;
-        MCB_TRY(ctx->reserve(res->tests, sizeof(mcb200_test) * cap_tests));
-        MCB_TRY(ctx->reserve(res->tests_sorted, sizeof(mcb200_test) * cap_tests));
-    }
-    res->cap_tests = cap_tests;
-    res->logged_tests = want_log;
-    res->ne_ps = soup->ne;
+    MCB_TRY(narrowphase_reserve(ctx, soup, res, flags));
+    const size_t cap_rec = res->cap_records, cap_exact = res->cap_exact, cap_tests = res->cap_tests;
+    MCB_CUDA(ctx, cudaMemsetAsync(res->cand_flag.p, 0, (size_t)nf, ctx->cur));
 
     // reset the narrowphase counters only (pairs / node tests stay)
     {
         result_counters_t* c = res->counters.as<result_counters_t>();
-        MCB_CUDA(ctx, cudaMemsetAsync(&c->n_tests, 0, sizeof(unsigned long long) * 5, ctx->stream)); // n_tests..n_log
-        MCB_CUDA(ctx, cudaMemsetAsync(&c->gp_violation, 0, sizeof(unsigned), ctx->stream));
-        MCB_CUDA(ctx, cudaMemsetAsync(&c->bad_face, 0xFF, sizeof(unsigned), ctx->stream));
+        MCB_CUDA(ctx, cudaMemsetAsync(&c->n_tests, 0, sizeof(unsigned long long) * 5, ctx->cur)); // n_tests..n_log
+        MCB_CUDA(ctx, cudaMemsetAsync(&c->gp_violation, 0, sizeof(unsigned), ctx->cur));
+        MCB_CUDA(ctx, cudaMemsetAsync(&c->bad_face, 0xFF, sizeof(unsigned), ctx->cur));
     }
 
     narrow_args_t a;
@@ -591,8 +603,8 @@ int narrowphase_run(mcb200_ctx* ctx, const mcb200_soup* soup, const mcb200_mesh*
     a.cap_tests = cap_tests;
 
     const unsigned grid = (unsigned)ctx->num_sms * 8u;
-    if (tri) MCB_LAUNCH(ctx, (k_tests<true, false>), grid, NBLOCK, 0, a);
-    else MCB_LAUNCH(ctx, (k_tests<false, false>), grid, NBLOCK, 0, a);
+    if (tri) MCB_LAUNCH_NAMED(ctx, "k_tests_filter_tri", (k_tests<true, false>), grid, NBLOCK, 0, a);
+    else MCB_LAUNCH_NAMED(ctx, "k_tests_filter_poly", (k_tests<false, false>), grid, NBLOCK, 0, a);
 
     plane_args_t pa;
     pa.n = a;
@@ -606,8 +618,8 @@ int narrowphase_run(mcb200_ctx* ctx, const mcb200_soup* soup, const mcb200_mesh*
     // exact-expansion pass over the compacted filter failures (own kernel: its local-memory footprint and divergence
     // stay out of the filter kernel)
     const unsigned egrid = (unsigned)ctx->num_sms * 4u;
-    if (tri) MCB_LAUNCH(ctx, (k_tests<true, true>), egrid, NBLOCK, 0, a);
-    else MCB_LAUNCH(ctx, (k_tests<false, true>), egrid, NBLOCK, 0, a);
+    if (tri) MCB_LAUNCH_NAMED(ctx, "k_tests_exact_tri", (k_tests<true, true>), egrid, NBLOCK, 0, a);
+    else MCB_LAUNCH_NAMED(ctx, "k_tests_exact_poly", (k_tests<false, true>), egrid, NBLOCK, 0, a);
 
     res->have_narrow = true;
     res->h_valid = false;

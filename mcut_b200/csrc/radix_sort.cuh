@@ -209,20 +209,38 @@ __global__ void __launch_bounds__(THREADS) k_onesweep_pass(const KeyT* __restric
         s_tile_excl[threadIdx.x] = excl_in_tile;
 
         // ---- decoupled look-back: sum of this digit's counts over all previous tiles ----
+        // At these sizes every tile of a pass is resident at once, so a tile usually finds AGGREGATES (not inclusive
+        // prefixes) in its predecessors and has to walk far back.  The walk therefore polls LOOK predecessors per step
+        // with independent loads instead of one dependent load per predecessor.
         {
+            constexpr int LOOK = 16;
             const unsigned d = threadIdx.x;
             unsigned prefix = 0;
             if (tile > 0) {
                 int t = (int)tile - 1;
-                while (t >= 0) {
-                    volatile unsigned* st = status + (size_t)t * RADIX + d;
-                    unsigned s;
-                    do {
-                        s = *st;
-                    } while ((s & FLAG_MASK) == 0);
-                    prefix += s & VALUE_MASK;
-                    if (s & FLAG_INCL) break;
-                    --t;
+                bool done = false;
+                while (!done) {
+                    unsigned sv[LOOK];
+#pragma unroll
+                    for (int k = 0; k < LOOK; ++k) {
+                        const int tt = t - k;
+                        volatile unsigned* st = status + (size_t)(tt >= 0 ? tt : 0) * RADIX + d;
+                        unsigned cur = FLAG_INCL + 0u;
+                        if (tt >= 0) cur = *st;
+                        sv[k] = cur; // before tile 0: an inclusive prefix of zero
+                    }
+                    // consume the ready statuses nearest-first; stop at the first not-ready one and poll again from it
+                    int used = 0;
+#pragma unroll
+                    for (int k = 0; k < LOOK; ++k) {
+                        if (done || used != k) continue;
+                        const unsigned sk = sv[k];
+                        if ((sk & FLAG_MASK) == 0) continue; // not published yet
+                        prefix += sk & VALUE_MASK;
+                        used = k + 1;
+                        if (sk & FLAG_INCL) done = true;
+                    }
+                    t -= used;
                 }
                 volatile unsigned* me = status + (size_t)tile * RADIX + d;
                 *me = FLAG_INCL | (prefix + total);
@@ -259,47 +277,58 @@ template <typename KeyT> struct items_for {
     static constexpr int value = sizeof(KeyT) == 4 ? 16 : 8;
 };
 
-// Sort n (or *d_n) keys [and values].  keys/vals are the in/out arrays, alt_* the ping-pong buffers.  Returns in
-// *result_in_alt whether the sorted data ended up in the alt buffers (odd number of passes).
-// scratch: hist [MAX_PASSES*RADIX] u32, status [npasses * tiles * RADIX] u32, tilectr [MAX_PASSES] u32.
+// scratch sizes a sort of n_max keys needs in the CURRENT scratch set (so callers can reserve before forking lanes)
+template <typename KeyT> int reserve_scratch(mcb200_ctx* ctx, size_t n_max, int npasses, bool need_alt_keys, bool need_alt_vals)
+{
+    constexpr int TILE = THREADS * items_for<KeyT>::value;
+    const size_t tiles = (n_max + TILE - 1) / TILE;
+    mcb200_ctx::sort_scratch_t& sc = ctx->sc();
+    MCB_TRY(ctx->reserve(sc.hist, sizeof(unsigned) * MAX_PASSES * RADIX));
+    MCB_TRY(ctx->reserve(sc.status, sizeof(unsigned) * (size_t)(npasses ? npasses : 1) * (tiles ? tiles : 1) * RADIX));
+    MCB_TRY(ctx->reserve(sc.tilectr, sizeof(unsigned) * MAX_PASSES));
+    if (need_alt_keys) MCB_TRY(ctx->reserve(sc.keys_alt, sizeof(KeyT) * (n_max ? n_max : 1)));
+    if (need_alt_vals) MCB_TRY(ctx->reserve(sc.vals_alt, sizeof(uint32_t) * (n_max ? n_max : 1)));
+    return 0;
+}
+
+// Sort n (or *d_n) keys [and values].  Pass 0 reads keys_in/vals_in, the passes then ping-pong between the (a) and (b)
+// buffers: in -> a -> b -> a ...  (b may alias the input when it may be overwritten).  *keys_out / *vals_out receive the
+// buffer the sorted data ended up in.  vals_in == nullptr with HAS_VALS: the value of element i is i.
 template <typename KeyT, typename ValT, bool HAS_VALS>
-int sort(mcb200_ctx* ctx, KeyT* keys, KeyT* alt_keys, ValT* vals, ValT* alt_vals, bool vals_are_iota,
-    const unsigned long long* d_n, size_t n_max, const pass_desc& pd, bool* result_in_alt)
+int sort(mcb200_ctx* ctx, const KeyT* keys_in, KeyT* keys_a, KeyT* keys_b, const ValT* vals_in, ValT* vals_a, ValT* vals_b,
+    const unsigned long long* d_n, size_t n_max, const pass_desc& pd, KeyT** keys_out, ValT** vals_out)
 {
     constexpr int ITEMS = items_for<KeyT>::value;
     constexpr int TILE = THREADS * ITEMS;
-    *result_in_alt = false;
+    if (keys_out) *keys_out = const_cast<KeyT*>(keys_in);
+    if (vals_out) *vals_out = const_cast<ValT*>(vals_in);
     if (n_max == 0 || pd.npasses == 0) return 0;
     const size_t tiles = (n_max + TILE - 1) / TILE;
-    MCB_TRY(ctx->reserve(ctx->sort_hist, sizeof(unsigned) * MAX_PASSES * RADIX));
-    MCB_TRY(ctx->reserve(ctx->sort_status, sizeof(unsigned) * (size_t)pd.npasses * tiles * RADIX));
-    MCB_TRY(ctx->reserve(ctx->sort_tilectr, sizeof(unsigned) * MAX_PASSES));
-    MCB_CUDA(ctx, cudaMemsetAsync(ctx->sort_hist.p, 0, sizeof(unsigned) * MAX_PASSES * RADIX, ctx->stream));
-    MCB_CUDA(ctx, cudaMemsetAsync(ctx->sort_tilectr.p, 0, sizeof(unsigned) * MAX_PASSES, ctx->stream));
+    MCB_TRY((reserve_scratch<KeyT>(ctx, n_max, pd.npasses, false, false)));
+    mcb200_ctx::sort_scratch_t& sc = ctx->sc();
+    MCB_CUDA(ctx, cudaMemsetAsync(sc.hist.p, 0, sizeof(unsigned) * MAX_PASSES * RADIX, ctx->cur));
+    MCB_CUDA(ctx, cudaMemsetAsync(sc.tilectr.p, 0, sizeof(unsigned) * MAX_PASSES, ctx->cur));
 
     const unsigned hgrid = (unsigned)((tiles < (size_t)ctx->num_sms * 4) ? tiles : (size_t)ctx->num_sms * 4);
-    MCB_LAUNCH(ctx, (k_histogram<KeyT>), hgrid, THREADS, 0, keys, d_n, n_max, pd, TILE, ctx->sort_hist.as<unsigned>(),
-        ctx->sort_status.as<unsigned>());
+    const char* hname = sizeof(KeyT) == 4 ? "sort_histogram_u32" : "sort_histogram_u64";
+    const char* pname = sizeof(KeyT) == 4 ? "onesweep_pass_u32_kv" : (HAS_VALS ? "onesweep_pass_u64_kv" : "onesweep_pass_u64_k");
+    MCB_LAUNCH_NAMED(ctx, hname, (k_histogram<KeyT>), hgrid, THREADS, 0, keys_in, d_n, n_max, pd, TILE, sc.hist.as<unsigned>(),
+        sc.status.as<unsigned>());
 
     // persistent grid: enough resident blocks to fill the machine, never more than tiles
     const unsigned pgrid = (unsigned)((tiles < (size_t)ctx->num_sms * 4) ? tiles : (size_t)ctx->num_sms * 4);
-    KeyT* kin = keys;
-    KeyT* kout = alt_keys;
-    ValT* vin = vals;
-    ValT* vout = alt_vals;
+    const KeyT* kin = keys_in;
+    const ValT* vin = vals_in;
     for (int p = 0; p < pd.npasses; ++p) {
-        const ValT* vsrc = (HAS_VALS && p == 0 && vals_are_iota) ? nullptr : vin;
-        MCB_LAUNCH(ctx, (k_onesweep_pass<KeyT, ValT, HAS_VALS, ITEMS>), pgrid, THREADS, 0, kin, kout, vsrc, vout, d_n, n_max,
-            pd.shift[p], pd.bits[p], p, ctx->sort_hist.as<unsigned>() + p * RADIX, ctx->sort_status.as<unsigned>(),
-            ctx->sort_tilectr.as<unsigned>() + p);
-        KeyT* tk = kin;
+        KeyT* kout = (p & 1) ? keys_b : keys_a;
+        ValT* vout = (p & 1) ? vals_b : vals_a;
+        MCB_LAUNCH_NAMED(ctx, pname, (k_onesweep_pass<KeyT, ValT, HAS_VALS, ITEMS>), pgrid, THREADS, 0, kin, kout, vin, vout, d_n, n_max,
+            pd.shift[p], pd.bits[p], p, sc.hist.as<unsigned>() + p * RADIX, sc.status.as<unsigned>(), sc.tilectr.as<unsigned>() + p);
         kin = kout;
-        kout = tk;
-        ValT* tv = vin;
         vin = vout;
-        vout = tv;
     }
-    *result_in_alt = (pd.npasses & 1) != 0;
+    if (keys_out) *keys_out = const_cast<KeyT*>(kin);
+    if (vals_out) *vals_out = const_cast<ValT*>(vin);
     return 0;
 }
 

@@ -231,6 +231,27 @@ static int bits_for(uint32_t n)
 
 } // namespace
 
+static rsort::pass_desc pair_passes(uint32_t nsf, uint32_t ncf)
+{
+    // ascending (src << 32 | cut): only the bits that can be set take part in the sort
+    return rsort::make_passes(0, bits_for(ncf), 32, 32 + bits_for(nsf));
+}
+
+int traverse_reserve(mcb200_ctx* ctx, const mcb200_mesh* src, const mcb200_mesh* cut, mcb200_result* res)
+{
+    if (res->cap_pairs == 0) {
+        size_t want = 4ull * ((size_t)src->nf + cut->nf);
+        if (want < (1u << 20)) want = 1u << 20;
+        res->cap_pairs = want;
+    }
+    MCB_TRY(ctx->reserve(res->pairs, sizeof(unsigned long long) * res->cap_pairs));
+    MCB_TRY(ctx->reserve(res->pairs_a, sizeof(unsigned long long) * res->cap_pairs));
+    MCB_TRY(ctx->reserve(res->pairs_b, sizeof(unsigned long long) * res->cap_pairs));
+    MCB_TRY(ctx->reserve(res->counters, sizeof(result_counters_t)));
+    return 0;
+}
+
+// the traversal kernel alone, on ctx->cur: pairs land in res->pairs in emission order
 int traverse_pairs(mcb200_ctx* ctx, const mcb200_mesh* src, const mcb200_mesh* cut, mcb200_result* res)
 {
     if (!src->built || !cut->built) {
@@ -240,19 +261,12 @@ int traverse_pairs(mcb200_ctx* ctx, const mcb200_mesh* src, const mcb200_mesh* c
     const bool query_is_cut = cut->nf > src->nf;
     const mcb200_mesh* q = query_is_cut ? cut : src;
     const mcb200_mesh* t = query_is_cut ? src : cut;
-
-    if (res->cap_pairs == 0) {
-        size_t want = 4ull * ((size_t)src->nf + cut->nf);
-        if (want < (1u << 20)) want = 1u << 20;
-        MCB_TRY(ctx->reserve(res->pairs, sizeof(unsigned long long) * want));
-        res->cap_pairs = want;
-    }
-    MCB_TRY(ctx->reserve(res->counters, sizeof(result_counters_t)));
-    MCB_CUDA(ctx, cudaMemsetAsync(res->counters.p, 0, sizeof(result_counters_t), ctx->stream));
+    MCB_TRY(traverse_reserve(ctx, src, cut, res));
+    MCB_CUDA(ctx, cudaMemsetAsync(res->counters.p, 0, sizeof(result_counters_t), ctx->cur));
     {
         // bad_face starts at "none"
         const size_t off = offsetof(result_counters_t, bad_face);
-        MCB_CUDA(ctx, cudaMemsetAsync(reinterpret_cast<char*>(res->counters.p) + off, 0xFF, sizeof(unsigned), ctx->stream));
+        MCB_CUDA(ctx, cudaMemsetAsync(reinterpret_cast<char*>(res->counters.p) + off, 0xFF, sizeof(unsigned), ctx->cur));
     }
     res->nsf = src->nf;
     res->nf_ps = src->nf + cut->nf;
@@ -260,6 +274,7 @@ int traverse_pairs(mcb200_ctx* ctx, const mcb200_mesh* src, const mcb200_mesh* c
     res->have_narrow = false;
     res->records_sorted_valid = false;
     res->tests_sorted_valid = false;
+    res->pairs_sorted = nullptr;
 
     traverse_args_t a;
     a.q_face_bbox = q->face_bbox.as<double>();
@@ -275,7 +290,6 @@ int traverse_pairs(mcb200_ctx* ctx, const mcb200_mesh* src, const mcb200_mesh* c
     a.pairs = res->pairs.as<unsigned long long>();
     a.cap_pairs = res->cap_pairs;
     a.counters = res->counters.as<result_counters_t>();
-
     // query groups = the maximal <=32-leaf treelets of the query mesh's own tree, listed by its refit kernel
     a.groups = q->groups.as<uint2>();
     a.n_groups = reinterpret_cast<const unsigned*>(q->groups.as<uint2>() + q->nf);
@@ -286,24 +300,25 @@ int traverse_pairs(mcb200_ctx* ctx, const mcb200_mesh* src, const mcb200_mesh* c
     const unsigned want_blocks = div_up(div_up((size_t)q->nf / 8u + 1u, GROUP_BATCH), WARPS_PER_BLOCK);
     const unsigned grid = want_blocks < max_blocks ? (want_blocks ? want_blocks : 1u) : max_blocks;
     MCB_LAUNCH(ctx, k_traverse, grid, TBLOCK, 0, a);
-
-    // ascending (src << 32 | cut): only the bits that can be set take part in the sort; an odd pass count gets a
-    // zero-bit (identity) pass appended so the result lands in res->pairs without a capacity-sized copy
-    rsort::pass_desc pd = rsort::make_passes(0, bits_for(cut->nf), 32, 32 + bits_for(src->nf));
-    if (pd.npasses & 1) {
-        pd.shift[pd.npasses] = 0;
-        pd.bits[pd.npasses] = 0;
-        pd.npasses++;
-    }
-    MCB_TRY(ctx->reserve(ctx->sort_keys_alt, sizeof(unsigned long long) * res->cap_pairs));
-    bool in_alt = false;
-    MCB_TRY((rsort::sort<unsigned long long, uint32_t, false>(ctx, res->pairs.as<unsigned long long>(),
-        ctx->sort_keys_alt.as<unsigned long long>(), nullptr, nullptr, false,
-        &res->counters.as<result_counters_t>()->n_pairs, res->cap_pairs, pd, &in_alt)));
-    if (in_alt) {
-        ctx->set_error("internal: pair sort ended in the alternate buffer", __FILE__, __LINE__);
-        return MCB200_ERR_INTERNAL;
-    }
     res->have_pairs = true;
+    return 0;
+}
+
+int sort_pairs_reserve(mcb200_ctx* ctx, const mcb200_mesh* src, const mcb200_mesh* cut, mcb200_result* res)
+{
+    const rsort::pass_desc pd = pair_passes(src->nf, cut->nf);
+    return rsort::reserve_scratch<unsigned long long>(ctx, res->cap_pairs, pd.npasses, false, false);
+}
+
+// canonical order of the pair set, on ctx->cur with ctx's current scratch set; res->pairs itself is left untouched
+// (the narrowphase may be reading it on the other lane)
+int sort_pairs(mcb200_ctx* ctx, const mcb200_mesh* src, const mcb200_mesh* cut, mcb200_result* res)
+{
+    const rsort::pass_desc pd = pair_passes(src->nf, cut->nf);
+    unsigned long long* out = nullptr;
+    MCB_TRY((rsort::sort<unsigned long long, uint32_t, false>(ctx, res->pairs.as<unsigned long long>(),
+        res->pairs_a.as<unsigned long long>(), res->pairs_b.as<unsigned long long>(), nullptr, nullptr, nullptr,
+        &res->counters.as<result_counters_t>()->n_pairs, res->cap_pairs, pd, &out, nullptr)));
+    res->pairs_sorted = out;
     return 0;
 }
