@@ -11,6 +11,7 @@
 //   build_oibvh        include/mcut/internal/bvh.h:117-125   source/bvh.cpp:219-636
 //   intersectOIBVHs    include/mcut/internal/bvh.h:127-133   source/bvh.cpp:638-783
 //   dispatch           include/mcut/internal/kernel.h:227    source/kernel.cpp:1536
+//   client_input_arrays_to_hmesh  source/preproc.cpp:57-468 (exposes com, shift and the perturbation of every retry)
 //   dump_mesh          source/kernel.cpp:158-186 ("polygon-soup" at :1737 exposes ps, "m0.v" at :3260
 //                      exposes ps vertices + intersection points in registry order)
 //   compute_polygon_plane_coefficients / compute_segment_plane_intersection_type /
@@ -34,6 +35,7 @@
 
 #include "mcut/mcut.h"
 #include "mcut/internal/bvh.h"
+#include "mcut/internal/frontend.h"
 #include "mcut/internal/hmesh.h"
 #include "mcut/internal/kernel.h"
 #include "mcut/internal/math.h"
@@ -59,6 +61,7 @@ struct state_t {
     int build_calls = 0;
     int isect_calls = 0;
     int dispatch_calls = 0;
+    int c2h_calls = 0;
     std::vector<double> events; // [kind, len, payload...]
     size_t max_events = (size_t)1 << 28;
     std::vector<double> timings_ms; // [kind(0 build,1 isect,2 ps->m0.v), value]
@@ -115,9 +118,9 @@ void push_bbox(std::vector<double>& o, const bbox_t& b)
     o.push_back(b.maximum().z());
 }
 
-struct event_t {
+struct log_event_t {
     std::vector<double> d;
-    explicit event_t(double kind)
+    explicit log_event_t(double kind)
     {
         d.push_back(kind);
         d.push_back(0.0);
@@ -196,6 +199,36 @@ void dump_mesh(const hmesh_t& mesh, const char* fbasename, const double /*multip
         }
         if (do_abort) throw abort_dispatch_t();
     }
+}
+
+bool client_input_arrays_to_hmesh(std::shared_ptr<context_t>& context_ptr, McFlags dispatchFlags, hmesh_t& halfedgeMesh,
+    const void* pVertices, const McUint32* pFaceIndices, const McUint32* pFaceSizes, const McUint32 numVertices,
+    const McUint32 numFaces, const double multiplier, const vec3_<double> srcmesh_cutmesh_com,
+    const vec3_<double> pre_quantization_translation, const vec3_<double>* perturbation)
+{
+    typedef bool (*fn_t)(std::shared_ptr<context_t>&, McFlags, hmesh_t&, const void*, const McUint32*, const McUint32*,
+        const McUint32, const McUint32, const double, const vec3_<double>, const vec3_<double>, const vec3_<double>*);
+    static fn_t real = real_fn<fn_t>(
+        "_Z28client_input_arrays_to_hmeshRSt10shared_ptrI9context_tEjR7hmesh_tPKvPKjS8_jjd5vec3_IdESA_PKSA_");
+    {
+        std::lock_guard<std::mutex> lk(g.mtx);
+        const int k = g.c2h_calls++;
+        const double com[3] = { srcmesh_cutmesh_com.x(), srcmesh_cutmesh_com.y(), srcmesh_cutmesh_com.z() };
+        const double sh[3] = { pre_quantization_translation.x(), pre_quantization_translation.y(), pre_quantization_translation.z() };
+        double pe[3] = { 0, 0, 0 };
+        if (perturbation) {
+            pe[0] = perturbation->x();
+            pe[1] = perturbation->y();
+            pe[2] = perturbation->z();
+        }
+        mcb::put<double>(g.out, idx_name("c2h", k, "com"), com, { 3 });
+        mcb::put<double>(g.out, idx_name("c2h", k, "shift"), sh, { 3 });
+        mcb::put<double>(g.out, idx_name("c2h", k, "pert"), pe, { 3 });
+        mcb::put_scalar<int32_t>(g.out, idx_name("c2h", k, "has_pert"), perturbation ? 1 : 0);
+        mcb::put_scalar<uint32_t>(g.out, idx_name("c2h", k, "num_vertices"), numVertices);
+    }
+    return real(context_ptr, dispatchFlags, halfedgeMesh, pVertices, pFaceIndices, pFaceSizes, numVertices, numFaces, multiplier,
+        srcmesh_cutmesh_com, pre_quantization_translation, perturbation);
 }
 
 void build_oibvh(thread_pool& pool, const hmesh_t& mesh, std::vector<bbox_t>& bvhAABBs,
@@ -296,7 +329,7 @@ int compute_polygon_plane_coefficients(vec3& normal, scalar_t& d_coeff, const ve
     static fn_t real = real_fn<fn_t>("_Z34compute_polygon_plane_coefficientsR5vec3_IdERdPKS0_id");
     const int r = real(normal, d_coeff, polygon_vertices, polygon_vertex_count, multiplier);
     if (g.log_events) {
-        event_t e(1);
+        log_event_t e(1);
         e.s(polygon_vertex_count);
         for (int i = 0; i < polygon_vertex_count; ++i) e.v3(polygon_vertices[i]);
         e.v3(normal);
@@ -314,7 +347,7 @@ char compute_segment_plane_intersection_type(const vec3& q, const vec3& r, const
     static fn_t real = real_fn<fn_t>("_Z39compute_segment_plane_intersection_typeRK5vec3_IdES2_RKSt6vectorIS0_SaIS0_EES2_id");
     // the start marker is logged BEFORE the call so nested orient3d/orient2d events follow it
     if (g.log_events) {
-        event_t e(2);
+        log_event_t e(2);
         e.v3(q);
         e.v3(r);
         e.s((double)polygon_vertices.size());
@@ -325,7 +358,7 @@ char compute_segment_plane_intersection_type(const vec3& q, const vec3& r, const
     }
     const char res = real(q, r, polygon_vertices, polygon_normal, polygon_normal_largest_component, multiplier);
     if (g.log_events) {
-        event_t e(7);
+        log_event_t e(7);
         e.s((double)res);
         e.commit();
     }
@@ -338,7 +371,7 @@ char compute_segment_plane_intersection(vec3& p, const vec3& normal, const scala
     static fn_t real = real_fn<fn_t>("_Z34compute_segment_plane_intersectionR5vec3_IdERKS0_RKdS3_S3_");
     const char res = real(p, normal, d_coeff, q, r);
     if (g.log_events) {
-        event_t e(5);
+        log_event_t e(5);
         e.v3(normal);
         e.s(d_coeff);
         e.v3(q);
@@ -357,7 +390,7 @@ char compute_point_in_polygon_test(const vec3& p, const std::vector<vec3>& polyg
     static fn_t real = real_fn<fn_t>("_Z29compute_point_in_polygon_testRK5vec3_IdERKSt6vectorIS0_SaIS0_EES2_id");
     const char res = real(p, polygon_vertices, polygon_normal, polygon_normal_largest_component, multiplier);
     if (g.log_events) {
-        event_t e(6);
+        log_event_t e(6);
         e.v3(p);
         e.s((double)polygon_vertices.size());
         for (const vec3& v : polygon_vertices) e.v3(v);
@@ -375,7 +408,7 @@ extern "C" double orient3d(const double* pa, const double* pb, const double* pc,
     static fn_t real = real_fn<fn_t>("orient3d");
     const double r = real(pa, pb, pc, pd);
     if (g.log_events) {
-        event_t e(3);
+        log_event_t e(3);
         for (int i = 0; i < 3; ++i) e.s(pa[i]);
         for (int i = 0; i < 3; ++i) e.s(pb[i]);
         for (int i = 0; i < 3; ++i) e.s(pc[i]);
@@ -401,7 +434,7 @@ extern "C" double orient2d(const double* pa, const double* pb, const double* pc)
     static fn_t real = real_fn<fn_t>("orient2d");
     const double r = real(pa, pb, pc);
     if (g.log_events) {
-        event_t e(4);
+        log_event_t e(4);
         for (int i = 0; i < 2; ++i) e.s(pa[i]);
         for (int i = 0; i < 2; ++i) e.s(pb[i]);
         for (int i = 0; i < 2; ++i) e.s(pc[i]);
@@ -542,6 +575,7 @@ int main(int argc, char** argv)
     mcb::put_scalar<int32_t>(g.out, "build_calls", g.build_calls);
     mcb::put_scalar<int32_t>(g.out, "isect_calls", g.isect_calls);
     mcb::put_scalar<int32_t>(g.out, "dispatch_calls", g.dispatch_calls);
+    mcb::put_scalar<int32_t>(g.out, "c2h_calls", g.c2h_calls);
     mcb::put_scalar<int64_t>(g.out, "orient3dadapt_calls", (int64_t)g_adapt_calls.load());
     mcb::put(g.out, "events", g.events);
     mcb::put(g.out, "timings_ms", g.timings_ms, 2);

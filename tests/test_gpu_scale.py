@@ -1,0 +1,105 @@
+"""-m gpu: BASELINE.json sizes.  The oracle port finishes these in seconds, so the comparison stays bit-exact; on top
+come size-independent properties (role swap, idempotence, shard union)."""
+import numpy as np
+import pytest
+
+from mcut_b200 import meshgen as mg
+
+pytestmark = pytest.mark.gpu
+
+
+def beq(a, b):
+    a = np.ascontiguousarray(a)
+    b = np.ascontiguousarray(b)
+    return a.shape == b.shape and a.dtype == b.dtype and a.tobytes() == b.tobytes()
+
+
+def compare(oracle, ctx, src, cut, flags, perturbation=None):
+    from mcut_b200 import stage
+    ref = oracle.intersect_stage(src, cut, flags, perturbation=perturbation)
+    got = stage.intersect_stage(ctx, src, cut, flags, perturbation=perturbation, want_boxes=False)
+    assert beq(got["pairs"], ref["pairs"]), "sorted candidate pair set"
+    assert got["status"] == ref["status"]
+    assert got["n_tests"] == len(ref["tests"])
+    assert got["n_exact"] == int(np.count_nonzero(ref["tests"]["exact_q"] | ref["tests"]["exact_r"]))
+    if ref["status"] == 0:
+        rr, gr = ref["records"], got["records"]
+        assert beq(gr["edge"], rr["edge"]) and beq(gr["face"], rr["face"]) and beq(gr["point"], rr["point"]), "registry"
+    assert beq(got["cand_faces"], ref["cand_faces"]) and beq(got["cand_normal"], ref["cand_normal"])
+    return ref, got
+
+
+def test_c2_two_spheres_1m(oracle, gpu_ctx):
+    src, cut, flags = mg.c2_two_spheres(k=289)
+    ref, got = compare(oracle, gpu_ctx, src, cut, flags)
+    assert got["n_pairs"] == 34464 and got["n_records"] == 5100  # == the reference's own run (harness)
+
+
+def test_c3_terrain_4m_one_plane(oracle, gpu_ctx):
+    """One of C3's 256 dispatches: 3,998,792-triangle terrain vs a single huge triangle (a one-leaf cut BVH)."""
+    ter = mg.terrain()
+    tri = np.array([[-900.0, -850.0, -4.1], [1400.0, -700.0, 3.3], [150.0, 1600.0, 1.7]])
+    cut = (tri, np.array([0, 1, 2], dtype=np.uint32), None)
+    compare(oracle, gpu_ctx, ter, cut, mg.MC_DISPATCH_VERTEX_ARRAY_DOUBLE | mg.MC_DISPATCH_ENFORCE_GENERAL_POSITION)
+
+
+def test_c4_small_pairs(oracle, gpu_ctx):
+    for j in range(6):
+        src, cut, flags = mg.c4_pair(j)
+        compare(oracle, gpu_ctx, src, cut, flags)
+
+
+def test_c5_dense_overlap_2m(oracle, gpu_ctx):
+    src, cut, flags = mg.c5_near_coplanar(k=409)
+    ref, got = compare(oracle, gpu_ctx, src, cut, flags)
+    assert got["n_pairs"] > 500000
+
+
+def test_role_swap_gives_transposed_pairs(gpu_ctx):
+    """Swapping source and cut (eps = 0 on both sides) must give the transposed pair set: the traversal picks its query
+    side by size, so this exercises both orientations."""
+    from mcut_b200 import stage
+    a = mg.cube_sphere(40, 20.0)
+    b = mg.cube_sphere(23, 20.0, rotation=mg.rot_z(0.3), centre=(11.0, 2.0, 1.0))
+    ctx = gpu_ctx
+
+    def pairs(src, cut):
+        ms, mc = stage.Mesh(ctx, *src), stage.Mesh(ctx, *cut)
+        ms.build(0.0)
+        mc.build(0.0)
+        res = stage.Result(ctx)
+        ctx.check(ctx.L.mcb200_bvh_intersect(ctx.h, ms.h, mc.h, res.h))
+        p = res.pairs()
+        for o in (res, ms, mc):
+            o.free()
+        return p
+
+    ab, ba = pairs(a, b), pairs(b, a)
+    swapped = np.sort((ba << np.uint64(32)) | (ba >> np.uint64(32)))
+    assert ab.size > 0 and beq(ab, swapped)
+
+
+def test_shards_partition_the_pair_set(gpu_ctx):
+    """traversing the query leaves in nparts round-robin slices yields disjoint pair sets whose union is the
+    unsharded set (what the NCCL all-gather reassembles)."""
+    from mcut_b200 import stage
+    src, cut, flags = mg.c2_two_spheres(k=64)
+    ctx = gpu_ctx
+    ms, mc = stage.Mesh(ctx, *src), stage.Mesh(ctx, *cut)
+    com, shift, sbb, cbb = stage.vertex_parameters(src[0], cut[0])
+    ms.set_frame(com, shift)
+    mc.set_frame(com, shift)
+    ms.build(0.0)
+    mc.build(stage.cut_bbox_eps(cbb))
+    res = stage.Result(ctx)
+    ctx.check(ctx.L.mcb200_bvh_intersect(ctx.h, ms.h, mc.h, res.h))
+    full = res.pairs()
+    parts = []
+    for part in range(3):
+        res.set_shard(part, 3, 256)
+        ctx.check(ctx.L.mcb200_bvh_intersect(ctx.h, ms.h, mc.h, res.h))
+        parts.append(res.pairs())
+    assert sum(p.size for p in parts) == full.size
+    assert beq(np.sort(np.concatenate(parts)), full)
+    for o in (res, ms, mc):
+        o.free()
