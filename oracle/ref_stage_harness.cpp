@@ -142,6 +142,7 @@ struct log_event_t {
 
 } // namespace
 
+#ifndef HARNESS_NO_HOOKS
 // ------------------------------------------------------------------------------------------------
 // interposed reference functions
 // ------------------------------------------------------------------------------------------------
@@ -444,6 +445,8 @@ extern "C" double orient2d(const double* pa, const double* pb, const double* pc)
     return r;
 }
 
+#endif // HARNESS_NO_HOOKS
+
 // ------------------------------------------------------------------------------------------------
 
 static void query_ccs(McContext ctx, mcb::file_t& out)
@@ -576,11 +579,13 @@ int main(int argc, char** argv)
     mcb::put_scalar<int32_t>(g.out, "isect_calls", g.isect_calls);
     mcb::put_scalar<int32_t>(g.out, "dispatch_calls", g.dispatch_calls);
     mcb::put_scalar<int32_t>(g.out, "c2h_calls", g.c2h_calls);
+#ifndef HARNESS_NO_HOOKS
     mcb::put_scalar<int64_t>(g.out, "orient3dadapt_calls", (int64_t)g_adapt_calls.load());
+#endif
     mcb::put(g.out, "events", g.events);
     mcb::put(g.out, "timings_ms", g.timings_ms, 2);
     mcb::write(argv[2], g.out);
-    std::fprintf(stderr, "harness: mcDispatch=%d builds=%d isects=%d dispatches=%d adapt=%ld events=%zu\n", rc,
-        g.build_calls, g.isect_calls, g.dispatch_calls, g_adapt_calls.load(), g.events.size());
+    std::fprintf(stderr, "harness: mcDispatch=%d builds=%d isects=%d dispatches=%d events=%zu\n", rc, g.build_calls, g.isect_calls,
+        g.dispatch_calls, g.events.size());
     return 0;
 }
