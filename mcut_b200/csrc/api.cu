@@ -337,6 +337,7 @@ void mcb200_mesh_free(mcb200_ctx* ctx, mcb200_mesh* m)
     ctx->release(m->meta);
     ctx->release(m->flags);
     ctx->release(m->groups);
+    ctx->release(m->group_up);
     delete m;
 }
 

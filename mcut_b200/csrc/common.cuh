@@ -167,6 +167,7 @@ struct mcb200_mesh {
     dbuf meta; // [nf-1] uint4 (left, right, first, last): compact copy of the node topology
     dbuf flags; // [nf-1] u32 refit arrival counters
     dbuf groups; // [nf] uint2 query groups (first leaf, count) + u32 counter after them
+    dbuf group_up; // [<= nf] box + parent word of every group root (input of the atomic climb)
     bool groups_valid = false;
 };
 

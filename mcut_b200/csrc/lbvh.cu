@@ -106,10 +106,18 @@ __global__ void __launch_bounds__(BLOCK) k_face_bbox(const void* __restrict__ xy
 }
 
 // ---- K_morton ---------------------------------------------------------------------------------------------------
+// Codes by face + the same codes as sort keys; the digit histograms of all four radix passes are accumulated here (shared
+// memory, one flush per block) and the sort's look-back status words are cleared, so the sort needs no histogram kernel
+// and no second read of the keys.
 __global__ void __launch_bounds__(BLOCK) k_morton(const double* __restrict__ face_bbox, uint32_t nf,
     const unsigned long long* __restrict__ root_ordered, double* __restrict__ root_decoded, uint32_t* __restrict__ codes,
-    uint32_t* __restrict__ sort_keys)
+    uint32_t* __restrict__ sort_keys, unsigned* __restrict__ hist /* [4][256] */, unsigned* __restrict__ status,
+    unsigned status_words)
 {
+    __shared__ unsigned s_hist[4 * 256];
+    for (int i = threadIdx.x; i < 4 * 256; i += BLOCK) s_hist[i] = 0;
+    for (unsigned i = blockIdx.x * BLOCK + threadIdx.x; i < status_words; i += gridDim.x * BLOCK) status[i] = 0u;
+    __syncthreads();
     double rmin[3], dims[3];
 #pragma unroll
     for (int j = 0; j < 3; ++j) {
@@ -131,6 +139,13 @@ __global__ void __launch_bounds__(BLOCK) k_morton(const double* __restrict__ fac
         const uint32_t code = morton3D(nrm[0], nrm[1], nrm[2]);
         codes[f] = code;
         sort_keys[f] = code;
+#pragma unroll
+        for (int p = 0; p < 4; ++p) atomicAdd(&s_hist[p * 256 + ((code >> (8 * p)) & 255u)], 1u);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 4 * 256; i += BLOCK) {
+        const unsigned c = s_hist[i];
+        if (c) atomicAdd(&hist[i], c);
     }
 }
 
@@ -242,30 +257,58 @@ __device__ __forceinline__ void load_face_box(const double* __restrict__ face_bb
     b[5] = e.y;
 }
 
-__device__ __forceinline__ void append_group(uint2* groups, unsigned* n_groups, uint32_t first, uint32_t count)
+// Slots in the group list for a whole block with ONE global atomic (tens of thousands of same-address atomics from
+// individual warps serialise in L2 and were the most expensive part of this kernel).  Every thread of the block must
+// call this; `want` is 0, 1 or 2.  Returns the first slot of the calling thread.
+__device__ __forceinline__ unsigned alloc_groups_block(unsigned* n_groups, unsigned want, unsigned* s_warp /*[BLOCK/32]*/,
+    unsigned* s_base)
 {
-    const unsigned m = __activemask();
-    const int leader = __ffs(m) - 1;
-    unsigned base = 0;
-    if ((int)lane_id() == leader) base = atomicAdd(n_groups, (unsigned)__popc(m));
-    base = __shfl_sync(m, base, leader);
-    groups[base + __popc(m & lanemask_lt())] = make_uint2(first, count);
+    const unsigned lane = lane_id(), w = threadIdx.x >> 5;
+    unsigned inc = want;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const unsigned t = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= (unsigned)o) inc += t;
+    }
+    if (lane == 31) s_warp[w] = inc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned tot = 0;
+        for (int i = 0; i < BLOCK / 32; ++i) {
+            const unsigned c = s_warp[i];
+            s_warp[i] = tot;
+            tot += c;
+        }
+        *s_base = tot ? atomicAdd(n_groups, tot) : 0u;
+    }
+    __syncthreads();
+    return *s_base + s_warp[w] + inc - want;
 }
 
-// Refit in two regimes, one kernel:
-//  * TREELETS: a node whose leaf range has at most 32 leaves gets both child boxes straight from the leaf boxes of its
-//    range (a Karras node knows its range and its split, so no other node's result is needed): no atomics, no fences.
-//    A block owns 256 consecutive node indices; since node i lies inside its own range, every such range falls inside
-//    the block's leaf window [i0-32, i0+288), which is gathered ONCE into shared memory with all loads in flight at once.
-//  * ABOVE THE TREELETS: the maximal treelets ("group roots", which are also the traversal's query groups) carry their
-//    box upwards with the classic arrival-counter scheme: the first thread to reach a node parks its box in the node and
-//    leaves, the second one merges and continues.  Only ~nf/16 nodes are refit this way.
+// what a group root carries upwards: its box and its parent word
+struct __align__(64) group_up_t {
+    double box[6];
+    uint32_t pw;
+    uint32_t pad[3];
+};
+
+// Refit in two regimes, two kernels:
+//  * k_refit_treelets: a node whose leaf range has at most 32 leaves gets both child boxes straight from the leaf boxes
+//    of its range (a Karras node knows its range and its split, so no other node's result is needed): no atomics, no
+//    fences.  A block owns 256 consecutive node indices; node i lies inside its own range, so every such range falls in
+//    the block's leaf window [i0-32, i0+288), gathered ONCE into shared memory with all loads in flight at once.  The
+//    maximal treelets ("group roots") are listed: they are the traversal's query groups and the starting points of ...
+//  * k_refit_climb: ... the classic atomic bottom-up pass for the ~nf/16 nodes above the treelets: one thread per group
+//    root carries its box upwards; the first thread to reach a node parks its box there and leaves, the second one
+//    merges and continues.  All climbers are resident at once, so the pass costs (levels above the treelets) x (one
+//    store / fence / atomic / load round trip), not a block-scheduling queue.
 constexpr int RHALO = 32;
 constexpr int RWIN = BLOCK + 2 * RHALO;
 
-__global__ void __launch_bounds__(BLOCK) k_refit(const double* __restrict__ face_bbox, const uint32_t* __restrict__ sorted_faces,
-    uint32_t nf, bvh_node_t* nodes, const uint4* __restrict__ meta, const uint32_t* __restrict__ parent, unsigned* flags,
-    uint2* __restrict__ groups, unsigned* __restrict__ n_groups)
+__global__ void __launch_bounds__(BLOCK) k_refit_treelets(const double* __restrict__ face_bbox,
+    const uint32_t* __restrict__ sorted_faces, uint32_t nf, bvh_node_t* nodes, const uint4* __restrict__ meta,
+    const uint32_t* __restrict__ parent, uint2* __restrict__ groups, group_up_t* __restrict__ group_up,
+    unsigned* __restrict__ n_groups)
 {
     __shared__ double s_box[RWIN][6];
     if (nf == 1) {
@@ -281,93 +324,118 @@ __global__ void __launch_bounds__(BLOCK) k_refit(const double* __restrict__ face
             nodes[0].first = 0;
             nodes[0].last = 0;
             groups[0] = make_uint2(0u, 1u);
+            group_up[0].pw = MCB200_NULL;
             *n_groups = 1u;
         }
         return;
     }
-    for (uint32_t i0 = blockIdx.x * BLOCK; i0 < nf; i0 += gridDim.x * BLOCK) {
-        __syncthreads();
-        for (int r = threadIdx.x; r < RWIN; r += BLOCK) {
-            const long long j = (long long)i0 - RHALO + r;
-            if (j >= 0 && j < (long long)nf) {
-                double b[6];
-                load_face_box(face_bbox, __ldg(sorted_faces + j), b);
+    const uint32_t i0 = blockIdx.x * BLOCK;
+    for (int r = threadIdx.x; r < RWIN; r += BLOCK) {
+        const long long j = (long long)i0 - RHALO + r;
+        if (j >= 0 && j < (long long)nf) {
+            double b[6];
+            load_face_box(face_bbox, __ldg(sorted_faces + j), b);
 #pragma unroll
-                for (int k = 0; k < 6; ++k) s_box[r][k] = b[k];
+            for (int k = 0; k < 6; ++k) s_box[r][k] = b[k];
+        }
+    }
+    __syncthreads();
+    const uint32_t i = i0 + threadIdx.x;
+    const int wbase = (int)i0 - RHALO; // leaf j sits in s_box[j - wbase]
+    __shared__ unsigned s_warp[BLOCK / 32], s_base;
+    // role 0: internal node i
+    bool root0 = false, root1 = false;
+    double box[6];
+    uint32_t pw0 = 0, pw1 = 0, first = 0, count = 0;
+    if (i < nf - 1u) {
+        const uint4 m = __ldg(meta + i);
+        first = m.z;
+        const uint32_t last = m.w;
+        count = last - first + 1u;
+        if (count <= 32u) {
+            const uint32_t gamma = m.x & ~MCB_LEAF_BIT;
+            double rb[6];
+#pragma unroll
+            for (int k = 0; k < 6; ++k) {
+                box[k] = s_box[(int)first - wbase][k];
+                rb[k] = s_box[(int)gamma + 1 - wbase][k];
+            }
+            for (uint32_t j = first + 1u; j <= gamma; ++j)
+#pragma unroll
+                for (int k = 0; k < 3; ++k) {
+                    box[k] = ref_min(box[k], s_box[(int)j - wbase][k]);
+                    box[3 + k] = ref_max(box[3 + k], s_box[(int)j - wbase][3 + k]);
+                }
+            for (uint32_t j = gamma + 2u; j <= last; ++j)
+#pragma unroll
+                for (int k = 0; k < 3; ++k) {
+                    rb[k] = ref_min(rb[k], s_box[(int)j - wbase][k]);
+                    rb[3 + k] = ref_max(rb[3 + k], s_box[(int)j - wbase][3 + k]);
+                }
+            store_box(nodes[i].lbox, box);
+            store_box(nodes[i].rbox, rb);
+            pw0 = (i == 0u) ? MCB200_NULL : __ldg(parent + i);
+            root0 = (i == 0u) || (pw0 & 2u); // a maximal treelet (or the whole tree)
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                box[k] = ref_min(box[k], rb[k]);
+                box[3 + k] = ref_max(box[3 + k], rb[3 + k]);
             }
         }
-        __syncthreads();
-        const uint32_t i = i0 + threadIdx.x;
-        const int wbase = (int)i0 - RHALO; // leaf j sits in s_box[j - wbase]
-        // two roles per thread: internal node i (if any) and leaf i (if any)
-#pragma unroll 1
-        for (int role = 0; role < 2; ++role) {
-            double box[6];
-            uint32_t pw;
-            if (role == 0) {
-                if (i >= nf - 1u) continue;
-                const uint4 m = __ldg(meta + i);
-                const uint32_t first = m.z, last = m.w, count = last - first + 1u;
-                if (count > 32u) continue;
-                const uint32_t gamma = m.x & ~MCB_LEAF_BIT;
-                double rb[6];
+    }
+    // role 1: leaf i, when it hangs directly under a node that covers more than 32 leaves
+    if (i < nf) {
+        pw1 = __ldg(parent + (nf - 1u + i));
+        root1 = (pw1 & 2u) != 0u;
+    }
+    unsigned g = alloc_groups_block(n_groups, (root0 ? 1u : 0u) + (root1 ? 1u : 0u), s_warp, &s_base);
+    if (root0) {
+        groups[g] = make_uint2(first, count);
+        store_box(group_up[g].box, box);
+        group_up[g].pw = pw0;
+        ++g;
+    }
+    if (root1) {
+        groups[g] = make_uint2(i, 1u);
+        double lb[6];
 #pragma unroll
-                for (int k = 0; k < 6; ++k) {
-                    box[k] = s_box[(int)first - wbase][k];
-                    rb[k] = s_box[(int)gamma + 1 - wbase][k];
-                }
-                for (uint32_t j = first + 1u; j <= gamma; ++j)
+        for (int k = 0; k < 6; ++k) lb[k] = s_box[(int)i - wbase][k];
+        store_box(group_up[g].box, lb);
+        group_up[g].pw = pw1;
+    }
+}
+
+__global__ void __launch_bounds__(BLOCK) k_refit_climb(bvh_node_t* nodes, const uint32_t* __restrict__ parent, unsigned* flags,
+    const group_up_t* __restrict__ group_up, const unsigned* __restrict__ n_groups)
+{
+    const unsigned ng = *n_groups;
+    for (unsigned g = blockIdx.x * BLOCK + threadIdx.x; g < ng; g += gridDim.x * BLOCK) {
+        uint32_t pw = group_up[g].pw;
+        if (pw == MCB200_NULL) continue; // the whole tree was one treelet
+        double box[6];
+        {
+            const double2* in = reinterpret_cast<const double2*>(group_up[g].box);
+            const double2 a = in[0], b = in[1], c = in[2];
+            box[0] = a.x; box[1] = a.y; box[2] = b.x; box[3] = b.y; box[4] = c.x; box[5] = c.y;
+        }
+        for (;;) {
+            const uint32_t p = pw >> 2;
+            bvh_node_t* nd = nodes + p;
+            const bool is_left = !(pw & 1u);
+            const uint32_t next_pw = (p == 0u) ? MCB200_NULL : __ldg(parent + p); // in flight while the fence drains
+            store_box(is_left ? nd->lbox : nd->rbox, box);
+            __threadfence();
+            const unsigned arrived = atomicAdd(flags + p, 1u);
+            if (arrived == 0) break; // sibling subtree not finished yet; its thread will continue from here
+            double sib[6];
+            load_box_cg(is_left ? nd->rbox : nd->lbox, sib);
 #pragma unroll
-                    for (int k = 0; k < 3; ++k) {
-                        box[k] = ref_min(box[k], s_box[(int)j - wbase][k]);
-                        box[3 + k] = ref_max(box[3 + k], s_box[(int)j - wbase][3 + k]);
-                    }
-                for (uint32_t j = gamma + 2u; j <= last; ++j)
-#pragma unroll
-                    for (int k = 0; k < 3; ++k) {
-                        rb[k] = ref_min(rb[k], s_box[(int)j - wbase][k]);
-                        rb[3 + k] = ref_max(rb[3 + k], s_box[(int)j - wbase][3 + k]);
-                    }
-                store_box(nodes[i].lbox, box);
-                store_box(nodes[i].rbox, rb);
-                if (i == 0u) { // the whole tree is one treelet
-                    append_group(groups, n_groups, first, count);
-                    continue;
-                }
-                pw = __ldg(parent + i);
-                if (!(pw & 2u)) continue; // inside a bigger treelet
-                append_group(groups, n_groups, first, count);
-#pragma unroll
-                for (int k = 0; k < 3; ++k) {
-                    box[k] = ref_min(box[k], rb[k]);
-                    box[3 + k] = ref_max(box[3 + k], rb[3 + k]);
-                }
-            } else {
-                if (i >= nf) continue;
-                pw = __ldg(parent + (nf - 1u + i));
-                if (!(pw & 2u)) continue; // its parent's thread covers it
-                append_group(groups, n_groups, i, 1u);
-#pragma unroll
-                for (int k = 0; k < 6; ++k) box[k] = s_box[(int)i - wbase][k];
+            for (int k = 0; k < 3; ++k) {
+                box[k] = ref_min(box[k], sib[k]);
+                box[3 + k] = ref_max(box[3 + k], sib[3 + k]);
             }
-            for (;;) {
-                const uint32_t p = pw >> 2;
-                bvh_node_t* nd = nodes + p;
-                const bool is_left = !(pw & 1u);
-                store_box(is_left ? nd->lbox : nd->rbox, box);
-                __threadfence();
-                const unsigned arrived = atomicAdd(flags + p, 1u);
-                if (arrived == 0) break; // sibling subtree not finished yet; its thread will continue from here
-                double sib[6];
-                load_box_cg(is_left ? nd->rbox : nd->lbox, sib);
-#pragma unroll
-                for (int k = 0; k < 3; ++k) {
-                    box[k] = ref_min(box[k], sib[k]);
-                    box[3 + k] = ref_max(box[3 + k], sib[3 + k]);
-                }
-                if (p == 0) break; // root merged; the mesh AABB itself comes from K_aabb's reduction
-                pw = __ldg(parent + p);
-            }
+            if (p == 0u) break; // root merged; the mesh AABB itself comes from K_aabb's reduction
+            pw = next_pw;
         }
     }
 }
@@ -391,6 +459,7 @@ int lbvh_reserve(mcb200_ctx* ctx, mcb200_mesh* m)
     MCB_TRY(ctx->reserve(m->meta, sizeof(uint4) * (size_t)nf));
     MCB_TRY(ctx->reserve(m->flags, sizeof(unsigned) * (size_t)nf));
     MCB_TRY(ctx->reserve(m->groups, sizeof(uint2) * (size_t)nf + sizeof(unsigned) * 4));
+    MCB_TRY(ctx->reserve(m->group_up, sizeof(group_up_t) * (size_t)nf));
     MCB_TRY((rsort::reserve_scratch<uint32_t>(ctx, nf, 4, true, true)));
     return 0;
 }
@@ -418,14 +487,16 @@ int lbvh_build(mcb200_ctx* ctx, mcb200_mesh* m, double eps)
     else
         MCB_LAUNCH(ctx, k_face_bbox<false>, grid, BLOCK, 0, m->d_xyz, m->frame, m->d_face_vtx, m->d_face_off, nf, eps,
             m->face_bbox.as<double>(), root_ord);
-    MCB_LAUNCH(ctx, k_morton, grid, BLOCK, 0, m->face_bbox.as<double>(), nf, root_ord, root_dec, m->codes.as<uint32_t>(),
-        m->sorted_codes.as<uint32_t>());
-
     // (code, face) ascending by code: in = sorted_codes (values implicit 0..nf-1), ping-pong scratch <-> mesh arrays;
-    // four passes end in the mesh's own arrays
+    // four passes end in the mesh's own arrays.  The histograms come out of k_morton.
     const rsort::pass_desc pd = rsort::make_passes(0, 32);
+    MCB_TRY(rsort::sort_prepare(ctx));
+    constexpr int SORT_TILE = rsort::THREADS * rsort::items_for<uint32_t>::value;
+    const unsigned status_words = (unsigned)(((size_t)nf + SORT_TILE - 1) / SORT_TILE) * rsort::RADIX * (unsigned)pd.npasses;
+    MCB_LAUNCH(ctx, k_morton, grid, BLOCK, 0, m->face_bbox.as<double>(), nf, root_ord, root_dec, m->codes.as<uint32_t>(),
+        m->sorted_codes.as<uint32_t>(), sc.hist.as<unsigned>(), sc.status.as<unsigned>(), status_words);
     uint32_t *kout = nullptr, *vout = nullptr;
-    MCB_TRY((rsort::sort<uint32_t, uint32_t, true>(ctx, m->sorted_codes.as<uint32_t>(), sc.keys_alt.as<uint32_t>(),
+    MCB_TRY((rsort::sort_passes<uint32_t, uint32_t, true>(ctx, m->sorted_codes.as<uint32_t>(), sc.keys_alt.as<uint32_t>(),
         m->sorted_codes.as<uint32_t>(), nullptr, sc.vals_alt.as<uint32_t>(), m->sorted_faces.as<uint32_t>(), nullptr, nf, pd, &kout,
         &vout)));
     if (kout != m->sorted_codes.as<uint32_t>() || vout != m->sorted_faces.as<uint32_t>()) {
@@ -437,9 +508,17 @@ int lbvh_build(mcb200_ctx* ctx, mcb200_mesh* m, double eps)
         MCB_LAUNCH(ctx, k_karras, g2, BLOCK, 0, m->sorted_codes.as<uint32_t>(), nf, m->nodes.as<bvh_node_t>(), m->meta.as<uint4>(),
             m->parent.as<uint32_t>());
     }
-    MCB_LAUNCH(ctx, k_refit, div_up(nf, BLOCK), BLOCK, 0, m->face_bbox.as<double>(), m->sorted_faces.as<uint32_t>(), nf,
-        m->nodes.as<bvh_node_t>(), m->meta.as<uint4>(), m->parent.as<uint32_t>(), m->flags.as<unsigned>(), m->groups.as<uint2>(),
-        n_groups);
+    MCB_LAUNCH(ctx, k_refit_treelets, div_up(nf, BLOCK), BLOCK, 0, m->face_bbox.as<double>(), m->sorted_faces.as<uint32_t>(), nf,
+        m->nodes.as<bvh_node_t>(), m->meta.as<uint4>(), m->parent.as<uint32_t>(), m->groups.as<uint2>(),
+        m->group_up.as<group_up_t>(), n_groups);
+    if (nf > 1) {
+        // enough threads for every group root to climb concurrently (about nf/16 of them; nf/4 is a safe bound for the grid,
+        // the kernel strides over the device-side count anyway)
+        const unsigned want = div_up((size_t)nf / 4u + 1u, BLOCK);
+        const unsigned gc = want < max_grid ? want : max_grid;
+        MCB_LAUNCH(ctx, k_refit_climb, gc, BLOCK, 0, m->nodes.as<bvh_node_t>(), m->parent.as<uint32_t>(), m->flags.as<unsigned>(),
+            m->group_up.as<group_up_t>(), n_groups);
+    }
     m->built = true;
     m->groups_valid = true;
     m->eps = eps;

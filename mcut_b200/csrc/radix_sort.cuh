@@ -291,30 +291,28 @@ template <typename KeyT> int reserve_scratch(mcb200_ctx* ctx, size_t n_max, int 
     return 0;
 }
 
-// Sort n (or *d_n) keys [and values].  Pass 0 reads keys_in/vals_in, the passes then ping-pong between the (a) and (b)
-// buffers: in -> a -> b -> a ...  (b may alias the input when it may be overwritten).  *keys_out / *vals_out receive the
-// buffer the sorted data ended up in.  vals_in == nullptr with HAS_VALS: the value of element i is i.
+// A sort is: prepare (clear histogram + tile tickets), histogram of every pass (k_histogram, or fused into the kernel
+// that produces the keys — see lbvh.cu: k_morton), then one sweep per pass.
+inline int sort_prepare(mcb200_ctx* ctx)
+{
+    mcb200_ctx::sort_scratch_t& sc = ctx->sc();
+    MCB_CUDA(ctx, cudaMemsetAsync(sc.hist.p, 0, sizeof(unsigned) * MAX_PASSES * RADIX, ctx->cur));
+    MCB_CUDA(ctx, cudaMemsetAsync(sc.tilectr.p, 0, sizeof(unsigned) * MAX_PASSES, ctx->cur));
+    return 0;
+}
+
+// Pass 0 reads keys_in/vals_in, the passes then ping-pong between the (a) and (b) buffers: in -> a -> b -> a ...
+// (b may alias the input when it may be overwritten).  *keys_out / *vals_out receive the buffer the sorted data ended up
+// in.  vals_in == nullptr with HAS_VALS: the value of element i is i.
 template <typename KeyT, typename ValT, bool HAS_VALS>
-int sort(mcb200_ctx* ctx, const KeyT* keys_in, KeyT* keys_a, KeyT* keys_b, const ValT* vals_in, ValT* vals_a, ValT* vals_b,
+int sort_passes(mcb200_ctx* ctx, const KeyT* keys_in, KeyT* keys_a, KeyT* keys_b, const ValT* vals_in, ValT* vals_a, ValT* vals_b,
     const unsigned long long* d_n, size_t n_max, const pass_desc& pd, KeyT** keys_out, ValT** vals_out)
 {
     constexpr int ITEMS = items_for<KeyT>::value;
     constexpr int TILE = THREADS * ITEMS;
-    if (keys_out) *keys_out = const_cast<KeyT*>(keys_in);
-    if (vals_out) *vals_out = const_cast<ValT*>(vals_in);
-    if (n_max == 0 || pd.npasses == 0) return 0;
     const size_t tiles = (n_max + TILE - 1) / TILE;
-    MCB_TRY((reserve_scratch<KeyT>(ctx, n_max, pd.npasses, false, false)));
     mcb200_ctx::sort_scratch_t& sc = ctx->sc();
-    MCB_CUDA(ctx, cudaMemsetAsync(sc.hist.p, 0, sizeof(unsigned) * MAX_PASSES * RADIX, ctx->cur));
-    MCB_CUDA(ctx, cudaMemsetAsync(sc.tilectr.p, 0, sizeof(unsigned) * MAX_PASSES, ctx->cur));
-
-    const unsigned hgrid = (unsigned)((tiles < (size_t)ctx->num_sms * 4) ? tiles : (size_t)ctx->num_sms * 4);
-    const char* hname = sizeof(KeyT) == 4 ? "sort_histogram_u32" : "sort_histogram_u64";
     const char* pname = sizeof(KeyT) == 4 ? "onesweep_pass_u32_kv" : (HAS_VALS ? "onesweep_pass_u64_kv" : "onesweep_pass_u64_k");
-    MCB_LAUNCH_NAMED(ctx, hname, (k_histogram<KeyT>), hgrid, THREADS, 0, keys_in, d_n, n_max, pd, TILE, sc.hist.as<unsigned>(),
-        sc.status.as<unsigned>());
-
     // persistent grid: enough resident blocks to fill the machine, never more than tiles
     const unsigned pgrid = (unsigned)((tiles < (size_t)ctx->num_sms * 4) ? tiles : (size_t)ctx->num_sms * 4);
     const KeyT* kin = keys_in;
@@ -330,6 +328,25 @@ int sort(mcb200_ctx* ctx, const KeyT* keys_in, KeyT* keys_a, KeyT* keys_b, const
     if (keys_out) *keys_out = const_cast<KeyT*>(kin);
     if (vals_out) *vals_out = const_cast<ValT*>(vin);
     return 0;
+}
+
+template <typename KeyT, typename ValT, bool HAS_VALS>
+int sort(mcb200_ctx* ctx, const KeyT* keys_in, KeyT* keys_a, KeyT* keys_b, const ValT* vals_in, ValT* vals_a, ValT* vals_b,
+    const unsigned long long* d_n, size_t n_max, const pass_desc& pd, KeyT** keys_out, ValT** vals_out)
+{
+    constexpr int TILE = THREADS * items_for<KeyT>::value;
+    if (keys_out) *keys_out = const_cast<KeyT*>(keys_in);
+    if (vals_out) *vals_out = const_cast<ValT*>(vals_in);
+    if (n_max == 0 || pd.npasses == 0) return 0;
+    const size_t tiles = (n_max + TILE - 1) / TILE;
+    MCB_TRY((reserve_scratch<KeyT>(ctx, n_max, pd.npasses, false, false)));
+    MCB_TRY(sort_prepare(ctx));
+    mcb200_ctx::sort_scratch_t& sc = ctx->sc();
+    const unsigned hgrid = (unsigned)((tiles < (size_t)ctx->num_sms * 4) ? tiles : (size_t)ctx->num_sms * 4);
+    const char* hname = sizeof(KeyT) == 4 ? "sort_histogram_u32" : "sort_histogram_u64";
+    MCB_LAUNCH_NAMED(ctx, hname, (k_histogram<KeyT>), hgrid, THREADS, 0, keys_in, d_n, n_max, pd, TILE, sc.hist.as<unsigned>(),
+        sc.status.as<unsigned>());
+    return sort_passes<KeyT, ValT, HAS_VALS>(ctx, keys_in, keys_a, keys_b, vals_in, vals_a, vals_b, d_n, n_max, pd, keys_out, vals_out);
 }
 
 } // namespace rsort

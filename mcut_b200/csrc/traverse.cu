@@ -108,13 +108,14 @@ __global__ void __launch_bounds__(TBLOCK) k_traverse(traverse_args_t a)
     unsigned nout = 0;
     unsigned long long ntests = 0;
 
-    for (;;) {
-        uint32_t g0 = 0;
-        if (lane == 0) g0 = atomicAdd(&a.counters->work_counter, (unsigned)GROUP_BATCH);
-        g0 = __shfl_sync(0xffffffffu, g0, 0);
-        if (g0 >= ngroups) break;
-        const uint32_t g1 = (g0 + GROUP_BATCH < ngroups) ? g0 + GROUP_BATCH : ngroups;
-        for (uint32_t g = g0; g < g1; ++g) {
+    // Groups are dealt to warps round-robin (static): the group list is in scheduling order of the refit kernel, so
+    // neighbouring entries are unrelated and the deal balances itself; a global ticket per group would put tens of
+    // thousands of same-address atomics on the critical path.
+    const uint32_t warp_global = (blockIdx.x * TBLOCK + threadIdx.x) >> 5;
+    const uint32_t nwarps = (gridDim.x * TBLOCK) >> 5;
+    {
+        {
+            for (uint32_t g = warp_global; g < ngroups; g += nwarps) {
             const uint2 grp = __ldg(a.groups + g);
             if (a.shard_nparts > 1 && (grp.x / a.shard_chunk) % a.shard_nparts != a.shard_part) continue;
             // ---- lane-resident query leaf + the group's union box ----
@@ -214,6 +215,7 @@ __global__ void __launch_bounds__(TBLOCK) k_traverse(traverse_args_t a)
                 __syncwarp();
             }
             if (ncand) drain_candidates(ws, 0, ncand, mybox, valid, myface, nout, ntests, a);
+            }
         }
     }
     flush_out(ws, nout, a);
