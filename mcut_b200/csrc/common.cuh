@@ -183,6 +183,14 @@ static_assert(sizeof(bvh_node_t) == 128, "bvh_node_t must be one 128-byte line")
 
 #define MCB_LEAF_BIT 0x80000000u
 
+// What a group root (a maximal treelet of <= 32 leaves) carries: its union box and its parent word.  Written by the
+// refit, read by the atomic climb and — as the query box of the group — by the traversal.
+struct __align__(64) group_up_t {
+    double box[6];
+    uint32_t pw;
+    uint32_t pad[3];
+};
+
 struct mcb200_soup {
     uint32_t nsf = 0, ncf = 0, nh = 0, ne = 0;
     dbuf face_vtx; // [nh] ps vertex ids in ps.get_vertices_around_face order

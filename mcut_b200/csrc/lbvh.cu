@@ -285,13 +285,6 @@ __device__ __forceinline__ unsigned alloc_groups_block(unsigned* n_groups, unsig
     return *s_base + s_warp[w] + inc - want;
 }
 
-// what a group root carries upwards: its box and its parent word
-struct __align__(64) group_up_t {
-    double box[6];
-    uint32_t pw;
-    uint32_t pad[3];
-};
-
 // Refit in two regimes, two kernels:
 //  * k_refit_treelets: a node whose leaf range has at most 32 leaves gets both child boxes straight from the leaf boxes
 //    of its range (a Karras node knows its range and its split, so no other node's result is needed): no atomics, no
@@ -324,6 +317,7 @@ __global__ void __launch_bounds__(BLOCK) k_refit_treelets(const double* __restri
             nodes[0].first = 0;
             nodes[0].last = 0;
             groups[0] = make_uint2(0u, 1u);
+            store_box(group_up[0].box, b);
             group_up[0].pw = MCB200_NULL;
             *n_groups = 1u;
         }

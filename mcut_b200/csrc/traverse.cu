@@ -41,6 +41,7 @@ struct traverse_args_t {
     const uint32_t* q_sorted_faces;
     uint32_t q_nf;
     const uint2* groups; // (first sorted leaf, leaf count <= 32)
+    const group_up_t* group_box; // union box of each group (written by the refit)
     const unsigned* n_groups;
     const double* t_root; // mesh AABB of the tree side (6 doubles)
     // tree side
@@ -116,43 +117,41 @@ __global__ void __launch_bounds__(TBLOCK) k_traverse(traverse_args_t a)
     {
         {
             for (uint32_t g = warp_global; g < ngroups; g += nwarps) {
+            // ---- one load round trip per group: descriptor + union box (from the refit).  The 32 leaf boxes are fetched
+            // only if the walk finds a candidate leaf at all — for most groups it does not ----
             const uint2 grp = __ldg(a.groups + g);
+            double gbox[6];
+            {
+                const double2* in = reinterpret_cast<const double2*>(a.group_box[g].box);
+                const double2 x = __ldg(in), y = __ldg(in + 1), z = __ldg(in + 2);
+                gbox[0] = x.x; gbox[1] = x.y; gbox[2] = y.x; gbox[3] = y.y; gbox[4] = z.x; gbox[5] = z.y;
+            }
             if (a.shard_nparts > 1 && (grp.x / a.shard_chunk) % a.shard_nparts != a.shard_part) continue;
-            // ---- lane-resident query leaf + the group's union box ----
+            ntests += 1ull;
+            if (!overlap6(gbox, troot)) continue;
             const uint32_t q = grp.x + lane;
             const bool valid = lane < grp.y;
+            bool have_leaf = false;
             uint32_t myface = 0;
             double mybox[6] = { DBL_MAX, DBL_MAX, DBL_MAX, -DBL_MAX, -DBL_MAX, -DBL_MAX };
-            if (valid) {
-                myface = __ldg(a.q_sorted_faces + q);
-                const double2* in = reinterpret_cast<const double2*>(a.q_face_bbox + 6 * (size_t)myface);
-                const double2 x = __ldg(in), y = __ldg(in + 1), z = __ldg(in + 2);
-                mybox[0] = x.x;
-                mybox[1] = x.y;
-                mybox[2] = y.x;
-                mybox[3] = y.y;
-                mybox[4] = z.x;
-                mybox[5] = z.y;
-            }
-            double gbox[6];
-#pragma unroll
-            for (int k = 0; k < 3; ++k) {
-                double mn = mybox[k], mx = mybox[3 + k];
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1) {
-                    mn = fmin(mn, __shfl_xor_sync(0xffffffffu, mn, o));
-                    mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+            auto fetch_leaf = [&]() {
+                if (have_leaf) return;
+                have_leaf = true;
+                if (valid) {
+                    myface = __ldg(a.q_sorted_faces + q);
+                    const double2* in = reinterpret_cast<const double2*>(a.q_face_bbox + 6 * (size_t)myface);
+                    const double2 x = __ldg(in), y = __ldg(in + 1), z = __ldg(in + 2);
+                    mybox[0] = x.x; mybox[1] = x.y; mybox[2] = y.x; mybox[3] = y.y; mybox[4] = z.x; mybox[5] = z.y;
                 }
-                gbox[k] = mn;
-                gbox[3 + k] = mx;
-            }
+            };
 
             // ---- walk the tree ----
-            unsigned size = overlap6(gbox, troot) ? 1u : 0u, ncand = 0;
+            unsigned size = 1u, ncand = 0;
             if (lane == 0) ws.stack[0] = 0u;
             __syncwarp();
             while (size > 0) {
                 while (ncand > 32) { // keep room for the up-to-64 leaves one step can add (CAND_CAP = 32 + 64)
+                    fetch_leaf();
                     drain_candidates(ws, ncand - 32, 32, mybox, valid, myface, nout, ntests, a);
                     ncand -= 32;
                 }
@@ -214,7 +213,10 @@ __global__ void __launch_bounds__(TBLOCK) k_traverse(traverse_args_t a)
                 }
                 __syncwarp();
             }
-            if (ncand) drain_candidates(ws, 0, ncand, mybox, valid, myface, nout, ntests, a);
+            if (ncand) {
+                fetch_leaf();
+                drain_candidates(ws, 0, ncand, mybox, valid, myface, nout, ntests, a);
+            }
             }
         }
     }
@@ -295,6 +297,7 @@ int traverse_pairs(mcb200_ctx* ctx, const mcb200_mesh* src, const mcb200_mesh* c
     // query groups = the maximal <=32-leaf treelets of the query mesh's own tree, listed by its refit kernel
     a.groups = q->groups.as<uint2>();
     a.n_groups = reinterpret_cast<const unsigned*>(q->groups.as<uint2>() + q->nf);
+    a.group_box = q->group_up.as<group_up_t>();
     a.t_root = reinterpret_cast<const double*>(t->root.as<unsigned long long>() + 6);
 
     // a persistent grid sized for the machine; groups are handed out by an atomic ticket
