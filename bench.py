@@ -223,11 +223,16 @@ def algorithmic_bytes(kname: str, src_nv, src_nf, cut_nv, cut_nf, counts, vbytes
         "k_face_bbox<true>": vbytes * V + 12 * F + 48 * F,
         "k_face_bbox<false>": vbytes * V + 12 * F + 48 * F,
         "k_morton": 48 * F + 8 * F,  # box in, code out twice (by face + sort key)
-        "(rsort::k_histogram<KeyT>)": None,  # filled per key type below
-        "k_karras": 4 * F + 16 * F + 8 * F,  # codes in, children/range + parents out
-        "k_refit": 48 * F + 4 * F + 2 * 48 * F + 48 * F,  # leaf box + id in, every node box written once, sibling read once
+        "onesweep_pass_u32_kv": 16 * F,  # one radix pass: key + value read once, written once
+        "k_karras": 4 * F + 16 * F + 8 * F + 16 * F,  # codes in; children/range in the node record + compact meta + parents out
+        # leaf box + face id in, the (31/32)F nodes inside the <=32-leaf treelets written once as 128-byte records
+        "k_refit_treelets": 48 * F + 4 * F + 128 * F * 31 / 32 + 64 * F / 32,
+        # the F/32 nodes above the treelets: group box in, node record out
+        "k_refit_climb": 64 * F / 32 + 128 * F / 32,
         "k_traverse": 48.0 * counts["n_node_tests"] + 8.0 * n_pairs,
-        "(k_tests<true,_false>)": 8.0 * n_pairs + 128.0 * n_tests,
+        "onesweep_pass_u64_k": 16.0 * n_pairs,
+        "k_tests_filter_tri": 8.0 * n_pairs + 128.0 * n_tests,
+        "k_tests_filter_poly": 8.0 * n_pairs + 128.0 * n_tests,
     }
     return table.get(kname)
 
@@ -360,29 +365,33 @@ def run_ours(args):
     res2 = stage.Result(ctx)
     d2h = {"bytes": 0}
 
+    from mcut_b200._lib import HostMesh, HostSoup
+    hm_src = HostMesh(0, host["sx"].ctypes.data, src_nv, host["sf"].ctypes.data, None, src_nf)
+    hm_cut = HostMesh(0, host["cx"].ctypes.data, cut_nv, host["cf"].ctypes.data, None, cut_nf)
+    h_soup = HostSoup(nh, ne, host["fe"].ctypes.data, host["ef"].ctypes.data)
+
     def step_e2e():
-        a = make_mesh(host["sx"], host["sf"], src_nv, src_nf)
-        b = make_mesh(host["cx"], host["cf"], cut_nv, cut_nf)
-        set_frame(a)
-        set_frame(b)
-        sp = make_soup()
-        ctx.check(L.mcb200_intersect_stage(ctx.h, a, b, eps, sp, res2.h, 0))
+        # ONE reference-facing call with host arrays: uploads are pipelined with the builds inside it
+        ctx.check(L.mcb200_intersect_stage_host(ctx.h, ctypes.byref(hm_src), ctypes.byref(hm_cut), com.ctypes.data_as(stage.c_dp),
+                                                shift.ctypes.data_as(stage.c_dp), None, eps, ctypes.byref(h_soup), res2.h, 0))
         cc = res2.counts()
         ctx.check(L.mcb200_result_read_pairs(ctx.h, res2.h, pairs_host.ctypes.data_as(stage.c_u64p), pairs_host.size))
         ctx.check(L.mcb200_result_read_records(ctx.h, res2.h, ctypes.cast(rec_host.ctypes.data, ctypes.POINTER(stage.Record)),
                                                rec_host.size // 4))
         d2h["bytes"] = int(cc.n_pairs) * 8 + int(cc.n_records) * 32 + 128
-        L.mcb200_soup_free(ctx.h, sp)
-        L.mcb200_mesh_free(ctx.h, a)
-        L.mcb200_mesh_free(ctx.h, b)
+        d2h["pairs"] = int(cc.n_pairs)
+        d2h["records"] = int(cc.n_records)
 
     e2e_steps = max(3, min(args.steps, 10))
     e2e_total = timed_loop(step_e2e, e2e_steps, max(args.warmup, 3), flush=False)
     e2e_ms = e2e_total / e2e_steps
-    h2d = sum(host[k].nbytes for k in ("sx", "sf", "cx", "cf", "fv", "fe", "ef"))
+    assert d2h["pairs"] == counts["n_pairs"] and d2h["records"] == counts["n_records"], "host-array path disagrees with the resident path"
+    h2d = sum(host[k].nbytes for k in ("sx", "sf", "cx", "cf", "fe", "ef"))
     e2e = {"value": world * counts["n_pairs"] / (e2e_ms * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms,
            "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h["bytes"]),
-           "note": "inputs = both meshes + polygon-soup topology from pinned host memory; outputs = sorted pairs, registry records, status"}
+           "call": "mcb200_intersect_stage_host",
+           "note": "inputs = both meshes + polygon-soup edge ids from pinned host memory (uploads pipelined with the builds on a copy "
+                   "stream); outputs = sorted pairs, registry records, status"}
 
     # ---- per-kernel device times (separate pass, event pair around every launch) -> roofline of the dominant kernel ----
     prof_steps = max(3, min(args.steps, 10))
@@ -410,17 +419,15 @@ def run_ours(args):
                     "ms_per_launch": kern[name]["ms_per_launch"], "share_of_step": kern[name]["ms_per_step"] / step_kernel_ms}
         break
     # whole-build figure (B_build = 24V + 296F per mesh)
-    build_names = [k for k in kern if k in ("k_face_bbox<true>", "k_face_bbox<false>", "k_morton", "k_karras", "k_refit")
-                   or "rsort" in k]
     stage_ms = {
-        "build_ms": sum(kern[k]["ms_per_step"] for k in kern if k in ("k_face_bbox<true>", "k_morton", "k_karras", "k_refit")),
+        "build_ms": sum(kern[k]["ms_per_step"] for k in kern if k.startswith(("k_face_bbox", "k_morton", "k_karras", "k_refit"))
+                    or k == "onesweep_pass_u32_kv"),
         "traverse_ms": kern.get("k_traverse", {}).get("ms_per_step", 0.0),
         "narrowphase_ms": sum(kern[k]["ms_per_step"] for k in kern if "k_tests" in k or "k_planes" in k),
-        "sort_ms": sum(kern[k]["ms_per_step"] for k in kern if "rsort" in k),
+        "pair_and_record_sort_ms": sum(kern[k]["ms_per_step"] for k in kern if "u64" in k),
         "other_ms": sum(kern[k]["ms_per_step"] for k in kern if "k_make_keys" in k or "k_gather" in k),
         "sum_of_kernels_ms": step_kernel_ms,
     }
-    del build_names
 
     # ---- sharded single dispatch (N > 1): leaf-range split + NCCL all-gather of pairs / records ----
     sharded = None

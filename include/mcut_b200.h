@@ -137,6 +137,10 @@ int mcb200_bvh_intersect(mcb200_ctx* ctx, const mcb200_mesh* src, const mcb200_m
  * chunks of `chunk` consecutive Morton-ordered leaves are dealt round-robin, this call handles the chunks with
  * index % nparts == part.  nparts == 1 restores the full range. */
 int mcb200_result_set_shard(mcb200_ctx* ctx, mcb200_result* res, uint32_t part, uint32_t nparts, uint32_t chunk);
+/* Size the candidate-pair buffer up front (default: 4 x (Fs + Fc), at least 2^20).  The reference's own container is a
+ * growing vector (bvh.cpp:638-720); here an overflowing run is reported by mcb200_result_counts with
+ * MCB200_ERR_CAPACITY, which also raises the capacity to what the run needed so the caller simply runs the stage again. */
+int mcb200_result_set_pair_capacity(mcb200_ctx* ctx, mcb200_result* res, uint64_t max_pairs);
 
 /* ---------------------------------------------------------------- (3) narrowphase -------------------------- */
 int mcb200_soup_create(mcb200_ctx* ctx, uint32_t nsf, uint32_t ncf, uint32_t nh, uint32_t ne, const uint32_t* face_vtx,
@@ -154,6 +158,29 @@ int mcb200_narrowphase(mcb200_ctx* ctx, const mcb200_soup* soup, const mcb200_me
 
 /* build(src) + build(cut) + intersect + narrowphase, nothing but kernel launches in between */
 int mcb200_intersect_stage(mcb200_ctx* ctx, mcb200_mesh* src, mcb200_mesh* cut, double cut_eps, const mcb200_soup* soup,
+    mcb200_result* res, uint32_t flags);
+
+/* The same stage straight from HOST arrays, with the uploads pipelined against the kernels on a copy stream: the source
+ * build starts as soon as the source mesh has landed, the cut build overlaps the polygon-soup upload, and the narrowphase
+ * waits for the soup only.  Pin the arrays (cudaHostAlloc / torch pin_memory) to get the overlap; pageable memory works
+ * but serialises.  The polygon-soup vertex lists are derived on the device from the face arrays (rotation rules of
+ * hmesh.cpp:705-733), so only face_edge / edge_f travel.  Meshes and soup live in context-owned staging buffers that
+ * are reused from call to call.  soup == NULL: the ids are computed here with mcb200_soup_ids. */
+typedef struct mcb200_host_mesh {
+    int is_float; /* MC_DISPATCH_VERTEX_ARRAY_FLOAT */
+    const void* xyz; /* [nv*3] */
+    uint32_t nv;
+    const uint32_t* face_vtx;
+    const uint32_t* face_sizes; /* NULL: triangles */
+    uint32_t nf;
+} mcb200_host_mesh;
+typedef struct mcb200_host_soup {
+    uint32_t nh, ne;
+    const uint32_t* face_edge; /* [nh] */
+    const uint32_t* edge_f; /* [ne*2] */
+} mcb200_host_soup;
+int mcb200_intersect_stage_host(mcb200_ctx* ctx, const mcb200_host_mesh* src, const mcb200_host_mesh* cut, const double com[3],
+    const double shift[3], const double perturbation[3] /* or NULL */, double cut_eps, const mcb200_host_soup* soup,
     mcb200_result* res, uint32_t flags);
 
 /* ---------------------------------------------------------------- reading results (D2H, synchronising) ----- */

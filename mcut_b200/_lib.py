@@ -25,6 +25,15 @@ class Counts(C.Structure):
                 ("n_records", C.c_uint64), ("n_cand_faces", C.c_uint64), ("status", C.c_int32), ("bad_face", C.c_uint32)]
 
 
+class HostMesh(C.Structure):
+    _fields_ = [("is_float", C.c_int), ("xyz", C.c_void_p), ("nv", C.c_uint32), ("face_vtx", C.c_void_p), ("face_sizes", C.c_void_p),
+                ("nf", C.c_uint32)]
+
+
+class HostSoup(C.Structure):
+    _fields_ = [("nh", C.c_uint32), ("ne", C.c_uint32), ("face_edge", C.c_void_p), ("edge_f", C.c_void_p)]
+
+
 class Record(C.Structure):
     _fields_ = [("edge", C.c_uint32), ("face", C.c_uint32), ("point", C.c_double * 3)]
 
@@ -59,11 +68,14 @@ SYMBOLS = {
     "mcb200_result_free": (None, [vp, vp]),
     "mcb200_bvh_intersect": (C.c_int, [vp, vp, vp, vp]),
     "mcb200_result_set_shard": (C.c_int, [vp, vp, C.c_uint32, C.c_uint32, C.c_uint32]),
+    "mcb200_result_set_pair_capacity": (C.c_int, [vp, vp, C.c_uint64]),
     "mcb200_soup_create": (C.c_int, [vp, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, c_u32p, c_u32p, c_u32p, C.POINTER(vp)]),
     "mcb200_soup_free": (None, [vp, vp]),
     "mcb200_soup_from_meshes": (C.c_int, [vp, vp, vp, C.POINTER(vp)]),
     "mcb200_narrowphase": (C.c_int, [vp, vp, vp, vp, vp, C.c_uint32]),
     "mcb200_intersect_stage": (C.c_int, [vp, vp, vp, C.c_double, vp, vp, C.c_uint32]),
+    "mcb200_intersect_stage_host": (C.c_int, [vp, C.POINTER(HostMesh), C.POINTER(HostMesh), c_dp, c_dp, c_dp, C.c_double,
+                                             C.POINTER(HostSoup), vp, C.c_uint32]),
     "mcb200_result_counts": (C.c_int, [vp, vp, C.POINTER(Counts)]),
     "mcb200_result_read_pairs": (C.c_int, [vp, vp, c_u64p, C.c_size_t]),
     "mcb200_result_read_records": (C.c_int, [vp, vp, C.POINTER(Record), C.c_size_t]),

@@ -97,6 +97,8 @@ int mcb200_ctx_create(int device, void* stream, mcb200_ctx** out)
         delete ctx;
         return (int)e;
     }
+    cudaStreamCreateWithFlags(&ctx->copy, cudaStreamNonBlocking);
+    for (auto& ev : ctx->ev_up) cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
     cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming);
     cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming);
     cudaEventCreateWithFlags(&ctx->ev_fork2, cudaEventDisableTiming);
@@ -118,6 +120,16 @@ void mcb200_ctx_destroy(mcb200_ctx* ctx)
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     cudaStreamSynchronize(ctx->aux);
+    cudaStreamSynchronize(ctx->copy);
+    for (int k = 0; k < 2; ++k) {
+        if (ctx->st_mesh[k]) mcb200_mesh_free(ctx, ctx->st_mesh[k]);
+        ctx->release(ctx->st_xyz[k]);
+        ctx->release(ctx->st_fv[k]);
+        ctx->release(ctx->st_fo[k]);
+    }
+    if (ctx->st_soup) mcb200_soup_free(ctx, ctx->st_soup);
+    cudaStreamDestroy(ctx->copy);
+    for (auto& ev : ctx->ev_up) cudaEventDestroy(ev);
     for (auto& sc : ctx->scratch) {
         ctx->release(sc.keys_alt);
         ctx->release(sc.vals_alt);
@@ -407,6 +419,15 @@ int mcb200_result_set_shard(mcb200_ctx* ctx, mcb200_result* res, uint32_t part, 
     return 0;
 }
 
+int mcb200_result_set_pair_capacity(mcb200_ctx* ctx, mcb200_result* res, uint64_t max_pairs)
+{
+    if (!ctx || !res) return MCB200_ERR_INVALID;
+    if (max_pairs == 0) MCB_FAIL(ctx, MCB200_ERR_INVALID, "set_pair_capacity: capacity must be positive");
+    res->cap_pairs = (size_t)max_pairs;
+    res->h_valid = false;
+    return 0;
+}
+
 // ---------------------------------------------------------------------------------------------------------- (2) traversal
 
 int mcb200_bvh_intersect(mcb200_ctx* ctx, const mcb200_mesh* src, const mcb200_mesh* cut, mcb200_result* res)
@@ -553,6 +574,160 @@ int mcb200_intersect_stage(mcb200_ctx* ctx, mcb200_mesh* src, mcb200_mesh* cut, 
     return rc;
 }
 
+// Stage the host arrays of one mesh into the context-owned staging mesh `k` (0 source, 1 cut); copies go to ctx->copy.
+static int stage_mesh(mcb200_ctx* ctx, int k, const mcb200_host_mesh* hm)
+{
+    if (!hm || !hm->xyz || !hm->face_vtx || hm->nv == 0 || hm->nf == 0) MCB_FAIL(ctx, MCB200_ERR_INVALID, "stage_host: empty mesh or NULL array");
+    if (!ctx->st_mesh[k]) {
+        ctx->st_mesh[k] = new mcb200_mesh();
+        ctx->st_mesh[k]->owns_arrays = false;
+    }
+    mcb200_mesh* m = ctx->st_mesh[k];
+    m->nv = hm->nv;
+    m->nf = hm->nf;
+    m->is_float = hm->is_float ? 1 : 0;
+    m->is_tri = 1;
+    m->h_face_vtx.clear(); // host copies are only needed by mcb200_soup_from_meshes; the staged path never keeps them
+    m->h_face_off.clear();
+    uint32_t nh = 3u * hm->nf;
+    std::vector<uint32_t> off;
+    if (hm->face_sizes) {
+        off.resize((size_t)hm->nf + 1);
+        uint32_t acc = 0;
+        for (uint32_t f = 0; f < hm->nf; ++f) {
+            if (hm->face_sizes[f] < 3) MCB_FAIL(ctx, MCB200_ERR_INVALID, "stage_host: a face has fewer than 3 vertices");
+            if (hm->face_sizes[f] != 3) m->is_tri = 0;
+            off[f] = acc;
+            acc += hm->face_sizes[f];
+        }
+        off[hm->nf] = acc;
+        nh = acc;
+    }
+    m->nh = nh;
+    const size_t vbytes = (size_t)hm->nv * 3 * (hm->is_float ? sizeof(float) : sizeof(double));
+    MCB_TRY(ctx->reserve(ctx->st_xyz[k], vbytes));
+    MCB_TRY(ctx->reserve(ctx->st_fv[k], sizeof(uint32_t) * (size_t)nh));
+    if (!m->is_tri) MCB_TRY(ctx->reserve(ctx->st_fo[k], sizeof(uint32_t) * ((size_t)hm->nf + 1)));
+    // buffers come from the main stream's pool order: make the copy stream wait for that point
+    MCB_CUDA(ctx, cudaEventRecord(ctx->ev_fork, ctx->stream));
+    MCB_CUDA(ctx, cudaStreamWaitEvent(ctx->copy, ctx->ev_fork, 0));
+    MCB_CUDA(ctx, cudaMemcpyAsync(ctx->st_xyz[k].p, hm->xyz, vbytes, cudaMemcpyHostToDevice, ctx->copy));
+    MCB_CUDA(ctx, cudaMemcpyAsync(ctx->st_fv[k].p, hm->face_vtx, sizeof(uint32_t) * (size_t)nh, cudaMemcpyHostToDevice, ctx->copy));
+    if (!m->is_tri) {
+        // `off` is a local: this (small, polygon-only) copy must complete before it goes out of scope
+        MCB_CUDA(ctx, cudaMemcpyAsync(ctx->st_fo[k].p, off.data(), sizeof(uint32_t) * off.size(), cudaMemcpyHostToDevice, ctx->copy));
+        MCB_CUDA(ctx, cudaStreamSynchronize(ctx->copy));
+    }
+    MCB_CUDA(ctx, cudaEventRecord(ctx->ev_up[k], ctx->copy));
+    m->d_xyz = ctx->st_xyz[k].p;
+    m->d_face_vtx = ctx->st_fv[k].as<uint32_t>();
+    m->d_face_off = m->is_tri ? nullptr : ctx->st_fo[k].as<uint32_t>();
+    m->built = false;
+    return 0;
+}
+
+int mcb200_intersect_stage_host(mcb200_ctx* ctx, const mcb200_host_mesh* hsrc, const mcb200_host_mesh* hcut, const double com[3],
+    const double shift[3], const double perturbation[3], double cut_eps, const mcb200_host_soup* hsoup, mcb200_result* res,
+    uint32_t flags)
+{
+    if (!ctx || !hsrc || !hcut || !res) return MCB200_ERR_INVALID;
+    MCB_CUDA(ctx, cudaSetDevice(ctx->device));
+    // the previous call's kernels may still be reading the staging buffers
+    MCB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    ctx->use_main();
+    // ---- uploads, in the order the stage consumes them: source mesh, cut mesh, polygon-soup ids ----
+    MCB_TRY(stage_mesh(ctx, 0, hsrc));
+    MCB_TRY(stage_mesh(ctx, 1, hcut));
+    mcb200_mesh* src = ctx->st_mesh[0];
+    mcb200_mesh* cut = ctx->st_mesh[1];
+    MCB_TRY(mcb200_mesh_set_frame(ctx, src, com, shift, nullptr));
+    MCB_TRY(mcb200_mesh_set_frame(ctx, cut, com, shift, perturbation));
+    if (!ctx->st_soup) ctx->st_soup = new mcb200_soup();
+    mcb200_soup* soup = ctx->st_soup;
+    std::vector<uint32_t> fv, fe, ev, ef; // only when the caller did not bring the ids
+    mcb200_host_soup local;
+    if (!hsoup) {
+        std::vector<uint32_t> so((size_t)hsrc->nf + 1), co((size_t)hcut->nf + 1);
+        for (uint32_t f = 0, a = 0; f <= hsrc->nf; ++f) {
+            so[f] = a;
+            if (f < hsrc->nf) a += hsrc->face_sizes ? hsrc->face_sizes[f] : 3u;
+        }
+        for (uint32_t f = 0, a = 0; f <= hcut->nf; ++f) {
+            co[f] = a;
+            if (f < hcut->nf) a += hcut->face_sizes ? hcut->face_sizes[f] : 3u;
+        }
+        const uint32_t nh = so[hsrc->nf] + co[hcut->nf];
+        fv.resize(nh);
+        fe.resize(nh);
+        ev.resize(2 * (size_t)nh);
+        ef.resize(2 * (size_t)nh);
+        uint32_t ne = 0;
+        const int rc = host_soup_ids(hsrc->nv, so.data(), hsrc->face_vtx, hsrc->nf, co.data(), hcut->face_vtx, hcut->nf, fv.data(), fe.data(),
+            ev.data(), ef.data(), &ne);
+        if (rc) MCB_FAIL(ctx, rc, "stage_host: polygon-soup ids: non-manifold edge, inconsistent winding or degenerate face");
+        local.nh = nh;
+        local.ne = ne;
+        local.face_edge = fe.data();
+        local.edge_f = ef.data();
+        hsoup = &local;
+    }
+    if (hsoup->nh != src->nh + cut->nh) MCB_FAIL(ctx, MCB200_ERR_INVALID, "stage_host: soup halfedge count does not match the meshes");
+    soup->nsf = src->nf;
+    soup->ncf = cut->nf;
+    soup->nh = hsoup->nh;
+    soup->ne = hsoup->ne;
+    soup->all_tri = (src->is_tri && cut->is_tri) ? 1 : 0;
+    MCB_TRY(ctx->reserve(soup->face_vtx, sizeof(uint32_t) * (size_t)soup->nh));
+    MCB_TRY(ctx->reserve(soup->face_edge, sizeof(uint32_t) * (size_t)soup->nh));
+    MCB_TRY(ctx->reserve(soup->edge_f, sizeof(uint32_t) * 2 * (size_t)(soup->ne ? soup->ne : 1)));
+    if (!soup->all_tri) MCB_TRY(ctx->reserve(soup->face_off, sizeof(uint32_t) * ((size_t)soup->nsf + soup->ncf + 1)));
+    // every other allocation of the stage, still before any lane forks
+    int rc = lbvh_reserve(ctx, src);
+    if (!rc) rc = traverse_reserve(ctx, src, cut, res);
+    if (!rc) rc = narrowphase_reserve(ctx, soup, res, flags);
+    ctx->use_aux();
+    if (!rc) rc = lbvh_reserve(ctx, cut);
+    if (!rc) rc = sort_pairs_reserve(ctx, src, cut, res);
+    ctx->use_main();
+    if (rc) return rc;
+    MCB_CUDA(ctx, cudaEventRecord(ctx->ev_fork, ctx->stream));
+    MCB_CUDA(ctx, cudaStreamWaitEvent(ctx->copy, ctx->ev_fork, 0));
+    MCB_CUDA(ctx, cudaMemcpyAsync(soup->face_edge.p, hsoup->face_edge, sizeof(uint32_t) * (size_t)soup->nh, cudaMemcpyHostToDevice, ctx->copy));
+    MCB_CUDA(ctx, cudaMemcpyAsync(soup->edge_f.p, hsoup->edge_f, sizeof(uint32_t) * 2 * (size_t)soup->ne, cudaMemcpyHostToDevice, ctx->copy));
+    MCB_CUDA(ctx, cudaEventRecord(ctx->ev_up[2], ctx->copy));
+
+    // ---- builds: each lane starts when its mesh has landed ----
+    frame_t cut_frame = cut->frame;
+    cut->frame.has_pert = 0;
+    for (int j = 0; j < 3; ++j) cut->frame.pert[j] = 0.0;
+    MCB_CUDA(ctx, cudaEventRecord(ctx->ev_fork, ctx->stream));
+    MCB_CUDA(ctx, cudaStreamWaitEvent(ctx->aux, ctx->ev_fork, 0));
+    MCB_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_up[0], 0));
+    rc = lbvh_build(ctx, src, 0.0);
+    ctx->use_aux();
+    cudaStreamWaitEvent(ctx->aux, ctx->ev_up[1], 0);
+    if (!rc) rc = lbvh_build(ctx, cut, cut_eps);
+    if (!rc) rc = soup_face_vtx_device(ctx, src, cut, soup); // needs both face arrays; the aux lane has both by now
+    cudaEventRecord(ctx->ev_join, ctx->aux);
+    ctx->use_main();
+    cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0);
+    cut->frame = cut_frame;
+    if (rc) return rc;
+    MCB_TRY(traverse_pairs(ctx, src, cut, res));
+    MCB_CUDA(ctx, cudaEventRecord(ctx->ev_fork2, ctx->stream));
+    MCB_CUDA(ctx, cudaStreamWaitEvent(ctx->aux, ctx->ev_fork2, 0));
+    ctx->use_aux();
+    rc = sort_pairs(ctx, src, cut, res);
+    cudaEventRecord(ctx->ev_join2, ctx->aux);
+    ctx->use_main();
+    cudaStreamWaitEvent(ctx->stream, ctx->ev_up[2], 0);
+    if (!rc) rc = narrowphase_run(ctx, soup, src, cut, res, flags);
+    cudaStreamWaitEvent(ctx->stream, ctx->ev_join2, 0);
+    if (rc) return rc;
+    if (!hsoup || hsoup == &local) MCB_CUDA(ctx, cudaStreamSynchronize(ctx->copy)); // local id arrays go out of scope
+    return 0;
+}
+
 // ---------------------------------------------------------------------------------------------------------- reads
 
 int mcb200_result_counts(mcb200_ctx* ctx, mcb200_result* res, mcb200_counts* out)
@@ -575,7 +750,12 @@ int mcb200_result_counts(mcb200_ctx* ctx, mcb200_result* res, mcb200_counts* out
         out->status = MCB200_STATUS_GENERAL_POSITION_VIOLATION;
     else
         out->status = MCB200_STATUS_SUCCESS;
-    if (h.pair_overflow) MCB_FAIL(ctx, MCB200_ERR_CAPACITY, "pair buffer overflow: call mcb200_bvh_intersect (it regrows and retries)");
+    if (h.pair_overflow) {
+        // regrow for the caller's retry: the counter kept counting past the capacity, so the needed size is known
+        res->cap_pairs = (size_t)h.n_pairs + (size_t)h.n_pairs / 8 + 1024;
+        res->h_valid = false;
+        MCB_FAIL(ctx, MCB200_ERR_CAPACITY, "pair buffer overflow: capacity has been raised, run the stage again");
+    }
     return 0;
 }
 

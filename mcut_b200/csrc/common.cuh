@@ -80,6 +80,12 @@ struct mcb200_ctx {
         dbuf keys_alt, vals_alt, hist, status, tilectr;
     } scratch[2];
     sort_scratch_t& sc() { return scratch[sci]; }
+    // staging for mcb200_intersect_stage_host: copy stream, upload-done events, reusable device copies of the inputs
+    cudaStream_t copy = nullptr;
+    cudaEvent_t ev_up[3] = { nullptr, nullptr, nullptr };
+    struct mcb200_mesh* st_mesh[2] = { nullptr, nullptr };
+    struct mcb200_soup* st_soup = nullptr;
+    dbuf st_xyz[2], st_fv[2], st_fo[2];
     void use_main() { cur = stream; sci = 0; }
     void use_aux() { cur = aux; sci = 1; }
 

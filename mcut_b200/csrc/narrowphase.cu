@@ -630,6 +630,38 @@ int narrowphase_run(mcb200_ctx* ctx, const mcb200_soup* soup, const mcb200_mesh*
     return 0;
 }
 
+// ps.get_vertices_around_face order of both meshes from their user face arrays (hmesh.cpp:705-733 returns halfedge
+// targets: the user's list rotated by one; cut faces were handed to add_face already rotated, kernel.cpp:1678): slot i of a
+// source face holds user[(i+1) % n], of a cut face user[(i+2) % n] + nsv.
+namespace {
+__global__ void __launch_bounds__(256) k_soup_face_vtx(const uint32_t* __restrict__ user_vtx, const uint32_t* __restrict__ face_off,
+    uint32_t nf, uint32_t rot, uint32_t voff, uint32_t* __restrict__ ps_vtx, uint32_t* __restrict__ ps_off, uint32_t off_base,
+    uint32_t face_base)
+{
+    for (uint32_t f = blockIdx.x * 256u + threadIdx.x; f < nf; f += gridDim.x * 256u) {
+        const uint32_t h0 = face_off ? face_off[f] : 3u * f;
+        const uint32_t n = face_off ? face_off[f + 1] - h0 : 3u;
+        for (uint32_t i = 0; i < n; ++i) ps_vtx[off_base + h0 + i] = __ldg(user_vtx + h0 + (i + rot) % n) + voff;
+        if (ps_off) {
+            ps_off[face_base + f] = off_base + h0;
+            if (f == nf - 1) ps_off[face_base + nf] = off_base + h0 + n;
+        }
+    }
+}
+} // namespace
+
+int soup_face_vtx_device(mcb200_ctx* ctx, const mcb200_mesh* src, const mcb200_mesh* cut, mcb200_soup* soup)
+{
+    const bool tri = src->is_tri && cut->is_tri;
+    uint32_t* off = tri ? nullptr : soup->face_off.as<uint32_t>();
+    const unsigned gs = div_up(src->nf, 256), gc = div_up(cut->nf, 256);
+    MCB_LAUNCH(ctx, k_soup_face_vtx, gs, 256, 0, src->d_face_vtx, src->d_face_off, src->nf, 1u, 0u, soup->face_vtx.as<uint32_t>(), off,
+        0u, 0u);
+    MCB_LAUNCH(ctx, k_soup_face_vtx, gc, 256, 0, cut->d_face_vtx, cut->d_face_off, cut->nf, 2u, src->nv, soup->face_vtx.as<uint32_t>(),
+        off, src->nh, src->nf);
+    return 0;
+}
+
 int narrowphase_sort_records(mcb200_ctx* ctx, mcb200_result* res)
 {
     if (res->records_sorted_valid) return 0;

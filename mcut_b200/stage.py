@@ -22,6 +22,8 @@ import numpy as np
 from . import _lib
 from ._lib import Counts, Record, Test, c_dp, c_i32p, c_u32p, c_u64p
 
+ERR_CAPACITY = -4  # include/mcut_b200.h: MCB200_ERR_CAPACITY
+
 MC_DISPATCH_VERTEX_ARRAY_FLOAT = 1 << 0
 MC_DISPATCH_VERTEX_ARRAY_DOUBLE = 1 << 1
 MC_DISPATCH_ENFORCE_GENERAL_POSITION = 1 << 15
@@ -213,6 +215,9 @@ class Result:
         self.h = C.c_void_p()
         ctx.check(ctx.L.mcb200_result_create(ctx.h, C.byref(self.h)))
 
+    def set_pair_capacity(self, max_pairs: int):
+        self.ctx.check(self.ctx.L.mcb200_result_set_pair_capacity(self.ctx.h, self.h, int(max_pairs)))
+
     def set_shard(self, part: int, nparts: int, chunk: int = 4096):
         self.ctx.check(self.ctx.L.mcb200_result_set_shard(self.ctx.h, self.h, part, nparts, chunk))
 
@@ -304,4 +309,77 @@ def intersect_stage(ctx: Context, src, cut, flags: int, gp_constant: float = 1e-
         out["tests"] = res.tests()
     for o in (soup, res, ms, mc):
         o.free()
+    return out
+
+
+def intersect_stage_host(ctx: Context, src, cut, flags: int = 0, gp_constant: float = 1e-4, perturbation=None, soup_ids_host=None,
+                         log_tests: bool = False, res: "Result" = None, params=None) -> Dict[str, object]:
+    """The same stage through the single pipelined C-ABI call `mcb200_intersect_stage_host`: uploads on a copy stream
+    overlap the builds, the polygon-soup vertex lists are derived on the device. `soup_ids_host` = (face_edge, edge_f, ne)
+    when the caller already holds `ps` (the reference does, kernel.cpp:1593-1732); None -> computed by the library.
+    `params` = (com, shift, eps) to skip the host-side vertex_parameters pass (it belongs to preproc, not to this stage)."""
+    from ._lib import HostMesh, HostSoup
+    sx, sf, ss = src
+    cx, cf, cs = cut
+    if params is None:
+        com, shift, sbb, cbb = vertex_parameters(sx, cx)
+        eps = cut_bbox_eps(cbb, gp_constant, bool(flags & MC_DISPATCH_ENFORCE_GENERAL_POSITION_ABSOLUTE))
+    else:
+        com, shift, eps = params
+    keep = []
+
+    def host_mesh(x, f, sz):
+        x = np.ascontiguousarray(x)
+        if x.dtype not in (np.float32, np.float64):
+            x = x.astype(np.float64)
+        f = np.ascontiguousarray(f, dtype=np.uint32)
+        keep.extend([x, f])
+        nf = len(f) // 3 if sz is None else len(sz)
+        szp = None
+        if sz is not None:
+            sz = np.ascontiguousarray(sz, dtype=np.uint32)
+            keep.append(sz)
+            szp = sz.ctypes.data
+        return HostMesh(1 if x.dtype == np.float32 else 0, x.ctypes.data, x.shape[0], f.ctypes.data, szp, nf)
+
+    hs, hc = host_mesh(sx, sf, ss), host_mesh(cx, cf, cs)
+    hsoup = None
+    if soup_ids_host is not None:
+        fe, ef, ne = soup_ids_host
+        fe = np.ascontiguousarray(fe, dtype=np.uint32)
+        ef = np.ascontiguousarray(ef, dtype=np.uint32)
+        keep.extend([fe, ef])
+        hsoup = C.byref(HostSoup(len(fe), int(ne), fe.ctypes.data, ef.ctypes.data))
+    own = res is None
+    if own:
+        res = Result(ctx)
+    com_a = np.ascontiguousarray(com, dtype=np.float64)
+    shift_a = np.ascontiguousarray(shift, dtype=np.float64)
+    pert_p = None
+    if perturbation is not None:
+        pert_a = np.ascontiguousarray(perturbation, dtype=np.float64)
+        keep.append(pert_a)
+        pert_p = pert_a.ctypes.data_as(C.POINTER(C.c_double))
+    fl = NARROW_LOG_TESTS if log_tests else 0
+    for attempt in range(3):
+        ctx.check(ctx.L.mcb200_intersect_stage_host(ctx.h, C.byref(hs), C.byref(hc), com_a.ctypes.data_as(C.POINTER(C.c_double)),
+                                                    shift_a.ctypes.data_as(C.POINTER(C.c_double)), pert_p, float(eps), hsoup, res.h,
+                                                    fl))
+        c = Counts()
+        rc = ctx.L.mcb200_result_counts(ctx.h, res.h, C.byref(c))
+        if rc == ERR_CAPACITY and attempt < 2:
+            continue  # the library raised the pair capacity: run again
+        ctx.check(rc)
+        break
+    out: Dict[str, object] = {
+        "com": com, "shift": shift, "eps": eps, "status": int(c.status), "bad_face": int(c.bad_face),
+        "n_pairs": int(c.n_pairs), "n_tests": int(c.n_tests), "n_exact": int(c.n_exact), "n_records": int(c.n_records),
+        "n_cand_faces": int(c.n_cand_faces), "pairs": res.pairs(), "records": res.records(),
+    }
+    faces, normal, d, mcmp = res.planes()
+    out.update({"cand_faces": faces, "cand_normal": normal, "cand_d": d, "cand_maxcomp": mcmp})
+    if log_tests:
+        out["tests"] = res.tests()
+    if own:
+        res.free()
     return out

@@ -75,3 +75,61 @@ def test_morton_codes_match_reference_formula(oracle, gpu_ctx):
     assert sorted(order.tolist()) == list(range(m.nf)), "sorted leaf order is a permutation"
     assert np.all(np.diff(want[order].astype(np.int64)) >= 0), "leaves ascend by Morton code"
     m.free()
+
+
+# ---- the single pipelined host-array call (mcb200_intersect_stage_host) ----
+def _check_host_call(ref, got):
+    assert beq(got["pairs"], ref["pairs"]), "sorted candidate pair set"
+    assert got["status"] == ref["status"]
+    if ref["status"] in (2, 3):
+        assert got["bad_face"] == ref["bad_face"]
+        return
+    assert beq(got["cand_faces"], ref["cand_faces"]) and beq(got["cand_normal"], ref["cand_normal"]) and beq(got["cand_d"], ref["cand_d"])
+    rt, gt = ref["tests"], got["tests"]
+    assert beq(gt["edge"], rt["edge"]) and beq(gt["face"], rt["face"]) and beq(gt["type"], rt["type"])
+    assert beq(gt["sign_q"], rt["sign_q"]) and beq(gt["sign_r"], rt["sign_r"]) and beq(gt["pip"], rt["pip"]) and beq(gt["point"], rt["point"])
+    if ref["status"] == 0:
+        rr, gr = ref["records"], got["records"]
+        assert beq(gr["edge"], rr["edge"]) and beq(gr["face"], rr["face"]) and beq(gr["point"], rr["point"]), "registry"
+
+
+@pytest.mark.parametrize("case", sorted(cases.ALL))
+def test_host_array_call_matches_oracle(oracle, gpu_ctx, case):
+    from mcut_b200 import stage
+    src, cut, flags = cases.ALL[case]()
+    ref = oracle.intersect_stage(src, cut, flags)
+    got = stage.intersect_stage_host(gpu_ctx, src, cut, flags, log_tests=True)  # the library numbers the polygon soup itself
+    _check_host_call(ref, got)
+
+
+def test_host_array_call_with_caller_soup_and_perturbation(oracle, gpu_ctx):
+    from mcut_b200 import stage
+    pert = np.array([1.3e-3, -0.7e-3, 2.1e-3])
+    for case in ("cube_cube_axis_aligned", "spheres_k16", "patch_vs_sphere"):
+        src, cut, flags = cases.ALL[case]()
+        ref = oracle.intersect_stage(src, cut, flags, perturbation=pert)
+        (sx, sf, ss), (cx, cf, cs) = src, cut
+        soff = np.arange(0, sf.size + 1, 3, dtype=np.uint32) if ss is None else np.concatenate([[0], np.cumsum(ss)]).astype(np.uint32)
+        coff = np.arange(0, cf.size + 1, 3, dtype=np.uint32) if cs is None else np.concatenate([[0], np.cumsum(cs)]).astype(np.uint32)
+        fv, fe, ev, ef = stage.soup_ids(sx.shape[0], soff, sf, coff, cf)
+        res = stage.Result(gpu_ctx)
+        for _ in range(2):  # the staging buffers and the result are reused across calls
+            got = stage.intersect_stage_host(gpu_ctx, src, cut, flags, perturbation=pert, soup_ids_host=(fe, ef, ev.shape[0]),
+                                             log_tests=True, res=res)
+            _check_host_call(ref, got)
+        res.free()
+
+
+def test_pair_capacity_is_regrown_on_overflow(oracle, gpu_ctx):
+    """A result whose pair buffer is too small reports MCB200_ERR_CAPACITY from mcb200_result_counts, raises its own
+    capacity, and the rerun is complete (no silent truncation)."""
+    from mcut_b200 import stage
+    src, cut, flags = cases.ALL["spheres_k16"]()
+    ref = oracle.intersect_stage(src, cut, flags)
+    res = stage.Result(gpu_ctx)
+    res.set_pair_capacity(64)
+    got = stage.intersect_stage_host(gpu_ctx, src, cut, flags, res=res)
+    assert beq(got["pairs"], ref["pairs"])
+    rr, gr = ref["records"], got["records"]
+    assert beq(gr["edge"], rr["edge"]) and beq(gr["face"], rr["face"]) and beq(gr["point"], rr["point"])
+    res.free()
