@@ -165,7 +165,10 @@ int mcb200_intersect_stage(mcb200_ctx* ctx, mcb200_mesh* src, mcb200_mesh* cut, 
  * waits for the soup only.  Pin the arrays (cudaHostAlloc / torch pin_memory) to get the overlap; pageable memory works
  * but serialises.  The polygon-soup vertex lists are derived on the device from the face arrays (rotation rules of
  * hmesh.cpp:705-733), so only face_edge / edge_f travel.  Meshes and soup live in context-owned staging buffers that
- * are reused from call to call.  soup == NULL: the ids are computed here with mcb200_soup_ids. */
+ * are reused from call to call.  soup == NULL: the polygon soup is numbered on the device (same ids as mcb200_soup_ids:
+ * an edge's id is the rank of its first halfedge in add_face order, hmesh.cpp:406-651), nothing but the two meshes
+ * travels; a non-manifold edge or inconsistent winding is then reported by mcb200_result_counts as
+ * MCB200_ERR_NON_MANIFOLD. */
 typedef struct mcb200_host_mesh {
     int is_float; /* MC_DISPATCH_VERTEX_ARRAY_FLOAT */
     const void* xyz; /* [nv*3] */
@@ -182,6 +185,10 @@ typedef struct mcb200_host_soup {
 int mcb200_intersect_stage_host(mcb200_ctx* ctx, const mcb200_host_mesh* src, const mcb200_host_mesh* cut, const double com[3],
     const double shift[3], const double perturbation[3] /* or NULL */, double cut_eps, const mcb200_host_soup* soup,
     mcb200_result* res, uint32_t flags);
+/* The polygon-soup ids the last mcb200_intersect_stage_host call of this context worked with (uploaded or numbered on the
+ * device): face_vtx[nh], face_edge[nh], edge_f[2*ne].  Any output may be NULL.  Synchronises. */
+int mcb200_staged_soup_read(mcb200_ctx* ctx, uint32_t* face_vtx, uint32_t* face_edge, uint32_t* edge_f, uint32_t capacity_edges,
+    uint32_t* nh, uint32_t* ne);
 
 /* ---------------------------------------------------------------- reading results (D2H, synchronising) ----- */
 int mcb200_result_counts(mcb200_ctx* ctx, mcb200_result* res, mcb200_counts* out);

@@ -76,6 +76,7 @@ SYMBOLS = {
     "mcb200_intersect_stage": (C.c_int, [vp, vp, vp, C.c_double, vp, vp, C.c_uint32]),
     "mcb200_intersect_stage_host": (C.c_int, [vp, C.POINTER(HostMesh), C.POINTER(HostMesh), c_dp, c_dp, c_dp, C.c_double,
                                              C.POINTER(HostSoup), vp, C.c_uint32]),
+    "mcb200_staged_soup_read": (C.c_int, [vp, c_u32p, c_u32p, c_u32p, C.c_uint32, c_u32p, c_u32p]),
     "mcb200_result_counts": (C.c_int, [vp, vp, C.POINTER(Counts)]),
     "mcb200_result_read_pairs": (C.c_int, [vp, vp, c_u64p, C.c_size_t]),
     "mcb200_result_read_records": (C.c_int, [vp, vp, C.POINTER(Record), C.c_size_t]),

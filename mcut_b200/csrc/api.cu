@@ -92,12 +92,16 @@ int mcb200_ctx_create(int device, void* stream, mcb200_ctx** out)
         }
         ctx->owns_stream = true;
     }
-    if ((e = cudaStreamCreateWithFlags(&ctx->aux, cudaStreamNonBlocking)) != cudaSuccess) {
+    int prio_lo = 0, prio_hi = 0; // numerically: lo = least urgent, hi = most urgent
+    cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
+    if ((e = cudaStreamCreateWithPriority(&ctx->aux, cudaStreamNonBlocking, prio_hi)) != cudaSuccess) {
         g_create_error = std::string("cudaStreamCreate(aux): ") + cudaGetErrorString(e);
         delete ctx;
         return (int)e;
     }
     cudaStreamCreateWithFlags(&ctx->copy, cudaStreamNonBlocking);
+    cudaStreamCreateWithPriority(&ctx->bg, cudaStreamNonBlocking, prio_lo);
+    cudaEventCreateWithFlags(&ctx->ev_bg, cudaEventDisableTiming);
     for (auto& ev : ctx->ev_up) cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
     cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming);
     cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming);
@@ -121,6 +125,9 @@ void mcb200_ctx_destroy(mcb200_ctx* ctx)
     cudaStreamSynchronize(ctx->stream);
     cudaStreamSynchronize(ctx->aux);
     cudaStreamSynchronize(ctx->copy);
+    cudaStreamSynchronize(ctx->bg);
+    cudaStreamDestroy(ctx->bg);
+    cudaEventDestroy(ctx->ev_bg);
     for (int k = 0; k < 2; ++k) {
         if (ctx->st_mesh[k]) mcb200_mesh_free(ctx, ctx->st_mesh[k]);
         ctx->release(ctx->st_xyz[k]);
@@ -128,6 +135,7 @@ void mcb200_ctx_destroy(mcb200_ctx* ctx)
         ctx->release(ctx->st_fo[k]);
     }
     if (ctx->st_soup) mcb200_soup_free(ctx, ctx->st_soup);
+    for (dbuf* b : { &ctx->st_tab_keys, &ctx->st_hfirst, &ctx->st_bsum }) ctx->release(*b);
     cudaStreamDestroy(ctx->copy);
     for (auto& ev : ctx->ev_up) cudaEventDestroy(ev);
     for (auto& sc : ctx->scratch) {
@@ -611,12 +619,17 @@ static int stage_mesh(mcb200_ctx* ctx, int k, const mcb200_host_mesh* hm)
     // buffers come from the main stream's pool order: make the copy stream wait for that point
     MCB_CUDA(ctx, cudaEventRecord(ctx->ev_fork, ctx->stream));
     MCB_CUDA(ctx, cudaStreamWaitEvent(ctx->copy, ctx->ev_fork, 0));
-    MCB_CUDA(ctx, cudaMemcpyAsync(ctx->st_xyz[k].p, hm->xyz, vbytes, cudaMemcpyHostToDevice, ctx->copy));
+    // the cut mesh sends its faces first: with them the polygon soup can be numbered while the coordinates still travel
+    if (k == 0) MCB_CUDA(ctx, cudaMemcpyAsync(ctx->st_xyz[k].p, hm->xyz, vbytes, cudaMemcpyHostToDevice, ctx->copy));
     MCB_CUDA(ctx, cudaMemcpyAsync(ctx->st_fv[k].p, hm->face_vtx, sizeof(uint32_t) * (size_t)nh, cudaMemcpyHostToDevice, ctx->copy));
     if (!m->is_tri) {
         // `off` is a local: this (small, polygon-only) copy must complete before it goes out of scope
         MCB_CUDA(ctx, cudaMemcpyAsync(ctx->st_fo[k].p, off.data(), sizeof(uint32_t) * off.size(), cudaMemcpyHostToDevice, ctx->copy));
         MCB_CUDA(ctx, cudaStreamSynchronize(ctx->copy));
+    }
+    if (k == 1) {
+        MCB_CUDA(ctx, cudaEventRecord(ctx->ev_up[2], ctx->copy)); // all face arrays are on the device
+        MCB_CUDA(ctx, cudaMemcpyAsync(ctx->st_xyz[k].p, hm->xyz, vbytes, cudaMemcpyHostToDevice, ctx->copy));
     }
     MCB_CUDA(ctx, cudaEventRecord(ctx->ev_up[k], ctx->copy));
     m->d_xyz = ctx->st_xyz[k].p;
@@ -644,43 +657,22 @@ int mcb200_intersect_stage_host(mcb200_ctx* ctx, const mcb200_host_mesh* hsrc, c
     MCB_TRY(mcb200_mesh_set_frame(ctx, cut, com, shift, perturbation));
     if (!ctx->st_soup) ctx->st_soup = new mcb200_soup();
     mcb200_soup* soup = ctx->st_soup;
-    std::vector<uint32_t> fv, fe, ev, ef; // only when the caller did not bring the ids
-    mcb200_host_soup local;
-    if (!hsoup) {
-        std::vector<uint32_t> so((size_t)hsrc->nf + 1), co((size_t)hcut->nf + 1);
-        for (uint32_t f = 0, a = 0; f <= hsrc->nf; ++f) {
-            so[f] = a;
-            if (f < hsrc->nf) a += hsrc->face_sizes ? hsrc->face_sizes[f] : 3u;
-        }
-        for (uint32_t f = 0, a = 0; f <= hcut->nf; ++f) {
-            co[f] = a;
-            if (f < hcut->nf) a += hcut->face_sizes ? hcut->face_sizes[f] : 3u;
-        }
-        const uint32_t nh = so[hsrc->nf] + co[hcut->nf];
-        fv.resize(nh);
-        fe.resize(nh);
-        ev.resize(2 * (size_t)nh);
-        ef.resize(2 * (size_t)nh);
-        uint32_t ne = 0;
-        const int rc = host_soup_ids(hsrc->nv, so.data(), hsrc->face_vtx, hsrc->nf, co.data(), hcut->face_vtx, hcut->nf, fv.data(), fe.data(),
-            ev.data(), ef.data(), &ne);
-        if (rc) MCB_FAIL(ctx, rc, "stage_host: polygon-soup ids: non-manifold edge, inconsistent winding or degenerate face");
-        local.nh = nh;
-        local.ne = ne;
-        local.face_edge = fe.data();
-        local.edge_f = ef.data();
-        hsoup = &local;
+    const bool number_on_device = (hsoup == nullptr);
+    if (number_on_device) {
+        MCB_TRY(soup_number_reserve(ctx, src, cut, soup));
+    } else {
+        if (hsoup->nh != src->nh + cut->nh || !hsoup->face_edge || !hsoup->edge_f)
+            MCB_FAIL(ctx, MCB200_ERR_INVALID, "stage_host: soup halfedge count does not match the meshes");
+        soup->nsf = src->nf;
+        soup->ncf = cut->nf;
+        soup->nh = hsoup->nh;
+        soup->ne = hsoup->ne;
+        soup->all_tri = (src->is_tri && cut->is_tri) ? 1 : 0;
+        MCB_TRY(ctx->reserve(soup->face_vtx, sizeof(uint32_t) * (size_t)soup->nh));
+        MCB_TRY(ctx->reserve(soup->face_edge, sizeof(uint32_t) * (size_t)soup->nh));
+        MCB_TRY(ctx->reserve(soup->edge_f, sizeof(uint32_t) * 2 * (size_t)(soup->ne ? soup->ne : 1)));
+        if (!soup->all_tri) MCB_TRY(ctx->reserve(soup->face_off, sizeof(uint32_t) * ((size_t)soup->nsf + soup->ncf + 1)));
     }
-    if (hsoup->nh != src->nh + cut->nh) MCB_FAIL(ctx, MCB200_ERR_INVALID, "stage_host: soup halfedge count does not match the meshes");
-    soup->nsf = src->nf;
-    soup->ncf = cut->nf;
-    soup->nh = hsoup->nh;
-    soup->ne = hsoup->ne;
-    soup->all_tri = (src->is_tri && cut->is_tri) ? 1 : 0;
-    MCB_TRY(ctx->reserve(soup->face_vtx, sizeof(uint32_t) * (size_t)soup->nh));
-    MCB_TRY(ctx->reserve(soup->face_edge, sizeof(uint32_t) * (size_t)soup->nh));
-    MCB_TRY(ctx->reserve(soup->edge_f, sizeof(uint32_t) * 2 * (size_t)(soup->ne ? soup->ne : 1)));
-    if (!soup->all_tri) MCB_TRY(ctx->reserve(soup->face_off, sizeof(uint32_t) * ((size_t)soup->nsf + soup->ncf + 1)));
     // every other allocation of the stage, still before any lane forks
     int rc = lbvh_reserve(ctx, src);
     if (!rc) rc = traverse_reserve(ctx, src, cut, res);
@@ -690,24 +682,36 @@ int mcb200_intersect_stage_host(mcb200_ctx* ctx, const mcb200_host_mesh* hsrc, c
     if (!rc) rc = sort_pairs_reserve(ctx, src, cut, res);
     ctx->use_main();
     if (rc) return rc;
-    MCB_CUDA(ctx, cudaEventRecord(ctx->ev_fork, ctx->stream));
-    MCB_CUDA(ctx, cudaStreamWaitEvent(ctx->copy, ctx->ev_fork, 0));
-    MCB_CUDA(ctx, cudaMemcpyAsync(soup->face_edge.p, hsoup->face_edge, sizeof(uint32_t) * (size_t)soup->nh, cudaMemcpyHostToDevice, ctx->copy));
-    MCB_CUDA(ctx, cudaMemcpyAsync(soup->edge_f.p, hsoup->edge_f, sizeof(uint32_t) * 2 * (size_t)soup->ne, cudaMemcpyHostToDevice, ctx->copy));
-    MCB_CUDA(ctx, cudaEventRecord(ctx->ev_up[2], ctx->copy));
+    if (!number_on_device) {
+        MCB_CUDA(ctx, cudaEventRecord(ctx->ev_fork, ctx->stream));
+        MCB_CUDA(ctx, cudaStreamWaitEvent(ctx->copy, ctx->ev_fork, 0));
+        MCB_CUDA(ctx, cudaMemcpyAsync(soup->face_edge.p, hsoup->face_edge, sizeof(uint32_t) * (size_t)soup->nh, cudaMemcpyHostToDevice, ctx->copy));
+        MCB_CUDA(ctx, cudaMemcpyAsync(soup->edge_f.p, hsoup->edge_f, sizeof(uint32_t) * 2 * (size_t)soup->ne, cudaMemcpyHostToDevice, ctx->copy));
+        MCB_CUDA(ctx, cudaEventRecord(ctx->ev_up[3], ctx->copy));
+    }
 
     // ---- builds: each lane starts when its mesh has landed ----
     frame_t cut_frame = cut->frame;
     cut->frame.has_pert = 0;
     for (int j = 0; j < 3; ++j) cut->frame.pert[j] = 0.0;
+    // the counters are reset here, while the lanes still wait for the uploads (the soup numbering reports into them)
+    MCB_TRY(result_reset_counters(ctx, res));
+    res->counters_zeroed = true;
     MCB_CUDA(ctx, cudaEventRecord(ctx->ev_fork, ctx->stream));
     MCB_CUDA(ctx, cudaStreamWaitEvent(ctx->aux, ctx->ev_fork, 0));
     MCB_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_up[0], 0));
     rc = lbvh_build(ctx, src, 0.0);
+    // the polygon soup needs the face arrays only: it is numbered on the lowest-priority lane while the cut mesh's
+    // coordinates still travel, and gives way to the builds whenever they have blocks to place
+    ctx->use_bg();
+    MCB_CUDA(ctx, cudaStreamWaitEvent(ctx->bg, ctx->ev_fork, 0));
+    MCB_CUDA(ctx, cudaStreamWaitEvent(ctx->bg, ctx->ev_up[2], 0));
+    if (!rc) rc = number_on_device ? soup_number_device(ctx, src, cut, soup, res->counters.as<result_counters_t>())
+                                   : soup_face_vtx_device(ctx, src, cut, soup);
+    cudaEventRecord(ctx->ev_bg, ctx->bg);
     ctx->use_aux();
     cudaStreamWaitEvent(ctx->aux, ctx->ev_up[1], 0);
     if (!rc) rc = lbvh_build(ctx, cut, cut_eps);
-    if (!rc) rc = soup_face_vtx_device(ctx, src, cut, soup); // needs both face arrays; the aux lane has both by now
     cudaEventRecord(ctx->ev_join, ctx->aux);
     ctx->use_main();
     cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0);
@@ -720,11 +724,34 @@ int mcb200_intersect_stage_host(mcb200_ctx* ctx, const mcb200_host_mesh* hsrc, c
     rc = sort_pairs(ctx, src, cut, res);
     cudaEventRecord(ctx->ev_join2, ctx->aux);
     ctx->use_main();
-    cudaStreamWaitEvent(ctx->stream, ctx->ev_up[2], 0);
+    cudaStreamWaitEvent(ctx->stream, ctx->ev_bg, 0);
+    if (!number_on_device) cudaStreamWaitEvent(ctx->stream, ctx->ev_up[3], 0);
     if (!rc) rc = narrowphase_run(ctx, soup, src, cut, res, flags);
     cudaStreamWaitEvent(ctx->stream, ctx->ev_join2, 0);
-    if (rc) return rc;
-    if (!hsoup || hsoup == &local) MCB_CUDA(ctx, cudaStreamSynchronize(ctx->copy)); // local id arrays go out of scope
+    return rc;
+}
+
+// Reads back the polygon-soup ids the last mcb200_intersect_stage_host call used (tests: device numbering == mcb200_soup_ids).
+int mcb200_staged_soup_read(mcb200_ctx* ctx, uint32_t* face_vtx, uint32_t* face_edge, uint32_t* edge_f, uint32_t capacity_edges,
+    uint32_t* nh_out, uint32_t* ne_out)
+{
+    if (!ctx || !ctx->st_soup) return MCB200_ERR_INVALID;
+    MCB_CUDA(ctx, cudaSetDevice(ctx->device));
+    mcb200_soup* soup = ctx->st_soup;
+    MCB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    // device numbering leaves the edge count in the ids themselves: the largest id + 1
+    std::vector<uint32_t> fe(soup->nh);
+    MCB_CUDA(ctx, cudaMemcpy(fe.data(), soup->face_edge.p, sizeof(uint32_t) * fe.size(), cudaMemcpyDeviceToHost));
+    uint32_t ne = 0;
+    for (uint32_t e : fe) ne = e + 1 > ne ? e + 1 : ne;
+    if (nh_out) *nh_out = soup->nh;
+    if (ne_out) *ne_out = ne;
+    if (face_edge) std::memcpy(face_edge, fe.data(), sizeof(uint32_t) * fe.size());
+    if (face_vtx) MCB_CUDA(ctx, cudaMemcpy(face_vtx, soup->face_vtx.p, sizeof(uint32_t) * soup->nh, cudaMemcpyDeviceToHost));
+    if (edge_f) {
+        if (capacity_edges < ne) MCB_FAIL(ctx, MCB200_ERR_CAPACITY, "staged_soup_read: edge_f capacity too small");
+        MCB_CUDA(ctx, cudaMemcpy(edge_f, soup->edge_f.p, sizeof(uint32_t) * 2 * (size_t)ne, cudaMemcpyDeviceToHost));
+    }
     return 0;
 }
 
@@ -750,6 +777,8 @@ int mcb200_result_counts(mcb200_ctx* ctx, mcb200_result* res, mcb200_counts* out
         out->status = MCB200_STATUS_GENERAL_POSITION_VIOLATION;
     else
         out->status = MCB200_STATUS_SUCCESS;
+    if (h.soup_error)
+        MCB_FAIL(ctx, MCB200_ERR_NON_MANIFOLD, "polygon-soup numbering: an edge is shared by three faces or by two faces wound the same way");
     if (h.pair_overflow) {
         // regrow for the caller's retry: the counter kept counting past the capacity, so the needed size is known
         res->cap_pairs = (size_t)h.n_pairs + (size_t)h.n_pairs / 8 + 1024;

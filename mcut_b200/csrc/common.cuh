@@ -82,12 +82,17 @@ struct mcb200_ctx {
     sort_scratch_t& sc() { return scratch[sci]; }
     // staging for mcb200_intersect_stage_host: copy stream, upload-done events, reusable device copies of the inputs
     cudaStream_t copy = nullptr;
-    cudaEvent_t ev_up[3] = { nullptr, nullptr, nullptr };
+    cudaStream_t bg = nullptr; // lowest-priority lane: work that must not take SM slots from the builds (soup numbering)
+    cudaEvent_t ev_bg = nullptr;
+    cudaEvent_t ev_up[4] = { nullptr, nullptr, nullptr };
     struct mcb200_mesh* st_mesh[2] = { nullptr, nullptr };
     struct mcb200_soup* st_soup = nullptr;
     dbuf st_xyz[2], st_fv[2], st_fo[2];
+    dbuf st_tab_keys, st_hfirst, st_bsum; // device-side polygon-soup numbering (soup_ids.cu)
+    size_t st_tab_cap = 0;
     void use_main() { cur = stream; sci = 0; }
     void use_aux() { cur = aux; sci = 1; }
+    void use_bg() { cur = bg; sci = 0; } // kernels on this lane bring their own buffers, never the sort scratch
 
     void set_error(const std::string& msg, const char* file, int line)
     {
@@ -220,7 +225,9 @@ struct result_counters_t {
     unsigned int pair_overflow;
     unsigned int work_counter; // dynamic work distribution (traversal groups)
     unsigned int work_counter2;
-    unsigned int pad[7];
+    unsigned int soup_error; // device-side soup numbering: an edge with three faces or two faces wound the same way
+    unsigned int soup_ne; // number of polygon-soup edges it found
+    unsigned int pad[5];
 };
 
 struct mcb200_result {
@@ -229,6 +236,7 @@ struct mcb200_result {
     dbuf pairs_a, pairs_b; // ping-pong buffers of the pair sort
     unsigned long long* pairs_sorted = nullptr; // ascending (src << 32 | cut): points into pairs_a or pairs_b
     size_t cap_pairs = 0;
+    bool counters_zeroed = false; // the caller already reset the counters for this run (mcb200_intersect_stage_host)
     dbuf cand_flag; // u8 [nf_ps]
     dbuf plane; // per ps face: normal[3], d  (4 doubles) ; maxcomp in separate int array
     dbuf plane_mc; // i32 per ps face

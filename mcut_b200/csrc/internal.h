@@ -8,6 +8,7 @@ int lbvh_reserve(mcb200_ctx* ctx, mcb200_mesh* mesh);
 int lbvh_build(mcb200_ctx* ctx, mcb200_mesh* mesh, double eps);
 // traverse.cu
 int traverse_reserve(mcb200_ctx* ctx, const mcb200_mesh* src, const mcb200_mesh* cut, mcb200_result* res);
+int result_reset_counters(mcb200_ctx* ctx, mcb200_result* res);
 int traverse_pairs(mcb200_ctx* ctx, const mcb200_mesh* src, const mcb200_mesh* cut, mcb200_result* res);
 int sort_pairs_reserve(mcb200_ctx* ctx, const mcb200_mesh* src, const mcb200_mesh* cut, mcb200_result* res);
 int sort_pairs(mcb200_ctx* ctx, const mcb200_mesh* src, const mcb200_mesh* cut, mcb200_result* res);
@@ -18,6 +19,9 @@ int narrowphase_run(mcb200_ctx* ctx, const mcb200_soup* soup, const mcb200_mesh*
 int soup_face_vtx_device(mcb200_ctx* ctx, const mcb200_mesh* src, const mcb200_mesh* cut, mcb200_soup* soup);
 int narrowphase_sort_records(mcb200_ctx* ctx, mcb200_result* res);
 int narrowphase_sort_tests(mcb200_ctx* ctx, mcb200_result* res);
+// soup_ids.cu
+int soup_number_reserve(mcb200_ctx* ctx, const mcb200_mesh* src, const mcb200_mesh* cut, mcb200_soup* soup);
+int soup_number_device(mcb200_ctx* ctx, const mcb200_mesh* src, const mcb200_mesh* cut, mcb200_soup* soup, result_counters_t* counters);
 // host_logic.cpp
 int host_soup_ids(uint32_t nsv, const uint32_t* src_off, const uint32_t* src_vtx, uint32_t nsf, const uint32_t* cut_off,
     const uint32_t* cut_vtx, uint32_t ncf, uint32_t* face_vtx, uint32_t* face_edge, uint32_t* edge_v, uint32_t* edge_f,

@@ -255,6 +255,15 @@ int traverse_reserve(mcb200_ctx* ctx, const mcb200_mesh* src, const mcb200_mesh*
     return 0;
 }
 
+int result_reset_counters(mcb200_ctx* ctx, mcb200_result* res)
+{
+    MCB_CUDA(ctx, cudaMemsetAsync(res->counters.p, 0, sizeof(result_counters_t), ctx->cur));
+    // bad_face starts at "none"
+    const size_t off = offsetof(result_counters_t, bad_face);
+    MCB_CUDA(ctx, cudaMemsetAsync(reinterpret_cast<char*>(res->counters.p) + off, 0xFF, sizeof(unsigned), ctx->cur));
+    return 0;
+}
+
 // the traversal kernel alone, on ctx->cur: pairs land in res->pairs in emission order
 int traverse_pairs(mcb200_ctx* ctx, const mcb200_mesh* src, const mcb200_mesh* cut, mcb200_result* res)
 {
@@ -266,12 +275,8 @@ int traverse_pairs(mcb200_ctx* ctx, const mcb200_mesh* src, const mcb200_mesh* c
     const mcb200_mesh* q = query_is_cut ? cut : src;
     const mcb200_mesh* t = query_is_cut ? src : cut;
     MCB_TRY(traverse_reserve(ctx, src, cut, res));
-    MCB_CUDA(ctx, cudaMemsetAsync(res->counters.p, 0, sizeof(result_counters_t), ctx->cur));
-    {
-        // bad_face starts at "none"
-        const size_t off = offsetof(result_counters_t, bad_face);
-        MCB_CUDA(ctx, cudaMemsetAsync(reinterpret_cast<char*>(res->counters.p) + off, 0xFF, sizeof(unsigned), ctx->cur));
-    }
+    if (!res->counters_zeroed) MCB_TRY(result_reset_counters(ctx, res));
+    res->counters_zeroed = false;
     res->nsf = src->nf;
     res->nf_ps = src->nf + cut->nf;
     res->h_valid = false;

@@ -383,3 +383,16 @@ def intersect_stage_host(ctx: Context, src, cut, flags: int = 0, gp_constant: fl
     if own:
         res.free()
     return out
+
+
+def staged_soup(ctx: Context):
+    """(face_vtx, face_edge, edge_f[ne,2]) the last intersect_stage_host call of `ctx` worked with."""
+    nh = C.c_uint32()
+    ne = C.c_uint32()
+    ctx.check(ctx.L.mcb200_staged_soup_read(ctx.h, None, None, None, 0, C.byref(nh), C.byref(ne)))
+    fv = np.empty(nh.value, dtype=np.uint32)
+    fe = np.empty(nh.value, dtype=np.uint32)
+    ef = np.empty((ne.value, 2), dtype=np.uint32)
+    ctx.check(ctx.L.mcb200_staged_soup_read(ctx.h, fv.ctypes.data_as(c_u32p), fe.ctypes.data_as(c_u32p), ef.ctypes.data_as(c_u32p),
+                                            ne.value, C.byref(nh), C.byref(ne)))
+    return fv, fe, ef

@@ -133,3 +133,36 @@ def test_pair_capacity_is_regrown_on_overflow(oracle, gpu_ctx):
     rr, gr = ref["records"], got["records"]
     assert beq(gr["edge"], rr["edge"]) and beq(gr["face"], rr["face"]) and beq(gr["point"], rr["point"])
     res.free()
+
+
+def _offsets(faces, sizes):
+    if sizes is None:
+        return np.arange(0, faces.size + 1, 3, dtype=np.uint32)
+    return np.concatenate([[0], np.cumsum(sizes)]).astype(np.uint32)
+
+
+@pytest.mark.parametrize("case", sorted(cases.ALL))
+def test_device_soup_numbering_equals_host_numbering(gpu_ctx, case):
+    """Edge ids handed out on the device (rank of an edge's first halfedge) == the sequential numbering of
+    mcb200_soup_ids, itself pinned against the reference's `ps` in tests/test_host_logic.py."""
+    from mcut_b200 import stage
+    src, cut, flags = cases.ALL[case]()
+    (sx, sf, ss), (cx, cf, cs) = src, cut
+    fv, fe, ev, ef = stage.soup_ids(sx.shape[0], _offsets(sf, ss), sf, _offsets(cf, cs), cf)
+    stage.intersect_stage_host(gpu_ctx, src, cut, flags)
+    gfv, gfe, gef = stage.staged_soup(gpu_ctx)
+    assert beq(gfv, fv), "ps.get_vertices_around_face order"
+    assert beq(gfe, fe), "edge id of every halfedge"
+    assert beq(gef, ef.reshape(-1, 2)), "faces of h0 / h1 of every edge"
+
+
+def test_device_soup_numbering_reports_bad_topology(gpu_ctx):
+    from mcut_b200 import stage
+    src, cut, flags = cases.ALL["hello"]()
+    sx, sf, ss = src
+    bad = sf.copy()
+    bad[0:3] = bad[0:3][::-1]  # one face wound the other way: its edges run the same way as the neighbours'
+    with pytest.raises(RuntimeError, match="numbering"):
+        stage.intersect_stage_host(gpu_ctx, (sx, bad, ss), cut, flags)
+    ok = stage.intersect_stage_host(gpu_ctx, src, cut, flags)  # the context is still usable
+    assert ok["status"] == 0
