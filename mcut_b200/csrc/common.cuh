@@ -90,6 +90,7 @@ struct mcb200_ctx {
     dbuf st_xyz[2], st_fv[2], st_fo[2];
     dbuf st_tab_keys, st_hfirst, st_bsum; // device-side polygon-soup numbering (soup_ids.cu)
     size_t st_tab_cap = 0;
+    bool sort_smem_opt_in[4] = { false, false, false, false }; // radix_sort.cuh: dynamic shared memory opt-in done
     void use_main() { cur = stream; sci = 0; }
     void use_aux() { cur = aux; sci = 1; }
     void use_bg() { cur = bg; sci = 0; } // kernels on this lane bring their own buffers, never the sort scratch

@@ -465,10 +465,50 @@ template <bool TRI> __global__ void __launch_bounds__(NBLOCK) k_planes(plane_arg
 }
 
 // ---- canonical ordering of records / logged tests -----------------------------------------------------------------------
+// Up to SMALL_SORT items (the usual case: an intersection curve crosses thousands of edges, not millions) are ordered by
+// counting: the rank of an item is the number of items with a smaller (edge, face) key — keys are unique — and the item is
+// written straight to its place.  32 items per block, 8 threads share one item's scan.  One launch instead of
+// key extraction + histogram + six radix passes + gather; those kernels return at once when n <= SMALL_SORT.
+constexpr unsigned SMALL_SORT = 16384;
+constexpr int RANK_CHUNK = 1024;
+
+template <typename T> __global__ void __launch_bounds__(256) k_rank_sort_small(const T* __restrict__ items,
+    const unsigned long long* d_n, unsigned long long cap, T* __restrict__ out)
+{
+    __shared__ unsigned long long s_keys[RANK_CHUNK];
+    const unsigned long long n64 = *d_n < cap ? *d_n : cap;
+    if (n64 > SMALL_SORT || (unsigned long long)blockIdx.x * 32u >= n64) return;
+    const unsigned n = (unsigned)n64;
+    const unsigned i = blockIdx.x * 32u + (threadIdx.x >> 3), sub = threadIdx.x & 7u;
+    const bool live = i < n;
+    const unsigned long long mine = live ? (((unsigned long long)items[i].edge << 32) | items[i].face) : ~0ull;
+    unsigned rank = 0;
+    for (unsigned base = 0; base < n; base += RANK_CHUNK) {
+        const unsigned cn = (n - base < (unsigned)RANK_CHUNK) ? n - base : (unsigned)RANK_CHUNK;
+        for (unsigned j = threadIdx.x; j < (unsigned)RANK_CHUNK; j += 256u)
+            s_keys[j] = j < cn ? (((unsigned long long)items[base + j].edge << 32) | items[base + j].face) : ~0ull;
+        __syncthreads();
+#pragma unroll 8
+        for (unsigned j = sub; j < (unsigned)RANK_CHUNK; j += 8u) rank += (s_keys[j] < mine) ? 1u : 0u;
+        __syncthreads();
+    }
+    rank += __shfl_xor_sync(0xffffffffu, rank, 1);
+    rank += __shfl_xor_sync(0xffffffffu, rank, 2);
+    rank += __shfl_xor_sync(0xffffffffu, rank, 4);
+    if (live) {
+        // the item is a few 8-byte words: the 8 threads of the group copy it together
+        static_assert(sizeof(T) % 8 == 0 && alignof(T) >= 8, "records are copied as 8-byte words");
+        const unsigned long long* src = reinterpret_cast<const unsigned long long*>(items + i);
+        unsigned long long* dst = reinterpret_cast<unsigned long long*>(out + rank);
+        for (unsigned w = sub; w < sizeof(T) / 8; w += 8u) dst[w] = src[w];
+    }
+}
+
 template <typename T> __global__ void __launch_bounds__(256) k_make_keys(const T* items, const unsigned long long* d_n,
     unsigned long long cap, unsigned long long* keys)
 {
     const unsigned long long n = *d_n < cap ? *d_n : cap;
+    if (n <= SMALL_SORT) return;
     for (unsigned long long i = (unsigned long long)blockIdx.x * 256 + threadIdx.x; i < n; i += (unsigned long long)gridDim.x * 256)
         keys[i] = ((unsigned long long)items[i].edge << 32) | items[i].face;
 }
@@ -477,6 +517,7 @@ template <typename T> __global__ void __launch_bounds__(256) k_gather(const T* i
     const unsigned long long* d_n, unsigned long long cap, T* out)
 {
     const unsigned long long n = *d_n < cap ? *d_n : cap;
+    if (n <= SMALL_SORT) return;
     for (unsigned long long i = (unsigned long long)blockIdx.x * 256 + threadIdx.x; i < n; i += (unsigned long long)gridDim.x * 256)
         out[i] = items[idx[i]];
 }
@@ -500,11 +541,13 @@ int sort_items(mcb200_ctx* ctx, const mcb200_result* res, const T* items, T* ite
     MCB_TRY((rsort::reserve_scratch<unsigned long long>(ctx, cap, pd.npasses, true, true)));
     mcb200_ctx::sort_scratch_t& sc = ctx->sc();
     const unsigned grid = (unsigned)ctx->num_sms * 2u;
+    MCB_LAUNCH_NAMED(ctx, "k_rank_sort_small", (k_rank_sort_small<T>), SMALL_SORT / 32u, 256, 0, items, d_n, (unsigned long long)cap,
+        items_sorted);
     MCB_LAUNCH_NAMED(ctx, "k_make_keys", (k_make_keys<T>), grid, 256, 0, items, d_n, (unsigned long long)cap, keys.as<unsigned long long>());
     unsigned long long* kout = nullptr;
     uint32_t* vout = nullptr;
     MCB_TRY((rsort::sort<unsigned long long, uint32_t, true>(ctx, keys.as<unsigned long long>(), sc.keys_alt.as<unsigned long long>(),
-        keys.as<unsigned long long>(), nullptr, sc.vals_alt.as<uint32_t>(), idx.as<uint32_t>(), d_n, cap, pd, &kout, &vout)));
+        keys.as<unsigned long long>(), nullptr, sc.vals_alt.as<uint32_t>(), idx.as<uint32_t>(), d_n, cap, pd, &kout, &vout, SMALL_SORT)));
     MCB_LAUNCH_NAMED(ctx, "k_gather", (k_gather<T>), grid, 256, 0, items, vout, d_n, (unsigned long long)cap, items_sorted);
     return 0;
 }

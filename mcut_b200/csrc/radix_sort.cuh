@@ -5,7 +5,7 @@
 //
 // Structure ("onesweep"): ONE histogram kernel reads the keys once and produces the digit histograms of
 // every pass; each pass is then a single sweep: a persistent grid takes 256-thread tiles by ticket, ranks
-// the tile's keys per digit with warp match/ballot, publishes the tile's digit counts and resolves its
+// the tile's keys per digit with per-lane byte counters in shared memory, publishes the tile's digit counts and resolves its
 // global offsets by decoupled look-back over the previous tiles (no second read of the keys, no separate
 // scan kernel), reorders the tile through shared memory and writes coalesced runs.
 // The sort is stable, so LSD passes compose.  Element counts may live on the device (d_n), so a sort can
@@ -73,12 +73,13 @@ __device__ __forceinline__ size_t resolve_n(const unsigned long long* d_n, size_
 template <typename KeyT>
 __global__ void __launch_bounds__(THREADS) k_histogram(const KeyT* __restrict__ keys, const unsigned long long* d_n,
     size_t n_max, pass_desc pd, int tile_items, unsigned* __restrict__ hist /* [npasses][RADIX] */,
-    unsigned* __restrict__ status)
+    unsigned* __restrict__ status, size_t skip_le)
 {
     __shared__ unsigned s_hist[MAX_PASSES * RADIX];
+    const size_t n = resolve_n(d_n, n_max);
+    if (n <= skip_le) return; // a small-n kernel already produced the sorted output
     for (int i = threadIdx.x; i < pd.npasses * RADIX; i += THREADS) s_hist[i] = 0;
     __syncthreads();
-    const size_t n = resolve_n(d_n, n_max);
     {
         const size_t tiles = (n + tile_items - 1) / tile_items;
         const size_t words = tiles * RADIX * (size_t)pd.npasses;
@@ -120,82 +121,161 @@ __device__ __forceinline__ unsigned block_exclusive_scan(unsigned v, unsigned* s
 }
 
 // ---- one pass ------------------------------------------------------------------------------------------------
+// Ranking.  A warp owns 32 * ITEMS consecutive keys, split into units of 256 keys; inside a unit every lane owns 8
+// CONSECUTIVE keys, so "input order" inside the unit is (lane, j).  The rank of a key among the unit's keys with the same
+// digit is then: (keys with that digit in lower lanes) + (earlier keys with that digit in my own lane).  Each lane counts
+// its own digits into a private column of byte counters (count <= 8), one lane per digit row turns the 32 bytes of that
+// row into their exclusive prefix (<= 248, still a byte) with two multiplies per word, and a second walk over the lane's
+// keys reads-and-bumps the counter to get the rank.  No MATCH.ANY and no votes: on sm_100 a dependent
+// __match_any_sync costs ~400 cycles and a warp-match ranking step ~1000 (tools/mb_match.cu), which made ranking half of
+// the pass; the byte-counter walk is ordinary shared-memory traffic.
 // vals_in == nullptr with HAS_VALS: the value of element i is i (saves materialising an iota array).
+constexpr int SUB = 8; // keys a lane owns per ranking unit
+constexpr int CNT_BYTES = WARPS * RADIX * 32; // byte counters: [warp][digit][lane]
+
+template <typename KeyT, typename ValT, bool HAS_VALS, int ITEMS> constexpr size_t pass_smem_bytes()
+{
+    constexpr size_t units = (size_t)WARPS * (ITEMS / SUB);
+    constexpr size_t staging = (size_t)THREADS * ITEMS * (sizeof(KeyT) + (HAS_VALS ? sizeof(ValT) : 0));
+    return (staging > (size_t)CNT_BYTES ? staging : (size_t)CNT_BYTES) + units * RADIX * sizeof(unsigned short);
+}
+
 template <typename KeyT, typename ValT, bool HAS_VALS, int ITEMS>
 __global__ void __launch_bounds__(THREADS) k_onesweep_pass(const KeyT* __restrict__ keys_in, KeyT* __restrict__ keys_out,
     const ValT* __restrict__ vals_in, ValT* __restrict__ vals_out, const unsigned long long* d_n, size_t n_max, int shift,
     int bits, int pass_index, const unsigned* __restrict__ hist /* [RADIX] of this pass */,
-    unsigned* status_all /* [npasses][tiles(n)][RADIX] */, unsigned* tile_counter)
+    unsigned* status_all /* [npasses][tiles(n)][RADIX] */, unsigned* tile_counter, size_t skip_le)
 {
+    static_assert(ITEMS % SUB == 0, "a lane owns whole groups of 8 keys");
+    static_assert(THREADS == RADIX, "one thread per digit in the per-digit steps");
     constexpr int TILE = THREADS * ITEMS;
-    __shared__ unsigned s_warp_hist[WARPS][RADIX];
+    constexpr int UPW = ITEMS / SUB; // ranking units per warp
+    constexpr int UNITS = WARPS * UPW;
+    constexpr size_t STAGING = (size_t)TILE * (sizeof(KeyT) + (HAS_VALS ? sizeof(ValT) : 0));
+    constexpr size_t REGION0 = STAGING > (size_t)CNT_BYTES ? STAGING : (size_t)CNT_BYTES;
+    extern __shared__ __align__(16) unsigned char s_dyn[];
+    // region 0: byte counters while ranking, then the key/value staging of the reorder
+    KeyT* s_keys = reinterpret_cast<KeyT*>(s_dyn);
+    ValT* s_vals = reinterpret_cast<ValT*>(s_dyn + (size_t)TILE * sizeof(KeyT));
+    unsigned short(*s_unit_hist)[RADIX] = reinterpret_cast<unsigned short(*)[RADIX]>(s_dyn + REGION0); // [UNITS][RADIX]
     __shared__ unsigned s_tile_excl[RADIX];
     __shared__ unsigned s_global_off[RADIX];
     __shared__ unsigned s_scan[WARPS];
     __shared__ unsigned s_tile;
-    __shared__ KeyT s_keys[TILE];
-    __shared__ ValT s_vals[HAS_VALS ? TILE : 1];
 
     const size_t n = resolve_n(d_n, n_max);
+    if (n <= skip_le) return;
     const unsigned num_tiles = (unsigned)((n + TILE - 1) / TILE);
     unsigned* status = status_all + (size_t)pass_index * num_tiles * RADIX;
     const unsigned lane = threadIdx.x & 31u, w = threadIdx.x >> 5;
-    const unsigned lt = lanemask_lt();
+    unsigned char* s_cnt = s_dyn + (size_t)w * (RADIX * 32); // this warp's counters: [digit][lane]
 
     // exclusive scan of the pass histogram: where each digit's bucket starts in the output
     unsigned my_bucket_base = block_exclusive_scan(hist[threadIdx.x], s_scan, nullptr);
 
     for (;;) {
         if (threadIdx.x == 0) s_tile = atomicAdd(tile_counter, 1u);
-        for (int i = threadIdx.x; i < WARPS * RADIX; i += THREADS) (&s_warp_hist[0][0])[i] = 0;
         __syncthreads();
         const unsigned tile = s_tile;
         if (tile >= num_tiles) break;
         const size_t tile_base = (size_t)tile * TILE;
         const unsigned tile_n = (unsigned)((n - tile_base < (size_t)TILE) ? (n - tile_base) : (size_t)TILE);
+        const bool full = tile_n == (unsigned)TILE;
 
-        // ---- load (warp-striped inside each warp's contiguous chunk) and rank ----
-        KeyT key[ITEMS];
-        ValT val[HAS_VALS ? ITEMS : 1];
-        unsigned short rank[ITEMS];
+        // ---- load: 8 consecutive keys per lane and unit (16-byte vector loads on full tiles) ----
+        __align__(16) KeyT key[ITEMS];
+        __align__(16) ValT val[HAS_VALS ? ITEMS : 4];
+        unsigned char rank[ITEMS];
 #pragma unroll
-        for (int j = 0; j < ITEMS; ++j) {
-            const unsigned local = w * (32 * ITEMS) + j * 32 + lane;
-            const bool valid = local < tile_n;
-            key[j] = valid ? keys_in[tile_base + local] : (KeyT)0;
-            if (HAS_VALS) val[j] = valid ? (vals_in ? vals_in[tile_base + local] : (ValT)(tile_base + local)) : (ValT)0;
-        }
+        for (int u = 0; u < UPW; ++u) {
+            const unsigned local0 = w * (32 * ITEMS) + u * (32 * SUB) + lane * SUB;
+            if (full) {
+                constexpr int KV = SUB * sizeof(KeyT) / 16;
+                const uint4* kp = reinterpret_cast<const uint4*>(keys_in + tile_base + local0);
 #pragma unroll
-        for (int j = 0; j < ITEMS; ++j) {
-            const unsigned local = w * (32 * ITEMS) + j * 32 + lane;
-            const bool valid = local < tile_n;
-            const unsigned vmask = __ballot_sync(0xffffffffu, valid);
-            unsigned r = 0;
-            if (valid) {
-                const unsigned d = digit_of(key[j], shift, bits);
-                const unsigned peers = __match_any_sync(vmask, d);
-                const int leader = __ffs(peers) - 1;
-                unsigned old = 0;
-                if ((int)lane == leader) {
-                    old = s_warp_hist[w][d];
-                    s_warp_hist[w][d] = old + __popc(peers);
+                for (int q = 0; q < KV; ++q) reinterpret_cast<uint4*>(&key[u * SUB])[q] = kp[q];
+                if (HAS_VALS) {
+                    if (vals_in) {
+                        constexpr int VV = SUB * sizeof(ValT) / 16;
+                        const uint4* vp = reinterpret_cast<const uint4*>(vals_in + tile_base + local0);
+#pragma unroll
+                        for (int q = 0; q < VV; ++q) reinterpret_cast<uint4*>(&val[u * SUB])[q] = vp[q];
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < SUB; ++j) val[u * SUB + j] = (ValT)(tile_base + local0 + j);
+                    }
                 }
-                old = __shfl_sync(peers, old, leader);
-                r = old + __popc(peers & lt);
+            } else {
+#pragma unroll
+                for (int j = 0; j < SUB; ++j) {
+                    const unsigned local = local0 + j;
+                    const bool valid = local < tile_n;
+                    key[u * SUB + j] = valid ? keys_in[tile_base + local] : (KeyT)0;
+                    if (HAS_VALS) val[u * SUB + j] = valid ? (vals_in ? vals_in[tile_base + local] : (ValT)(tile_base + local)) : (ValT)0;
+                }
             }
-            rank[j] = (unsigned short)r;
+        }
+
+        // ---- rank, unit by unit ----
+#pragma unroll
+        for (int u = 0; u < UPW; ++u) {
+            const unsigned local0 = w * (32 * ITEMS) + u * (32 * SUB) + lane * SUB;
+            {
+                const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll
+                for (int q = 0; q < RADIX * 32 / 16 / 32; ++q) reinterpret_cast<uint4*>(s_cnt)[q * 32 + lane] = z;
+            }
+            __syncwarp();
+#pragma unroll
+            for (int j = 0; j < SUB; ++j) {
+                if (full || local0 + j < tile_n) {
+                    const unsigned d = digit_of(key[u * SUB + j], shift, bits);
+                    s_cnt[d * 32 + lane] += 1;
+                }
+            }
+            __syncwarp();
+            // one lane per digit row: 32 byte counts -> exclusive prefix over the lanes, row total -> unit histogram
+#pragma unroll
+            for (int k = 0; k < RADIX / 32; ++k) {
+                const unsigned d = k * 32 + lane;
+                uint4* row = reinterpret_cast<uint4*>(s_cnt + d * 32);
+                uint4 r0 = row[0], r1 = row[1];
+                unsigned wv[8] = { r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w };
+                unsigned running = 0;
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const unsigned t = wv[i];
+                    const unsigned tot = (t * 0x01010101u) >> 24; // <= 32
+                    wv[i] = (t << 8) * 0x01010101u + running * 0x01010101u; // byte b: earlier bytes of the word + earlier words
+                    running += tot;
+                }
+                row[0] = make_uint4(wv[0], wv[1], wv[2], wv[3]);
+                row[1] = make_uint4(wv[4], wv[5], wv[6], wv[7]);
+                s_unit_hist[w * UPW + u][d] = (unsigned short)running;
+            }
+            __syncwarp();
+#pragma unroll
+            for (int j = 0; j < SUB; ++j) {
+                unsigned char r = 0;
+                if (full || local0 + j < tile_n) {
+                    const unsigned d = digit_of(key[u * SUB + j], shift, bits);
+                    r = s_cnt[d * 32 + lane];
+                    s_cnt[d * 32 + lane] = (unsigned char)(r + 1);
+                }
+                rank[u * SUB + j] = r;
+            }
             __syncwarp();
         }
         __syncthreads();
 
-        // ---- per-digit: warp counts -> exclusive warp offsets, tile total ----
+        // ---- per-digit: unit counts -> exclusive unit offsets, tile total ----
         unsigned total = 0;
         {
             const unsigned d = threadIdx.x;
 #pragma unroll
-            for (int i = 0; i < WARPS; ++i) {
-                const unsigned c = s_warp_hist[i][d];
-                s_warp_hist[i][d] = total;
+            for (int i = 0; i < UNITS; ++i) {
+                const unsigned c = s_unit_hist[i][d];
+                s_unit_hist[i][d] = (unsigned short)total;
                 total += c;
             }
         }
@@ -247,17 +327,20 @@ __global__ void __launch_bounds__(THREADS) k_onesweep_pass(const KeyT* __restric
             }
             s_global_off[d] = my_bucket_base + prefix;
         }
-        __syncthreads();
+        __syncthreads(); // ranking is over in every warp: region 0 may now hold the staged keys
 
         // ---- reorder the tile through shared memory ----
 #pragma unroll
-        for (int j = 0; j < ITEMS; ++j) {
-            const unsigned local = w * (32 * ITEMS) + j * 32 + lane;
-            if (local < tile_n) {
-                const unsigned d = digit_of(key[j], shift, bits);
-                const unsigned pos = s_tile_excl[d] + s_warp_hist[w][d] + rank[j];
-                s_keys[pos] = key[j];
-                if (HAS_VALS) s_vals[pos] = val[j];
+        for (int u = 0; u < UPW; ++u) {
+            const unsigned local0 = w * (32 * ITEMS) + u * (32 * SUB) + lane * SUB;
+#pragma unroll
+            for (int j = 0; j < SUB; ++j) {
+                if (full || local0 + j < tile_n) {
+                    const unsigned d = digit_of(key[u * SUB + j], shift, bits);
+                    const unsigned pos = s_tile_excl[d] + s_unit_hist[w * UPW + u][d] + rank[u * SUB + j];
+                    s_keys[pos] = key[u * SUB + j];
+                    if (HAS_VALS) s_vals[pos] = val[u * SUB + j];
+                }
             }
         }
         __syncthreads();
@@ -306,7 +389,7 @@ inline int sort_prepare(mcb200_ctx* ctx)
 // in.  vals_in == nullptr with HAS_VALS: the value of element i is i.
 template <typename KeyT, typename ValT, bool HAS_VALS>
 int sort_passes(mcb200_ctx* ctx, const KeyT* keys_in, KeyT* keys_a, KeyT* keys_b, const ValT* vals_in, ValT* vals_a, ValT* vals_b,
-    const unsigned long long* d_n, size_t n_max, const pass_desc& pd, KeyT** keys_out, ValT** vals_out)
+    const unsigned long long* d_n, size_t n_max, const pass_desc& pd, KeyT** keys_out, ValT** vals_out, size_t skip_le = 0)
 {
     constexpr int ITEMS = items_for<KeyT>::value;
     constexpr int TILE = THREADS * ITEMS;
@@ -317,11 +400,21 @@ int sort_passes(mcb200_ctx* ctx, const KeyT* keys_in, KeyT* keys_a, KeyT* keys_b
     const unsigned pgrid = (unsigned)((tiles < (size_t)ctx->num_sms * 4) ? tiles : (size_t)ctx->num_sms * 4);
     const KeyT* kin = keys_in;
     const ValT* vin = vals_in;
+    constexpr size_t smem = pass_smem_bytes<KeyT, ValT, HAS_VALS, ITEMS>();
+    {
+        // the opt-in is per function and per device; a context is bound to one device
+        const int which = (sizeof(KeyT) == 8 ? 2 : 0) + (HAS_VALS ? 1 : 0);
+        if (!ctx->sort_smem_opt_in[which]) {
+            MCB_CUDA(ctx, cudaFuncSetAttribute(k_onesweep_pass<KeyT, ValT, HAS_VALS, ITEMS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                (int)smem));
+            ctx->sort_smem_opt_in[which] = true;
+        }
+    }
     for (int p = 0; p < pd.npasses; ++p) {
         KeyT* kout = (p & 1) ? keys_b : keys_a;
         ValT* vout = (p & 1) ? vals_b : vals_a;
-        MCB_LAUNCH_NAMED(ctx, pname, (k_onesweep_pass<KeyT, ValT, HAS_VALS, ITEMS>), pgrid, THREADS, 0, kin, kout, vin, vout, d_n, n_max,
-            pd.shift[p], pd.bits[p], p, sc.hist.as<unsigned>() + p * RADIX, sc.status.as<unsigned>(), sc.tilectr.as<unsigned>() + p);
+        MCB_LAUNCH_NAMED(ctx, pname, (k_onesweep_pass<KeyT, ValT, HAS_VALS, ITEMS>), pgrid, THREADS, smem, kin, kout, vin, vout, d_n, n_max,
+            pd.shift[p], pd.bits[p], p, sc.hist.as<unsigned>() + p * RADIX, sc.status.as<unsigned>(), sc.tilectr.as<unsigned>() + p, skip_le);
         kin = kout;
         vin = vout;
     }
@@ -332,7 +425,7 @@ int sort_passes(mcb200_ctx* ctx, const KeyT* keys_in, KeyT* keys_a, KeyT* keys_b
 
 template <typename KeyT, typename ValT, bool HAS_VALS>
 int sort(mcb200_ctx* ctx, const KeyT* keys_in, KeyT* keys_a, KeyT* keys_b, const ValT* vals_in, ValT* vals_a, ValT* vals_b,
-    const unsigned long long* d_n, size_t n_max, const pass_desc& pd, KeyT** keys_out, ValT** vals_out)
+    const unsigned long long* d_n, size_t n_max, const pass_desc& pd, KeyT** keys_out, ValT** vals_out, size_t skip_le = 0)
 {
     constexpr int TILE = THREADS * items_for<KeyT>::value;
     if (keys_out) *keys_out = const_cast<KeyT*>(keys_in);
@@ -345,8 +438,9 @@ int sort(mcb200_ctx* ctx, const KeyT* keys_in, KeyT* keys_a, KeyT* keys_b, const
     const unsigned hgrid = (unsigned)((tiles < (size_t)ctx->num_sms * 4) ? tiles : (size_t)ctx->num_sms * 4);
     const char* hname = sizeof(KeyT) == 4 ? "sort_histogram_u32" : "sort_histogram_u64";
     MCB_LAUNCH_NAMED(ctx, hname, (k_histogram<KeyT>), hgrid, THREADS, 0, keys_in, d_n, n_max, pd, TILE, sc.hist.as<unsigned>(),
-        sc.status.as<unsigned>());
-    return sort_passes<KeyT, ValT, HAS_VALS>(ctx, keys_in, keys_a, keys_b, vals_in, vals_a, vals_b, d_n, n_max, pd, keys_out, vals_out);
+        sc.status.as<unsigned>(), skip_le);
+    return sort_passes<KeyT, ValT, HAS_VALS>(ctx, keys_in, keys_a, keys_b, vals_in, vals_a, vals_b, d_n, n_max, pd, keys_out, vals_out,
+        skip_le);
 }
 
 } // namespace rsort
