@@ -354,7 +354,6 @@ void mcb200_mesh_free(mcb200_ctx* ctx, mcb200_mesh* m)
     ctx->release(m->sorted_faces);
     ctx->release(m->nodes);
     ctx->release(m->parent);
-    ctx->release(m->meta);
     ctx->release(m->flags);
     ctx->release(m->groups);
     ctx->release(m->group_up);

@@ -176,7 +176,6 @@ struct mcb200_mesh {
     dbuf sorted_faces; // [nf] u32 (leaf -> face)
     dbuf nodes; // [max(nf-1,1)] bvh_node_t (128 B)
     dbuf parent; // [2nf-1] u32 parent of internal node i / leaf (nf-1+j)
-    dbuf meta; // [nf-1] uint4 (left, right, first, last): compact copy of the node topology
     dbuf flags; // [nf-1] u32 refit arrival counters
     dbuf groups; // [nf] uint2 query groups (first leaf, count) + u32 counter after them
     dbuf group_up; // [<= nf] box + parent word of every group root (input of the atomic climb)

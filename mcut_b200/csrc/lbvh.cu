@@ -151,9 +151,10 @@ __global__ void __launch_bounds__(BLOCK) k_morton(const double* __restrict__ fac
 
 // ---- K_karras ---------------------------------------------------------------------------------------------------
 // One thread per internal node (Karras 2012).  A block owns 256 consecutive nodes and stages the sorted codes of a
-// +-1024 window in shared memory: the range/split binary searches of almost every node stay inside that window, so
-// their ~40 dependent probes cost shared-memory latency instead of L2 latency.
-constexpr int KHALO = 1024;
+// +-512 window in shared memory: the range/split binary searches of almost every node (every range up to 256 leaves,
+// the doubling search overshoots by 2x) stay inside that window, so their dependent probes cost shared-memory latency
+// instead of L2 latency; the few larger nodes fall back to global loads.
+constexpr int KHALO = 512;
 constexpr int KWIN = BLOCK + 2 * KHALO;
 
 struct code_window {
@@ -173,54 +174,6 @@ struct code_window {
         return __clz(ci ^ cj);
     }
 };
-
-__global__ void __launch_bounds__(BLOCK) k_karras(const uint32_t* __restrict__ codes, uint32_t nf, bvh_node_t* __restrict__ nodes,
-    uint4* __restrict__ meta, uint32_t* __restrict__ parent)
-{
-    __shared__ uint32_t s_win[KWIN];
-    const int n = (int)nf;
-    for (int i0 = blockIdx.x * BLOCK; i0 < n - 1; i0 += gridDim.x * BLOCK) {
-        const int base = i0 - KHALO;
-        __syncthreads();
-        for (int r = threadIdx.x; r < KWIN; r += BLOCK) {
-            const int j = base + r;
-            s_win[r] = (j >= 0 && j < n) ? __ldg(codes + j) : 0u;
-        }
-        __syncthreads();
-        const int i = i0 + (int)threadIdx.x;
-        if (i >= n - 1) continue;
-        const code_window cw { codes, s_win, base, n };
-        const uint32_t ci = cw.get(i);
-        const int d = (cw.delta(i, ci, i + 1) - cw.delta(i, ci, i - 1)) >= 0 ? 1 : -1;
-        const int dmin = cw.delta(i, ci, i - d);
-        int lmax = 2;
-        while (cw.delta(i, ci, i + lmax * d) > dmin) lmax <<= 1;
-        int l = 0;
-        for (int t = lmax >> 1; t >= 1; t >>= 1)
-            if (cw.delta(i, ci, i + (l + t) * d) > dmin) l += t;
-        const int j = i + l * d;
-        const int dnode = cw.delta(i, ci, j);
-        int s = 0;
-        int t = l;
-        do {
-            t = (t + 1) >> 1;
-            if (cw.delta(i, ci, i + (s + t) * d) > dnode) s += t;
-        } while (t > 1);
-        const int gamma = i + s * d + (d < 0 ? -1 : 0);
-        const int lo = i < j ? i : j, hi = i < j ? j : i;
-        const uint32_t left = (lo == gamma) ? (MCB_LEAF_BIT | (uint32_t)gamma) : (uint32_t)gamma;
-        const uint32_t right = (hi == gamma + 1) ? (MCB_LEAF_BIT | (uint32_t)(gamma + 1)) : (uint32_t)(gamma + 1);
-        const uint4 m = make_uint4(left, right, (uint32_t)lo, (uint32_t)hi);
-        *reinterpret_cast<uint4*>(&nodes[i].left) = m; // inside the 128-byte record the traversal reads
-        meta[i] = m; // compact copy the refit reads coalesced
-        // parent word of a child: (parent index << 2) | (parent covers more than 32 leaves) << 1 | (child is the right one)
-        // — everything the refit needs to know about the parent without touching the parent's record
-        const uint32_t pw = ((uint32_t)i << 2) | ((hi - lo + 1 > 32) ? 2u : 0u);
-        parent[(left & MCB_LEAF_BIT) ? (nf - 1 + (left & ~MCB_LEAF_BIT)) : left] = pw;
-        parent[(right & MCB_LEAF_BIT) ? (nf - 1 + (right & ~MCB_LEAF_BIT)) : right] = pw | 1u;
-        if (i == 0) parent[0] = MCB200_NULL;
-    }
-}
 
 // ---- K_refit ----------------------------------------------------------------------------------------------------
 // One thread per leaf carries its box up; the first thread to reach a node parks its box in the node and leaves,
@@ -285,12 +238,16 @@ __device__ __forceinline__ unsigned alloc_groups_block(unsigned* n_groups, unsig
     return *s_base + s_warp[w] + inc - want;
 }
 
-// Refit in two regimes, two kernels:
-//  * k_refit_treelets: a node whose leaf range has at most 32 leaves gets both child boxes straight from the leaf boxes
-//    of its range (a Karras node knows its range and its split, so no other node's result is needed): no atomics, no
-//    fences.  A block owns 256 consecutive node indices; node i lies inside its own range, so every such range falls in
-//    the block's leaf window [i0-32, i0+288), gathered ONCE into shared memory with all loads in flight at once.  The
+// Tree and refit in two regimes, two kernels:
+//  * k_tree: one thread per internal node finds its range and split (Karras 2012) from the block's shared window of
+//    sorted codes.  A node whose leaf range has at most 32 leaves then gets both child boxes straight from the leaf boxes
+//    of its range (it knows its range and its split, so no other node's result is needed): no atomics, no fences, and the
+//    whole 128-byte record (boxes + topology) is written at once.  Node i lies inside its own range, so every such range
+//    falls in the block's leaf window [i0-32, i0+288), gathered into shared memory while the code window loads.  The
 //    maximal treelets ("group roots") are listed: they are the traversal's query groups and the starting points of ...
+//    Whether a node's PARENT covers more than 32 leaves is decided locally: the parent's range is the set of keys sharing
+//    the parent's prefix (length delta(i, i - d), the `dmin` of the range search), so it has more than 32 leaves exactly
+//    when the key 32 positions beyond the node's far end still shares that prefix.
 //  * k_refit_climb: ... the classic atomic bottom-up pass for the ~nf/16 nodes above the treelets: one thread per group
 //    root carries its box upwards; the first thread to reach a node parks its box there and leaves, the second one
 //    merges and continues.  All climbers are resident at once, so the pass costs (levels above the treelets) x (one
@@ -298,12 +255,13 @@ __device__ __forceinline__ unsigned alloc_groups_block(unsigned* n_groups, unsig
 constexpr int RHALO = 32;
 constexpr int RWIN = BLOCK + 2 * RHALO;
 
-__global__ void __launch_bounds__(BLOCK) k_refit_treelets(const double* __restrict__ face_bbox,
-    const uint32_t* __restrict__ sorted_faces, uint32_t nf, bvh_node_t* nodes, const uint4* __restrict__ meta,
-    const uint32_t* __restrict__ parent, uint2* __restrict__ groups, group_up_t* __restrict__ group_up,
-    unsigned* __restrict__ n_groups)
+__global__ void __launch_bounds__(BLOCK) k_tree(const uint32_t* __restrict__ codes, const double* __restrict__ face_bbox,
+    const uint32_t* __restrict__ sorted_faces, uint32_t nf, bvh_node_t* nodes, uint32_t* __restrict__ parent,
+    uint2* __restrict__ groups, group_up_t* __restrict__ group_up, unsigned* __restrict__ n_groups)
 {
+    __shared__ uint32_t s_win[KWIN];
     __shared__ double s_box[RWIN][6];
+    __shared__ unsigned s_warp[BLOCK / 32], s_base;
     if (nf == 1) {
         // a single leaf (e.g. the planar-section triangle): pseudo-root whose right child can never be hit
         if (blockIdx.x == 0 && threadIdx.x == 0) {
@@ -323,71 +281,126 @@ __global__ void __launch_bounds__(BLOCK) k_refit_treelets(const double* __restri
         }
         return;
     }
+    const int n = (int)nf;
     const uint32_t i0 = blockIdx.x * BLOCK;
-    for (int r = threadIdx.x; r < RWIN; r += BLOCK) {
-        const long long j = (long long)i0 - RHALO + r;
-        if (j >= 0 && j < (long long)nf) {
-            double b[6];
-            load_face_box(face_bbox, __ldg(sorted_faces + j), b);
+    const int cbase = (int)i0 - KHALO;
+    {
+        // both windows with every load in flight before the first store (a load->store loop would serialise L2 round trips)
+        static_assert(KWIN % BLOCK == 0 && RWIN <= 2 * BLOCK, "window shapes");
+        uint32_t cw_reg[KWIN / BLOCK];
 #pragma unroll
-            for (int k = 0; k < 6; ++k) s_box[r][k] = b[k];
+        for (int k = 0; k < KWIN / BLOCK; ++k) {
+            const int j = cbase + k * BLOCK + (int)threadIdx.x;
+            cw_reg[k] = (j >= 0 && j < n) ? __ldg(codes + j) : 0u;
+        }
+        const long long j0 = (long long)i0 - RHALO + threadIdx.x, j1 = j0 + BLOCK;
+        const bool have0 = j0 >= 0 && j0 < (long long)nf, have1 = threadIdx.x < RWIN - BLOCK && j1 < (long long)nf;
+        const uint32_t f0 = have0 ? __ldg(sorted_faces + j0) : 0u, f1 = have1 ? __ldg(sorted_faces + j1) : 0u;
+        double b0[6], b1[6];
+        if (have0) load_face_box(face_bbox, f0, b0);
+        if (have1) load_face_box(face_bbox, f1, b1);
+#pragma unroll
+        for (int k = 0; k < KWIN / BLOCK; ++k) s_win[k * BLOCK + threadIdx.x] = cw_reg[k];
+        if (have0) {
+#pragma unroll
+            for (int k = 0; k < 6; ++k) s_box[threadIdx.x][k] = b0[k];
+        }
+        if (have1) {
+#pragma unroll
+            for (int k = 0; k < 6; ++k) s_box[BLOCK + threadIdx.x][k] = b1[k];
         }
     }
     __syncthreads();
     const uint32_t i = i0 + threadIdx.x;
     const int wbase = (int)i0 - RHALO; // leaf j sits in s_box[j - wbase]
-    __shared__ unsigned s_warp[BLOCK / 32], s_base;
-    // role 0: internal node i
-    bool root0 = false, root1 = false;
-    double box[6];
-    uint32_t pw0 = 0, pw1 = 0, first = 0, count = 0;
+    const code_window cw { codes, s_win, cbase, n };
+
+    // ---- topology first: node i's range, split and children; is it (or leaf i) the root of a maximal treelet? ----
+    bool root0 = false, root1 = false, small = false;
+    int lo = 0, hi = 0, gamma = 0;
     if (i < nf - 1u) {
-        const uint4 m = __ldg(meta + i);
-        first = m.z;
-        const uint32_t last = m.w;
-        count = last - first + 1u;
-        if (count <= 32u) {
-            const uint32_t gamma = m.x & ~MCB_LEAF_BIT;
-            double rb[6];
+        const int ii = (int)i;
+        const uint32_t ci = cw.get(ii);
+        const int d = (cw.delta(ii, ci, ii + 1) - cw.delta(ii, ci, ii - 1)) >= 0 ? 1 : -1;
+        const int dmin = cw.delta(ii, ci, ii - d); // = length of the parent's prefix
+        int lmax = 2;
+        while (cw.delta(ii, ci, ii + lmax * d) > dmin) lmax <<= 1;
+        int l = 0;
+        for (int t = lmax >> 1; t >= 1; t >>= 1)
+            if (cw.delta(ii, ci, ii + (l + t) * d) > dmin) l += t;
+        const int j = ii + l * d;
+        const int dnode = cw.delta(ii, ci, j);
+        int sp = 0;
+        int t = l;
+        do {
+            t = (t + 1) >> 1;
+            if (cw.delta(ii, ci, ii + (sp + t) * d) > dnode) sp += t;
+        } while (t > 1);
+        gamma = ii + sp * d + (d < 0 ? -1 : 0);
+        lo = ii < j ? ii : j;
+        hi = ii < j ? j : ii;
+        const uint32_t left = (lo == gamma) ? (MCB_LEAF_BIT | (uint32_t)gamma) : (uint32_t)gamma;
+        const uint32_t right = (hi == gamma + 1) ? (MCB_LEAF_BIT | (uint32_t)(gamma + 1)) : (uint32_t)(gamma + 1);
+        // parent word of a child: (parent index << 2) | (child is the right one); read by the climb
+        const uint32_t pw = (uint32_t)i << 2;
+        parent[(left & MCB_LEAF_BIT) ? (nf - 1 + (left & ~MCB_LEAF_BIT)) : left] = pw;
+        parent[(right & MCB_LEAF_BIT) ? (nf - 1 + (right & ~MCB_LEAF_BIT)) : right] = pw | 1u;
+        if (i == 0) parent[0] = MCB200_NULL;
+        *reinterpret_cast<uint4*>(&nodes[i].left) = make_uint4(left, right, (uint32_t)lo, (uint32_t)hi);
+        small = hi - lo + 1 <= 32;
+        if (small) {
+            // a maximal treelet: the whole tree, or the parent's range reaches past 32 leaves
+            const int probe = (d > 0) ? hi - 32 : lo + 32;
+            root0 = (i == 0u) || (probe >= 0 && probe < n && cw.delta(ii, ci, probe) >= dmin);
+        }
+    }
+    // leaf i hangs directly under a node that covers more than 32 leaves?  A leaf joins the neighbour it shares the longer
+    // prefix with; that prefix is its parent's.
+    if (i < nf) {
+        const int ii = (int)i;
+        const uint32_t ci = cw.get(ii);
+        const int dl = cw.delta(ii, ci, ii - 1), dr = cw.delta(ii, ci, ii + 1);
+        const bool is_left = dr > dl;
+        const int dp = is_left ? dr : dl;
+        const int probe = is_left ? ii + 32 : ii - 32;
+        root1 = probe >= 0 && probe < n && cw.delta(ii, ci, probe) >= dp;
+    }
+    // the block-wide slot allocation (a barrier) sits here, before the box loops whose length differs from thread to thread
+    unsigned g = alloc_groups_block(n_groups, (root0 ? 1u : 0u) + (root1 ? 1u : 0u), s_warp, &s_base);
+
+    // ---- boxes of the small nodes straight from the leaf window ----
+    if (small) {
+        double box[6], rb[6];
 #pragma unroll
-            for (int k = 0; k < 6; ++k) {
-                box[k] = s_box[(int)first - wbase][k];
-                rb[k] = s_box[(int)gamma + 1 - wbase][k];
+        for (int k = 0; k < 6; ++k) {
+            box[k] = s_box[lo - wbase][k];
+            rb[k] = s_box[gamma + 1 - wbase][k];
+        }
+        for (int q = lo + 1; q <= gamma; ++q)
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                box[k] = ref_min(box[k], s_box[q - wbase][k]);
+                box[3 + k] = ref_max(box[3 + k], s_box[q - wbase][3 + k]);
             }
-            for (uint32_t j = first + 1u; j <= gamma; ++j)
+        for (int q = gamma + 2; q <= hi; ++q)
 #pragma unroll
-                for (int k = 0; k < 3; ++k) {
-                    box[k] = ref_min(box[k], s_box[(int)j - wbase][k]);
-                    box[3 + k] = ref_max(box[3 + k], s_box[(int)j - wbase][3 + k]);
-                }
-            for (uint32_t j = gamma + 2u; j <= last; ++j)
-#pragma unroll
-                for (int k = 0; k < 3; ++k) {
-                    rb[k] = ref_min(rb[k], s_box[(int)j - wbase][k]);
-                    rb[3 + k] = ref_max(rb[3 + k], s_box[(int)j - wbase][3 + k]);
-                }
-            store_box(nodes[i].lbox, box);
-            store_box(nodes[i].rbox, rb);
-            pw0 = (i == 0u) ? MCB200_NULL : __ldg(parent + i);
-            root0 = (i == 0u) || (pw0 & 2u); // a maximal treelet (or the whole tree)
+            for (int k = 0; k < 3; ++k) {
+                rb[k] = ref_min(rb[k], s_box[q - wbase][k]);
+                rb[3 + k] = ref_max(rb[3 + k], s_box[q - wbase][3 + k]);
+            }
+        store_box(nodes[i].lbox, box);
+        store_box(nodes[i].rbox, rb);
+        if (root0) {
 #pragma unroll
             for (int k = 0; k < 3; ++k) {
                 box[k] = ref_min(box[k], rb[k]);
                 box[3 + k] = ref_max(box[3 + k], rb[3 + k]);
             }
+            groups[g] = make_uint2((uint32_t)lo, (uint32_t)(hi - lo + 1));
+            store_box(group_up[g].box, box);
+            group_up[g].pw = (i == 0u) ? MCB200_NULL : i; // where the climb finds this root's parent word
+            ++g;
         }
-    }
-    // role 1: leaf i, when it hangs directly under a node that covers more than 32 leaves
-    if (i < nf) {
-        pw1 = __ldg(parent + (nf - 1u + i));
-        root1 = (pw1 & 2u) != 0u;
-    }
-    unsigned g = alloc_groups_block(n_groups, (root0 ? 1u : 0u) + (root1 ? 1u : 0u), s_warp, &s_base);
-    if (root0) {
-        groups[g] = make_uint2(first, count);
-        store_box(group_up[g].box, box);
-        group_up[g].pw = pw0;
-        ++g;
     }
     if (root1) {
         groups[g] = make_uint2(i, 1u);
@@ -395,7 +408,7 @@ __global__ void __launch_bounds__(BLOCK) k_refit_treelets(const double* __restri
 #pragma unroll
         for (int k = 0; k < 6; ++k) lb[k] = s_box[(int)i - wbase][k];
         store_box(group_up[g].box, lb);
-        group_up[g].pw = pw1;
+        group_up[g].pw = nf - 1u + i;
     }
 }
 
@@ -404,8 +417,9 @@ __global__ void __launch_bounds__(BLOCK) k_refit_climb(bvh_node_t* nodes, const 
 {
     const unsigned ng = *n_groups;
     for (unsigned g = blockIdx.x * BLOCK + threadIdx.x; g < ng; g += gridDim.x * BLOCK) {
-        uint32_t pw = group_up[g].pw;
-        if (pw == MCB200_NULL) continue; // the whole tree was one treelet
+        const uint32_t slot = group_up[g].pw;
+        if (slot == MCB200_NULL) continue; // the whole tree was one treelet
+        uint32_t pw = __ldg(parent + slot);
         double box[6];
         {
             const double2* in = reinterpret_cast<const double2*>(group_up[g].box);
@@ -450,7 +464,6 @@ int lbvh_reserve(mcb200_ctx* ctx, mcb200_mesh* m)
     MCB_TRY(ctx->reserve(m->sorted_faces, sizeof(uint32_t) * (size_t)nf));
     MCB_TRY(ctx->reserve(m->nodes, sizeof(bvh_node_t) * (size_t)(nf > 1 ? nf - 1 : 1)));
     MCB_TRY(ctx->reserve(m->parent, sizeof(uint32_t) * (2 * (size_t)nf)));
-    MCB_TRY(ctx->reserve(m->meta, sizeof(uint4) * (size_t)nf));
     MCB_TRY(ctx->reserve(m->flags, sizeof(unsigned) * (size_t)nf));
     MCB_TRY(ctx->reserve(m->groups, sizeof(uint2) * (size_t)nf + sizeof(unsigned) * 4));
     MCB_TRY(ctx->reserve(m->group_up, sizeof(group_up_t) * (size_t)nf));
@@ -497,13 +510,8 @@ int lbvh_build(mcb200_ctx* ctx, mcb200_mesh* m, double eps)
         ctx->set_error("internal: Morton sort must use an even number of passes", __FILE__, __LINE__);
         return MCB200_ERR_INTERNAL;
     }
-    if (nf > 1) {
-        const unsigned g2 = div_up(nf - 1, BLOCK); // one 256-node window per block
-        MCB_LAUNCH(ctx, k_karras, g2, BLOCK, 0, m->sorted_codes.as<uint32_t>(), nf, m->nodes.as<bvh_node_t>(), m->meta.as<uint4>(),
-            m->parent.as<uint32_t>());
-    }
-    MCB_LAUNCH(ctx, k_refit_treelets, div_up(nf, BLOCK), BLOCK, 0, m->face_bbox.as<double>(), m->sorted_faces.as<uint32_t>(), nf,
-        m->nodes.as<bvh_node_t>(), m->meta.as<uint4>(), m->parent.as<uint32_t>(), m->groups.as<uint2>(),
+    MCB_LAUNCH(ctx, k_tree, div_up(nf, BLOCK), BLOCK, 0, m->sorted_codes.as<uint32_t>(), m->face_bbox.as<double>(),
+        m->sorted_faces.as<uint32_t>(), nf, m->nodes.as<bvh_node_t>(), m->parent.as<uint32_t>(), m->groups.as<uint2>(),
         m->group_up.as<group_up_t>(), n_groups);
     if (nf > 1) {
         // enough threads for every group root to climb concurrently (about nf/16 of them; nf/4 is a safe bound for the grid,
