@@ -102,6 +102,8 @@ int mcb200_ctx_create(int device, void* stream, mcb200_ctx** out)
     cudaStreamCreateWithFlags(&ctx->copy, cudaStreamNonBlocking);
     cudaStreamCreateWithPriority(&ctx->bg, cudaStreamNonBlocking, prio_lo);
     cudaEventCreateWithFlags(&ctx->ev_bg, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&ctx->ev_np, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&ctx->ev_np2, cudaEventDisableTiming);
     for (auto& ev : ctx->ev_up) cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
     cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming);
     cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming);
@@ -128,6 +130,8 @@ void mcb200_ctx_destroy(mcb200_ctx* ctx)
     cudaStreamSynchronize(ctx->bg);
     cudaStreamDestroy(ctx->bg);
     cudaEventDestroy(ctx->ev_bg);
+    cudaEventDestroy(ctx->ev_np);
+    cudaEventDestroy(ctx->ev_np2);
     for (int k = 0; k < 2; ++k) {
         if (ctx->st_mesh[k]) mcb200_mesh_free(ctx, ctx->st_mesh[k]);
         ctx->release(ctx->st_xyz[k]);

@@ -166,6 +166,19 @@ struct code_window {
         const int r = j - base;
         return ((unsigned)r < (unsigned)KWIN) ? win[r] : __ldg(codes + j);
     }
+    // window-only probe: a key outside the shared window reads as "no common prefix" and raises `miss`
+    __device__ __forceinline__ int delta_win(int i, uint32_t ci, int j, bool& miss) const
+    {
+        if (j < 0 || j >= n) return -1;
+        const int r = j - base;
+        if ((unsigned)r >= (unsigned)KWIN) {
+            miss = true;
+            return -1;
+        }
+        const uint32_t cj = win[r];
+        if (ci == cj) return 32 + __clz((unsigned)i ^ (unsigned)j);
+        return __clz(ci ^ cj);
+    }
     __device__ __forceinline__ int delta(int i, uint32_t ci, int j) const
     {
         if (j < 0 || j >= n) return -1;
@@ -208,6 +221,49 @@ __device__ __forceinline__ void load_face_box(const double* __restrict__ face_bb
     b[3] = c.y;
     b[4] = e.x;
     b[5] = e.y;
+}
+
+// Range, split and direction of internal node i (Karras 2012, Fig. 4).  WINDOW_ONLY: probes never leave the shared code
+// window; a search that would is abandoned with `miss` set (such a node covers more than 512 leaves) and is redone later
+// with global probes, off the block's common path.
+struct node_topology {
+    int lo, hi, gamma, d, dmin;
+};
+template <bool WINDOW_ONLY> __device__ __forceinline__ node_topology karras_node(const code_window& cw, int ii, bool& miss)
+{
+    auto dl = [&](int j) -> int { return WINDOW_ONLY ? cw.delta_win(ii, cw.get(ii), j, miss) : cw.delta(ii, cw.get(ii), j); };
+    node_topology t;
+    t.d = (dl(ii + 1) - dl(ii - 1)) >= 0 ? 1 : -1;
+    t.dmin = dl(ii - t.d); // = length of the parent's prefix
+    int lmax = 2;
+    while (dl(ii + lmax * t.d) > t.dmin) lmax <<= 1;
+    int l = 0;
+    for (int s = lmax >> 1; s >= 1; s >>= 1)
+        if (dl(ii + (l + s) * t.d) > t.dmin) l += s;
+    const int j = ii + l * t.d;
+    const int dnode = dl(j);
+    int sp = 0;
+    int s = l;
+    do {
+        s = (s + 1) >> 1;
+        if (dl(ii + (sp + s) * t.d) > dnode) sp += s;
+    } while (s > 1);
+    t.gamma = ii + sp * t.d + (t.d < 0 ? -1 : 0);
+    t.lo = ii < j ? ii : j;
+    t.hi = ii < j ? j : ii;
+    return t;
+}
+
+__device__ __forceinline__ void write_topology(bvh_node_t* nodes, uint32_t* parent, uint32_t nf, uint32_t i, const node_topology& t)
+{
+    const uint32_t left = (t.lo == t.gamma) ? (MCB_LEAF_BIT | (uint32_t)t.gamma) : (uint32_t)t.gamma;
+    const uint32_t right = (t.hi == t.gamma + 1) ? (MCB_LEAF_BIT | (uint32_t)(t.gamma + 1)) : (uint32_t)(t.gamma + 1);
+    // parent word of a child: (parent index << 2) | (child is the right one); read by the climb
+    const uint32_t pw = i << 2;
+    parent[(left & MCB_LEAF_BIT) ? (nf - 1 + (left & ~MCB_LEAF_BIT)) : left] = pw;
+    parent[(right & MCB_LEAF_BIT) ? (nf - 1 + (right & ~MCB_LEAF_BIT)) : right] = pw | 1u;
+    if (i == 0) parent[0] = MCB200_NULL;
+    *reinterpret_cast<uint4*>(&nodes[i].left) = make_uint4(left, right, (uint32_t)t.lo, (uint32_t)t.hi);
 }
 
 // Slots in the group list for a whole block with ONE global atomic (tens of thousands of same-address atomics from
@@ -316,42 +372,22 @@ __global__ void __launch_bounds__(BLOCK) k_tree(const uint32_t* __restrict__ cod
     const code_window cw { codes, s_win, cbase, n };
 
     // ---- topology first: node i's range, split and children; is it (or leaf i) the root of a maximal treelet? ----
-    bool root0 = false, root1 = false, small = false;
+    bool root0 = false, root1 = false, small = false, deferred = false;
     int lo = 0, hi = 0, gamma = 0;
     if (i < nf - 1u) {
         const int ii = (int)i;
-        const uint32_t ci = cw.get(ii);
-        const int d = (cw.delta(ii, ci, ii + 1) - cw.delta(ii, ci, ii - 1)) >= 0 ? 1 : -1;
-        const int dmin = cw.delta(ii, ci, ii - d); // = length of the parent's prefix
-        int lmax = 2;
-        while (cw.delta(ii, ci, ii + lmax * d) > dmin) lmax <<= 1;
-        int l = 0;
-        for (int t = lmax >> 1; t >= 1; t >>= 1)
-            if (cw.delta(ii, ci, ii + (l + t) * d) > dmin) l += t;
-        const int j = ii + l * d;
-        const int dnode = cw.delta(ii, ci, j);
-        int sp = 0;
-        int t = l;
-        do {
-            t = (t + 1) >> 1;
-            if (cw.delta(ii, ci, ii + (sp + t) * d) > dnode) sp += t;
-        } while (t > 1);
-        gamma = ii + sp * d + (d < 0 ? -1 : 0);
-        lo = ii < j ? ii : j;
-        hi = ii < j ? j : ii;
-        const uint32_t left = (lo == gamma) ? (MCB_LEAF_BIT | (uint32_t)gamma) : (uint32_t)gamma;
-        const uint32_t right = (hi == gamma + 1) ? (MCB_LEAF_BIT | (uint32_t)(gamma + 1)) : (uint32_t)(gamma + 1);
-        // parent word of a child: (parent index << 2) | (child is the right one); read by the climb
-        const uint32_t pw = (uint32_t)i << 2;
-        parent[(left & MCB_LEAF_BIT) ? (nf - 1 + (left & ~MCB_LEAF_BIT)) : left] = pw;
-        parent[(right & MCB_LEAF_BIT) ? (nf - 1 + (right & ~MCB_LEAF_BIT)) : right] = pw | 1u;
-        if (i == 0) parent[0] = MCB200_NULL;
-        *reinterpret_cast<uint4*>(&nodes[i].left) = make_uint4(left, right, (uint32_t)lo, (uint32_t)hi);
-        small = hi - lo + 1 <= 32;
-        if (small) {
-            // a maximal treelet: the whole tree, or the parent's range reaches past 32 leaves
-            const int probe = (d > 0) ? hi - 32 : lo + 32;
-            root0 = (i == 0u) || (probe >= 0 && probe < n && cw.delta(ii, ci, probe) >= dmin);
+        const node_topology t = karras_node<true>(cw, ii, deferred);
+        if (!deferred) {
+            write_topology(nodes, parent, nf, i, t);
+            lo = t.lo;
+            hi = t.hi;
+            gamma = t.gamma;
+            small = hi - lo + 1 <= 32;
+            if (small) {
+                // a maximal treelet: the whole tree, or the parent's range reaches past 32 leaves
+                const int probe = (t.d > 0) ? hi - 32 : lo + 32;
+                root0 = (i == 0u) || (probe >= 0 && probe < n && cw.delta(ii, cw.get(ii), probe) >= t.dmin);
+            }
         }
     }
     // leaf i hangs directly under a node that covers more than 32 leaves?  A leaf joins the neighbour it shares the longer
@@ -409,6 +445,12 @@ __global__ void __launch_bounds__(BLOCK) k_tree(const uint32_t* __restrict__ cod
         for (int k = 0; k < 6; ++k) lb[k] = s_box[(int)i - wbase][k];
         store_box(group_up[g].box, lb);
         group_up[g].pw = nf - 1u + i;
+    }
+    // the few nodes whose range leaves the window (> 512 leaves): dependent global probes, now that nobody waits for them
+    if (deferred) {
+        bool unused = false;
+        const node_topology t = karras_node<false>(cw, (int)i, unused);
+        write_topology(nodes, parent, nf, i, t);
     }
 }
 

@@ -354,13 +354,17 @@ __device__ __forceinline__ bool setup_test(const narrow_args_t& a, uint32_t s, u
     return overlap6(eb, tbox);
 }
 
+// Work items: the exact kernel takes queue entries (pair, slot); the filter takes pairs and walks the slots of its pair
+// in a loop (SPLIT, one thread per (pair, slot), is kept for experiments: it was slower, the per-pair loads dominate).
 template <bool TRI, bool EXACT> __global__ void __launch_bounds__(NBLOCK) k_tests(narrow_args_t a)
 {
+    constexpr bool SPLIT = false; // measured: 6 short threads per pair cost 2.4x the instructions and 38 us instead of 27
     unsigned long long n_items;
     if (EXACT) {
         n_items = a.counters->n_exact < a.cap_exact ? a.counters->n_exact : a.cap_exact;
     } else {
         n_items = a.counters->n_pairs < a.cap_pairs ? a.counters->n_pairs : a.cap_pairs;
+        if (SPLIT) n_items *= 6ull;
     }
     unsigned n_tests_local = 0, gp = 0;
     for (unsigned long long it = (unsigned long long)blockIdx.x * NBLOCK + threadIdx.x; it < n_items;
@@ -371,6 +375,9 @@ template <bool TRI, bool EXACT> __global__ void __launch_bounds__(NBLOCK) k_test
             const unsigned long long e = a.exact_queue[it];
             pair_index = e >> 8;
             only_slot = (uint32_t)(e & 0xFFu);
+        } else if (SPLIT) {
+            pair_index = it / 6ull;
+            only_slot = (uint32_t)(it - pair_index * 6ull);
         }
         const unsigned long long pr = a.pairs[pair_index];
         const uint32_t s = (uint32_t)(pr >> 32), c = (uint32_t)(pr & 0xFFFFFFFFu);
@@ -378,7 +385,7 @@ template <bool TRI, bool EXACT> __global__ void __launch_bounds__(NBLOCK) k_test
         const uint32_t ns = TRI ? 3u : __ldg(a.face_off + s + 1) - hs;
         const uint32_t hc = TRI ? 3u * (a.nsf + c) : __ldg(a.face_off + a.nsf + c);
         const uint32_t nc = TRI ? 3u : __ldg(a.face_off + a.nsf + c + 1) - hc;
-        if (!EXACT) {
+        if (!EXACT && (!SPLIT || only_slot == 0u)) {
             a.cand_flag[s] = 1;
             a.cand_flag[a.nsf + c] = 1;
         }
@@ -395,7 +402,7 @@ template <bool TRI, bool EXACT> __global__ void __launch_bounds__(NBLOCK) k_test
         load_box(a.cut_bbox + 6 * (size_t)c, cbox);
         const face_view SF { &a, hs, ns }, CF { &a, hc, nc };
         const uint32_t nslots = ns + nc;
-        for (uint32_t slot = EXACT ? only_slot : 0u; slot < (EXACT ? only_slot + 1u : nslots); ++slot) {
+        for (uint32_t slot = (EXACT || SPLIT) ? only_slot : 0u; slot < ((EXACT || SPLIT) ? only_slot + 1u : nslots); ++slot) {
             uint32_t edge, tested_face;
             bool from_src;
             double q[3], r[3];
@@ -467,40 +474,57 @@ template <bool TRI> __global__ void __launch_bounds__(NBLOCK) k_planes(plane_arg
 // ---- canonical ordering of records / logged tests -----------------------------------------------------------------------
 // Up to SMALL_SORT items (the usual case: an intersection curve crosses thousands of edges, not millions) are ordered by
 // counting: the rank of an item is the number of items with a smaller (edge, face) key — keys are unique — and the item is
-// written straight to its place.  32 items per block, 8 threads share one item's scan.  One launch instead of
+// written straight to its place.  16 items per block, 16 threads share one item's scan.  One launch instead of
 // key extraction + histogram + six radix passes + gather; those kernels return at once when n <= SMALL_SORT.
 constexpr unsigned SMALL_SORT = 16384;
-constexpr int RANK_CHUNK = 1024;
+constexpr int RANK_CHUNK = 4096; // keys staged per round (32 KB)
+constexpr int RANK_ITEMS = 16; // items per block: 16 threads share one item's scan
+
+template <typename T> __device__ __forceinline__ unsigned long long item_key(const T* item)
+{
+    // {uint32 edge, uint32 face} lead every item: one 8-byte load, halves swapped into (edge << 32 | face)
+    const unsigned long long v = __ldg(reinterpret_cast<const unsigned long long*>(item));
+    return (v << 32) | (v >> 32);
+}
 
 template <typename T> __global__ void __launch_bounds__(256) k_rank_sort_small(const T* __restrict__ items,
     const unsigned long long* d_n, unsigned long long cap, T* __restrict__ out)
 {
+    static_assert(sizeof(T) % 8 == 0 && alignof(T) >= 8 && offsetof(T, edge) == 0 && offsetof(T, face) == 4, "item layout");
     __shared__ unsigned long long s_keys[RANK_CHUNK];
     const unsigned long long n64 = *d_n < cap ? *d_n : cap;
-    if (n64 > SMALL_SORT || (unsigned long long)blockIdx.x * 32u >= n64) return;
+    if (n64 > SMALL_SORT || (unsigned long long)blockIdx.x * RANK_ITEMS >= n64) return;
     const unsigned n = (unsigned)n64;
-    const unsigned i = blockIdx.x * 32u + (threadIdx.x >> 3), sub = threadIdx.x & 7u;
+    const unsigned i = blockIdx.x * RANK_ITEMS + (threadIdx.x >> 4), sub = threadIdx.x & 15u;
     const bool live = i < n;
-    const unsigned long long mine = live ? (((unsigned long long)items[i].edge << 32) | items[i].face) : ~0ull;
+    const unsigned long long mine = live ? item_key(items + i) : ~0ull;
     unsigned rank = 0;
     for (unsigned base = 0; base < n; base += RANK_CHUNK) {
         const unsigned cn = (n - base < (unsigned)RANK_CHUNK) ? n - base : (unsigned)RANK_CHUNK;
-        for (unsigned j = threadIdx.x; j < (unsigned)RANK_CHUNK; j += 256u)
-            s_keys[j] = j < cn ? (((unsigned long long)items[base + j].edge << 32) | items[base + j].face) : ~0ull;
+        unsigned long long tmp[RANK_CHUNK / 256];
+#pragma unroll
+        for (int k = 0; k < RANK_CHUNK / 256; ++k) {
+            const unsigned j = k * 256u + threadIdx.x;
+            tmp[k] = j < cn ? item_key(items + base + j) : ~0ull;
+        }
+#pragma unroll
+        for (int k = 0; k < RANK_CHUNK / 256; ++k) s_keys[k * 256u + threadIdx.x] = tmp[k];
         __syncthreads();
-#pragma unroll 8
-        for (unsigned j = sub; j < (unsigned)RANK_CHUNK; j += 8u) rank += (s_keys[j] < mine) ? 1u : 0u;
+        // 16 consecutive keys per step and item; the 2 items of a warp read the same addresses (broadcast)
+        const unsigned steps = (cn + 15u) >> 4;
+#pragma unroll 4
+        for (unsigned st = 0; st < steps; ++st) rank += (s_keys[st * 16u + sub] < mine) ? 1u : 0u;
         __syncthreads();
     }
     rank += __shfl_xor_sync(0xffffffffu, rank, 1);
     rank += __shfl_xor_sync(0xffffffffu, rank, 2);
     rank += __shfl_xor_sync(0xffffffffu, rank, 4);
+    rank += __shfl_xor_sync(0xffffffffu, rank, 8);
     if (live) {
-        // the item is a few 8-byte words: the 8 threads of the group copy it together
-        static_assert(sizeof(T) % 8 == 0 && alignof(T) >= 8, "records are copied as 8-byte words");
+        // the item is a few 8-byte words: the threads of the group copy it together
         const unsigned long long* src = reinterpret_cast<const unsigned long long*>(items + i);
         unsigned long long* dst = reinterpret_cast<unsigned long long*>(out + rank);
-        for (unsigned w = sub; w < sizeof(T) / 8; w += 8u) dst[w] = src[w];
+        for (unsigned w = sub; w < sizeof(T) / 8; w += 16u) dst[w] = src[w];
     }
 }
 
@@ -541,7 +565,7 @@ int sort_items(mcb200_ctx* ctx, const mcb200_result* res, const T* items, T* ite
     MCB_TRY((rsort::reserve_scratch<unsigned long long>(ctx, cap, pd.npasses, true, true)));
     mcb200_ctx::sort_scratch_t& sc = ctx->sc();
     const unsigned grid = (unsigned)ctx->num_sms * 2u;
-    MCB_LAUNCH_NAMED(ctx, "k_rank_sort_small", (k_rank_sort_small<T>), SMALL_SORT / 32u, 256, 0, items, d_n, (unsigned long long)cap,
+    MCB_LAUNCH_NAMED(ctx, "k_rank_sort_small", (k_rank_sort_small<T>), SMALL_SORT / RANK_ITEMS, 256, 0, items, d_n, (unsigned long long)cap,
         items_sorted);
     MCB_LAUNCH_NAMED(ctx, "k_make_keys", (k_make_keys<T>), grid, 256, 0, items, d_n, (unsigned long long)cap, keys.as<unsigned long long>());
     unsigned long long* kout = nullptr;
@@ -649,6 +673,15 @@ int narrowphase_run(mcb200_ctx* ctx, const mcb200_soup* soup, const mcb200_mesh*
     if (tri) MCB_LAUNCH_NAMED(ctx, "k_tests_filter_tri", (k_tests<true, false>), grid, NBLOCK, 0, a);
     else MCB_LAUNCH_NAMED(ctx, "k_tests_filter_poly", (k_tests<false, false>), grid, NBLOCK, 0, a);
 
+    // The plane data of the candidate faces is an OUTPUT (consumed downstream by the host); the tests compute the planes
+    // they need themselves.  It only depends on the candidate flags the filter just wrote, so it runs beside the exact
+    // pass and the record sort on the background lane.
+    cudaStream_t lane = ctx->cur;
+    const int lane_sci = ctx->sci;
+    MCB_CUDA(ctx, cudaEventRecord(ctx->ev_np, lane));
+    MCB_CUDA(ctx, cudaStreamWaitEvent(ctx->bg, ctx->ev_np, 0));
+    ctx->use_bg();
+
     plane_args_t pa;
     pa.n = a;
     pa.plane = res->plane.as<double>();
@@ -657,6 +690,9 @@ int narrowphase_run(mcb200_ctx* ctx, const mcb200_soup* soup, const mcb200_mesh*
     const unsigned pgrid = div_up(nf, NBLOCK) < grid ? div_up(nf, NBLOCK) : grid;
     if (tri) MCB_LAUNCH(ctx, k_planes<true>, pgrid, NBLOCK, 0, pa);
     else MCB_LAUNCH(ctx, k_planes<false>, pgrid, NBLOCK, 0, pa);
+    MCB_CUDA(ctx, cudaEventRecord(ctx->ev_np2, ctx->bg));
+    ctx->cur = lane;
+    ctx->sci = lane_sci;
 
     // exact-expansion pass over the compacted filter failures (own kernel: its local-memory footprint and divergence
     // stay out of the filter kernel)
@@ -670,6 +706,7 @@ int narrowphase_run(mcb200_ctx* ctx, const mcb200_soup* soup, const mcb200_mesh*
     res->tests_sorted_valid = false;
     MCB_TRY(narrowphase_sort_records(ctx, res));
     if (want_log) MCB_TRY(narrowphase_sort_tests(ctx, res));
+    MCB_CUDA(ctx, cudaStreamWaitEvent(ctx->cur, ctx->ev_np2, 0)); // the plane data joins here
     return 0;
 }
 
