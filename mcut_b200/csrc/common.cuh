@@ -234,6 +234,7 @@ struct mcb200_result {
     dbuf counters; // result_counters_t
     dbuf pairs; // u64 [cap_pairs], in the order the traversal emitted them (what the narrowphase consumes)
     dbuf pairs_a, pairs_b; // ping-pong buffers of the pair sort
+    dbuf live_groups; // u32 [query nf]: query groups that reach a leaf of the other tree (traverse.cu: k_group_filter)
     unsigned long long* pairs_sorted = nullptr; // ascending (src << 32 | cut): points into pairs_a or pairs_b
     size_t cap_pairs = 0;
     bool counters_zeroed = false; // the caller already reset the counters for this run (mcb200_intersect_stage_host)

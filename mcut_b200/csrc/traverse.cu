@@ -7,7 +7,11 @@
 //   * the mesh with more faces is the QUERY side; its leaves are grouped by the query mesh's OWN tree: a group is a
 //     maximal subtree with at most 32 leaves (listed by lbvh.cu's k_refit).  Such treelets are spatially compact — cutting the Morton
 //     order into fixed runs of 32 is not: a run that straddles an octant boundary has a union box spanning the mesh;
-//   * one warp owns a group: lane l keeps leaf l's box in registers, the warp keeps the group's union box;
+//   * most groups are nowhere near the other mesh.  k_group_filter settles those with ONE THREAD per group: a depth-first
+//     walk of the other tree with the group's union box that stops at the first leaf it reaches ("live") or when the stack
+//     runs empty ("dead").  Only the live groups — a few percent, the ones along the intersection curve — get a warp;
+//     before this split every warp had ~13 groups dealt to it and the few warps holding two or three live ones set the time;
+//   * one warp owns a live group: lane l keeps leaf l's box in registers, the warp keeps the group's union box;
 //   * the warp walks the other mesh's tree with a stack in shared memory, up to 32 nodes per step — one node per
 //     lane, one 128-byte line per node carrying both children's boxes; surviving internal children are pushed with
 //     __ballot_sync/__popc slots, surviving leaves go to a shared candidate list;
@@ -35,6 +39,15 @@ struct warp_scratch_t {
     unsigned long long out[OUT_CAP];
 };
 
+// A live group and where its warp resumes the walk: the filter thread's unexplored frontier (the node whose leaf child it
+// hit + its stack).  A frontier that does not fit restarts at the root.
+constexpr int LIVE_NODES = 14;
+struct __align__(64) live_group_t {
+    uint32_t group, count;
+    uint32_t node[LIVE_NODES];
+};
+static_assert(sizeof(live_group_t) == 64, "one 64-byte row per live group");
+
 struct traverse_args_t {
     // query side
     const double* q_face_bbox;
@@ -43,6 +56,7 @@ struct traverse_args_t {
     const uint2* groups; // (first sorted leaf, leaf count <= 32)
     const group_up_t* group_box; // union box of each group (written by the refit)
     const unsigned* n_groups;
+    live_group_t* live; // groups that reach a leaf of the other tree (k_group_filter); count in counters->work_counter
     const double* t_root; // mesh AABB of the tree side (6 doubles)
     // tree side
     const bvh_node_t* t_nodes;
@@ -96,29 +110,105 @@ __device__ __forceinline__ void drain_candidates(warp_scratch_t& ws, unsigned fi
     ntests += count;
 }
 
+constexpr int FBLOCK = 128;
+constexpr int FSTACK = 48; // private depth-first stack; a walk that would outgrow it declares the group live (conservative)
+constexpr int FVISITS = 32; // so does a walk that has not settled after this many nodes: its warp finishes it, 32 nodes a step
+
+__global__ void __launch_bounds__(FBLOCK) k_group_filter(traverse_args_t a)
+{
+    const uint32_t ngroups = *a.n_groups;
+    const unsigned lane = lane_id();
+    const unsigned lt = lanemask_lt();
+    unsigned long long ntests = 0;
+    for (uint32_t g0 = (blockIdx.x * FBLOCK + threadIdx.x) & ~31u; g0 < ngroups; g0 += gridDim.x * FBLOCK) {
+        const uint32_t g = g0 + lane;
+        bool live = false;
+        uint32_t stack[FSTACK];
+        int size = 0;
+        if (g < ngroups) {
+            const uint2 grp = __ldg(a.groups + g);
+            const bool mine = !(a.shard_nparts > 1 && (grp.x / a.shard_chunk) % a.shard_nparts != a.shard_part);
+            if (mine) {
+                double gbox[6];
+                {
+                    const double2* in = reinterpret_cast<const double2*>(a.group_box[g].box);
+                    const double2 x = __ldg(in), y = __ldg(in + 1), z = __ldg(in + 2);
+                    gbox[0] = x.x; gbox[1] = x.y; gbox[2] = y.x; gbox[3] = y.y; gbox[4] = z.x; gbox[5] = z.y;
+                }
+                double troot[6];
+#pragma unroll
+                for (int k = 0; k < 6; ++k) troot[k] = __ldg(a.t_root + k);
+                ntests += 1ull;
+                if (overlap6(gbox, troot)) {
+                    size = 1;
+                    stack[0] = 0u;
+                    int visits = 0;
+                    while (size > 0 && !live) {
+                        const uint32_t node = stack[size - 1];
+                        const double2* nd = reinterpret_cast<const double2*>(a.t_nodes + node);
+                        const double2 l0 = __ldg(nd), l1 = __ldg(nd + 1), l2 = __ldg(nd + 2);
+                        const double2 r0 = __ldg(nd + 3), r1 = __ldg(nd + 4), r2 = __ldg(nd + 5);
+                        const uint2 ch = __ldg(reinterpret_cast<const uint2*>(nd + 6));
+                        const double lb[6] = { l0.x, l0.y, l1.x, l1.y, l2.x, l2.y };
+                        const double rb[6] = { r0.x, r0.y, r1.x, r1.y, r2.x, r2.y };
+                        const bool hitL = overlap6(gbox, lb);
+                        const bool hitR = (ch.y != MCB200_NULL) && overlap6(gbox, rb);
+                        ntests += 2ull;
+                        // live: a leaf is reached (the node stays on the stack: its warp collects the leaves), or the walk is
+                        // taking long, or the stack is about to overflow
+                        if ((hitL && (ch.x & MCB_LEAF_BIT)) || (hitR && (ch.y & MCB_LEAF_BIT)) || ++visits >= FVISITS || size + 1 > FSTACK) {
+                            live = true;
+                        } else {
+                            --size;
+                            if (hitR) stack[size++] = ch.y;
+                            if (hitL) stack[size++] = ch.x; // left first out: depth-first, left to right
+                        }
+                    }
+                }
+            }
+        }
+        const unsigned m = __ballot_sync(0xffffffffu, live);
+        if (m) {
+            unsigned base = 0;
+            if (lane == 0) base = atomicAdd(&a.counters->work_counter, (unsigned)__popc(m));
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if (live) {
+                live_group_t rec;
+                rec.group = g;
+                const bool fits = size <= LIVE_NODES;
+                rec.count = fits ? (uint32_t)size : 1u;
+#pragma unroll
+                for (int k = 0; k < LIVE_NODES; ++k) rec.node[k] = (fits && k < size) ? stack[k] : 0u;
+                a.live[base + __popc(m & lt)] = rec;
+            }
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) ntests += __shfl_xor_sync(0xffffffffu, ntests, o);
+    if (lane == 0 && ntests) atomicAdd(&a.counters->n_node_tests, ntests);
+}
+
 __global__ void __launch_bounds__(TBLOCK) k_traverse(traverse_args_t a)
 {
     __shared__ warp_scratch_t s_ws[WARPS_PER_BLOCK];
     warp_scratch_t& ws = s_ws[threadIdx.x >> 5];
     const unsigned lane = lane_id();
     const unsigned lt = lanemask_lt();
-    const uint32_t ngroups = *a.n_groups;
-    double troot[6];
-#pragma unroll
-    for (int k = 0; k < 6; ++k) troot[k] = __ldg(a.t_root + k);
+    const uint32_t nlive = a.counters->work_counter; // written by k_group_filter
     unsigned nout = 0;
     unsigned long long ntests = 0;
 
-    // Groups are dealt to warps round-robin (static): the group list is in scheduling order of the refit kernel, so
-    // neighbouring entries are unrelated and the deal balances itself; a global ticket per group would put tens of
-    // thousands of same-address atomics on the critical path.
+    // Live groups are dealt to warps round-robin (static); there are usually fewer of them than warps.
     const uint32_t warp_global = (blockIdx.x * TBLOCK + threadIdx.x) >> 5;
     const uint32_t nwarps = (gridDim.x * TBLOCK) >> 5;
     {
         {
-            for (uint32_t g = warp_global; g < ngroups; g += nwarps) {
-            // ---- one load round trip per group: descriptor + union box (from the refit).  The 32 leaf boxes are fetched
-            // only if the walk finds a candidate leaf at all — for most groups it does not ----
+            for (uint32_t li = warp_global; li < nlive; li += nwarps) {
+            // ---- descriptor + union box (from the refit); the 32 leaf boxes are fetched when the first candidates are drained
+            const live_group_t* lg = a.live + li;
+            const uint32_t g = __ldg(&lg->group);
+            const uint32_t nstart = __ldg(&lg->count);
+            const uint32_t start_node = lane < nstart ? __ldg(&lg->node[lane]) : 0u;
             const uint2 grp = __ldg(a.groups + g);
             double gbox[6];
             {
@@ -126,9 +216,6 @@ __global__ void __launch_bounds__(TBLOCK) k_traverse(traverse_args_t a)
                 const double2 x = __ldg(in), y = __ldg(in + 1), z = __ldg(in + 2);
                 gbox[0] = x.x; gbox[1] = x.y; gbox[2] = y.x; gbox[3] = y.y; gbox[4] = z.x; gbox[5] = z.y;
             }
-            if (a.shard_nparts > 1 && (grp.x / a.shard_chunk) % a.shard_nparts != a.shard_part) continue;
-            ntests += 1ull;
-            if (!overlap6(gbox, troot)) continue;
             const uint32_t q = grp.x + lane;
             const bool valid = lane < grp.y;
             bool have_leaf = false;
@@ -146,8 +233,8 @@ __global__ void __launch_bounds__(TBLOCK) k_traverse(traverse_args_t a)
             };
 
             // ---- walk the tree ----
-            unsigned size = 1u, ncand = 0;
-            if (lane == 0) ws.stack[0] = 0u;
+            unsigned size = nstart, ncand = 0;
+            if (lane < nstart) ws.stack[lane] = start_node;
             __syncwarp();
             while (size > 0) {
                 while (ncand > 32) { // keep room for the up-to-64 leaves one step can add (CAND_CAP = 32 + 64)
@@ -252,6 +339,7 @@ int traverse_reserve(mcb200_ctx* ctx, const mcb200_mesh* src, const mcb200_mesh*
     MCB_TRY(ctx->reserve(res->pairs_a, sizeof(unsigned long long) * res->cap_pairs));
     MCB_TRY(ctx->reserve(res->pairs_b, sizeof(unsigned long long) * res->cap_pairs));
     MCB_TRY(ctx->reserve(res->counters, sizeof(result_counters_t)));
+    MCB_TRY(ctx->reserve(res->live_groups, sizeof(live_group_t) * (size_t)(src->nf > cut->nf ? src->nf : cut->nf)));
     return 0;
 }
 
@@ -305,7 +393,13 @@ int traverse_pairs(mcb200_ctx* ctx, const mcb200_mesh* src, const mcb200_mesh* c
     a.group_box = q->group_up.as<group_up_t>();
     a.t_root = reinterpret_cast<const double*>(t->root.as<unsigned long long>() + 6);
 
-    // a persistent grid sized for the machine; groups are handed out by an atomic ticket
+    a.live = res->live_groups.as<live_group_t>();
+    {
+        const unsigned fb = div_up((size_t)q->nf / 8u + 1u, FBLOCK); // about two thirds of the leaves' groups per pass of the grid
+        const unsigned fmax = (unsigned)ctx->num_sms * 16u;
+        MCB_LAUNCH(ctx, k_group_filter, fb < fmax ? fb : fmax, FBLOCK, 0, a);
+    }
+    // a persistent grid sized for the machine
     const unsigned max_blocks = (unsigned)ctx->num_sms * 8u;
     const unsigned want_blocks = div_up(div_up((size_t)q->nf / 8u + 1u, GROUP_BATCH), WARPS_PER_BLOCK);
     const unsigned grid = want_blocks < max_blocks ? (want_blocks ? want_blocks : 1u) : max_blocks;
