@@ -292,7 +292,8 @@ __device__ __forceinline__ double ref_max(double a, double b) { return (a < b) ?
 // closed-interval AABB overlap (math.h:931-941); boxes as min xyz, max xyz
 __device__ __forceinline__ bool overlap6(const double* a, const double* b)
 {
-    return (a[0] <= b[3] && a[3] >= b[0]) && (a[1] <= b[4] && a[4] >= b[1]) && (a[2] <= b[5] && a[5] >= b[2]);
+    // six independent compares combined without short-circuit branches (no NaNs reach here: boxes are min/max of finite input)
+    return ((a[0] <= b[3]) & (a[3] >= b[0]) & (a[1] <= b[4]) & (a[4] >= b[1]) & (a[2] <= b[5]) & (a[5] >= b[2])) != 0;
 }
 
 // internal coordinate of vertex v: x' = (x - com) + shift (+ perturbation); float input does the first two

@@ -91,28 +91,38 @@ __device__ __forceinline__ void drain_candidates(warp_scratch_t& ws, unsigned fi
     bool valid, uint32_t myface, unsigned& nout, unsigned long long& ntests, const traverse_args_t& a)
 {
     const unsigned lt = lanemask_lt();
-    for (unsigned k = first; k < first + count; ++k) {
-        const double* cb = ws.cand_box[k];
-        const bool hit = valid && overlap6(mybox, cb);
-        const unsigned mask = __ballot_sync(0xffffffffu, hit);
-        if (mask) {
-            if (hit) {
-                const uint32_t tf = ws.cand_face[k];
-                const unsigned long long pair = a.query_is_cut ? (((unsigned long long)tf << 32) | myface)
-                                                               : (((unsigned long long)myface << 32) | tf);
-                ws.out[nout + __popc(mask & lt)] = pair;
-            }
-            nout += __popc(mask);
-            __syncwarp();
-            if (nout > OUT_CAP - 32) flush_out(ws, nout, a);
+    auto emit_hits = [&](unsigned k, bool hit, unsigned mask) {
+        if (hit) {
+            const uint32_t tf = ws.cand_face[k];
+            const unsigned long long pair = a.query_is_cut ? (((unsigned long long)tf << 32) | myface)
+                                                           : (((unsigned long long)myface << 32) | tf);
+            ws.out[nout + __popc(mask & lt)] = pair;
         }
+        nout += __popc(mask);
+        __syncwarp();
+        if (nout > OUT_CAP - 32) flush_out(ws, nout, a);
+    };
+    // two candidates per step: their box loads and compares are independent
+    unsigned k = first;
+    for (; k + 1 < first + count; k += 2) {
+        const bool hit0 = valid && overlap6(mybox, ws.cand_box[k]);
+        const bool hit1 = valid && overlap6(mybox, ws.cand_box[k + 1]);
+        const unsigned m0 = __ballot_sync(0xffffffffu, hit0);
+        const unsigned m1 = __ballot_sync(0xffffffffu, hit1);
+        if (m0) emit_hits(k, hit0, m0);
+        if (m1) emit_hits(k + 1, hit1, m1);
+    }
+    if (k < first + count) {
+        const bool hit = valid && overlap6(mybox, ws.cand_box[k]);
+        const unsigned m = __ballot_sync(0xffffffffu, hit);
+        if (m) emit_hits(k, hit, m);
     }
     ntests += count;
 }
 
 constexpr int FBLOCK = 128;
 constexpr int FSTACK = 48; // private depth-first stack; a walk that would outgrow it declares the group live (conservative)
-constexpr int FVISITS = 32; // so does a walk that has not settled after this many nodes: its warp finishes it, 32 nodes a step
+constexpr int FVISITS = 12; // so does a walk that has not settled after this many nodes: its warp finishes it, 32 nodes a step
 
 __global__ void __launch_bounds__(FBLOCK) k_group_filter(traverse_args_t a)
 {
