@@ -212,6 +212,21 @@ def pinned_copy(torch, a: np.ndarray):
     return t, t.numpy()
 
 
+def kernel_traffic(kname: str):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of `kname` from the committed `ncu --set full` capture of
+    this same command (profiles/*_traffic.json, written by tools/ncu_to_profiles.py); None when no capture names it."""
+    import glob
+    best = None
+    for f in sorted(glob.glob(os.path.join(ROOT, "profiles", "*_traffic.json"))):
+        try:
+            d = json.load(open(f))
+        except Exception:
+            continue
+        if kname in d:
+            best = d[kname]["dram_bytes_per_launch"]
+    return best
+
+
 def algorithmic_bytes(kname: str, src_nv, src_nf, cut_nv, cut_nf, counts, vbytes=24):
     """Algorithmic bytes per LAUNCH of a kernel (SURVEY.md §8-d figures).  Build kernels run once
     per mesh, so their per-launch figure uses the mean mesh size."""
@@ -224,11 +239,11 @@ def algorithmic_bytes(kname: str, src_nv, src_nf, cut_nv, cut_nf, counts, vbytes
         "k_face_bbox<false>": vbytes * V + 12 * F + 48 * F,
         "k_morton": 48 * F + 8 * F,  # box in, code out twice (by face + sort key)
         "onesweep_pass_u32_kv": 16 * F,  # one radix pass: key + value read once, written once
-        "k_karras": 4 * F + 16 * F + 8 * F + 16 * F,  # codes in; children/range in the node record + compact meta + parents out
-        # leaf box + face id in, the (31/32)F nodes inside the <=32-leaf treelets written once as 128-byte records
-        "k_refit_treelets": 48 * F + 4 * F + 128 * F * 31 / 32 + 64 * F / 32,
-        # the F/32 nodes above the treelets: group box in, node record out
-        "k_refit_climb": 64 * F / 32 + 128 * F / 32,
+        # codes + leaf boxes (gathered through the sorted order) in; every node inside the <=32-leaf treelets ((31/32)F of
+        # them) written once as a 128-byte record, topology of the rest, parent words, group list out
+        "k_tree": 4 * F + 48 * F + 4 * F + 128 * F * 31 / 32 + 16 * F / 32 + 8 * F + 72 * F / 16,
+        # the F/32 nodes above the treelets: group box in, node boxes out
+        "k_refit_climb": 64 * F / 16 + 96 * F / 32,
         "k_traverse": 48.0 * counts["n_node_tests"] + 8.0 * n_pairs,
         "onesweep_pass_u64_k": 16.0 * n_pairs,
         "k_tests_filter_tri": 8.0 * n_pairs + 128.0 * n_tests,
@@ -420,17 +435,17 @@ def run_ours(args):
             continue
         achieved = ab / (kern[name]["ms_per_launch"] * 1e-3) / 1e9
         roofline = {"kernel": name, "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                    "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": ab,
+                    "traffic": kernel_traffic(name), "peak_source": peak_src, "algorithmic_bytes_per_launch": ab,
                     "ms_per_launch": kern[name]["ms_per_launch"], "share_of_step": kern[name]["ms_per_step"] / step_kernel_ms}
         break
     # whole-build figure (B_build = 24V + 296F per mesh)
     stage_ms = {
-        "build_ms": sum(kern[k]["ms_per_step"] for k in kern if k.startswith(("k_face_bbox", "k_morton", "k_karras", "k_refit"))
+        "build_ms": sum(kern[k]["ms_per_step"] for k in kern if k.startswith(("k_face_bbox", "k_morton", "k_tree", "k_refit"))
                     or k == "onesweep_pass_u32_kv"),
-        "traverse_ms": kern.get("k_traverse", {}).get("ms_per_step", 0.0),
+        "traverse_ms": sum(kern[k]["ms_per_step"] for k in kern if k in ("k_traverse", "k_group_filter")),
         "narrowphase_ms": sum(kern[k]["ms_per_step"] for k in kern if "k_tests" in k or "k_planes" in k),
         "pair_and_record_sort_ms": sum(kern[k]["ms_per_step"] for k in kern if "u64" in k),
-        "other_ms": sum(kern[k]["ms_per_step"] for k in kern if "k_make_keys" in k or "k_gather" in k),
+        "other_ms": sum(kern[k]["ms_per_step"] for k in kern if "k_make_keys" in k or "k_gather" in k or "k_rank_sort" in k),
         "sum_of_kernels_ms": step_kernel_ms,
     }
 

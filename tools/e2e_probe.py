@@ -1,5 +1,6 @@
 """Ad-hoc: where does the host-array call spend its time?  (run on the GPU box)"""
-import ctypes, time, sys
+import ctypes, os, sys, time
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
 import numpy as np, torch
 from mcut_b200 import stage, meshgen
 from mcut_b200._lib import HostMesh, HostSoup
