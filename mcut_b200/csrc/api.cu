@@ -99,6 +99,7 @@ int mcb200_ctx_create(int device, void* stream, mcb200_ctx** out)
         delete ctx;
         return (int)e;
     }
+    if (const char* e = std::getenv("MCB200_PDL")) ctx->pdl = (e[0] != '0');
     cudaStreamCreateWithFlags(&ctx->copy, cudaStreamNonBlocking);
     cudaStreamCreateWithPriority(&ctx->bg, cudaStreamNonBlocking, prio_lo);
     cudaEventCreateWithFlags(&ctx->ev_bg, cudaEventDisableTiming);

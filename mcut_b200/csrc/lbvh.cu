@@ -40,6 +40,7 @@ __global__ void __launch_bounds__(BLOCK) k_face_bbox(const void* __restrict__ xy
     const uint32_t* __restrict__ face_vtx, const uint32_t* __restrict__ face_off, uint32_t nf, double eps,
     double* __restrict__ face_bbox, unsigned long long* __restrict__ root_ordered)
 {
+    pdl_prologue();
     double bmin[3] = { DBL_MAX, DBL_MAX, DBL_MAX }, bmax[3] = { -DBL_MAX, -DBL_MAX, -DBL_MAX };
     for (uint32_t f = blockIdx.x * BLOCK + threadIdx.x; f < nf; f += gridDim.x * BLOCK) {
         const uint32_t h0 = TRI ? 3u * f : face_off[f];
@@ -114,6 +115,7 @@ __global__ void __launch_bounds__(BLOCK) k_morton(const double* __restrict__ fac
     uint32_t* __restrict__ sort_keys, unsigned* __restrict__ hist /* [4][256] */, unsigned* __restrict__ status,
     unsigned status_words)
 {
+    pdl_prologue();
     __shared__ unsigned s_hist[4 * 256];
     for (int i = threadIdx.x; i < 4 * 256; i += BLOCK) s_hist[i] = 0;
     for (unsigned i = blockIdx.x * BLOCK + threadIdx.x; i < status_words; i += gridDim.x * BLOCK) status[i] = 0u;
@@ -315,6 +317,7 @@ __global__ void __launch_bounds__(BLOCK) k_tree(const uint32_t* __restrict__ cod
     const uint32_t* __restrict__ sorted_faces, uint32_t nf, bvh_node_t* nodes, uint32_t* __restrict__ parent,
     uint2* __restrict__ groups, group_up_t* __restrict__ group_up, unsigned* __restrict__ n_groups)
 {
+    pdl_prologue();
     __shared__ uint32_t s_win[KWIN];
     __shared__ double s_box[RWIN][6];
     __shared__ unsigned s_warp[BLOCK / 32], s_base;
@@ -457,6 +460,7 @@ __global__ void __launch_bounds__(BLOCK) k_tree(const uint32_t* __restrict__ cod
 __global__ void __launch_bounds__(BLOCK) k_refit_climb(bvh_node_t* nodes, const uint32_t* __restrict__ parent, unsigned* flags,
     const group_up_t* __restrict__ group_up, const unsigned* __restrict__ n_groups)
 {
+    pdl_prologue();
     const unsigned ng = *n_groups;
     for (unsigned g = blockIdx.x * BLOCK + threadIdx.x; g < ng; g += gridDim.x * BLOCK) {
         const uint32_t slot = group_up[g].pw;

@@ -358,6 +358,7 @@ __device__ __forceinline__ bool setup_test(const narrow_args_t& a, uint32_t s, u
 // in a loop (SPLIT, one thread per (pair, slot), is kept for experiments: it was slower, the per-pair loads dominate).
 template <bool TRI, bool EXACT> __global__ void __launch_bounds__(NBLOCK) k_tests(narrow_args_t a)
 {
+    pdl_prologue();
     constexpr bool SPLIT = false; // measured: 6 short threads per pair cost 2.4x the instructions and 38 us instead of 27
     unsigned long long n_items;
     if (EXACT) {
@@ -446,6 +447,7 @@ struct plane_args_t {
 
 template <bool TRI> __global__ void __launch_bounds__(NBLOCK) k_planes(plane_args_t pa)
 {
+    pdl_prologue();
     const narrow_args_t& a = pa.n;
     for (uint32_t f = blockIdx.x * NBLOCK + threadIdx.x; f < a.nf; f += gridDim.x * NBLOCK) {
         if (!a.cand_flag[f]) continue;
@@ -490,6 +492,7 @@ template <typename T> __device__ __forceinline__ unsigned long long item_key(con
 template <typename T> __global__ void __launch_bounds__(256) k_rank_sort_small(const T* __restrict__ items,
     const unsigned long long* d_n, unsigned long long cap, T* __restrict__ out)
 {
+    pdl_prologue();
     static_assert(sizeof(T) % 8 == 0 && alignof(T) >= 8 && offsetof(T, edge) == 0 && offsetof(T, face) == 4, "item layout");
     __shared__ unsigned long long s_keys[RANK_CHUNK];
     const unsigned long long n64 = *d_n < cap ? *d_n : cap;
@@ -531,6 +534,7 @@ template <typename T> __global__ void __launch_bounds__(256) k_rank_sort_small(c
 template <typename T> __global__ void __launch_bounds__(256) k_make_keys(const T* items, const unsigned long long* d_n,
     unsigned long long cap, unsigned long long* keys)
 {
+    pdl_prologue();
     const unsigned long long n = *d_n < cap ? *d_n : cap;
     if (n <= SMALL_SORT) return;
     for (unsigned long long i = (unsigned long long)blockIdx.x * 256 + threadIdx.x; i < n; i += (unsigned long long)gridDim.x * 256)
@@ -540,6 +544,7 @@ template <typename T> __global__ void __launch_bounds__(256) k_make_keys(const T
 template <typename T> __global__ void __launch_bounds__(256) k_gather(const T* items, const uint32_t* idx,
     const unsigned long long* d_n, unsigned long long cap, T* out)
 {
+    pdl_prologue();
     const unsigned long long n = *d_n < cap ? *d_n : cap;
     if (n <= SMALL_SORT) return;
     for (unsigned long long i = (unsigned long long)blockIdx.x * 256 + threadIdx.x; i < n; i += (unsigned long long)gridDim.x * 256)
@@ -718,6 +723,7 @@ __global__ void __launch_bounds__(256) k_soup_face_vtx(const uint32_t* __restric
     uint32_t nf, uint32_t rot, uint32_t voff, uint32_t* __restrict__ ps_vtx, uint32_t* __restrict__ ps_off, uint32_t off_base,
     uint32_t face_base)
 {
+    pdl_prologue();
     for (uint32_t f = blockIdx.x * 256u + threadIdx.x; f < nf; f += gridDim.x * 256u) {
         const uint32_t h0 = face_off ? face_off[f] : 3u * f;
         const uint32_t n = face_off ? face_off[f + 1] - h0 : 3u;

@@ -75,6 +75,7 @@ __global__ void __launch_bounds__(THREADS) k_histogram(const KeyT* __restrict__ 
     size_t n_max, pass_desc pd, int tile_items, unsigned* __restrict__ hist /* [npasses][RADIX] */,
     unsigned* __restrict__ status, size_t skip_le)
 {
+    pdl_prologue();
     __shared__ unsigned s_hist[MAX_PASSES * RADIX];
     const size_t n = resolve_n(d_n, n_max);
     if (n <= skip_le) return; // a small-n kernel already produced the sorted output
@@ -146,6 +147,7 @@ __global__ void __launch_bounds__(THREADS) k_onesweep_pass(const KeyT* __restric
     int bits, int pass_index, const unsigned* __restrict__ hist /* [RADIX] of this pass */,
     unsigned* status_all /* [npasses][tiles(n)][RADIX] */, unsigned* tile_counter, size_t skip_le)
 {
+    pdl_prologue();
     static_assert(ITEMS % SUB == 0, "a lane owns whole groups of 8 keys");
     static_assert(THREADS == RADIX, "one thread per digit in the per-digit steps");
     constexpr int TILE = THREADS * ITEMS;

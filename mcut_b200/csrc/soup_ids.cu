@@ -71,6 +71,7 @@ __device__ __forceinline__ void face_span(const soup_args_t& a, uint32_t f, uint
 // cut faces (kernel.cpp:1678 hands add_face a list that is already rotated once).
 __global__ void __launch_bounds__(SBLOCK) k_soup_insert(soup_args_t a)
 {
+    pdl_prologue();
     const uint32_t nf = a.nsf + a.ncf;
     for (uint32_t f = blockIdx.x * SBLOCK + threadIdx.x; f < nf; f += gridDim.x * SBLOCK) {
         uint32_t h0, n;
@@ -110,6 +111,7 @@ __global__ void __launch_bounds__(SBLOCK) k_soup_insert(soup_args_t a)
 // (2) slot -> smallest user, per-block count of edge owners.  Two users running the same way = inconsistent winding.
 __global__ void __launch_bounds__(SBLOCK) k_soup_first(soup_args_t a)
 {
+    pdl_prologue();
     __shared__ uint32_t wsum[SBLOCK / 32];
     const uint32_t nf = a.nsf + a.ncf;
     const uint32_t f = blockIdx.x * SBLOCK + threadIdx.x;
@@ -147,6 +149,7 @@ __global__ void __launch_bounds__(SBLOCK) k_soup_first(soup_args_t a)
 // (3a) exclusive scan of the block counts, one block
 __global__ void __launch_bounds__(1024) k_soup_scan(uint32_t* bsum, uint32_t nb, result_counters_t* counters)
 {
+    pdl_prologue();
     __shared__ uint32_t wtot[32];
     __shared__ uint32_t carry;
     if (threadIdx.x == 0) carry = 0;
@@ -188,6 +191,7 @@ __global__ void __launch_bounds__(1024) k_soup_scan(uint32_t* bsum, uint32_t nb,
 // (3b) owners take their ids: rank in halfedge order
 __global__ void __launch_bounds__(SBLOCK) k_soup_assign(soup_args_t a)
 {
+    pdl_prologue();
     __shared__ uint32_t wtot[SBLOCK / 32];
     const uint32_t nf = a.nsf + a.ncf;
     const uint32_t f = blockIdx.x * SBLOCK + threadIdx.x;
@@ -220,6 +224,7 @@ __global__ void __launch_bounds__(SBLOCK) k_soup_assign(soup_args_t a)
 // (4) the second user copies the id and signs in as the face of h1
 __global__ void __launch_bounds__(SBLOCK) k_soup_twin(soup_args_t a)
 {
+    pdl_prologue();
     const uint32_t nf = a.nsf + a.ncf;
     const uint32_t f = blockIdx.x * SBLOCK + threadIdx.x;
     if (f >= nf) return;

@@ -126,6 +126,7 @@ constexpr int FVISITS = 12; // so does a walk that has not settled after this ma
 
 __global__ void __launch_bounds__(FBLOCK) k_group_filter(traverse_args_t a)
 {
+    pdl_prologue();
     const uint32_t ngroups = *a.n_groups;
     const unsigned lane = lane_id();
     const unsigned lt = lanemask_lt();
@@ -200,6 +201,7 @@ __global__ void __launch_bounds__(FBLOCK) k_group_filter(traverse_args_t a)
 
 __global__ void __launch_bounds__(TBLOCK) k_traverse(traverse_args_t a)
 {
+    pdl_prologue();
     __shared__ warp_scratch_t s_ws[WARPS_PER_BLOCK];
     warp_scratch_t& ws = s_ws[threadIdx.x >> 5];
     const unsigned lane = lane_id();
