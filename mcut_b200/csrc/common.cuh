@@ -238,6 +238,7 @@ struct mcb200_result {
     dbuf live_groups; // u32 [query nf]: query groups that reach a leaf of the other tree (traverse.cu: k_group_filter)
     unsigned long long* pairs_sorted = nullptr; // ascending (src << 32 | cut): points into pairs_a or pairs_b
     size_t cap_pairs = 0;
+    bool narrow_counters_fresh = false; // the narrowphase counters are still as result_reset_counters left them
     bool counters_zeroed = false; // the caller already reset the counters for this run (mcb200_intersect_stage_host)
     dbuf cand_flag; // u8 [nf_ps]
     dbuf plane; // per ps face: normal[3], d  (4 doubles) ; maxcomp in separate int array
@@ -340,6 +341,28 @@ __device__ __forceinline__ void pdl_prologue()
     asm volatile("griddepcontrol.launch_dependents;");
 #endif
     asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+
+// Several small fills in ONE launch (a cudaMemsetAsync per counter block costs a stream operation each, and every one
+// of them breaks the programmatic launch chain between the kernels around it).
+struct fill_list_t {
+    unsigned* p[8];
+    unsigned words[8];
+    unsigned value[8];
+    int n;
+    void add(void* ptr, size_t nwords, unsigned v)
+    {
+        p[n] = static_cast<unsigned*>(ptr);
+        words[n] = (unsigned)nwords;
+        value[n] = v;
+        ++n;
+    }
+};
+static __global__ void __launch_bounds__(256) k_fill(fill_list_t L)
+{
+    pdl_prologue();
+    for (int e = 0; e < L.n; ++e)
+        for (unsigned i = blockIdx.x * 256u + threadIdx.x; i < L.words[e]; i += gridDim.x * 256u) L.p[e][i] = L.value[e];
 }
 
 static inline unsigned div_up(size_t a, size_t b) { return (unsigned)((a + b - 1) / b); }

@@ -38,7 +38,7 @@ __device__ __forceinline__ unsigned morton3D(float x, float y, float z)
 template <bool TRI>
 __global__ void __launch_bounds__(BLOCK) k_face_bbox(const void* __restrict__ xyz, frame_t fr,
     const uint32_t* __restrict__ face_vtx, const uint32_t* __restrict__ face_off, uint32_t nf, double eps,
-    double* __restrict__ face_bbox, unsigned long long* __restrict__ root_ordered)
+    double* __restrict__ face_bbox, unsigned long long* __restrict__ root_ordered, unsigned* __restrict__ arrival_flags)
 {
     pdl_prologue();
     double bmin[3] = { DBL_MAX, DBL_MAX, DBL_MAX }, bmax[3] = { -DBL_MAX, -DBL_MAX, -DBL_MAX };
@@ -62,6 +62,7 @@ __global__ void __launch_bounds__(BLOCK) k_face_bbox(const void* __restrict__ xy
                 mn[j] = __dsub_rn(mn[j], eps);
             }
         }
+        arrival_flags[f] = 0u; // the refit's arrival counter of node f (saves a memset pass over the array)
         double* out = face_bbox + 6 * (size_t)f;
         // 48-byte rows: three 16-byte stores
         reinterpret_cast<double2*>(out)[0] = make_double2(mn[0], mn[1]);
@@ -526,24 +527,31 @@ int lbvh_build(mcb200_ctx* ctx, mcb200_mesh* m, double eps)
 
     unsigned long long* root_ord = m->root.as<unsigned long long>();
     double* root_dec = reinterpret_cast<double*>(root_ord + 6);
-    MCB_CUDA(ctx, cudaMemsetAsync(root_ord, 0xFF, sizeof(unsigned long long) * 3, ctx->cur));
-    MCB_CUDA(ctx, cudaMemsetAsync(root_ord + 3, 0x00, sizeof(unsigned long long) * 3, ctx->cur));
-    MCB_CUDA(ctx, cudaMemsetAsync(m->flags.p, 0, sizeof(unsigned) * (size_t)nf, ctx->cur));
     unsigned* n_groups = reinterpret_cast<unsigned*>(m->groups.as<uint2>() + nf);
-    MCB_CUDA(ctx, cudaMemsetAsync(n_groups, 0, sizeof(unsigned) * 4, ctx->cur));
+    {
+        // every small reset of the build in one launch: mesh AABB accumulators (min side all-ones, max side zero in the
+        // ordered encoding), group counter, radix histograms and tile tickets.  The arrival flags (one word per face) are
+        // cleared by k_face_bbox on its way through the faces.
+        fill_list_t fl {};
+        fl.add(root_ord, 6, 0xFFFFFFFFu);
+        fl.add(root_ord + 3, 6, 0u);
+        fl.add(n_groups, 4, 0u);
+        fl.add(sc.hist.p, (size_t)rsort::MAX_PASSES * rsort::RADIX, 0u);
+        fl.add(sc.tilectr.p, rsort::MAX_PASSES, 0u);
+        MCB_LAUNCH(ctx, k_fill, 8, 256, 0, fl);
+    }
 
     const unsigned max_grid = (unsigned)ctx->num_sms * 8u;
     const unsigned grid = div_up(nf, BLOCK) < max_grid ? div_up(nf, BLOCK) : max_grid;
     if (m->is_tri)
         MCB_LAUNCH(ctx, k_face_bbox<true>, grid, BLOCK, 0, m->d_xyz, m->frame, m->d_face_vtx, m->d_face_off, nf, eps,
-            m->face_bbox.as<double>(), root_ord);
+            m->face_bbox.as<double>(), root_ord, m->flags.as<unsigned>());
     else
         MCB_LAUNCH(ctx, k_face_bbox<false>, grid, BLOCK, 0, m->d_xyz, m->frame, m->d_face_vtx, m->d_face_off, nf, eps,
-            m->face_bbox.as<double>(), root_ord);
+            m->face_bbox.as<double>(), root_ord, m->flags.as<unsigned>());
     // (code, face) ascending by code: in = sorted_codes (values implicit 0..nf-1), ping-pong scratch <-> mesh arrays;
     // four passes end in the mesh's own arrays.  The histograms come out of k_morton.
     const rsort::pass_desc pd = rsort::make_passes(0, 32);
-    MCB_TRY(rsort::sort_prepare(ctx));
     constexpr int SORT_TILE = rsort::THREADS * rsort::items_for<uint32_t>::value;
     const unsigned status_words = (unsigned)(((size_t)nf + SORT_TILE - 1) / SORT_TILE) * rsort::RADIX * (unsigned)pd.npasses;
     MCB_LAUNCH(ctx, k_morton, grid, BLOCK, 0, m->face_bbox.as<double>(), nf, root_ord, root_dec, m->codes.as<uint32_t>(),

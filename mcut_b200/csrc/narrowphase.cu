@@ -642,12 +642,15 @@ int narrowphase_run(mcb200_ctx* ctx, const mcb200_soup* soup, const mcb200_mesh*
     MCB_CUDA(ctx, cudaMemsetAsync(res->cand_flag.p, 0, (size_t)nf, ctx->cur));
 
     // reset the narrowphase counters only (pairs / node tests stay)
-    {
+    if (!res->narrow_counters_fresh) { // a rerun on existing pairs (e.g. another perturbation)
         result_counters_t* c = res->counters.as<result_counters_t>();
-        MCB_CUDA(ctx, cudaMemsetAsync(&c->n_tests, 0, sizeof(unsigned long long) * 5, ctx->cur)); // n_tests..n_log
-        MCB_CUDA(ctx, cudaMemsetAsync(&c->gp_violation, 0, sizeof(unsigned), ctx->cur));
-        MCB_CUDA(ctx, cudaMemsetAsync(&c->bad_face, 0xFF, sizeof(unsigned), ctx->cur));
+        fill_list_t fl {};
+        fl.add(&c->n_tests, 10, 0u); // n_tests .. n_log
+        fl.add(&c->gp_violation, 1, 0u);
+        fl.add(&c->bad_face, 1, 0xFFFFFFFFu);
+        MCB_LAUNCH(ctx, k_fill, 1, 256, 0, fl);
     }
+    res->narrow_counters_fresh = false;
 
     narrow_args_t a;
     a.src_xyz = src->d_xyz;

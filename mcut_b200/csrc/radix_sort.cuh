@@ -381,8 +381,10 @@ template <typename KeyT> int reserve_scratch(mcb200_ctx* ctx, size_t n_max, int 
 inline int sort_prepare(mcb200_ctx* ctx)
 {
     mcb200_ctx::sort_scratch_t& sc = ctx->sc();
-    MCB_CUDA(ctx, cudaMemsetAsync(sc.hist.p, 0, sizeof(unsigned) * MAX_PASSES * RADIX, ctx->cur));
-    MCB_CUDA(ctx, cudaMemsetAsync(sc.tilectr.p, 0, sizeof(unsigned) * MAX_PASSES, ctx->cur));
+    fill_list_t fl {};
+    fl.add(sc.hist.p, (size_t)MAX_PASSES * RADIX, 0u);
+    fl.add(sc.tilectr.p, MAX_PASSES, 0u);
+    MCB_LAUNCH(ctx, k_fill, 8, 256, 0, fl);
     return 0;
 }
 

@@ -357,10 +357,15 @@ int traverse_reserve(mcb200_ctx* ctx, const mcb200_mesh* src, const mcb200_mesh*
 
 int result_reset_counters(mcb200_ctx* ctx, mcb200_result* res)
 {
-    MCB_CUDA(ctx, cudaMemsetAsync(res->counters.p, 0, sizeof(result_counters_t), ctx->cur));
-    // bad_face starts at "none"
-    const size_t off = offsetof(result_counters_t, bad_face);
-    MCB_CUDA(ctx, cudaMemsetAsync(reinterpret_cast<char*>(res->counters.p) + off, 0xFF, sizeof(unsigned), ctx->cur));
+    // all zero, bad_face starts at "none"
+    unsigned* w = res->counters.as<unsigned>();
+    const size_t bf = offsetof(result_counters_t, bad_face) / 4, nw = sizeof(result_counters_t) / 4;
+    fill_list_t fl {}; // three disjoint ranges: entries of one launch are not ordered against each other
+    fl.add(w, bf, 0u);
+    fl.add(w + bf, 1, 0xFFFFFFFFu);
+    fl.add(w + bf + 1, nw - bf - 1, 0u);
+    MCB_LAUNCH(ctx, k_fill, 1, 256, 0, fl);
+    res->narrow_counters_fresh = true;
     return 0;
 }
 
