@@ -562,6 +562,14 @@ int mcb200_intersect_stage(mcb200_ctx* ctx, mcb200_mesh* src, mcb200_mesh* cut, 
         cut->frame = cut_frame;
         return rc;
     }
+    // resets that nothing before the traversal depends on: up front, not between the kernels of the critical path
+    rc = result_reset_counters(ctx, res);
+    res->counters_zeroed = (rc == 0);
+    if (!rc) rc = narrowphase_prezero(ctx, soup, res);
+    if (rc) {
+        cut->frame = cut_frame;
+        return rc;
+    }
     // ---- the two LBVH builds side by side ----
     MCB_CUDA(ctx, cudaEventRecord(ctx->ev_fork, ctx->stream));
     MCB_CUDA(ctx, cudaStreamWaitEvent(ctx->aux, ctx->ev_fork, 0));
@@ -701,6 +709,7 @@ int mcb200_intersect_stage_host(mcb200_ctx* ctx, const mcb200_host_mesh* hsrc, c
     // the counters are reset here, while the lanes still wait for the uploads (the soup numbering reports into them)
     MCB_TRY(result_reset_counters(ctx, res));
     res->counters_zeroed = true;
+    MCB_TRY(narrowphase_prezero(ctx, soup, res));
     MCB_CUDA(ctx, cudaEventRecord(ctx->ev_fork, ctx->stream));
     MCB_CUDA(ctx, cudaStreamWaitEvent(ctx->aux, ctx->ev_fork, 0));
     MCB_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_up[0], 0));

@@ -238,6 +238,7 @@ struct mcb200_result {
     dbuf live_groups; // u32 [query nf]: query groups that reach a leaf of the other tree (traverse.cu: k_group_filter)
     unsigned long long* pairs_sorted = nullptr; // ascending (src << 32 | cut): points into pairs_a or pairs_b
     size_t cap_pairs = 0;
+    bool cand_flag_fresh = false; // candidate flags already cleared for the coming narrowphase
     bool narrow_counters_fresh = false; // the narrowphase counters are still as result_reset_counters left them
     bool counters_zeroed = false; // the caller already reset the counters for this run (mcb200_intersect_stage_host)
     dbuf cand_flag; // u8 [nf_ps]

@@ -16,6 +16,7 @@ int sort_pairs(mcb200_ctx* ctx, const mcb200_mesh* src, const mcb200_mesh* cut, 
 int narrowphase_reserve(mcb200_ctx* ctx, const mcb200_soup* soup, mcb200_result* res, uint32_t flags);
 int narrowphase_run(mcb200_ctx* ctx, const mcb200_soup* soup, const mcb200_mesh* src, const mcb200_mesh* cut,
     mcb200_result* res, uint32_t flags);
+int narrowphase_prezero(mcb200_ctx* ctx, const mcb200_soup* soup, mcb200_result* res);
 int soup_face_vtx_device(mcb200_ctx* ctx, const mcb200_mesh* src, const mcb200_mesh* cut, mcb200_soup* soup);
 int narrowphase_sort_records(mcb200_ctx* ctx, mcb200_result* res);
 int narrowphase_sort_tests(mcb200_ctx* ctx, mcb200_result* res);

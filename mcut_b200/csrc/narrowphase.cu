@@ -639,7 +639,8 @@ int narrowphase_run(mcb200_ctx* ctx, const mcb200_soup* soup, const mcb200_mesh*
     const bool want_log = (flags & MCB200_NARROW_LOG_TESTS) != 0;
     MCB_TRY(narrowphase_reserve(ctx, soup, res, flags));
     const size_t cap_rec = res->cap_records, cap_exact = res->cap_exact, cap_tests = res->cap_tests;
-    MCB_CUDA(ctx, cudaMemsetAsync(res->cand_flag.p, 0, (size_t)nf, ctx->cur));
+    if (!res->cand_flag_fresh) MCB_CUDA(ctx, cudaMemsetAsync(res->cand_flag.p, 0, (size_t)nf, ctx->cur));
+    res->cand_flag_fresh = false;
 
     // reset the narrowphase counters only (pairs / node tests stay)
     if (!res->narrow_counters_fresh) { // a rerun on existing pairs (e.g. another perturbation)
@@ -748,6 +749,14 @@ int soup_face_vtx_device(mcb200_ctx* ctx, const mcb200_mesh* src, const mcb200_m
         0u, 0u);
     MCB_LAUNCH(ctx, k_soup_face_vtx, gc, 256, 0, cut->d_face_vtx, cut->d_face_off, cut->nf, 2u, src->nv, soup->face_vtx.as<uint32_t>(),
         off, src->nh, src->nf);
+    return 0;
+}
+
+// The stage calls clear the candidate flags up front (before the lanes fork), off the path between traversal and filter.
+int narrowphase_prezero(mcb200_ctx* ctx, const mcb200_soup* soup, mcb200_result* res)
+{
+    MCB_CUDA(ctx, cudaMemsetAsync(res->cand_flag.p, 0, (size_t)soup->nsf + soup->ncf, ctx->cur));
+    res->cand_flag_fresh = true;
     return 0;
 }
 
