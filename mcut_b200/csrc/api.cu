@@ -537,6 +537,25 @@ int mcb200_narrowphase(mcb200_ctx* ctx, const mcb200_soup* soup, const mcb200_me
     return narrowphase_run(ctx, soup, src, cut, res, flags);
 }
 
+// Issue the two builds' launches alternately: main lane <- src, aux lane <- cut.
+static int build_both_interleaved(mcb200_ctx* ctx, mcb200_mesh* src, mcb200_mesh* cut, double cut_eps)
+{
+    std::vector<std::function<int()>> qa, qb;
+    ctx->use_main();
+    ctx->recording = &qa;
+    int rc = lbvh_build(ctx, src, 0.0);
+    ctx->use_aux();
+    ctx->recording = &qb;
+    if (!rc) rc = lbvh_build(ctx, cut, cut_eps);
+    ctx->recording = nullptr;
+    ctx->use_main();
+    for (size_t i = 0; !rc && (i < qa.size() || i < qb.size()); ++i) {
+        if (i < qa.size()) rc = qa[i]();
+        if (!rc && i < qb.size()) rc = qb[i]();
+    }
+    return rc;
+}
+
 int mcb200_intersect_stage(mcb200_ctx* ctx, mcb200_mesh* src, mcb200_mesh* cut, double cut_eps, const mcb200_soup* soup,
     mcb200_result* res, uint32_t flags)
 {
@@ -573,11 +592,8 @@ int mcb200_intersect_stage(mcb200_ctx* ctx, mcb200_mesh* src, mcb200_mesh* cut, 
     // ---- the two LBVH builds side by side ----
     MCB_CUDA(ctx, cudaEventRecord(ctx->ev_fork, ctx->stream));
     MCB_CUDA(ctx, cudaStreamWaitEvent(ctx->aux, ctx->ev_fork, 0));
-    rc = lbvh_build(ctx, src, 0.0);
-    ctx->use_aux();
-    if (!rc) rc = lbvh_build(ctx, cut, cut_eps);
+    rc = build_both_interleaved(ctx, src, cut, cut_eps);
     cudaEventRecord(ctx->ev_join, ctx->aux);
-    ctx->use_main();
     cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0);
     cut->frame = cut_frame;
     if (rc) return rc;

@@ -11,6 +11,7 @@
 #include <cstdint>
 #include <cstdio>
 #include <cstring>
+#include <functional>
 #include <string>
 #include <vector>
 
@@ -90,6 +91,7 @@ struct mcb200_ctx {
     dbuf st_xyz[2], st_fv[2], st_fo[2];
     dbuf st_tab_keys, st_hfirst, st_bsum; // device-side polygon-soup numbering (soup_ids.cu)
     size_t st_tab_cap = 0;
+    std::vector<std::function<int()>>* recording = nullptr; // MCB_LAUNCH queues here instead of launching (see the macro)
     bool pdl = true; // programmatic dependent launch between in-stream kernels (MCB200_PDL=0 turns it off)
     bool sort_smem_opt_in[4] = { false, false, false, false }; // radix_sort.cuh: dynamic shared memory opt-in done
     void use_main() { cur = stream; sci = 0; }
@@ -371,35 +373,47 @@ static inline unsigned div_up(size_t a, size_t b) { return (unsigned)((a + b - 1
 // launch accounting: every kernel launch of the product goes through this macro
 #define MCB_LAUNCH(ctx, kernel, grid, block, smem, ...) MCB_LAUNCH_NAMED(ctx, #kernel, kernel, grid, block, smem, __VA_ARGS__)
 
+// The launch is a closure: normally it runs at once; while ctx->recording is set it is queued instead, so that the
+// launches of two lanes can be issued alternately (the host needs ~5 us per launch: issuing one lane's ten kernels before
+// the other lane's first one would start that lane ~50 us late).
 #define MCB_LAUNCH_NAMED(ctx, name, kernel, grid, block, smem, ...)              \
     do {                                                                         \
-        mcb200_ctx::prof_rec pr__ { name, nullptr, nullptr };                    \
-        if ((ctx)->profiling) {                                                  \
-            pr__.a = (ctx)->prof_event();                                        \
-            pr__.b = (ctx)->prof_event();                                        \
-            cudaEventRecord(pr__.a, (ctx)->cur);                              \
-        }                                                                        \
-        {                                                                        \
+        mcb200_ctx* c__ = (ctx);                                                 \
+        cudaStream_t st__ = c__->cur;                                            \
+        auto fn__ = [=]() -> int {                                               \
+            mcb200_ctx::prof_rec pr__ { name, nullptr, nullptr };                \
+            if (c__->profiling) {                                                \
+                pr__.a = c__->prof_event();                                      \
+                pr__.b = c__->prof_event();                                      \
+                cudaEventRecord(pr__.a, st__);                                   \
+            }                                                                    \
             cudaLaunchConfig_t cfg__ = {};                                       \
             cfg__.gridDim = dim3(grid);                                          \
             cfg__.blockDim = dim3(block);                                        \
             cfg__.dynamicSmemBytes = (smem);                                     \
-            cfg__.stream = (ctx)->cur;                                           \
+            cfg__.stream = st__;                                                 \
             cudaLaunchAttribute at__[1];                                         \
             at__[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;     \
             at__[0].val.programmaticStreamSerializationAllowed = 1;              \
             cfg__.attrs = at__;                                                  \
-            cfg__.numAttrs = (ctx)->pdl ? 1u : 0u;                               \
+            cfg__.numAttrs = c__->pdl ? 1u : 0u;                                 \
             cudaLaunchKernelEx(&cfg__, kernel, __VA_ARGS__);                     \
-        }                                                                        \
-        if ((ctx)->profiling) {                                                  \
-            cudaEventRecord(pr__.b, (ctx)->cur);                              \
-            (ctx)->prof.push_back(pr__);                                         \
-        }                                                                        \
-        (ctx)->launches++;                                                       \
-        cudaError_t le__ = cudaPeekAtLastError();                                \
-        if (le__ != cudaSuccess) {                                               \
-            (ctx)->set_error(std::string(name) + " launch: " + cudaGetErrorString(le__), __FILE__, __LINE__); \
-            return (int)le__;                                                    \
+            if (c__->profiling) {                                                \
+                cudaEventRecord(pr__.b, st__);                                   \
+                c__->prof.push_back(pr__);                                       \
+            }                                                                    \
+            c__->launches++;                                                     \
+            cudaError_t le__ = cudaPeekAtLastError();                            \
+            if (le__ != cudaSuccess) {                                           \
+                c__->set_error(std::string(name) + ": " + cudaGetErrorString(le__), __FILE__, __LINE__); \
+                return (int)le__;                                                \
+            }                                                                    \
+            return 0;                                                            \
+        };                                                                       \
+        if (c__->recording) {                                                    \
+            c__->recording->push_back(fn__);                                     \
+        } else {                                                                 \
+            const int rc__ = fn__();                                             \
+            if (rc__) return rc__;                                               \
         }                                                                        \
     } while (0)
