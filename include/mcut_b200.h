@@ -102,6 +102,10 @@ int mcb200_mesh_adopt_device(mcb200_ctx* ctx, int is_float, const void* d_xyz, u
  * vertex (bit-identical to materialising it, and a perturbation retry costs nothing). */
 int mcb200_mesh_set_frame(mcb200_ctx* ctx, mcb200_mesh* mesh, const double com[3], const double shift[3],
     const double perturbation[3] /* or NULL */);
+/* Replace the coordinates of a mesh in place (same vertex count and type); faces, face boxes and the BVH are kept.
+ * This is the perturbation retry of the reference (preproc.cpp:2560-2700): the cut mesh gets new coordinates, the cut
+ * BVH of the first pass stays (its boxes were enlarged to cover every perturbation, bvh.cpp:242-314). */
+int mcb200_mesh_update_xyz(mcb200_ctx* ctx, mcb200_mesh* mesh, const void* xyz, uint32_t nv);
 void mcb200_mesh_free(mcb200_ctx* ctx, mcb200_mesh* mesh);
 
 /* ---------------------------------------------------------------- (1) LBVH build --------------------------- */
@@ -145,6 +149,9 @@ int mcb200_result_set_pair_capacity(mcb200_ctx* ctx, mcb200_result* res, uint64_
 /* ---------------------------------------------------------------- (3) narrowphase -------------------------- */
 int mcb200_soup_create(mcb200_ctx* ctx, uint32_t nsf, uint32_t ncf, uint32_t nh, uint32_t ne, const uint32_t* face_vtx,
     const uint32_t* face_edge, const uint32_t* edge_f, mcb200_soup** soup);
+/* Same with explicit face sizes (polygon soups; face_sizes == NULL: triangles).  face_sizes[f] for f in [0, nsf + ncf). */
+int mcb200_soup_create_sized(mcb200_ctx* ctx, uint32_t nsf, uint32_t ncf, uint32_t nh, uint32_t ne, const uint32_t* face_vtx,
+    const uint32_t* face_edge, const uint32_t* edge_f, const uint32_t* face_sizes, mcb200_soup** soup);
 void mcb200_soup_free(mcb200_ctx* ctx, mcb200_soup* soup);
 /* Builds the soup ids on the host from the two meshes' face arrays and uploads them (mcb200_soup_ids + create). */
 int mcb200_soup_from_meshes(mcb200_ctx* ctx, const mcb200_mesh* src, const mcb200_mesh* cut, mcb200_soup** soup);

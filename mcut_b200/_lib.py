@@ -59,6 +59,7 @@ SYMBOLS = {
                                   c_u32p, c_u32p]),
     "mcb200_mesh_create": (C.c_int, [vp, C.c_int, vp, C.c_uint32, c_u32p, c_u32p, C.c_uint32, C.POINTER(vp)]),
     "mcb200_mesh_adopt_device": (C.c_int, [vp, C.c_int, vp, C.c_uint32, vp, vp, C.c_uint32, C.c_uint32, C.POINTER(vp)]),
+    "mcb200_mesh_update_xyz": (C.c_int, [vp, vp, vp, C.c_uint32]),
     "mcb200_mesh_set_frame": (C.c_int, [vp, vp, c_dp, c_dp, c_dp]),
     "mcb200_mesh_free": (None, [vp, vp]),
     "mcb200_bvh_build": (C.c_int, [vp, vp, C.c_double]),
@@ -70,6 +71,8 @@ SYMBOLS = {
     "mcb200_result_set_shard": (C.c_int, [vp, vp, C.c_uint32, C.c_uint32, C.c_uint32]),
     "mcb200_result_set_pair_capacity": (C.c_int, [vp, vp, C.c_uint64]),
     "mcb200_soup_create": (C.c_int, [vp, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, c_u32p, c_u32p, c_u32p, C.POINTER(vp)]),
+    "mcb200_soup_create_sized": (C.c_int, [vp, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, c_u32p, c_u32p, c_u32p, c_u32p,
+                                          C.POINTER(vp)]),
     "mcb200_soup_free": (None, [vp, vp]),
     "mcb200_soup_from_meshes": (C.c_int, [vp, vp, vp, C.POINTER(vp)]),
     "mcb200_narrowphase": (C.c_int, [vp, vp, vp, vp, vp, C.c_uint32]),

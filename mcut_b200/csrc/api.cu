@@ -299,6 +299,18 @@ int mcb200_mesh_create(mcb200_ctx* ctx, int is_float, const void* xyz, uint32_t 
     return 0;
 }
 
+int mcb200_mesh_update_xyz(mcb200_ctx* ctx, mcb200_mesh* mesh, const void* xyz, uint32_t nv)
+{
+    if (!ctx || !mesh || !xyz) return MCB200_ERR_INVALID;
+    if (nv != mesh->nv) MCB_FAIL(ctx, MCB200_ERR_INVALID, "mesh_update_xyz: vertex count differs from the mesh");
+    if (!mesh->owns_arrays) MCB_FAIL(ctx, MCB200_ERR_INVALID, "mesh_update_xyz: the mesh borrows its arrays (adopted device memory)");
+    MCB_CUDA(ctx, cudaSetDevice(ctx->device));
+    const size_t vbytes = (size_t)nv * 3 * (mesh->is_float ? sizeof(float) : sizeof(double));
+    MCB_CUDA(ctx, cudaMemcpyAsync(const_cast<void*>(mesh->d_xyz), xyz, vbytes, cudaMemcpyHostToDevice, ctx->stream));
+    MCB_CUDA(ctx, cudaStreamSynchronize(ctx->stream)); // the caller's array is only borrowed for the call
+    return 0;
+}
+
 int mcb200_mesh_adopt_device(mcb200_ctx* ctx, int is_float, const void* d_xyz, uint32_t nv, const uint32_t* d_face_vtx,
     const uint32_t* d_face_off, uint32_t nf, uint32_t nh, mcb200_mesh** out)
 {
@@ -487,6 +499,40 @@ int mcb200_soup_create(mcb200_ctx* ctx, uint32_t nsf, uint32_t ncf, uint32_t nh,
         return rc;
     }
     *out = s;
+    return 0;
+}
+
+int mcb200_soup_create_sized(mcb200_ctx* ctx, uint32_t nsf, uint32_t ncf, uint32_t nh, uint32_t ne, const uint32_t* face_vtx,
+    const uint32_t* face_edge, const uint32_t* edge_f, const uint32_t* face_sizes, mcb200_soup** out)
+{
+    MCB_TRY(mcb200_soup_create(ctx, nsf, ncf, nh, ne, face_vtx, face_edge, edge_f, out));
+    if (!face_sizes) return 0;
+    mcb200_soup* s = *out;
+    const size_t nf = (size_t)nsf + ncf;
+    std::vector<uint32_t> off(nf + 1);
+    bool tri = true;
+    uint32_t acc = 0;
+    for (size_t f = 0; f < nf; ++f) {
+        off[f] = acc;
+        acc += face_sizes[f];
+        if (face_sizes[f] != 3u) tri = false;
+        if (face_sizes[f] < 3u) {
+            mcb200_soup_free(ctx, s);
+            *out = nullptr;
+            MCB_FAIL(ctx, MCB200_ERR_INVALID, "soup_create_sized: a face has fewer than 3 vertices");
+        }
+    }
+    off[nf] = acc;
+    if (acc != nh) {
+        mcb200_soup_free(ctx, s);
+        *out = nullptr;
+        MCB_FAIL(ctx, MCB200_ERR_INVALID, "soup_create_sized: face sizes do not add up to the halfedge count");
+    }
+    s->all_tri = tri ? 1 : 0;
+    if (!tri) {
+        MCB_TRY(upload(ctx, s->face_off, off.data(), sizeof(uint32_t) * off.size()));
+        MCB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    }
     return 0;
 }
 

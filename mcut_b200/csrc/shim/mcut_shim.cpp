@@ -28,6 +28,7 @@
 #include "mcut/internal/math.h"
 
 #include "../../../include/mcut_b200.h"
+#include "mcut_hook.h"
 
 namespace {
 
@@ -38,6 +39,16 @@ struct device_tree_t {
     mcb200_mesh* mesh = nullptr;
     uint32_t nf = 0;
 };
+
+// What the last intersectOIBVHs() of this API thread worked with: dispatch() runs on the same thread right after it (and
+// again, with new cut coordinates, on every general-position retry) and its narrowphase hook continues from here.
+struct last_intersect_t {
+    mcb200_ctx* ctx = nullptr;
+    mcb200_mesh* src = nullptr;
+    mcb200_mesh* cut = nullptr;
+    mcb200_result* res = nullptr;
+};
+thread_local last_intersect_t t_last;
 
 std::mutex g_mutex;
 std::unordered_map<const void*, device_tree_t> g_trees; // key: address of the caller's bvhAABBs vector
@@ -143,7 +154,12 @@ void intersectOIBVHs(std::map<fd_t, std::vector<fd_t>>& ps_face_to_potentially_i
     check(ctx, mcb200_result_counts(ctx, res, &counts), "result_counts");
     std::vector<uint64_t> pairs((size_t)counts.n_pairs);
     check(ctx, mcb200_result_read_pairs(ctx, res, pairs.data(), pairs.size()), "read_pairs");
-    mcb200_result_free(ctx, res);
+    // the pairs stay on the device for the narrowphase hook (mcb200_hook_narrowphase below)
+    if (t_last.res) mcb200_result_free(t_last.ctx, t_last.res);
+    t_last.ctx = ctx;
+    t_last.src = s.mesh;
+    t_last.cut = c.mesh;
+    t_last.res = res;
 
     const uint32_t nsf = (uint32_t)srcMeshBvhLeafNodeFaces.size();
     // pairs are sorted by (src, cut): source keys arrive in ascending order -> amortised O(1) hinted inserts
@@ -164,4 +180,143 @@ void intersectOIBVHs(std::map<fd_t, std::vector<fd_t>>& ps_face_to_potentially_i
         const uint32_t sf = (uint32_t)(p >> 32), cf = (uint32_t)(p & 0xFFFFFFFFu) + nsf;
         ps_face_to_potentially_intersecting_others[fd_t(cf)].push_back(fd_t(sf));
     }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Narrowphase hook (mcut_hook.h): replaces kernel.cpp:1779-3206 inside a live dispatch().
+// ---------------------------------------------------------------------------------------------------------------------
+int mcb200_hook_narrowphase(const hmesh_t& ps, int sm_vtx_cnt, int sm_face_count,
+    const std::map<fd_t, std::vector<fd_t>>& ps_face_to_potentially_intersecting_others, hmesh_t& m0,
+    std::unordered_map<fd_t, vec3>& ps_tested_face_to_plane_normal,
+    std::unordered_map<fd_t, scalar_t>& ps_tested_face_to_plane_normal_d_param,
+    std::unordered_map<fd_t, int>& ps_tested_face_to_plane_normal_max_comp,
+    std::unordered_map<fd_t, std::vector<vec3>>& ps_tested_face_to_vertices,
+    std::vector<std::pair<ed_t, fd_t>>& m0_ivtx_to_intersection_registry_entry, std::vector<vd_t>& cm_border_reentrant_ivtx_list,
+    std::unordered_map<ed_t, std::vector<vd_t>>& ps_intersecting_edges,
+    std::map<pair<fd_t>, std::vector<vd_t>>& cutpath_edge_creation_info,
+    std::unordered_map<fd_t, std::vector<vd_t>>& ps_iface_to_ivtx_list, bool& partial_cut_detected, int& bad_face)
+{
+    (void)ps_face_to_potentially_intersecting_others; // the same pairs are still on the device, in t_last.res
+    if (!t_last.res) throw std::runtime_error("mcut_b200: narrowphase hook reached without a device broadphase on this thread");
+    mcb200_ctx* ctx = t_last.ctx;
+    const uint32_t nv = (uint32_t)ps.number_of_vertices(), nf = (uint32_t)ps.number_of_faces(), ne = (uint32_t)ps.number_of_edges();
+    const uint32_t nsv = (uint32_t)sm_vtx_cnt, nsf = (uint32_t)sm_face_count, ncv = nv - nsv, ncf = nf - nsf;
+
+    // ---- coordinates as dispatch() sees them now (the cut mesh moves on every general-position retry) ----
+    {
+        std::vector<double> xyz(3 * (size_t)(nsv > ncv ? nsv : ncv));
+        for (uint32_t v = 0; v < nsv; ++v) {
+            const vec3& p = ps.vertex(vd_t(v));
+            xyz[3 * (size_t)v] = p.x();
+            xyz[3 * (size_t)v + 1] = p.y();
+            xyz[3 * (size_t)v + 2] = p.z();
+        }
+        check(ctx, mcb200_mesh_update_xyz(ctx, t_last.src, xyz.data(), nsv), "mesh_update_xyz(src)");
+        for (uint32_t v = 0; v < ncv; ++v) {
+            const vec3& p = ps.vertex(vd_t(nsv + v));
+            xyz[3 * (size_t)v] = p.x();
+            xyz[3 * (size_t)v + 1] = p.y();
+            xyz[3 * (size_t)v + 2] = p.z();
+        }
+        check(ctx, mcb200_mesh_update_xyz(ctx, t_last.cut, xyz.data(), ncv), "mesh_update_xyz(cut)");
+    }
+
+    // ---- the ids of `ps` as flat arrays: vertex and edge of every halfedge slot, faces of h0 / h1 of every edge ----
+    std::vector<uint32_t> face_vtx, face_edge, edge_f(2 * (size_t)ne);
+    face_vtx.reserve(3 * (size_t)nf);
+    face_edge.reserve(3 * (size_t)nf);
+    std::vector<uint32_t> sizes(nf);
+    for (uint32_t f = 0; f < nf; ++f) {
+        const std::vector<hd_t>& hs = ps.get_halfedges_around_face(fd_t(f));
+        sizes[f] = (uint32_t)hs.size();
+        for (const hd_t& h : hs) {
+            face_vtx.push_back((uint32_t)ps.target(h));
+            face_edge.push_back((uint32_t)ps.edge(h));
+        }
+    }
+    for (uint32_t e = 0; e < ne; ++e) {
+        const fd_t f0 = ps.face(ps.halfedge(ed_t(e), 0)), f1 = ps.face(ps.halfedge(ed_t(e), 1));
+        edge_f[2 * (size_t)e] = (f0 == hmesh_t::null_face()) ? MCB200_NULL : (uint32_t)f0;
+        edge_f[2 * (size_t)e + 1] = (f1 == hmesh_t::null_face()) ? MCB200_NULL : (uint32_t)f1;
+    }
+    mcb200_soup* soup = nullptr;
+    check(ctx, mcb200_soup_create_sized(ctx, nsf, ncf, (uint32_t)face_vtx.size(), ne, face_vtx.data(), face_edge.data(), edge_f.data(),
+                   sizes.data(), &soup),
+        "soup_create");
+
+    // ---- device narrowphase on the resident trees / pairs ----
+    const int rc = mcb200_narrowphase(ctx, soup, t_last.src, t_last.cut, t_last.res, 0);
+    mcb200_counts counts;
+    const int rc2 = rc ? rc : mcb200_result_counts(ctx, t_last.res, &counts);
+    if (rc2) {
+        mcb200_soup_free(ctx, soup);
+        check(ctx, rc2, "narrowphase");
+    }
+    if (counts.status == MCB200_STATUS_INVALID_SRC_MESH || counts.status == MCB200_STATUS_INVALID_CUT_MESH) {
+        bad_face = (int)counts.bad_face;
+        mcb200_soup_free(ctx, soup);
+        return counts.status == MCB200_STATUS_INVALID_CUT_MESH ? MCB200_HOOK_INVALID_CUT_MESH : MCB200_HOOK_INVALID_SRC_MESH;
+    }
+    if (counts.status == MCB200_STATUS_GENERAL_POSITION_VIOLATION) {
+        mcb200_soup_free(ctx, soup);
+        return MCB200_HOOK_GENERAL_POSITION_VIOLATION;
+    }
+
+    // ---- plane data of the candidate faces (kernel.cpp:2184-2356) ----
+    {
+        const size_t n = (size_t)counts.n_cand_faces;
+        std::vector<uint32_t> faces(n);
+        std::vector<double> normal(3 * n), d(n);
+        std::vector<int32_t> mc(n);
+        check(ctx, mcb200_result_read_planes(ctx, t_last.res, faces.data(), normal.data(), d.data(), mc.data(), n), "read_planes");
+        std::vector<vd_t> tmp;
+        for (size_t k = 0; k < n; ++k) {
+            const fd_t f(faces[k]);
+            ps_tested_face_to_plane_normal[f] = vec3(normal[3 * k], normal[3 * k + 1], normal[3 * k + 2]);
+            ps_tested_face_to_plane_normal_d_param[f] = d[k];
+            ps_tested_face_to_plane_normal_max_comp[f] = (int)mc[k];
+            std::vector<vec3>& verts = ps_tested_face_to_vertices[f];
+            ps.get_vertices_around_face(tmp, f);
+            verts.reserve(tmp.size());
+            for (const vd_t& v : tmp) verts.push_back(ps.vertex(v));
+        }
+    }
+
+    // ---- the registry (kernel.cpp:2601-2655, merged form :2673-2868), records in canonical (edge, face) order ----
+    std::vector<mcb200_record> rec((size_t)counts.n_records);
+    check(ctx, mcb200_result_read_records(ctx, t_last.res, rec.data(), rec.size()), "read_records");
+    mcb200_soup_free(ctx, soup);
+    m0_ivtx_to_intersection_registry_entry.reserve(rec.size());
+    for (const mcb200_record& r : rec) {
+        const ed_t tested_edge(r.edge);
+        const fd_t tested_face(r.face);
+        const vd_t v = m0.add_vertex(vec3(r.point[0], r.point[1], r.point[2])); // ps_vtx_cnt + index in the registry
+        m0_ivtx_to_intersection_registry_entry.push_back(std::make_pair(tested_edge, tested_face));
+        ps_intersecting_edges[tested_edge].push_back(v);
+        const hd_t h0 = ps.halfedge(tested_edge, 0), h1 = ps.halfedge(tested_edge, 1);
+        const fd_t h0_face = ps.face(h0), h1_face = ps.face(h1);
+        const fd_t tested_edge_face = h0_face != hmesh_t::null_face() ? h0_face : h1_face;
+        const bool tested_edge_belongs_to_cm = ((int)tested_edge_face) >= sm_face_count;
+        const fd_t face_pqr = tested_edge_face;
+        const fd_t face_pqs = tested_edge_face == h0_face ? h1_face : hmesh_t::null_face();
+        if (tested_edge_belongs_to_cm) { // key format: {source-mesh face, cut-mesh face}
+            cutpath_edge_creation_info[make_pair(tested_face, face_pqr)].push_back(v);
+            if (face_pqs != hmesh_t::null_face()) cutpath_edge_creation_info[make_pair(tested_face, face_pqs)].push_back(v);
+        } else {
+            cutpath_edge_creation_info[make_pair(tested_edge_face, tested_face)].push_back(v);
+            const fd_t other = (tested_edge_face == h0_face) ? h1_face : h0_face;
+            if (other != hmesh_t::null_face()) cutpath_edge_creation_info[make_pair(other, tested_face)].push_back(v);
+        }
+        if (tested_edge_belongs_to_cm && (h0_face == hmesh_t::null_face() || h1_face == hmesh_t::null_face())) // ps.is_border(tested_edge)
+            cm_border_reentrant_ivtx_list.push_back(v);
+        ps_iface_to_ivtx_list[tested_face].push_back(v);
+        if (h0_face != hmesh_t::null_face()) ps_iface_to_ivtx_list[h0_face].push_back(v);
+        if (h1_face != hmesh_t::null_face()) ps_iface_to_ivtx_list[h1_face].push_back(v);
+        if (!partial_cut_detected) {
+            const bool is_cs_edge = ((int)ps.source(h0)) >= sm_vtx_cnt;
+            const bool is_border = (h0_face == hmesh_t::null_face() || h1_face == hmesh_t::null_face());
+            partial_cut_detected = (is_cs_edge && is_border);
+        }
+    }
+    return MCB200_HOOK_OK;
 }

@@ -22,7 +22,7 @@ needs_ref = pytest.mark.skipif(not (os.path.exists(DRIVER) and os.path.exists(SH
                                reason="oracle/_ref/api_driver or the shim is not built (needs /root/reference at build time)")
 
 
-def run_driver(tmp, tag, src, cut, flags, preload, extra=()):
+def run_driver(tmp, tag, src, cut, flags, preload, extra=(), driver=None):
     d = {"src_xyz": src[0], "src_faces": src[1], "cut_xyz": cut[0], "cut_faces": cut[1], "flags": np.array([flags], dtype=np.uint32)}
     if src[2] is not None:
         d["src_sizes"] = src[2]
@@ -31,7 +31,7 @@ def run_driver(tmp, tag, src, cut, flags, preload, extra=()):
     ip, op = os.path.join(tmp, f"{tag}.in.mcb"), os.path.join(tmp, f"{tag}.out.mcb")
     write_mcb(ip, d)
     env = dict(os.environ, LD_PRELOAD=":".join(preload))
-    r = subprocess.run([DRIVER, ip, op, *extra], capture_output=True, text=True, cwd=tmp, env=env)
+    r = subprocess.run([driver or DRIVER, ip, op, *extra], capture_output=True, text=True, cwd=tmp, env=env)
     assert r.returncode == 0, r.stderr[-2000:]
     return read_mcb(op)
 
@@ -73,3 +73,54 @@ def test_planar_section_through_the_shim(tmp_path):
     for k in ("cc_type", "cc_nv", "cc_nf", "cc_vertices", "cc_faces"):
         assert a[k].tobytes() == b[k].tobytes(), k
     assert a["cc_type"].size > 0
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# The whole hot path inside a live mcDispatch: oracle/_ref/libmcut_hooked.so is the reference with the inline narrowphase
+# of dispatch() (kernel.cpp:1779-3206) replaced by ONE call to mcb200_hook_narrowphase() (oracle/make_hooked_kernel.py,
+# mcut_b200/csrc/shim/mcut_hook.h); broadphase AND narrowphase then run on the B200, everything else is the reference.
+# The registry comes back in canonical (edge, face) order while the reference's own order depends on its thread count,
+# so intersection vertices may be numbered differently: components are compared as geometry (bit-exact coordinates,
+# faces as cyclic vertex sequences), not as index arrays.
+# ---------------------------------------------------------------------------------------------------------------------
+HOOKED = os.path.join(ROOT, "oracle", "_ref", "api_driver_hooked")
+needs_hooked = pytest.mark.skipif(not (os.path.exists(DRIVER) and os.path.exists(HOOKED)),
+                                  reason="oracle/_ref/api_driver_hooked is not built (needs /root/reference at build time)")
+
+
+def canonical_components(out):
+    comps = []
+    vo = fo = so = 0
+    allv = np.ascontiguousarray(out["cc_vertices"]).reshape(-1, 3)
+    allf = np.ascontiguousarray(out["cc_faces"]).reshape(-1)
+    alls = np.ascontiguousarray(out["cc_face_sizes"]).reshape(-1)
+    attrs = np.ascontiguousarray(out["cc_attrs"]).reshape(-1, 3)
+    for i in range(out["cc_type"].size):
+        nv, nf = int(out["cc_nv"][i]), int(out["cc_nf"][i])
+        verts = allv[vo:vo + nv]
+        sizes = alls[so:so + nf]
+        nidx = int(sizes.sum())
+        idx = allf[fo:fo + nidx]
+        vo, fo, so = vo + nv, fo + nidx, so + nf
+        keys = [v.tobytes() for v in verts]
+        faces, o = [], 0
+        for n in sizes.tolist():
+            cyc = [keys[j] for j in idx[o:o + n].tolist()]
+            o += n
+            k = min(range(n), key=lambda t: cyc[t:] + cyc[:t])
+            faces.append(tuple(cyc[k:] + cyc[:k]))
+        comps.append((int(out["cc_type"][i]), tuple(int(x) for x in attrs[i]), nv, tuple(sorted(faces))))
+    return sorted(comps)
+
+
+@needs_hooked
+@pytest.mark.parametrize("case", ["hello", "spheres_k16", "patch_vs_sphere", "cube_cube_axis_aligned", "ico_pair", "float_spheres",
+                                  "uv12", "terrain_plane"])
+def test_mcdispatch_with_device_narrowphase_gives_the_same_components(tmp_path, case):
+    src, cut, flags = cases.ALL[case]()
+    a = run_driver(str(tmp_path), "ref", src, cut, flags, [NODUMP])
+    b = run_driver(str(tmp_path), "hooked", src, cut, flags, [NODUMP], driver=HOOKED)
+    assert int(a["mcDispatch_result"][0]) == int(b["mcDispatch_result"][0])
+    assert a["cc_type"].size == b["cc_type"].size and a["cc_type"].size > 0
+    assert sorted(a["cc_nv"].tolist()) == sorted(b["cc_nv"].tolist()) and sorted(a["cc_nf"].tolist()) == sorted(b["cc_nf"].tolist())
+    assert canonical_components(a) == canonical_components(b)
