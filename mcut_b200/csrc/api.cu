@@ -459,6 +459,11 @@ int mcb200_bvh_intersect(mcb200_ctx* ctx, const mcb200_mesh* src, const mcb200_m
     if (!ctx || !src || !cut || !res) return MCB200_ERR_INVALID;
     MCB_CUDA(ctx, cudaSetDevice(ctx->device));
     ctx->use_main();
+    {
+        // a mesh that so far only served as the query side of a stage call has no node records yet
+        const mcb200_mesh* t = (cut->nf > src->nf) ? src : cut;
+        if (t->built && !t->has_nodes) MCB_TRY(lbvh_build(ctx, const_cast<mcb200_mesh*>(t), t->eps, false));
+    }
     for (int attempt = 0; attempt < 2; ++attempt) {
         MCB_TRY(traverse_pairs(ctx, src, cut, res));
         MCB_TRY(sort_pairs(ctx, src, cut, res));
@@ -589,10 +594,12 @@ static int build_both_interleaved(mcb200_ctx* ctx, mcb200_mesh* src, mcb200_mesh
     std::vector<std::function<int()>> qa, qb;
     ctx->use_main();
     ctx->recording = &qa;
-    int rc = lbvh_build(ctx, src, 0.0);
+    // the mesh with more faces is the traversal's query side (traverse.cu): it needs its groups, not its node records
+    const bool query_is_cut = cut->nf > src->nf;
+    int rc = lbvh_build(ctx, src, 0.0, !query_is_cut);
     ctx->use_aux();
     ctx->recording = &qb;
-    if (!rc) rc = lbvh_build(ctx, cut, cut_eps);
+    if (!rc) rc = lbvh_build(ctx, cut, cut_eps, query_is_cut);
     ctx->recording = nullptr;
     ctx->use_main();
     for (size_t i = 0; !rc && (i < qa.size() || i < qb.size()); ++i) {
@@ -775,7 +782,8 @@ int mcb200_intersect_stage_host(mcb200_ctx* ctx, const mcb200_host_mesh* hsrc, c
     MCB_CUDA(ctx, cudaEventRecord(ctx->ev_fork, ctx->stream));
     MCB_CUDA(ctx, cudaStreamWaitEvent(ctx->aux, ctx->ev_fork, 0));
     MCB_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_up[0], 0));
-    rc = lbvh_build(ctx, src, 0.0);
+    const bool query_is_cut = cut->nf > src->nf; // the query side of the traversal needs groups only
+    rc = lbvh_build(ctx, src, 0.0, !query_is_cut);
     // the polygon soup needs the face arrays only: it is numbered on the lowest-priority lane while the cut mesh's
     // coordinates still travel, and gives way to the builds whenever they have blocks to place
     ctx->use_bg();
@@ -786,7 +794,7 @@ int mcb200_intersect_stage_host(mcb200_ctx* ctx, const mcb200_host_mesh* hsrc, c
     cudaEventRecord(ctx->ev_bg, ctx->bg);
     ctx->use_aux();
     cudaStreamWaitEvent(ctx->aux, ctx->ev_up[1], 0);
-    if (!rc) rc = lbvh_build(ctx, cut, cut_eps);
+    if (!rc) rc = lbvh_build(ctx, cut, cut_eps, query_is_cut);
     cudaEventRecord(ctx->ev_join, ctx->aux);
     ctx->use_main();
     cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0);

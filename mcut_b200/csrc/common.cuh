@@ -183,6 +183,7 @@ struct mcb200_mesh {
     dbuf groups; // [nf] uint2 query groups (first leaf, count) + u32 counter after them
     dbuf group_up; // [<= nf] box + parent word of every group root (input of the atomic climb)
     bool groups_valid = false;
+    bool has_nodes = false; // false after a query-only build: groups exist, node records do not
 };
 
 // One LBVH node: both children's boxes live in the parent so one 128-byte line feeds a traversal step.

@@ -314,6 +314,9 @@ __device__ __forceinline__ unsigned alloc_groups_block(unsigned* n_groups, unsig
 constexpr int RHALO = 32;
 constexpr int RWIN = BLOCK + 2 * RHALO;
 
+// NODES = false: the mesh will only be the QUERY side of a traversal — it needs its groups (maximal treelets + union boxes)
+// but nobody will walk its tree, so no node record, no parent word is written and the climb kernel is not run.
+template <bool NODES>
 __global__ void __launch_bounds__(BLOCK) k_tree(const uint32_t* __restrict__ codes, const double* __restrict__ face_bbox,
     const uint32_t* __restrict__ sorted_faces, uint32_t nf, bvh_node_t* nodes, uint32_t* __restrict__ parent,
     uint2* __restrict__ groups, group_up_t* __restrict__ group_up, unsigned* __restrict__ n_groups)
@@ -382,7 +385,7 @@ __global__ void __launch_bounds__(BLOCK) k_tree(const uint32_t* __restrict__ cod
         const int ii = (int)i;
         const node_topology t = karras_node<true>(cw, ii, deferred);
         if (!deferred) {
-            write_topology(nodes, parent, nf, i, t);
+            if (NODES) write_topology(nodes, parent, nf, i, t);
             lo = t.lo;
             hi = t.hi;
             gamma = t.gamma;
@@ -409,7 +412,7 @@ __global__ void __launch_bounds__(BLOCK) k_tree(const uint32_t* __restrict__ cod
     unsigned g = alloc_groups_block(n_groups, (root0 ? 1u : 0u) + (root1 ? 1u : 0u), s_warp, &s_base);
 
     // ---- boxes of the small nodes straight from the leaf window ----
-    if (small) {
+    if (small && (NODES || root0)) {
         double box[6], rb[6];
 #pragma unroll
         for (int k = 0; k < 6; ++k) {
@@ -428,8 +431,10 @@ __global__ void __launch_bounds__(BLOCK) k_tree(const uint32_t* __restrict__ cod
                 rb[k] = ref_min(rb[k], s_box[q - wbase][k]);
                 rb[3 + k] = ref_max(rb[3 + k], s_box[q - wbase][3 + k]);
             }
-        store_box(nodes[i].lbox, box);
-        store_box(nodes[i].rbox, rb);
+        if (NODES) {
+            store_box(nodes[i].lbox, box);
+            store_box(nodes[i].rbox, rb);
+        }
         if (root0) {
 #pragma unroll
             for (int k = 0; k < 3; ++k) {
@@ -451,7 +456,7 @@ __global__ void __launch_bounds__(BLOCK) k_tree(const uint32_t* __restrict__ cod
         group_up[g].pw = nf - 1u + i;
     }
     // the few nodes whose range leaves the window (> 512 leaves): dependent global probes, now that nobody waits for them
-    if (deferred) {
+    if (NODES && deferred) {
         bool unused = false;
         const node_topology t = karras_node<false>(cw, (int)i, unused);
         write_topology(nodes, parent, nf, i, t);
@@ -519,7 +524,7 @@ int lbvh_reserve(mcb200_ctx* ctx, mcb200_mesh* m)
 }
 
 // Everything is enqueued on ctx->cur (the caller picks the lane); all allocations happen in lbvh_reserve.
-int lbvh_build(mcb200_ctx* ctx, mcb200_mesh* m, double eps)
+int lbvh_build(mcb200_ctx* ctx, mcb200_mesh* m, double eps, bool query_only)
 {
     MCB_TRY(lbvh_reserve(ctx, m));
     const uint32_t nf = m->nf;
@@ -564,10 +569,17 @@ int lbvh_build(mcb200_ctx* ctx, mcb200_mesh* m, double eps)
         ctx->set_error("internal: Morton sort must use an even number of passes", __FILE__, __LINE__);
         return MCB200_ERR_INTERNAL;
     }
-    MCB_LAUNCH(ctx, k_tree, div_up(nf, BLOCK), BLOCK, 0, m->sorted_codes.as<uint32_t>(), m->face_bbox.as<double>(),
-        m->sorted_faces.as<uint32_t>(), nf, m->nodes.as<bvh_node_t>(), m->parent.as<uint32_t>(), m->groups.as<uint2>(),
-        m->group_up.as<group_up_t>(), n_groups);
-    if (nf > 1) {
+    if (nf <= 1) query_only = false; // the one-leaf pseudo tree is free
+    if (query_only)
+        MCB_LAUNCH(ctx, k_tree<false>, div_up(nf, BLOCK), BLOCK, 0, m->sorted_codes.as<uint32_t>(), m->face_bbox.as<double>(),
+            m->sorted_faces.as<uint32_t>(), nf, m->nodes.as<bvh_node_t>(), m->parent.as<uint32_t>(), m->groups.as<uint2>(),
+            m->group_up.as<group_up_t>(), n_groups);
+    else
+        MCB_LAUNCH(ctx, k_tree<true>, div_up(nf, BLOCK), BLOCK, 0, m->sorted_codes.as<uint32_t>(), m->face_bbox.as<double>(),
+            m->sorted_faces.as<uint32_t>(), nf, m->nodes.as<bvh_node_t>(), m->parent.as<uint32_t>(), m->groups.as<uint2>(),
+            m->group_up.as<group_up_t>(), n_groups);
+    m->has_nodes = !query_only;
+    if (nf > 1 && !query_only) {
         // enough threads for every group root to climb concurrently (about nf/16 of them; nf/4 is a safe bound for the grid,
         // the kernel strides over the device-side count anyway)
         const unsigned want = div_up((size_t)nf / 4u + 1u, BLOCK);

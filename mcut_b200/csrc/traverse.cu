@@ -379,6 +379,10 @@ int traverse_pairs(mcb200_ctx* ctx, const mcb200_mesh* src, const mcb200_mesh* c
     const bool query_is_cut = cut->nf > src->nf;
     const mcb200_mesh* q = query_is_cut ? cut : src;
     const mcb200_mesh* t = query_is_cut ? src : cut;
+    if (!t->has_nodes) {
+        ctx->set_error("bvh_intersect: the tree-side mesh was built query-only (internal: rebuild it fully first)", __FILE__, __LINE__);
+        return MCB200_ERR_INTERNAL;
+    }
     MCB_TRY(traverse_reserve(ctx, src, cut, res));
     if (!res->counters_zeroed) MCB_TRY(result_reset_counters(ctx, res));
     res->counters_zeroed = false;
