@@ -664,7 +664,7 @@ int mcb200_intersect_stage(mcb200_ctx* ctx, mcb200_mesh* src, mcb200_mesh* cut, 
 }
 
 // Stage the host arrays of one mesh into the context-owned staging mesh `k` (0 source, 1 cut); copies go to ctx->copy.
-static int stage_mesh(mcb200_ctx* ctx, int k, const mcb200_host_mesh* hm)
+static int stage_mesh(mcb200_ctx* ctx, int k, const mcb200_host_mesh* hm, bool last)
 {
     if (!hm || !hm->xyz || !hm->face_vtx || hm->nv == 0 || hm->nf == 0) MCB_FAIL(ctx, MCB200_ERR_INVALID, "stage_host: empty mesh or NULL array");
     if (!ctx->st_mesh[k]) {
@@ -700,15 +700,16 @@ static int stage_mesh(mcb200_ctx* ctx, int k, const mcb200_host_mesh* hm)
     // buffers come from the main stream's pool order: make the copy stream wait for that point
     MCB_CUDA(ctx, cudaEventRecord(ctx->ev_fork, ctx->stream));
     MCB_CUDA(ctx, cudaStreamWaitEvent(ctx->copy, ctx->ev_fork, 0));
-    // the cut mesh sends its faces first: with them the polygon soup can be numbered while the coordinates still travel
-    if (k == 0) MCB_CUDA(ctx, cudaMemcpyAsync(ctx->st_xyz[k].p, hm->xyz, vbytes, cudaMemcpyHostToDevice, ctx->copy));
+    // the mesh that travels last sends its faces first: with them the polygon soup can be numbered while the coordinates
+    // are still on their way
+    if (!last) MCB_CUDA(ctx, cudaMemcpyAsync(ctx->st_xyz[k].p, hm->xyz, vbytes, cudaMemcpyHostToDevice, ctx->copy));
     MCB_CUDA(ctx, cudaMemcpyAsync(ctx->st_fv[k].p, hm->face_vtx, sizeof(uint32_t) * (size_t)nh, cudaMemcpyHostToDevice, ctx->copy));
     if (!m->is_tri) {
         // `off` is a local: this (small, polygon-only) copy must complete before it goes out of scope
         MCB_CUDA(ctx, cudaMemcpyAsync(ctx->st_fo[k].p, off.data(), sizeof(uint32_t) * off.size(), cudaMemcpyHostToDevice, ctx->copy));
         MCB_CUDA(ctx, cudaStreamSynchronize(ctx->copy));
     }
-    if (k == 1) {
+    if (last) {
         MCB_CUDA(ctx, cudaEventRecord(ctx->ev_up[2], ctx->copy)); // all face arrays are on the device
         MCB_CUDA(ctx, cudaMemcpyAsync(ctx->st_xyz[k].p, hm->xyz, vbytes, cudaMemcpyHostToDevice, ctx->copy));
     }
@@ -729,9 +730,15 @@ int mcb200_intersect_stage_host(mcb200_ctx* ctx, const mcb200_host_mesh* hsrc, c
     // the previous call's kernels may still be reading the staging buffers
     MCB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     ctx->use_main();
-    // ---- uploads, in the order the stage consumes them: source mesh, cut mesh, polygon-soup ids ----
-    MCB_TRY(stage_mesh(ctx, 0, hsrc));
-    MCB_TRY(stage_mesh(ctx, 1, hcut));
+    // ---- uploads, in the order the stage consumes them.  The tree-side mesh goes first: its build is the longer one
+    // (node records + climb); the query-side mesh (the one with more faces) travels last, its shorter build is the tail ----
+    if (hcut->nf > hsrc->nf) {
+        MCB_TRY(stage_mesh(ctx, 0, hsrc, false));
+        MCB_TRY(stage_mesh(ctx, 1, hcut, true));
+    } else {
+        MCB_TRY(stage_mesh(ctx, 1, hcut, false));
+        MCB_TRY(stage_mesh(ctx, 0, hsrc, true));
+    }
     mcb200_mesh* src = ctx->st_mesh[0];
     mcb200_mesh* cut = ctx->st_mesh[1];
     MCB_TRY(mcb200_mesh_set_frame(ctx, src, com, shift, nullptr));
