@@ -105,6 +105,7 @@ int mcb200_ctx_create(int device, void* stream, mcb200_ctx** out)
     cudaEventCreateWithFlags(&ctx->ev_bg, cudaEventDisableTiming);
     cudaEventCreateWithFlags(&ctx->ev_np, cudaEventDisableTiming);
     cudaEventCreateWithFlags(&ctx->ev_np2, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&ctx->ev_np3, cudaEventDisableTiming);
     for (auto& ev : ctx->ev_up) cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
     cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming);
     cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming);
@@ -133,6 +134,7 @@ void mcb200_ctx_destroy(mcb200_ctx* ctx)
     cudaEventDestroy(ctx->ev_bg);
     cudaEventDestroy(ctx->ev_np);
     cudaEventDestroy(ctx->ev_np2);
+    cudaEventDestroy(ctx->ev_np3);
     for (int k = 0; k < 2; ++k) {
         if (ctx->st_mesh[k]) mcb200_mesh_free(ctx, ctx->st_mesh[k]);
         ctx->release(ctx->st_xyz[k]);

@@ -84,7 +84,7 @@ struct mcb200_ctx {
     // staging for mcb200_intersect_stage_host: copy stream, upload-done events, reusable device copies of the inputs
     cudaStream_t copy = nullptr;
     cudaStream_t bg = nullptr; // lowest-priority lane: work that must not take SM slots from the builds (soup numbering)
-    cudaEvent_t ev_bg = nullptr, ev_np = nullptr, ev_np2 = nullptr; // narrowphase: fork to / join from the background lane
+    cudaEvent_t ev_bg = nullptr, ev_np = nullptr, ev_np2 = nullptr, ev_np3 = nullptr; // narrowphase: fork to / join from the background lane
     cudaEvent_t ev_up[4] = { nullptr, nullptr, nullptr };
     struct mcb200_mesh* st_mesh[2] = { nullptr, nullptr };
     struct mcb200_soup* st_soup = nullptr;

@@ -19,8 +19,8 @@ int narrowphase_run(mcb200_ctx* ctx, const mcb200_soup* soup, const mcb200_mesh*
     mcb200_result* res, uint32_t flags);
 int narrowphase_prezero(mcb200_ctx* ctx, const mcb200_soup* soup, mcb200_result* res);
 int soup_face_vtx_device(mcb200_ctx* ctx, const mcb200_mesh* src, const mcb200_mesh* cut, mcb200_soup* soup);
-int narrowphase_sort_records(mcb200_ctx* ctx, mcb200_result* res);
-int narrowphase_sort_tests(mcb200_ctx* ctx, mcb200_result* res);
+int narrowphase_sort_records(mcb200_ctx* ctx, mcb200_result* res, int part = 3);
+int narrowphase_sort_tests(mcb200_ctx* ctx, mcb200_result* res, int part = 3);
 // soup_ids.cu
 int soup_number_reserve(mcb200_ctx* ctx, const mcb200_mesh* src, const mcb200_mesh* cut, mcb200_soup* soup);
 int soup_number_device(mcb200_ctx* ctx, const mcb200_mesh* src, const mcb200_mesh* cut, mcb200_soup* soup, result_counters_t* counters);

@@ -558,9 +558,11 @@ static int bits_for(uint32_t n)
     return b;
 }
 
+// part: 1 = the small-n kernel, 2 = the radix path (its kernels return at once when the small-n kernel applies), 3 = both.
+// The two parts may run on different lanes: they write items_sorted under mutually exclusive conditions.
 template <typename T>
 int sort_items(mcb200_ctx* ctx, const mcb200_result* res, const T* items, T* items_sorted, dbuf& keys, dbuf& idx,
-    const unsigned long long* d_n, size_t cap, uint32_t nfaces, uint32_t nedges_bound)
+    const unsigned long long* d_n, size_t cap, uint32_t nfaces, uint32_t nedges_bound, int part)
 {
     if (cap == 0) return 0;
     (void)res;
@@ -570,8 +572,10 @@ int sort_items(mcb200_ctx* ctx, const mcb200_result* res, const T* items, T* ite
     MCB_TRY((rsort::reserve_scratch<unsigned long long>(ctx, cap, pd.npasses, true, true)));
     mcb200_ctx::sort_scratch_t& sc = ctx->sc();
     const unsigned grid = (unsigned)ctx->num_sms * 2u;
-    MCB_LAUNCH_NAMED(ctx, "k_rank_sort_small", (k_rank_sort_small<T>), SMALL_SORT / RANK_ITEMS, 256, 0, items, d_n, (unsigned long long)cap,
-        items_sorted);
+    if (part & 1)
+        MCB_LAUNCH_NAMED(ctx, "k_rank_sort_small", (k_rank_sort_small<T>), SMALL_SORT / RANK_ITEMS, 256, 0, items, d_n,
+            (unsigned long long)cap, items_sorted);
+    if (!(part & 2)) return 0;
     MCB_LAUNCH_NAMED(ctx, "k_make_keys", (k_make_keys<T>), grid, 256, 0, items, d_n, (unsigned long long)cap, keys.as<unsigned long long>());
     unsigned long long* kout = nullptr;
     uint32_t* vout = nullptr;
@@ -699,7 +703,6 @@ int narrowphase_run(mcb200_ctx* ctx, const mcb200_soup* soup, const mcb200_mesh*
     const unsigned pgrid = div_up(nf, NBLOCK) < grid ? div_up(nf, NBLOCK) : grid;
     if (tri) MCB_LAUNCH(ctx, k_planes<true>, pgrid, NBLOCK, 0, pa);
     else MCB_LAUNCH(ctx, k_planes<false>, pgrid, NBLOCK, 0, pa);
-    MCB_CUDA(ctx, cudaEventRecord(ctx->ev_np2, ctx->bg));
     ctx->cur = lane;
     ctx->sci = lane_sci;
 
@@ -713,9 +716,21 @@ int narrowphase_run(mcb200_ctx* ctx, const mcb200_soup* soup, const mcb200_mesh*
     res->h_valid = false;
     res->records_sorted_valid = false;
     res->tests_sorted_valid = false;
-    MCB_TRY(narrowphase_sort_records(ctx, res));
-    if (want_log) MCB_TRY(narrowphase_sort_tests(ctx, res));
-    MCB_CUDA(ctx, cudaStreamWaitEvent(ctx->cur, ctx->ev_np2, 0)); // the plane data joins here
+    // Canonical order of the registry.  The small-n kernel stays on this lane; the radix path — nine launches that return
+    // at once in the usual small case — goes to the background lane behind the plane kernel, so its launches are not paid
+    // on the critical path.  (Scratch set 0 is free: this lane's last radix sort was the source mesh's Morton sort.)
+    MCB_CUDA(ctx, cudaEventRecord(ctx->ev_np3, lane));
+    MCB_CUDA(ctx, cudaStreamWaitEvent(ctx->bg, ctx->ev_np3, 0));
+    ctx->use_bg();
+    int rc = narrowphase_sort_records(ctx, res, 2);
+    if (!rc && want_log) rc = narrowphase_sort_tests(ctx, res, 2);
+    cudaEventRecord(ctx->ev_np2, ctx->bg);
+    ctx->cur = lane;
+    ctx->sci = lane_sci;
+    if (rc) return rc;
+    MCB_TRY(narrowphase_sort_records(ctx, res, 1));
+    if (want_log) MCB_TRY(narrowphase_sort_tests(ctx, res, 1));
+    MCB_CUDA(ctx, cudaStreamWaitEvent(ctx->cur, ctx->ev_np2, 0)); // the plane data and the radix path join here
     return 0;
 }
 
@@ -760,22 +775,22 @@ int narrowphase_prezero(mcb200_ctx* ctx, const mcb200_soup* soup, mcb200_result*
     return 0;
 }
 
-int narrowphase_sort_records(mcb200_ctx* ctx, mcb200_result* res)
+int narrowphase_sort_records(mcb200_ctx* ctx, mcb200_result* res, int part)
 {
     if (res->records_sorted_valid) return 0;
     result_counters_t* c = res->counters.as<result_counters_t>();
     MCB_TRY(sort_items<mcb200_record>(ctx, res, res->records.as<mcb200_record>(), res->records_sorted.as<mcb200_record>(),
-        res->rec_keys, res->rec_idx, &c->n_records, res->cap_records, res->nf_ps, res->ne_ps));
-    res->records_sorted_valid = true;
+        res->rec_keys, res->rec_idx, &c->n_records, res->cap_records, res->nf_ps, res->ne_ps, part));
+    if (part & 1) res->records_sorted_valid = true; // narrowphase_run issues part 2 first, part 1 last
     return 0;
 }
 
-int narrowphase_sort_tests(mcb200_ctx* ctx, mcb200_result* res)
+int narrowphase_sort_tests(mcb200_ctx* ctx, mcb200_result* res, int part)
 {
     if (res->tests_sorted_valid || !res->logged_tests) return 0;
     result_counters_t* c = res->counters.as<result_counters_t>();
     MCB_TRY(sort_items<mcb200_test>(ctx, res, res->tests.as<mcb200_test>(), res->tests_sorted.as<mcb200_test>(), res->test_keys,
-        res->test_idx, &c->n_log, res->cap_tests, res->nf_ps, res->ne_ps));
-    res->tests_sorted_valid = true;
+        res->test_idx, &c->n_log, res->cap_tests, res->nf_ps, res->ne_ps, part));
+    if (part & 1) res->tests_sorted_valid = true;
     return 0;
 }

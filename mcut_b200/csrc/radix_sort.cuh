@@ -27,37 +27,48 @@ constexpr unsigned FLAG_AGG = 0x40000000u;
 constexpr unsigned FLAG_INCL = 0x80000000u;
 constexpr unsigned VALUE_MASK = 0x3FFFFFFFu;
 
+// One radix digit: `bits` bits of the key starting at `shift`, continued by `bits2` bits starting at `shift2` (bits2 = 0
+// for an ordinary digit).  A digit may straddle the two bit ranges of a packed key such as (src face << 32 | cut face):
+// the digits then tile the CONCATENATION of the ranges, so 20 + 20 significant bits cost five 8-bit passes, not six.
+struct digit_desc {
+    int shift, bits, shift2, bits2;
+};
+
 struct pass_desc {
-    int shift[MAX_PASSES];
-    int bits[MAX_PASSES];
+    digit_desc d[MAX_PASSES];
     int npasses;
 };
 
-// 8-bit chunks over the bit ranges [lo0, hi0) and [lo1, hi1) (second range optional: hi1 <= lo1)
+// 8-bit chunks over the concatenation of the bit ranges [lo0, hi0) and [lo1, hi1) (second range optional: hi1 <= lo1)
 static inline pass_desc make_passes(int lo0, int hi0, int lo1 = 0, int hi1 = 0)
 {
     pass_desc p;
     p.npasses = 0;
-    for (int b = lo0; b < hi0 && p.npasses < MAX_PASSES; b += RADIX_BITS) {
-        p.shift[p.npasses] = b;
-        p.bits[p.npasses] = (hi0 - b < RADIX_BITS) ? hi0 - b : RADIX_BITS;
-        p.npasses++;
+    const int n0 = hi0 > lo0 ? hi0 - lo0 : 0, n1 = hi1 > lo1 ? hi1 - lo1 : 0;
+    for (int pos = 0; pos < n0 + n1 && p.npasses < MAX_PASSES; pos += RADIX_BITS) {
+        digit_desc& d = p.d[p.npasses++];
+        const int len = (n0 + n1 - pos < RADIX_BITS) ? n0 + n1 - pos : RADIX_BITS;
+        if (pos >= n0) { // entirely in the second range
+            d.shift = lo1 + (pos - n0);
+            d.bits = len;
+            d.shift2 = 0;
+            d.bits2 = 0;
+        } else {
+            d.shift = lo0 + pos;
+            d.bits = (n0 - pos < len) ? n0 - pos : len;
+            d.shift2 = lo1;
+            d.bits2 = len - d.bits;
+        }
     }
-    for (int b = lo1; b < hi1 && p.npasses < MAX_PASSES; b += RADIX_BITS) {
-        p.shift[p.npasses] = b;
-        p.bits[p.npasses] = (hi1 - b < RADIX_BITS) ? hi1 - b : RADIX_BITS;
-        p.npasses++;
-    }
-    for (int i = p.npasses; i < MAX_PASSES; ++i) {
-        p.shift[i] = 0;
-        p.bits[i] = 0;
-    }
+    for (int i = p.npasses; i < MAX_PASSES; ++i) p.d[i] = digit_desc { 0, 0, 0, 0 };
     return p;
 }
 
-template <typename KeyT> __device__ __forceinline__ unsigned digit_of(KeyT k, int shift, int bits)
+template <typename KeyT> __device__ __forceinline__ unsigned digit_of(KeyT k, const digit_desc& d)
 {
-    return (unsigned)(k >> shift) & ((1u << bits) - 1u);
+    const unsigned lo = (unsigned)(k >> d.shift) & ((1u << d.bits) - 1u);
+    const unsigned hi = d.bits2 ? ((unsigned)(k >> d.shift2) & ((1u << d.bits2) - 1u)) << d.bits : 0u;
+    return lo | hi;
 }
 
 __device__ __forceinline__ size_t resolve_n(const unsigned long long* d_n, size_t n_max)
@@ -88,7 +99,7 @@ __global__ void __launch_bounds__(THREADS) k_histogram(const KeyT* __restrict__ 
     }
     for (size_t i = (size_t)blockIdx.x * THREADS + threadIdx.x; i < n; i += (size_t)gridDim.x * THREADS) {
         const KeyT k = keys[i];
-        for (int p = 0; p < pd.npasses; ++p) atomicAdd(&s_hist[p * RADIX + digit_of(k, pd.shift[p], pd.bits[p])], 1u);
+        for (int p = 0; p < pd.npasses; ++p) atomicAdd(&s_hist[p * RADIX + digit_of(k, pd.d[p])], 1u);
     }
     __syncthreads();
     for (int i = threadIdx.x; i < pd.npasses * RADIX; i += THREADS) {
@@ -143,8 +154,8 @@ template <typename KeyT, typename ValT, bool HAS_VALS, int ITEMS> constexpr size
 
 template <typename KeyT, typename ValT, bool HAS_VALS, int ITEMS>
 __global__ void __launch_bounds__(THREADS) k_onesweep_pass(const KeyT* __restrict__ keys_in, KeyT* __restrict__ keys_out,
-    const ValT* __restrict__ vals_in, ValT* __restrict__ vals_out, const unsigned long long* d_n, size_t n_max, int shift,
-    int bits, int pass_index, const unsigned* __restrict__ hist /* [RADIX] of this pass */,
+    const ValT* __restrict__ vals_in, ValT* __restrict__ vals_out, const unsigned long long* d_n, size_t n_max,
+    digit_desc dd, int pass_index, const unsigned* __restrict__ hist /* [RADIX] of this pass */,
     unsigned* status_all /* [npasses][tiles(n)][RADIX] */, unsigned* tile_counter, size_t skip_le)
 {
     pdl_prologue();
@@ -231,7 +242,7 @@ __global__ void __launch_bounds__(THREADS) k_onesweep_pass(const KeyT* __restric
 #pragma unroll
             for (int j = 0; j < SUB; ++j) {
                 if (full || local0 + j < tile_n) {
-                    const unsigned d = digit_of(key[u * SUB + j], shift, bits);
+                    const unsigned d = digit_of(key[u * SUB + j], dd);
                     s_cnt[d * 32 + lane] += 1;
                 }
             }
@@ -260,7 +271,7 @@ __global__ void __launch_bounds__(THREADS) k_onesweep_pass(const KeyT* __restric
             for (int j = 0; j < SUB; ++j) {
                 unsigned char r = 0;
                 if (full || local0 + j < tile_n) {
-                    const unsigned d = digit_of(key[u * SUB + j], shift, bits);
+                    const unsigned d = digit_of(key[u * SUB + j], dd);
                     r = s_cnt[d * 32 + lane];
                     s_cnt[d * 32 + lane] = (unsigned char)(r + 1);
                 }
@@ -338,7 +349,7 @@ __global__ void __launch_bounds__(THREADS) k_onesweep_pass(const KeyT* __restric
 #pragma unroll
             for (int j = 0; j < SUB; ++j) {
                 if (full || local0 + j < tile_n) {
-                    const unsigned d = digit_of(key[u * SUB + j], shift, bits);
+                    const unsigned d = digit_of(key[u * SUB + j], dd);
                     const unsigned pos = s_tile_excl[d] + s_unit_hist[w * UPW + u][d] + rank[u * SUB + j];
                     s_keys[pos] = key[u * SUB + j];
                     if (HAS_VALS) s_vals[pos] = val[u * SUB + j];
@@ -349,7 +360,7 @@ __global__ void __launch_bounds__(THREADS) k_onesweep_pass(const KeyT* __restric
         // ---- coalesced runs out ----
         for (unsigned i = threadIdx.x; i < tile_n; i += THREADS) {
             const KeyT k = s_keys[i];
-            const unsigned d = digit_of(k, shift, bits);
+            const unsigned d = digit_of(k, dd);
             const size_t dst = (size_t)s_global_off[d] + (i - s_tile_excl[d]);
             keys_out[dst] = k;
             if (HAS_VALS) vals_out[dst] = s_vals[i];
@@ -418,7 +429,7 @@ int sort_passes(mcb200_ctx* ctx, const KeyT* keys_in, KeyT* keys_a, KeyT* keys_b
         KeyT* kout = (p & 1) ? keys_b : keys_a;
         ValT* vout = (p & 1) ? vals_b : vals_a;
         MCB_LAUNCH_NAMED(ctx, pname, (k_onesweep_pass<KeyT, ValT, HAS_VALS, ITEMS>), pgrid, THREADS, smem, kin, kout, vin, vout, d_n, n_max,
-            pd.shift[p], pd.bits[p], p, sc.hist.as<unsigned>() + p * RADIX, sc.status.as<unsigned>(), sc.tilectr.as<unsigned>() + p, skip_le);
+            pd.d[p], p, sc.hist.as<unsigned>() + p * RADIX, sc.status.as<unsigned>(), sc.tilectr.as<unsigned>() + p, skip_le);
         kin = kout;
         vin = vout;
     }

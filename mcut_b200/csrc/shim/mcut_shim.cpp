@@ -15,6 +15,7 @@
 // kernel.cpp:2086-2105), bvhAABBs[0] (preproc.cpp:2896-2897) and — from intersectOIBVHs — the candidate map.  The device
 // tree itself stays resident and is found again through a side table keyed by the address of the caller's bvhAABBs
 // vector.  Built only where the reference's headers exist (see ../Makefile: target shim); it contains no reference code.
+#include <cstdio>
 #include <cstdlib>
 #include <map>
 #include <mutex>
@@ -75,7 +76,11 @@ mcb200_ctx* thread_ctx()
 
 void check(mcb200_ctx* ctx, int rc, const char* what)
 {
-    if (rc != 0) throw std::runtime_error(std::string("mcut_b200: ") + what + ": " + mcb200_last_error(ctx));
+    if (rc == 0) return;
+    const std::string msg = std::string("mcut_b200: ") + what + ": " + mcb200_last_error(ctx);
+    // the reference turns the exception into MC_INVALID_OPERATION and drops its text: keep it visible
+    std::fprintf(stderr, "%s\n", msg.c_str());
+    throw std::runtime_error(msg);
 }
 
 } // namespace

@@ -33,7 +33,9 @@ def run_driver(tmp, tag, src, cut, flags, preload, extra=(), driver=None):
     env = dict(os.environ, LD_PRELOAD=":".join(preload))
     r = subprocess.run([driver or DRIVER, ip, op, *extra], capture_output=True, text=True, cwd=tmp, env=env)
     assert r.returncode == 0, r.stderr[-2000:]
-    return read_mcb(op)
+    out = read_mcb(op)
+    out["_stderr"] = r.stderr[-2000:]
+    return out
 
 
 @needs_ref
@@ -120,7 +122,7 @@ def test_mcdispatch_with_device_narrowphase_gives_the_same_components(tmp_path, 
     src, cut, flags = cases.ALL[case]()
     a = run_driver(str(tmp_path), "ref", src, cut, flags, [NODUMP])
     b = run_driver(str(tmp_path), "hooked", src, cut, flags, [NODUMP], driver=HOOKED)
-    assert int(a["mcDispatch_result"][0]) == int(b["mcDispatch_result"][0])
+    assert int(a["mcDispatch_result"][0]) == int(b["mcDispatch_result"][0]), b["_stderr"]
     assert a["cc_type"].size == b["cc_type"].size and a["cc_type"].size > 0
     assert sorted(a["cc_nv"].tolist()) == sorted(b["cc_nv"].tolist()) and sorted(a["cc_nf"].tolist()) == sorted(b["cc_nf"].tolist())
     assert canonical_components(a) == canonical_components(b)

@@ -103,3 +103,48 @@ def test_shards_partition_the_pair_set(gpu_ctx):
     assert beq(np.sort(np.concatenate(parts)), full)
     for o in (res, ms, mc):
         o.free()
+
+
+def test_c2_through_the_single_host_array_call(oracle, gpu_ctx):
+    """BASELINE size through mcb200_intersect_stage_host: pipelined uploads, polygon soup numbered on the device, query-only
+    build of the larger mesh.  Same pairs, same registry; and a second call on the same context reuses every buffer."""
+    from mcut_b200 import stage
+    src, cut, flags = mg.c2_two_spheres(k=289)
+    ref = oracle.intersect_stage(src, cut, flags)
+    res = stage.Result(gpu_ctx)
+    for _ in range(2):
+        got = stage.intersect_stage_host(gpu_ctx, src, cut, flags, res=res)
+        assert got["n_pairs"] == 34464 and got["n_records"] == 5100
+        assert beq(got["pairs"], ref["pairs"])
+        rr, gr = ref["records"], got["records"]
+        assert beq(gr["edge"], rr["edge"]) and beq(gr["face"], rr["face"]) and beq(gr["point"], rr["point"])
+        assert beq(got["cand_faces"], ref["cand_faces"]) and beq(got["cand_normal"], ref["cand_normal"])
+    res.free()
+
+
+def test_query_only_mesh_is_completed_on_demand(oracle, gpu_ctx):
+    """mcb200_intersect_stage builds the larger mesh query-only (groups, no node records).  Using that mesh afterwards as
+    the TREE side of mcb200_bvh_intersect must still work: the library completes its build first."""
+    from mcut_b200 import stage
+    big = mg.cube_sphere(30, 20.0)
+    small = mg.cube_sphere(12, 20.0, rotation=mg.rot_z(0.2), centre=(15.0, 1.0, 2.0))
+    huge = mg.cube_sphere(41, 20.0, rotation=mg.rot_x(0.1), centre=(-14.0, 3.0, 1.0))
+    ctx = gpu_ctx
+    mb, ms, mh = stage.Mesh(ctx, *big), stage.Mesh(ctx, *small), stage.Mesh(ctx, *huge)
+    soup = stage.Soup(ctx, mb, ms)
+    res = stage.Result(ctx)
+    ctx.check(ctx.L.mcb200_intersect_stage(ctx.h, mb.h, ms.h, 0.0, soup.h, res.h, 0))  # `big` is the query side here
+    n1 = res.counts().n_pairs
+    res2 = stage.Result(ctx)
+    mh.build(0.0)
+    ctx.check(ctx.L.mcb200_bvh_intersect(ctx.h, mb.h, mh.h, res2.h))  # now `big` is the tree side (huge has more faces)
+    got = res2.pairs()
+    # reference answer from fully built meshes
+    mb2, mh2 = stage.Mesh(ctx, *big), stage.Mesh(ctx, *huge)
+    mb2.build(0.0)
+    mh2.build(0.0)
+    res3 = stage.Result(ctx)
+    ctx.check(ctx.L.mcb200_bvh_intersect(ctx.h, mb2.h, mh2.h, res3.h))
+    assert n1 > 0 and got.size > 0 and beq(got, res3.pairs())
+    for o in (res, res2, res3, soup, mb, ms, mh, mb2, mh2):
+        o.free()
