@@ -39,7 +39,7 @@ def bench_name(n):
     m = re.match(r"k_tests<(\(bool\))?([01]), (\(bool\))?([01])>", n)
     if m:
         return "k_tests_%s_%s" % ("exact" if m.group(4) == "1" else "filter", "tri" if m.group(2) == "1" else "poly")
-    m = re.match(r"k_(face_bbox|planes)<(\(bool\))?([01])>", n)
+    m = re.match(r"k_(face_bbox|planes|tree)<(\(bool\))?([01])>", n)
     if m:
         return "k_%s<%s>" % (m.group(1), "true" if m.group(3) == "1" else "false")
     return re.sub(r"[(<].*", "", n)
