@@ -360,6 +360,21 @@ def run_ours(args):
             total_ms = float(t.item())
         return total_ms
 
+    def settle_capacity(step, result):
+        """One untimed run: a dispatch whose pair count exceeds the default buffer reports MCB200_ERR_CAPACITY from
+        mcb200_result_counts, which also raises the capacity; the timed loops then run with buffers that fit."""
+        for _ in range(4):
+            try:
+                step()
+                result.counts()
+                return
+            except stage.Mcb200Error as e:
+                if e.code != stage.ERR_CAPACITY:
+                    raise
+        raise RuntimeError("pair buffer did not settle")
+
+    settle_capacity(step_resident, res)
+
     # ---- value: resident inputs ----
     launches0 = ctx.launches
     sampler = ClockSampler(local_rank)
@@ -400,6 +415,7 @@ def run_ours(args):
         d2h["pairs"] = int(cc.n_pairs)
         d2h["records"] = int(cc.n_records)
 
+    settle_capacity(step_e2e, res2)
     e2e_steps = max(3, min(args.steps, 10))
     e2e_total = timed_loop(step_e2e, e2e_steps, max(args.warmup, 3), flush=False)
     e2e_ms = e2e_total / e2e_steps
