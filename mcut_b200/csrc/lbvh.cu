@@ -558,7 +558,7 @@ int lbvh_build(mcb200_ctx* ctx, mcb200_mesh* m, double eps, bool query_only)
     // four passes end in the mesh's own arrays.  The histograms come out of k_morton.
     const rsort::pass_desc pd = rsort::make_passes(0, 32);
     constexpr int SORT_TILE = rsort::THREADS * rsort::items_for<uint32_t>::value;
-    const unsigned status_words = (unsigned)(((size_t)nf + SORT_TILE - 1) / SORT_TILE) * rsort::RADIX * (unsigned)pd.npasses;
+    const unsigned status_words = (unsigned)rsort::status_rows(((size_t)nf + SORT_TILE - 1) / SORT_TILE) * rsort::RADIX * (unsigned)pd.npasses;
     MCB_LAUNCH(ctx, k_morton, grid, BLOCK, 0, m->face_bbox.as<double>(), nf, root_ord, root_dec, m->codes.as<uint32_t>(),
         m->sorted_codes.as<uint32_t>(), sc.hist.as<unsigned>(), sc.status.as<unsigned>(), status_words);
     uint32_t *kout = nullptr, *vout = nullptr;

@@ -27,6 +27,11 @@ constexpr unsigned FLAG_AGG = 0x40000000u;
 constexpr unsigned FLAG_INCL = 0x80000000u;
 constexpr unsigned VALUE_MASK = 0x3FFFFFFFu;
 
+// Status rows of one pass: one row of RADIX words per tile (the tile's digit counts) followed by one row per GROUP of
+// LOOK_GROUP consecutive tiles (the group's digit counts) — see the look-back in k_onesweep_pass.
+constexpr int LOOK_GROUP = 16;
+__host__ __device__ __forceinline__ size_t status_rows(size_t tiles) { return tiles + (tiles + LOOK_GROUP - 1) / LOOK_GROUP; }
+
 // One radix digit: `bits` bits of the key starting at `shift`, continued by `bits2` bits starting at `shift2` (bits2 = 0
 // for an ordinary digit).  A digit may straddle the two bit ranges of a packed key such as (src face << 32 | cut face):
 // the digits then tile the CONCATENATION of the ranges, so 20 + 20 significant bits cost five 8-bit passes, not six.
@@ -94,7 +99,7 @@ __global__ void __launch_bounds__(THREADS) k_histogram(const KeyT* __restrict__ 
     __syncthreads();
     {
         const size_t tiles = (n + tile_items - 1) / tile_items;
-        const size_t words = tiles * RADIX * (size_t)pd.npasses;
+        const size_t words = status_rows(tiles) * RADIX * (size_t)pd.npasses;
         for (size_t i = (size_t)blockIdx.x * THREADS + threadIdx.x; i < words; i += (size_t)gridDim.x * THREADS) status[i] = 0u;
     }
     for (size_t i = (size_t)blockIdx.x * THREADS + threadIdx.x; i < n; i += (size_t)gridDim.x * THREADS) {
@@ -179,7 +184,8 @@ __global__ void __launch_bounds__(THREADS) k_onesweep_pass(const KeyT* __restric
     const size_t n = resolve_n(d_n, n_max);
     if (n <= skip_le) return;
     const unsigned num_tiles = (unsigned)((n + TILE - 1) / TILE);
-    unsigned* status = status_all + (size_t)pass_index * num_tiles * RADIX;
+    unsigned* status = status_all + (size_t)pass_index * status_rows(num_tiles) * RADIX;
+    unsigned* gstatus = status + (size_t)num_tiles * RADIX; // group rows
     const unsigned lane = threadIdx.x & 31u, w = threadIdx.x >> 5;
     unsigned char* s_cnt = s_dyn + (size_t)w * (RADIX * 32); // this warp's counters: [digit][lane]
 
@@ -292,52 +298,80 @@ __global__ void __launch_bounds__(THREADS) k_onesweep_pass(const KeyT* __restric
                 total += c;
             }
         }
-        // publish the tile's digit count as early as possible so successors can look back
+        // publish the tile's digit count as early as possible
         {
             const unsigned d = threadIdx.x;
             volatile unsigned* st = status + (size_t)tile * RADIX + d;
-            *st = (tile == 0) ? (FLAG_INCL | total) : (FLAG_AGG | total);
+            *st = FLAG_AGG | total;
         }
         const unsigned excl_in_tile = block_exclusive_scan(total, s_scan, nullptr);
         s_tile_excl[threadIdx.x] = excl_in_tile;
 
-        // ---- decoupled look-back: sum of this digit's counts over all previous tiles ----
-        // At these sizes every tile of a pass is resident at once, so a tile usually finds AGGREGATES (not inclusive
-        // prefixes) in its predecessors and has to walk far back.  The walk therefore polls LOOK predecessors per step
-        // with independent loads instead of one dependent load per predecessor.
+        // ---- two-level look-back: sum of this digit's counts over all previous tiles ----
+        // At these sizes every tile of a pass is resident at once and publishes at about the same moment, so a chained
+        // look-back would walk all the way back (tiles/16 dependent L2 round trips).  Instead tiles form groups of 16:
+        // a tile sums the counts of the earlier tiles of its own group (one round of independent loads); the LAST tile
+        // of a group also publishes the group total; then the totals of all earlier groups are summed, 16 per round.
+        // Two or three dependent round trips whatever the tile count.  Every awaited tile holds an earlier ticket, so
+        // it is running (or done) and never waits for a later one: no deadlock under any block schedule.
         {
-            constexpr int LOOK = 16;
             const unsigned d = threadIdx.x;
+            const unsigned g = tile / LOOK_GROUP, j = tile % LOOK_GROUP;
             unsigned prefix = 0;
-            if (tile > 0) {
-                int t = (int)tile - 1;
+            {
+                unsigned sv[LOOK_GROUP - 1];
+                bool all;
+                do {
+                    all = true;
+#pragma unroll
+                    for (int k = 0; k < LOOK_GROUP - 1; ++k) {
+                        unsigned cur = FLAG_AGG;
+                        if ((unsigned)k < j) cur = *reinterpret_cast<volatile unsigned*>(status + (size_t)(g * LOOK_GROUP + k) * RADIX + d);
+                        sv[k] = cur;
+                        all = all && ((cur & FLAG_MASK) != 0u);
+                    }
+                } while (!all);
+#pragma unroll
+                for (int k = 0; k < LOOK_GROUP - 1; ++k) prefix += sv[k] & VALUE_MASK;
+            }
+            if (j == LOOK_GROUP - 1) {
+                volatile unsigned* gp = gstatus + (size_t)g * RADIX + d;
+                *gp = FLAG_AGG | (prefix + total);
+            }
+            // earlier groups: decoupled look-back over GROUP rows, 16 polled per step, nearest first.  A group row starts as
+            // the group's total (FLAG_AGG) and is upgraded by its last tile to the inclusive prefix (FLAG_INCL) once that tile
+            // knows its own prefix — with many waves of tiles the walk stops at the first inclusive row it meets.
+            unsigned before = 0;
+            if (g > 0) {
+                int t = (int)g - 1;
                 bool done = false;
                 while (!done) {
-                    unsigned sv[LOOK];
+                    unsigned sv[LOOK_GROUP];
 #pragma unroll
-                    for (int k = 0; k < LOOK; ++k) {
-                        const int tt = t - k;
-                        volatile unsigned* st = status + (size_t)(tt >= 0 ? tt : 0) * RADIX + d;
-                        unsigned cur = FLAG_INCL + 0u;
-                        if (tt >= 0) cur = *st;
-                        sv[k] = cur; // before tile 0: an inclusive prefix of zero
+                    for (int k = 0; k < LOOK_GROUP; ++k) {
+                        const int gg = t - k;
+                        unsigned cur = FLAG_INCL + 0u; // before group 0: an inclusive prefix of zero
+                        if (gg >= 0) cur = *reinterpret_cast<volatile unsigned*>(gstatus + (size_t)gg * RADIX + d);
+                        sv[k] = cur;
                     }
-                    // consume the ready statuses nearest-first; stop at the first not-ready one and poll again from it
                     int used = 0;
 #pragma unroll
-                    for (int k = 0; k < LOOK; ++k) {
+                    for (int k = 0; k < LOOK_GROUP; ++k) {
                         if (done || used != k) continue;
                         const unsigned sk = sv[k];
-                        if ((sk & FLAG_MASK) == 0) continue; // not published yet
-                        prefix += sk & VALUE_MASK;
+                        if ((sk & FLAG_MASK) == 0) continue; // not published yet: poll again from here
+                        before += sk & VALUE_MASK;
                         used = k + 1;
                         if (sk & FLAG_INCL) done = true;
                     }
                     t -= used;
                 }
-                volatile unsigned* me = status + (size_t)tile * RADIX + d;
-                *me = FLAG_INCL | (prefix + total);
             }
+            if (j == LOOK_GROUP - 1) {
+                volatile unsigned* gp = gstatus + (size_t)g * RADIX + d;
+                *gp = FLAG_INCL | (before + prefix + total);
+            }
+            prefix += before;
             s_global_off[d] = my_bucket_base + prefix;
         }
         __syncthreads(); // ranking is over in every warp: region 0 may now hold the staged keys
@@ -380,7 +414,7 @@ template <typename KeyT> int reserve_scratch(mcb200_ctx* ctx, size_t n_max, int 
     const size_t tiles = (n_max + TILE - 1) / TILE;
     mcb200_ctx::sort_scratch_t& sc = ctx->sc();
     MCB_TRY(ctx->reserve(sc.hist, sizeof(unsigned) * MAX_PASSES * RADIX));
-    MCB_TRY(ctx->reserve(sc.status, sizeof(unsigned) * (size_t)(npasses ? npasses : 1) * (tiles ? tiles : 1) * RADIX));
+    MCB_TRY(ctx->reserve(sc.status, sizeof(unsigned) * (size_t)(npasses ? npasses : 1) * status_rows(tiles ? tiles : 1) * RADIX));
     MCB_TRY(ctx->reserve(sc.tilectr, sizeof(unsigned) * MAX_PASSES));
     if (need_alt_keys) MCB_TRY(ctx->reserve(sc.keys_alt, sizeof(KeyT) * (n_max ? n_max : 1)));
     if (need_alt_vals) MCB_TRY(ctx->reserve(sc.vals_alt, sizeof(uint32_t) * (n_max ? n_max : 1)));
