@@ -146,6 +146,22 @@ int mcb200_result_set_shard(mcb200_ctx* ctx, mcb200_result* res, uint32_t part, 
  * MCB200_ERR_CAPACITY, which also raises the capacity to what the run needed so the caller simply runs the stage again. */
 int mcb200_result_set_pair_capacity(mcb200_ctx* ctx, mcb200_result* res, uint64_t max_pairs);
 
+/* ---------------------------------------------------------------- input validation --------- */
+/* The two O(V+F) passes the reference runs on every input mesh before the kernel, on the device-resident mesh:
+ * find_connected_components (kernel.cpp:235-364, via check_input_mesh, preproc.cpp:505-578: a mesh with more than one
+ * component is rejected) and mesh_is_closed (preproc.cpp:1957-1990, feeds kernel_input.*_is_watertight).  Component ids
+ * are the reference's: components numbered in the order of their smallest vertex, unused vertices count. */
+typedef struct mcb200_validation {
+    uint32_t n_components;
+    uint32_t n_border_edges; /* edges used by one face only */
+    int is_closed; /* n_border_edges == 0 */
+} mcb200_validation;
+int mcb200_mesh_validate(mcb200_ctx* ctx, mcb200_mesh* mesh, mcb200_validation* out);
+/* After mcb200_mesh_validate: fccmap[nf] (component of every face), cc_vertex_count / cc_face_count [n_components].
+ * Any output may be NULL; `capacity_components` bounds the two count arrays. */
+int mcb200_mesh_read_components(mcb200_ctx* ctx, mcb200_mesh* mesh, int32_t* fccmap, int32_t* cc_vertex_count,
+    int32_t* cc_face_count, size_t capacity_components);
+
 /* ---------------------------------------------------------------- (3) narrowphase -------------------------- */
 int mcb200_soup_create(mcb200_ctx* ctx, uint32_t nsf, uint32_t ncf, uint32_t nh, uint32_t ne, const uint32_t* face_vtx,
     const uint32_t* face_edge, const uint32_t* edge_f, mcb200_soup** soup);

@@ -34,6 +34,10 @@ class HostSoup(C.Structure):
     _fields_ = [("nh", C.c_uint32), ("ne", C.c_uint32), ("face_edge", C.c_void_p), ("edge_f", C.c_void_p)]
 
 
+class Validation(C.Structure):
+    _fields_ = [("n_components", C.c_uint32), ("n_border_edges", C.c_uint32), ("is_closed", C.c_int)]
+
+
 class Record(C.Structure):
     _fields_ = [("edge", C.c_uint32), ("face", C.c_uint32), ("point", C.c_double * 3)]
 
@@ -60,6 +64,8 @@ SYMBOLS = {
     "mcb200_mesh_create": (C.c_int, [vp, C.c_int, vp, C.c_uint32, c_u32p, c_u32p, C.c_uint32, C.POINTER(vp)]),
     "mcb200_mesh_adopt_device": (C.c_int, [vp, C.c_int, vp, C.c_uint32, vp, vp, C.c_uint32, C.c_uint32, C.POINTER(vp)]),
     "mcb200_mesh_update_xyz": (C.c_int, [vp, vp, vp, C.c_uint32]),
+    "mcb200_mesh_validate": (C.c_int, [vp, vp, C.POINTER(Validation)]),
+    "mcb200_mesh_read_components": (C.c_int, [vp, vp, c_i32p, c_i32p, c_i32p, C.c_size_t]),
     "mcb200_mesh_set_frame": (C.c_int, [vp, vp, c_dp, c_dp, c_dp]),
     "mcb200_mesh_free": (None, [vp, vp]),
     "mcb200_bvh_build": (C.c_int, [vp, vp, C.c_double]),

@@ -313,6 +313,39 @@ int mcb200_mesh_update_xyz(mcb200_ctx* ctx, mcb200_mesh* mesh, const void* xyz, 
     return 0;
 }
 
+int mcb200_mesh_validate(mcb200_ctx* ctx, mcb200_mesh* mesh, mcb200_validation* out)
+{
+    if (!ctx || !mesh || !out) return MCB200_ERR_INVALID;
+    MCB_CUDA(ctx, cudaSetDevice(ctx->device));
+    ctx->use_main();
+    MCB_TRY(mesh_validate_run(ctx, mesh));
+    uint32_t info[4];
+    MCB_CUDA(ctx, cudaMemcpyAsync(info, mesh->cc_info.p, sizeof(info), cudaMemcpyDeviceToHost, ctx->stream));
+    MCB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    out->n_components = info[0];
+    out->n_border_edges = info[1];
+    out->is_closed = info[1] == 0u ? 1 : 0;
+    mesh->n_components = info[0];
+    return 0;
+}
+
+int mcb200_mesh_read_components(mcb200_ctx* ctx, mcb200_mesh* mesh, int32_t* fccmap, int32_t* cc_vertex_count,
+    int32_t* cc_face_count, size_t capacity_components)
+{
+    if (!ctx || !mesh) return MCB200_ERR_INVALID;
+    if (!mesh->validated) MCB_FAIL(ctx, MCB200_ERR_INVALID, "read_components: run mcb200_mesh_validate first");
+    MCB_CUDA(ctx, cudaSetDevice(ctx->device));
+    if ((cc_vertex_count || cc_face_count) && capacity_components < mesh->n_components)
+        MCB_FAIL(ctx, MCB200_ERR_CAPACITY, "read_components: capacity smaller than the number of components");
+    if (fccmap) MCB_CUDA(ctx, cudaMemcpyAsync(fccmap, mesh->cc_fmap.p, sizeof(int32_t) * mesh->nf, cudaMemcpyDeviceToHost, ctx->stream));
+    if (cc_vertex_count)
+        MCB_CUDA(ctx, cudaMemcpyAsync(cc_vertex_count, mesh->cc_vcount.p, sizeof(int32_t) * mesh->n_components, cudaMemcpyDeviceToHost, ctx->stream));
+    if (cc_face_count)
+        MCB_CUDA(ctx, cudaMemcpyAsync(cc_face_count, mesh->cc_fcount.p, sizeof(int32_t) * mesh->n_components, cudaMemcpyDeviceToHost, ctx->stream));
+    MCB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
 int mcb200_mesh_adopt_device(mcb200_ctx* ctx, int is_float, const void* d_xyz, uint32_t nv, const uint32_t* d_face_vtx,
     const uint32_t* d_face_off, uint32_t nf, uint32_t nh, mcb200_mesh** out)
 {
@@ -376,6 +409,7 @@ void mcb200_mesh_free(mcb200_ctx* ctx, mcb200_mesh* m)
     ctx->release(m->flags);
     ctx->release(m->groups);
     ctx->release(m->group_up);
+    for (dbuf* b : { &m->cc_label, &m->cc_id, &m->cc_vcount, &m->cc_fcount, &m->cc_fmap, &m->cc_info }) ctx->release(*b);
     delete m;
 }
 

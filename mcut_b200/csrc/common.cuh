@@ -182,6 +182,10 @@ struct mcb200_mesh {
     dbuf flags; // [nf-1] u32 refit arrival counters
     dbuf groups; // [nf] uint2 query groups (first leaf, count) + u32 counter after them
     dbuf group_up; // [<= nf] box + parent word of every group root (input of the atomic climb)
+    // input validation products (validate.cu)
+    dbuf cc_label, cc_id, cc_vcount, cc_fcount, cc_fmap, cc_info;
+    bool validated = false;
+    uint32_t n_components = 0;
     bool groups_valid = false;
     bool has_nodes = false; // false after a query-only build: groups exist, node records do not
 };

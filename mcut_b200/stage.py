@@ -173,6 +173,19 @@ class Mesh:
         self.ctx.check(self.ctx.L.mcb200_bvh_read(self.ctx.h, self.h, _dp(bb), _dp(root)))
         return bb, root
 
+    def validate(self):
+        """find_connected_components + mesh_is_closed on the device.  Returns
+        (n_components, fccmap[nf], cc_vertex_count[n], cc_face_count[n], n_border_edges)."""
+        v = _lib.Validation()
+        self.ctx.check(self.ctx.L.mcb200_mesh_validate(self.ctx.h, self.h, C.byref(v)))
+        n = int(v.n_components)
+        fcc = np.zeros(self.nf, dtype=np.int32)
+        cv = np.zeros(max(n, 1), dtype=np.int32)
+        cf = np.zeros(max(n, 1), dtype=np.int32)
+        self.ctx.check(self.ctx.L.mcb200_mesh_read_components(self.ctx.h, self.h, fcc.ctypes.data_as(c_i32p), cv.ctypes.data_as(c_i32p),
+                                                              cf.ctypes.data_as(c_i32p), max(n, 1)))
+        return n, fcc, cv[:n], cf[:n], int(v.n_border_edges)
+
     def read_morton(self):
         codes = np.zeros(self.nf, dtype=np.uint32)
         order = np.zeros(self.nf, dtype=np.uint32)

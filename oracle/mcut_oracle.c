@@ -1355,3 +1355,102 @@ int mco_narrowphase(const mco_soup_t* ps, const uint64_t* pairs, size_t npairs, 
     }
     return out->status;
 }
+
+
+/* ======================================================================================================================
+ * Input validation passes
+ * ==================================================================================================================== */
+
+/* source/kernel.cpp:235-364.  The reference walks the vertices in index order and floods each unvisited one breadth-first
+ * through get_vertices_around_vertex; only the partition and the discovery order of the components escape, so a plain
+ * adjacency-list flood in the same vertex order restates it. */
+int mco_connected_components(uint32_t nv, const uint32_t* face_off, const uint32_t* face_vtx, uint32_t nf, int32_t* fccmap,
+    int32_t* cc_vertex_count, int32_t* cc_face_count)
+{
+    const uint32_t nh = face_off[nf];
+    uint32_t* deg = (uint32_t*)calloc((size_t)nv + 1, sizeof(uint32_t));
+    uint32_t* adj = (uint32_t*)malloc(sizeof(uint32_t) * 2 * (size_t)(nh ? nh : 1));
+    int32_t* visited = (int32_t*)malloc(sizeof(int32_t) * (size_t)nv);
+    uint32_t* queue = (uint32_t*)malloc(sizeof(uint32_t) * (size_t)nv);
+    uint32_t f, i, v;
+    int ncc = 0;
+    for (f = 0; f < nf; ++f) {
+        const uint32_t n = face_off[f + 1] - face_off[f];
+        for (i = 0; i < n; ++i) {
+            deg[face_vtx[face_off[f] + i] + 1] += 1;
+            deg[face_vtx[face_off[f] + (i + 1) % n] + 1] += 1;
+        }
+    }
+    for (v = 0; v < nv; ++v) deg[v + 1] += deg[v]; /* offsets */
+    {
+        uint32_t* fill = (uint32_t*)malloc(sizeof(uint32_t) * (size_t)nv);
+        for (v = 0; v < nv; ++v) fill[v] = deg[v];
+        for (f = 0; f < nf; ++f) {
+            const uint32_t n = face_off[f + 1] - face_off[f];
+            for (i = 0; i < n; ++i) {
+                const uint32_t a = face_vtx[face_off[f] + i], b = face_vtx[face_off[f] + (i + 1) % n];
+                adj[fill[a]++] = b;
+                adj[fill[b]++] = a;
+            }
+        }
+        free(fill);
+    }
+    for (v = 0; v < nv; ++v) visited[v] = -1;
+    for (v = 0; v < nv; ++v) {
+        uint32_t head = 0, tail = 0;
+        if (visited[v] != -1) continue;
+        visited[v] = ncc;
+        cc_vertex_count[ncc] = 1;
+        cc_face_count[ncc] = 0;
+        queue[tail++] = v;
+        while (head < tail) {
+            const uint32_t u = queue[head++];
+            uint32_t k;
+            for (k = deg[u]; k < deg[u + 1]; ++k) {
+                const uint32_t w = adj[k];
+                if (visited[w] == -1) {
+                    visited[w] = ncc;
+                    cc_vertex_count[ncc] += 1;
+                    queue[tail++] = w;
+                }
+            }
+        }
+        ++ncc;
+    }
+    for (f = 0; f < nf; ++f) { /* kernel.cpp:330-360: the component of the face's first vertex */
+        const int32_t c = visited[face_vtx[face_off[f]]];
+        fccmap[f] = c;
+        cc_face_count[c] += 1;
+    }
+    free(deg);
+    free(adj);
+    free(visited);
+    free(queue);
+    return ncc;
+}
+
+/* source/preproc.cpp:1957-1990: a halfedge without a face exists exactly when an edge is used by one face only. */
+uint32_t mco_border_edges(uint32_t nv, const uint32_t* face_off, const uint32_t* face_vtx, uint32_t nf)
+{
+    /* count the uses of every unordered vertex pair with a sort of the pairs */
+    const uint32_t nh = face_off[nf];
+    uint64_t* keys = (uint64_t*)malloc(sizeof(uint64_t) * (size_t)(nh ? nh : 1));
+    uint32_t f, i, h = 0, border = 0;
+    (void)nv;
+    for (f = 0; f < nf; ++f) {
+        const uint32_t n = face_off[f + 1] - face_off[f];
+        for (i = 0; i < n; ++i) {
+            const uint32_t a = face_vtx[face_off[f] + i], b = face_vtx[face_off[f] + (i + 1) % n];
+            keys[h++] = ((uint64_t)(a < b ? a : b) << 32) | (a < b ? b : a);
+        }
+    }
+    qsort(keys, nh, sizeof(uint64_t), cmp_u64);
+    for (i = 0; i < nh;) {
+        uint32_t j = i + 1;
+        while (j < nh && keys[j] == keys[i]) ++j;
+        if (j - i == 1) ++border;
+        i = j;
+    }
+    free(keys);
+    return border;
+}

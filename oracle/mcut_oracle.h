@@ -135,6 +135,18 @@ int mco_narrowphase(const mco_soup_t* ps, const uint64_t* pairs, size_t npairs, 
     const double* cut_bboxes, int stop_on_gp, mco_narrow_out_t* out);
 void mco_narrow_free(mco_narrow_out_t* o);
 
+
+/* ---- input validation passes ------------------------------------------------------------------------ */
+/* find_connected_components (source/kernel.cpp:235-364): components of the VERTEX graph (edges = face edges), ids in the
+ * order a scan over the vertices discovers them (so a component's id is the rank of its smallest vertex; a vertex that no
+ * face uses is a component of its own).  fccmap[f] = component of the face's vertices; returns the number of components.
+ * cc_vertex_count / cc_face_count need room for nv entries. */
+int mco_connected_components(uint32_t nv, const uint32_t* face_off, const uint32_t* face_vtx, uint32_t nf, int32_t* fccmap,
+    int32_t* cc_vertex_count, int32_t* cc_face_count);
+/* mesh_is_closed (source/preproc.cpp:1957-1990): every halfedge has a face, i.e. no edge is used by one face only.
+ * Returns the number of border edges (0 = watertight). */
+uint32_t mco_border_edges(uint32_t nv, const uint32_t* face_off, const uint32_t* face_vtx, uint32_t nf);
+
 #ifdef __cplusplus
 }
 #endif

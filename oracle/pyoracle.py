@@ -142,8 +142,42 @@ def ref() -> C.CDLL:
         R.ref_point_in_polygon.restype = C.c_char
         R.ref_vertex_parameters.argtypes = [C.c_uint, C.c_void_p, C.c_uint, C.c_void_p, C.c_uint, c_dp, c_dp, c_dp, c_dp]
         R.ref_vertex_parameters.restype = C.c_int
+        R.ref_validate.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_int)]
+        R.ref_validate.restype = C.c_int
         _REF = R
     return _REF
+
+
+def ref_validate(nv: int, face_off: np.ndarray, face_vtx: np.ndarray):
+    """find_connected_components + mesh_is_closed of the unmodified reference (kernel.cpp:235-364, preproc.cpp:1957-1990)."""
+    R = ref()
+    nf = len(face_off) - 1
+    fo = np.ascontiguousarray(face_off, dtype=np.uint32)
+    fv = np.ascontiguousarray(face_vtx, dtype=np.uint32)
+    fcc = np.zeros(nf, dtype=np.int32)
+    cv = np.zeros(nv, dtype=np.int32)
+    cf = np.zeros(nv, dtype=np.int32)
+    closed = C.c_int(0)
+    n = R.ref_validate(nv, fo.ctypes.data, fv.ctypes.data, nf, fcc.ctypes.data, cv.ctypes.data, cf.ctypes.data, C.byref(closed))
+    return n, fcc, cv[:max(n, 0)].copy(), cf[:max(n, 0)].copy(), bool(closed.value)
+
+
+def validate(nv: int, face_off: np.ndarray, face_vtx: np.ndarray):
+    """The oracle's restatement of the same two passes; returns (n, fccmap, cc_vertex_count, cc_face_count, border_edges)."""
+    L = lib()
+    nf = len(face_off) - 1
+    fo = np.ascontiguousarray(face_off, dtype=np.uint32)
+    fv = np.ascontiguousarray(face_vtx, dtype=np.uint32)
+    fcc = np.zeros(nf, dtype=np.int32)
+    cv = np.zeros(nv, dtype=np.int32)
+    cf = np.zeros(nv, dtype=np.int32)
+    L.mco_connected_components.argtypes = [C.c_uint32, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.mco_connected_components.restype = C.c_int
+    L.mco_border_edges.argtypes = [C.c_uint32, C.c_void_p, C.c_void_p, C.c_uint32]
+    L.mco_border_edges.restype = C.c_uint32
+    n = L.mco_connected_components(nv, fo.ctypes.data, fv.ctypes.data, nf, fcc.ctypes.data, cv.ctypes.data, cf.ctypes.data)
+    border = L.mco_border_edges(nv, fo.ctypes.data, fv.ctypes.data, nf)
+    return n, fcc, cv[:n].copy(), cf[:n].copy(), int(border)
 
 
 # ------------------------------------------------------------------------------------------------

@@ -7,6 +7,8 @@
 #include "mcut/mcut.h"
 #include "mcut/internal/bvh.h"
 #include "mcut/internal/math.h"
+#include "mcut/internal/hmesh.h"
+#include "mcut/internal/tpool.h"
 
 extern unsigned int morton3D(float x, float y, float z); // source/bvh.cpp:206
 extern int get_ostensibly_implicit_bvh_size(const int t); // source/bvh.cpp:131
@@ -22,7 +24,38 @@ static std::vector<vec3> to_vec(const double* v, int n)
     return out;
 }
 
+extern int find_connected_components(thread_pool& scheduler, std::vector<int>& fccmap, const hmesh_t& mesh,
+    std::vector<int>& cc_to_vertex_count, std::vector<int>& cc_to_face_count); // source/kernel.cpp:235
+extern bool mesh_is_closed(const hmesh_t& mesh); // source/preproc.cpp:1957
+
 extern "C" {
+
+// find_connected_components + mesh_is_closed on a mesh given as arrays (the half-edge mesh is built the reference's way:
+// add_vertex / add_face in order).  Returns the number of components, -1 if a face could not be added.
+int ref_validate(int nv, const unsigned* face_off, const unsigned* face_vtx, int nf, int* fccmap, int* cc_vertex_count,
+    int* cc_face_count, int* is_closed)
+{
+    hmesh_t m;
+    for (int v = 0; v < nv; ++v) m.add_vertex(vec3((double)v, 0.0, 0.0));
+    std::vector<vd_t> fv;
+    for (int f = 0; f < nf; ++f) {
+        fv.clear();
+        for (unsigned h = face_off[f]; h < face_off[f + 1]; ++h) fv.push_back(vd_t(face_vtx[h]));
+        if (m.add_face(fv) == hmesh_t::null_face()) return -1;
+    }
+    // zero helper threads: with helpers the reference's per-component face count is a data race (`cc_to_face_count[id] += 1`
+    // from several pool threads without atomics, kernel.cpp:330-352) and comes out short on meshes above 2048 faces
+    thread_pool pool(0, 1);
+    std::vector<int> map, cv, cf;
+    const int n = find_connected_components(pool, map, m, cv, cf);
+    for (int f = 0; f < nf; ++f) fccmap[f] = map[f];
+    for (int c = 0; c < n; ++c) {
+        cc_vertex_count[c] = cv[c];
+        cc_face_count[c] = cf[c];
+    }
+    *is_closed = mesh_is_closed(m) ? 1 : 0;
+    return n;
+}
 
 unsigned ref_morton3D(float x, float y, float z) { return morton3D(x, y, z); }
 int ref_oibvh_size(int t) { return get_ostensibly_implicit_bvh_size(t); }
