@@ -60,6 +60,13 @@ def workload(name: str):
         return meshgen.c2_two_spheres(k=92), "C2-small: two cube-spheres, 101,568 triangles each (smoke size)"
     if name == "c5":
         return meshgen.c5_near_coplanar(k=409), "C5: two near-coplanar cube-spheres, 2,007,372 triangles each"
+    if name == "c3":
+        tri = np.array([[-900.0, -850.0, -4.1], [1400.0, -700.0, 3.3], [150.0, 1600.0, 1.7]])
+        cut = (tri, np.array([0, 1, 2], dtype=np.uint32), None)
+        flags = meshgen.MC_DISPATCH_VERTEX_ARRAY_DOUBLE | meshgen.MC_DISPATCH_ENFORCE_GENERAL_POSITION
+        return (meshgen.terrain(), cut, flags), "C3 (one of its 256 dispatches): 3,998,792-triangle terrain cut by one triangle"
+    if name == "c4":
+        return meshgen.c4_pair(0), "C4 (one of its 10,000 dispatches): two icospheres of 5,120 triangles"
     raise SystemExit(f"unknown workload {name}")
 
 

@@ -166,3 +166,39 @@ def test_device_soup_numbering_reports_bad_topology(gpu_ctx):
         stage.intersect_stage_host(gpu_ctx, (sx, bad, ss), cut, flags)
     ok = stage.intersect_stage_host(gpu_ctx, src, cut, flags)  # the context is still usable
     assert ok["status"] == 0
+
+
+def test_contexts_in_parallel_threads(oracle):
+    """The MultipleContextsInParallel pattern (tutorials/MultipleContextsInParallel/MultipleContextsInParallel.cpp:129-345):
+    several host threads, one context each, dispatching at the same time.  Every result must still equal the oracle's."""
+    import threading
+    from mcut_b200 import stage
+    names = ["hello", "spheres_k16", "patch_vs_sphere", "cube_cube_tris_offset", "uv12", "ico_pair", "float_spheres", "spheres_k8"]
+    inputs = {n: cases.ALL[n]() for n in names}
+    refs = {n: oracle.intersect_stage(*inputs[n]) for n in names}
+    errors = []
+
+    def worker(tid):
+        try:
+            ctx = stage.Context(0)
+            res = stage.Result(ctx)
+            for rep in range(6):
+                n = names[(tid + rep) % len(names)]
+                src, cut, flags = inputs[n]
+                got = stage.intersect_stage_host(ctx, src, cut, flags, res=res)
+                ref = refs[n]
+                assert beq(got["pairs"], ref["pairs"]), (tid, n, "pairs")
+                assert got["status"] == ref["status"], (tid, n, "status")
+                if ref["status"] == 0:
+                    assert beq(got["records"]["point"], ref["records"]["point"]) and beq(got["records"]["edge"], ref["records"]["edge"]), (tid, n)
+            res.free()
+            ctx.close()
+        except Exception as e:  # noqa: BLE001
+            errors.append(repr(e))
+
+    threads = [threading.Thread(target=worker, args=(t,)) for t in range(6)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert not errors, errors
