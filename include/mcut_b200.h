@@ -173,6 +173,12 @@ void mcb200_soup_free(mcb200_ctx* ctx, mcb200_soup* soup);
 int mcb200_soup_from_meshes(mcb200_ctx* ctx, const mcb200_mesh* src, const mcb200_mesh* cut, mcb200_soup** soup);
 
 #define MCB200_NARROW_LOG_TESTS 1u /* also keep one log entry per edge/face test (parity checks) */
+/* mcb200_intersect_stage_host only: the caller vouches that the source (cut) mesh arrays are bit-for-bit the ones passed to
+ * the previous call on this context, so their upload is skipped (C3: one 4M-triangle terrain against 256 planes; the BVH
+ * is still rebuilt because the internal coordinates depend on both meshes through `com`).  The C API of the reference
+ * only lends its arrays for the duration of a dispatch, so the shim never sets these. */
+#define MCB200_STAGE_SRC_RESIDENT 2u
+#define MCB200_STAGE_CUT_RESIDENT 4u
 /* Consumes res's pairs; uses the face AABBs of the meshes' builds (cut ones enlarged) for the edge cull and the
  * meshes' CURRENT frames for coordinates (so a perturbed cut frame is tested against unperturbed boxes, exactly
  * like preproc.cpp:2562-2945).  Asynchronous. */

@@ -700,7 +700,7 @@ int mcb200_intersect_stage(mcb200_ctx* ctx, mcb200_mesh* src, mcb200_mesh* cut, 
 }
 
 // Stage the host arrays of one mesh into the context-owned staging mesh `k` (0 source, 1 cut); copies go to ctx->copy.
-static int stage_mesh(mcb200_ctx* ctx, int k, const mcb200_host_mesh* hm, bool last)
+static int stage_mesh(mcb200_ctx* ctx, int k, const mcb200_host_mesh* hm, bool last, bool resident)
 {
     if (!hm || !hm->xyz || !hm->face_vtx || hm->nv == 0 || hm->nf == 0) MCB_FAIL(ctx, MCB200_ERR_INVALID, "stage_host: empty mesh or NULL array");
     if (!ctx->st_mesh[k]) {
@@ -708,6 +708,17 @@ static int stage_mesh(mcb200_ctx* ctx, int k, const mcb200_host_mesh* hm, bool l
         ctx->st_mesh[k]->owns_arrays = false;
     }
     mcb200_mesh* m = ctx->st_mesh[k];
+    if (resident) {
+        // the caller vouches that this mesh's arrays are the ones of the previous call on this context: nothing travels
+        if (!m->d_xyz || m->nv != hm->nv || m->nf != hm->nf || m->is_float != (hm->is_float ? 1 : 0))
+            MCB_FAIL(ctx, MCB200_ERR_INVALID, "stage_host: *_RESIDENT flag, but the staged mesh has different counts (or none was staged)");
+        MCB_CUDA(ctx, cudaEventRecord(ctx->ev_fork, ctx->stream));
+        MCB_CUDA(ctx, cudaStreamWaitEvent(ctx->copy, ctx->ev_fork, 0));
+        if (last) MCB_CUDA(ctx, cudaEventRecord(ctx->ev_up[2], ctx->copy));
+        MCB_CUDA(ctx, cudaEventRecord(ctx->ev_up[k], ctx->copy));
+        m->built = false;
+        return 0;
+    }
     m->nv = hm->nv;
     m->nf = hm->nf;
     m->is_float = hm->is_float ? 1 : 0;
@@ -768,12 +779,13 @@ int mcb200_intersect_stage_host(mcb200_ctx* ctx, const mcb200_host_mesh* hsrc, c
     ctx->use_main();
     // ---- uploads, in the order the stage consumes them.  The tree-side mesh goes first: its build is the longer one
     // (node records + climb); the query-side mesh (the one with more faces) travels last, its shorter build is the tail ----
+    const bool src_res = (flags & MCB200_STAGE_SRC_RESIDENT) != 0, cut_res = (flags & MCB200_STAGE_CUT_RESIDENT) != 0;
     if (hcut->nf > hsrc->nf) {
-        MCB_TRY(stage_mesh(ctx, 0, hsrc, false));
-        MCB_TRY(stage_mesh(ctx, 1, hcut, true));
+        MCB_TRY(stage_mesh(ctx, 0, hsrc, false, src_res));
+        MCB_TRY(stage_mesh(ctx, 1, hcut, true, cut_res));
     } else {
-        MCB_TRY(stage_mesh(ctx, 1, hcut, false));
-        MCB_TRY(stage_mesh(ctx, 0, hsrc, true));
+        MCB_TRY(stage_mesh(ctx, 1, hcut, false, cut_res));
+        MCB_TRY(stage_mesh(ctx, 0, hsrc, true, src_res));
     }
     mcb200_mesh* src = ctx->st_mesh[0];
     mcb200_mesh* cut = ctx->st_mesh[1];

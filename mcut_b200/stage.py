@@ -23,6 +23,8 @@ from . import _lib
 from ._lib import Counts, Record, Test, c_dp, c_i32p, c_u32p, c_u64p
 
 ERR_CAPACITY = -4  # include/mcut_b200.h: MCB200_ERR_CAPACITY
+STAGE_SRC_RESIDENT = 2  # MCB200_STAGE_SRC_RESIDENT
+STAGE_CUT_RESIDENT = 4  # MCB200_STAGE_CUT_RESIDENT
 
 MC_DISPATCH_VERTEX_ARRAY_FLOAT = 1 << 0
 MC_DISPATCH_VERTEX_ARRAY_DOUBLE = 1 << 1
@@ -326,7 +328,8 @@ def intersect_stage(ctx: Context, src, cut, flags: int, gp_constant: float = 1e-
 
 
 def intersect_stage_host(ctx: Context, src, cut, flags: int = 0, gp_constant: float = 1e-4, perturbation=None, soup_ids_host=None,
-                         log_tests: bool = False, res: "Result" = None, params=None) -> Dict[str, object]:
+                         log_tests: bool = False, res: "Result" = None, params=None, src_resident: bool = False,
+                         cut_resident: bool = False) -> Dict[str, object]:
     """The same stage through the single pipelined C-ABI call `mcb200_intersect_stage_host`: uploads on a copy stream
     overlap the builds, the polygon-soup vertex lists are derived on the device. `soup_ids_host` = (face_edge, edge_f, ne)
     when the caller already holds `ps` (the reference does, kernel.cpp:1593-1732); None -> computed by the library.
@@ -373,7 +376,7 @@ def intersect_stage_host(ctx: Context, src, cut, flags: int = 0, gp_constant: fl
         pert_a = np.ascontiguousarray(perturbation, dtype=np.float64)
         keep.append(pert_a)
         pert_p = pert_a.ctypes.data_as(C.POINTER(C.c_double))
-    fl = NARROW_LOG_TESTS if log_tests else 0
+    fl = (NARROW_LOG_TESTS if log_tests else 0) | (STAGE_SRC_RESIDENT if src_resident else 0) | (STAGE_CUT_RESIDENT if cut_resident else 0)
     for attempt in range(3):
         ctx.check(ctx.L.mcb200_intersect_stage_host(ctx.h, C.byref(hs), C.byref(hc), com_a.ctypes.data_as(C.POINTER(C.c_double)),
                                                     shift_a.ctypes.data_as(C.POINTER(C.c_double)), pert_p, float(eps), hsoup, res.h,

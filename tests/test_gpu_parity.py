@@ -202,3 +202,22 @@ def test_contexts_in_parallel_threads(oracle):
     for t in threads:
         t.join()
     assert not errors, errors
+
+
+def test_resident_source_mesh_across_dispatches(oracle, gpu_ctx):
+    """C3's pattern: one terrain, many cutting planes.  After the first call the source arrays are declared resident
+    (MCB200_STAGE_SRC_RESIDENT): only the cut mesh travels, the BVH is rebuilt for the new frame, results stay exact."""
+    from mcut_b200 import meshgen as mg, stage
+    ter = mg.terrain(n=120)
+    flags = mg.MC_DISPATCH_VERTEX_ARRAY_DOUBLE | mg.MC_DISPATCH_ENFORCE_GENERAL_POSITION
+    res = stage.Result(gpu_ctx)
+    for k in range(4):
+        tri = np.array([[-900.0, -850.0 + 40.0 * k, -4.1 + k], [1400.0, -700.0, 3.3 - 0.5 * k], [150.0 + 30.0 * k, 1600.0, 1.7]])
+        cut = (tri, np.array([0, 1, 2], dtype=np.uint32), None)
+        ref = oracle.intersect_stage(ter, cut, flags)
+        got = stage.intersect_stage_host(gpu_ctx, ter, cut, flags, res=res, src_resident=(k > 0))
+        assert beq(got["pairs"], ref["pairs"]) and got["status"] == ref["status"]
+        if ref["status"] == 0:
+            rr, gr = ref["records"], got["records"]
+            assert beq(gr["edge"], rr["edge"]) and beq(gr["face"], rr["face"]) and beq(gr["point"], rr["point"])
+    res.free()
