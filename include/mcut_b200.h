@@ -162,6 +162,14 @@ int mcb200_mesh_validate(mcb200_ctx* ctx, mcb200_mesh* mesh, mcb200_validation* 
 int mcb200_mesh_read_components(mcb200_ctx* ctx, mcb200_mesh* mesh, int32_t* fccmap, int32_t* cc_vertex_count,
     int32_t* cc_face_count, size_t capacity_components);
 
+/* Winding number of `query` with respect to the mesh: getWindingNumber(), preproc.cpp:1907-1955, the sum of
+ * calculate_signed_solid_angle() over the faces (triangles :1650-1698, quads :1700-1810).  `query` is in the internal
+ * coordinates the mesh's frame produces (for the reference's use: vertex 0 of the other mesh, transformed).  ~1 = inside,
+ * ~0 = outside (check_and_store_input_mesh_intersection_type uses eps 1e-7, :1999-2122).  Agrees with the reference to
+ * ~1e-13 (device atan2); MCB200_ERR_INVALID for a mesh with faces of more than four vertices (those need the reference's
+ * CDT, which stays on the host). */
+int mcb200_mesh_winding_number(mcb200_ctx* ctx, mcb200_mesh* mesh, const double query[3], double* winding_number);
+
 /* ---------------------------------------------------------------- (3) narrowphase -------------------------- */
 int mcb200_soup_create(mcb200_ctx* ctx, uint32_t nsf, uint32_t ncf, uint32_t nh, uint32_t ne, const uint32_t* face_vtx,
     const uint32_t* face_edge, const uint32_t* edge_f, mcb200_soup** soup);

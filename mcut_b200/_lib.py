@@ -65,6 +65,7 @@ SYMBOLS = {
     "mcb200_mesh_adopt_device": (C.c_int, [vp, C.c_int, vp, C.c_uint32, vp, vp, C.c_uint32, C.c_uint32, C.POINTER(vp)]),
     "mcb200_mesh_update_xyz": (C.c_int, [vp, vp, vp, C.c_uint32]),
     "mcb200_mesh_validate": (C.c_int, [vp, vp, C.POINTER(Validation)]),
+    "mcb200_mesh_winding_number": (C.c_int, [vp, vp, c_dp, C.POINTER(C.c_double)]),
     "mcb200_mesh_read_components": (C.c_int, [vp, vp, c_i32p, c_i32p, c_i32p, C.c_size_t]),
     "mcb200_mesh_set_frame": (C.c_int, [vp, vp, c_dp, c_dp, c_dp]),
     "mcb200_mesh_free": (None, [vp, vp]),

@@ -329,6 +329,22 @@ int mcb200_mesh_validate(mcb200_ctx* ctx, mcb200_mesh* mesh, mcb200_validation* 
     return 0;
 }
 
+int mcb200_mesh_winding_number(mcb200_ctx* ctx, mcb200_mesh* mesh, const double query[3], double* winding_number)
+{
+    if (!ctx || !mesh || !query || !winding_number) return MCB200_ERR_INVALID;
+    MCB_CUDA(ctx, cudaSetDevice(ctx->device));
+    ctx->use_main();
+    MCB_TRY(mesh_winding_run(ctx, mesh, query));
+    double out[2];
+    MCB_CUDA(ctx, cudaMemcpyAsync(out, mesh->cc_wn.p, sizeof(out), cudaMemcpyDeviceToHost, ctx->stream));
+    MCB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    unsigned unsupported;
+    std::memcpy(&unsupported, &out[1], sizeof(unsigned));
+    if (unsupported) MCB_FAIL(ctx, MCB200_ERR_INVALID, "winding_number: the mesh has faces with more than four vertices (host CDT path)");
+    *winding_number = out[0];
+    return 0;
+}
+
 int mcb200_mesh_read_components(mcb200_ctx* ctx, mcb200_mesh* mesh, int32_t* fccmap, int32_t* cc_vertex_count,
     int32_t* cc_face_count, size_t capacity_components)
 {
@@ -409,7 +425,7 @@ void mcb200_mesh_free(mcb200_ctx* ctx, mcb200_mesh* m)
     ctx->release(m->flags);
     ctx->release(m->groups);
     ctx->release(m->group_up);
-    for (dbuf* b : { &m->cc_label, &m->cc_id, &m->cc_vcount, &m->cc_fcount, &m->cc_fmap, &m->cc_info }) ctx->release(*b);
+    for (dbuf* b : { &m->cc_label, &m->cc_id, &m->cc_vcount, &m->cc_fcount, &m->cc_fmap, &m->cc_info, &m->cc_wn }) ctx->release(*b);
     delete m;
 }
 

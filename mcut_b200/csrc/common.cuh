@@ -183,7 +183,7 @@ struct mcb200_mesh {
     dbuf groups; // [nf] uint2 query groups (first leaf, count) + u32 counter after them
     dbuf group_up; // [<= nf] box + parent word of every group root (input of the atomic climb)
     // input validation products (validate.cu)
-    dbuf cc_label, cc_id, cc_vcount, cc_fcount, cc_fmap, cc_info;
+    dbuf cc_label, cc_id, cc_vcount, cc_fcount, cc_fmap, cc_info, cc_wn;
     bool validated = false;
     uint32_t n_components = 0;
     bool groups_valid = false;

@@ -188,6 +188,13 @@ class Mesh:
                                                               cf.ctypes.data_as(c_i32p), max(n, 1)))
         return n, fcc, cv[:n], cf[:n], int(v.n_border_edges)
 
+    def winding_number(self, query) -> float:
+        """getWindingNumber of the reference (preproc.cpp:1907-1955) for a point in this mesh's internal coordinates."""
+        q = np.ascontiguousarray(query, dtype=np.float64)
+        out = C.c_double(0.0)
+        self.ctx.check(self.ctx.L.mcb200_mesh_winding_number(self.ctx.h, self.h, q.ctypes.data_as(c_dp), C.byref(out)))
+        return float(out.value)
+
     def read_morton(self):
         codes = np.zeros(self.nf, dtype=np.uint32)
         order = np.zeros(self.nf, dtype=np.uint32)

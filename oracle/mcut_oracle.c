@@ -1454,3 +1454,107 @@ uint32_t mco_border_edges(uint32_t nv, const uint32_t* face_off, const uint32_t*
     free(keys);
     return border;
 }
+
+
+/* ======================================================================================================================
+ * Winding number
+ * ==================================================================================================================== */
+static void w_sub(double* o, const double* a, const double* b) { o[0] = a[0] - b[0]; o[1] = a[1] - b[1]; o[2] = a[2] - b[2]; }
+static double w_dot(const double* a, const double* b)
+{
+    double r = 0.0; /* dot_product accumulates from 0.0 (math.h:634-642) */
+    r += a[0] * b[0];
+    r += a[1] * b[1];
+    r += a[2] * b[2];
+    return r;
+}
+static double w_len(const double* a) { return sqrt(w_dot(a, a)); } /* length() = sqrt(squared_length()) (math.h) */
+static void w_cross(double* o, const double* a, const double* b)
+{
+    o[0] = a[1] * b[2] - a[2] * b[1];
+    o[1] = a[2] * b[0] - a[0] * b[2];
+    o[2] = a[0] * b[1] - a[1] * b[0];
+}
+static void w_div(double* o, const double* a, double s) { o[0] = a[0] / s; o[1] = a[1] / s; o[2] = a[2] / s; }
+
+static const double W_PI = 3.14159265358979323846;
+
+/* source/preproc.cpp:1650-1698 */
+double mco_solid_angle_tri(const double a[3], const double b[3], const double c[3], const double q[3])
+{
+    double qa[3], qb[3], qc[3], na[3], nb[3], nc[3], e1[3], e2[3], cr[3];
+    double al, bl, cl, numerator, denominator;
+    w_sub(qa, a, q);
+    w_sub(qb, b, q);
+    w_sub(qc, c, q);
+    al = w_len(qa);
+    bl = w_len(qb);
+    cl = w_len(qc);
+    if (al == 0.0 || bl == 0.0 || cl == 0.0) return 0.0;
+    w_div(na, qa, al);
+    w_div(nb, qb, bl);
+    w_div(nc, qc, cl);
+    w_sub(e1, nb, na);
+    w_sub(e2, nc, na);
+    w_cross(cr, e1, e2);
+    numerator = w_dot(na, cr);
+    if (numerator == 0.0) return 0.0;
+    denominator = 1.0 + w_dot(na, nb) + w_dot(na, nc) + w_dot(nb, nc);
+    return atan2(numerator, denominator) / (2. * W_PI);
+}
+
+/* source/preproc.cpp:1700-1810 */
+double mco_solid_angle_quad(const double a[3], const double b[3], const double c[3], const double d[3], const double q[3])
+{
+    double v[4][3], len[4], diag02[3], diag13[3], v01[3], v23[3], cr[3], bary[4];
+    double dot01, dot12, dot23, dot30, omega = 0.0;
+    int i;
+    w_sub(v[0], a, q);
+    w_sub(v[1], b, q);
+    w_sub(v[2], c, q);
+    w_sub(v[3], d, q);
+    for (i = 0; i < 4; ++i) len[i] = w_len(v[i]);
+    if (len[0] == 0.0 || len[1] == 0.0 || len[2] == 0.0 || len[3] == 0.0) return 0.0;
+    for (i = 0; i < 4; ++i) w_div(v[i], v[i], len[i]);
+    w_sub(diag02, v[2], v[0]);
+    w_sub(diag13, v[3], v[1]);
+    w_sub(v01, v[1], v[0]);
+    w_sub(v23, v[3], v[2]);
+    w_cross(cr, v23, diag13);
+    bary[0] = w_dot(v[3], cr);
+    w_cross(cr, v23, diag02);
+    bary[1] = -w_dot(v[2], cr);
+    w_cross(cr, v01, diag13);
+    bary[2] = -w_dot(v[1], cr);
+    w_cross(cr, v01, diag02);
+    bary[3] = w_dot(v[0], cr);
+    dot01 = w_dot(v[0], v[1]);
+    dot12 = w_dot(v[1], v[2]);
+    dot23 = w_dot(v[2], v[3]);
+    dot30 = w_dot(v[3], v[0]);
+    if (bary[0] * bary[2] < bary[1] * bary[3]) { /* split 0-2 */
+        const double n012 = bary[3], n023 = bary[1], dot02 = w_dot(v[0], v[2]);
+        if (n012 != 0.0) omega = atan2(n012, 1.0 + dot01 + dot12 + dot02);
+        if (n023 != 0.0) omega += atan2(n023, 1.0 + dot02 + dot23 + dot30);
+    } else { /* split 1-3 */
+        const double n013 = -bary[2], n123 = -bary[0], dot13 = w_dot(v[1], v[3]);
+        if (n013 != 0.0) omega = atan2(n013, 1.0 + dot01 + dot13 + dot30);
+        if (n123 != 0.0) omega += atan2(n123, 1.0 + dot12 + dot23 + dot13);
+    }
+    return omega / (2. * W_PI);
+}
+
+/* source/preproc.cpp:1812-1955, sequential form */
+double mco_winding_number(const double* xyz, const uint32_t* face_off, const uint32_t* face_vtx, uint32_t nf, const double q[3])
+{
+    double wn = 0.0;
+    uint32_t f;
+    for (f = 0; f < nf; ++f) {
+        const uint32_t h = face_off[f], n = face_off[f + 1] - h;
+        const double *a = xyz + 3 * (size_t)face_vtx[h], *b = xyz + 3 * (size_t)face_vtx[h + 1], *c = xyz + 3 * (size_t)face_vtx[h + 2];
+        if (n == 3) wn += mco_solid_angle_tri(a, b, c, q);
+        else if (n == 4) wn += mco_solid_angle_quad(a, b, c, xyz + 3 * (size_t)face_vtx[h + 3], q);
+        else return NAN;
+    }
+    return wn;
+}

@@ -147,6 +147,14 @@ int mco_connected_components(uint32_t nv, const uint32_t* face_off, const uint32
  * Returns the number of border edges (0 = watertight). */
 uint32_t mco_border_edges(uint32_t nv, const uint32_t* face_off, const uint32_t* face_vtx, uint32_t nf);
 
+/* ---- winding-number inside/outside query --------------------------------------------------------------- */
+/* calculate_signed_solid_angle, triangle (source/preproc.cpp:1650-1698) and quad (:1700-1810) forms, already divided by
+ * 2*pi as in the reference; mco_winding_number sums them over the faces in face order (getWindingNumber, :1907-1955; faces
+ * with more than 4 vertices go through the reference's CDT, which is out of scope: returns NAN for such a mesh). */
+double mco_solid_angle_tri(const double a[3], const double b[3], const double c[3], const double q[3]);
+double mco_solid_angle_quad(const double a[3], const double b[3], const double c[3], const double d[3], const double q[3]);
+double mco_winding_number(const double* xyz, const uint32_t* face_off, const uint32_t* face_vtx, uint32_t nf, const double q[3]);
+
 #ifdef __cplusplus
 }
 #endif

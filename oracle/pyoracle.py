@@ -162,6 +162,30 @@ def ref_validate(nv: int, face_off: np.ndarray, face_vtx: np.ndarray):
     return n, fcc, cv[:max(n, 0)].copy(), cf[:max(n, 0)].copy(), bool(closed.value)
 
 
+def winding_number(xyz: np.ndarray, face_off: np.ndarray, face_vtx: np.ndarray, query) -> float:
+    """The oracle's getWindingNumber (preproc.cpp:1650-1955, sequential sum); NaN for faces with more than 4 vertices."""
+    L = lib()
+    L.mco_winding_number.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p]
+    L.mco_winding_number.restype = C.c_double
+    x = np.ascontiguousarray(xyz, dtype=np.float64)
+    fo = np.ascontiguousarray(face_off, dtype=np.uint32)
+    fv = np.ascontiguousarray(face_vtx, dtype=np.uint32)
+    q = np.ascontiguousarray(query, dtype=np.float64)
+    return float(L.mco_winding_number(x.ctypes.data, fo.ctypes.data, fv.ctypes.data, len(fo) - 1, q.ctypes.data))
+
+
+def solid_angle(pts, query, use_ref: bool = False) -> float:
+    """calculate_signed_solid_angle of 3 or 4 points (preproc.cpp:1650-1810): the oracle's or the reference's own."""
+    L = ref() if use_ref else lib()
+    names = {(3, False): "mco_solid_angle_tri", (4, False): "mco_solid_angle_quad", (3, True): "ref_solid_angle_tri",
+             (4, True): "ref_solid_angle_quad"}
+    fn = getattr(L, names[(len(pts), use_ref)])
+    fn.argtypes = [c_dp] * (len(pts) + 1)
+    fn.restype = C.c_double
+    arrs = [np.ascontiguousarray(p, dtype=np.float64) for p in list(pts) + [query]]
+    return float(fn(*[a.ctypes.data_as(c_dp) for a in arrs]))
+
+
 def validate(nv: int, face_off: np.ndarray, face_vtx: np.ndarray):
     """The oracle's restatement of the same two passes; returns (n, fccmap, cc_vertex_count, cc_face_count, border_edges)."""
     L = lib()

@@ -28,7 +28,23 @@ extern int find_connected_components(thread_pool& scheduler, std::vector<int>& f
     std::vector<int>& cc_to_vertex_count, std::vector<int>& cc_to_face_count); // source/kernel.cpp:235
 extern bool mesh_is_closed(const hmesh_t& mesh); // source/preproc.cpp:1957
 
+extern double calculate_signed_solid_angle(const vec3_<double>& a, const vec3_<double>& b, const vec3_<double>& c,
+    const vec3_<double>& query, const double multiplier); // source/preproc.cpp:1650
+extern double calculate_signed_solid_angle(const vec3_<double>& a, const vec3_<double>& b, const vec3_<double>& c,
+    const vec3_<double>& d, const vec3_<double>& query, const double multiplier); // source/preproc.cpp:1702
+
 extern "C" {
+
+double ref_solid_angle_tri(const double* a, const double* b, const double* c, const double* q)
+{
+    return calculate_signed_solid_angle(vec3_<double>(a[0], a[1], a[2]), vec3_<double>(b[0], b[1], b[2]), vec3_<double>(c[0], c[1], c[2]),
+        vec3_<double>(q[0], q[1], q[2]), 1.0);
+}
+double ref_solid_angle_quad(const double* a, const double* b, const double* c, const double* d, const double* q)
+{
+    return calculate_signed_solid_angle(vec3_<double>(a[0], a[1], a[2]), vec3_<double>(b[0], b[1], b[2]), vec3_<double>(c[0], c[1], c[2]),
+        vec3_<double>(d[0], d[1], d[2]), vec3_<double>(q[0], q[1], q[2]), 1.0);
+}
 
 // find_connected_components + mesh_is_closed on a mesh given as arrays (the half-edge mesh is built the reference's way:
 // add_vertex / add_face in order).  Returns the number of components, -1 if a face could not be added.

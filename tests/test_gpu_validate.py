@@ -39,3 +39,50 @@ def test_device_validation_at_scale(oracle, gpu_ctx):
     assert got[0] == want[0] and got[4] == want[4] and got[4] > 0
     assert np.array_equal(got[1], want[1]) and np.array_equal(got[2], want[2]) and np.array_equal(got[3], want[3])
     m.free()
+
+
+def test_device_winding_number_equals_oracle(oracle, gpu_ctx):
+    """mcb200_mesh_winding_number vs the oracle's sequential getWindingNumber: same classification (eps 1e-7 in the
+    reference), values within 1e-11 (device atan2 and a different summation order), triangles and quads."""
+    from mcut_b200 import meshgen as mg, stage
+    rng = np.random.default_rng(5)
+    x, f, s = mg.cube_sphere(40, 20.0, rotation=mg.rot_z(0.3), centre=(3.0, -2.0, 1.0))
+    off = np.arange(0, f.size + 1, 3, dtype=np.uint32)
+    m = stage.Mesh(gpu_ctx, x, f, s)
+    for q in [np.array([3.0, -2.0, 1.0]), np.array([60.0, 0.0, 0.0]), *(rng.normal(size=3) * 15.0 for _ in range(20))]:
+        want = oracle.winding_number(x, off, f, q)
+        got = m.winding_number(q)
+        assert abs(got - want) < 1e-11, (q, got, want)
+        assert (abs(1.0 - got) < 1e-7) == (abs(1.0 - want) < 1e-7) and (abs(got) < 1e-7) == (abs(want) < 1e-7)
+    m.free()
+    (sx, sf, ss), _, _ = mg.hello_world()
+    sx = sx.astype(np.float64)
+    qoff = np.concatenate([[0], np.cumsum(ss)]).astype(np.uint32)
+    m = stage.Mesh(gpu_ctx, sx, sf, ss)
+    for q in [sx.mean(axis=0), sx.mean(axis=0) + 100.0, sx[0]]:
+        assert abs(m.winding_number(q) - oracle.winding_number(sx, qoff, sf, q)) < 1e-12
+    m.free()
+
+
+def test_device_winding_number_follows_the_frame(oracle, gpu_ctx):
+    """The mesh is stored in user coordinates; the query is given in the internal frame (x - com) + shift."""
+    from mcut_b200 import meshgen as mg, stage
+    x, f, s = mg.cube_sphere(16, 20.0)
+    off = np.arange(0, f.size + 1, 3, dtype=np.uint32)
+    com, shift = np.array([1.5, -2.0, 0.25]), np.array([30.0, 31.0, 29.5])
+    m = stage.Mesh(gpu_ctx, x, f, s)
+    m.set_frame(com, shift)
+    xi = (x - com) + shift
+    q = (np.array([2.0, 3.0, -4.0]) - com) + shift
+    assert abs(m.winding_number(q) - oracle.winding_number(xi, off, f, q)) < 1e-11 and abs(m.winding_number(q) - 1.0) < 1e-9
+    m.free()
+
+
+def test_device_winding_number_refuses_big_polygons(gpu_ctx):
+    from mcut_b200 import stage
+    xyz = np.array([[0, 0, 0], [1, 0, 0], [1.5, 1, 0], [0.5, 2, 0], [-0.5, 1, 0], [0, 0, 1.0]])
+    faces = np.array([0, 1, 2, 3, 4, 0, 1, 5], dtype=np.uint32)
+    m = stage.Mesh(gpu_ctx, xyz, faces, np.array([5, 3], dtype=np.uint32))
+    with pytest.raises(RuntimeError, match="four vertices"):
+        m.winding_number([0.2, 0.2, 0.2])
+    m.free()

@@ -31,3 +31,29 @@ def test_known_answers(oracle):
     assert n == 1 and border == 4  # two triangles sharing one edge
     n, fcc, cv, cf, border = oracle.validate(*cases["sphere_with_holes"])
     assert n == 1 and border > 0
+
+
+@needs_ref
+def test_solid_angles_equal_reference_bitwise(oracle):
+    """calculate_signed_solid_angle, triangle and quad forms (preproc.cpp:1650-1810): oracle == reference, bit for bit."""
+    rng = np.random.default_rng(11)
+    for i in range(4000):
+        pts = [rng.normal(size=3) * rng.choice([1e-3, 1.0, 50.0]) for _ in range(4)]
+        q = rng.normal(size=3)
+        if i % 40 == 0:
+            q = pts[i % 3].copy()  # query on a vertex: the reference returns 0
+        for k in (3, 4):
+            a, b = oracle.solid_angle(pts[:k], q), oracle.solid_angle(pts[:k], q, use_ref=True)
+            assert np.float64(a).tobytes() == np.float64(b).tobytes(), (i, k)
+
+
+def test_winding_number_known_answers(oracle):
+    from mcut_b200 import meshgen as mg
+    x, f, s = mg.cube_sphere(12, 20.0)
+    off = np.arange(0, f.size + 1, 3, dtype=np.uint32)
+    assert abs(oracle.winding_number(x, off, f, [1.0, 2.0, -3.0]) - 1.0) < 1e-12  # inside (check_and_store..., preproc.cpp:2039)
+    assert abs(oracle.winding_number(x, off, f, [50.0, 2.0, -3.0])) < 1e-12  # outside
+    (sx, sf, ss), _, _ = mg.hello_world()  # the cube of quads
+    qoff = np.concatenate([[0], np.cumsum(ss)]).astype(np.uint32)
+    centre = sx.astype(np.float64).mean(axis=0)
+    assert abs(abs(oracle.winding_number(sx.astype(np.float64), qoff, sf, centre)) - 1.0) < 1e-12
