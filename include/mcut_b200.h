@@ -173,6 +173,11 @@ int mcb200_mesh_winding_number(mcb200_ctx* ctx, mcb200_mesh* mesh, const double 
 /* ---------------------------------------------------------------- (3) narrowphase -------------------------- */
 int mcb200_soup_create(mcb200_ctx* ctx, uint32_t nsf, uint32_t ncf, uint32_t nh, uint32_t ne, const uint32_t* face_vtx,
     const uint32_t* face_edge, const uint32_t* edge_f, mcb200_soup** soup);
+/* Number the polygon soup of two meshes ON THE DEVICE (no host pass over the faces): same ids as mcb200_soup_ids /
+ * the reference's `ps` (first-use edge ids in add_face order, hmesh.cpp:406-651; vertex lists as halfedge targets).  The
+ * meshes' face arrays must be the ones the reference built `ps` from (user order).  `res` receives the error flag: a
+ * non-manifold edge or inconsistent winding is reported by mcb200_result_counts as MCB200_ERR_NON_MANIFOLD. */
+int mcb200_soup_number(mcb200_ctx* ctx, const mcb200_mesh* src, const mcb200_mesh* cut, mcb200_result* res, mcb200_soup** soup);
 /* Same with explicit face sizes (polygon soups; face_sizes == NULL: triangles).  face_sizes[f] for f in [0, nsf + ncf). */
 int mcb200_soup_create_sized(mcb200_ctx* ctx, uint32_t nsf, uint32_t ncf, uint32_t nh, uint32_t ne, const uint32_t* face_vtx,
     const uint32_t* face_edge, const uint32_t* edge_f, const uint32_t* face_sizes, mcb200_soup** soup);

@@ -78,6 +78,7 @@ SYMBOLS = {
     "mcb200_result_set_shard": (C.c_int, [vp, vp, C.c_uint32, C.c_uint32, C.c_uint32]),
     "mcb200_result_set_pair_capacity": (C.c_int, [vp, vp, C.c_uint64]),
     "mcb200_soup_create": (C.c_int, [vp, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, c_u32p, c_u32p, c_u32p, C.POINTER(vp)]),
+    "mcb200_soup_number": (C.c_int, [vp, vp, vp, vp, C.POINTER(vp)]),
     "mcb200_soup_create_sized": (C.c_int, [vp, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, c_u32p, c_u32p, c_u32p, c_u32p,
                                           C.POINTER(vp)]),
     "mcb200_soup_free": (None, [vp, vp]),

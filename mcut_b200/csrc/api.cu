@@ -100,6 +100,15 @@ int mcb200_ctx_create(int device, void* stream, mcb200_ctx** out)
         return (int)e;
     }
     if (const char* e = std::getenv("MCB200_PDL")) ctx->pdl = (e[0] != '0');
+    {
+        // keep freed blocks in the stream-ordered pool instead of handing them back to the driver at every synchronisation:
+        // a dispatch allocates a few hundred MB of build products, and mapping that memory anew costs far more than the stage
+        cudaMemPool_t pool = nullptr;
+        if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess && pool) {
+            unsigned long long keep = ~0ull;
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+        }
+    }
     cudaStreamCreateWithFlags(&ctx->copy, cudaStreamNonBlocking);
     cudaStreamCreateWithPriority(&ctx->bg, cudaStreamNonBlocking, prio_lo);
     cudaEventCreateWithFlags(&ctx->ev_bg, cudaEventDisableTiming);
@@ -555,6 +564,31 @@ int mcb200_soup_create(mcb200_ctx* ctx, uint32_t nsf, uint32_t ncf, uint32_t nh,
         mcb200_soup_free(ctx, s);
         return rc;
     }
+    *out = s;
+    return 0;
+}
+
+int mcb200_soup_number(mcb200_ctx* ctx, const mcb200_mesh* src, const mcb200_mesh* cut, mcb200_result* res, mcb200_soup** out)
+{
+    if (!ctx || !src || !cut || !res || !out) return MCB200_ERR_INVALID;
+    *out = nullptr;
+    MCB_CUDA(ctx, cudaSetDevice(ctx->device));
+    ctx->use_main();
+    MCB_TRY(ctx->reserve(res->counters, sizeof(result_counters_t)));
+    mcb200_soup* s = new mcb200_soup();
+    int rc = soup_number_reserve(ctx, src, cut, s);
+    if (!rc) {
+        result_counters_t* c = res->counters.as<result_counters_t>();
+        fill_list_t fl {};
+        fl.add(&c->soup_error, 2, 0u); // soup_error, soup_ne
+        MCB_LAUNCH(ctx, k_fill, 1, 256, 0, fl);
+        rc = soup_number_device(ctx, src, cut, s, c);
+    }
+    if (rc) {
+        mcb200_soup_free(ctx, s);
+        return rc;
+    }
+    res->h_valid = false;
     *out = s;
     return 0;
 }

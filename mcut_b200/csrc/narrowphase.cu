@@ -355,17 +355,15 @@ __device__ __forceinline__ bool setup_test(const narrow_args_t& a, uint32_t s, u
 }
 
 // Work items: the exact kernel takes queue entries (pair, slot); the filter takes pairs and walks the slots of its pair
-// in a loop (SPLIT, one thread per (pair, slot), is kept for experiments: it was slower, the per-pair loads dominate).
+// in a loop (one thread per (pair, slot) was measured slower: 2.4x the instructions, the per-pair loads dominate).
 template <bool TRI, bool EXACT> __global__ void __launch_bounds__(NBLOCK) k_tests(narrow_args_t a)
 {
     pdl_prologue();
-    constexpr bool SPLIT = false; // measured: 6 short threads per pair cost 2.4x the instructions and 38 us instead of 27
     unsigned long long n_items;
     if (EXACT) {
         n_items = a.counters->n_exact < a.cap_exact ? a.counters->n_exact : a.cap_exact;
     } else {
         n_items = a.counters->n_pairs < a.cap_pairs ? a.counters->n_pairs : a.cap_pairs;
-        if (SPLIT) n_items *= 6ull;
     }
     unsigned n_tests_local = 0, gp = 0;
     for (unsigned long long it = (unsigned long long)blockIdx.x * NBLOCK + threadIdx.x; it < n_items;
@@ -376,9 +374,6 @@ template <bool TRI, bool EXACT> __global__ void __launch_bounds__(NBLOCK) k_test
             const unsigned long long e = a.exact_queue[it];
             pair_index = e >> 8;
             only_slot = (uint32_t)(e & 0xFFu);
-        } else if (SPLIT) {
-            pair_index = it / 6ull;
-            only_slot = (uint32_t)(it - pair_index * 6ull);
         }
         const unsigned long long pr = a.pairs[pair_index];
         const uint32_t s = (uint32_t)(pr >> 32), c = (uint32_t)(pr & 0xFFFFFFFFu);
@@ -386,7 +381,7 @@ template <bool TRI, bool EXACT> __global__ void __launch_bounds__(NBLOCK) k_test
         const uint32_t ns = TRI ? 3u : __ldg(a.face_off + s + 1) - hs;
         const uint32_t hc = TRI ? 3u * (a.nsf + c) : __ldg(a.face_off + a.nsf + c);
         const uint32_t nc = TRI ? 3u : __ldg(a.face_off + a.nsf + c + 1) - hc;
-        if (!EXACT && (!SPLIT || only_slot == 0u)) {
+        if (!EXACT) {
             a.cand_flag[s] = 1;
             a.cand_flag[a.nsf + c] = 1;
         }
@@ -403,7 +398,7 @@ template <bool TRI, bool EXACT> __global__ void __launch_bounds__(NBLOCK) k_test
         load_box(a.cut_bbox + 6 * (size_t)c, cbox);
         const face_view SF { &a, hs, ns }, CF { &a, hc, nc };
         const uint32_t nslots = ns + nc;
-        for (uint32_t slot = (EXACT || SPLIT) ? only_slot : 0u; slot < ((EXACT || SPLIT) ? only_slot + 1u : nslots); ++slot) {
+        for (uint32_t slot = EXACT ? only_slot : 0u; slot < (EXACT ? only_slot + 1u : nslots); ++slot) {
             uint32_t edge, tested_face;
             bool from_src;
             double q[3], r[3];

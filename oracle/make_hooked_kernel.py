@@ -23,6 +23,7 @@ start -= 1  # the opening line of the banner
 end = [i for i, l in enumerate(src) if l.strip() == "// Create edges from the new intersection points"]
 assert len(end) == 1 and end[0] > decl[0], "end marker not found exactly once: %r" % end
 region = open(inc, encoding="utf-8").read().rstrip("\n").split("\n")
-text = ['#include "mcut_hook.h" // mcut_b200 narrowphase hook'] + src[:start] + region + src[end[0]:]
+marker = 'extern "C" { int mcb200_kernel_is_hooked = 1; } // tells the adapter that nobody will read face_bboxes on the host'
+text = ['#include "mcut_hook.h" // mcut_b200 narrowphase hook', marker] + src[:start] + region + src[end[0]:]
 open(out, "w", encoding="utf-8").write("\n".join(text))
 print("kernel_hooked.cpp: replaced reference lines %d..%d (%d lines) by %d lines" % (start + 1, end[0], end[0] - start, len(region)))
