@@ -18,6 +18,7 @@
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
+#include <deque>
 #include <map>
 #include <mutex>
 #include <stdexcept>
@@ -75,6 +76,7 @@ struct last_intersect_t {
     capture_t src_cap, cut_cap;
 };
 thread_local last_intersect_t t_last;
+thread_local std::deque<const void*> t_recent; // keys of the trees this thread built, oldest first
 
 std::mutex g_mutex;
 std::unordered_map<const void*, device_tree_t> g_trees; // key: address of the caller's bvhAABBs vector
@@ -192,6 +194,21 @@ void build_oibvh(thread_pool& /*pool*/, const hmesh_t& mesh, std::vector<bbox_t>
 {
     scope_timer timer("build_oibvh");
     mcb200_ctx* ctx = thread_ctx();
+    {
+        // the caller's vector is being rebuilt (next dispatch / next attempt): release the previous tree FIRST, so that
+        // the new one is carved out of the blocks the memory pool just got back instead of freshly mapped memory
+        std::lock_guard<std::mutex> lk(g_mutex);
+        auto it = g_trees.find(&bvhAABBs);
+        if (it != g_trees.end()) {
+            if (t_last.src == it->second.mesh || t_last.cut == it->second.mesh) { // the hook state refers to it
+                if (t_last.res) mcb200_result_free(t_last.ctx, t_last.res);
+                if (t_last.soup) mcb200_soup_free(t_last.ctx, t_last.soup);
+                t_last = last_intersect_t();
+            }
+            mcb200_mesh_free(it->second.ctx, it->second.mesh);
+            g_trees.erase(it);
+        }
+    }
     device_tree_t t;
     t.ctx = ctx;
     const uint32_t nf = (uint32_t)mesh.number_of_faces();
@@ -252,9 +269,19 @@ void build_oibvh(thread_pool& /*pool*/, const hmesh_t& mesh, std::vector<bbox_t>
     bvhLeafNodeFaces.clear();
 
     std::lock_guard<std::mutex> lk(g_mutex);
-    auto it = g_trees.find(&bvhAABBs);
-    if (it != g_trees.end()) mcb200_mesh_free(it->second.ctx, it->second.mesh); // same caller vector rebuilt
     g_trees[&bvhAABBs] = t;
+    // A dispatch uses two trees.  The caller's vectors usually live at the same addresses from one dispatch to the next
+    // (then the tree was released above); if they do not, trees of this thread beyond the four most recent are released.
+    t_recent.push_back(&bvhAABBs);
+    while (t_recent.size() > 4) {
+        const void* old = t_recent.front();
+        t_recent.pop_front();
+        auto it = g_trees.find(old);
+        if (it == g_trees.end() || old == static_cast<const void*>(&bvhAABBs)) continue;
+        if (it->second.mesh == t_last.src || it->second.mesh == t_last.cut) continue; // still needed by the hook
+        mcb200_mesh_free(it->second.ctx, it->second.mesh);
+        g_trees.erase(it);
+    }
 }
 
 void intersectOIBVHs(std::map<fd_t, std::vector<fd_t>>& ps_face_to_potentially_intersecting_others,
@@ -272,6 +299,10 @@ void intersectOIBVHs(std::map<fd_t, std::vector<fd_t>>& ps_face_to_potentially_i
         c = ic->second;
     }
     mcb200_ctx* ctx = s.ctx; // both trees were built on this API thread's context
+    // the previous dispatch's result and soup go back to the memory pool BEFORE the new ones are carved out of it
+    if (t_last.res) mcb200_result_free(t_last.ctx, t_last.res);
+    if (t_last.soup) mcb200_soup_free(t_last.ctx, t_last.soup);
+    t_last = last_intersect_t();
     mcb200_result* res = nullptr;
     check(ctx, mcb200_result_create(ctx, &res), "result_create");
     check(ctx, mcb200_bvh_intersect(ctx, s.mesh, c.mesh, res), "bvh_intersect");
@@ -289,9 +320,6 @@ void intersectOIBVHs(std::map<fd_t, std::vector<fd_t>>& ps_face_to_potentially_i
         check(ctx, mcb200_result_read_pairs(ctx, res, pairs.data(), pairs.size()), "read_pairs");
     }
     // the pairs stay on the device for the narrowphase hook (mcb200_hook_narrowphase below)
-    if (t_last.res) mcb200_result_free(t_last.ctx, t_last.res);
-    if (t_last.soup) mcb200_soup_free(t_last.ctx, t_last.soup);
-    t_last = last_intersect_t();
     t_last.ctx = ctx;
     t_last.src = s.mesh;
     t_last.cut = c.mesh;
