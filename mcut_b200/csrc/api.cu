@@ -967,6 +967,16 @@ int mcb200_result_counts(mcb200_ctx* ctx, mcb200_result* res, mcb200_counts* out
         out->status = MCB200_STATUS_SUCCESS;
     if (h.soup_error)
         MCB_FAIL(ctx, MCB200_ERR_NON_MANIFOLD, "polygon-soup numbering: an edge is shared by three faces or by two faces wound the same way");
+    if (res->have_narrow && (h.n_records > res->cap_records || h.n_exact > res->cap_exact || (res->logged_tests && h.n_log > res->cap_tests))) {
+        // The narrowphase buffers are sized from the pair capacity (2 records, 6 queue entries per pair); an input that
+        // needs more gets a pair capacity that provides it, and the caller runs the stage again — nothing is dropped silently.
+        size_t need = res->cap_pairs;
+        if (h.n_records > res->cap_records) need = std::max(need, (size_t)h.n_records / 2 + 1024);
+        if (h.n_exact > res->cap_exact || (res->logged_tests && h.n_log > res->cap_tests)) need = std::max(need, res->cap_pairs * 2);
+        res->cap_pairs = need;
+        res->h_valid = false;
+        MCB_FAIL(ctx, MCB200_ERR_CAPACITY, "narrowphase buffer overflow: capacity has been raised, run the stage again");
+    }
     if (h.pair_overflow) {
         // regrow for the caller's retry: the counter kept counting past the capacity, so the needed size is known
         res->cap_pairs = (size_t)h.n_pairs + (size_t)h.n_pairs / 8 + 1024;

@@ -437,9 +437,16 @@ int mcb200_hook_narrowphase(const hmesh_t& ps, int sm_vtx_cnt, int sm_face_count
     }
 
     // ---- device narrowphase on the resident trees / pairs ----
-    const int rc = mcb200_narrowphase(ctx, soup, t_last.src, t_last.cut, t_last.res, 0);
+    int rc = mcb200_narrowphase(ctx, soup, t_last.src, t_last.cut, t_last.res, 0);
     mcb200_counts counts;
-    const int rc2 = rc ? rc : mcb200_result_counts(ctx, t_last.res, &counts);
+    int rc2 = rc ? rc : mcb200_result_counts(ctx, t_last.res, &counts);
+    for (int attempt = 0; rc2 == MCB200_ERR_CAPACITY && attempt < 3; ++attempt) {
+        // a narrowphase buffer was too small for this input: the library has raised the capacities; the pairs are
+        // produced again (their buffer moves when it grows) and the narrowphase repeated
+        rc = mcb200_bvh_intersect(ctx, t_last.src, t_last.cut, t_last.res);
+        if (!rc) rc = mcb200_narrowphase(ctx, soup, t_last.src, t_last.cut, t_last.res, 0);
+        rc2 = rc ? rc : mcb200_result_counts(ctx, t_last.res, &counts);
+    }
     if (rc2) {
         if (own_soup) mcb200_soup_free(ctx, soup);
         check(ctx, rc2, "narrowphase");
