@@ -2,6 +2,8 @@
 import ctypes as C
 import os
 import re
+import subprocess
+import sys
 
 import pytest
 
@@ -57,3 +59,33 @@ def test_product_never_imports_the_oracle():
                 text = open(os.path.join(dirpath, f), errors="ignore").read()
                 for needle in ("pyoracle", "mcut_oracle", "import oracle", "from oracle", "stage_harness", "libref_unit"):
                     assert needle not in text, f"{os.path.join(dirpath, f)} references the oracle ({needle})"
+
+
+# ---- the reference-facing adapter (built only where the reference's headers exist) ----
+SHIM = os.path.join(ROOT, "mcut_b200", "lib", "libmcut_b200_shim.so")
+REF = "/root/reference"
+
+
+@pytest.mark.skipif(not os.path.exists(SHIM), reason="shim not built (needs /root/reference at build time)")
+def test_shim_defines_the_interposed_reference_symbols():
+    """The adapter must DEFINE exactly the symbols it takes over: build_oibvh / intersectOIBVHs (bvh.h:117-133),
+    client_input_arrays_to_hmesh (preproc.cpp:57) and the narrowphase hook the patched kernel calls."""
+    out = subprocess.run(["nm", "-D", "--defined-only", "-C", SHIM], capture_output=True, text=True).stdout
+    for needle in ("build_oibvh(", "intersectOIBVHs(", "client_input_arrays_to_hmesh(", "mcb200_hook_narrowphase("):
+        assert needle in out, needle
+    undefined = subprocess.run(["nm", "-D", "--undefined-only", SHIM], capture_output=True, text=True).stdout
+    assert "mcb200_narrowphase" in undefined and "mcb200_bvh_build" in undefined  # it goes through the C-ABI, nothing else
+
+
+@pytest.mark.skipif(not os.path.exists(os.path.join(REF, "source", "kernel.cpp")), reason="reference sources not present")
+def test_hook_recipe_finds_its_markers(tmp_path):
+    """oracle/make_hooked_kernel.py locates the narrowphase region of dispatch() by markers; the output goes to a scratch
+    directory here (never into the repo) and must contain the hook call and none of the replaced stages."""
+    outp = tmp_path / "kernel_hooked.cpp"
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "oracle", "make_hooked_kernel.py"), REF,
+                        os.path.join(ROOT, "mcut_b200", "csrc", "shim", "kernel_hook_region.inc"), str(outp)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    text = outp.read_text(errors="replace")
+    assert "mcb200_hook_narrowphase(ps, sm_vtx_cnt, sm_face_count" in text and "mcb200_kernel_is_hooked" in text
+    assert 'TIMESTACK_PUSH("Prepare edge-to-face pairs")' not in text and 'TIMESTACK_PUSH("Cull redundant edge-face pairs")' not in text
+    assert "// Create edges from the new intersection points" in text
