@@ -1,11 +1,13 @@
 // mcut_b200/csrc/lbvh.cu — (1) LBVH construction on the device.
 //
 // Replaces build_oibvh() (include/mcut/internal/bvh.h:117-125, source/bvh.cpp:219-636):
-//   K_aabb    face AABBs (+eps enlargement) and the mesh AABB            bvh.cpp:242-368, math.h:866-928
-//   K_morton  30-bit Morton codes, the reference's float formula          bvh.cpp:196-217, :373-433
-//   sort      one-sweep radix sort of (code, face)                        bvh.cpp:437-442 (std::sort there)
-//   K_karras  radix tree over the sorted codes (Karras 2012)              replaces the implicit OIBVH layout :444-493
-//   K_refit   atomic bottom-up AABB refit                                 bvh.cpp:498-635 (one parallel_for per level there)
+//   k_face_bbox    face AABBs (+eps enlargement) and the mesh AABB               bvh.cpp:242-368, math.h:866-928
+//   k_morton       30-bit Morton codes, the reference's float formula;           bvh.cpp:196-217, :373-433
+//                  also the four digit histograms of the sort
+//   radix passes   one-sweep radix sort of (code, face)  (radix_sort.cuh)        bvh.cpp:437-442 (std::sort there)
+//   k_tree         radix tree over the sorted codes (Karras 2012) fused with     replaces the implicit OIBVH layout :444-493
+//                  the box refit of every subtree of <= 32 leaves                and the bottom of bvh.cpp:498-635
+//   k_refit_climb  atomic bottom-up refit of the nodes above those subtrees      bvh.cpp:498-635 (one parallel_for per level there)
 // Only face AABBs, the mesh AABB and the leaf-pair SET escape this stage, and every internal box is the exact
 // min/max union of its leaves, so the tree shape is free: an LBVH yields the same pairs.
 #include "internal.h"
@@ -152,7 +154,7 @@ __global__ void __launch_bounds__(BLOCK) k_morton(const double* __restrict__ fac
     }
 }
 
-// ---- K_karras ---------------------------------------------------------------------------------------------------
+// ---- Karras topology (used by k_tree) ---------------------------------------------------------------------------
 // One thread per internal node (Karras 2012).  A block owns 256 consecutive nodes and stages the sorted codes of a
 // +-512 window in shared memory: the range/split binary searches of almost every node (every range up to 256 leaves,
 // the doubling search overshoots by 2x) stay inside that window, so their dependent probes cost shared-memory latency
@@ -191,7 +193,7 @@ struct code_window {
     }
 };
 
-// ---- K_refit ----------------------------------------------------------------------------------------------------
+// ---- refit helpers ------------------------------------------------------------------------------------------------
 // One thread per leaf carries its box up; the first thread to reach a node parks its box in the node and leaves,
 // the second one merges and continues (atomic arrival counter per internal node).
 __device__ __forceinline__ void store_box(double* dst, const double* b)

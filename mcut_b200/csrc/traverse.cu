@@ -5,7 +5,7 @@
 // closed intervals (math.h:931-941) whatever the trees look like, so the device walks its own LBVHs:
 //
 //   * the mesh with more faces is the QUERY side; its leaves are grouped by the query mesh's OWN tree: a group is a
-//     maximal subtree with at most 32 leaves (listed by lbvh.cu's k_refit).  Such treelets are spatially compact — cutting the Morton
+//     maximal subtree with at most 32 leaves (listed by lbvh.cu's k_tree).  Such treelets are spatially compact — cutting the Morton
 //     order into fixed runs of 32 is not: a run that straddles an octant boundary has a union box spanning the mesh;
 //   * most groups are nowhere near the other mesh.  k_group_filter settles those with ONE THREAD per group: a depth-first
 //     walk of the other tree with the group's union box that stops at the first leaf it reaches ("live") or when the stack
