@@ -307,7 +307,8 @@ __device__ __forceinline__ void log_test(const narrow_args_t& a, uint32_t edge, 
 template <bool TRI>
 __device__ __forceinline__ bool setup_test(const narrow_args_t& a, uint32_t s, uint32_t c, uint32_t slot, uint32_t hs,
     uint32_t ns, uint32_t hc, uint32_t nc, const double (*sv)[3], const double (*cv)[3], const double* sbox,
-    const double* cbox, uint32_t& edge, uint32_t& tested_face, bool& edge_from_src, double* q, double* r)
+    const double* cbox, uint32_t& edge, uint32_t& tested_face, bool& edge_from_src, double* q, double* r,
+    const uint32_t* pre_edge = nullptr, const uint2* pre_ef = nullptr)
 {
     edge_from_src = slot < ns;
     const uint32_t i = edge_from_src ? slot : slot - ns;
@@ -315,8 +316,9 @@ __device__ __forceinline__ bool setup_test(const narrow_args_t& a, uint32_t s, u
     const uint32_t hbase = edge_from_src ? hs : hc;
     const uint32_t own_face = edge_from_src ? s : a.nsf + c;
     tested_face = edge_from_src ? a.nsf + c : s;
-    edge = __ldg(a.face_edge + hbase + i);
-    const uint2 ef = __ldg(reinterpret_cast<const uint2*>(a.edge_f) + edge);
+    // the triangle filter fetches the six edge ids and their face pairs up front (two round trips instead of twelve)
+    edge = pre_edge ? pre_edge[slot] : __ldg(a.face_edge + hbase + i);
+    const uint2 ef = pre_ef ? pre_ef[slot] : __ldg(reinterpret_cast<const uint2*>(a.edge_f) + edge);
     const bool is_h0 = (ef.x == own_face);
     const double* tbox = edge_from_src ? cbox : sbox; // box of the tested face
     if (!is_h0) {
@@ -398,11 +400,25 @@ template <bool TRI, bool EXACT> __global__ void __launch_bounds__(NBLOCK) k_test
         load_box(a.cut_bbox + 6 * (size_t)c, cbox);
         const face_view SF { &a, hs, ns }, CF { &a, hc, nc };
         const uint32_t nslots = ns + nc;
+        uint32_t pre_edge[6];
+        uint2 pre_ef[6];
+        constexpr bool PREFETCH = TRI && !EXACT;
+        if (PREFETCH) {
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                pre_edge[k] = __ldg(a.face_edge + hs + k);
+                pre_edge[3 + k] = __ldg(a.face_edge + hc + k);
+            }
+#pragma unroll
+            for (int k = 0; k < 6; ++k) pre_ef[k] = __ldg(reinterpret_cast<const uint2*>(a.edge_f) + pre_edge[k]);
+        }
         for (uint32_t slot = EXACT ? only_slot : 0u; slot < (EXACT ? only_slot + 1u : nslots); ++slot) {
             uint32_t edge, tested_face;
             bool from_src;
             double q[3], r[3];
-            if (!setup_test<TRI>(a, s, c, slot, hs, ns, hc, nc, sv, cv, sbox, cbox, edge, tested_face, from_src, q, r)) continue;
+            if (!setup_test<TRI>(a, s, c, slot, hs, ns, hc, nc, sv, cv, sbox, cbox, edge, tested_face, from_src, q, r,
+                    PREFETCH ? pre_edge : nullptr, PREFETCH ? pre_ef : nullptr))
+                continue;
             test_out_t o;
             const bool done = from_src ? eval_test<TRI, EXACT>(CF, cv, q, r, o, gp) : eval_test<TRI, EXACT>(SF, sv, q, r, o, gp);
             if (!EXACT) n_tests_local++;
