@@ -221,3 +221,16 @@ def test_resident_source_mesh_across_dispatches(oracle, gpu_ctx):
             rr, gr = ref["records"], got["records"]
             assert beq(gr["edge"], rr["edge"]) and beq(gr["face"], rr["face"]) and beq(gr["point"], rr["point"])
     res.free()
+
+
+def test_disjoint_meshes_give_empty_results(oracle, gpu_ctx):
+    """No AABB overlap at all: zero pairs, zero tests, zero records, status SUCCESS — through both entry points."""
+    from mcut_b200 import meshgen as mg, stage
+    a = mg.cube_sphere(10, 20.0)
+    b = mg.cube_sphere(7, 5.0, centre=(200.0, 0.0, 0.0))
+    flags = mg.MC_DISPATCH_VERTEX_ARRAY_DOUBLE | mg.MC_DISPATCH_ENFORCE_GENERAL_POSITION
+    ref = oracle.intersect_stage(a, b, flags)
+    assert len(ref["pairs"]) == 0 and ref["status"] == 0
+    for got in (stage.intersect_stage(gpu_ctx, a, b, flags, log_tests=True), stage.intersect_stage_host(gpu_ctx, a, b, flags, log_tests=True)):
+        assert got["n_pairs"] == 0 and got["n_records"] == 0 and got["status"] == 0 and len(got["pairs"]) == 0
+        assert len(got["records"]) == 0 and len(got["cand_faces"]) == 0 and len(got["tests"]) == 0
