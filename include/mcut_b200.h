@@ -18,6 +18,11 @@
  *                                                       intersection points, registry), arithmetic of source/math.cpp
  *                                                       :130-287,:391-427,:553-902 and source/shewchuk.c:1611-2410
  *   mcb200_intersect_stage                              the three of them back to back without host round trips
+ *   mcb200_intersect_stage_host                         the same from HOST arrays in one call: uploads pipelined with the builds,
+ *                                                       polygon soup numbered on the device (mcb200_soup_number)
+ *   mcb200_mesh_validate / _read_components             find_connected_components(), source/kernel.cpp:235-364;
+ *                                                       mesh_is_closed(), source/preproc.cpp:1957-1990        
+ *   mcb200_mesh_winding_number                          getWindingNumber(), source/preproc.cpp:1650-1955       
  *
  * Conventions: every function returns 0 on success, a negative MCB200_ERR_* or a positive cudaError_t otherwise;
  * mcb200_last_error() gives the text.  Host arrays are borrowed for the duration of the call only.  One
@@ -43,7 +48,7 @@ enum {
     MCB200_ERR_NO_DEVICE = -1, /* no CUDA device / not an sm_100 part: the product never falls back to the CPU */
     MCB200_ERR_INVALID = -2, /* bad argument (NULL, zero faces, face smaller than a triangle, ...) */
     MCB200_ERR_NON_MANIFOLD = -3, /* mcb200_soup_ids: an edge is used twice in the same direction (hmesh.cpp:612-628) */
-    MCB200_ERR_CAPACITY = -4, /* caller-provided output array too small; required size is returned */
+    MCB200_ERR_CAPACITY = -4, /* an output array or a device buffer was too small; device capacities are raised for a rerun */
     MCB200_ERR_INTERNAL = -5
 };
 
