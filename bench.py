@@ -247,13 +247,13 @@ def algorithmic_bytes(kname: str, src_nv, src_nf, cut_nv, cut_nf, counts, vbytes
         "k_morton": 48 * F + 8 * F,  # box in, code out twice (by face + sort key)
         "onesweep_pass_u32_kv": 16 * F,  # one radix pass: key + value read once, written once
         # codes + leaf boxes (gathered through the sorted order) in; every node inside the <=32-leaf treelets ((31/32)F of
-        # them) written once as a 128-byte record, topology of the rest, parent words, group list out
-        "k_tree<true>": 4 * F + 48 * F + 4 * F + 128 * F * 31 / 32 + 16 * F / 32 + 8 * F + 72 * F / 16,
+        # them) written once as a 64-byte record, topology of the rest, parent words, group list out
+        "k_tree<true>": 4 * F + 48 * F + 4 * F + 64 * F * 31 / 32 + 16 * F / 32 + 8 * F + 40 * F / 16,
         # query-only build (the mesh that is only the traversal's query side): no node records, no parent words
-        "k_tree<false>": 4 * F + 48 * F + 4 * F + 72 * F / 16,
+        "k_tree<false>": 4 * F + 48 * F + 4 * F + 40 * F / 16,
         # the F/32 nodes above the treelets: group box in, node boxes out
-        "k_refit_climb": 64 * F / 16 + 96 * F / 32,
-        "k_traverse": 48.0 * counts["n_node_tests"] + 8.0 * n_pairs,
+        "k_refit_climb": 32 * F / 16 + 48 * F / 32,
+        "k_traverse": 24.0 * counts["n_node_tests"] + 8.0 * n_pairs,
         "onesweep_pass_u64_k": 16.0 * n_pairs,
         "k_tests_filter_tri": 8.0 * n_pairs + 128.0 * n_tests,
         "k_tests_filter_poly": 8.0 * n_pairs + 128.0 * n_tests,

@@ -177,7 +177,7 @@ struct mcb200_mesh {
     dbuf codes; // [nf] u32 Morton code by face (kept for parity reads)
     dbuf sorted_codes; // [nf] u32
     dbuf sorted_faces; // [nf] u32 (leaf -> face)
-    dbuf nodes; // [max(nf-1,1)] bvh_node_t (128 B)
+    dbuf nodes; // [max(nf-1,1)] bvh_node_t (64 B)
     dbuf parent; // [2nf-1] u32 parent of internal node i / leaf (nf-1+j)
     dbuf flags; // [nf-1] u32 refit arrival counters
     dbuf groups; // [nf] uint2 query groups (first leaf, count) + u32 counter after them
@@ -190,25 +190,42 @@ struct mcb200_mesh {
     bool has_nodes = false; // false after a query-only build: groups exist, node records do not
 };
 
-// One LBVH node: both children's boxes live in the parent so one 128-byte line feeds a traversal step.
-struct __align__(128) bvh_node_t {
-    double lbox[6]; // min xyz, max xyz of the left child
-    double rbox[6];
-    uint32_t left, right; // child ids; bit31 set => leaf, low bits = sorted leaf index
+// One LBVH node: both children's boxes live in the parent, so one 64-byte record feeds a traversal step.  The boxes are
+// single precision, rounded OUTWARDS (min down, max up): inner nodes only prune, and a conservative box never prunes a
+// true overlap; the decisive leaf-level test uses the exact double face boxes.  A leaf child carries the FACE id.
+struct __align__(64) bvh_node_t {
+    float lbox[6]; // min xyz, max xyz of the left child
+    float rbox[6];
+    uint32_t left, right; // child ids; bit31 set => leaf, low bits = face id
     uint32_t first, last; // leaf range covered (Karras)
-    uint32_t pad[4];
 };
-static_assert(sizeof(bvh_node_t) == 128, "bvh_node_t must be one 128-byte line");
+static_assert(sizeof(bvh_node_t) == 64, "bvh_node_t must be one 64-byte record");
 
 #define MCB_LEAF_BIT 0x80000000u
 
-// What a group root (a maximal treelet of <= 32 leaves) carries: its union box and its parent word.  Written by the
-// refit, read by the atomic climb and — as the query box of the group — by the traversal.
-struct __align__(64) group_up_t {
-    double box[6];
+// What a group root (a maximal treelet of <= 32 leaves) carries: its union box (conservative, single precision) and the
+// slot of its parent word.  Written by k_tree, read by the atomic climb and — as the query box of the group — by the
+// traversal.
+struct __align__(32) group_up_t {
+    float box[6];
     uint32_t pw;
-    uint32_t pad[3];
+    uint32_t pad;
 };
+static_assert(sizeof(group_up_t) == 32, "group_up_t is one 32-byte sector");
+
+// conservative single-precision copy of a double box
+__device__ __forceinline__ void box_to_float(const double* b, float* f)
+{
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        f[k] = __double2float_rd(b[k]);
+        f[3 + k] = __double2float_ru(b[3 + k]);
+    }
+}
+__device__ __forceinline__ bool overlap6f(const float* a, const float* b)
+{
+    return ((a[0] <= b[3]) & (a[3] >= b[0]) & (a[1] <= b[4]) & (a[4] >= b[1]) & (a[2] <= b[5]) & (a[5] >= b[2])) != 0;
+}
 
 struct mcb200_soup {
     uint32_t nsf = 0, ncf = 0, nh = 0, ne = 0;

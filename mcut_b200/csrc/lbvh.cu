@@ -196,18 +196,18 @@ struct code_window {
 // ---- refit helpers ------------------------------------------------------------------------------------------------
 // One thread per leaf carries its box up; the first thread to reach a node parks its box in the node and leaves,
 // the second one merges and continues (atomic arrival counter per internal node).
-__device__ __forceinline__ void store_box(double* dst, const double* b)
+__device__ __forceinline__ void store_box(float* dst, const float* b) // 24 bytes, 8-byte aligned
 {
-    reinterpret_cast<double2*>(dst)[0] = make_double2(b[0], b[1]);
-    reinterpret_cast<double2*>(dst)[1] = make_double2(b[2], b[3]);
-    reinterpret_cast<double2*>(dst)[2] = make_double2(b[4], b[5]);
+    reinterpret_cast<float2*>(dst)[0] = make_float2(b[0], b[1]);
+    reinterpret_cast<float2*>(dst)[1] = make_float2(b[2], b[3]);
+    reinterpret_cast<float2*>(dst)[2] = make_float2(b[4], b[5]);
 }
-__device__ __forceinline__ void load_box_cg(const double* src, double* b)
+__device__ __forceinline__ void load_box_cg(const float* src, float* b)
 {
     // written by another SM moments ago: read through L2
-    const double2 a = __ldcg(reinterpret_cast<const double2*>(src));
-    const double2 c = __ldcg(reinterpret_cast<const double2*>(src) + 1);
-    const double2 e = __ldcg(reinterpret_cast<const double2*>(src) + 2);
+    const float2 a = __ldcg(reinterpret_cast<const float2*>(src));
+    const float2 c = __ldcg(reinterpret_cast<const float2*>(src) + 1);
+    const float2 e = __ldcg(reinterpret_cast<const float2*>(src) + 2);
     b[0] = a.x;
     b[1] = a.y;
     b[2] = c.x;
@@ -259,14 +259,19 @@ template <bool WINDOW_ONLY> __device__ __forceinline__ node_topology karras_node
     return t;
 }
 
-__device__ __forceinline__ void write_topology(bvh_node_t* nodes, uint32_t* parent, uint32_t nf, uint32_t i, const node_topology& t)
+// `face_of(j)` = face id of sorted leaf j.  A leaf child is recorded by its FACE id (the traversal needs nothing else of
+// it); the parent word of a leaf still lives at its sorted position.
+template <typename FaceOf>
+__device__ __forceinline__ void write_topology(bvh_node_t* nodes, uint32_t* parent, uint32_t nf, uint32_t i, const node_topology& t,
+    FaceOf face_of)
 {
-    const uint32_t left = (t.lo == t.gamma) ? (MCB_LEAF_BIT | (uint32_t)t.gamma) : (uint32_t)t.gamma;
-    const uint32_t right = (t.hi == t.gamma + 1) ? (MCB_LEAF_BIT | (uint32_t)(t.gamma + 1)) : (uint32_t)(t.gamma + 1);
+    const bool lleaf = (t.lo == t.gamma), rleaf = (t.hi == t.gamma + 1);
+    const uint32_t left = lleaf ? (MCB_LEAF_BIT | face_of(t.gamma)) : (uint32_t)t.gamma;
+    const uint32_t right = rleaf ? (MCB_LEAF_BIT | face_of(t.gamma + 1)) : (uint32_t)(t.gamma + 1);
     // parent word of a child: (parent index << 2) | (child is the right one); read by the climb
     const uint32_t pw = i << 2;
-    parent[(left & MCB_LEAF_BIT) ? (nf - 1 + (left & ~MCB_LEAF_BIT)) : left] = pw;
-    parent[(right & MCB_LEAF_BIT) ? (nf - 1 + (right & ~MCB_LEAF_BIT)) : right] = pw | 1u;
+    parent[lleaf ? (nf - 1 + (uint32_t)t.gamma) : (uint32_t)t.gamma] = pw;
+    parent[rleaf ? (nf - 1 + (uint32_t)(t.gamma + 1)) : (uint32_t)(t.gamma + 1)] = pw | 1u;
     if (i == 0) parent[0] = MCB200_NULL;
     *reinterpret_cast<uint4*>(&nodes[i].left) = make_uint4(left, right, (uint32_t)t.lo, (uint32_t)t.hi);
 }
@@ -325,17 +330,20 @@ __global__ void __launch_bounds__(BLOCK) k_tree(const uint32_t* __restrict__ cod
 {
     pdl_prologue();
     __shared__ uint32_t s_win[KWIN];
-    __shared__ double s_box[RWIN][6];
+    __shared__ float s_box[RWIN][6]; // conservative single-precision leaf boxes of the block's leaf window
+    __shared__ uint32_t s_face[RWIN]; // their face ids
     __shared__ unsigned s_warp[BLOCK / 32], s_base;
     if (nf == 1) {
         // a single leaf (e.g. the planar-section triangle): pseudo-root whose right child can never be hit
         if (blockIdx.x == 0 && threadIdx.x == 0) {
-            double b[6];
-            load_face_box(face_bbox, sorted_faces[0], b);
+            double bd[6];
+            load_face_box(face_bbox, sorted_faces[0], bd);
+            float b[6];
+            box_to_float(bd, b);
             store_box(nodes[0].lbox, b);
-            const double e[6] = { DBL_MAX, DBL_MAX, DBL_MAX, -DBL_MAX, -DBL_MAX, -DBL_MAX };
+            const float e[6] = { FLT_MAX, FLT_MAX, FLT_MAX, -FLT_MAX, -FLT_MAX, -FLT_MAX };
             store_box(nodes[0].rbox, e);
-            nodes[0].left = MCB_LEAF_BIT | 0u;
+            nodes[0].left = MCB_LEAF_BIT | sorted_faces[0];
             nodes[0].right = MCB200_NULL;
             nodes[0].first = 0;
             nodes[0].last = 0;
@@ -367,12 +375,12 @@ __global__ void __launch_bounds__(BLOCK) k_tree(const uint32_t* __restrict__ cod
 #pragma unroll
         for (int k = 0; k < KWIN / BLOCK; ++k) s_win[k * BLOCK + threadIdx.x] = cw_reg[k];
         if (have0) {
-#pragma unroll
-            for (int k = 0; k < 6; ++k) s_box[threadIdx.x][k] = b0[k];
+            box_to_float(b0, s_box[threadIdx.x]);
+            s_face[threadIdx.x] = f0;
         }
         if (have1) {
-#pragma unroll
-            for (int k = 0; k < 6; ++k) s_box[BLOCK + threadIdx.x][k] = b1[k];
+            box_to_float(b1, s_box[BLOCK + threadIdx.x]);
+            s_face[BLOCK + threadIdx.x] = f1;
         }
     }
     __syncthreads();
@@ -380,6 +388,11 @@ __global__ void __launch_bounds__(BLOCK) k_tree(const uint32_t* __restrict__ cod
     const int wbase = (int)i0 - RHALO; // leaf j sits in s_box[j - wbase]
     const code_window cw { codes, s_win, cbase, n };
 
+    // face id of sorted leaf j: from the block's window when it is there (every leaf child of a small node is)
+    auto face_of = [&](int j) -> uint32_t {
+        const int r = j - wbase;
+        return ((unsigned)r < (unsigned)RWIN) ? s_face[r] : __ldg(sorted_faces + j);
+    };
     // ---- topology first: node i's range, split and children; is it (or leaf i) the root of a maximal treelet? ----
     bool root0 = false, root1 = false, small = false, deferred = false;
     int lo = 0, hi = 0, gamma = 0;
@@ -387,7 +400,7 @@ __global__ void __launch_bounds__(BLOCK) k_tree(const uint32_t* __restrict__ cod
         const int ii = (int)i;
         const node_topology t = karras_node<true>(cw, ii, deferred);
         if (!deferred) {
-            if (NODES) write_topology(nodes, parent, nf, i, t);
+            if (NODES) write_topology(nodes, parent, nf, i, t, face_of);
             lo = t.lo;
             hi = t.hi;
             gamma = t.gamma;
@@ -415,7 +428,7 @@ __global__ void __launch_bounds__(BLOCK) k_tree(const uint32_t* __restrict__ cod
 
     // ---- boxes of the small nodes straight from the leaf window ----
     if (small && (NODES || root0)) {
-        double box[6], rb[6];
+        float box[6], rb[6];
 #pragma unroll
         for (int k = 0; k < 6; ++k) {
             box[k] = s_box[lo - wbase][k];
@@ -424,14 +437,14 @@ __global__ void __launch_bounds__(BLOCK) k_tree(const uint32_t* __restrict__ cod
         for (int q = lo + 1; q <= gamma; ++q)
 #pragma unroll
             for (int k = 0; k < 3; ++k) {
-                box[k] = ref_min(box[k], s_box[q - wbase][k]);
-                box[3 + k] = ref_max(box[3 + k], s_box[q - wbase][3 + k]);
+                box[k] = fminf(box[k], s_box[q - wbase][k]);
+                box[3 + k] = fmaxf(box[3 + k], s_box[q - wbase][3 + k]);
             }
         for (int q = gamma + 2; q <= hi; ++q)
 #pragma unroll
             for (int k = 0; k < 3; ++k) {
-                rb[k] = ref_min(rb[k], s_box[q - wbase][k]);
-                rb[3 + k] = ref_max(rb[3 + k], s_box[q - wbase][3 + k]);
+                rb[k] = fminf(rb[k], s_box[q - wbase][k]);
+                rb[3 + k] = fmaxf(rb[3 + k], s_box[q - wbase][3 + k]);
             }
         if (NODES) {
             store_box(nodes[i].lbox, box);
@@ -440,8 +453,8 @@ __global__ void __launch_bounds__(BLOCK) k_tree(const uint32_t* __restrict__ cod
         if (root0) {
 #pragma unroll
             for (int k = 0; k < 3; ++k) {
-                box[k] = ref_min(box[k], rb[k]);
-                box[3 + k] = ref_max(box[3 + k], rb[3 + k]);
+                box[k] = fminf(box[k], rb[k]);
+                box[3 + k] = fmaxf(box[3 + k], rb[3 + k]);
             }
             groups[g] = make_uint2((uint32_t)lo, (uint32_t)(hi - lo + 1));
             store_box(group_up[g].box, box);
@@ -451,7 +464,7 @@ __global__ void __launch_bounds__(BLOCK) k_tree(const uint32_t* __restrict__ cod
     }
     if (root1) {
         groups[g] = make_uint2(i, 1u);
-        double lb[6];
+        float lb[6];
 #pragma unroll
         for (int k = 0; k < 6; ++k) lb[k] = s_box[(int)i - wbase][k];
         store_box(group_up[g].box, lb);
@@ -461,7 +474,7 @@ __global__ void __launch_bounds__(BLOCK) k_tree(const uint32_t* __restrict__ cod
     if (NODES && deferred) {
         bool unused = false;
         const node_topology t = karras_node<false>(cw, (int)i, unused);
-        write_topology(nodes, parent, nf, i, t);
+        write_topology(nodes, parent, nf, i, t, face_of);
     }
 }
 
@@ -474,10 +487,10 @@ __global__ void __launch_bounds__(BLOCK) k_refit_climb(bvh_node_t* nodes, const 
         const uint32_t slot = group_up[g].pw;
         if (slot == MCB200_NULL) continue; // the whole tree was one treelet
         uint32_t pw = __ldg(parent + slot);
-        double box[6];
+        float box[6];
         {
-            const double2* in = reinterpret_cast<const double2*>(group_up[g].box);
-            const double2 a = in[0], b = in[1], c = in[2];
+            const float2* in = reinterpret_cast<const float2*>(group_up[g].box);
+            const float2 a = in[0], b = in[1], c = in[2];
             box[0] = a.x; box[1] = a.y; box[2] = b.x; box[3] = b.y; box[4] = c.x; box[5] = c.y;
         }
         for (;;) {
@@ -489,12 +502,12 @@ __global__ void __launch_bounds__(BLOCK) k_refit_climb(bvh_node_t* nodes, const 
             __threadfence();
             const unsigned arrived = atomicAdd(flags + p, 1u);
             if (arrived == 0) break; // sibling subtree not finished yet; its thread will continue from here
-            double sib[6];
+            float sib[6];
             load_box_cg(is_left ? nd->rbox : nd->lbox, sib);
 #pragma unroll
             for (int k = 0; k < 3; ++k) {
-                box[k] = ref_min(box[k], sib[k]);
-                box[3 + k] = ref_max(box[3 + k], sib[3 + k]);
+                box[k] = fminf(box[k], sib[k]);
+                box[3 + k] = fmaxf(box[3 + k], sib[3 + k]);
             }
             if (p == 0u) break; // root merged; the mesh AABB itself comes from K_aabb's reduction
             pw = next_pw;

@@ -61,6 +61,7 @@ struct traverse_args_t {
     // tree side
     const bvh_node_t* t_nodes;
     const uint32_t* t_sorted_faces;
+    const double* t_face_bbox; // exact face boxes of the tree side: the decisive test of a candidate leaf
     uint32_t t_nf;
     int query_is_cut; // emit (tree_face << 32 | query_face) instead
     // sharding of the query leaf range
@@ -91,6 +92,16 @@ __device__ __forceinline__ void drain_candidates(warp_scratch_t& ws, unsigned fi
     bool valid, uint32_t myface, unsigned& nout, unsigned long long& ntests, const traverse_args_t& a)
 {
     const unsigned lt = lanemask_lt();
+    // The tree's node boxes are conservative single-precision hulls; the decisive test uses the exact face boxes, fetched
+    // here for the whole batch with independent loads (one round trip).
+    __syncwarp();
+    for (unsigned k = lane_id(); k < count; k += 32) {
+        const double2* in = reinterpret_cast<const double2*>(a.t_face_bbox + 6 * (size_t)ws.cand_face[first + k]);
+        const double2 x = __ldg(in), y = __ldg(in + 1), z = __ldg(in + 2);
+        double* cb = ws.cand_box[first + k];
+        cb[0] = x.x; cb[1] = x.y; cb[2] = y.x; cb[3] = y.y; cb[4] = z.x; cb[5] = z.y;
+    }
+    __syncwarp();
     auto emit_hits = [&](unsigned k, bool hit, unsigned mask) {
         if (hit) {
             const uint32_t tf = ws.cand_face[k];
@@ -120,6 +131,26 @@ __device__ __forceinline__ void drain_candidates(warp_scratch_t& ws, unsigned fi
     ntests += count;
 }
 
+// one 64-byte node record: four 16-byte loads
+__device__ __forceinline__ void fetch_node(const bvh_node_t* nd, float* lb, float* rb, uint32_t& left, uint32_t& right)
+{
+    const uint4* p = reinterpret_cast<const uint4*>(nd);
+    const uint4 q0 = __ldg(p), q1 = __ldg(p + 1), q2 = __ldg(p + 2), q3 = __ldg(p + 3);
+    lb[0] = __uint_as_float(q0.x); lb[1] = __uint_as_float(q0.y); lb[2] = __uint_as_float(q0.z); lb[3] = __uint_as_float(q0.w);
+    lb[4] = __uint_as_float(q1.x); lb[5] = __uint_as_float(q1.y);
+    rb[0] = __uint_as_float(q1.z); rb[1] = __uint_as_float(q1.w);
+    rb[2] = __uint_as_float(q2.x); rb[3] = __uint_as_float(q2.y); rb[4] = __uint_as_float(q2.z); rb[5] = __uint_as_float(q2.w);
+    left = q3.x;
+    right = q3.y;
+}
+
+__device__ __forceinline__ void load_group_box(const group_up_t* g, float* gbox)
+{
+    const float2* in = reinterpret_cast<const float2*>(g->box);
+    const float2 x = __ldg(in), y = __ldg(in + 1), z = __ldg(in + 2);
+    gbox[0] = x.x; gbox[1] = x.y; gbox[2] = y.x; gbox[3] = y.y; gbox[4] = z.x; gbox[5] = z.y;
+}
+
 constexpr int FBLOCK = 128;
 constexpr int FSTACK = 48; // private depth-first stack; a walk that would outgrow it declares the group live (conservative)
 constexpr int FVISITS = 12; // so does a walk that has not settled after this many nodes: its warp finishes it, 32 nodes a step
@@ -140,30 +171,27 @@ __global__ void __launch_bounds__(FBLOCK) k_group_filter(traverse_args_t a)
             const uint2 grp = __ldg(a.groups + g);
             const bool mine = !(a.shard_nparts > 1 && (grp.x / a.shard_chunk) % a.shard_nparts != a.shard_part);
             if (mine) {
-                double gbox[6];
+                float gbox[6];
+                load_group_box(a.group_box + g, gbox);
+                float troot[6];
                 {
-                    const double2* in = reinterpret_cast<const double2*>(a.group_box[g].box);
-                    const double2 x = __ldg(in), y = __ldg(in + 1), z = __ldg(in + 2);
-                    gbox[0] = x.x; gbox[1] = x.y; gbox[2] = y.x; gbox[3] = y.y; gbox[4] = z.x; gbox[5] = z.y;
-                }
-                double troot[6];
+                    double td[6];
 #pragma unroll
-                for (int k = 0; k < 6; ++k) troot[k] = __ldg(a.t_root + k);
+                    for (int k = 0; k < 6; ++k) td[k] = __ldg(a.t_root + k);
+                    box_to_float(td, troot);
+                }
                 ntests += 1ull;
-                if (overlap6(gbox, troot)) {
+                if (overlap6f(gbox, troot)) {
                     size = 1;
                     stack[0] = 0u;
                     int visits = 0;
                     while (size > 0 && !live) {
                         const uint32_t node = stack[size - 1];
-                        const double2* nd = reinterpret_cast<const double2*>(a.t_nodes + node);
-                        const double2 l0 = __ldg(nd), l1 = __ldg(nd + 1), l2 = __ldg(nd + 2);
-                        const double2 r0 = __ldg(nd + 3), r1 = __ldg(nd + 4), r2 = __ldg(nd + 5);
-                        const uint2 ch = __ldg(reinterpret_cast<const uint2*>(nd + 6));
-                        const double lb[6] = { l0.x, l0.y, l1.x, l1.y, l2.x, l2.y };
-                        const double rb[6] = { r0.x, r0.y, r1.x, r1.y, r2.x, r2.y };
-                        const bool hitL = overlap6(gbox, lb);
-                        const bool hitR = (ch.y != MCB200_NULL) && overlap6(gbox, rb);
+                        float lb[6], rb[6];
+                        uint2 ch;
+                        fetch_node(a.t_nodes + node, lb, rb, ch.x, ch.y);
+                        const bool hitL = overlap6f(gbox, lb);
+                        const bool hitR = (ch.y != MCB200_NULL) && overlap6f(gbox, rb);
                         ntests += 2ull;
                         // live: a leaf is reached (the node stays on the stack: its warp collects the leaves), or the walk is
                         // taking long, or the stack is about to overflow
@@ -222,12 +250,8 @@ __global__ void __launch_bounds__(TBLOCK) k_traverse(traverse_args_t a)
             const uint32_t nstart = __ldg(&lg->count);
             const uint32_t start_node = lane < nstart ? __ldg(&lg->node[lane]) : 0u;
             const uint2 grp = __ldg(a.groups + g);
-            double gbox[6];
-            {
-                const double2* in = reinterpret_cast<const double2*>(a.group_box[g].box);
-                const double2 x = __ldg(in), y = __ldg(in + 1), z = __ldg(in + 2);
-                gbox[0] = x.x; gbox[1] = x.y; gbox[2] = y.x; gbox[3] = y.y; gbox[4] = z.x; gbox[5] = z.y;
-            }
+            float gbox[6];
+            load_group_box(a.group_box + g, gbox);
             const uint32_t q = grp.x + lane;
             const bool valid = lane < grp.y;
             bool have_leaf = false;
@@ -261,19 +285,12 @@ __global__ void __launch_bounds__(TBLOCK) k_traverse(traverse_args_t a)
                 const bool active = lane < take;
                 bool hitL = false, hitR = false;
                 uint32_t left = 0, right = 0;
-                double lb[6], rb[6];
                 if (active) {
                     const uint32_t node = ws.stack[size - 1 - lane];
-                    const double2* nd = reinterpret_cast<const double2*>(a.t_nodes + node);
-                    const double2 l0 = __ldg(nd), l1 = __ldg(nd + 1), l2 = __ldg(nd + 2);
-                    const double2 r0 = __ldg(nd + 3), r1 = __ldg(nd + 4), r2 = __ldg(nd + 5);
-                    const uint2 ch = __ldg(reinterpret_cast<const uint2*>(nd + 6));
-                    lb[0] = l0.x; lb[1] = l0.y; lb[2] = l1.x; lb[3] = l1.y; lb[4] = l2.x; lb[5] = l2.y;
-                    rb[0] = r0.x; rb[1] = r0.y; rb[2] = r1.x; rb[3] = r1.y; rb[4] = r2.x; rb[5] = r2.y;
-                    left = ch.x;
-                    right = ch.y;
-                    hitL = overlap6(gbox, lb);
-                    hitR = (right != MCB200_NULL) && overlap6(gbox, rb);
+                    float lb[6], rb[6];
+                    fetch_node(a.t_nodes + node, lb, rb, left, right);
+                    hitL = overlap6f(gbox, lb);
+                    hitR = (right != MCB200_NULL) && overlap6f(gbox, rb);
                 }
                 __syncwarp();
                 size -= take;
@@ -289,25 +306,15 @@ __global__ void __launch_bounds__(TBLOCK) k_traverse(traverse_args_t a)
                     if (pr) ws.stack[size + __popc(mr & lt)] = right;
                     size += __popc(mr);
                 }
-                // leaf children -> candidate list (box travels with it, no second fetch)
+                // leaf children -> candidate list (the child id IS the face id; its exact box is fetched when the list is drained)
                 {
                     const bool cl = hitL && (left & MCB_LEAF_BIT);
                     const unsigned ml = __ballot_sync(0xffffffffu, cl);
-                    if (cl) {
-                        const unsigned slot = ncand + __popc(ml & lt);
-#pragma unroll
-                        for (int k = 0; k < 6; ++k) ws.cand_box[slot][k] = lb[k];
-                        ws.cand_face[slot] = __ldg(a.t_sorted_faces + (left & ~MCB_LEAF_BIT));
-                    }
+                    if (cl) ws.cand_face[ncand + __popc(ml & lt)] = left & ~MCB_LEAF_BIT;
                     ncand += __popc(ml);
                     const bool cr = hitR && (right & MCB_LEAF_BIT);
                     const unsigned mr = __ballot_sync(0xffffffffu, cr);
-                    if (cr) {
-                        const unsigned slot = ncand + __popc(mr & lt);
-#pragma unroll
-                        for (int k = 0; k < 6; ++k) ws.cand_box[slot][k] = rb[k];
-                        ws.cand_face[slot] = __ldg(a.t_sorted_faces + (right & ~MCB_LEAF_BIT));
-                    }
+                    if (cr) ws.cand_face[ncand + __popc(mr & lt)] = right & ~MCB_LEAF_BIT;
                     ncand += __popc(mr);
                 }
                 __syncwarp();
@@ -400,6 +407,7 @@ int traverse_pairs(mcb200_ctx* ctx, const mcb200_mesh* src, const mcb200_mesh* c
     a.q_nf = q->nf;
     a.t_nodes = t->nodes.as<bvh_node_t>();
     a.t_sorted_faces = t->sorted_faces.as<uint32_t>();
+    a.t_face_bbox = t->face_bbox.as<double>();
     a.t_nf = t->nf;
     a.query_is_cut = query_is_cut ? 1 : 0;
     a.shard_part = res->shard_part;
