@@ -117,6 +117,13 @@ void mcb200_mesh_free(mcb200_ctx* ctx, mcb200_mesh* mesh);
 /* Face AABBs (enlarged by eps when eps > 0), mesh AABB, 30-bit Morton codes of the reference's formula, one-sweep
  * radix sort, Karras tree, atomic bottom-up refit.  Asynchronous on the context's stream. */
 int mcb200_bvh_build(mcb200_ctx* ctx, mcb200_mesh* mesh, double eps);
+/* build_oibvh()'s `face_bboxes` argument is in/out: the function resizes the vector and EXPANDS the boxes it finds there
+ * (bvh.cpp:242-272), and preproc.cpp never clears it between the builds of one mcDispatch (:2453-2461, :2733-2760).  So
+ * on the rebuild that follows a floating-polygon repartition, faces [0, n) start from the box they had (already enlarged
+ * by eps once) and are enlarged again.  Hand the caller's incoming boxes over with this call and the NEXT build of `mesh`
+ * reproduces that: box = union(prior box, box of the face's vertices), then enlarged by eps.  n = 0 clears. */
+int mcb200_mesh_set_prior_face_boxes(mcb200_ctx* ctx, mcb200_mesh* mesh, const double* boxes /* [n*6] min xyz, max xyz */,
+    uint32_t n);
 /* D2H of what build_oibvh() hands back to its caller: face_bboxes [nf*6] (min xyz, max xyz; may be NULL) and the
  * mesh AABB (bvhAABBs[0]).  Synchronises the stream. */
 int mcb200_bvh_read(mcb200_ctx* ctx, const mcb200_mesh* mesh, double* face_bboxes, double root_bbox[6]);

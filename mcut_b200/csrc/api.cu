@@ -425,6 +425,7 @@ void mcb200_mesh_free(mcb200_ctx* ctx, mcb200_mesh* m)
         if (m->d_face_off) cudaFreeAsync(const_cast<uint32_t*>(m->d_face_off), ctx->stream);
     }
     ctx->release(m->face_bbox);
+    ctx->release(m->prior_bbox);
     ctx->release(m->root);
     ctx->release(m->codes);
     ctx->release(m->sorted_codes);
@@ -446,6 +447,22 @@ int mcb200_bvh_build(mcb200_ctx* ctx, mcb200_mesh* m, double eps)
     MCB_CUDA(ctx, cudaSetDevice(ctx->device));
     ctx->use_main();
     return lbvh_build(ctx, m, eps);
+}
+
+int mcb200_mesh_set_prior_face_boxes(mcb200_ctx* ctx, mcb200_mesh* m, const double* boxes, uint32_t n)
+{
+    if (!ctx || !m || (n && !boxes)) return MCB200_ERR_INVALID;
+    MCB_CUDA(ctx, cudaSetDevice(ctx->device));
+    m->n_prior = 0;
+    if (n == 0) return 0;
+    if (n > m->nf) n = m->nf; // build_oibvh resizes the vector to the face count first
+    ctx->use_main();
+    MCB_TRY(ctx->reserve(m->prior_bbox, sizeof(double) * 6 * (size_t)n));
+    // a rare path (one call per repartition retry): a plain blocking copy, visible to whichever lane builds next
+    MCB_CUDA(ctx, cudaMemcpyAsync(m->prior_bbox.p, boxes, sizeof(double) * 6 * (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
+    MCB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    m->n_prior = n;
+    return 0;
 }
 
 int mcb200_bvh_read(mcb200_ctx* ctx, const mcb200_mesh* m, double* face_bboxes, double root_bbox[6])

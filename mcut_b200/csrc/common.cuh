@@ -173,6 +173,8 @@ struct mcb200_mesh {
     bool built = false;
     double eps = 0.0;
     dbuf face_bbox; // [nf][6] double
+    dbuf prior_bbox; // boxes the next build starts from (mcb200_mesh_set_prior_face_boxes), [n_prior][6] double
+    uint32_t n_prior = 0;
     dbuf root; // 6 x u64 (order-preserving encoding) + 6 double (decoded)
     dbuf codes; // [nf] u32 Morton code by face (kept for parity reads)
     dbuf sorted_codes; // [nf] u32

@@ -40,7 +40,8 @@ __device__ __forceinline__ unsigned morton3D(float x, float y, float z)
 template <bool TRI>
 __global__ void __launch_bounds__(BLOCK) k_face_bbox(const void* __restrict__ xyz, frame_t fr,
     const uint32_t* __restrict__ face_vtx, const uint32_t* __restrict__ face_off, uint32_t nf, double eps,
-    double* __restrict__ face_bbox, unsigned long long* __restrict__ root_ordered, unsigned* __restrict__ arrival_flags)
+    double* __restrict__ face_bbox, unsigned long long* __restrict__ root_ordered, unsigned* __restrict__ arrival_flags,
+    const double* __restrict__ prior, uint32_t n_prior)
 {
     pdl_prologue();
     double bmin[3] = { DBL_MAX, DBL_MAX, DBL_MAX }, bmax[3] = { -DBL_MAX, -DBL_MAX, -DBL_MAX };
@@ -55,6 +56,16 @@ __global__ void __launch_bounds__(BLOCK) k_face_bbox(const void* __restrict__ xy
             for (int j = 0; j < 3; ++j) {
                 mx[j] = ref_max(mx[j], p[j]);
                 mn[j] = ref_min(mn[j], p[j]);
+            }
+        }
+        if (f < n_prior) {
+            // build_oibvh() only RESIZES the caller's face_bboxes (bvh.cpp:242) and expands what is there: on the rebuild
+            // after a floating-polygon repartition (preproc.cpp:2733-2760) a face keeps the (enlarged) box it had
+            const double* pb = prior + 6 * (size_t)f;
+#pragma unroll
+            for (int j = 0; j < 3; ++j) {
+                mn[j] = ref_min(__ldg(pb + j), mn[j]);
+                mx[j] = ref_max(__ldg(pb + 3 + j), mx[j]);
             }
         }
         if (eps > 0.0) {
@@ -563,12 +574,15 @@ int lbvh_build(mcb200_ctx* ctx, mcb200_mesh* m, double eps, bool query_only)
 
     const unsigned max_grid = (unsigned)ctx->num_sms * 8u;
     const unsigned grid = div_up(nf, BLOCK) < max_grid ? div_up(nf, BLOCK) : max_grid;
+    const double* prior = m->n_prior ? m->prior_bbox.as<double>() : nullptr;
+    const uint32_t n_prior = m->n_prior < nf ? m->n_prior : nf;
     if (m->is_tri)
         MCB_LAUNCH(ctx, k_face_bbox<true>, grid, BLOCK, 0, m->d_xyz, m->frame, m->d_face_vtx, m->d_face_off, nf, eps,
-            m->face_bbox.as<double>(), root_ord, m->flags.as<unsigned>());
+            m->face_bbox.as<double>(), root_ord, m->flags.as<unsigned>(), prior, n_prior);
     else
         MCB_LAUNCH(ctx, k_face_bbox<false>, grid, BLOCK, 0, m->d_xyz, m->frame, m->d_face_vtx, m->d_face_off, nf, eps,
-            m->face_bbox.as<double>(), root_ord, m->flags.as<unsigned>());
+            m->face_bbox.as<double>(), root_ord, m->flags.as<unsigned>(), prior, n_prior);
+    m->n_prior = 0; // consumed: the boxes are part of face_bbox now
     // (code, face) ascending by code: in = sorted_codes (values implicit 0..nf-1), ping-pong scratch <-> mesh arrays;
     // four passes end in the mesh's own arrays.  The histograms come out of k_morton.
     const rsort::pass_desc pd = rsort::make_passes(0, 32);

@@ -245,6 +245,20 @@ void build_oibvh(thread_pool& /*pool*/, const hmesh_t& mesh, std::vector<bbox_t>
         check(ctx, mcb200_mesh_create(ctx, 0, xyz.data(), nv, idx.data(), sizes.data(), nf, &t.mesh), "mesh_create");
         check(ctx, mcb200_mesh_set_frame(ctx, t.mesh, nullptr, nullptr, nullptr), "set_frame");
     }
+    if (!face_bboxes.empty()) {
+        // `face_bboxes` is in/out in the reference: build_oibvh resizes it and EXPANDS what is there (bvh.cpp:242-272), and
+        // preproc.cpp keeps one vector per mesh for a whole mcDispatch, so the rebuild after a floating-polygon repartition
+        // (preproc.cpp:2733-2760) starts from the previous boxes.  Same here.  (With the hooked kernel the boxes never leave
+        // the device and the vector arrives empty: that rebuild then gets the tight boxes — fewer candidates, same result.)
+        const size_t n = face_bboxes.size() < (size_t)nf ? face_bboxes.size() : (size_t)nf;
+        std::vector<double> prior(6 * n);
+        for (size_t f = 0; f < n; ++f) {
+            const vec3_<double>&lo = face_bboxes[f].minimum(), &hi = face_bboxes[f].maximum();
+            double* b = prior.data() + 6 * f;
+            b[0] = lo.x(), b[1] = lo.y(), b[2] = lo.z(), b[3] = hi.x(), b[4] = hi.y(), b[5] = hi.z();
+        }
+        check(ctx, mcb200_mesh_set_prior_face_boxes(ctx, t.mesh, prior.data(), (uint32_t)n), "set_prior_face_boxes");
+    }
     check(ctx, mcb200_bvh_build(ctx, t.mesh, slightEnlargmentEps), "bvh_build");
 
     // face_bboxes are read by the kernel's cull step only (kernel.cpp:2086-2160); the hooked kernel has no such step and

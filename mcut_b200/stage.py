@@ -166,7 +166,11 @@ class Mesh:
         f = lambda a: None if a is None else _dp(np.ascontiguousarray(a, dtype=np.float64))
         self.ctx.check(self.ctx.L.mcb200_mesh_set_frame(self.ctx.h, self.h, f(com), f(shift), f(perturbation)))
 
-    def build(self, eps: float = 0.0):
+    def build(self, eps: float = 0.0, prior_boxes=None):
+        """`prior_boxes` [n,6]: what the caller's face_bboxes vector held on entry to build_oibvh (in/out there)."""
+        if prior_boxes is not None and len(prior_boxes):
+            pb = np.ascontiguousarray(prior_boxes, dtype=np.float64)
+            self.ctx.check(self.ctx.L.mcb200_mesh_set_prior_face_boxes(self.ctx.h, self.h, _dp(pb), pb.shape[0]))
         self.ctx.check(self.ctx.L.mcb200_bvh_build(self.ctx.h, self.h, float(eps)))
 
     def read_bvh(self, want_boxes: bool = True):
@@ -214,10 +218,20 @@ class Mesh:
 
 
 class Soup:
-    def __init__(self, ctx: Context, src: Mesh, cut: Mesh):
+    def __init__(self, ctx: Context, src: Mesh, cut: Mesh, tables=None):
+        """`tables` = dict(edges [ne,4] = source(h0), target(h0), face(h0), face(h1); face_vtx; face_sizes; face_edge): the
+        caller's own polygon soup (what the reference's `ps` holds) instead of the numbering rules applied to the arrays."""
         self.ctx = ctx
         self.h = C.c_void_p()
-        ctx.check(ctx.L.mcb200_soup_from_meshes(ctx.h, src.h, cut.h, C.byref(self.h)))
+        if tables is None:
+            ctx.check(ctx.L.mcb200_soup_from_meshes(ctx.h, src.h, cut.h, C.byref(self.h)))
+            return
+        u32 = lambda a: np.ascontiguousarray(a, dtype=np.uint32)  # noqa: E731
+        edges = u32(tables["edges"]).reshape(-1, 4)
+        edge_f, fv, fe, fs = u32(edges[:, 2:]), u32(tables["face_vtx"]), u32(tables["face_edge"]), u32(tables["face_sizes"])
+        p = lambda a: a.ctypes.data_as(C.POINTER(C.c_uint32))  # noqa: E731
+        ctx.check(ctx.L.mcb200_soup_create_sized(ctx.h, src.nf, cut.nf, fv.size, edges.shape[0], p(fv), p(fe), p(edge_f), p(fs),
+                                                 C.byref(self.h)))
 
     def free(self):
         if self.h:
@@ -296,22 +310,28 @@ class Result:
 
 
 def intersect_stage(ctx: Context, src, cut, flags: int, gp_constant: float = 1e-4, perturbation=None, log_tests: bool = False,
-                    want_boxes: bool = True) -> Dict[str, object]:
+                    want_boxes: bool = True, params=None, prior_boxes=(None, None), soup_tables=None) -> Dict[str, object]:
     """One kernel invocation's intersect stage on user arrays, through the C-ABI with host buffers.
-    `src`/`cut` = (xyz[V,3] float32|float64, faces_flat uint32, sizes uint32|None)."""
+    `src`/`cut` = (xyz[V,3] float32|float64, faces_flat uint32, sizes uint32|None).
+    `params` = (com, shift, eps) replaces the frame derived from the arrays (zeros: the arrays are internal coordinates);
+    `prior_boxes` = (src, cut) face boxes the two builds start from (see Mesh.build); `soup_tables`: see Soup."""
     sx, sf, ss = src
     cx, cf, cs = cut
-    com, shift, sbb, cbb = vertex_parameters(sx, cx)
-    eps = cut_bbox_eps(cbb, gp_constant, bool(flags & MC_DISPATCH_ENFORCE_GENERAL_POSITION_ABSOLUTE))
+    if params is None:
+        com, shift, sbb, cbb = vertex_parameters(sx, cx)
+        eps = cut_bbox_eps(cbb, gp_constant, bool(flags & MC_DISPATCH_ENFORCE_GENERAL_POSITION_ABSOLUTE))
+    else:
+        com, shift = (np.ascontiguousarray(a, dtype=np.float64) for a in params[:2])
+        eps = float(params[2])
     ms = Mesh(ctx, sx, sf, ss)
     mc = Mesh(ctx, cx, cf, cs)
     ms.set_frame(com, shift)
     mc.set_frame(com, shift)  # boxes/BVH of the cut mesh always come from the unperturbed frame
-    ms.build(0.0)
-    mc.build(eps)
+    ms.build(0.0, prior_boxes[0])
+    mc.build(eps, prior_boxes[1])
     res = Result(ctx)
     ctx.check(ctx.L.mcb200_bvh_intersect(ctx.h, ms.h, mc.h, res.h))
-    soup = Soup(ctx, ms, mc)
+    soup = Soup(ctx, ms, mc, soup_tables)
     if perturbation is not None:
         mc.set_frame(com, shift, perturbation)
     ctx.check(ctx.L.mcb200_narrowphase(ctx.h, soup.h, ms.h, mc.h, res.h, NARROW_LOG_TESTS if log_tests else 0))

@@ -119,6 +119,15 @@ double mco_cut_bbox_eps(const double cut_bbox[6], double gp_constant, int absolu
 void mco_face_bboxes(const double* xyz, const uint32_t* face_off, const uint32_t* face_vtx, uint32_t nf, double eps,
     double* bboxes, double root[6])
 {
+    mco_face_bboxes_prior(xyz, face_off, face_vtx, nf, eps, NULL, 0, bboxes, root);
+}
+
+/* build_oibvh() resizes the caller's face_bboxes and expands what it finds there (bvh.cpp:242, :253-264); preproc.cpp keeps
+ * one such vector per mesh for a whole mcDispatch (:2453, never cleared), so the rebuild after a floating-polygon repartition
+ * (:2733-2760) starts faces [0, n_prior) from the box they had, and enlarges it again. */
+void mco_face_bboxes_prior(const double* xyz, const uint32_t* face_off, const uint32_t* face_vtx, uint32_t nf, double eps,
+    const double* prior, uint32_t n_prior, double* bboxes, double root[6])
+{
     for (int j = 0; j < 3; ++j) {
         root[j] = DBL_MAX;
         root[3 + j] = -DBL_MAX;
@@ -126,8 +135,8 @@ void mco_face_bboxes(const double* xyz, const uint32_t* face_off, const uint32_t
     for (uint32_t f = 0; f < nf; ++f) {
         double* b = bboxes + 6 * (size_t)f;
         for (int j = 0; j < 3; ++j) {
-            b[j] = DBL_MAX;
-            b[3 + j] = -DBL_MAX;
+            b[j] = f < n_prior ? prior[6 * (size_t)f + j] : DBL_MAX;
+            b[3 + j] = f < n_prior ? prior[6 * (size_t)f + 3 + j] : -DBL_MAX;
         }
         for (uint32_t h = face_off[f]; h < face_off[f + 1]; ++h) {
             const double* p = xyz + 3 * (size_t)face_vtx[h];

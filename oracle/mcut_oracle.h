@@ -47,6 +47,8 @@ double mco_cut_bbox_eps(const double cut_bbox[6], double gp_constant, int absolu
 /* ---- a2/a3: face AABBs, mesh AABB, Morton codes (source/bvh.cpp:196-217, :242-433) ---------------- */
 void mco_face_bboxes(const double* xyz, const uint32_t* face_off, const uint32_t* face_vtx, uint32_t nf, double eps,
     double* bboxes /* [nf*6] */, double root[6]);
+void mco_face_bboxes_prior(const double* xyz, const uint32_t* face_off, const uint32_t* face_vtx, uint32_t nf, double eps,
+    const double* prior /* [n_prior*6] or NULL */, uint32_t n_prior, double* bboxes, double root[6]);
 uint32_t mco_morton3D(float x, float y, float z);
 void mco_morton_codes(const double* bboxes, uint32_t nf, const double root[6], uint32_t* codes);
 

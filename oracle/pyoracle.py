@@ -74,6 +74,8 @@ def lib() -> C.CDLL:
         L.mco_cut_bbox_eps.restype = C.c_double
         L.mco_face_bboxes.argtypes = [c_dp, c_u32p, c_u32p, C.c_uint32, C.c_double, c_dp, c_dp]
         L.mco_face_bboxes.restype = None
+        L.mco_face_bboxes_prior.argtypes = [c_dp, c_u32p, c_u32p, C.c_uint32, C.c_double, c_dp, C.c_uint32, c_dp, c_dp]
+        L.mco_face_bboxes_prior.restype = None
         L.mco_morton3D.argtypes = [C.c_float, C.c_float, C.c_float]
         L.mco_morton3D.restype = C.c_uint32
         L.mco_morton_codes.argtypes = [c_dp, C.c_uint32, c_dp, c_u32p]
@@ -247,11 +249,16 @@ def transform_vertices(xyz: np.ndarray, com: np.ndarray, shift: np.ndarray, pert
     return out
 
 
-def face_bboxes(xyz: np.ndarray, off: np.ndarray, vtx: np.ndarray, eps: float):
+def face_bboxes(xyz: np.ndarray, off: np.ndarray, vtx: np.ndarray, eps: float, prior=None):
+    """`prior` [n,6]: the boxes build_oibvh finds in the caller's face_bboxes vector (it only expands them)."""
     nf = off.size - 1
     bb = np.zeros((nf, 6))
     root = np.zeros(6)
-    lib().mco_face_bboxes(dp(xyz), u32p(off), u32p(vtx), nf, float(eps), dp(bb), dp(root))
+    if prior is None or len(prior) == 0:
+        lib().mco_face_bboxes(dp(xyz), u32p(off), u32p(vtx), nf, float(eps), dp(bb), dp(root))
+    else:
+        pb = np.ascontiguousarray(prior, dtype=np.float64)[:nf]
+        lib().mco_face_bboxes_prior(dp(xyz), u32p(off), u32p(vtx), nf, float(eps), dp(pb), pb.shape[0], dp(bb), dp(root))
     return bb, root
 
 
@@ -308,7 +315,25 @@ class SoupHandle:
             pass
 
 
-def narrowphase(soup: SoupHandle, pairs: np.ndarray, src_bb: np.ndarray, cut_bb: np.ndarray, stop_on_gp: bool = True
+class SoupTables:
+    """An mco_soup_t over the caller's own tables (what the reference's `ps` holds): `edges` [ne,4] = source(h0), target(h0),
+    face(h0), face(h1); `face_vtx` = halfedge targets around each face; `face_edge` = edge of each halfedge."""
+
+    def __init__(self, xyz, src_nv, src_nf, edges, face_vtx, face_sizes, face_edge):
+        self.xyz = np.ascontiguousarray(xyz, dtype=np.float64)
+        edges = np.ascontiguousarray(edges, dtype=np.uint32).reshape(-1, 4)
+        self.edge_v = np.ascontiguousarray(edges[:, :2])
+        self.edge_f = np.ascontiguousarray(edges[:, 2:])
+        self.face_vtx = np.ascontiguousarray(face_vtx, dtype=np.uint32)
+        self.face_edge = np.ascontiguousarray(face_edge, dtype=np.uint32)
+        self.face_off = face_offsets(self.face_vtx, np.ascontiguousarray(face_sizes, dtype=np.uint32))
+        self.nv, self.nf, self.ne, self.nh = self.xyz.shape[0], self.face_off.size - 1, edges.shape[0], self.face_vtx.size
+        self.src_nv, self.src_nf = int(src_nv), int(src_nf)
+        self.c = Soup(self.nv, self.nf, self.ne, self.nh, self.src_nv, self.src_nf, dp(self.xyz), u32p(self.face_off),
+                      u32p(self.face_vtx), u32p(self.face_edge), u32p(self.edge_v), u32p(self.edge_f))
+
+
+def narrowphase(soup, pairs: np.ndarray, src_bb: np.ndarray, cut_bb: np.ndarray, stop_on_gp: bool = True
                 ) -> Dict[str, object]:
     out = NarrowOut()
     pairs = np.ascontiguousarray(pairs, dtype=np.uint64)
@@ -341,22 +366,34 @@ def narrowphase(soup: SoupHandle, pairs: np.ndarray, src_bb: np.ndarray, cut_bb:
     return res
 
 
-def intersect_stage(src, cut, flags: int, gp_constant: float = 1e-4, perturbation=None) -> Dict[str, object]:
+def intersect_stage(src, cut, flags: int, gp_constant: float = 1e-4, perturbation=None, params=None,
+                    prior_boxes=(None, None), soup_tables=None) -> Dict[str, object]:
     """The whole intersect stage of one kernel invocation on user arrays (the oracle's mcDispatch slice):
-    re-centring -> face boxes -> candidate pairs -> polygon soup -> narrowphase."""
+    re-centring -> face boxes -> candidate pairs -> polygon soup -> narrowphase.
+    `params` = (com, shift, eps) replaces the frame derived from the arrays (zeros = the arrays already are internal
+    coordinates: what a retry on a repartitioned mesh works with)."""
     from mcut_b200 import meshgen as mg  # flag constants only
     sx, sf, ss = src
     cx, cf, cs = cut
-    com, shift, sbb, cbb = vertex_parameters(sx, cx)
+    if params is None:
+        com, shift, sbb, cbb = vertex_parameters(sx, cx)
+    else:
+        com, shift = (np.ascontiguousarray(a, dtype=np.float64) for a in params[:2])
     sxi = transform_vertices(sx, com, shift)
     cxi0 = transform_vertices(cx, com, shift)
     cxi = cxi0 if perturbation is None else transform_vertices(cx, com, shift, perturbation)
     soff, coff = face_offsets(sf, ss), face_offsets(cf, cs)
-    eps = lib().mco_cut_bbox_eps(dp(cbb), gp_constant, int(bool(flags & mg.MC_DISPATCH_ENFORCE_GENERAL_POSITION_ABSOLUTE)))
-    sb, sroot = face_bboxes(sxi, soff, np.ascontiguousarray(sf), 0.0)
-    cb, croot = face_bboxes(cxi0, coff, np.ascontiguousarray(cf), eps)  # boxes come from the UNperturbed cut mesh
+    if params is None:
+        eps = lib().mco_cut_bbox_eps(dp(cbb), gp_constant, int(bool(flags & mg.MC_DISPATCH_ENFORCE_GENERAL_POSITION_ABSOLUTE)))
+    else:
+        eps = float(params[2])
+    sb, sroot = face_bboxes(sxi, soff, np.ascontiguousarray(sf), 0.0, prior_boxes[0])
+    cb, croot = face_bboxes(cxi0, coff, np.ascontiguousarray(cf), eps, prior_boxes[1])  # from the UNperturbed cut mesh
     pairs, ntests = oibvh_pairs(sb, cb)
-    soup = SoupHandle(sxi, soff, np.ascontiguousarray(sf), cxi, coff, np.ascontiguousarray(cf))
+    if soup_tables is None:
+        soup = SoupHandle(sxi, soff, np.ascontiguousarray(sf), cxi, coff, np.ascontiguousarray(cf))
+    else:
+        soup = SoupTables(np.concatenate([sxi, cxi]), sxi.shape[0], soff.size - 1, **soup_tables)
     nar = narrowphase(soup, pairs, sb, cb)
     nar.update({"com": com, "shift": shift, "eps": eps, "src_bboxes": sb, "cut_bboxes": cb, "src_root": sroot,
                 "cut_root": croot, "pairs": pairs, "bvh_tests": ntests, "soup": soup, "src_xyz": sxi, "cut_xyz": cxi})

@@ -307,6 +307,11 @@ void dispatch(output_t& out, const input_t& in)
             dump_hmesh_arrays(g.out, idx_name("dispatch", k, "cut_"), *in.cut_mesh);
         }
         mcb::put_scalar<int32_t>(g.out, idx_name("dispatch", k, "gp_count"), in.general_position_enforcement_count);
+        // which intersectOIBVHs / build_oibvh results this invocation consumes: the latest ones (a retry after a
+        // floating-polygon repartition rebuilds one tree and traverses again, a perturbation retry does neither)
+        mcb::put_scalar<int32_t>(g.out, idx_name("dispatch", k, "isect_calls"), g.isect_calls);
+        mcb::put_scalar<int32_t>(g.out, idx_name("dispatch", k, "build_calls"), g.build_calls);
+        mcb::put_scalar<int32_t>(g.out, idx_name("dispatch", k, "c2h_calls"), g.c2h_calls);
         mcb::put_scalar<uint64_t>(g.out, idx_name("dispatch", k, "event_offset"), (uint64_t)g.events.size());
     }
     bool aborted = false;

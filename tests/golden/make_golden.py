@@ -14,7 +14,10 @@ Two kinds of files are written next to this script:
                         class) of every kernel invocation (with the perturbation of each retry), intersection points,
                         connected-component summary.
 
-Run:  python tests/golden/make_golden.py
+  corpus/bench_NNN.npz  the same record for pair NNN of the reference's own regression corpus
+                        (tests/meshes/benchmarks/{src,cut}-meshNNN.off, run by tests/source/benchmark.cpp), input arrays included
+
+Run:  python tests/golden/make_golden.py [--corpus-only]
 """
 from __future__ import annotations
 
@@ -36,6 +39,8 @@ from mcut_b200.mcbio import read_mcb, write_mcb  # noqa: E402
 from oracle import pyoracle as po  # noqa: E402
 from ref_events import SoupIndex, decode_dispatch  # noqa: E402
 
+REFERENCE = os.environ.get("MCUT_REFERENCE", "/root/reference")
+CORPUS = range(0, 61)  # benchmark.cpp runs pairs 000..060
 STAGE_CASES = ["hello", "spheres_k8", "uv12", "ico_pair", "cube_cube_axis_aligned", "cube_cube_tris_offset", "patch_vs_sphere",
                "terrain_plane", "float_spheres", "coplanar_rotated", "near_coplanar_tilt"]
 
@@ -238,8 +243,44 @@ def canonical_cc_hash(o):
     return np.array(out, dtype=np.uint64)
 
 
+def read_off(path):
+    """Minimal OFF reader (vertices as float64; faces of any size) -> (xyz, faces, sizes) as tests/cases.py returns them."""
+    with open(path) as fh:
+        tok = [t for line in fh for t in line.split("#")[0].split()]
+    assert tok[0] == "OFF"
+    nv, nf = int(tok[1]), int(tok[2])
+    p = 4
+    xyz = np.array([float(t) for t in tok[p:p + 3 * nv]], dtype=np.float64).reshape(nv, 3)
+    p += 3 * nv
+    faces, sizes = [], []
+    for _ in range(nf):
+        n = int(tok[p])
+        faces.extend(int(t) for t in tok[p + 1:p + 1 + n])
+        sizes.append(n)
+        p += 1 + n
+    return xyz, np.array(faces, dtype=np.uint32), np.array(sizes, dtype=np.uint32)
+
+
 def stage_fixture(name, td):
     src, cut, flags = cases.ALL[name]()
+    return stage_fixture_from(src, cut, flags, td, name)
+
+
+def corpus_fixture(i, td):
+    """Pair i of the reference's own regression corpus (tests/source/benchmark.cpp: src-meshNNN.off x cut-meshNNN.off with
+    VERTEX_ARRAY_DOUBLE | ENFORCE_GENERAL_POSITION).  The input arrays are stored in the fixture: the GPU box has no
+    /root/reference."""
+    d = os.path.join(REFERENCE, "tests", "meshes", "benchmarks")
+    src = read_off(os.path.join(d, f"src-mesh{i:03d}.off"))
+    cut = read_off(os.path.join(d, f"cut-mesh{i:03d}.off"))
+    flags = cases.DBL
+    fx = stage_fixture_from(src, cut, flags, td, f"bench{i:03d}")
+    for tag, m in (("src", src), ("cut", cut)):
+        fx[f"in_{tag}_xyz"], fx[f"in_{tag}_faces"], fx[f"in_{tag}_sizes"] = m
+    return fx
+
+
+def stage_fixture_from(src, cut, flags, td, name):
     o = run_harness(src, cut, flags, td, name)
     fx = {"flags": np.array([flags], dtype=np.uint32), "mcDispatch_result": o["mcDispatch_result"]}
     nc2h = int(o["c2h_calls"][0])
@@ -261,20 +302,58 @@ def stage_fixture(name, td):
     fx["ps_face_edges"] = o["dispatch0_ps_face_edges"]
     nd = int(o["dispatch_calls"][0])
     fx["n_dispatch"] = np.array([nd], dtype=np.int32)
-    # the cut-mesh conversions after the first one carry the perturbation of each retry (preproc.cpp:2650-2665)
-    perts = [o[f"c2h{k}_pert"] for k in range(2, nc2h)]
-    has = [int(o[f"c2h{k}_has_pert"][0]) for k in range(2, nc2h)]
+    # the cut-mesh conversions after the first one carry the perturbation of each retry (preproc.cpp:2650-2665); the one in
+    # effect for an invocation is the latest conversion before it (a floating-polygon retry converts nothing)
+    nv0 = (o["dispatch0_src_xyz"].shape[0], o["dispatch0_cut_xyz"].shape[0])
+    nf0 = (o["dispatch0_src_face_sizes"].size, o["dispatch0_cut_face_sizes"].size)
     for k in range(nd):
         idx = SoupIndex(o[f"dispatch{k}_ps_xyz"], o[f"dispatch{k}_ps_face_sizes"], o[f"dispatch{k}_ps_face_vtx"], o[f"dispatch{k}_ps_edges"])
         ev = o["events"][int(o[f"dispatch{k}_event_offset"][0]):int(o[f"dispatch{k}_event_end"][0])]
         planes, tests = decode_dispatch(ev, idx)
         st = int(o[f"dispatch{k}_status"][0])
         fx[f"d{k}_status_raw"] = np.array([st], dtype=np.int32)
-        pert = np.zeros(3)
-        if k >= 1 and k - 1 < len(perts) and has[k - 1]:
-            pert = perts[k - 1]
+        last_c2h = int(o[f"dispatch{k}_c2h_calls"][0]) - 1
+        has_pert = last_c2h >= 2 and int(o[f"c2h{last_c2h}_has_pert"][0]) != 0
+        pert = o[f"c2h{last_c2h}_pert"] if has_pert else np.zeros(3)
         fx[f"d{k}_pert"] = pert
-        fx[f"d{k}_has_pert"] = np.array([1 if (k >= 1 and k - 1 < len(has) and has[k - 1]) else 0], dtype=np.int32)
+        fx[f"d{k}_has_pert"] = np.array([1 if has_pert else 0], dtype=np.int32)
+        # a retry after the reference's floating-polygon resolution (preproc.cpp, host side, out of scope here) runs on a
+        # REPARTITIONED mesh: record the meshes as that invocation got them (internal coordinates), the boxes and the
+        # candidate pairs in effect, so the stage can be replayed on them with the identity frame
+        nvk = (o[f"dispatch{k}_src_xyz"].shape[0], o[f"dispatch{k}_cut_xyz"].shape[0])
+        nfk = (o[f"dispatch{k}_src_face_sizes"].size, o[f"dispatch{k}_cut_face_sizes"].size)
+        repart = nvk != nv0 or nfk != nf0
+        fx[f"d{k}_repartitioned"] = np.array([1 if repart else 0], dtype=np.int32)
+        if repart:
+            nb = int(o[f"dispatch{k}_build_calls"][0])
+            src_b = [j for j in range(nb) if float(o[f"build{j}_eps"][0]) == 0.0 and o[f"build{j}_face_bboxes"].shape[0] == nfk[0]]
+            cut_b = [j for j in range(nb) if float(o[f"build{j}_eps"][0]) > 0.0 and o[f"build{j}_face_bboxes"].shape[0] == nfk[1]]
+            assert src_b and cut_b, "no build_oibvh call matches the repartitioned meshes"
+            jb, jc = src_b[-1], cut_b[-1]
+            assert np.array_equal(o[f"build{jb}_xyz"], o[f"dispatch{k}_src_xyz"])
+            fx[f"d{k}_src_xyz"] = o[f"dispatch{k}_src_xyz"]
+            fx[f"d{k}_src_faces"], fx[f"d{k}_src_sizes"] = o[f"dispatch{k}_src_face_vtx"], o[f"dispatch{k}_src_face_sizes"]
+            fx[f"d{k}_cut_faces"], fx[f"d{k}_cut_sizes"] = o[f"dispatch{k}_cut_face_vtx"], o[f"dispatch{k}_cut_face_sizes"]
+            fx[f"d{k}_cut_xyz_unperturbed"] = o[f"build{jc}_xyz"]
+            fx[f"d{k}_src_bboxes"], fx[f"d{k}_cut_bboxes"] = o[f"build{jb}_face_bboxes"], o[f"build{jc}_face_bboxes"]
+            fx[f"d{k}_eps"] = o[f"build{jc}_eps"]
+            # the half-edge meshes have a history now (faces removed and added): their polygon soup is not the one the
+            # numbering rules derive from flat arrays, so the reference's own tables are part of the replay input
+            for name in ("ps_edges", "ps_face_vtx", "ps_face_sizes", "ps_face_edges"):
+                fx[f"d{k}_{name}"] = o[f"dispatch{k}_{name}"]
+            # build_oibvh's face_bboxes is in/out and preproc.cpp never clears it: the rebuild starts from the boxes of the
+            # previous build of the same mesh (eps tells the two meshes apart: 0 for the source mesh)
+            all_src = [j for j in range(nb) if float(o[f"build{j}_eps"][0]) == 0.0]
+            all_cut = [j for j in range(nb) if float(o[f"build{j}_eps"][0]) > 0.0]
+            for tag, j, side in (("src", jb, all_src), ("cut", jc, all_cut)):
+                before = [i for i in side if i < j]
+                fx[f"d{k}_{tag}_prior_bboxes"] = o[f"build{before[-1]}_face_bboxes"] if before else np.zeros((0, 6))
+            ji = int(o[f"dispatch{k}_isect_calls"][0]) - 1
+            mek = o[f"isect{ji}_map_entries"]
+            Fsk = int(o[f"isect{ji}_src_face_count"][0])
+            assert Fsk == nfk[0]
+            fwk = mek[mek[:, 0] < Fsk]
+            fx[f"d{k}_pairs"] = np.sort((fwk[:, 0].astype(np.uint64) << np.uint64(32)) | (fwk[:, 1].astype(np.uint64) - np.uint64(Fsk)))
         fx[f"d{k}_cut_xyz"] = o[f"dispatch{k}_cut_xyz"]
         faces = sorted(planes)
         fx[f"d{k}_plane_faces"] = np.array(faces, dtype=np.uint32)
@@ -300,9 +379,23 @@ def stage_fixture(name, td):
     return fx
 
 
+def write_corpus(td):
+    os.makedirs(os.path.join(HERE, "corpus"), exist_ok=True)
+    for i in CORPUS:
+        fx = corpus_fixture(i, td)
+        np.savez_compressed(os.path.join(HERE, "corpus", f"bench_{i:03d}.npz"), **fx)
+        print(f"corpus/bench_{i:03d}.npz: dispatches={int(fx['n_dispatch'][0])} pairs={fx['pairs'].size} "
+              f"tests0={fx['d0_test_edge'].size} result={int(fx['mcDispatch_result'][0])} ccs={fx['cc_type'].size}")
+
+
 def main():
     if not po.ref_available():
         raise SystemExit("oracle/_ref is missing: run `make -C oracle ref` where /root/reference exists")
+    corpus_only = "--corpus-only" in sys.argv
+    if corpus_only:
+        with tempfile.TemporaryDirectory() as td:
+            write_corpus(td)
+        return
     rng = np.random.default_rng(20261017)
     unit = {}
     unit["o3d_pts"], unit["o3d_out"] = gen_orient3d(rng)
@@ -317,6 +410,7 @@ def main():
             np.savez_compressed(os.path.join(HERE, f"stage_{name}.npz"), **fx)
             print(f"stage_{name}.npz: dispatches={int(fx['n_dispatch'][0])} pairs={fx['pairs'].size} "
                   f"tests0={fx['d0_test_edge'].size} result={int(fx['mcDispatch_result'][0])} ccs={fx['cc_type'].size}")
+        write_corpus(td)
 
 
 if __name__ == "__main__":

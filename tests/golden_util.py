@@ -20,6 +20,39 @@ def load_stage(name):
     return np.load(os.path.join(GOLDEN, f"stage_{name}.npz"))
 
 
+def _corpus_ids():
+    d = os.path.join(GOLDEN, "corpus")
+    return sorted(int(f[6:9]) for f in os.listdir(d) if f.startswith("bench_") and f.endswith(".npz")) if os.path.isdir(d) else []
+
+
+CORPUS_CASES = _corpus_ids()  # pairs of the reference's own regression corpus (tests/source/benchmark.cpp)
+
+
+def load_corpus(i):
+    """-> (fixture, src, cut, flags); the input arrays travel inside the fixture (tests/golden/make_golden.py)."""
+    fx = np.load(os.path.join(GOLDEN, "corpus", f"bench_{i:03d}.npz"))
+    src = (fx["in_src_xyz"], fx["in_src_faces"], fx["in_src_sizes"])
+    cut = (fx["in_cut_xyz"], fx["in_cut_faces"], fx["in_cut_sizes"])
+    return fx, src, cut, int(fx["flags"][0])
+
+
+def replay_inputs(fx, k, src, cut):
+    """keyword arguments for intersect_stage that replay kernel invocation k of a fixture: the caller's arrays, or - for a
+    retry on meshes the reference repartitioned (floating-polygon resolution, host side) - the meshes that invocation got,
+    which are internal coordinates already (identity frame, the recorded eps), together with the boxes build_oibvh found in
+    its in/out face_bboxes argument and the reference's own polygon-soup tables (a repartitioned half-edge mesh carries the
+    ids of its history; the reference hands `ps` to the narrowphase, and so does the drop-in hook)."""
+    pert = fx[f"d{k}_pert"] if int(fx[f"d{k}_has_pert"][0]) else None
+    if f"d{k}_repartitioned" not in fx.files or not int(fx[f"d{k}_repartitioned"][0]):
+        return dict(src=src, cut=cut, perturbation=pert)
+    s = (fx[f"d{k}_src_xyz"], fx[f"d{k}_src_faces"], fx[f"d{k}_src_sizes"])
+    c = (fx[f"d{k}_cut_xyz_unperturbed"], fx[f"d{k}_cut_faces"], fx[f"d{k}_cut_sizes"])
+    return dict(src=s, cut=c, perturbation=pert, params=(np.zeros(3), np.zeros(3), float(fx[f"d{k}_eps"][0])),
+                prior_boxes=(fx[f"d{k}_src_prior_bboxes"], fx[f"d{k}_cut_prior_bboxes"]),
+                soup_tables=dict(edges=fx[f"d{k}_ps_edges"], face_vtx=fx[f"d{k}_ps_face_vtx"],
+                                 face_sizes=fx[f"d{k}_ps_face_sizes"], face_edge=fx[f"d{k}_ps_face_edges"]))
+
+
 def load_units():
     return np.load(os.path.join(GOLDEN, "unit_vectors.npz"), allow_pickle=True)
 

@@ -31,33 +31,35 @@ def _key3(p) -> bytes:
 
 
 class SoupIndex:
-    """coordinate -> vertex id, (v,v) -> edge id, vertex tuple -> face id, from the reference's ps dump."""
+    """coordinates -> edge id / face id, from the reference's ps dump.  Keys are coordinate bit patterns (some corpus meshes
+    hold several vertices at one position, so a position does not name a vertex; an edge or a face is still named by the
+    positions of its vertices unless two of them coincide entirely: naming such a one raises)."""
 
     def __init__(self, ps_xyz, ps_face_sizes, ps_face_vtx, ps_edges):
         self.xyz = ps_xyz
-        self.vid: Dict[bytes, int] = {}
-        for i, p in enumerate(ps_xyz):
-            k = _key3(p)
-            if k in self.vid:
-                raise ValueError("duplicate vertex coordinates in polygon soup; cannot resolve ids from coordinates")
-            self.vid[k] = i
-        self.edge: Dict[Tuple[int, int], int] = {}
+        key = [_key3(p) for p in ps_xyz]
+        self.edge: Dict[Tuple[bytes, bytes], int] = {}
         for e, (vs, vt, _f0, _f1) in enumerate(ps_edges):
-            self.edge[(int(vs), int(vt))] = e
-        self.face: Dict[Tuple[int, ...], int] = {}
+            k = (key[int(vs)], key[int(vt)])
+            self.edge[k] = e if k not in self.edge else -1  # ambiguous: an error only if a test names it
+        self.face: Dict[Tuple[bytes, ...], int] = {}
         off = 0
         for f, n in enumerate(ps_face_sizes):
-            self.face[tuple(int(v) for v in ps_face_vtx[off:off + n])] = f
+            k = tuple(key[int(v)] for v in ps_face_vtx[off:off + n])
+            self.face[k] = f if k not in self.face else -1
             off += int(n)
 
-    def v(self, p) -> int:
-        return self.vid[_key3(p)]
-
     def e(self, q, r) -> int:
-        return self.edge[(self.v(q), self.v(r))]  # the reference always passes source(h0), target(h0)
+        e = self.edge[(_key3(q), _key3(r))]  # the reference always passes source(h0), target(h0)
+        if e < 0:
+            raise ValueError("two polygon-soup edges share both end positions; cannot resolve ids from coordinates")
+        return e
 
     def f(self, verts) -> int:
-        return self.face[tuple(self.v(p) for p in verts)]
+        f = self.face[tuple(_key3(p) for p in verts)]
+        if f < 0:
+            raise ValueError("two polygon-soup faces share all vertex positions; cannot resolve ids from coordinates")
+        return f
 
 
 def decode_dispatch(events: np.ndarray, idx: SoupIndex):

@@ -4,23 +4,41 @@ import numpy as np
 import pytest
 
 import cases
-from golden_util import STAGE_CASES, beq, check_tests_against_fixture, load_stage, narrowphase_violation_expected
+from golden_util import (CORPUS_CASES, STAGE_CASES, beq, check_tests_against_fixture, load_corpus, load_stage,
+                         narrowphase_violation_expected, replay_inputs)
 
 pytestmark = pytest.mark.gpu
 
 
 @pytest.mark.parametrize("case", STAGE_CASES)
 def test_cuda_stage_matches_reference_fixture(gpu_ctx, case):
-    from mcut_b200 import stage
     fx = load_stage(case)
     src, cut, flags = cases.ALL[case]()
+    check_cuda_against_fixture(gpu_ctx, fx, src, cut, flags)
+
+
+@pytest.mark.parametrize("pair", CORPUS_CASES)
+def test_cuda_stage_on_reference_regression_corpus(gpu_ctx, pair):
+    """The reference's own regression corpus (tests/source/benchmark.cpp, pairs 000..060), every kernel invocation the
+    reference went through: perturbation retries and the retries on meshes its floating-polygon resolution repartitioned
+    (replayed with the in/out face boxes and the polygon-soup tables that invocation had)."""
+    fx, src, cut, flags = load_corpus(pair)
+    check_cuda_against_fixture(gpu_ctx, fx, src, cut, flags)
+
+
+def check_cuda_against_fixture(gpu_ctx, fx, src, cut, flags):
+    from mcut_b200 import stage
     for k in range(int(fx["n_dispatch"][0])):
-        pert = fx[f"d{k}_pert"] if int(fx[f"d{k}_has_pert"][0]) else None
-        r = stage.intersect_stage(gpu_ctx, src, cut, flags, perturbation=pert, log_tests=True)
-        assert beq(r["com"], fx["com"]) and beq(r["shift"], fx["shift"]) and r["eps"] == float(fx["eps"][0])
-        assert beq(r["src_bboxes"], fx["src_bboxes"]) and beq(r["cut_bboxes"], fx["cut_bboxes"]), "face AABBs"
-        assert beq(r["src_root"], fx["src_root"]) and beq(r["cut_root"], fx["cut_root"]), "mesh AABBs"
-        assert beq(r["pairs"], fx["pairs"]), "candidate pair set"
+        kw = replay_inputs(fx, k, src, cut)
+        r = stage.intersect_stage(gpu_ctx, flags=flags, log_tests=True, **kw)
+        if "params" in kw:
+            assert beq(r["src_bboxes"], fx[f"d{k}_src_bboxes"]) and beq(r["cut_bboxes"], fx[f"d{k}_cut_bboxes"]), "face AABBs"
+            assert beq(r["pairs"], fx[f"d{k}_pairs"]), "candidate pair set of the retry on the repartitioned mesh"
+        else:
+            assert beq(r["com"], fx["com"]) and beq(r["shift"], fx["shift"]) and r["eps"] == float(fx["eps"][0])
+            assert beq(r["src_bboxes"], fx["src_bboxes"]) and beq(r["cut_bboxes"], fx["cut_bboxes"]), "face AABBs"
+            assert beq(r["src_root"], fx["src_root"]) and beq(r["cut_root"], fx["cut_root"]), "mesh AABBs"
+            assert beq(r["pairs"], fx["pairs"]), "candidate pair set"
         assert beq(r["cand_faces"], fx[f"d{k}_plane_faces"])
         assert beq(r["cand_normal"], fx[f"d{k}_plane_normal"]) and beq(r["cand_d"], fx[f"d{k}_plane_d"])
         assert beq(r["cand_maxcomp"], fx[f"d{k}_plane_mc"])

@@ -4,7 +4,8 @@ import numpy as np
 import pytest
 
 import cases
-from golden_util import STAGE_CASES, beq, check_tests_against_fixture, load_stage, narrowphase_violation_expected
+from golden_util import (CORPUS_CASES, STAGE_CASES, beq, check_tests_against_fixture, load_corpus, load_stage,
+                         narrowphase_violation_expected, replay_inputs)
 
 
 @pytest.mark.parametrize("case", STAGE_CASES)
@@ -12,10 +13,29 @@ def test_stage_matches_reference(oracle, case):
     fx = load_stage(case)
     src, cut, flags = cases.ALL[case]()
     assert int(fx["flags"][0]) == flags
+    check_oracle_against_fixture(oracle, fx, src, cut, flags)
+
+
+@pytest.mark.parametrize("pair", CORPUS_CASES)
+def test_reference_regression_corpus(oracle, pair):
+    """src-meshNNN.off x cut-meshNNN.off of the reference's tests/meshes/benchmarks (polygons of up to 12 vertices, open
+    meshes, coincident vertices, general-position retries): every stage output of every kernel invocation."""
+    fx, src, cut, flags = load_corpus(pair)
+    check_oracle_against_fixture(oracle, fx, src, cut, flags)
+
+
+def test_corpus_is_complete():
+    assert CORPUS_CASES == list(range(61)), "tests/source/benchmark.cpp runs pairs 000..060"
+
+
+def check_oracle_against_fixture(oracle, fx, src, cut, flags):
     nd = int(fx["n_dispatch"][0])
     for k in range(nd):
-        pert = fx[f"d{k}_pert"] if int(fx[f"d{k}_has_pert"][0]) else None
-        r = oracle.intersect_stage(src, cut, flags, perturbation=pert)
+        kw = replay_inputs(fx, k, src, cut)
+        r = oracle.intersect_stage(flags=flags, **kw)
+        if "params" in kw:
+            assert beq(r["src_bboxes"], fx[f"d{k}_src_bboxes"]) and beq(r["cut_bboxes"], fx[f"d{k}_cut_bboxes"]), "face AABBs"
+            assert beq(r["pairs"], fx[f"d{k}_pairs"]), "candidate pair set of the retry on the repartitioned mesh"
         if k == 0:
             assert beq(r["com"], fx["com"]) and beq(r["shift"], fx["shift"]) and r["eps"] == float(fx["eps"][0])
             assert beq(r["src_xyz"], fx["src_xyz_internal"]), "re-centred source coordinates"
