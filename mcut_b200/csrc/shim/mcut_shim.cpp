@@ -73,6 +73,7 @@ struct last_intersect_t {
     mcb200_result* res = nullptr;
     mcb200_soup* soup = nullptr; // device-numbered polygon soup of (src, cut), made on first use
     bool from_arrays = false; // both meshes came from captured user arrays: the hook takes the fast path
+    bool src_from_arrays = false, cut_from_arrays = false; // each mesh on its own (a repartition retry rebuilds only one)
     capture_t src_cap, cut_cap;
 };
 thread_local last_intersect_t t_last;
@@ -339,6 +340,8 @@ void intersectOIBVHs(std::map<fd_t, std::vector<fd_t>>& ps_face_to_potentially_i
     t_last.cut = c.mesh;
     t_last.res = res;
     t_last.from_arrays = s.from_arrays && c.from_arrays;
+    t_last.src_from_arrays = s.from_arrays;
+    t_last.cut_from_arrays = c.from_arrays;
     t_last.src_cap = s.cap;
     t_last.cut_cap = c.cap;
 
@@ -378,7 +381,7 @@ int mcb200_hook_narrowphase(const hmesh_t& ps, int sm_vtx_cnt, int sm_face_count
     std::map<pair<fd_t>, std::vector<vd_t>>& cutpath_edge_creation_info,
     std::unordered_map<fd_t, std::vector<vd_t>>& ps_iface_to_ivtx_list, bool& partial_cut_detected, int& bad_face)
 {
-    scope_timer timer(t_last.from_arrays ? "narrowphase hook (arrays)" : "narrowphase hook (generic)");
+    scope_timer timer(t_last.from_arrays ? "narrowphase hook (arrays)" : "narrowphase hook (generic or mixed)");
     (void)ps_face_to_potentially_intersecting_others; // the same pairs are still on the device, in t_last.res
     if (!t_last.res) throw std::runtime_error("mcut_b200: narrowphase hook reached without a device broadphase on this thread");
     mcb200_ctx* ctx = t_last.ctx;
@@ -389,22 +392,34 @@ int mcb200_hook_narrowphase(const hmesh_t& ps, int sm_vtx_cnt, int sm_face_count
     bool own_soup = true;
     // ---- fast path: both meshes live on the device as the user's own arrays ----
     // The cut mesh of THIS attempt is the most recent conversion on this thread (same arrays, new perturbation); three of
-    // its vertices are compared with `ps` bit for bit before it is trusted.
-    bool fast = t_last.from_arrays && t_last.src_cap.nv == nsv && t_last.src_cap.nf == nsf && t_last.cut_cap.nv == ncv
-        && t_last.cut_cap.nf == ncf;
+    // its vertices are compared with `ps` bit for bit before it is trusted.  A device mesh that was made from the user's own arrays keeps them (possibly float) and applies the frame itself; one
+    // that was flattened from a half-edge mesh (a repartitioned mesh, or no capture) holds internal coordinates.
+    const bool src_arrays = t_last.src_from_arrays && t_last.src_cap.nv == nsv && t_last.src_cap.nf == nsf;
+    bool cut_arrays = t_last.cut_from_arrays && t_last.cut_cap.nv == ncv && t_last.cut_cap.nf == ncf;
     capture_t cut_now = t_last.cut_cap;
-    if (fast) {
+    if (cut_arrays) {
         if (t_latest_capture.xyz == t_last.cut_cap.xyz && t_latest_capture.nv == ncv && t_latest_capture.nf == ncf) cut_now = t_latest_capture;
         const uint32_t probe[3] = { 0u, ncv / 2u, ncv - 1u };
         for (uint32_t v : probe) {
             double want[3];
             captured_vertex(cut_now, v, want);
             const vec3& p = ps.vertex(vd_t(nsv + v));
-            if (p.x() != want[0] || p.y() != want[1] || p.z() != want[2]) fast = false;
+            if (p.x() != want[0] || p.y() != want[1] || p.z() != want[2]) cut_arrays = false;
         }
     }
-    if (fast) {
+    if (t_last.cut_from_arrays && !cut_arrays) {
+        // not the conversion this thread saw last: fall back to the coordinates of `ps` (possible when the device copy
+        // holds doubles and the counts agree; the frame becomes the identity)
+        if (t_last.cut_cap.is_float || t_last.cut_cap.nv != ncv || t_last.cut_cap.nf != ncf)
+            throw std::runtime_error("mcut_b200: the cut mesh of this dispatch() is not the one its device tree was built from");
+        check(ctx, mcb200_mesh_set_frame(ctx, t_last.cut, nullptr, nullptr, nullptr), "set_frame(cut, identity)");
+    }
+    if (t_last.src_from_arrays && !src_arrays)
+        throw std::runtime_error("mcut_b200: the source mesh of this dispatch() is not the one its device tree was built from");
+    const bool fast = src_arrays && cut_arrays;
+    if (cut_arrays)
         check(ctx, mcb200_mesh_set_frame(ctx, t_last.cut, cut_now.com, cut_now.shift, cut_now.has_pert ? cut_now.pert : nullptr), "set_frame(cut)");
+    if (fast) {
         if (!t_last.soup) check(ctx, mcb200_soup_number(ctx, t_last.src, t_last.cut, t_last.res, &t_last.soup), "soup_number");
         soup = t_last.soup; // the numbering does not depend on coordinates: one per broadphase, reused by every retry
         own_soup = false;
@@ -412,20 +427,24 @@ int mcb200_hook_narrowphase(const hmesh_t& ps, int sm_vtx_cnt, int sm_face_count
         // ---- generic path: coordinates as dispatch() sees them now (the cut mesh moves on every general-position retry) ----
         {
             std::vector<double> xyz(3 * (size_t)(nsv > ncv ? nsv : ncv));
-            for (uint32_t v = 0; v < nsv; ++v) {
-                const vec3& p = ps.vertex(vd_t(v));
-                xyz[3 * (size_t)v] = p.x();
-                xyz[3 * (size_t)v + 1] = p.y();
-                xyz[3 * (size_t)v + 2] = p.z();
+            if (!src_arrays) {
+                for (uint32_t v = 0; v < nsv; ++v) {
+                    const vec3& p = ps.vertex(vd_t(v));
+                    xyz[3 * (size_t)v] = p.x();
+                    xyz[3 * (size_t)v + 1] = p.y();
+                    xyz[3 * (size_t)v + 2] = p.z();
+                }
+                check(ctx, mcb200_mesh_update_xyz(ctx, t_last.src, xyz.data(), nsv), "mesh_update_xyz(src)");
             }
-            check(ctx, mcb200_mesh_update_xyz(ctx, t_last.src, xyz.data(), nsv), "mesh_update_xyz(src)");
-            for (uint32_t v = 0; v < ncv; ++v) {
-                const vec3& p = ps.vertex(vd_t(nsv + v));
-                xyz[3 * (size_t)v] = p.x();
-                xyz[3 * (size_t)v + 1] = p.y();
-                xyz[3 * (size_t)v + 2] = p.z();
+            if (!cut_arrays) {
+                for (uint32_t v = 0; v < ncv; ++v) {
+                    const vec3& p = ps.vertex(vd_t(nsv + v));
+                    xyz[3 * (size_t)v] = p.x();
+                    xyz[3 * (size_t)v + 1] = p.y();
+                    xyz[3 * (size_t)v + 2] = p.z();
+                }
+                check(ctx, mcb200_mesh_update_xyz(ctx, t_last.cut, xyz.data(), ncv), "mesh_update_xyz(cut)");
             }
-            check(ctx, mcb200_mesh_update_xyz(ctx, t_last.cut, xyz.data(), ncv), "mesh_update_xyz(cut)");
         }
         // ---- the ids of `ps` as flat arrays: vertex and edge of every halfedge slot, faces of h0 / h1 of every edge ----
         std::vector<uint32_t> face_vtx, face_edge, edge_f(2 * (size_t)ne);
@@ -465,6 +484,10 @@ int mcb200_hook_narrowphase(const hmesh_t& ps, int sm_vtx_cnt, int sm_face_count
         if (own_soup) mcb200_soup_free(ctx, soup);
         check(ctx, rc2, "narrowphase");
     }
+    if (getenv("MCB200_HOOK_DEBUG"))
+        std::fprintf(stderr, "[mcut_b200 hook] %s path: ps nv=%u nf=%u ne=%u (src nv=%u nf=%u) pairs=%llu tests=%llu exact=%llu records=%llu cand_faces=%llu status=%d\n",
+            fast ? "arrays" : "generic", nv, nf, ne, nsv, nsf, (unsigned long long)counts.n_pairs, (unsigned long long)counts.n_tests,
+            (unsigned long long)counts.n_exact, (unsigned long long)counts.n_records, (unsigned long long)counts.n_cand_faces, (int)counts.status);
     if (counts.status == MCB200_STATUS_INVALID_SRC_MESH || counts.status == MCB200_STATUS_INVALID_CUT_MESH) {
         bad_face = (int)counts.bad_face;
         if (own_soup) mcb200_soup_free(ctx, soup);

@@ -126,3 +126,122 @@ def test_mcdispatch_with_device_narrowphase_gives_the_same_components(tmp_path, 
     assert a["cc_type"].size == b["cc_type"].size and a["cc_type"].size > 0
     assert sorted(a["cc_nv"].tolist()) == sorted(b["cc_nv"].tolist()) and sorted(a["cc_nf"].tolist()) == sorted(b["cc_nf"].tolist())
     assert canonical_components(a) == canonical_components(b)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# The reference's own regression corpus (tests/source/benchmark.cpp: pairs 000..060) through the live drop-in.  27 of the
+# pairs make the reference repartition a face (floating-polygon resolution) and rebuild a BVH from a half-edge mesh with
+# a history: the shim's generic path (flattened hmesh, in/out face boxes) is what runs there.
+# ---------------------------------------------------------------------------------------------------------------------
+from golden_util import CORPUS_CASES, load_corpus  # noqa: E402
+
+_ref_runs = {}
+
+
+def _reference_run(tmp_path_factory, pair):
+    if pair not in _ref_runs:
+        _, src, cut, flags = load_corpus(pair)
+        _ref_runs[pair] = run_driver(str(tmp_path_factory.mktemp(f"ref{pair:03d}")), "ref", src, cut, flags, [NODUMP])
+    return _ref_runs[pair]
+
+
+@needs_ref
+@pytest.mark.parametrize("pair", CORPUS_CASES)
+def test_corpus_mcdispatch_with_shim_is_bit_identical(tmp_path, tmp_path_factory, pair):
+    fx, src, cut, flags = load_corpus(pair)
+    a = _reference_run(tmp_path_factory, pair)
+    b = run_driver(str(tmp_path), "b200", src, cut, flags, [SHIM, NODUMP])
+    assert int(a["mcDispatch_result"][0]) == int(b["mcDispatch_result"][0]) == int(fx["mcDispatch_result"][0]), b["_stderr"]
+    for k in ("cc_type", "cc_attrs", "cc_nv", "cc_nf", "cc_vertices", "cc_faces", "cc_face_sizes"):
+        assert a[k].shape == b[k].shape and a[k].tobytes() == b[k].tobytes(), k
+    assert sorted(zip(a["cc_type"].tolist(), a["cc_nv"].tolist(), a["cc_nf"].tolist())) == \
+        sorted(zip(fx["cc_type"].tolist(), fx["cc_nv"].tolist(), fx["cc_nf"].tolist())), "the committed fixture"
+
+
+def split_components(out):
+    """[(type, attrs, distinct positions [n,3], faces as tuples of indices into them)] per connected component."""
+    comps = []
+    vo = fo = so = 0
+    allv = np.ascontiguousarray(out["cc_vertices"]).reshape(-1, 3)
+    allf = np.ascontiguousarray(out["cc_faces"]).reshape(-1)
+    alls = np.ascontiguousarray(out["cc_face_sizes"]).reshape(-1)
+    attrs = np.ascontiguousarray(out["cc_attrs"]).reshape(-1, 3)
+    for i in range(out["cc_type"].size):
+        nv, nf = int(out["cc_nv"][i]), int(out["cc_nf"][i])
+        verts = allv[vo:vo + nv]
+        sizes = alls[so:so + nf]
+        nidx = int(sizes.sum())
+        idx = allf[fo:fo + nidx]
+        vo, fo, so = vo + nv, fo + nidx, so + nf
+        uniq, inv = np.unique(verts, axis=0, return_inverse=True)  # sealed fragments may hold a seam vertex twice
+        inv = inv.reshape(-1)
+        faces, o = [], 0
+        for n in sizes.tolist():
+            faces.append(tuple(int(inv[j]) for j in idx[o:o + n]))
+            o += n
+        comps.append((int(out["cc_type"][i]), tuple(int(x) for x in attrs[i]), uniq, faces))
+    return comps
+
+
+def components_equivalent(a, b, tol):
+    """Same components as geometry: every component of `a` has a partner in `b` with the same type and attributes whose
+    distinct vertex positions pair up one to one within `tol` (0: bit-exact) and whose faces are the same cyclic vertex
+    sequences under that pairing."""
+    ca, cb = split_components(a), split_components(b)
+    if len(ca) != len(cb):
+        return False
+    used = set()
+
+    def canon(faces, rename):
+        out = []
+        for f in faces:
+            g = [rename[v] for v in f]
+            k = min(range(len(g)), key=lambda t: g[t:] + g[:t])
+            out.append(tuple(g[k:] + g[:k]))
+        return sorted(out)
+
+    for ty, at, va, fa in ca:
+        ok = False
+        for j, (ty2, at2, vb, fb) in enumerate(cb):
+            if j in used or ty2 != ty or at2 != at or va.shape != vb.shape or len(fa) != len(fb):
+                continue
+            d = np.abs(va[:, None, :] - vb[None, :, :]).max(axis=2)  # tiny meshes: all pairs
+            near = d.argmin(axis=1)
+            if len(set(near.tolist())) != len(near) or not np.all(d[np.arange(len(near)), near] <= tol):
+                continue
+            if canon(fa, {i: int(near[i]) for i in range(len(near))}) == canon(fb, {i: i for i in range(vb.shape[0])}):
+                used.add(j)
+                ok = True
+                break
+        if not ok:
+            return False
+    return True
+
+
+@needs_hooked
+@pytest.mark.parametrize("pair", CORPUS_CASES)
+def test_corpus_mcdispatch_with_device_narrowphase(tmp_path, tmp_path_factory, pair):
+    """Hooked dispatch() on the corpus.  The registry comes back in canonical (edge, face) order; the reference numbers its
+    intersection vertices in the iteration order of a std::unordered_map (kernel.cpp:1779), an accident of the STL.  Where
+    that numbering only names things the components are bit-identical as geometry (all 34 pairs without a repartition and
+    22 of the others).  Where the reference's
+    floating-polygon resolution runs (27 pairs) the numbering decides from which polygon edges the partition segment is
+    computed (preproc.cpp:1000-1126: midpoints of edge pairs, a priority queue with ties): the partition vertices then
+    agree to rounding (pairs 30, 34, 35, 58), or another equally valid segment is chosen (pair 47); the component
+    inventory (count per type and location/patch attributes) is the same in every case."""
+    fx, src, cut, flags = load_corpus(pair)
+    a = _reference_run(tmp_path_factory, pair)
+    b = run_driver(str(tmp_path), "hooked", src, cut, flags, [NODUMP], driver=HOOKED)
+    assert int(a["mcDispatch_result"][0]) == int(b["mcDispatch_result"][0]), b["_stderr"]
+    assert a["cc_type"].size == b["cc_type"].size and a["cc_type"].size > 0
+    inventory = lambda o: sorted(zip(o["cc_type"].tolist(), map(tuple, np.asarray(o["cc_attrs"]).reshape(-1, 3).tolist())))  # noqa: E731
+    assert inventory(a) == inventory(b)
+    repartitioned = any(int(fx[f"d{k}_repartitioned"][0]) for k in range(int(fx["n_dispatch"][0])))
+    if not repartitioned:
+        assert components_equivalent(a, b, 0.0)
+    elif pair not in OTHER_PARTITION_SEGMENT:
+        assert components_equivalent(a, b, 1e-9)
+
+
+# repartition pairs where the hooked run picks another (equally valid) partition segment than the reference's numbering
+OTHER_PARTITION_SEGMENT = {47}

@@ -156,6 +156,24 @@ def test_device_soup_numbering_equals_host_numbering(gpu_ctx, case):
     assert beq(gef, ef.reshape(-1, 2)), "faces of h0 / h1 of every edge"
 
 
+def test_device_soup_numbering_on_the_reference_corpus(gpu_ctx):
+    """The same on the 61 pairs of the reference's regression corpus (polygons, open meshes), against the `ps` tables the
+    reference itself built (tests/golden/corpus), and the records of the host-array call against its intersection points."""
+    from golden_util import CORPUS_CASES, load_corpus, narrowphase_violation_expected
+    from mcut_b200 import stage
+    for pair in CORPUS_CASES:
+        fx, src, cut, flags = load_corpus(pair)
+        r = stage.intersect_stage_host(gpu_ctx, src, cut, flags)
+        gfv, gfe, gef = stage.staged_soup(gpu_ctx)
+        assert beq(gfv, fx["ps_face_vtx"]), f"pair {pair}: ps.get_vertices_around_face order"
+        assert beq(gfe, fx["ps_face_edges"]), f"pair {pair}: edge id of every halfedge"
+        assert beq(gef, np.ascontiguousarray(fx["ps_edges"][:, 2:])), f"pair {pair}: faces of h0 / h1 of every edge"
+        if not narrowphase_violation_expected(fx, 0) and "d0_ipoints_sorted" in fx.files:
+            pts = np.ascontiguousarray(r["records"]["point"]).reshape(-1, 3)
+            pts = pts[np.lexsort((pts[:, 2], pts[:, 1], pts[:, 0]))] if len(pts) else pts
+            assert beq(pts, fx["d0_ipoints_sorted"]), f"pair {pair}: intersection points"
+
+
 def test_device_soup_numbering_reports_bad_topology(gpu_ctx):
     from mcut_b200 import stage
     src, cut, flags = cases.ALL["hello"]()
