@@ -135,22 +135,43 @@ def test_mcdispatch_with_device_narrowphase_gives_the_same_components(tmp_path, 
 # ---------------------------------------------------------------------------------------------------------------------
 from golden_util import CORPUS_CASES, load_corpus  # noqa: E402
 
-_ref_runs = {}
+_corpus_runs = {}
 
 
-def _reference_run(tmp_path_factory, pair):
-    if pair not in _ref_runs:
-        _, src, cut, flags = load_corpus(pair)
-        _ref_runs[pair] = run_driver(str(tmp_path_factory.mktemp(f"ref{pair:03d}")), "ref", src, cut, flags, [NODUMP])
-    return _ref_runs[pair]
+def _corpus_run(tmp_path_factory, mode, pair):
+    """One driver process per pair and mode ("ref", "shim", "hooked").  A process spends a second or two creating its CUDA
+    context, so the first request of a mode launches ALL its pairs eight at a time; the tests then look their result up."""
+    if mode not in _corpus_runs:
+        from concurrent.futures import ThreadPoolExecutor
+        base = str(tmp_path_factory.mktemp(f"corpus_{mode}"))
+
+        def one(p):
+            _, src, cut, flags = load_corpus(p)
+            d = os.path.join(base, f"{p:03d}")
+            os.makedirs(d, exist_ok=True)
+            try:
+                if mode == "ref":
+                    return run_driver(d, "ref", src, cut, flags, [NODUMP])
+                if mode == "shim":
+                    return run_driver(d, "b200", src, cut, flags, [SHIM, NODUMP])
+                return run_driver(d, "hooked", src, cut, flags, [NODUMP], driver=HOOKED)
+            except BaseException as e:  # surfaces in the test of that pair
+                return e
+
+        with ThreadPoolExecutor(max_workers=8) as ex:
+            _corpus_runs[mode] = dict(zip(CORPUS_CASES, ex.map(one, CORPUS_CASES)))
+    r = _corpus_runs[mode][pair]
+    if isinstance(r, BaseException):
+        raise r
+    return r
 
 
 @needs_ref
 @pytest.mark.parametrize("pair", CORPUS_CASES)
-def test_corpus_mcdispatch_with_shim_is_bit_identical(tmp_path, tmp_path_factory, pair):
+def test_corpus_mcdispatch_with_shim_is_bit_identical(tmp_path_factory, pair):
     fx, src, cut, flags = load_corpus(pair)
-    a = _reference_run(tmp_path_factory, pair)
-    b = run_driver(str(tmp_path), "b200", src, cut, flags, [SHIM, NODUMP])
+    a = _corpus_run(tmp_path_factory, "ref", pair)
+    b = _corpus_run(tmp_path_factory, "shim", pair)
     assert int(a["mcDispatch_result"][0]) == int(b["mcDispatch_result"][0]) == int(fx["mcDispatch_result"][0]), b["_stderr"]
     for k in ("cc_type", "cc_attrs", "cc_nv", "cc_nf", "cc_vertices", "cc_faces", "cc_face_sizes"):
         assert a[k].shape == b[k].shape and a[k].tobytes() == b[k].tobytes(), k
@@ -220,7 +241,7 @@ def components_equivalent(a, b, tol):
 
 @needs_hooked
 @pytest.mark.parametrize("pair", CORPUS_CASES)
-def test_corpus_mcdispatch_with_device_narrowphase(tmp_path, tmp_path_factory, pair):
+def test_corpus_mcdispatch_with_device_narrowphase(tmp_path_factory, pair):
     """Hooked dispatch() on the corpus.  The registry comes back in canonical (edge, face) order; the reference numbers its
     intersection vertices in the iteration order of a std::unordered_map (kernel.cpp:1779), an accident of the STL.  Where
     that numbering only names things the components are bit-identical as geometry (all 34 pairs without a repartition and
@@ -230,8 +251,8 @@ def test_corpus_mcdispatch_with_device_narrowphase(tmp_path, tmp_path_factory, p
     agree to rounding (pairs 30, 34, 35, 58), or another equally valid segment is chosen (pair 47); the component
     inventory (count per type and location/patch attributes) is the same in every case."""
     fx, src, cut, flags = load_corpus(pair)
-    a = _reference_run(tmp_path_factory, pair)
-    b = run_driver(str(tmp_path), "hooked", src, cut, flags, [NODUMP], driver=HOOKED)
+    a = _corpus_run(tmp_path_factory, "ref", pair)
+    b = _corpus_run(tmp_path_factory, "hooked", pair)
     assert int(a["mcDispatch_result"][0]) == int(b["mcDispatch_result"][0]), b["_stderr"]
     assert a["cc_type"].size == b["cc_type"].size and a["cc_type"].size > 0
     inventory = lambda o: sorted(zip(o["cc_type"].tolist(), map(tuple, np.asarray(o["cc_attrs"]).reshape(-1, 3).tolist())))  # noqa: E731
