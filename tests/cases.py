@@ -103,6 +103,36 @@ def float_spheres():
         mg.MC_DISPATCH_VERTEX_ARRAY_FLOAT | mg.MC_DISPATCH_ENFORCE_GENERAL_POSITION)
 
 
+# ---- the reference's known-answer inputs for the general-position classification (tests/source/degenerateInput.cpp:58-144:
+# float arrays, no general-position enforcement, mcDispatch must answer MC_INVALID_OPERATION) ----
+_T3 = np.array([0, 1, 2], dtype=np.uint32)
+_S3 = np.array([3], dtype=np.uint32)
+
+
+def degenerate_edge_edge():
+    """degenerateInput.cpp:58-82: one intersection point would come from two edges crossing."""
+    s = np.array([[0, 0, 0], [3, 0, 0], [0, 3, 0]], dtype=np.float32)
+    c = np.array([[0, 2, -1], [3, 2, -1], [0, 2, 2]], dtype=np.float32)
+    return (s, _T3, _S3), (c, _T3, _S3), mg.MC_DISPATCH_VERTEX_ARRAY_FLOAT
+
+
+def degenerate_face_vertex():
+    """degenerateInput.cpp:87-112: a cut-mesh vertex lies on the source triangle."""
+    s = np.array([[0, 0, 0], [3, 0, 0], [0, 3, 0]], dtype=np.float32)
+    c = np.array([[1, 1, -3], [3, 1, -3], [1, 1, 0]], dtype=np.float32)
+    return (s, _T3, _S3), (c, _T3, _S3), mg.MC_DISPATCH_VERTEX_ARRAY_FLOAT
+
+
+def degenerate_zero_area():
+    """degenerateInput.cpp:117-144.  The test hands DOUBLE arrays to MC_DISPATCH_VERTEX_ARRAY_FLOAT: the library reads the
+    first 12 floats of each buffer, i.e. the two halves of each double; that accident is part of the known answer."""
+    s = np.array([[-1, -1, 0], [1, -1, 0], [1, 1, 0], [-1, -1, 0]], dtype=np.float64).view(np.float32).reshape(-1, 3)[:4].copy()
+    c = np.array([[-1, 0, 1], [2, 0, 1], [2, 0, -1], [-1, 0, -1]], dtype=np.float64).view(np.float32).reshape(-1, 3)[:4].copy()
+    sf = np.array([0, 1, 2, 0, 2, 3], dtype=np.uint32)
+    return (s, sf, np.array([3, 3], dtype=np.uint32)), (c, np.array([0, 1, 2, 3], dtype=np.uint32), np.array([4], dtype=np.uint32)), \
+        mg.MC_DISPATCH_VERTEX_ARRAY_FLOAT
+
+
 ALL = {
     "hello": hello,
     "spheres_k8": spheres_k8,
@@ -118,4 +148,7 @@ ALL = {
     "float_spheres": float_spheres,
     "coplanar_rotated": coplanar_rotated,
     "near_coplanar_tilt": near_coplanar_tilt,
+    "degenerate_edge_edge": degenerate_edge_edge,
+    "degenerate_face_vertex": degenerate_face_vertex,
+    "degenerate_zero_area": degenerate_zero_area,
 }

@@ -17,7 +17,7 @@ Two kinds of files are written next to this script:
   corpus/bench_NNN.npz  the same record for pair NNN of the reference's own regression corpus
                         (tests/meshes/benchmarks/{src,cut}-meshNNN.off, run by tests/source/benchmark.cpp), input arrays included
 
-Run:  python tests/golden/make_golden.py [--corpus-only]
+Run:  python tests/golden/make_golden.py [--corpus-only | --only=case,case]
 """
 from __future__ import annotations
 
@@ -42,7 +42,8 @@ from ref_events import SoupIndex, decode_dispatch  # noqa: E402
 REFERENCE = os.environ.get("MCUT_REFERENCE", "/root/reference")
 CORPUS = range(0, 61)  # benchmark.cpp runs pairs 000..060
 STAGE_CASES = ["hello", "spheres_k8", "uv12", "ico_pair", "cube_cube_axis_aligned", "cube_cube_tris_offset", "patch_vs_sphere",
-               "terrain_plane", "float_spheres", "coplanar_rotated", "near_coplanar_tilt"]
+               "terrain_plane", "float_spheres", "coplanar_rotated", "near_coplanar_tilt", "degenerate_edge_edge",
+               "degenerate_face_vertex", "degenerate_zero_area"]
 
 
 def dp(a):
@@ -395,6 +396,12 @@ def main():
     if corpus_only:
         with tempfile.TemporaryDirectory() as td:
             write_corpus(td)
+        return
+    only = [a.split("=", 1)[1].split(",") for a in sys.argv if a.startswith("--only=")]
+    if only:
+        with tempfile.TemporaryDirectory() as td:
+            for name in only[0]:
+                np.savez_compressed(os.path.join(HERE, f"stage_{name}.npz"), **stage_fixture(name, td))
         return
     rng = np.random.default_rng(20261017)
     unit = {}

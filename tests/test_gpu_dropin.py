@@ -266,3 +266,15 @@ def test_corpus_mcdispatch_with_device_narrowphase(tmp_path_factory, pair):
 
 # repartition pairs where the hooked run picks another (equally valid) partition segment than the reference's numbering
 OTHER_PARTITION_SEGMENT = {47}
+
+
+@needs_hooked
+@pytest.mark.parametrize("case", ["degenerate_edge_edge", "degenerate_face_vertex", "degenerate_zero_area"])
+def test_degenerate_inputs_are_rejected_like_the_reference(tmp_path, case):
+    """tests/source/degenerateInput.cpp:58-144: float input, no general-position enforcement -> MC_INVALID_OPERATION (-2),
+    from the narrowphase's general-position classification (edge/edge, vertex on face) or its degenerate-face rule."""
+    src, cut, flags = cases.ALL[case]()
+    a = run_driver(str(tmp_path), "ref", src, cut, flags, [NODUMP])
+    b = run_driver(str(tmp_path), "b200", src, cut, flags, [SHIM, NODUMP])
+    c = run_driver(str(tmp_path), "hooked", src, cut, flags, [NODUMP], driver=HOOKED)
+    assert int(a["mcDispatch_result"][0]) == int(b["mcDispatch_result"][0]) == int(c["mcDispatch_result"][0]) == -2, c["_stderr"]

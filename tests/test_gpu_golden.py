@@ -39,6 +39,10 @@ def check_cuda_against_fixture(gpu_ctx, fx, src, cut, flags):
             assert beq(r["src_bboxes"], fx["src_bboxes"]) and beq(r["cut_bboxes"], fx["cut_bboxes"]), "face AABBs"
             assert beq(r["src_root"], fx["src_root"]) and beq(r["cut_root"], fx["cut_root"]), "mesh AABBs"
             assert beq(r["pairs"], fx["pairs"]), "candidate pair set"
+        raw = int(fx[f"d{k}_status_raw"][0])
+        if raw in (-1, -2):  # status_t::INVALID_SRC_MESH / INVALID_CUT_MESH (kernel.cpp:2237-2244): a degenerate candidate face
+            assert r["status"] == (stage.STATUS_INVALID_SRC_MESH if raw == -1 else stage.STATUS_INVALID_CUT_MESH)
+            continue
         assert beq(r["cand_faces"], fx[f"d{k}_plane_faces"])
         assert beq(r["cand_normal"], fx[f"d{k}_plane_normal"]) and beq(r["cand_d"], fx[f"d{k}_plane_d"])
         assert beq(r["cand_maxcomp"], fx[f"d{k}_plane_mc"])

@@ -50,6 +50,10 @@ def check_oracle_against_fixture(oracle, fx, src, cut, flags):
             assert beq(np.concatenate([soup.edge_v, soup.edge_f], 1), fx["ps_edges"]), "polygon-soup edge numbering"
             assert beq(soup.face_vtx, fx["ps_face_vtx"]) and beq(soup.face_edge, fx["ps_face_edges"])
         assert beq(r["cut_xyz"], fx[f"d{k}_cut_xyz"]), "cut coordinates of this kernel invocation (perturbation applied)"
+        raw = int(fx[f"d{k}_status_raw"][0])
+        if raw in (-1, -2):  # status_t::INVALID_SRC_MESH / INVALID_CUT_MESH (kernel.cpp:2237-2244): a degenerate candidate face
+            assert r["status"] == (2 if raw == -1 else 3)
+            continue
         assert beq(r["cand_faces"], fx[f"d{k}_plane_faces"])
         assert beq(r["cand_normal"], fx[f"d{k}_plane_normal"]) and beq(r["cand_d"], fx[f"d{k}_plane_d"])
         assert beq(r["cand_maxcomp"], fx[f"d{k}_plane_mc"])
