@@ -76,6 +76,21 @@ template <typename KeyT> __device__ __forceinline__ unsigned digit_of(KeyT k, co
     return lo | hi;
 }
 
+// The same digit with the loop-invariant parts hoisted (masks in place, second shift already reduced by `bits`):
+// two shifts and one (a & m1) | (b & m2).
+struct digit_fast {
+    int shift, shift2;
+    unsigned m1, m2;
+    __device__ __forceinline__ explicit digit_fast(const digit_desc& d)
+        : shift(d.shift), shift2(d.bits2 ? d.shift2 - d.bits : 0), m1((1u << d.bits) - 1u), m2(d.bits2 ? ((1u << d.bits2) - 1u) << d.bits : 0u)
+    {
+    }
+    template <typename KeyT> __device__ __forceinline__ unsigned operator()(KeyT k) const
+    {
+        return ((unsigned)(k >> shift) & m1) | ((unsigned)(k >> shift2) & m2);
+    }
+};
+
 __device__ __forceinline__ size_t resolve_n(const unsigned long long* d_n, size_t n_max)
 {
     if (!d_n) return n_max;
@@ -137,47 +152,54 @@ __device__ __forceinline__ unsigned block_exclusive_scan(unsigned v, unsigned* s
     return base + inc - v;
 }
 
-// ---- one pass ------------------------------------------------------------------------------------------------
-// Ranking.  A warp owns 32 * ITEMS consecutive keys, split into units of 256 keys; inside a unit every lane owns 8
-// CONSECUTIVE keys, so "input order" inside the unit is (lane, j).  The rank of a key among the unit's keys with the same
-// digit is then: (keys with that digit in lower lanes) + (earlier keys with that digit in my own lane).  Each lane counts
-// its own digits into a private column of byte counters (count <= 8), one lane per digit row turns the 32 bytes of that
-// row into their exclusive prefix (<= 248, still a byte) with two multiplies per word, and a second walk over the lane's
-// keys reads-and-bumps the counter to get the rank.  No MATCH.ANY and no votes: on sm_100 a dependent
-// __match_any_sync costs ~400 cycles and a warp-match ranking step ~1000 (tools/mb_match.cu), which made ranking half of
-// the pass; the byte-counter walk is ordinary shared-memory traffic.
-// vals_in == nullptr with HAS_VALS: the value of element i is i (saves materialising an iota array).
-constexpr int SUB = 8; // keys a lane owns per ranking unit
-constexpr int CNT_BYTES = WARPS * RADIX * 32; // byte counters: [warp][digit][lane]
+#ifdef MCB_SORT_PROFILE
+__device__ unsigned long long g_sort_phase[8];
+#define MCB_PHASE(i)                                                                                                            \
+    do {                                                                                                                        \
+        if (threadIdx.x == 0) {                                                                                                 \
+            const long long now_ = clock64();                                                                                   \
+            atomicAdd(&g_sort_phase[i], (unsigned long long)(now_ - phase_t_));                                                 \
+            phase_t_ = now_;                                                                                                    \
+        }                                                                                                                       \
+    } while (0)
+#else
+#define MCB_PHASE(i)
+#endif
 
+// ---- one pass ------------------------------------------------------------------------------------------------
+// Ranking.  A warp owns 32 * ITEMS consecutive keys of the tile, striped: item j of a lane is key j * 32 + lane of the
+// warp's chunk, so "input order" inside the chunk is (j, lane).  For item j the lanes find their peers (same digit) with
+// one __ballot_sync per digit bit; the highest peer adds the group's size to the warp's running count of that digit
+// (shared-memory atomicAdd returning the old value) and hands the old value to its peers by shuffle:
+//     rank = keys with this digit in earlier items of the warp (old) + peers in lower lanes.
+// After the last item the warp's counters ARE its digit histogram.  Measured on sm_100 (tools/mb_match.cu, 32 warps on
+// an SM): this step costs ~31 SM cycles per warp-item, __match_any_sync-based ranking ~135, and the previous scheme here
+// (per-lane byte counters in shared memory + a multiply-based prefix over every digit row) ~76 at the IPC it reached -
+// with 64 KB of counters per block (2 blocks per SM) against 8 KB now.
+// vals_in == nullptr with HAS_VALS: the value of element i is i (saves materialising an iota array).
 template <typename KeyT, typename ValT, bool HAS_VALS, int ITEMS> constexpr size_t pass_smem_bytes()
 {
-    constexpr size_t units = (size_t)WARPS * (ITEMS / SUB);
-    constexpr size_t staging = (size_t)THREADS * ITEMS * (sizeof(KeyT) + (HAS_VALS ? sizeof(ValT) : 0));
-    return (staging > (size_t)CNT_BYTES ? staging : (size_t)CNT_BYTES) + units * RADIX * sizeof(unsigned short);
+    return (size_t)THREADS * ITEMS * (sizeof(KeyT) + (HAS_VALS ? sizeof(ValT) : 0)) + (size_t)WARPS * RADIX * sizeof(unsigned);
 }
 
 template <typename KeyT, typename ValT, bool HAS_VALS, int ITEMS>
-__global__ void __launch_bounds__(THREADS) k_onesweep_pass(const KeyT* __restrict__ keys_in, KeyT* __restrict__ keys_out,
+__global__ void __launch_bounds__(THREADS, 3) k_onesweep_pass(const KeyT* __restrict__ keys_in, KeyT* __restrict__ keys_out,
     const ValT* __restrict__ vals_in, ValT* __restrict__ vals_out, const unsigned long long* d_n, size_t n_max,
     digit_desc dd, int pass_index, const unsigned* __restrict__ hist /* [RADIX] of this pass */,
     unsigned* status_all /* [npasses][tiles(n)][RADIX] */, unsigned* tile_counter, size_t skip_le)
 {
     pdl_prologue();
-    static_assert(ITEMS % SUB == 0, "a lane owns whole groups of 8 keys");
     static_assert(THREADS == RADIX, "one thread per digit in the per-digit steps");
     constexpr int TILE = THREADS * ITEMS;
-    constexpr int UPW = ITEMS / SUB; // ranking units per warp
-    constexpr int UNITS = WARPS * UPW;
     constexpr size_t STAGING = (size_t)TILE * (sizeof(KeyT) + (HAS_VALS ? sizeof(ValT) : 0));
-    constexpr size_t REGION0 = STAGING > (size_t)CNT_BYTES ? STAGING : (size_t)CNT_BYTES;
     extern __shared__ __align__(16) unsigned char s_dyn[];
-    // region 0: byte counters while ranking, then the key/value staging of the reorder
+    // region 0: key/value staging of the reorder; then the warps' digit counters
     KeyT* s_keys = reinterpret_cast<KeyT*>(s_dyn);
     ValT* s_vals = reinterpret_cast<ValT*>(s_dyn + (size_t)TILE * sizeof(KeyT));
-    unsigned short(*s_unit_hist)[RADIX] = reinterpret_cast<unsigned short(*)[RADIX]>(s_dyn + REGION0); // [UNITS][RADIX]
+    unsigned* s_wcnt = reinterpret_cast<unsigned*>(s_dyn + STAGING); // [WARPS][RADIX]
     __shared__ unsigned s_tile_excl[RADIX];
     __shared__ unsigned s_global_off[RADIX];
+    __shared__ unsigned s_tile_hist[RADIX];
     __shared__ unsigned s_scan[WARPS];
     __shared__ unsigned s_tile;
 
@@ -187,7 +209,10 @@ __global__ void __launch_bounds__(THREADS) k_onesweep_pass(const KeyT* __restric
     unsigned* status = status_all + (size_t)pass_index * status_rows(num_tiles) * RADIX;
     unsigned* gstatus = status + (size_t)num_tiles * RADIX; // group rows
     const unsigned lane = threadIdx.x & 31u, w = threadIdx.x >> 5;
-    unsigned char* s_cnt = s_dyn + (size_t)w * (RADIX * 32); // this warp's counters: [digit][lane]
+    unsigned* my_cnt = s_wcnt + w * RADIX; // this warp's counters
+    const digit_fast digit(dd);
+    const int nbits = dd.bits + dd.bits2;
+    const unsigned lanes_below = (1u << lane) - 1u;
 
     // exclusive scan of the pass histogram: where each digit's bucket starts in the output
     unsigned my_bucket_base = block_exclusive_scan(hist[threadIdx.x], s_scan, nullptr);
@@ -200,114 +225,55 @@ __global__ void __launch_bounds__(THREADS) k_onesweep_pass(const KeyT* __restric
         const size_t tile_base = (size_t)tile * TILE;
         const unsigned tile_n = (unsigned)((n - tile_base < (size_t)TILE) ? (n - tile_base) : (size_t)TILE);
         const bool full = tile_n == (unsigned)TILE;
+        const unsigned local0 = w * (32 * ITEMS) + lane; // item j: local0 + 32 j
+#ifdef MCB_SORT_PROFILE
+        long long phase_t_ = clock64();
+#endif
 
-        // ---- load: 8 consecutive keys per lane and unit (16-byte vector loads on full tiles) ----
-        __align__(16) KeyT key[ITEMS];
-        __align__(16) ValT val[HAS_VALS ? ITEMS : 4];
-        unsigned char rank[ITEMS];
+        // ---- load (coalesced: a warp reads 32 consecutive keys per item) ----
+        KeyT key[ITEMS];
+        ValT val[HAS_VALS ? ITEMS : 1];
+        unsigned short rank[ITEMS];
 #pragma unroll
-        for (int u = 0; u < UPW; ++u) {
-            const unsigned local0 = w * (32 * ITEMS) + u * (32 * SUB) + lane * SUB;
-            if (full) {
-                constexpr int KV = SUB * sizeof(KeyT) / 16;
-                const uint4* kp = reinterpret_cast<const uint4*>(keys_in + tile_base + local0);
-#pragma unroll
-                for (int q = 0; q < KV; ++q) reinterpret_cast<uint4*>(&key[u * SUB])[q] = kp[q];
-                if (HAS_VALS) {
-                    if (vals_in) {
-                        constexpr int VV = SUB * sizeof(ValT) / 16;
-                        const uint4* vp = reinterpret_cast<const uint4*>(vals_in + tile_base + local0);
-#pragma unroll
-                        for (int q = 0; q < VV; ++q) reinterpret_cast<uint4*>(&val[u * SUB])[q] = vp[q];
-                    } else {
-#pragma unroll
-                        for (int j = 0; j < SUB; ++j) val[u * SUB + j] = (ValT)(tile_base + local0 + j);
-                    }
-                }
-            } else {
-#pragma unroll
-                for (int j = 0; j < SUB; ++j) {
-                    const unsigned local = local0 + j;
-                    const bool valid = local < tile_n;
-                    key[u * SUB + j] = valid ? keys_in[tile_base + local] : (KeyT)0;
-                    if (HAS_VALS) val[u * SUB + j] = valid ? (vals_in ? vals_in[tile_base + local] : (ValT)(tile_base + local)) : (ValT)0;
-                }
-            }
+        for (int j = 0; j < ITEMS; ++j) {
+            const unsigned local = local0 + 32u * j;
+            const bool valid = full || local < tile_n;
+            key[j] = valid ? keys_in[tile_base + local] : (KeyT)0;
+            if (HAS_VALS) val[j] = valid ? (vals_in ? vals_in[tile_base + local] : (ValT)(tile_base + local)) : (ValT)0;
         }
 
-        // ---- rank, unit by unit ----
-#pragma unroll
-        for (int u = 0; u < UPW; ++u) {
-            const unsigned local0 = w * (32 * ITEMS) + u * (32 * SUB) + lane * SUB;
-            {
-                const uint4 z = make_uint4(0u, 0u, 0u, 0u);
-#pragma unroll
-                for (int q = 0; q < RADIX * 32 / 16 / 32; ++q) reinterpret_cast<uint4*>(s_cnt)[q * 32 + lane] = z;
-            }
-            __syncwarp();
-#pragma unroll
-            for (int j = 0; j < SUB; ++j) {
-                if (full || local0 + j < tile_n) {
-                    const unsigned d = digit_of(key[u * SUB + j], dd);
-                    s_cnt[d * 32 + lane] += 1;
-                }
-            }
-            __syncwarp();
-            // one lane per digit row: 32 byte counts -> exclusive prefix over the lanes, row total -> unit histogram
-#pragma unroll
-            for (int k = 0; k < RADIX / 32; ++k) {
-                const unsigned d = k * 32 + lane;
-                uint4* row = reinterpret_cast<uint4*>(s_cnt + d * 32);
-                uint4 r0 = row[0], r1 = row[1];
-                unsigned wv[8] = { r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w };
-                unsigned running = 0;
-#pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    const unsigned t = wv[i];
-                    const unsigned tot = (t * 0x01010101u) >> 24; // <= 32
-                    wv[i] = (t << 8) * 0x01010101u + running * 0x01010101u; // byte b: earlier bytes of the word + earlier words
-                    running += tot;
-                }
-                row[0] = make_uint4(wv[0], wv[1], wv[2], wv[3]);
-                row[1] = make_uint4(wv[4], wv[5], wv[6], wv[7]);
-                s_unit_hist[w * UPW + u][d] = (unsigned short)running;
-            }
-            __syncwarp();
-#pragma unroll
-            for (int j = 0; j < SUB; ++j) {
-                unsigned char r = 0;
-                if (full || local0 + j < tile_n) {
-                    const unsigned d = digit_of(key[u * SUB + j], dd);
-                    r = s_cnt[d * 32 + lane];
-                    s_cnt[d * 32 + lane] = (unsigned char)(r + 1);
-                }
-                rank[u * SUB + j] = r;
-            }
-            __syncwarp();
+#ifdef MCB_SORT_PROFILE
+        {
+            unsigned acc_ = 0;
+            for (int j = 0; j < ITEMS; ++j) acc_ += (unsigned)key[j];
+            if (acc_ == 0x12345u) s_scan[0] = acc_; // forces the loads to land
+            __syncthreads();
         }
+        MCB_PHASE(0);
+#endif
+        // ---- the tile's digit counts first: published before the ranking starts, so that the tiles that wait for them in
+        //      their look-back wait for a few hundred cycles of shared-memory atomics instead of a whole ranking phase ----
+        s_tile_hist[threadIdx.x] = 0u;
+#pragma unroll
+        for (int q = 0; q < RADIX / 32; ++q) my_cnt[q * 32 + lane] = 0u;
         __syncthreads();
-
-        // ---- per-digit: unit counts -> exclusive unit offsets, tile total ----
-        unsigned total = 0;
-        {
-            const unsigned d = threadIdx.x;
 #pragma unroll
-            for (int i = 0; i < UNITS; ++i) {
-                const unsigned c = s_unit_hist[i][d];
-                s_unit_hist[i][d] = (unsigned short)total;
-                total += c;
-            }
-        }
-        // publish the tile's digit count as early as possible
+        for (int j = 0; j < ITEMS; ++j)
+            if (full || local0 + 32u * j < tile_n) atomicAdd(&s_tile_hist[digit(key[j])], 1u);
+        __syncthreads();
+        const unsigned total = s_tile_hist[threadIdx.x];
         {
-            const unsigned d = threadIdx.x;
-            volatile unsigned* st = status + (size_t)tile * RADIX + d;
+            volatile unsigned* st = status + (size_t)tile * RADIX + threadIdx.x;
             *st = FLAG_AGG | total;
         }
+        MCB_PHASE(7);
+
         const unsigned excl_in_tile = block_exclusive_scan(total, s_scan, nullptr);
         s_tile_excl[threadIdx.x] = excl_in_tile;
 
-        // ---- two-level look-back: sum of this digit's counts over all previous tiles ----
+        // ---- two-level look-back: sum of this digit's counts over all previous tiles.  It runs BEFORE the ranking: what it
+        //      waits for is other tiles' histograms, which are a few hundred cycles old by now, and the tiles that wait for
+        //      THIS tile's group total do not have to sit through its ranking phase ----
         // At these sizes every tile of a pass is resident at once and publishes at about the same moment, so a chained
         // look-back would walk all the way back (tiles/16 dependent L2 round trips).  Instead tiles form groups of 16:
         // a tile sums the counts of the earlier tiles of its own group (one round of independent loads); the LAST tile
@@ -374,32 +340,73 @@ __global__ void __launch_bounds__(THREADS) k_onesweep_pass(const KeyT* __restric
             prefix += before;
             s_global_off[d] = my_bucket_base + prefix;
         }
-        __syncthreads(); // ranking is over in every warp: region 0 may now hold the staged keys
+        MCB_PHASE(3);
+
+        // ---- rank ----
+#pragma unroll
+        for (int j = 0; j < ITEMS; ++j) {
+            const bool valid = full || local0 + 32u * j < tile_n;
+            const unsigned d = digit(key[j]);
+            unsigned peers = full ? 0xffffffffu : __ballot_sync(0xffffffffu, valid);
+#pragma unroll
+            for (int b = 0; b < 8; ++b) {
+                if (b < nbits) { // uniform
+                    const bool bit = (d >> b) & 1u;
+                    const unsigned bal = __ballot_sync(0xffffffffu, bit);
+                    peers &= bit ? bal : ~bal;
+                }
+            }
+            // a valid lane is its own peer, so peers != 0 there; lanes past the end take no part
+            const int leader = 31 - __clz(peers);
+            unsigned before = 0;
+            if (valid && (int)lane == leader) before = atomicAdd(&my_cnt[d], (unsigned)__popc(peers));
+            before = __shfl_sync(0xffffffffu, before, leader & 31);
+            rank[j] = (unsigned short)(before + __popc(peers & lanes_below));
+        }
+        __syncthreads();
+        MCB_PHASE(1);
+
+        // ---- per-digit: warp counts -> exclusive warp offsets ----
+        {
+            const unsigned d = threadIdx.x;
+            unsigned run = 0;
+#pragma unroll
+            for (int i = 0; i < WARPS; ++i) {
+                const unsigned c = s_wcnt[i * RADIX + d];
+                s_wcnt[i * RADIX + d] = run;
+                run += c;
+            }
+        }
+        MCB_PHASE(2);
+        __syncthreads(); // warp offsets and tile offsets are in place
+        MCB_PHASE(4);
 
         // ---- reorder the tile through shared memory ----
+        // (all the offset loads first: the compiler cannot prove that the staging stores leave the offset tables alone)
 #pragma unroll
-        for (int u = 0; u < UPW; ++u) {
-            const unsigned local0 = w * (32 * ITEMS) + u * (32 * SUB) + lane * SUB;
+        for (int j = 0; j < ITEMS; ++j) {
+            const unsigned d = digit(key[j]);
+            rank[j] = (unsigned short)(s_tile_excl[d] + my_cnt[d] + rank[j]); // position in the tile, < TILE <= 4096
+        }
 #pragma unroll
-            for (int j = 0; j < SUB; ++j) {
-                if (full || local0 + j < tile_n) {
-                    const unsigned d = digit_of(key[u * SUB + j], dd);
-                    const unsigned pos = s_tile_excl[d] + s_unit_hist[w * UPW + u][d] + rank[u * SUB + j];
-                    s_keys[pos] = key[u * SUB + j];
-                    if (HAS_VALS) s_vals[pos] = val[u * SUB + j];
-                }
+        for (int j = 0; j < ITEMS; ++j) {
+            if (full || local0 + 32u * j < tile_n) {
+                s_keys[rank[j]] = key[j];
+                if (HAS_VALS) s_vals[rank[j]] = val[j];
             }
         }
         __syncthreads();
+        MCB_PHASE(5);
         // ---- coalesced runs out ----
         for (unsigned i = threadIdx.x; i < tile_n; i += THREADS) {
             const KeyT k = s_keys[i];
-            const unsigned d = digit_of(k, dd);
+            const unsigned d = digit(k);
             const size_t dst = (size_t)s_global_off[d] + (i - s_tile_excl[d]);
             keys_out[dst] = k;
             if (HAS_VALS) vals_out[dst] = s_vals[i];
         }
         __syncthreads();
+        MCB_PHASE(6);
     }
 }
 

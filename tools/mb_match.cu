@@ -34,6 +34,25 @@ __global__ void k(unsigned* out, long long* cyc, int mode)
             old = __shfl_sync(p, old, leader); unsigned r = old + __popc(p & lt); __syncwarp();
             acc += r; x = (x * 5u + 1u + i) & 255u;
         }
+    } else if (mode == 5) { // ballot ranking of 16 register-resident keys per lane, leader atomicAdd + shuffle (throughput form)
+        unsigned lt = (1u << lane) - 1u;
+        unsigned keys[16];
+        for (int j = 0; j < 16; ++j) keys[j] = (x * (2 * j + 1) + j * 37u) & 255u;
+        for (int i = 0; i < 16; ++i) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                const unsigned d = keys[j];
+                unsigned p = 0xffffffffu;
+#pragma unroll
+                for (int b = 0; b < 8; ++b) { unsigned bal = __ballot_sync(0xffffffffu, (d >> b) & 1u); p &= ((d >> b) & 1u) ? bal : ~bal; }
+                const int leader = 31 - __clz(p);
+                unsigned old = 0;
+                if ((int)lane == leader) old = atomicAdd(&sh[d], __popc(p));
+                old = __shfl_sync(0xffffffffu, old, leader);
+                acc += old + __popc(p & lt);
+            }
+            for (int j = 0; j < 16; ++j) keys[j] = (keys[j] * 5u + 1u + i) & 255u;
+        }
     }
     long long t1 = clock64();
     out[blockIdx.x * blockDim.x + threadIdx.x] = acc;
@@ -42,8 +61,8 @@ __global__ void k(unsigned* out, long long* cyc, int mode)
 int main()
 {
     unsigned* out; long long* cyc; cudaMalloc(&out, 4 * 1024 * 1024); cudaMallocManaged(&cyc, 64);
-    for (int warps = 1; warps <= 8; warps *= 8)
-        for (int mode = 0; mode < 5; ++mode) {
+    for (int warps = 1; warps <= 32; warps *= (warps == 8 ? 4 : 8))
+        for (int mode = 0; mode < 6; ++mode) {
             k<<<1, 32 * warps>>>(out, cyc, mode); cudaDeviceSynchronize();
             k<<<1, 32 * warps>>>(out, cyc, mode); cudaDeviceSynchronize();
             printf("warps=%d mode=%d cycles/op=%.1f\n", warps, mode, (double)cyc[mode] / 256.0);
