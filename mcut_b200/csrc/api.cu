@@ -100,6 +100,7 @@ int mcb200_ctx_create(int device, void* stream, mcb200_ctx** out)
         return (int)e;
     }
     if (const char* e = std::getenv("MCB200_PDL")) ctx->pdl = (e[0] != '0');
+    if (const char* e = std::getenv("MCB200_MORTON_SORT_BITS")) ctx->morton_sort_bits = (std::atoi(e) >= 30) ? 30 : 24;
     {
         // keep freed blocks in the stream-ordered pool instead of handing them back to the driver at every synchronisation:
         // a dispatch allocates a few hundred MB of build products, and mapping that memory anew costs far more than the stage

@@ -127,7 +127,7 @@ __global__ void __launch_bounds__(BLOCK) k_face_bbox(const void* __restrict__ xy
 __global__ void __launch_bounds__(BLOCK) k_morton(const double* __restrict__ face_bbox, uint32_t nf,
     const unsigned long long* __restrict__ root_ordered, double* __restrict__ root_decoded, uint32_t* __restrict__ codes,
     uint32_t* __restrict__ sort_keys, unsigned* __restrict__ hist /* [4][256] */, unsigned* __restrict__ status,
-    unsigned status_words)
+    unsigned status_words, unsigned key_shift, int npasses)
 {
     pdl_prologue();
     __shared__ unsigned s_hist[4 * 256];
@@ -154,9 +154,11 @@ __global__ void __launch_bounds__(BLOCK) k_morton(const double* __restrict__ fac
         }
         const uint32_t code = morton3D(nrm[0], nrm[1], nrm[2]);
         codes[f] = code;
-        sort_keys[f] = code;
+        const uint32_t key = code >> key_shift; // the leaves are ordered by the top bits of the code (lbvh_build)
+        sort_keys[f] = key;
 #pragma unroll
-        for (int p = 0; p < 4; ++p) atomicAdd(&s_hist[p * 256 + ((code >> (8 * p)) & 255u)], 1u);
+        for (int p = 0; p < 4; ++p)
+            if (p < npasses) atomicAdd(&s_hist[p * 256 + ((key >> (8 * p)) & 255u)], 1u);
     }
     __syncthreads();
     for (int i = threadIdx.x; i < 4 * 256; i += BLOCK) {
@@ -585,17 +587,28 @@ int lbvh_build(mcb200_ctx* ctx, mcb200_mesh* m, double eps, bool query_only)
     m->n_prior = 0; // consumed: the boxes are part of face_bbox now
     // (code, face) ascending by code: in = sorted_codes (values implicit 0..nf-1), ping-pong scratch <-> mesh arrays;
     // four passes end in the mesh's own arrays.  The histograms come out of k_morton.
-    const rsort::pass_desc pd = rsort::make_passes(0, 32);
+    // The leaves are ordered by the top `morton_sort_bits` bits of their code.  Nothing that leaves this stage depends on the
+    // order (the pair SET is tree-independent and the treelets hold up to 32 leaves anyway), so the default sorts 24 bits in
+    // three passes; codes that tie are told apart by their position, as equal codes always were.  With an odd number of
+    // passes the keys start in the scratch buffer so that the last pass lands in the mesh's own arrays.
+    const int sort_bits = ctx->morton_sort_bits >= 30 ? 32 : 24;
+    const unsigned key_shift = sort_bits == 32 ? 0u : 6u;
+    const rsort::pass_desc pd = rsort::make_passes(0, sort_bits);
     constexpr int SORT_TILE = rsort::THREADS * rsort::items_for<uint32_t>::value;
     const unsigned status_words = (unsigned)rsort::status_rows(((size_t)nf + SORT_TILE - 1) / SORT_TILE) * rsort::RADIX * (unsigned)pd.npasses;
-    MCB_LAUNCH(ctx, k_morton, grid, BLOCK, 0, m->face_bbox.as<double>(), nf, root_ord, root_dec, m->codes.as<uint32_t>(),
-        m->sorted_codes.as<uint32_t>(), sc.hist.as<unsigned>(), sc.status.as<unsigned>(), status_words);
+    const bool odd = (pd.npasses & 1) != 0;
+    uint32_t* keys_in = odd ? sc.keys_alt.as<uint32_t>() : m->sorted_codes.as<uint32_t>();
+    uint32_t* keys_a = odd ? m->sorted_codes.as<uint32_t>() : sc.keys_alt.as<uint32_t>();
+    uint32_t* keys_b = odd ? sc.keys_alt.as<uint32_t>() : m->sorted_codes.as<uint32_t>();
+    uint32_t* vals_a = odd ? m->sorted_faces.as<uint32_t>() : sc.vals_alt.as<uint32_t>();
+    uint32_t* vals_b = odd ? sc.vals_alt.as<uint32_t>() : m->sorted_faces.as<uint32_t>();
+    MCB_LAUNCH(ctx, k_morton, grid, BLOCK, 0, m->face_bbox.as<double>(), nf, root_ord, root_dec, m->codes.as<uint32_t>(), keys_in,
+        sc.hist.as<unsigned>(), sc.status.as<unsigned>(), status_words, key_shift, pd.npasses);
     uint32_t *kout = nullptr, *vout = nullptr;
-    MCB_TRY((rsort::sort_passes<uint32_t, uint32_t, true>(ctx, m->sorted_codes.as<uint32_t>(), sc.keys_alt.as<uint32_t>(),
-        m->sorted_codes.as<uint32_t>(), nullptr, sc.vals_alt.as<uint32_t>(), m->sorted_faces.as<uint32_t>(), nullptr, nf, pd, &kout,
+    MCB_TRY((rsort::sort_passes<uint32_t, uint32_t, true>(ctx, keys_in, keys_a, keys_b, nullptr, vals_a, vals_b, nullptr, nf, pd, &kout,
         &vout)));
     if (kout != m->sorted_codes.as<uint32_t>() || vout != m->sorted_faces.as<uint32_t>()) {
-        ctx->set_error("internal: Morton sort must use an even number of passes", __FILE__, __LINE__);
+        ctx->set_error("internal: the Morton sort did not end in the mesh's arrays", __FILE__, __LINE__);
         return MCB200_ERR_INTERNAL;
     }
     if (nf <= 1) query_only = false; // the one-leaf pseudo tree is free
