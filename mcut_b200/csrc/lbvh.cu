@@ -3,7 +3,7 @@
 // Replaces build_oibvh() (include/mcut/internal/bvh.h:117-125, source/bvh.cpp:219-636):
 //   k_face_bbox    face AABBs (+eps enlargement) and the mesh AABB               bvh.cpp:242-368, math.h:866-928
 //   k_morton       30-bit Morton codes, the reference's float formula;           bvh.cpp:196-217, :373-433
-//                  also the four digit histograms of the sort
+//                  also the digit histograms of the sort's passes
 //   radix passes   one-sweep radix sort of (code, face)  (radix_sort.cuh)        bvh.cpp:437-442 (std::sort there)
 //   k_tree         radix tree over the sorted codes (Karras 2012) fused with     replaces the implicit OIBVH layout :444-493
 //                  the box refit of every subtree of <= 32 leaves                and the bottom of bvh.cpp:498-635
@@ -121,7 +121,7 @@ __global__ void __launch_bounds__(BLOCK) k_face_bbox(const void* __restrict__ xy
 }
 
 // ---- K_morton ---------------------------------------------------------------------------------------------------
-// Codes by face + the same codes as sort keys; the digit histograms of all four radix passes are accumulated here (shared
+// Codes by face + the same codes as sort keys; the digit histograms of all radix passes of the sort are accumulated here (shared
 // memory, one flush per block) and the sort's look-back status words are cleared, so the sort needs no histogram kernel
 // and no second read of the keys.
 __global__ void __launch_bounds__(BLOCK) k_morton(const double* __restrict__ face_bbox, uint32_t nf,
@@ -321,7 +321,7 @@ __device__ __forceinline__ unsigned alloc_groups_block(unsigned* n_groups, unsig
 //  * k_tree: one thread per internal node finds its range and split (Karras 2012) from the block's shared window of
 //    sorted codes.  A node whose leaf range has at most 32 leaves then gets both child boxes straight from the leaf boxes
 //    of its range (it knows its range and its split, so no other node's result is needed): no atomics, no fences, and the
-//    whole 128-byte record (boxes + topology) is written at once.  Node i lies inside its own range, so every such range
+//    whole 64-byte record (boxes + topology) is written at once.  Node i lies inside its own range, so every such range
 //    falls in the block's leaf window [i0-32, i0+288), gathered into shared memory while the code window loads.  The
 //    maximal treelets ("group roots") are listed: they are the traversal's query groups and the starting points of ...
 //    Whether a node's PARENT covers more than 32 leaves is decided locally: the parent's range is the set of keys sharing
@@ -585,9 +585,8 @@ int lbvh_build(mcb200_ctx* ctx, mcb200_mesh* m, double eps, bool query_only)
         MCB_LAUNCH(ctx, k_face_bbox<false>, grid, BLOCK, 0, m->d_xyz, m->frame, m->d_face_vtx, m->d_face_off, nf, eps,
             m->face_bbox.as<double>(), root_ord, m->flags.as<unsigned>(), prior, n_prior);
     m->n_prior = 0; // consumed: the boxes are part of face_bbox now
-    // (code, face) ascending by code: in = sorted_codes (values implicit 0..nf-1), ping-pong scratch <-> mesh arrays;
-    // four passes end in the mesh's own arrays.  The histograms come out of k_morton.
-    // The leaves are ordered by the top `morton_sort_bits` bits of their code.  Nothing that leaves this stage depends on the
+    // (key, face) ascending by key (values implicit 0..nf-1), ping-pong scratch <-> mesh arrays; the histograms come out
+    // of k_morton.  The leaves are ordered by the top `morton_sort_bits` bits of their code.  Nothing that leaves this stage depends on the
     // order (the pair SET is tree-independent and the treelets hold up to 32 leaves anyway), so the default sorts 24 bits in
     // three passes; codes that tie are told apart by their position, as equal codes always were.  With an odd number of
     // passes the keys start in the scratch buffer so that the last pass lands in the mesh's own arrays.
