@@ -23,6 +23,23 @@ def test_device_validation_equals_oracle(oracle, gpu_ctx, case):
     m.free()
 
 
+def test_device_validation_on_the_reference_corpus(oracle, gpu_ctx):
+    """The 122 meshes of the reference's regression corpus (polygons of up to 32 vertices, open meshes): device == oracle,
+    which equals the reference's own functions on them (tests/test_oracle_validate.py)."""
+    from golden_util import CORPUS_CASES, load_corpus
+    from mcut_b200 import stage
+    for pair in CORPUS_CASES:
+        _, src, cut, _ = load_corpus(pair)
+        for x, f, s in (src, cut):
+            off = np.concatenate([[0], np.cumsum(s)]).astype(np.uint32)
+            m = stage.Mesh(gpu_ctx, x, f, s)
+            n, fcc, cv, cf, border = m.validate()
+            rn, rfcc, rcv, rcf, rborder = oracle.validate(x.shape[0], off, f)
+            assert n == rn and border == rborder, pair
+            assert np.array_equal(fcc, rfcc) and np.array_equal(cv, rcv) and np.array_equal(cf, rcf), pair
+            m.free()
+
+
 def test_device_validation_at_scale(oracle, gpu_ctx):
     """1M-triangle sphere: one closed component; the same with a cap cut off: border edges appear."""
     from mcut_b200 import meshgen as mg, stage

@@ -23,6 +23,20 @@ def test_oracle_validation_equals_reference(oracle, case):
     assert (border == 0) == closed_ref
 
 
+@needs_ref
+def test_oracle_validation_equals_reference_on_the_regression_corpus(oracle):
+    """All 122 meshes of the reference's regression corpus (polygons of up to 32 vertices, 60 of them open)."""
+    from golden_util import CORPUS_CASES, load_corpus
+    for pair in CORPUS_CASES:
+        _, src, cut, _ = load_corpus(pair)
+        for x, f, s in (src, cut):
+            off = np.concatenate([[0], np.cumsum(s)]).astype(np.uint32)
+            n_ref, fcc_ref, cv_ref, cf_ref, closed_ref = oracle.ref_validate(x.shape[0], off, f)
+            n, fcc, cv, cf, border = oracle.validate(x.shape[0], off, f)
+            assert n == n_ref and np.array_equal(fcc, fcc_ref) and np.array_equal(cv, cv_ref) and np.array_equal(cf, cf_ref), pair
+            assert (border == 0) == closed_ref, pair
+
+
 def test_known_answers(oracle):
     cases = validate_cases.all_cases()
     n, fcc, cv, cf, border = oracle.validate(*cases["two_spheres_and_a_stray_vertex"])
