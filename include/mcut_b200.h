@@ -182,6 +182,18 @@ int mcb200_mesh_read_components(mcb200_ctx* ctx, mcb200_mesh* mesh, int32_t* fcc
  * CDT, which stays on the host). */
 int mcb200_mesh_winding_number(mcb200_ctx* ctx, mcb200_mesh* mesh, const double query[3], double* winding_number);
 
+/* The inside/outside verdict mcDispatch stores for MC_DISPATCH_INCLUDE_INTERSECTION_TYPE when the surfaces do NOT cut each
+ * other (no candidate pair, preproc.cpp:2865-2901, or no connected component beyond the two inputs, :3693-3725):
+ * check_and_store_input_mesh_intersection_type(), preproc.cpp:1999-2122, decision for decision — watertightness of both
+ * meshes (mcb200_mesh_validate), closed-interval overlap of the two mesh AABBs (bvhAABBs[0]; both meshes must be built),
+ * winding number of one mesh's first vertex with respect to the other (mcb200_mesh_winding_number, eps 1e-7).  Values are
+ * those of McDispatchIntersectionType (mcut.h:486-492); STANDARD is the caller's answer when the surfaces do cut. */
+#define MCB200_INTERSECTION_TYPE_STANDARD 0u
+#define MCB200_INTERSECTION_TYPE_INSIDE_CUTMESH (1u << 1)
+#define MCB200_INTERSECTION_TYPE_INSIDE_SOURCEMESH (1u << 2)
+#define MCB200_INTERSECTION_TYPE_NONE (1u << 3)
+int mcb200_intersection_type_without_cut(mcb200_ctx* ctx, mcb200_mesh* src, mcb200_mesh* cut, uint32_t* type);
+
 /* ---------------------------------------------------------------- (3) narrowphase -------------------------- */
 int mcb200_soup_create(mcb200_ctx* ctx, uint32_t nsf, uint32_t ncf, uint32_t nh, uint32_t ne, const uint32_t* face_vtx,
     const uint32_t* face_edge, const uint32_t* edge_f, mcb200_soup** soup);

@@ -70,6 +70,7 @@ SYMBOLS = {
     "mcb200_mesh_set_frame": (C.c_int, [vp, vp, c_dp, c_dp, c_dp]),
     "mcb200_mesh_free": (None, [vp, vp]),
     "mcb200_bvh_build": (C.c_int, [vp, vp, C.c_double]),
+    "mcb200_intersection_type_without_cut": (C.c_int, [vp, vp, vp, C.POINTER(C.c_uint32)]),
     "mcb200_mesh_set_prior_face_boxes": (C.c_int, [vp, vp, C.POINTER(C.c_double), C.c_uint32]),
     "mcb200_bvh_read": (C.c_int, [vp, vp, c_dp, c_dp]),
     "mcb200_bvh_read_morton": (C.c_int, [vp, vp, c_u32p, c_u32p]),

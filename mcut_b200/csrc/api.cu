@@ -355,6 +355,61 @@ int mcb200_mesh_winding_number(mcb200_ctx* ctx, mcb200_mesh* mesh, const double 
     return 0;
 }
 
+int mcb200_intersection_type_without_cut(mcb200_ctx* ctx, mcb200_mesh* src, mcb200_mesh* cut, uint32_t* type)
+{
+    // check_and_store_input_mesh_intersection_type(), preproc.cpp:1999-2122, decision for decision
+    if (!ctx || !src || !cut || !type) return MCB200_ERR_INVALID;
+    if (!src->built || !cut->built) MCB_FAIL(ctx, MCB200_ERR_INVALID, "intersection_type: both meshes must be built (their mesh AABBs are an input)");
+    mcb200_validation vs, vc;
+    MCB_TRY(mcb200_mesh_validate(ctx, src, &vs)); // mesh_is_closed(): no border edge (preproc.cpp:1957-1990)
+    MCB_TRY(mcb200_mesh_validate(ctx, cut, &vc));
+    const bool sm_closed = vs.is_closed != 0, cm_closed = vc.is_closed != 0;
+    double sb[6], cb[6];
+    MCB_TRY(mcb200_bvh_read(ctx, src, nullptr, sb)); // bvhAABBs[0] of each mesh
+    MCB_TRY(mcb200_bvh_read(ctx, cut, nullptr, cb));
+    bool boxes_meet = true; // intersect_bounding_boxes(): closed intervals (math.h:931-941)
+    for (int j = 0; j < 3; ++j)
+        if (sb[j] > cb[3 + j] || cb[j] > sb[3 + j]) boxes_meet = false;
+    const double eps = 1e-7; // windingNumberEps
+    auto inside = [&](mcb200_mesh* point_of, mcb200_mesh* mesh, bool& in) -> int {
+        double q[3], wn = 0.0;
+        ctx->use_main();
+        MCB_TRY(mesh_vertex_position(ctx, point_of, 0u, q)); // "pick any point (we chose the 1st)"
+        MCB_TRY(mcb200_mesh_winding_number(ctx, mesh, q, &wn));
+        in = std::fabs(1.0 - wn) < eps;
+        return 0;
+    };
+    *type = MCB200_INTERSECTION_TYPE_NONE;
+    if ((!sm_closed && !cm_closed) || !boxes_meet) return 0;
+    bool in = false;
+    if (sm_closed && cm_closed) {
+        // the mesh with the larger AABB is tested first
+        auto diag2 = [](const double* b) {
+            const double x = b[3] - b[0], y = b[4] - b[1], z = b[5] - b[2];
+            return 0.0 + x * x + y * y + z * z; // squared_length = dot_product, accumulated left to right (math.h:634-642)
+        };
+        const bool sm_larger = diag2(sb) > diag2(cb);
+        mcb200_mesh* a = sm_larger ? src : cut;
+        mcb200_mesh* b = sm_larger ? cut : src;
+        MCB_TRY(inside(b, a, in));
+        if (in) {
+            *type = sm_larger ? MCB200_INTERSECTION_TYPE_INSIDE_SOURCEMESH : MCB200_INTERSECTION_TYPE_INSIDE_CUTMESH;
+            return 0;
+        }
+        MCB_TRY(inside(src, b, in)); // the reference takes the SOURCE mesh's first vertex here, whichever mesh is "A" (:2053)
+        if (in) *type = sm_larger ? MCB200_INTERSECTION_TYPE_INSIDE_CUTMESH : MCB200_INTERSECTION_TYPE_INSIDE_SOURCEMESH;
+        return 0;
+    }
+    if (sm_closed) {
+        MCB_TRY(inside(cut, src, in));
+        if (in) *type = MCB200_INTERSECTION_TYPE_INSIDE_SOURCEMESH;
+        return 0;
+    }
+    MCB_TRY(inside(src, cut, in));
+    if (in) *type = MCB200_INTERSECTION_TYPE_INSIDE_CUTMESH;
+    return 0;
+}
+
 int mcb200_mesh_read_components(mcb200_ctx* ctx, mcb200_mesh* mesh, int32_t* fccmap, int32_t* cc_vertex_count,
     int32_t* cc_face_count, size_t capacity_components)
 {

@@ -27,6 +27,7 @@ int soup_number_device(mcb200_ctx* ctx, const mcb200_mesh* src, const mcb200_mes
 // validate.cu
 int mesh_validate_run(mcb200_ctx* ctx, mcb200_mesh* mesh);
 int mesh_winding_run(mcb200_ctx* ctx, mcb200_mesh* mesh, const double query[3]);
+int mesh_vertex_position(mcb200_ctx* ctx, mcb200_mesh* mesh, uint32_t v, double out[3]);
 // host_logic.cpp
 int host_soup_ids(uint32_t nsv, const uint32_t* src_off, const uint32_t* src_vtx, uint32_t nsf, const uint32_t* cut_off,
     const uint32_t* cut_vtx, uint32_t ncf, uint32_t* face_vtx, uint32_t* face_edge, uint32_t* edge_v, uint32_t* edge_f,

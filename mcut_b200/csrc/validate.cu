@@ -388,13 +388,36 @@ __global__ void __launch_bounds__(VBLOCK) k_winding_final(const double* partial,
     if (threadIdx.x == 0) out[0] = s_sum[0];
 }
 
+__global__ void k_vertex_position(const void* xyz, frame_t fr, uint32_t v, double* out)
+{
+    pdl_prologue();
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        double p[3];
+        load_vertex(xyz, fr, v, p);
+        out[0] = p[0], out[1] = p[1], out[2] = p[2];
+    }
+}
+
 } // namespace
+
+// internal coordinates of vertex v (what hmesh_t::vertex(v) holds in the reference after client_input_arrays_to_hmesh)
+int mesh_vertex_position(mcb200_ctx* ctx, mcb200_mesh* m, uint32_t v, double out[3])
+{
+    if (v >= m->nv) return MCB200_ERR_INVALID;
+    const unsigned grid = (unsigned)ctx->num_sms * 4u;
+    MCB_TRY(ctx->reserve(m->cc_wn, sizeof(double) * ((size_t)grid + 2 + 3)));
+    double* d = m->cc_wn.as<double>() + (size_t)grid + 2;
+    MCB_LAUNCH(ctx, k_vertex_position, 1, 32, 0, m->d_xyz, m->frame, v, d);
+    MCB_CUDA(ctx, cudaMemcpyAsync(out, d, sizeof(double) * 3, cudaMemcpyDeviceToHost, ctx->cur));
+    MCB_CUDA(ctx, cudaStreamSynchronize(ctx->cur));
+    return 0;
+}
 
 // winding number of `query` (internal coordinates, like the mesh's frame produces) into mesh->cc_wn[0]; [1] = unsupported flag
 int mesh_winding_run(mcb200_ctx* ctx, mcb200_mesh* m, const double query[3])
 {
     const unsigned grid = (unsigned)ctx->num_sms * 4u;
-    MCB_TRY(ctx->reserve(m->cc_wn, sizeof(double) * ((size_t)grid + 2)));
+    MCB_TRY(ctx->reserve(m->cc_wn, sizeof(double) * ((size_t)grid + 2 + 3)));
     winding_args_t a;
     a.xyz = m->d_xyz;
     a.frame = m->frame;

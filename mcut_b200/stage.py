@@ -354,6 +354,38 @@ def intersect_stage(ctx: Context, src, cut, flags: int, gp_constant: float = 1e-
     return out
 
 
+INTERSECTION_TYPE_STANDARD, INTERSECTION_TYPE_INSIDE_CUTMESH, INTERSECTION_TYPE_INSIDE_SOURCEMESH, INTERSECTION_TYPE_NONE = 0, 2, 4, 8
+
+
+def intersection_type(ctx: Context, src, cut, flags: int, gp_constant: float = 1e-4) -> int:
+    """What MC_DISPATCH_INCLUDE_INTERSECTION_TYPE reports for one kernel invocation: STANDARD when the narrowphase finds
+    intersection points (the reference decides that later, from the number of connected components: preproc.cpp:3693-3725),
+    otherwise the verdict of check_and_store_input_mesh_intersection_type (mcb200_intersection_type_without_cut)."""
+    sx, sf, ss = src
+    cx, cf, cs = cut
+    com, shift, sbb, cbb = vertex_parameters(sx, cx)
+    eps = cut_bbox_eps(cbb, gp_constant, bool(flags & MC_DISPATCH_ENFORCE_GENERAL_POSITION_ABSOLUTE))
+    ms, mc = Mesh(ctx, sx, sf, ss), Mesh(ctx, cx, cf, cs)
+    ms.set_frame(com, shift)
+    mc.set_frame(com, shift)
+    ms.build(0.0)
+    mc.build(eps)
+    res = Result(ctx)
+    ctx.check(ctx.L.mcb200_bvh_intersect(ctx.h, ms.h, mc.h, res.h))
+    soup = Soup(ctx, ms, mc)
+    ctx.check(ctx.L.mcb200_narrowphase(ctx.h, soup.h, ms.h, mc.h, res.h, 0))
+    c = res.counts()
+    if int(c.status) == STATUS_SUCCESS and int(c.n_records) > 0:
+        out = INTERSECTION_TYPE_STANDARD
+    else:
+        t = C.c_uint32(0)
+        ctx.check(ctx.L.mcb200_intersection_type_without_cut(ctx.h, ms.h, mc.h, C.byref(t)))
+        out = int(t.value)
+    for o in (soup, res, ms, mc):
+        o.free()
+    return out
+
+
 def intersect_stage_host(ctx: Context, src, cut, flags: int = 0, gp_constant: float = 1e-4, perturbation=None, soup_ids_host=None,
                          log_tests: bool = False, res: "Result" = None, params=None, src_resident: bool = False,
                          cut_resident: bool = False) -> Dict[str, object]:

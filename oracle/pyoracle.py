@@ -398,3 +398,47 @@ def intersect_stage(src, cut, flags: int, gp_constant: float = 1e-4, perturbatio
     nar.update({"com": com, "shift": shift, "eps": eps, "src_bboxes": sb, "cut_bboxes": cb, "src_root": sroot,
                 "cut_root": croot, "pairs": pairs, "bvh_tests": ntests, "soup": soup, "src_xyz": sxi, "cut_xyz": cxi})
     return nar
+
+
+INTERSECTION_TYPE_STANDARD, INTERSECTION_TYPE_INSIDE_CUTMESH, INTERSECTION_TYPE_INSIDE_SOURCEMESH, INTERSECTION_TYPE_NONE = 0, 2, 4, 8
+
+
+def intersection_type_without_cut(src_xyz, src_off, src_vtx, cut_xyz, cut_off, cut_vtx, src_root, cut_root) -> int:
+    """check_and_store_input_mesh_intersection_type(), preproc.cpp:1999-2122, on internal coordinates: watertightness
+    (mesh_is_closed, :1957-1990), closed-interval overlap of the mesh AABBs (math.h:931-941), winding number of a first
+    vertex (getWindingNumber, :1907-1955; eps 1e-7)."""
+    sm_closed = validate(src_xyz.shape[0], src_off, src_vtx)[4] == 0
+    cm_closed = validate(cut_xyz.shape[0], cut_off, cut_vtx)[4] == 0
+    meet = all(not (src_root[j] > cut_root[3 + j] or cut_root[j] > src_root[3 + j]) for j in range(3))
+    if (not sm_closed and not cm_closed) or not meet:
+        return INTERSECTION_TYPE_NONE
+    meshes = {"s": (src_xyz, src_off, src_vtx), "c": (cut_xyz, cut_off, cut_vtx)}
+
+    def inside(point, mesh):
+        x, off, vtx = meshes[mesh]
+        return abs(1.0 - winding_number(x, off, vtx, point)) < 1e-7
+
+    if sm_closed and cm_closed:
+        def diag2(b):
+            x, y, z = b[3] - b[0], b[4] - b[1], b[5] - b[2]
+            return 0.0 + x * x + y * y + z * z
+        sm_larger = diag2(src_root) > diag2(cut_root)
+        a, b = ("s", "c") if sm_larger else ("c", "s")
+        if inside(meshes[b][0][0], a):
+            return INTERSECTION_TYPE_INSIDE_SOURCEMESH if sm_larger else INTERSECTION_TYPE_INSIDE_CUTMESH
+        if inside(src_xyz[0], b):  # the reference takes the SOURCE mesh's first vertex here whichever mesh is "A" (:2053)
+            return INTERSECTION_TYPE_INSIDE_CUTMESH if sm_larger else INTERSECTION_TYPE_INSIDE_SOURCEMESH
+        return INTERSECTION_TYPE_NONE
+    if sm_closed:
+        return INTERSECTION_TYPE_INSIDE_SOURCEMESH if inside(cut_xyz[0], "s") else INTERSECTION_TYPE_NONE
+    return INTERSECTION_TYPE_INSIDE_CUTMESH if inside(src_xyz[0], "c") else INTERSECTION_TYPE_NONE
+
+
+def intersection_type(src, cut, flags: int) -> int:
+    """STANDARD when the narrowphase of this invocation finds intersection points, else the verdict above."""
+    r = intersect_stage(src, cut, flags)
+    if r["status"] == 0 and len(r["records"]) > 0:
+        return INTERSECTION_TYPE_STANDARD
+    soff, coff = face_offsets(src[1], src[2]), face_offsets(cut[1], cut[2])
+    return intersection_type_without_cut(r["src_xyz"], soff, np.ascontiguousarray(src[1]), r["cut_xyz"], coff,
+                                         np.ascontiguousarray(cut[1]), r["src_root"], r["cut_root"])

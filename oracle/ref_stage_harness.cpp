@@ -576,6 +576,13 @@ int main(int argc, char** argv)
         if (rep == repeat - 1) {
             mcb::put_scalar<int32_t>(g.out, "mcDispatch_result", (int32_t)err);
             mcb::put_scalar<double>(g.out, "mcDispatch_ms", std::chrono::duration<double, std::milli>(t1 - t0).count());
+            {
+                // MC_DISPATCH_INCLUDE_INTERSECTION_TYPE: what check_and_store_input_mesh_intersection_type() decided
+                McDispatchIntersectionType it = MC_DISPATCH_INTERSECTION_TYPE_MAX_ENUM;
+                if (mcGetInfo(ctx, MC_CONTEXT_DISPATCH_INTERSECTION_TYPE, sizeof(it), &it, NULL) != MC_NO_ERROR)
+                    it = MC_DISPATCH_INTERSECTION_TYPE_MAX_ENUM;
+                mcb::put_scalar<uint32_t>(g.out, "intersection_type", (uint32_t)it);
+            }
             if (want_cc && !g.abort_after_narrowphase) query_ccs(ctx, g.out);
         }
         mcReleaseContext(ctx);

@@ -17,7 +17,7 @@ Two kinds of files are written next to this script:
   corpus/bench_NNN.npz  the same record for pair NNN of the reference's own regression corpus
                         (tests/meshes/benchmarks/{src,cut}-meshNNN.off, run by tests/source/benchmark.cpp), input arrays included
 
-Run:  python tests/golden/make_golden.py [--corpus-only | --only=case,case]
+Run:  python tests/golden/make_golden.py [--corpus-only | --only=case,case | --itype-only]
 """
 from __future__ import annotations
 
@@ -389,13 +389,32 @@ def write_corpus(td):
               f"tests0={fx['d0_test_edge'].size} result={int(fx['mcDispatch_result'][0])} ccs={fx['cc_type'].size}")
 
 
+def write_itype(td):
+    """intersection_type.npz: what the reference reports through MC_CONTEXT_DISPATCH_INTERSECTION_TYPE for tests/itype_cases.py"""
+    import itype_cases
+    names, vals, rcs = [], [], []
+    for name, (src, cut, flags, _) in itype_cases.CASES.items():
+        o = run_harness(src, cut, flags, td, "itype", extra=["--no-events"])
+        names.append(name)
+        vals.append(int(o["intersection_type"][0]))
+        rcs.append(int(o["mcDispatch_result"][0]))
+        print(f"intersection type {name}: {vals[-1]} (mcDispatch {rcs[-1]})")
+    np.savez_compressed(os.path.join(HERE, "intersection_type.npz"), names=np.array(names), types=np.array(vals, dtype=np.uint32),
+                        results=np.array(rcs, dtype=np.int32))
+
+
 def main():
+    if "--itype-only" in sys.argv:
+        with tempfile.TemporaryDirectory() as td:
+            write_itype(td)
+        return
     if not po.ref_available():
         raise SystemExit("oracle/_ref is missing: run `make -C oracle ref` where /root/reference exists")
     corpus_only = "--corpus-only" in sys.argv
     if corpus_only:
         with tempfile.TemporaryDirectory() as td:
             write_corpus(td)
+        write_itype(td)
         return
     only = [a.split("=", 1)[1].split(",") for a in sys.argv if a.startswith("--only=")]
     if only:
@@ -418,6 +437,7 @@ def main():
             print(f"stage_{name}.npz: dispatches={int(fx['n_dispatch'][0])} pairs={fx['pairs'].size} "
                   f"tests0={fx['d0_test_edge'].size} result={int(fx['mcDispatch_result'][0])} ccs={fx['cc_type'].size}")
         write_corpus(td)
+        write_itype(td)
 
 
 if __name__ == "__main__":

@@ -103,3 +103,13 @@ def test_device_winding_number_refuses_big_polygons(gpu_ctx):
     with pytest.raises(RuntimeError, match="four vertices"):
         m.winding_number([0.2, 0.2, 0.2])
     m.free()
+
+
+def test_device_intersection_type_equals_reference(gpu_ctx):
+    """mcb200_intersection_type_without_cut (+ STANDARD when the narrowphase finds points) on the inputs of the reference's
+    tests/source/intersectionType.cpp: the verdicts the unmodified reference reported (tests/golden/intersection_type.npz)."""
+    import itype_cases
+    from mcut_b200 import stage
+    from test_oracle_itype import REF
+    for name, (src, cut, flags, _) in itype_cases.CASES.items():
+        assert stage.intersection_type(gpu_ctx, src, cut, flags) == REF[name], name
