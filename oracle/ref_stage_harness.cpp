@@ -31,6 +31,7 @@
 #include <dlfcn.h>
 #include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "mcut/mcut.h"
@@ -515,7 +516,7 @@ int main(int argc, char** argv)
         std::fprintf(stderr, "usage: %s <in.mcb> <out.mcb> [--helpers N] [--no-events] [--abort-after-narrowphase] [--no-cc] [--repeat R] [--planar nx ny nz off]\n", argv[0]);
         return 2;
     }
-    int helpers = 0, repeat = 1;
+    int helpers = 0, repeat = 1, contexts = 1;
     bool want_cc = true, planar = false;
     double pn[3] = { 0, 0, 1 }, poff = 0.5;
     for (int i = 3; i < argc; ++i) {
@@ -525,6 +526,7 @@ int main(int argc, char** argv)
         else if (a == "--abort-after-narrowphase") g.abort_after_narrowphase = true;
         else if (a == "--no-cc") want_cc = false;
         else if (a == "--repeat" && i + 1 < argc) repeat = std::atoi(argv[++i]);
+        else if (a == "--contexts" && i + 1 < argc) contexts = std::atoi(argv[++i]);
         else if (a == "--planar" && i + 4 < argc) {
             planar = true;
             pn[0] = std::atof(argv[++i]);
@@ -542,6 +544,46 @@ int main(int argc, char** argv)
     const uint32_t nsv = (uint32_t)sx.dims[0];
     const uint32_t* ssz = in.count("src_sizes") ? in.at("src_sizes").as<uint32_t>() : NULL;
     const uint32_t nsf = ssz ? (uint32_t)in.at("src_sizes").count() : (uint32_t)(in.at("src_faces").count() / 3);
+
+    if (contexts > 1) {
+        // The MultipleContextsInParallel pattern (tutorials/MultipleContextsInParallel, tests/source/
+        // concurrentSynchronizedContexts.cpp): N contexts, each dispatching the same input from its own thread at the same
+        // time.  Every context must come back with the same connected components; the first one's are written out.
+        const mcb::array_t& cx = in.at("cut_xyz");
+        const uint32_t ncv = (uint32_t)cx.dims[0];
+        const uint32_t* csz = in.count("cut_sizes") ? in.at("cut_sizes").as<uint32_t>() : NULL;
+        const uint32_t ncf = csz ? (uint32_t)in.at("cut_sizes").count() : (uint32_t)(in.at("cut_faces").count() / 3);
+        std::vector<mcb::file_t> outs((size_t)contexts);
+        std::vector<int32_t> results((size_t)contexts, -1000);
+        std::vector<std::thread> th;
+        for (int c = 0; c < contexts; ++c)
+            th.emplace_back([&, c]() {
+                McContext ctx = MC_NULL_HANDLE;
+                if (mcCreateContextWithHelpers(&ctx, MC_NULL_HANDLE, (uint32_t)helpers) != MC_NO_ERROR) return;
+                const McResult err = mcDispatch(ctx, flags, sx.bytes.data(), in.at("src_faces").as<uint32_t>(), ssz, nsv, nsf,
+                    cx.bytes.data(), in.at("cut_faces").as<uint32_t>(), csz, ncv, ncf);
+                results[(size_t)c] = (int32_t)err;
+                if (err == MC_NO_ERROR) query_ccs(ctx, outs[(size_t)c]);
+                mcReleaseContext(ctx);
+            });
+        for (std::thread& t : th) t.join();
+        int identical = 1;
+        for (int c = 1; c < contexts; ++c) {
+            if (results[(size_t)c] != results[0] || outs[(size_t)c].size() != outs[0].size()) identical = 0;
+            for (const auto& kv : outs[0]) {
+                const auto it = outs[(size_t)c].find(kv.first);
+                if (it == outs[(size_t)c].end() || it->second.bytes != kv.second.bytes) identical = 0;
+            }
+        }
+        for (const auto& kv : outs[0]) g.out[kv.first] = kv.second;
+        mcb::put_scalar<int32_t>(g.out, "mcDispatch_result", results[0]);
+        mcb::put_scalar<int32_t>(g.out, "contexts", contexts);
+        mcb::put_scalar<int32_t>(g.out, "contexts_identical", identical);
+        mcb::put(g.out, "contexts_results", results);
+        mcb::write(argv[2], g.out);
+        std::fprintf(stderr, "harness: %d contexts in parallel, identical=%d, mcDispatch=%d\n", contexts, identical, results[0]);
+        return 0;
+    }
 
     int rc = 0;
     for (int rep = 0; rep < repeat; ++rep) {

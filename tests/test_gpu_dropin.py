@@ -278,3 +278,23 @@ def test_degenerate_inputs_are_rejected_like_the_reference(tmp_path, case):
     b = run_driver(str(tmp_path), "b200", src, cut, flags, [SHIM, NODUMP])
     c = run_driver(str(tmp_path), "hooked", src, cut, flags, [NODUMP], driver=HOOKED)
     assert int(a["mcDispatch_result"][0]) == int(b["mcDispatch_result"][0]) == int(c["mcDispatch_result"][0]) == -2, c["_stderr"]
+
+
+@needs_hooked
+@pytest.mark.parametrize("case", ["spheres_k16", "hello"])
+def test_contexts_in_parallel_through_the_drop_in(tmp_path, case):
+    """The MultipleContextsInParallel pattern (tutorials/MultipleContextsInParallel, tests/source/
+    concurrentSynchronizedContexts.cpp; BASELINE config 4): six MCUT contexts dispatch the same input from six threads at the
+    same time.  The adapter gives every API thread its own device context; all six must return the same components, equal
+    to the reference's."""
+    src, cut, flags = cases.ALL[case]()
+    extra = ["--contexts", "6"]
+    a = run_driver(str(tmp_path), "ref", src, cut, flags, [NODUMP])
+    b = run_driver(str(tmp_path), "b200", src, cut, flags, [SHIM, NODUMP], extra)
+    c = run_driver(str(tmp_path), "hooked", src, cut, flags, [NODUMP], extra, driver=HOOKED)
+    for o in (b, c):
+        assert int(o["contexts"][0]) == 6 and int(o["contexts_identical"][0]) == 1, o["_stderr"]
+        assert o["contexts_results"].tolist() == [0] * 6
+    for k in ("cc_type", "cc_attrs", "cc_nv", "cc_nf", "cc_vertices", "cc_faces", "cc_face_sizes"):
+        assert a[k].shape == b[k].shape and a[k].tobytes() == b[k].tobytes(), k
+    assert components_equivalent(a, c, 0.0)
