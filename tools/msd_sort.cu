@@ -2,8 +2,9 @@
 // as planned in DESIGN.md §9 (a).  One unstable bucket scatter on the top 12 bits (no look-back, no ranking votes), then
 // one block per bucket sorts its keys in shared memory.  Stand-alone: generates cube-sphere-ordered keys like C2's,
 // checks the result against std::sort, prints the event time of every kernel next to a three-pass reference figure the
-// caller supplies by running tools/sort_phase.cu.  Written at the end of round 1 without GPU time left: compile-checked
-// only (nvcc, sm_100a) — measure before believing anything here.
+// caller supplies by running tools/sort_phase.cu.  Measured once on a B200 (1,003,686 keys): histogram 8-10 us, scan 7-8 us,
+// scatter 12.3 us, bitonic bucket sort 182 us (result correct) against 3 x 25 us for three one-sweep passes: the scatter
+// is worth having, the bitonic network is not - a counting sort per bucket is the next thing to try.
 // build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -o tools/msd_sort.bin tools/msd_sort.cu
 #include <algorithm>
 #include <cmath>
