@@ -6,6 +6,7 @@
 // scatter 12.3 us, bitonic bucket sort 182 us (result correct) against 3 x 25 us for three one-sweep passes: the scatter
 // is worth having, the bitonic network is not - a counting sort per bucket is the next thing to try.
 // build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -o tools/msd_sort.bin tools/msd_sort.cu
+// run:   tools/msd_sort.bin [k = 409] [1 = counting bucket sort (k_local_count, not measured yet) instead of the bitonic one]
 #include <algorithm>
 #include <cmath>
 #include <cstdint>
@@ -140,6 +141,56 @@ __global__ void __launch_bounds__(THREADS) k_local(const uint32_t* __restrict__ 
     }
 }
 
+// ---- K4': one block per bucket, counting sort on the 12 low bits.  After the bucket scatter nothing needs to be stable any
+// more (keys that agree in all 24 bits may come out in any order), so the slot inside a bin is just the return value of a
+// shared-memory atomicAdd: no ballots, no network.  NOT MEASURED YET (written after the GPU budget of round 1 was spent). ----
+__global__ void __launch_bounds__(THREADS) k_local_count(const uint32_t* __restrict__ keys_in, const uint32_t* __restrict__ vals_in,
+    const unsigned* __restrict__ start, uint32_t* __restrict__ keys_out, uint32_t* __restrict__ vals_out)
+{
+    constexpr int LB = 1 << LOW_BITS, PER = LB / THREADS; // 4096 bins, 16 per thread
+    __shared__ unsigned s_bin[LB];
+    __shared__ unsigned s_warp[THREADS / 32];
+    const unsigned lane = threadIdx.x & 31u, w = threadIdx.x >> 5;
+    for (unsigned b = blockIdx.x; b < (unsigned)NB; b += gridDim.x) {
+        const unsigned lo = start[b], cnt = start[b + 1] - lo;
+        if (cnt == 0) continue;
+        for (int i = threadIdx.x; i < LB; i += THREADS) s_bin[i] = 0u;
+        __syncthreads();
+        for (unsigned i = threadIdx.x; i < cnt; i += THREADS) atomicAdd(&s_bin[keys_in[lo + i] & (LB - 1)], 1u);
+        __syncthreads();
+        // exclusive scan over the bins: thread t owns bins [16 t, 16 t + 16)
+        unsigned c[PER], sum = 0;
+#pragma unroll
+        for (int k = 0; k < PER; ++k) {
+            c[k] = s_bin[threadIdx.x * PER + k];
+            sum += c[k];
+        }
+        unsigned inc = sum;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned v = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= (unsigned)o) inc += v;
+        }
+        if (lane == 31) s_warp[w] = inc;
+        __syncthreads();
+        unsigned run = inc - sum;
+        for (unsigned i = 0; i < w; ++i) run += s_warp[i];
+#pragma unroll
+        for (int k = 0; k < PER; ++k) {
+            s_bin[threadIdx.x * PER + k] = run; // the bin's cursor
+            run += c[k];
+        }
+        __syncthreads();
+        for (unsigned i = threadIdx.x; i < cnt; i += THREADS) {
+            const uint32_t key = keys_in[lo + i];
+            const unsigned dst = lo + atomicAdd(&s_bin[key & (LB - 1)], 1u);
+            keys_out[dst] = key;
+            vals_out[dst] = vals_in[lo + i];
+        }
+        __syncthreads();
+    }
+}
+
 static uint32_t spread8(uint32_t v)
 {
     v = (v | (v << 16)) & 0x030000FFu;
@@ -152,6 +203,7 @@ static uint32_t spread8(uint32_t v)
 int main(int argc, char** argv)
 {
     const int k = argc > 1 ? atoi(argv[1]) : 409; // 6 k^2 keys, cube-sphere order (C2 has 1,002,252 triangles)
+    const bool counting = argc > 2 && atoi(argv[2]) != 0; // second argument 1: the counting bucket sort instead of the bitonic one
     std::vector<uint32_t> h;
     h.reserve(6 * (size_t)k * k);
     for (int f = 0; f < 6; ++f)
@@ -193,7 +245,10 @@ int main(int argc, char** argv)
         cudaEventRecord(ev[2]);
         k_scatter<<<tiles, THREADS>>>(kin, n, cursor, kmid, vmid);
         cudaEventRecord(ev[3]);
-        k_local<<<sms * 8, THREADS>>>(kmid, vmid, start, kout, vout, misc + 1);
+        if (counting)
+            k_local_count<<<sms * 8, THREADS>>>(kmid, vmid, start, kout, vout);
+        else
+            k_local<<<sms * 8, THREADS>>>(kmid, vmid, start, kout, vout, misc + 1);
         cudaEventRecord(ev[4]);
         cudaDeviceSynchronize();
         float t[4];
