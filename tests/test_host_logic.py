@@ -34,6 +34,20 @@ def test_frame_eps_and_soup_ids_match_reference(stage, oracle, case):
     assert beq(fv, fx["ps_face_vtx"]) and beq(fe, fx["ps_face_edges"])
 
 
+def test_frame_eps_and_soup_ids_match_reference_on_the_regression_corpus(stage, oracle):
+    """The same on the 61 pairs of the reference's regression corpus (polygons of up to 32 vertices, open meshes)."""
+    from golden_util import CORPUS_CASES, load_corpus
+    for pair in CORPUS_CASES:
+        fx, (sx, sf, ss), (cx, cf, cs), flags = load_corpus(pair)
+        com, shift, sbb, cbb = stage.vertex_parameters(sx, cx)
+        assert beq(com, fx["com"]) and beq(shift, fx["shift"]), pair
+        assert stage.cut_bbox_eps(cbb, 1e-4, False) == float(fx["eps"][0]), pair
+        soff, coff = oracle.face_offsets(sf, ss), oracle.face_offsets(cf, cs)
+        fv, fe, ev, ef = stage.soup_ids(sx.shape[0], soff, np.ascontiguousarray(sf), coff, np.ascontiguousarray(cf))
+        assert beq(np.concatenate([ev, ef], 1), fx["ps_edges"]), pair
+        assert beq(fv, fx["ps_face_vtx"]) and beq(fe, fx["ps_face_edges"]), pair
+
+
 def test_soup_ids_reject_bad_winding(stage):
     from mcut_b200.stage import Mcb200Error
     # two triangles sharing an edge in the SAME direction (inconsistent winding): hmesh.cpp:612-628 refuses the face
