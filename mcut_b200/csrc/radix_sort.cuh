@@ -152,6 +152,7 @@ __device__ __forceinline__ unsigned block_exclusive_scan(unsigned v, unsigned* s
     return base + inc - v;
 }
 
+// Per-phase clocks of a pass (thread 0 of every block), compiled in only by tools/sort_phase.cu (-DMCB_SORT_PROFILE).
 #ifdef MCB_SORT_PROFILE
 __device__ unsigned long long g_sort_phase[8];
 #define MCB_PHASE(i)                                                                                                            \
