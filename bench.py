@@ -59,7 +59,10 @@ def workload(name: str):
     if name == "c2small":
         return meshgen.c2_two_spheres(k=92), "C2-small: two cube-spheres, 101,568 triangles each (smoke size)"
     if name == "c5":
-        return meshgen.c5_near_coplanar(k=409), "C5: two near-coplanar cube-spheres, 2,007,372 triangles each"
+        return meshgen.c5_coplanar_regions(k=409), ("C5: dense overlap of two cube-spheres, 2,007,372 triangles each, with near-coplanar "
+                                                    "regions (1,037,662 tests need the exact orient3d stages)")
+    if name == "c5dense":
+        return meshgen.c5_near_coplanar(k=409), "C5-dense: SURVEY's original recipe (dense overlap, no exact tests), 2,007,372 triangles each"
     if name == "c3":
         tri = np.array([[-900.0, -850.0, -4.1], [1400.0, -700.0, 3.3], [150.0, 1600.0, 1.7]])
         cut = (tri, np.array([0, 1, 2], dtype=np.uint32), None)

@@ -234,7 +234,10 @@ int mcb200_intersect_stage(mcb200_ctx* ctx, mcb200_mesh* src, mcb200_mesh* cut, 
  * are reused from call to call.  soup == NULL: the polygon soup is numbered on the device (same ids as mcb200_soup_ids:
  * an edge's id is the rank of its first halfedge in add_face order, hmesh.cpp:406-651), nothing but the two meshes
  * travels; a non-manifold edge or inconsistent winding is then reported by mcb200_result_counts as
- * MCB200_ERR_NON_MANIFOLD. */
+ * MCB200_ERR_NON_MANIFOLD.
+ * LIFETIME (the one exception to "borrowed for the duration of the call"): the call returns with the uploads still in
+ * flight, so the host arrays must stay valid and unchanged until the next synchronising call on the context
+ * (mcb200_result_counts, any mcb200_result_read_*, mcb200_ctx_sync) has returned. */
 typedef struct mcb200_host_mesh {
     int is_float; /* MC_DISPATCH_VERTEX_ARRAY_FLOAT */
     const void* xyz; /* [nv*3] */

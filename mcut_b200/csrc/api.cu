@@ -619,6 +619,16 @@ int mcb200_soup_create(mcb200_ctx* ctx, uint32_t nsf, uint32_t ncf, uint32_t nh,
     if (!ctx || !out) return MCB200_ERR_INVALID;
     *out = nullptr;
     if (!face_vtx || !face_edge || !edge_f || nsf == 0 || ncf == 0) MCB_FAIL(ctx, MCB200_ERR_INVALID, "soup_create: NULL array or empty mesh");
+    {
+        // the narrowphase indexes face boxes by edge_f and edge_f by face_edge: an id out of range would be an illegal
+        // address on the device (and poison the context), so it is refused here.  edge_f[2e] (the face of h0) may be
+        // MCB200_NULL for a border edge of a repartitioned mesh: the h1 face then owns the edge's tests.
+        const uint32_t nf = nsf + ncf;
+        uint32_t bad = 0;
+        for (size_t i = 0; i < (size_t)nh; ++i) bad |= (face_edge[i] >= ne) ? 1u : 0u;
+        for (size_t i = 0; i < 2 * (size_t)ne; ++i) bad |= (edge_f[i] >= nf && edge_f[i] != MCB200_NULL) ? 1u : 0u;
+        if (bad) MCB_FAIL(ctx, MCB200_ERR_INVALID, "soup_create: an edge id in face_edge or a face id in edge_f is out of range");
+    }
     MCB_CUDA(ctx, cudaSetDevice(ctx->device));
     mcb200_soup* s = new mcb200_soup();
     s->nsf = nsf;

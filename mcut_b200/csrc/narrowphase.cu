@@ -321,7 +321,7 @@ __device__ __forceinline__ bool setup_test(const narrow_args_t& a, uint32_t s, u
     const uint2 ef = pre_ef ? pre_ef[slot] : __ldg(reinterpret_cast<const uint2*>(a.edge_f) + edge);
     const bool is_h0 = (ef.x == own_face);
     const double* tbox = edge_from_src ? cbox : sbox; // box of the tested face
-    if (!is_h0) {
+    if (!is_h0 && ef.x != MCB200_NULL) { // (an edge whose h0 has no face — a border after a repartition — is owned by the h1 face)
         // the face of h0 owns this test whenever it is paired with the tested face too
         double ob[6];
         load_box(face_box_ptr(a, ef.x), ob);

@@ -43,6 +43,16 @@ __device__ __forceinline__ uint32_t uf_find(uint32_t* label, uint32_t x)
     }
 }
 
+// read-only walk to the root (no path halving): used once hooking is over, when other threads finalise labels concurrently
+__device__ __forceinline__ uint32_t uf_root(const uint32_t* label, uint32_t x)
+{
+    for (;;) {
+        const uint32_t p = *reinterpret_cast<const volatile uint32_t*>(label + x);
+        if (p == x) return x;
+        x = p;
+    }
+}
+
 __device__ __forceinline__ void uf_union(uint32_t* label, uint32_t a, uint32_t b)
 {
     for (;;) {
@@ -117,7 +127,10 @@ __global__ void __launch_bounds__(VBLOCK) k_cc_flatten(validate_args_t a)
     const uint32_t v = blockIdx.x * VBLOCK + threadIdx.x;
     unsigned is_root = 0;
     if (v < a.nv) {
-        const uint32_t r = uf_find(a.label, v);
+        // Read-only find: a halving write from a concurrent walker could otherwise land AFTER another thread's final store
+        // and put a non-root ancestor back into its label.  The only stores of this kernel write a vertex's own root into
+        // its own slot, which keeps every path valid (and only shortens it) for the walkers still under way.
+        const uint32_t r = uf_root(a.label, v);
         is_root = (r == v) ? 1u : 0u;
         if (!is_root) a.label[v] = r; // roots keep label[v] == v; nobody hooks any more, so this is final
     }

@@ -57,11 +57,12 @@ def rot_axis(axis, a: float) -> np.ndarray:
 # ----------------------------------------------------------------------------------------------
 # cube-sphere: each cube face a k x k quad grid split into 2k^2 triangles; 12k^2 tris, 6k^2+2 verts
 # ----------------------------------------------------------------------------------------------
-def cube_sphere_dirs(k: int) -> Tuple[np.ndarray, np.ndarray]:
-    """Unit directions + triangle indices of a cube-sphere with k subdivisions per cube edge."""
+def cube_sphere_grid(k: int) -> Tuple[np.ndarray, np.ndarray, np.ndarray]:
+    """Unit directions, triangle indices and the per-cube-face vertex-id grids ``vid[6, k+1, k+1]`` of a cube-sphere
+    with k subdivisions per cube edge.  Cell (f, i, j) holds triangles 2(f k^2 + i k + j) and +1:
+    (v00, v10, v11) and (v00, v11, v01) with vAB = vid[f, i+A, j+B]."""
     n = k + 1
     # integer lattice points on the surface of the cube [0,k]^3, welded by a dict-free numpy unique
-    faces_pts = []
     lin = np.arange(n, dtype=np.int64)
     a, b = np.meshgrid(lin, lin, indexing="ij")
     a = a.ravel()
@@ -105,7 +106,13 @@ def cube_sphere_dirs(k: int) -> Tuple[np.ndarray, np.ndarray]:
     # tan-warp for more uniform triangles, then normalise
     c = np.tan(c * (math.pi / 4.0))
     d = c / np.linalg.norm(c, axis=1, keepdims=True)
-    return d, tris.astype(np.uint32)
+    return d, tris.astype(np.uint32), vid.reshape(6, n, n)
+
+
+def cube_sphere_dirs(k: int) -> Tuple[np.ndarray, np.ndarray]:
+    """Unit directions + triangle indices of a cube-sphere with k subdivisions per cube edge."""
+    d, tris, _ = cube_sphere_grid(k)
+    return d, tris
 
 
 def cube_sphere(k: int, radius: float = 20.0, rotation: Optional[np.ndarray] = None,
@@ -134,8 +141,9 @@ def _sph_field(d: np.ndarray) -> np.ndarray:
 
 def c5_near_coplanar(k: int = 409, radius: float = 20.0, amp: float = 1e-3, noise: float = 1e-9,
                      seed: int = 77) -> Tuple[Mesh, Mesh, int]:
-    """C5: two cube-spheres, B = A rotated by 1e-3 rad and displaced radially by a shallow sign-changing
-    field + 1e-9-scale white noise: long shallow-angle crossings that stress the exact orient3d fallback."""
+    """Round-1 C5 recipe (SURVEY §8-d as written): dense overlap, but NO test reaches the exact stages — the stage-A
+    filter is relative to the permanent and only fails within ~1e-15 of a plane.  Kept as a dense-overlap case; the
+    BASELINE config 5 workload is `c5_coplanar_regions`."""
     a = cube_sphere(k, radius)
     d, _ = cube_sphere_dirs(k)
     rot = rot_axis((1.0, 2.0, 3.0), 1e-3)
@@ -144,6 +152,159 @@ def c5_near_coplanar(k: int = 409, radius: float = 20.0, amp: float = 1e-3, nois
     radial = amp * _sph_field(d) + noise * u
     b = cube_sphere(k, radius, rotation=rot, radial=radial)
     return a, b, MC_DISPATCH_VERTEX_ARRAY_DOUBLE | MC_DISPATCH_ENFORCE_GENERAL_POSITION
+
+
+LATTICE_BITS = 47  # coordinates of the C5 meshes are multiples of 2^-47 (see c5_coplanar_regions)
+
+
+def _snap(x: np.ndarray) -> np.ndarray:
+    return np.round(x * float(1 << LATTICE_BITS)) / float(1 << LATTICE_BITS)
+
+
+def raycast_cube_sphere(k: int, a_xyz: np.ndarray, vid: np.ndarray, d: np.ndarray):
+    """Where the ray from the origin along unit direction d[i] meets the piecewise-planar surface of the cube-sphere
+    (a_xyz, vid) centred at the origin: returns (points, ok, tri) with tri[i] = the three vertex ids of the hit triangle.
+    The triangle is found analytically (cube face -> inverse tan-warp -> grid cell -> which of the cell's two triangles);
+    ok is False where neither triangle of the cell holds the hit well inside (the ray passes close to a mesh edge)."""
+    ax = np.argmax(np.abs(d), axis=1)
+    sgn = np.sign(d[np.arange(d.shape[0]), ax])
+    # cube-face frames exactly as cube_sphere_grid lays them out: on face f the grid coordinates (i, j) run along axes (p, q)
+    face = np.where(sgn > 0, ax * 2, ax * 2 + 1)
+    pq = {0: (1, 2), 1: (2, 1), 2: (2, 0), 3: (0, 2), 4: (0, 1), 5: (1, 0)}
+    out = np.zeros_like(d)
+    ok = np.zeros(d.shape[0], dtype=bool)
+    tri = np.zeros((d.shape[0], 3), dtype=np.int64)
+    for f in range(6):
+        m = np.nonzero(face == f)[0]
+        if m.size == 0:
+            continue
+        p_ax, q_ax = pq[f]
+        major = np.abs(d[m, f // 2])
+        s_p = np.arctan(d[m, p_ax] / major) / (math.pi / 4.0)
+        s_q = np.arctan(d[m, q_ax] / major) / (math.pi / 4.0)
+        ci = np.clip(np.floor((s_p + 1.0) * 0.5 * k).astype(np.int64), 0, k - 1)
+        cj = np.clip(np.floor((s_q + 1.0) * 0.5 * k).astype(np.int64), 0, k - 1)
+        i00, i10, i11, i01 = vid[f, ci, cj], vid[f, ci + 1, cj], vid[f, ci + 1, cj + 1], vid[f, ci, cj + 1]
+        dd = d[m]
+        done = np.zeros(m.size, dtype=bool)
+        res = np.zeros((m.size, 3))
+        rtri = np.zeros((m.size, 3), dtype=np.int64)
+        for (j0, j1, j2) in ((i00, i10, i11), (i00, i11, i01)):
+            t0, t1, t2 = a_xyz[j0], a_xyz[j1], a_xyz[j2]
+            nrm = np.cross(t1 - t0, t2 - t0)
+            t = np.einsum("ij,ij->i", nrm, t0) / np.einsum("ij,ij->i", nrm, dd)
+            hit = dd * t[:, None]
+
+            def side(p0, p1):
+                return np.einsum("ij,ij->i", np.cross(p1 - p0, hit - p0), nrm)
+            area2 = np.einsum("ij,ij->i", nrm, nrm)
+            w0, w1, w2 = side(t1, t2) / area2, side(t2, t0) / area2, side(t0, t1) / area2
+            inside = (w0 > 1e-4) & (w1 > 1e-4) & (w2 > 1e-4) & ~done
+            res[inside] = hit[inside]
+            rtri[inside] = np.stack([j0, j1, j2], 1)[inside]
+            done |= inside
+        out[m] = res
+        ok[m] = done
+        tri[m] = rtri
+    return out, ok, tri
+
+
+def _nearly_on_plane(p: np.ndarray, a0: np.ndarray, a1: np.ndarray, a2: np.ndarray, reach: int = 24) -> np.ndarray:
+    """For every row: a lattice point (multiples of 2^-LATTICE_BITS) next to p that lies extremely close to — but not on —
+    the plane of the lattice triangle (a0, a1, a2).  With N the (integer) plane normal, the signed distance of p + delta is
+    proportional to D0 + N.delta: for each of the (2 reach + 1)^2 offsets along the two axes where |N| is larger, the offset
+    along the third axis that brings the sum closest to zero is a rounding; the best non-zero sum over all of them wins.
+    Exact integer arithmetic has the last word (the point must not be ON the plane)."""
+    scale = 1 << LATTICE_BITS
+    to_int = lambda x: np.array([[int(v) for v in row] for row in np.round(x * float(scale))], dtype=object)  # noqa: E731
+    A0, A1, A2, Q0 = to_int(a0), to_int(a1), to_int(a2), to_int(p)
+    U, V = A1 - A0, A2 - A0
+    N = np.stack([U[:, 1] * V[:, 2] - U[:, 2] * V[:, 1], U[:, 2] * V[:, 0] - U[:, 0] * V[:, 2], U[:, 0] * V[:, 1] - U[:, 1] * V[:, 0]], 1)
+    W = Q0 - A0
+    D0 = N[:, 0] * W[:, 0] + N[:, 1] * W[:, 1] + N[:, 2] * W[:, 2]
+    S = np.array([max(abs(n[0]), abs(n[1]), abs(n[2])) for n in N], dtype=object)
+    nhat = np.array([[float(n[j]) / float(s) for j in range(3)] for n, s in zip(N, S)])
+    d0 = np.array([float(d) / float(s) for d, s in zip(D0, S)])
+    n_rows = p.shape[0]
+    order = np.argsort(-np.abs(nhat), axis=1)  # axes by decreasing |N|: the last one is the fine adjustment
+    rows = np.arange(n_rows)
+    n_a, n_b, n_c = nhat[rows, order[:, 0]], nhat[rows, order[:, 1]], nhat[rows, order[:, 2]]
+    r = np.arange(-reach, reach + 1, dtype=np.float64)
+    ia, ib = [g.ravel() for g in np.meshgrid(r, r, indexing="ij")]
+    best = np.zeros((n_rows, 3), dtype=np.int64)
+    for lo in range(0, n_rows, 4096):
+        hi = min(lo + 4096, n_rows)
+        w = d0[lo:hi, None] + n_a[lo:hi, None] * ia[None, :] + n_b[lo:hi, None] * ib[None, :]
+        nc = np.where(np.abs(n_c[lo:hi]) < 1e-6, 1e-6, n_c[lo:hi])[:, None]  # a normal (almost) along an axis: no fine adjustment
+        kc = np.clip(np.round(-w / nc), -200000.0, 200000.0)
+        res = np.abs(w + kc * n_c[lo:hi, None])
+        res[res < 1e-9] = np.inf  # would be (or be indistinguishable from) a point ON the plane: exactly zero determinant
+        pick = np.argmin(res, axis=1)
+        sel = np.arange(hi - lo)
+        best[np.arange(lo, hi), order[lo:hi, 0]] = ia[pick].astype(np.int64)
+        best[np.arange(lo, hi), order[lo:hi, 1]] = ib[pick].astype(np.int64)
+        best[np.arange(lo, hi), order[lo:hi, 2]] = kc[sel, pick].astype(np.int64)
+    D = D0 + N[:, 0] * best[:, 0] + N[:, 1] * best[:, 1] + N[:, 2] * best[:, 2]
+    assert all(int(v) != 0 for v in D), "a chosen lattice point lies exactly on its plane"
+    q = Q0 + best.astype(object)
+    return np.array([[float(int(v)) for v in row] for row in q]) / float(scale)
+
+
+def c5_coplanar_regions(k: int = 409, radius: float = 20.0, amp: float = 1e-3, noise: float = 1e-9, seed: int = 77,
+                        cap_cos: float = 0.93, touch: bool = False) -> Tuple[Mesh, Mesh, int]:
+    """BASELINE config 5: two ~2M-triangle noisy spheres in dense overlap with NEAR-COPLANAR REGIONS that defeat the
+    stage-A orient3d filter (shewchuk.c: the filter is RELATIVE, |det| <= 7.8e-16 * permanent: a point must lie within
+    ~1e-15 triangle sizes of a plane, so metre-scale noise never gets there).
+    A = cube-sphere.  B = A's topology rotated by 1e-3 rad about (1,2,3), radially displaced by a smooth sign-changing
+    field (amplitude `amp`) + white noise: shallow crossings everywhere.  Inside six spherical caps (cos to the cap axis >
+    cap_cos, ~20 % of the sphere) B is a re-triangulation of A's own piecewise-planar surface: each of its vertices is put
+    next to the plane of the A triangle under it, closer than the filter can resolve but never exactly on it.
+    What makes that survive the reference's re-centring x' = (x - com) + shift (preproc.cpp:124-176), whose rounding would
+    otherwise push every point ~1e-14 off its plane: ALL coordinates are multiples of 2^-47.  Then both additions round
+    to a grid the inputs already lie on, so within one binade of the intermediate and of the result they add the same
+    constant to every coordinate — an exact translation, and determinants keep their exact values.  The near-planar
+    vertex is the lattice point, among the 11^3 around the ray-cast hit, with the smallest non-zero exact determinant."""
+    flags = MC_DISPATCH_VERTEX_ARRAY_DOUBLE | MC_DISPATCH_ENFORCE_GENERAL_POSITION
+    # the exact-integer search takes ~25 s at k = 409: keep the arrays for later calls on the same machine (tests + bench)
+    cache = None
+    if k >= 128:
+        import os
+        import tempfile
+        cache = os.path.join(tempfile.gettempdir(), f"mcut_b200_c5_{k}_{radius!r}_{amp!r}_{noise!r}_{seed}_{cap_cos!r}_{int(touch)}_v2.npz")
+        if os.path.exists(cache):
+            try:
+                z = np.load(cache)
+                return (z["a"], z["f"], None), (z["b"], z["f"], None), flags
+            except Exception:
+                pass
+    d_a, tris, vid = cube_sphere_grid(k)
+    a_xyz = _snap(np.ascontiguousarray(d_a * radius))
+    rot = rot_axis((1.0, 2.0, 3.0), 1e-3)
+    d_b = d_a @ rot.T
+    rng = np.random.default_rng(seed)
+    u = rng.uniform(-1.0, 1.0, size=d_b.shape[0])
+    radial = amp * _sph_field(d_a) + noise * u
+    b_xyz = _snap(d_b * (radius * (1.0 + radial))[:, None])
+    axes = np.array([[1, 2, 2], [-2, 1, 2], [2, -2, 1], [-1, -2, -2], [2, -1, -2], [-2, 2, -1]], dtype=np.float64) / 3.0
+    in_cap = (d_b @ axes.T).max(axis=1) > cap_cos
+    idx = np.nonzero(in_cap)[0]
+    hit, ok, tri = raycast_cube_sphere(k, a_xyz, vid, d_b[idx])
+    idx, hit, tri = idx[ok], hit[ok], tri[ok]
+    b_xyz[idx] = _nearly_on_plane(hit, a_xyz[tri[:, 0]], a_xyz[tri[:, 1]], a_xyz[tri[:, 2]])
+    if touch:
+        # optional: ONE vertex of B exactly on a vertex of A — an exactly zero determinant, i.e. a general-position violation
+        # (status -4) on the unperturbed attempt, as any input with coincident geometry produces
+        b_xyz[idx[0]] = a_xyz[tri[0, 0]]
+    faces = np.ascontiguousarray(tris.ravel())
+    b_xyz = np.ascontiguousarray(b_xyz)
+    if cache:
+        try:
+            tmp = cache + f".{os.getpid()}.tmp.npz"
+            np.savez(tmp, a=a_xyz, b=b_xyz, f=faces)
+            os.replace(tmp, cache)
+        except Exception:
+            pass
+    return (a_xyz, faces, None), (b_xyz, faces, None), flags
 
 
 # ----------------------------------------------------------------------------------------------

@@ -78,6 +78,18 @@ def near_coplanar_small():
     return mg.c5_near_coplanar(k=10, radius=20.0, amp=1e-3, noise=1e-9, seed=77)
 
 
+def c5_regions_small():
+    """BASELINE config 5 in miniature: dense shallow overlap + regions where the cutter re-triangulates the source's own
+    surface to within the resolution of the stage-A orient3d filter (lattice coordinates, see meshgen.c5_coplanar_regions):
+    ~800 of the tests need the exact stages, with non-zero determinants."""
+    return mg.c5_coplanar_regions(k=12)
+
+
+def c5_regions_touch():
+    """The same with one exactly coincident vertex: general-position violation (status -4) on the unperturbed attempt."""
+    return mg.c5_coplanar_regions(k=12, touch=True)
+
+
 def _tilted_grids(tilt, n=12):
     """Two open triangle grids that are coplanar up to `tilt` rad, then put in a generic orientation so the
     orient3d determinant cancels: the stage-A filter fails on most tests (exact-expansion stress)."""
@@ -145,6 +157,8 @@ ALL = {
     "patch_vs_sphere": patch_vs_sphere,
     "terrain_plane": terrain_plane,
     "near_coplanar_small": near_coplanar_small,
+    "c5_regions_small": c5_regions_small,
+    "c5_regions_touch": c5_regions_touch,
     "float_spheres": float_spheres,
     "coplanar_rotated": coplanar_rotated,
     "near_coplanar_tilt": near_coplanar_tilt,

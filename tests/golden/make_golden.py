@@ -42,7 +42,7 @@ from ref_events import SoupIndex, decode_dispatch  # noqa: E402
 REFERENCE = os.environ.get("MCUT_REFERENCE", "/root/reference")
 CORPUS = range(0, 61)  # benchmark.cpp runs pairs 000..060
 STAGE_CASES = ["hello", "spheres_k8", "uv12", "ico_pair", "cube_cube_axis_aligned", "cube_cube_tris_offset", "patch_vs_sphere",
-               "terrain_plane", "float_spheres", "coplanar_rotated", "near_coplanar_tilt", "degenerate_edge_edge",
+               "terrain_plane", "float_spheres", "coplanar_rotated", "near_coplanar_tilt", "c5_regions_small", "degenerate_edge_edge",
                "degenerate_face_vertex", "degenerate_zero_area"]
 
 

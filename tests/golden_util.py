@@ -7,7 +7,7 @@ import numpy as np
 
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 STAGE_CASES = ["hello", "spheres_k8", "uv12", "ico_pair", "cube_cube_axis_aligned", "cube_cube_tris_offset", "patch_vs_sphere",
-               "terrain_plane", "float_spheres", "coplanar_rotated", "near_coplanar_tilt", "degenerate_edge_edge",
+               "terrain_plane", "float_spheres", "coplanar_rotated", "near_coplanar_tilt", "c5_regions_small", "degenerate_edge_edge",
                "degenerate_face_vertex", "degenerate_zero_area"]
 
 

@@ -49,10 +49,22 @@ def test_c4_small_pairs(oracle, gpu_ctx):
         compare(oracle, gpu_ctx, src, cut, flags)
 
 
-def test_c5_dense_overlap_2m(oracle, gpu_ctx):
-    src, cut, flags = mg.c5_near_coplanar(k=409)
+def test_c5_near_coplanar_regions_2m(oracle, gpu_ctx):
+    """BASELINE config 5 at full size (2 x 2,007,372 triangles): dense shallow overlap + regions where the cutter lies within
+    the resolution of the stage-A orient3d filter of the source's own faces.  More than a million tests go through the
+    exact-expansion kernel; pairs, every test count, every record (edge, face, point) equal the oracle bit for bit."""
+    src, cut, flags = mg.c5_coplanar_regions(k=409)
     ref, got = compare(oracle, gpu_ctx, src, cut, flags)
-    assert got["n_pairs"] > 500000
+    assert got["n_pairs"] == 21547246 and got["n_tests"] == 37823783
+    assert got["n_exact"] == 1037662 and got["n_exact"] >= 100000
+    assert got["status"] == 0 and got["n_records"] == 749808
+
+
+def test_c5_dense_overlap_without_exact_tests(oracle, gpu_ctx):
+    """SURVEY's original C5 recipe at a quarter of the size: the same dense overlap, no test reaches the exact stages."""
+    src, cut, flags = mg.c5_near_coplanar(k=204)
+    ref, got = compare(oracle, gpu_ctx, src, cut, flags)
+    assert got["n_pairs"] > 100000 and got["n_exact"] == 0
 
 
 def test_role_swap_gives_transposed_pairs(gpu_ctx):
