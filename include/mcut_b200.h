@@ -65,6 +65,16 @@ typedef struct mcb200_mesh mcb200_mesh; /* device-resident mesh (+ its face AABB
 typedef struct mcb200_soup mcb200_soup; /* device-resident polygon-soup topology of a (source, cut) pair */
 typedef struct mcb200_result mcb200_result; /* device-resident outputs of traversal + narrowphase */
 
+/* The order in which the reference registers intersection points (= how it numbers the intersection vertices of m0):
+ * the iteration order of its std::unordered_map<ed_t, ...> ps_edge_face_intersection_pairs (source/kernel.cpp:1779-1852) walked
+ * in parallel_for blocks (include/mcut/internal/tpool.h:354-472; kernel.cpp:2415-2868).  cand_faces = the polygon-soup ids of
+ * all faces that have a candidate partner, ASCENDING (the keys of ps_face_to_potentially_intersecting_others); face_off /
+ * face_edge as in mcb200_soup_ids (face_off == NULL: triangles); helper_threads = the dispatch's thread-pool size.
+ * rank[e] (e < ne) receives the position of edge e in that order, MCB200_NULL for edges of no candidate face.  Registry
+ * order = records sorted by (rank[edge], face). */
+int mcb200_reference_edge_rank(uint32_t n_cand_faces, const uint32_t* cand_faces, const uint32_t* face_off,
+    const uint32_t* face_edge, uint32_t ne, uint32_t helper_threads, uint32_t* rank);
+
 /* ---------------------------------------------------------------- context ---------------------------------- */
 int mcb200_device_count(void);
 /* stream == NULL: the context creates its own non-blocking stream.  Otherwise `stream` is a cudaStream_t the

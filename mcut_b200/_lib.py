@@ -61,6 +61,7 @@ SYMBOLS = {
     "mcb200_cut_bbox_eps": (C.c_double, [c_dp, C.c_double, C.c_int]),
     "mcb200_soup_ids": (C.c_int, [C.c_uint32, c_u32p, c_u32p, C.c_uint32, c_u32p, c_u32p, C.c_uint32, c_u32p, c_u32p, c_u32p,
                                   c_u32p, c_u32p]),
+    "mcb200_reference_edge_rank": (C.c_int, [C.c_uint32, c_u32p, c_u32p, c_u32p, C.c_uint32, C.c_uint32, c_u32p]),
     "mcb200_mesh_create": (C.c_int, [vp, C.c_int, vp, C.c_uint32, c_u32p, c_u32p, C.c_uint32, C.POINTER(vp)]),
     "mcb200_mesh_adopt_device": (C.c_int, [vp, C.c_int, vp, C.c_uint32, vp, vp, C.c_uint32, C.c_uint32, C.POINTER(vp)]),
     "mcb200_mesh_update_xyz": (C.c_int, [vp, vp, vp, C.c_uint32]),

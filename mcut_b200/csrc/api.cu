@@ -486,11 +486,12 @@ void mcb200_mesh_free(mcb200_ctx* ctx, mcb200_mesh* m)
     ctx->release(m->codes);
     ctx->release(m->sorted_codes);
     ctx->release(m->sorted_faces);
-    ctx->release(m->nodes);
-    ctx->release(m->parent);
+    ctx->release(m->wide);
+    ctx->release(m->sorted_bbox);
     ctx->release(m->flags);
     ctx->release(m->groups);
-    ctx->release(m->group_up);
+    ctx->release(m->group_box);
+    delete m->lv;
     for (dbuf* b : { &m->cc_label, &m->cc_id, &m->cc_vcount, &m->cc_fcount, &m->cc_fmap, &m->cc_info, &m->cc_wn }) ctx->release(*b);
     delete m;
 }
@@ -560,7 +561,7 @@ void mcb200_result_free(mcb200_ctx* ctx, mcb200_result* r)
 {
     if (!ctx || !r) return;
     cudaSetDevice(ctx->device);
-    dbuf* all[] = { &r->counters, &r->pairs, &r->pairs_a, &r->pairs_b, &r->live_groups, &r->cand_flag, &r->plane, &r->plane_mc, &r->exact_queue, &r->records, &r->rec_keys,
+    dbuf* all[] = { &r->counters, &r->pairs, &r->pairs_a, &r->pairs_b, &r->items, &r->cand_flag, &r->plane, &r->plane_mc, &r->exact_queue, &r->records, &r->rec_keys,
         &r->rec_idx, &r->records_sorted, &r->tests, &r->tests_sorted, &r->test_keys, &r->test_idx };
     for (dbuf* b : all) ctx->release(*b);
     delete r;
@@ -593,11 +594,6 @@ int mcb200_bvh_intersect(mcb200_ctx* ctx, const mcb200_mesh* src, const mcb200_m
     if (!ctx || !src || !cut || !res) return MCB200_ERR_INVALID;
     MCB_CUDA(ctx, cudaSetDevice(ctx->device));
     ctx->use_main();
-    {
-        // a mesh that so far only served as the query side of a stage call has no node records yet
-        const mcb200_mesh* t = (cut->nf > src->nf) ? src : cut;
-        if (t->built && !t->has_nodes) MCB_TRY(lbvh_build(ctx, const_cast<mcb200_mesh*>(t), t->eps, false));
-    }
     for (int attempt = 0; attempt < 2; ++attempt) {
         MCB_TRY(traverse_pairs(ctx, src, cut, res));
         MCB_TRY(sort_pairs(ctx, src, cut, res));
@@ -763,12 +759,10 @@ static int build_both_interleaved(mcb200_ctx* ctx, mcb200_mesh* src, mcb200_mesh
     std::vector<std::function<int()>> qa, qb;
     ctx->use_main();
     ctx->recording = &qa;
-    // the mesh with more faces is the traversal's query side (traverse.cu): it needs its groups, not its node records
-    const bool query_is_cut = cut->nf > src->nf;
-    int rc = lbvh_build(ctx, src, 0.0, !query_is_cut);
+    int rc = lbvh_build(ctx, src, 0.0);
     ctx->use_aux();
     ctx->recording = &qb;
-    if (!rc) rc = lbvh_build(ctx, cut, cut_eps, query_is_cut);
+    if (!rc) rc = lbvh_build(ctx, cut, cut_eps);
     ctx->recording = nullptr;
     ctx->use_main();
     for (size_t i = 0; !rc && (i < qa.size() || i < qb.size()); ++i) {
@@ -970,8 +964,7 @@ int mcb200_intersect_stage_host(mcb200_ctx* ctx, const mcb200_host_mesh* hsrc, c
     MCB_CUDA(ctx, cudaEventRecord(ctx->ev_fork, ctx->stream));
     MCB_CUDA(ctx, cudaStreamWaitEvent(ctx->aux, ctx->ev_fork, 0));
     MCB_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_up[0], 0));
-    const bool query_is_cut = cut->nf > src->nf; // the query side of the traversal needs groups only
-    rc = lbvh_build(ctx, src, 0.0, !query_is_cut);
+    rc = lbvh_build(ctx, src, 0.0);
     // the polygon soup needs the face arrays only: it is numbered on the lowest-priority lane while the cut mesh's
     // coordinates still travel, and gives way to the builds whenever they have blocks to place
     ctx->use_bg();
@@ -982,7 +975,7 @@ int mcb200_intersect_stage_host(mcb200_ctx* ctx, const mcb200_host_mesh* hsrc, c
     cudaEventRecord(ctx->ev_bg, ctx->bg);
     ctx->use_aux();
     cudaStreamWaitEvent(ctx->aux, ctx->ev_up[1], 0);
-    if (!rc) rc = lbvh_build(ctx, cut, cut_eps, query_is_cut);
+    if (!rc) rc = lbvh_build(ctx, cut, cut_eps);
     cudaEventRecord(ctx->ev_join, ctx->aux);
     ctx->use_main();
     cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0);
@@ -1050,12 +1043,12 @@ int mcb200_result_counts(mcb200_ctx* ctx, mcb200_result* res, mcb200_counts* out
         out->status = MCB200_STATUS_SUCCESS;
     if (h.soup_error)
         MCB_FAIL(ctx, MCB200_ERR_NON_MANIFOLD, "polygon-soup numbering: an edge is shared by three faces or by two faces wound the same way");
-    if (res->have_narrow && (h.n_records > res->cap_records || h.n_exact > res->cap_exact || (res->logged_tests && h.n_log > res->cap_tests))) {
+    if (res->have_narrow && (h.n_records > res->cap_records || h.n_queue > res->cap_exact || (res->logged_tests && h.n_log > res->cap_tests))) {
         // The narrowphase buffers are sized from the pair capacity (2 records, 6 queue entries per pair); an input that
         // needs more gets a pair capacity that provides it, and the caller runs the stage again — nothing is dropped silently.
         size_t need = res->cap_pairs;
         if (h.n_records > res->cap_records) need = std::max(need, (size_t)h.n_records / 2 + 1024);
-        if (h.n_exact > res->cap_exact || (res->logged_tests && h.n_log > res->cap_tests)) need = std::max(need, res->cap_pairs * 2);
+        if (h.n_queue > res->cap_exact || (res->logged_tests && h.n_log > res->cap_tests)) need = std::max(need, res->cap_pairs * 2);
         res->cap_pairs = need;
         res->h_valid = false;
         MCB_FAIL(ctx, MCB200_ERR_CAPACITY, "narrowphase buffer overflow: capacity has been raised, run the stage again");

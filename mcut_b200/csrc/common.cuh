@@ -6,6 +6,7 @@
 #include <cuda_runtime.h>
 
 #include <cfloat>
+#include <cstddef>
 #include <cmath>
 
 #include <cstdint>
@@ -180,41 +181,40 @@ struct mcb200_mesh {
     dbuf codes; // [nf] u32 Morton code by face (kept for parity reads)
     dbuf sorted_codes; // [nf] u32
     dbuf sorted_faces; // [nf] u32 (leaf -> face)
-    dbuf nodes; // [max(nf-1,1)] bvh_node_t (64 B)
-    dbuf parent; // [2nf-1] u32 parent of internal node i / leaf (nf-1+j)
-    dbuf flags; // [nf-1] u32 refit arrival counters
+    dbuf wide; // float [blocks][6][32]: the boxes of every level of the wide tree, level 0 (sorted leaves) first
+    dbuf sorted_bbox; // [nf][6] double: the exact face boxes in leaf order (what the traversal's decisive test reads)
+    dbuf flags; // u32 [4]: block-done ticket of k_leaves (+ spare words)
     dbuf groups; // [nf] uint2 query groups (first leaf, count) + u32 counter after them
-    dbuf group_up; // [<= nf] box + parent word of every group root (input of the atomic climb)
+    dbuf group_box; // [<= nf] union box of every group
+    struct wide_levels_t* lv = nullptr; // host copy of the level table (set by lbvh_build)
     // input validation products (validate.cu)
     dbuf cc_label, cc_id, cc_vcount, cc_fcount, cc_fmap, cc_info, cc_wn;
     bool validated = false;
     uint32_t n_components = 0;
     bool groups_valid = false;
-    bool has_nodes = false; // false after a query-only build: groups exist, node records do not
 };
 
-// One LBVH node: both children's boxes live in the parent, so one 64-byte record feeds a traversal step.  The boxes are
-// single precision, rounded OUTWARDS (min down, max up): inner nodes only prune, and a conservative box never prunes a
-// true overlap; the decisive leaf-level test uses the exact double face boxes.  A leaf child carries the FACE id.
-struct __align__(64) bvh_node_t {
-    float lbox[6]; // min xyz, max xyz of the left child
-    float rbox[6];
-    uint32_t left, right; // child ids; bit31 set => leaf, low bits = face id
-    uint32_t first, last; // leaf range covered (Karras)
+// The tree over the Morton-sorted leaves is IMPLICIT and 32-wide (the reference's OIBVH is implicit and binary,
+// bvh.cpp:444-493): level 0 = the sorted leaves, node i of level l covers nodes [32 i, 32 i + 32) of level l - 1, the top level
+// has at most 32 nodes.  Only boxes are stored — single precision, rounded OUTWARDS (inner levels only prune; the decisive
+// test uses the exact double face boxes) — in blocks of 32 boxes laid out [6][32], so that a warp testing the 32 children of
+// a node issues six fully coalesced 128-byte loads.  Unused slots hold an empty box (min = +FLT_MAX, max = -FLT_MAX).
+constexpr int MCB_MAX_LEVELS = 8;
+struct wide_levels_t {
+    const float* boxes; // all levels, level 0 first
+    uint32_t n[MCB_MAX_LEVELS]; // nodes per level; n[0] = faces
+    uint32_t off[MCB_MAX_LEVELS]; // first block of level l in `boxes` (in blocks of 32 boxes = 192 floats)
+    int top; // highest level (>= 1); n[top] <= 32
 };
-static_assert(sizeof(bvh_node_t) == 64, "bvh_node_t must be one 64-byte record");
+#define MCB_WBLOCK_FLOATS 192
 
-#define MCB_LEAF_BIT 0x80000000u
-
-// What a group root (a maximal treelet of <= 32 leaves) carries: its union box (conservative, single precision) and the
-// slot of its parent word.  Written by k_tree, read by the atomic climb and — as the query box of the group — by the
-// traversal.
-struct __align__(32) group_up_t {
+// Union box (conservative, single precision) of a query group: a maximal subtree of at most 32 leaves of the radix tree over the
+// sorted codes (lbvh.cu: k_leaves).
+struct __align__(32) group_box_t {
     float box[6];
-    uint32_t pw;
-    uint32_t pad;
+    uint32_t pad[2];
 };
-static_assert(sizeof(group_up_t) == 32, "group_up_t is one 32-byte sector");
+static_assert(sizeof(group_box_t) == 32, "group_box_t is one 32-byte sector");
 
 // conservative single-precision copy of a double box
 __device__ __forceinline__ void box_to_float(const double* b, float* f)
@@ -251,18 +251,20 @@ struct result_counters_t {
     unsigned int gp_violation;
     unsigned int bad_face; // min polygon-soup id of a degenerate candidate face, 0xFFFFFFFF if none
     unsigned int pair_overflow;
-    unsigned int work_counter; // dynamic work distribution (traversal groups)
-    unsigned int work_counter2;
+    unsigned int work_counter; // number of traversal work items (k_group_top)
     unsigned int soup_error; // device-side soup numbering: an edge with three faces or two faces wound the same way
     unsigned int soup_ne; // number of polygon-soup edges it found
-    unsigned int pad[5];
+    unsigned long long n_queue; // tests the filter kernel handed to the second kernel (stage-A failures + crossings)
+    unsigned int pad[4];
 };
+static_assert(offsetof(result_counters_t, n_queue) % 8 == 0, "n_queue is atomically incremented as a 64-bit word");
 
 struct mcb200_result {
     dbuf counters; // result_counters_t
     dbuf pairs; // u64 [cap_pairs], in the order the traversal emitted them (what the narrowphase consumes)
     dbuf pairs_a, pairs_b; // ping-pong buffers of the pair sort
-    dbuf live_groups; // u32 [query nf]: query groups that reach a leaf of the other tree (traverse.cu: k_group_filter)
+    dbuf items; // uint2 [cap_items]: (query group, node of the other tree's level S) pairs whose boxes overlap (traverse.cu: k_group_top)
+    size_t cap_items = 0;
     unsigned long long* pairs_sorted = nullptr; // ascending (src << 32 | cut): points into pairs_a or pairs_b
     size_t cap_pairs = 0;
     bool cand_flag_fresh = false; // candidate flags already cleared for the coming narrowphase

@@ -155,3 +155,71 @@ extern "C" int mcb200_soup_ids(uint32_t nsv, const uint32_t* src_off, const uint
         return MCB200_ERR_INVALID;
     return host_soup_ids(nsv, src_off, src_vtx, nsf, cut_off, cut_vtx, ncf, face_vtx, face_edge, edge_v, edge_f, ne);
 }
+
+// ---- the reference's registry order -------------------------------------------------------------------------------------
+// In which order does the reference register intersection points, i.e. how does it number the intersection vertices of
+// m0?  It is an accident of its containers, but everything downstream of the narrowphase — including which edges the
+// floating-polygon resolution computes its partition segment from (preproc.cpp:1000-1126) — follows that numbering, so a
+// drop-in has to reproduce it:
+//   * kernel.cpp:1781-1852 fills std::unordered_map<ed_t, ...> ps_edge_face_intersection_pairs: the candidate faces (keys of
+//     a std::map: ascending) are cut into blocks by parallel_for (tpool.h:354-392, :420-472: `helpers + 1` threads, at least
+//     1024 elements each); a block inserts the edges of its faces in first-seen order into a local map; the MASTER's
+//     block — the last one — becomes the map, the other blocks' edges are then inserted in block order;
+//   * kernel.cpp:2415-2672 walks that map in ITERATION order, again in blocks, and concatenates the per-block registries
+//     master block first (:2673-2868); an edge's faces are visited in ascending id.
+// The iteration order of a libstdc++ unordered_map is a function of the insertion sequence (identity hash of the
+// descriptor's 32-bit index, hmesh.h:628-634; the mapped type plays no part), so replaying the sequence into a map of
+// 32-bit keys built by the same toolchain yields the same order.  rank[e] = position of edge e in the registry order, or
+// MCB200_NULL for edges of no candidate face.
+#include <algorithm>
+#include <unordered_map>
+
+extern "C" int mcb200_reference_edge_rank(uint32_t n_cand_faces, const uint32_t* cand_faces, const uint32_t* face_off,
+    const uint32_t* face_edge, uint32_t ne, uint32_t helper_threads, uint32_t* rank)
+{
+    if ((n_cand_faces && !cand_faces) || !face_edge || (ne && !rank)) return MCB200_ERR_INVALID;
+    for (uint32_t e = 0; e < ne; ++e) rank[e] = MCB200_NULL;
+    if (n_cand_faces == 0) return 0;
+    for (uint32_t i = 1; i < n_cand_faces; ++i)
+        if (cand_faces[i] <= cand_faces[i - 1]) return MCB200_ERR_INVALID; // keys of a std::map
+    typedef std::unordered_map<uint32_t, char> edge_set_t;
+    const uint32_t available = helper_threads + 1u;
+    auto schedule = [&](uint32_t length, uint32_t& nthreads, uint32_t& block_size) { // get_scheduling_parameters, tpool.h:354-392
+        const uint32_t max_threads = (length + 1023u) / 1024u;
+        nthreads = std::min(available, max_threads);
+        block_size = length / nthreads;
+    };
+    auto block = [&](uint32_t a, uint32_t b) {
+        edge_set_t local;
+        for (uint32_t i = a; i < b; ++i) {
+            const uint32_t f = cand_faces[i];
+            const uint32_t h0 = face_off ? face_off[f] : 3u * f, h1 = face_off ? face_off[f + 1] : 3u * f + 3u;
+            for (uint32_t h = h0; h < h1; ++h) local[face_edge[h]];
+        }
+        return local;
+    };
+    uint32_t nthreads = 1, block_size = 0;
+    schedule(n_cand_faces, nthreads, block_size);
+    std::vector<edge_set_t> futures(nthreads - 1);
+    uint32_t block_start = 0;
+    for (uint32_t i = 0; i + 1 < nthreads; ++i) {
+        futures[i] = block(block_start, block_start + block_size);
+        block_start += block_size;
+    }
+    edge_set_t all = block(block_start, n_cand_faces);
+    for (const edge_set_t& f : futures)
+        for (edge_set_t::const_iterator i = f.cbegin(); i != f.cend(); ++i)
+            if (all.find(i->first) == all.cend()) all[i->first] = i->second;
+    std::vector<uint32_t> order;
+    order.reserve(all.size());
+    for (edge_set_t::const_iterator i = all.cbegin(); i != all.cend(); ++i) {
+        if (i->first >= ne) return MCB200_ERR_INVALID;
+        order.push_back(i->first);
+    }
+    schedule((uint32_t)order.size(), nthreads, block_size);
+    const size_t master_first = (size_t)(nthreads - 1) * block_size;
+    uint32_t next = 0;
+    for (size_t k = master_first; k < order.size(); ++k) rank[order[k]] = next++;
+    for (size_t k = 0; k < master_first; ++k) rank[order[k]] = next++;
+    return 0;
+}

@@ -5,8 +5,7 @@
 
 // lbvh.cu
 int lbvh_reserve(mcb200_ctx* ctx, mcb200_mesh* mesh);
-// query_only: groups without node records (the mesh will not be the tree side of a traversal until it is built fully)
-int lbvh_build(mcb200_ctx* ctx, mcb200_mesh* mesh, double eps, bool query_only = false);
+int lbvh_build(mcb200_ctx* ctx, mcb200_mesh* mesh, double eps);
 // traverse.cu
 int traverse_reserve(mcb200_ctx* ctx, const mcb200_mesh* src, const mcb200_mesh* cut, mcb200_result* res);
 int result_reset_counters(mcb200_ctx* ctx, mcb200_result* res);

@@ -5,11 +5,16 @@
 //   k_morton       30-bit Morton codes, the reference's float formula;           bvh.cpp:196-217, :373-433
 //                  also the digit histograms of the sort's passes
 //   radix passes   one-sweep radix sort of (code, face)  (radix_sort.cuh)        bvh.cpp:437-442 (std::sort there)
-//   k_tree         radix tree over the sorted codes (Karras 2012) fused with     replaces the implicit OIBVH layout :444-493
-//                  the box refit of every subtree of <= 32 leaves                and the bottom of bvh.cpp:498-635
-//   k_refit_climb  atomic bottom-up refit of the nodes above those subtrees      bvh.cpp:498-635 (one parallel_for per level there)
-// Only face AABBs, the mesh AABB and the leaf-pair SET escape this stage, and every internal box is the exact
-// min/max union of its leaves, so the tree shape is free: an LBVH yields the same pairs.
+//   k_leaves       everything above the sorted leaves in ONE kernel:             the implicit OIBVH layout bvh.cpp:444-493 and the
+//                  * the leaf boxes in sorted order (single precision, outwards)  level-by-level refit bvh.cpp:498-635
+//                  * an implicit 32-wide tree over them (level l node i = nodes
+//                    [32i, 32i+32) of level l-1), every level's boxes, the upper
+//                    levels by the last block to finish (atomic ticket)
+//                  * the QUERY GROUPS: the maximal subtrees of <= 32 leaves of the
+//                    binary radix tree over the sorted codes (Karras 2012), found
+//                    from the tree's delta function alone, without building it
+// Only face AABBs, the mesh AABB and the leaf-pair SET escape this stage, and every internal box is a (conservative) union
+// of its leaves' boxes, so the tree shape is free: any hierarchy over the same leaves yields the same pairs.
 #include "internal.h"
 #include "radix_sort.cuh"
 
@@ -40,8 +45,7 @@ __device__ __forceinline__ unsigned morton3D(float x, float y, float z)
 template <bool TRI>
 __global__ void __launch_bounds__(BLOCK) k_face_bbox(const void* __restrict__ xyz, frame_t fr,
     const uint32_t* __restrict__ face_vtx, const uint32_t* __restrict__ face_off, uint32_t nf, double eps,
-    double* __restrict__ face_bbox, unsigned long long* __restrict__ root_ordered, unsigned* __restrict__ arrival_flags,
-    const double* __restrict__ prior, uint32_t n_prior)
+    double* __restrict__ face_bbox, unsigned long long* __restrict__ root_ordered, const double* __restrict__ prior, uint32_t n_prior)
 {
     pdl_prologue();
     double bmin[3] = { DBL_MAX, DBL_MAX, DBL_MAX }, bmax[3] = { -DBL_MAX, -DBL_MAX, -DBL_MAX };
@@ -75,7 +79,6 @@ __global__ void __launch_bounds__(BLOCK) k_face_bbox(const void* __restrict__ xy
                 mn[j] = __dsub_rn(mn[j], eps);
             }
         }
-        arrival_flags[f] = 0u; // the refit's arrival counter of node f (saves a memset pass over the array)
         double* out = face_bbox + 6 * (size_t)f;
         // 48-byte rows: three 16-byte stores
         reinterpret_cast<double2*>(out)[0] = make_double2(mn[0], mn[1]);
@@ -167,132 +170,18 @@ __global__ void __launch_bounds__(BLOCK) k_morton(const double* __restrict__ fac
     }
 }
 
-// ---- Karras topology (used by k_tree) ---------------------------------------------------------------------------
-// One thread per internal node (Karras 2012).  A block owns 256 consecutive nodes and stages the sorted codes of a
-// +-512 window in shared memory: the range/split binary searches of almost every node (every range up to 256 leaves,
-// the doubling search overshoots by 2x) stay inside that window, so their dependent probes cost shared-memory latency
-// instead of L2 latency; the few larger nodes fall back to global loads.
-constexpr int KHALO = 512;
-constexpr int KWIN = BLOCK + 2 * KHALO;
-
-struct code_window {
-    const uint32_t* codes;
-    const uint32_t* win; // shared copy of codes[base, base + KWIN)
-    int base, n;
-    __device__ __forceinline__ uint32_t get(int j) const
-    {
-        const int r = j - base;
-        return ((unsigned)r < (unsigned)KWIN) ? win[r] : __ldg(codes + j);
-    }
-    // window-only probe: a key outside the shared window reads as "no common prefix" and raises `miss`
-    __device__ __forceinline__ int delta_win(int i, uint32_t ci, int j, bool& miss) const
-    {
-        if (j < 0 || j >= n) return -1;
-        const int r = j - base;
-        if ((unsigned)r >= (unsigned)KWIN) {
-            miss = true;
-            return -1;
-        }
-        const uint32_t cj = win[r];
-        if (ci == cj) return 32 + __clz((unsigned)i ^ (unsigned)j);
-        return __clz(ci ^ cj);
-    }
-    __device__ __forceinline__ int delta(int i, uint32_t ci, int j) const
-    {
-        if (j < 0 || j >= n) return -1;
-        const uint32_t cj = get(j);
-        if (ci == cj) return 32 + __clz((unsigned)i ^ (unsigned)j); // duplicate codes: tie-break on the index
-        return __clz(ci ^ cj);
-    }
-};
-
-// ---- refit helpers ------------------------------------------------------------------------------------------------
-// One thread per leaf carries its box up; the first thread to reach a node parks its box in the node and leaves,
-// the second one merges and continues (atomic arrival counter per internal node).
+// 24 bytes, 8-byte aligned
 __device__ __forceinline__ void store_box(float* dst, const float* b) // 24 bytes, 8-byte aligned
 {
     reinterpret_cast<float2*>(dst)[0] = make_float2(b[0], b[1]);
     reinterpret_cast<float2*>(dst)[1] = make_float2(b[2], b[3]);
     reinterpret_cast<float2*>(dst)[2] = make_float2(b[4], b[5]);
 }
-__device__ __forceinline__ void load_box_cg(const float* src, float* b)
-{
-    // written by another SM moments ago: read through L2
-    const float2 a = __ldcg(reinterpret_cast<const float2*>(src));
-    const float2 c = __ldcg(reinterpret_cast<const float2*>(src) + 1);
-    const float2 e = __ldcg(reinterpret_cast<const float2*>(src) + 2);
-    b[0] = a.x;
-    b[1] = a.y;
-    b[2] = c.x;
-    b[3] = c.y;
-    b[4] = e.x;
-    b[5] = e.y;
-}
-
-__device__ __forceinline__ void load_face_box(const double* __restrict__ face_bbox, uint32_t face, double* b)
-{
-    const double2* in = reinterpret_cast<const double2*>(face_bbox + 6 * (size_t)face);
-    const double2 a = __ldg(in), c = __ldg(in + 1), e = __ldg(in + 2);
-    b[0] = a.x;
-    b[1] = a.y;
-    b[2] = c.x;
-    b[3] = c.y;
-    b[4] = e.x;
-    b[5] = e.y;
-}
-
-// Range, split and direction of internal node i (Karras 2012, Fig. 4).  WINDOW_ONLY: probes never leave the shared code
-// window; a search that would is abandoned with `miss` set (such a node covers more than 512 leaves) and is redone later
-// with global probes, off the block's common path.
-struct node_topology {
-    int lo, hi, gamma, d, dmin;
-};
-template <bool WINDOW_ONLY> __device__ __forceinline__ node_topology karras_node(const code_window& cw, int ii, bool& miss)
-{
-    auto dl = [&](int j) -> int { return WINDOW_ONLY ? cw.delta_win(ii, cw.get(ii), j, miss) : cw.delta(ii, cw.get(ii), j); };
-    node_topology t;
-    t.d = (dl(ii + 1) - dl(ii - 1)) >= 0 ? 1 : -1;
-    t.dmin = dl(ii - t.d); // = length of the parent's prefix
-    int lmax = 2;
-    while (dl(ii + lmax * t.d) > t.dmin) lmax <<= 1;
-    int l = 0;
-    for (int s = lmax >> 1; s >= 1; s >>= 1)
-        if (dl(ii + (l + s) * t.d) > t.dmin) l += s;
-    const int j = ii + l * t.d;
-    const int dnode = dl(j);
-    int sp = 0;
-    int s = l;
-    do {
-        s = (s + 1) >> 1;
-        if (dl(ii + (sp + s) * t.d) > dnode) sp += s;
-    } while (s > 1);
-    t.gamma = ii + sp * t.d + (t.d < 0 ? -1 : 0);
-    t.lo = ii < j ? ii : j;
-    t.hi = ii < j ? j : ii;
-    return t;
-}
-
-// `face_of(j)` = face id of sorted leaf j.  A leaf child is recorded by its FACE id (the traversal needs nothing else of
-// it); the parent word of a leaf still lives at its sorted position.
-template <typename FaceOf>
-__device__ __forceinline__ void write_topology(bvh_node_t* nodes, uint32_t* parent, uint32_t nf, uint32_t i, const node_topology& t,
-    FaceOf face_of)
-{
-    const bool lleaf = (t.lo == t.gamma), rleaf = (t.hi == t.gamma + 1);
-    const uint32_t left = lleaf ? (MCB_LEAF_BIT | face_of(t.gamma)) : (uint32_t)t.gamma;
-    const uint32_t right = rleaf ? (MCB_LEAF_BIT | face_of(t.gamma + 1)) : (uint32_t)(t.gamma + 1);
-    // parent word of a child: (parent index << 2) | (child is the right one); read by the climb
-    const uint32_t pw = i << 2;
-    parent[lleaf ? (nf - 1 + (uint32_t)t.gamma) : (uint32_t)t.gamma] = pw;
-    parent[rleaf ? (nf - 1 + (uint32_t)(t.gamma + 1)) : (uint32_t)(t.gamma + 1)] = pw | 1u;
-    if (i == 0) parent[0] = MCB200_NULL;
-    *reinterpret_cast<uint4*>(&nodes[i].left) = make_uint4(left, right, (uint32_t)t.lo, (uint32_t)t.hi);
-}
 
 // Slots in the group list for a whole block with ONE global atomic (tens of thousands of same-address atomics from
 // individual warps serialise in L2 and were the most expensive part of this kernel).  Every thread of the block must
-// call this; `want` is 0, 1 or 2.  Returns the first slot of the calling thread.
-__device__ __forceinline__ unsigned alloc_groups_block(unsigned* n_groups, unsigned want, unsigned* s_warp /*[BLOCK/32]*/,
+// call this; `want` is small.  Returns the first slot of the calling thread.
+__device__ __forceinline__ unsigned alloc_groups_block(unsigned* n_groups, unsigned want, unsigned* s_warp /*[blockDim.x/32]*/,
     unsigned* s_base)
 {
     const unsigned lane = lane_id(), w = threadIdx.x >> 5;
@@ -306,7 +195,7 @@ __device__ __forceinline__ unsigned alloc_groups_block(unsigned* n_groups, unsig
     __syncthreads();
     if (threadIdx.x == 0) {
         unsigned tot = 0;
-        for (int i = 0; i < BLOCK / 32; ++i) {
+        for (unsigned i = 0; i < blockDim.x / 32u; ++i) {
             const unsigned c = s_warp[i];
             s_warp[i] = tot;
             tot += c;
@@ -317,218 +206,341 @@ __device__ __forceinline__ unsigned alloc_groups_block(unsigned* n_groups, unsig
     return *s_base + s_warp[w] + inc - want;
 }
 
-// Tree and refit in two regimes, two kernels:
-//  * k_tree: one thread per internal node finds its range and split (Karras 2012) from the block's shared window of
-//    sorted codes.  A node whose leaf range has at most 32 leaves then gets both child boxes straight from the leaf boxes
-//    of its range (it knows its range and its split, so no other node's result is needed): no atomics, no fences, and the
-//    whole 64-byte record (boxes + topology) is written at once.  Node i lies inside its own range, so every such range
-//    falls in the block's leaf window [i0-32, i0+288), gathered into shared memory while the code window loads.  The
-//    maximal treelets ("group roots") are listed: they are the traversal's query groups and the starting points of ...
-//    Whether a node's PARENT covers more than 32 leaves is decided locally: the parent's range is the set of keys sharing
-//    the parent's prefix (length delta(i, i - d), the `dmin` of the range search), so it has more than 32 leaves exactly
-//    when the key 32 positions beyond the node's far end still shares that prefix.
-//  * k_refit_climb: ... the classic atomic bottom-up pass for the ~nf/16 nodes above the treelets: one thread per group
-//    root carries its box upwards; the first thread to reach a node parks its box there and leaves, the second one
-//    merges and continues.  All climbers are resident at once, so the pass costs (levels above the treelets) x (one
-//    store / fence / atomic / load round trip), not a block-scheduling queue.
-constexpr int RHALO = 32;
-constexpr int RWIN = BLOCK + 2 * RHALO;
+// ---- K_leaves -----------------------------------------------------------------------------------------------------
+// One block = 1024 consecutive sorted leaves = 32 level-1 nodes = ONE level-2 node.
+//
+// Wide tree.  Leaf j's exact box is gathered through the sorted order, rounded outwards to single precision and stored in the
+// level-0 array; a warp-wide min/max of 32 consecutive leaves is a level-1 box, the block's 32 level-1 boxes give its
+// level-2 box.  Levels 3.. (F/32768 nodes and fewer) are finished by whichever block takes the last ticket.  Fixed runs of
+// 32 leaves may straddle a coarse cell boundary of the Morton curve and get a fat box; on the TREE side of a traversal that
+// costs one extra step now and then (the children are tight again) and nothing else.
+//
+// Query groups.  On the QUERY side a fat box would be ruinous (the group's box steers its whole walk), so the leaves are
+// grouped the way a binary radix tree over the sorted codes (Karras 2012) would group them: a group is a maximal subtree
+// with at most 32 leaves.  The tree is never built.  With delta(j) = the length of the common prefix of codes j-1 and j
+// (ties broken by the index, as in the paper), the radix-tree node that splits between leaves j-1 and j covers the maximal
+// run of leaves around that boundary whose inner boundaries all have a LARGER delta; leaves j-1 and j lie in different
+// groups exactly when that run holds more than 32 leaves.  So each boundary counts larger deltas to its left and right
+// (it stops at 32; most boundaries stop after one or two steps) and is a group boundary or not — independent, no atomics.
+constexpr int LB_THREADS = 256;
+constexpr int LB_LEAVES = 1024;
+constexpr int LB_HL = 34, LB_HR = 66; // halo of the code window: boundaries up to 32 + 31 past the block are classified
+constexpr int LB_WIN = LB_LEAVES + LB_HL + LB_HR;
+constexpr int LB_BOXES = LB_LEAVES + 32; // leaf boxes kept in shared memory: a group may run 31 leaves into the next block
+constexpr int LB_ITEMS = LB_LEAVES / LB_THREADS; // 4 leaf blocks (chunks of 32 leaves) per warp
+constexpr int LB_LOG = 5; // range-minimum tables over 1, 2, 4, 8, 16 boundaries
 
-// NODES = false: the mesh will only be the QUERY side of a traversal — it needs its groups (maximal treelets + union boxes)
-// but nobody will walk its tree, so no node record, no parent word is written and the climb kernel is not run.
-template <bool NODES>
-__global__ void __launch_bounds__(BLOCK) k_tree(const uint32_t* __restrict__ codes, const double* __restrict__ face_bbox,
-    const uint32_t* __restrict__ sorted_faces, uint32_t nf, bvh_node_t* nodes, uint32_t* __restrict__ parent,
-    uint2* __restrict__ groups, group_up_t* __restrict__ group_up, unsigned* __restrict__ n_groups)
+__device__ __forceinline__ void warp_union(float* b)
 {
-    pdl_prologue();
-    __shared__ uint32_t s_win[KWIN];
-    __shared__ float s_box[RWIN][6]; // conservative single-precision leaf boxes of the block's leaf window
-    __shared__ uint32_t s_face[RWIN]; // their face ids
-    __shared__ unsigned s_warp[BLOCK / 32], s_base;
-    if (nf == 1) {
-        // a single leaf (e.g. the planar-section triangle): pseudo-root whose right child can never be hit
-        if (blockIdx.x == 0 && threadIdx.x == 0) {
-            double bd[6];
-            load_face_box(face_bbox, sorted_faces[0], bd);
-            float b[6];
-            box_to_float(bd, b);
-            store_box(nodes[0].lbox, b);
-            const float e[6] = { FLT_MAX, FLT_MAX, FLT_MAX, -FLT_MAX, -FLT_MAX, -FLT_MAX };
-            store_box(nodes[0].rbox, e);
-            nodes[0].left = MCB_LEAF_BIT | sorted_faces[0];
-            nodes[0].right = MCB200_NULL;
-            nodes[0].first = 0;
-            nodes[0].last = 0;
-            groups[0] = make_uint2(0u, 1u);
-            store_box(group_up[0].box, b);
-            group_up[0].pw = MCB200_NULL;
-            *n_groups = 1u;
-        }
-        return;
-    }
-    const int n = (int)nf;
-    const uint32_t i0 = blockIdx.x * BLOCK;
-    const int cbase = (int)i0 - KHALO;
-    {
-        // both windows with every load in flight before the first store (a load->store loop would serialise L2 round trips)
-        static_assert(KWIN % BLOCK == 0 && RWIN <= 2 * BLOCK, "window shapes");
-        uint32_t cw_reg[KWIN / BLOCK];
 #pragma unroll
-        for (int k = 0; k < KWIN / BLOCK; ++k) {
-            const int j = cbase + k * BLOCK + (int)threadIdx.x;
-            cw_reg[k] = (j >= 0 && j < n) ? __ldg(codes + j) : 0u;
-        }
-        const long long j0 = (long long)i0 - RHALO + threadIdx.x, j1 = j0 + BLOCK;
-        const bool have0 = j0 >= 0 && j0 < (long long)nf, have1 = threadIdx.x < RWIN - BLOCK && j1 < (long long)nf;
-        const uint32_t f0 = have0 ? __ldg(sorted_faces + j0) : 0u, f1 = have1 ? __ldg(sorted_faces + j1) : 0u;
-        double b0[6], b1[6];
-        if (have0) load_face_box(face_bbox, f0, b0);
-        if (have1) load_face_box(face_bbox, f1, b1);
+    for (int o = 16; o > 0; o >>= 1) {
 #pragma unroll
-        for (int k = 0; k < KWIN / BLOCK; ++k) s_win[k * BLOCK + threadIdx.x] = cw_reg[k];
-        if (have0) {
-            box_to_float(b0, s_box[threadIdx.x]);
-            s_face[threadIdx.x] = f0;
+        for (int k = 0; k < 3; ++k) {
+            b[k] = fminf(b[k], __shfl_xor_sync(0xffffffffu, b[k], o));
+            b[3 + k] = fmaxf(b[3 + k], __shfl_xor_sync(0xffffffffu, b[3 + k], o));
         }
-        if (have1) {
-            box_to_float(b1, s_box[BLOCK + threadIdx.x]);
-            s_face[BLOCK + threadIdx.x] = f1;
-        }
-    }
-    __syncthreads();
-    const uint32_t i = i0 + threadIdx.x;
-    const int wbase = (int)i0 - RHALO; // leaf j sits in s_box[j - wbase]
-    const code_window cw { codes, s_win, cbase, n };
-
-    // face id of sorted leaf j: from the block's window when it is there (every leaf child of a small node is)
-    auto face_of = [&](int j) -> uint32_t {
-        const int r = j - wbase;
-        return ((unsigned)r < (unsigned)RWIN) ? s_face[r] : __ldg(sorted_faces + j);
-    };
-    // ---- topology first: node i's range, split and children; is it (or leaf i) the root of a maximal treelet? ----
-    bool root0 = false, root1 = false, small = false, deferred = false;
-    int lo = 0, hi = 0, gamma = 0;
-    if (i < nf - 1u) {
-        const int ii = (int)i;
-        const node_topology t = karras_node<true>(cw, ii, deferred);
-        if (!deferred) {
-            if (NODES) write_topology(nodes, parent, nf, i, t, face_of);
-            lo = t.lo;
-            hi = t.hi;
-            gamma = t.gamma;
-            small = hi - lo + 1 <= 32;
-            if (small) {
-                // a maximal treelet: the whole tree, or the parent's range reaches past 32 leaves
-                const int probe = (t.d > 0) ? hi - 32 : lo + 32;
-                root0 = (i == 0u) || (probe >= 0 && probe < n && cw.delta(ii, cw.get(ii), probe) >= t.dmin);
-            }
-        }
-    }
-    // leaf i hangs directly under a node that covers more than 32 leaves?  A leaf joins the neighbour it shares the longer
-    // prefix with; that prefix is its parent's.
-    if (i < nf) {
-        const int ii = (int)i;
-        const uint32_t ci = cw.get(ii);
-        const int dl = cw.delta(ii, ci, ii - 1), dr = cw.delta(ii, ci, ii + 1);
-        const bool is_left = dr > dl;
-        const int dp = is_left ? dr : dl;
-        const int probe = is_left ? ii + 32 : ii - 32;
-        root1 = probe >= 0 && probe < n && cw.delta(ii, ci, probe) >= dp;
-    }
-    // the block-wide slot allocation (a barrier) sits here, before the box loops whose length differs from thread to thread
-    unsigned g = alloc_groups_block(n_groups, (root0 ? 1u : 0u) + (root1 ? 1u : 0u), s_warp, &s_base);
-
-    // ---- boxes of the small nodes straight from the leaf window ----
-    if (small && (NODES || root0)) {
-        float box[6], rb[6];
-#pragma unroll
-        for (int k = 0; k < 6; ++k) {
-            box[k] = s_box[lo - wbase][k];
-            rb[k] = s_box[gamma + 1 - wbase][k];
-        }
-        for (int q = lo + 1; q <= gamma; ++q)
-#pragma unroll
-            for (int k = 0; k < 3; ++k) {
-                box[k] = fminf(box[k], s_box[q - wbase][k]);
-                box[3 + k] = fmaxf(box[3 + k], s_box[q - wbase][3 + k]);
-            }
-        for (int q = gamma + 2; q <= hi; ++q)
-#pragma unroll
-            for (int k = 0; k < 3; ++k) {
-                rb[k] = fminf(rb[k], s_box[q - wbase][k]);
-                rb[3 + k] = fmaxf(rb[3 + k], s_box[q - wbase][3 + k]);
-            }
-        if (NODES) {
-            store_box(nodes[i].lbox, box);
-            store_box(nodes[i].rbox, rb);
-        }
-        if (root0) {
-#pragma unroll
-            for (int k = 0; k < 3; ++k) {
-                box[k] = fminf(box[k], rb[k]);
-                box[3 + k] = fmaxf(box[3 + k], rb[3 + k]);
-            }
-            groups[g] = make_uint2((uint32_t)lo, (uint32_t)(hi - lo + 1));
-            store_box(group_up[g].box, box);
-            group_up[g].pw = (i == 0u) ? MCB200_NULL : i; // where the climb finds this root's parent word
-            ++g;
-        }
-    }
-    if (root1) {
-        groups[g] = make_uint2(i, 1u);
-        float lb[6];
-#pragma unroll
-        for (int k = 0; k < 6; ++k) lb[k] = s_box[(int)i - wbase][k];
-        store_box(group_up[g].box, lb);
-        group_up[g].pw = nf - 1u + i;
-    }
-    // the few nodes whose range leaves the window (> 512 leaves): dependent global probes, now that nobody waits for them
-    if (NODES && deferred) {
-        bool unused = false;
-        const node_topology t = karras_node<false>(cw, (int)i, unused);
-        write_topology(nodes, parent, nf, i, t, face_of);
     }
 }
 
-__global__ void __launch_bounds__(BLOCK) k_refit_climb(bvh_node_t* nodes, const uint32_t* __restrict__ parent, unsigned* flags,
-    const group_up_t* __restrict__ group_up, const unsigned* __restrict__ n_groups)
+__device__ __forceinline__ void empty_box(float* b)
+{
+    b[0] = b[1] = b[2] = FLT_MAX;
+    b[3] = b[4] = b[5] = -FLT_MAX;
+}
+
+// Segmented scans of the 32 boxes of one chunk (lane = leaf), segments starting at the lanes whose bit is set in `heads`:
+//   pre[c] = union of the boxes from the start of the lane's segment (or of the chunk) up to the lane,
+//   suf[c] = union from the lane to the end of its segment (or of the chunk).
+__device__ __forceinline__ void segmented_unions(const float* box, unsigned heads, float* pre, float* suf)
+{
+    const unsigned lane = lane_id();
+#pragma unroll
+    for (int c = 0; c < 6; ++c) pre[c] = suf[c] = box[c];
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        // lanes (lane - d, lane] hold no segment start: the value d lanes below belongs to the same segment
+        const bool up = lane >= (unsigned)d && ((heads >> (lane - d + 1u)) & ((1u << d) - 1u)) == 0u;
+        // lanes (lane, lane + d] hold no segment start
+        const bool down = lane + d < 32u && ((heads >> (lane + 1u)) & ((1u << d) - 1u)) == 0u;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            const float pu = __shfl_up_sync(0xffffffffu, pre[c], d), pU = __shfl_up_sync(0xffffffffu, pre[3 + c], d);
+            const float sd = __shfl_down_sync(0xffffffffu, suf[c], d), sD = __shfl_down_sync(0xffffffffu, suf[3 + c], d);
+            if (up) {
+                pre[c] = fminf(pre[c], pu);
+                pre[3 + c] = fmaxf(pre[3 + c], pU);
+            }
+            if (down) {
+                suf[c] = fminf(suf[c], sd);
+                suf[3 + c] = fmaxf(suf[3 + c], sD);
+            }
+        }
+    }
+}
+
+__global__ void __launch_bounds__(LB_THREADS, 3) k_leaves(const uint32_t* __restrict__ codes, const double* __restrict__ face_bbox,
+    const uint32_t* __restrict__ sorted_faces, uint32_t nf, float* __restrict__ wide, double* __restrict__ sorted_bbox, wide_levels_t lv,
+    uint2* __restrict__ groups, group_box_t* __restrict__ group_box, unsigned* __restrict__ n_groups, unsigned* __restrict__ done_ticket)
 {
     pdl_prologue();
-    const unsigned ng = *n_groups;
-    for (unsigned g = blockIdx.x * BLOCK + threadIdx.x; g < ng; g += gridDim.x * BLOCK) {
-        const uint32_t slot = group_up[g].pw;
-        if (slot == MCB200_NULL) continue; // the whole tree was one treelet
-        uint32_t pw = __ldg(parent + slot);
-        float box[6];
-        {
-            const float2* in = reinterpret_cast<const float2*>(group_up[g].box);
-            const float2 a = in[0], b = in[1], c = in[2];
-            box[0] = a.x; box[1] = a.y; box[2] = b.x; box[3] = b.y; box[4] = c.x; box[5] = c.y;
-        }
-        for (;;) {
-            const uint32_t p = pw >> 2;
-            bvh_node_t* nd = nodes + p;
-            const bool is_left = !(pw & 1u);
-            const uint32_t next_pw = (p == 0u) ? MCB200_NULL : __ldg(parent + p); // in flight while the fence drains
-            store_box(is_left ? nd->lbox : nd->rbox, box);
-            __threadfence();
-            const unsigned arrived = atomicAdd(flags + p, 1u);
-            if (arrived == 0) break; // sibling subtree not finished yet; its thread will continue from here
-            float sib[6];
-            load_box_cg(is_left ? nd->rbox : nd->lbox, sib);
+    __shared__ uint32_t s_code[LB_WIN];
+    // s_lam[0]: delta + 1 of the boundary before window leaf k (0 at the ends of the array); s_lam[t]: minimum over 2^t boundaries
+    __shared__ uint8_t s_lam[LB_LOG][LB_WIN];
+    __shared__ float s_pre[6][LB_BOXES]; // per chunk of 32 leaves: union from the start of the leaf's segment (or chunk) up to the leaf
+    __shared__ uint32_t s_flag[LB_BOXES / 32 + 2];
+    __shared__ float s_l1[6][32];
+    __shared__ unsigned s_warp[LB_THREADS / 32], s_base, s_ticket;
+    const unsigned lane = lane_id(), w = threadIdx.x >> 5;
+    const long long base = (long long)blockIdx.x * LB_LEAVES; // first leaf of the block
+    const long long wbase = base - LB_HL; // leaf index of window slot 0
+
+    // ---- loads: the code window and the face ids (coalesced), then the exact boxes through the face ids ----
+    {
+        constexpr int R = (LB_WIN + LB_THREADS - 1) / LB_THREADS;
+        uint32_t creg[R];
 #pragma unroll
-            for (int k = 0; k < 3; ++k) {
-                box[k] = fminf(box[k], sib[k]);
-                box[3 + k] = fmaxf(box[3 + k], sib[3 + k]);
-            }
-            if (p == 0u) break; // root merged; the mesh AABB itself comes from K_aabb's reduction
-            pw = next_pw;
+        for (int r = 0; r < R; ++r) {
+            const int k = r * LB_THREADS + (int)threadIdx.x;
+            const long long j = wbase + k;
+            creg[r] = (k < LB_WIN && j >= 0 && j < (long long)nf) ? __ldg(codes + j) : 0u;
         }
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            const int k = r * LB_THREADS + (int)threadIdx.x;
+            if (k < LB_WIN) s_code[k] = creg[r];
+        }
+    }
+    __syncthreads();
+    // ---- delta of every boundary of the window, then its range minima ----
+    for (int k = threadIdx.x; k < LB_WIN; k += LB_THREADS) {
+        const long long j = wbase + k;
+        unsigned lam = 0;
+        if (k >= 1 && j >= 1 && j < (long long)nf) {
+            const uint32_t ca = s_code[k - 1], cb = s_code[k];
+            lam = 1u + (unsigned)((ca == cb) ? 32 + __clz((unsigned)(j - 1) ^ (unsigned)j) : __clz(ca ^ cb));
+        }
+        s_lam[0][k] = (uint8_t)lam;
+    }
+#pragma unroll
+    for (int t = 1; t < LB_LOG; ++t) {
+        __syncthreads();
+        const int half = 1 << (t - 1);
+        for (int k = threadIdx.x; k < LB_WIN; k += LB_THREADS) {
+            const unsigned x = s_lam[t - 1][k], y = (k + half < LB_WIN) ? s_lam[t - 1][k + half] : 0u;
+            s_lam[t][k] = (uint8_t)(x < y ? x : y);
+        }
+    }
+    __syncthreads();
+    // ---- group boundaries among the boundaries [base, base + 1056): how many consecutive boundaries on either side have
+    //      a larger delta (binary lifting over the range minima, at most 31 each way) ----
+    for (int r = 0; r < (LB_BOXES + LB_THREADS - 1) / LB_THREADS; ++r) {
+        const int b = r * LB_THREADS + (int)threadIdx.x; // boundary before leaf base + b
+        bool flag = false;
+        if (b < LB_BOXES) {
+            const long long j = base + b;
+            if (j == 0 || j >= (long long)nf) {
+                flag = true;
+            } else {
+                const int k = b + LB_HL;
+                const unsigned lam = s_lam[0][k];
+                int lo = k, hi = k + 1; // boundaries (lo, k) and [k + 1, hi) are known to be larger
+#pragma unroll
+                for (int t = LB_LOG - 1; t >= 0; --t) {
+                    const int span = 1 << t;
+                    if (s_lam[t][lo - span] > lam) lo -= span;
+                    if (s_lam[t][hi] > lam) hi += span;
+                }
+                flag = (k - lo) + (hi - k - 1) + 2 > 32;
+            }
+        }
+        const unsigned m = __ballot_sync(0xffffffffu, flag);
+        const unsigned word = (unsigned)(r * LB_THREADS + (int)threadIdx.x) >> 5;
+        if (lane == 0 && word < LB_BOXES / 32 + 2) s_flag[word] = m;
+    }
+    __syncthreads();
+    // chunks q = 4 w + i (i < 4) belong to warp w; warp 0 also fetches the 32 leaves after the block (i == 4, q = 32)
+    constexpr int NI = LB_ITEMS + 1;
+    uint32_t face[NI];
+    bool have[NI];
+#pragma unroll
+    for (int i = 0; i < NI; ++i) {
+        const unsigned q = (i < LB_ITEMS) ? w * LB_ITEMS + i : 32u;
+        const long long j = base + 32ll * q + lane;
+        have[i] = (i < LB_ITEMS || w == 0) && j < (long long)nf;
+        face[i] = have[i] ? __ldg(sorted_faces + j) : 0u;
+    }
+    double2 bx[NI][3];
+#pragma unroll
+    for (int i = 0; i < NI; ++i) {
+        if (have[i]) {
+            const double2* in = reinterpret_cast<const double2*>(face_bbox + 6 * (size_t)face[i]);
+            bx[i][0] = __ldg(in);
+            bx[i][1] = __ldg(in + 1);
+            bx[i][2] = __ldg(in + 2);
+        }
+    }
+    // ---- leaf boxes: exact copy in sorted order, single precision outwards -> level 0 ([6][32] blocks), level-1 boxes,
+    //      segmented unions for the groups ----
+    const uint32_t nb0 = (nf + 31u) / 32u;
+    float suf[LB_ITEMS][6];
+#pragma unroll
+    for (int i = 0; i < NI; ++i) {
+        if (i == LB_ITEMS && w != 0) break;
+        const unsigned q = (i < LB_ITEMS) ? w * LB_ITEMS + i : 32u;
+        float fb[6];
+        if (have[i]) {
+            const double d[6] = { bx[i][0].x, bx[i][0].y, bx[i][1].x, bx[i][1].y, bx[i][2].x, bx[i][2].y };
+            box_to_float(d, fb);
+            if (i < LB_ITEMS) {
+                double2* out = reinterpret_cast<double2*>(sorted_bbox + 6 * (size_t)(base + 32ll * q + lane));
+                out[0] = bx[i][0];
+                out[1] = bx[i][1];
+                out[2] = bx[i][2];
+            }
+        } else {
+            empty_box(fb);
+        }
+        float pre[6], sf[6];
+        segmented_unions(fb, s_flag[q], pre, sf);
+#pragma unroll
+        for (int c = 0; c < 6; ++c) s_pre[c][32u * q + lane] = pre[c];
+        if (i < LB_ITEMS) {
+#pragma unroll
+            for (int c = 0; c < 6; ++c) suf[i][c] = sf[c];
+            const unsigned long long blk = (unsigned long long)blockIdx.x * 32u + q;
+            if (blk < nb0) {
+                float* dst = wide + ((size_t)lv.off[0] + blk) * MCB_WBLOCK_FLOATS + lane;
+#pragma unroll
+                for (int c = 0; c < 6; ++c) dst[c * 32] = fb[c];
+            }
+            warp_union(fb);
+            if (lane == 0)
+#pragma unroll
+                for (int c = 0; c < 6; ++c) s_l1[c][q] = fb[c];
+        }
+    }
+    __syncthreads();
+    // ---- groups that start in this block: a group is a segment, possibly continued in the next chunk ----
+    {
+        unsigned want = 0;
+        unsigned cnt_of[LB_ITEMS];
+#pragma unroll
+        for (int i = 0; i < LB_ITEMS; ++i) {
+            const unsigned q = w * LB_ITEMS + i, p = q * 32u + lane; // leaf base + p
+            cnt_of[i] = 0;
+            if (base + p < (long long)nf && ((s_flag[q] >> lane) & 1u)) {
+                // the next group boundary is at most 32 leaves away
+                const unsigned rest = lane < 31u ? (s_flag[q] >> (lane + 1u)) : 0u;
+                if (rest) {
+                    cnt_of[i] = (unsigned)__ffs((int)rest);
+                } else {
+                    const unsigned t = (unsigned)__ffs((int)s_flag[q + 1u]) - 1u; // leaves of the next chunk that still belong
+                    cnt_of[i] = 32u - lane + t;
+                    if (t > 0u) {
+#pragma unroll
+                        for (int c = 0; c < 3; ++c) {
+                            suf[i][c] = fminf(suf[i][c], s_pre[c][(q + 1u) * 32u + t - 1u]);
+                            suf[i][3 + c] = fmaxf(suf[i][3 + c], s_pre[3 + c][(q + 1u) * 32u + t - 1u]);
+                        }
+                    }
+                }
+                ++want;
+            }
+        }
+        unsigned g = alloc_groups_block(n_groups, want, s_warp, &s_base);
+#pragma unroll
+        for (int i = 0; i < LB_ITEMS; ++i) {
+            if (!cnt_of[i]) continue;
+            const unsigned p = (w * LB_ITEMS + i) * 32u + lane;
+            groups[g] = make_uint2((uint32_t)(base + p), cnt_of[i]);
+            store_box(group_box[g].box, suf[i]);
+            ++g;
+        }
+    }
+    // ---- level 1 block of this leaf range, its level-2 node; the levels above by the last block ----
+    if (w == 0) {
+        float b1[6];
+        const unsigned long long node1 = (unsigned long long)blockIdx.x * 32u + lane;
+        if (node1 < lv.n[1]) {
+#pragma unroll
+            for (int c = 0; c < 6; ++c) b1[c] = s_l1[c][lane];
+        } else {
+            empty_box(b1);
+        }
+        float* dst = wide + ((size_t)lv.off[1] + blockIdx.x) * MCB_WBLOCK_FLOATS + lane;
+#pragma unroll
+        for (int c = 0; c < 6; ++c) dst[c * 32] = b1[c];
+        if (lv.top >= 2) {
+            warp_union(b1);
+            if (lane == 0) {
+                float* d2 = wide + ((size_t)lv.off[2] + (blockIdx.x >> 5)) * MCB_WBLOCK_FLOATS + (blockIdx.x & 31u);
+#pragma unroll
+                for (int c = 0; c < 6; ++c) d2[c * 32] = b1[c];
+                __threadfence();
+                s_ticket = atomicAdd(done_ticket, 1u);
+            }
+        }
+    }
+    if (lv.top < 2) return;
+    __syncthreads();
+    if (s_ticket != gridDim.x - 1u) return;
+    __threadfence();
+    for (int l = 2; l <= lv.top; ++l) {
+        // pad level l up to a whole block with empty boxes
+        const uint32_t nl = lv.n[l], padded = ((nl + 31u) / 32u) * 32u;
+        for (uint32_t i = nl + threadIdx.x; i < padded; i += LB_THREADS) {
+            float* d = wide + ((size_t)lv.off[l] + (i >> 5)) * MCB_WBLOCK_FLOATS + (i & 31u);
+            d[0] = d[32] = d[64] = FLT_MAX;
+            d[96] = d[128] = d[160] = -FLT_MAX;
+        }
+        if (l < lv.top) {
+            const uint32_t nup = lv.n[l + 1];
+            for (uint32_t i = w; i < nup; i += LB_THREADS / 32) {
+                const uint32_t child = 32u * i + lane;
+                float b[6];
+                if (child < nl) {
+                    const float* src = wide + ((size_t)lv.off[l] + i) * MCB_WBLOCK_FLOATS + lane;
+#pragma unroll
+                    for (int c = 0; c < 6; ++c) b[c] = __ldcg(src + c * 32);
+                } else {
+                    empty_box(b);
+                }
+                warp_union(b);
+                if (lane == 0) {
+                    float* d = wide + ((size_t)lv.off[l + 1] + (i >> 5)) * MCB_WBLOCK_FLOATS + (i & 31u);
+#pragma unroll
+                    for (int c = 0; c < 6; ++c) d[c * 32] = b[c];
+                }
+            }
+        }
+        __syncthreads();
     }
 }
 
 } // namespace
+
+// level table of the implicit 32-wide tree over nf leaves
+static void make_levels(uint32_t nf, wide_levels_t& lv)
+{
+    std::memset(&lv, 0, sizeof(lv));
+    uint32_t acc = 0;
+    lv.n[0] = nf;
+    for (int l = 0; l < MCB_MAX_LEVELS; ++l) {
+        const uint32_t nb = (lv.n[l] + 31u) / 32u;
+        lv.off[l] = acc;
+        acc += nb;
+        if (l >= 1 && lv.n[l] <= 32u) {
+            lv.top = l;
+            break;
+        }
+        if (l + 1 < MCB_MAX_LEVELS) lv.n[l + 1] = nb;
+    }
+}
+
+static size_t wide_blocks(const wide_levels_t& lv)
+{
+    return (size_t)lv.off[lv.top] + 1u;
+}
 
 int lbvh_reserve(mcb200_ctx* ctx, mcb200_mesh* m)
 {
@@ -537,22 +549,25 @@ int lbvh_reserve(mcb200_ctx* ctx, mcb200_mesh* m)
         return MCB200_ERR_INVALID;
     }
     const uint32_t nf = m->nf;
+    if (!m->lv) m->lv = new wide_levels_t();
+    make_levels(nf, *m->lv);
     MCB_TRY(ctx->reserve(m->face_bbox, sizeof(double) * 6 * (size_t)nf));
     MCB_TRY(ctx->reserve(m->root, sizeof(unsigned long long) * 6 + sizeof(double) * 6));
     MCB_TRY(ctx->reserve(m->codes, sizeof(uint32_t) * (size_t)nf));
     MCB_TRY(ctx->reserve(m->sorted_codes, sizeof(uint32_t) * (size_t)nf));
     MCB_TRY(ctx->reserve(m->sorted_faces, sizeof(uint32_t) * (size_t)nf));
-    MCB_TRY(ctx->reserve(m->nodes, sizeof(bvh_node_t) * (size_t)(nf > 1 ? nf - 1 : 1)));
-    MCB_TRY(ctx->reserve(m->parent, sizeof(uint32_t) * (2 * (size_t)nf)));
-    MCB_TRY(ctx->reserve(m->flags, sizeof(unsigned) * (size_t)nf));
+    MCB_TRY(ctx->reserve(m->wide, sizeof(float) * MCB_WBLOCK_FLOATS * wide_blocks(*m->lv)));
+    MCB_TRY(ctx->reserve(m->sorted_bbox, sizeof(double) * 6 * (size_t)nf));
+    MCB_TRY(ctx->reserve(m->flags, sizeof(unsigned) * 4));
     MCB_TRY(ctx->reserve(m->groups, sizeof(uint2) * (size_t)nf + sizeof(unsigned) * 4));
-    MCB_TRY(ctx->reserve(m->group_up, sizeof(group_up_t) * (size_t)nf));
+    MCB_TRY(ctx->reserve(m->group_box, sizeof(group_box_t) * (size_t)nf));
     MCB_TRY((rsort::reserve_scratch<uint32_t>(ctx, nf, 4, true, true)));
+    m->lv->boxes = m->wide.as<float>();
     return 0;
 }
 
 // Everything is enqueued on ctx->cur (the caller picks the lane); all allocations happen in lbvh_reserve.
-int lbvh_build(mcb200_ctx* ctx, mcb200_mesh* m, double eps, bool query_only)
+int lbvh_build(mcb200_ctx* ctx, mcb200_mesh* m, double eps)
 {
     MCB_TRY(lbvh_reserve(ctx, m));
     const uint32_t nf = m->nf;
@@ -563,12 +578,12 @@ int lbvh_build(mcb200_ctx* ctx, mcb200_mesh* m, double eps, bool query_only)
     unsigned* n_groups = reinterpret_cast<unsigned*>(m->groups.as<uint2>() + nf);
     {
         // every small reset of the build in one launch: mesh AABB accumulators (min side all-ones, max side zero in the
-        // ordered encoding), group counter, radix histograms and tile tickets.  The arrival flags (one word per face) are
-        // cleared by k_face_bbox on its way through the faces.
+        // ordered encoding), group counter, the last-block ticket, radix histograms and tile tickets
         fill_list_t fl {};
         fl.add(root_ord, 6, 0xFFFFFFFFu);
         fl.add(root_ord + 3, 6, 0u);
         fl.add(n_groups, 4, 0u);
+        fl.add(m->flags.p, 4, 0u);
         fl.add(sc.hist.p, (size_t)rsort::MAX_PASSES * rsort::RADIX, 0u);
         fl.add(sc.tilectr.p, rsort::MAX_PASSES, 0u);
         MCB_LAUNCH(ctx, k_fill, 8, 256, 0, fl);
@@ -580,14 +595,14 @@ int lbvh_build(mcb200_ctx* ctx, mcb200_mesh* m, double eps, bool query_only)
     const uint32_t n_prior = m->n_prior < nf ? m->n_prior : nf;
     if (m->is_tri)
         MCB_LAUNCH(ctx, k_face_bbox<true>, grid, BLOCK, 0, m->d_xyz, m->frame, m->d_face_vtx, m->d_face_off, nf, eps,
-            m->face_bbox.as<double>(), root_ord, m->flags.as<unsigned>(), prior, n_prior);
+            m->face_bbox.as<double>(), root_ord, prior, n_prior);
     else
         MCB_LAUNCH(ctx, k_face_bbox<false>, grid, BLOCK, 0, m->d_xyz, m->frame, m->d_face_vtx, m->d_face_off, nf, eps,
-            m->face_bbox.as<double>(), root_ord, m->flags.as<unsigned>(), prior, n_prior);
+            m->face_bbox.as<double>(), root_ord, prior, n_prior);
     m->n_prior = 0; // consumed: the boxes are part of face_bbox now
     // (key, face) ascending by key (values implicit 0..nf-1), ping-pong scratch <-> mesh arrays; the histograms come out
     // of k_morton.  The leaves are ordered by the top `morton_sort_bits` bits of their code.  Nothing that leaves this stage depends on the
-    // order (the pair SET is tree-independent and the treelets hold up to 32 leaves anyway), so the default sorts 24 bits in
+    // order (the pair SET is tree-independent and the groups hold up to 32 leaves anyway), so the default sorts 24 bits in
     // three passes; codes that tie are told apart by their position, as equal codes always were.  With an odd number of
     // passes the keys start in the scratch buffer so that the last pass lands in the mesh's own arrays.
     const int sort_bits = ctx->morton_sort_bits >= 30 ? 32 : 24;
@@ -610,24 +625,9 @@ int lbvh_build(mcb200_ctx* ctx, mcb200_mesh* m, double eps, bool query_only)
         ctx->set_error("internal: the Morton sort did not end in the mesh's arrays", __FILE__, __LINE__);
         return MCB200_ERR_INTERNAL;
     }
-    if (nf <= 1) query_only = false; // the one-leaf pseudo tree is free
-    if (query_only)
-        MCB_LAUNCH(ctx, k_tree<false>, div_up(nf, BLOCK), BLOCK, 0, m->sorted_codes.as<uint32_t>(), m->face_bbox.as<double>(),
-            m->sorted_faces.as<uint32_t>(), nf, m->nodes.as<bvh_node_t>(), m->parent.as<uint32_t>(), m->groups.as<uint2>(),
-            m->group_up.as<group_up_t>(), n_groups);
-    else
-        MCB_LAUNCH(ctx, k_tree<true>, div_up(nf, BLOCK), BLOCK, 0, m->sorted_codes.as<uint32_t>(), m->face_bbox.as<double>(),
-            m->sorted_faces.as<uint32_t>(), nf, m->nodes.as<bvh_node_t>(), m->parent.as<uint32_t>(), m->groups.as<uint2>(),
-            m->group_up.as<group_up_t>(), n_groups);
-    m->has_nodes = !query_only;
-    if (nf > 1 && !query_only) {
-        // enough threads for every group root to climb concurrently (about nf/16 of them; nf/4 is a safe bound for the grid,
-        // the kernel strides over the device-side count anyway)
-        const unsigned want = div_up((size_t)nf / 4u + 1u, BLOCK);
-        const unsigned gc = want < max_grid ? want : max_grid;
-        MCB_LAUNCH(ctx, k_refit_climb, gc, BLOCK, 0, m->nodes.as<bvh_node_t>(), m->parent.as<uint32_t>(), m->flags.as<unsigned>(),
-            m->group_up.as<group_up_t>(), n_groups);
-    }
+    MCB_LAUNCH(ctx, k_leaves, div_up(nf, LB_LEAVES), LB_THREADS, 0, m->sorted_codes.as<uint32_t>(), m->face_bbox.as<double>(),
+        m->sorted_faces.as<uint32_t>(), nf, m->wide.as<float>(), m->sorted_bbox.as<double>(), *m->lv, m->groups.as<uint2>(), m->group_box.as<group_box_t>(), n_groups,
+        m->flags.as<unsigned>());
     m->built = true;
     m->groups_valid = true;
     m->eps = eps;

@@ -187,11 +187,12 @@ __device__ __noinline__ bool best_triple(const face_view& G, const double* norma
     return found;
 }
 
-// One edge/face test (kernel.cpp:2483-2656).  Returns false when the stage-A filter failed and EXACT is off
-// (the caller queues the test for k_exact); otherwise fills `o`.
+// One edge/face test (kernel.cpp:2483-2656).  With EXACT off it returns false unless the test is a CERTIFIED non-crossing
+// (both stage-A determinants pass the error-bound filter and have the same sign): the caller queues everything else for
+// the second kernel (`needs_exact` tells it whether a stage-A filter failed); with EXACT on it always fills `o`.
 template <bool TRI, bool EXACT>
 __device__ __forceinline__ bool eval_test(const face_view& G, const double (*gv)[3], const double* q, const double* r,
-    test_out_t& o, unsigned& gp_violation)
+    test_out_t& o, unsigned& gp_violation, bool& needs_exact)
 {
     double normal[3], d = 0.0;
     int mc = 0;
@@ -228,7 +229,10 @@ __device__ __forceinline__ bool eval_test(const face_view& G, const double (*gv)
     double detr = pred::orient3d_stageA(A, B, C, r, cr, permr);
     o.exact = (uint8_t)((cq ? 0 : 1) | (cr ? 0 : 2));
     if (!cq || !cr) {
-        if (!EXACT) return false;
+        if (!EXACT) {
+            needs_exact = true;
+            return false;
+        }
         if (!cq) detq = pred::orient3d_adapt(A, B, C, q, permq);
         if (!cr) detr = pred::orient3d_adapt(A, B, C, r, permr);
     }
@@ -243,6 +247,10 @@ __device__ __forceinline__ bool eval_test(const face_view& G, const double (*gv)
     else if ((detr < 0.0 && detq < 0.0) || (detr > 0.0 && detq > 0.0)) o.type = '0';
     else o.type = '1';
     if (o.type == '0') return true;
+    // The filter kernel settles the certified non-crossings only (98 % of the tests of a dense overlap): an edge that does
+    // cross the plane — plane point, point-in-polygon, registry record — is left to the second kernel, so that this
+    // kernel's register budget is the two stage-A determinants and nothing else.
+    if (!EXACT) return false;
     if (!have_plane) mc = face_plane<TRI>(G, gv, normal, d);
     if (o.type == '1') {
         pred::segment_plane_point(o.p, normal, d, q, r); // kernel.cpp:2559-2564
@@ -363,11 +371,11 @@ template <bool TRI, bool EXACT> __global__ void __launch_bounds__(NBLOCK) k_test
     pdl_prologue();
     unsigned long long n_items;
     if (EXACT) {
-        n_items = a.counters->n_exact < a.cap_exact ? a.counters->n_exact : a.cap_exact;
+        n_items = a.counters->n_queue < a.cap_exact ? a.counters->n_queue : a.cap_exact;
     } else {
         n_items = a.counters->n_pairs < a.cap_pairs ? a.counters->n_pairs : a.cap_pairs;
     }
-    unsigned n_tests_local = 0, gp = 0;
+    unsigned n_tests_local = 0, n_exact_local = 0, gp = 0;
     for (unsigned long long it = (unsigned long long)blockIdx.x * NBLOCK + threadIdx.x; it < n_items;
          it += (unsigned long long)gridDim.x * NBLOCK) {
         unsigned long long pair_index = it;
@@ -412,38 +420,52 @@ template <bool TRI, bool EXACT> __global__ void __launch_bounds__(NBLOCK) k_test
 #pragma unroll
             for (int k = 0; k < 6; ++k) pre_ef[k] = __ldg(reinterpret_cast<const uint2*>(a.edge_f) + pre_edge[k]);
         }
-        for (uint32_t slot = EXACT ? only_slot : 0u; slot < (EXACT ? only_slot + 1u : nslots); ++slot) {
+        auto run_slot = [&](uint32_t slot) {
             uint32_t edge, tested_face;
             bool from_src;
             double q[3], r[3];
             if (!setup_test<TRI>(a, s, c, slot, hs, ns, hc, nc, sv, cv, sbox, cbox, edge, tested_face, from_src, q, r,
                     PREFETCH ? pre_edge : nullptr, PREFETCH ? pre_ef : nullptr))
-                continue;
+                return;
             test_out_t o;
-            const bool done = from_src ? eval_test<TRI, EXACT>(CF, cv, q, r, o, gp) : eval_test<TRI, EXACT>(SF, sv, q, r, o, gp);
-            if (!EXACT) n_tests_local++;
+            bool needs_exact = false;
+            const bool done = from_src ? eval_test<TRI, EXACT>(CF, cv, q, r, o, gp, needs_exact)
+                                       : eval_test<TRI, EXACT>(SF, sv, q, r, o, gp, needs_exact);
+            if (!EXACT) {
+                n_tests_local++;
+                n_exact_local += needs_exact ? 1u : 0u;
+            }
             if (!done) {
                 // slot index fits 8 bits only for faces with < 128 vertices each; larger faces are evaluated in place
                 if (nslots <= 255u) {
-                    const unsigned long long qs = alloc_slot(&a.counters->n_exact);
+                    const unsigned long long qs = alloc_slot(&a.counters->n_queue);
                     if (qs < a.cap_exact) a.exact_queue[qs] = (pair_index << 8) | slot;
-                    continue;
+                    return;
                 }
-                if (from_src) eval_test<TRI, true>(CF, cv, q, r, o, gp);
-                else eval_test<TRI, true>(SF, sv, q, r, o, gp);
+                if (from_src) eval_test<TRI, true>(CF, cv, q, r, o, gp, needs_exact);
+                else eval_test<TRI, true>(SF, sv, q, r, o, gp, needs_exact);
             }
             emit(a, edge, tested_face, o);
             log_test(a, edge, tested_face, o);
+        };
+        if (TRI && !EXACT) {
+            // six slots, unrolled: every vertex / edge-id selection below is a compile-time index (no local-memory arrays)
+#pragma unroll
+            for (uint32_t slot = 0; slot < 6u; ++slot) run_slot(slot);
+        } else {
+            for (uint32_t slot = EXACT ? only_slot : 0u; slot < (EXACT ? only_slot + 1u : nslots); ++slot) run_slot(slot);
         }
     }
     // counters: one atomic per warp
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
         n_tests_local += __shfl_xor_sync(0xffffffffu, n_tests_local, o);
+        n_exact_local += __shfl_xor_sync(0xffffffffu, n_exact_local, o);
         gp |= __shfl_xor_sync(0xffffffffu, gp, o);
     }
     if (lane_id() == 0) {
         if (n_tests_local) atomicAdd(&a.counters->n_tests, (unsigned long long)n_tests_local);
+        if (n_exact_local) atomicAdd(&a.counters->n_exact, (unsigned long long)n_exact_local);
         if (gp) atomicOr(&a.counters->gp_violation, 1u);
     }
 }
@@ -662,6 +684,7 @@ int narrowphase_run(mcb200_ctx* ctx, const mcb200_soup* soup, const mcb200_mesh*
         result_counters_t* c = res->counters.as<result_counters_t>();
         fill_list_t fl {};
         fl.add(&c->n_tests, 10, 0u); // n_tests .. n_log
+        fl.add(&c->n_queue, 2, 0u);
         fl.add(&c->gp_violation, 1, 0u);
         fl.add(&c->bad_face, 1, 0xFFFFFFFFu);
         MCB_LAUNCH(ctx, k_fill, 1, 256, 0, fl);

@@ -23,6 +23,15 @@ enum mcb200_hook_status {
     MCB200_HOOK_GENERAL_POSITION_VIOLATION = 3 // kernel.cpp:2543-2551, :2588-2597
 };
 
+// how many helper threads the calling dispatch() has (input.scheduler->get_num_threads()): the reference's registry order
+// depends on it (its parallel_for block layout), and the hook reproduces that order
+void mcb200_hook_set_scheduler_threads(uint32_t helper_threads);
+
+// the face AABBs of the dispatch (input.*_hmesh_face_aabb_array_ptr).  The device hook ignores them (its boxes never left the
+// GPU); the CPU stand-in of the tests (oracle/hook_oracle.cpp) needs them for the edge-box cull.
+void mcb200_hook_set_face_boxes(const std::vector<bounding_box_t<vec3_<double>>>* src_boxes,
+    const std::vector<bounding_box_t<vec3_<double>>>* cut_boxes);
+
 int mcb200_hook_narrowphase(
     const hmesh_t& ps, // polygon soup: source mesh + cut-mesh faces (kernel.cpp:1593-1732)
     int sm_vtx_cnt, int sm_face_count,

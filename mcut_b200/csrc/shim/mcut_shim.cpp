@@ -36,6 +36,7 @@
 
 #include "../../../include/mcut_b200.h"
 #include "mcut_hook.h"
+#include "hook_fill.h"
 
 namespace {
 
@@ -370,6 +371,10 @@ void intersectOIBVHs(std::map<fd_t, std::vector<fd_t>>& ps_face_to_potentially_i
 // ---------------------------------------------------------------------------------------------------------------------
 // Narrowphase hook (mcut_hook.h): replaces kernel.cpp:1779-3206 inside a live dispatch().
 // ---------------------------------------------------------------------------------------------------------------------
+static thread_local uint32_t t_pool_threads = 0;
+void mcb200_hook_set_scheduler_threads(uint32_t helper_threads) { t_pool_threads = helper_threads; }
+void mcb200_hook_set_face_boxes(const std::vector<bounding_box_t<vec3_<double>>>*, const std::vector<bounding_box_t<vec3_<double>>>*) {}
+
 int mcb200_hook_narrowphase(const hmesh_t& ps, int sm_vtx_cnt, int sm_face_count,
     const std::map<fd_t, std::vector<fd_t>>& ps_face_to_potentially_intersecting_others, hmesh_t& m0,
     std::unordered_map<fd_t, vec3>& ps_tested_face_to_plane_normal,
@@ -382,7 +387,7 @@ int mcb200_hook_narrowphase(const hmesh_t& ps, int sm_vtx_cnt, int sm_face_count
     std::unordered_map<fd_t, std::vector<vd_t>>& ps_iface_to_ivtx_list, bool& partial_cut_detected, int& bad_face)
 {
     scope_timer timer(t_last.from_arrays ? "narrowphase hook (arrays)" : "narrowphase hook (generic or mixed)");
-    (void)ps_face_to_potentially_intersecting_others; // the same pairs are still on the device, in t_last.res
+    // (the candidate pairs themselves are still on the device, in t_last.res; the map is only replayed for its order)
     if (!t_last.res) throw std::runtime_error("mcut_b200: narrowphase hook reached without a device broadphase on this thread");
     mcb200_ctx* ctx = t_last.ctx;
     const uint32_t nv = (uint32_t)ps.number_of_vertices(), nf = (uint32_t)ps.number_of_faces(), ne = (uint32_t)ps.number_of_edges();
@@ -498,61 +503,30 @@ int mcb200_hook_narrowphase(const hmesh_t& ps, int sm_vtx_cnt, int sm_face_count
         return MCB200_HOOK_GENERAL_POSITION_VIOLATION;
     }
 
-    // ---- plane data of the candidate faces (kernel.cpp:2184-2356) ----
+    // ---- plane data of the candidate faces (kernel.cpp:2184-2356), faces ascending ----
+    const size_t n_cand = (size_t)counts.n_cand_faces;
+    std::vector<uint32_t> cand_faces(n_cand);
     {
-        const size_t n = (size_t)counts.n_cand_faces;
-        std::vector<uint32_t> faces(n);
-        std::vector<double> normal(3 * n), d(n);
-        std::vector<int32_t> mc(n);
-        check(ctx, mcb200_result_read_planes(ctx, t_last.res, faces.data(), normal.data(), d.data(), mc.data(), n), "read_planes");
-        std::vector<vd_t> tmp;
-        for (size_t k = 0; k < n; ++k) {
-            const fd_t f(faces[k]);
-            ps_tested_face_to_plane_normal[f] = vec3(normal[3 * k], normal[3 * k + 1], normal[3 * k + 2]);
-            ps_tested_face_to_plane_normal_d_param[f] = d[k];
-            ps_tested_face_to_plane_normal_max_comp[f] = (int)mc[k];
-            std::vector<vec3>& verts = ps_tested_face_to_vertices[f];
-            ps.get_vertices_around_face(tmp, f);
-            verts.reserve(tmp.size());
-            for (const vd_t& v : tmp) verts.push_back(ps.vertex(v));
-        }
+        std::vector<double> normal(3 * n_cand), d(n_cand);
+        std::vector<int32_t> mc(n_cand);
+        check(ctx, mcb200_result_read_planes(ctx, t_last.res, cand_faces.data(), normal.data(), d.data(), mc.data(), n_cand), "read_planes");
+        mcb200_hook_dump("device", n_cand, cand_faces.data(), normal.data(), d.data(), mc.data(), nullptr, 0);
+        mcb200_hook_fill_planes(ps, n_cand, cand_faces.data(), normal.data(), d.data(), mc.data(), ps_tested_face_to_plane_normal,
+            ps_tested_face_to_plane_normal_d_param, ps_tested_face_to_plane_normal_max_comp, ps_tested_face_to_vertices);
     }
 
     // ---- the registry (kernel.cpp:2601-2655, merged form :2673-2868), records in canonical (edge, face) order ----
     std::vector<mcb200_record> rec((size_t)counts.n_records);
     check(ctx, mcb200_result_read_records(ctx, t_last.res, rec.data(), rec.size()), "read_records");
     if (own_soup) mcb200_soup_free(ctx, soup);
-    m0_ivtx_to_intersection_registry_entry.reserve(rec.size());
-    for (const mcb200_record& r : rec) {
-        const ed_t tested_edge(r.edge);
-        const fd_t tested_face(r.face);
-        const vd_t v = m0.add_vertex(vec3(r.point[0], r.point[1], r.point[2])); // ps_vtx_cnt + index in the registry
-        m0_ivtx_to_intersection_registry_entry.push_back(std::make_pair(tested_edge, tested_face));
-        ps_intersecting_edges[tested_edge].push_back(v);
-        const hd_t h0 = ps.halfedge(tested_edge, 0), h1 = ps.halfedge(tested_edge, 1);
-        const fd_t h0_face = ps.face(h0), h1_face = ps.face(h1);
-        const fd_t tested_edge_face = h0_face != hmesh_t::null_face() ? h0_face : h1_face;
-        const bool tested_edge_belongs_to_cm = ((int)tested_edge_face) >= sm_face_count;
-        const fd_t face_pqr = tested_edge_face;
-        const fd_t face_pqs = tested_edge_face == h0_face ? h1_face : hmesh_t::null_face();
-        if (tested_edge_belongs_to_cm) { // key format: {source-mesh face, cut-mesh face}
-            cutpath_edge_creation_info[make_pair(tested_face, face_pqr)].push_back(v);
-            if (face_pqs != hmesh_t::null_face()) cutpath_edge_creation_info[make_pair(tested_face, face_pqs)].push_back(v);
-        } else {
-            cutpath_edge_creation_info[make_pair(tested_edge_face, tested_face)].push_back(v);
-            const fd_t other = (tested_edge_face == h0_face) ? h1_face : h0_face;
-            if (other != hmesh_t::null_face()) cutpath_edge_creation_info[make_pair(other, tested_face)].push_back(v);
-        }
-        if (tested_edge_belongs_to_cm && (h0_face == hmesh_t::null_face() || h1_face == hmesh_t::null_face())) // ps.is_border(tested_edge)
-            cm_border_reentrant_ivtx_list.push_back(v);
-        ps_iface_to_ivtx_list[tested_face].push_back(v);
-        if (h0_face != hmesh_t::null_face()) ps_iface_to_ivtx_list[h0_face].push_back(v);
-        if (h1_face != hmesh_t::null_face()) ps_iface_to_ivtx_list[h1_face].push_back(v);
-        if (!partial_cut_detected) {
-            const bool is_cs_edge = ((int)ps.source(h0)) >= sm_vtx_cnt;
-            const bool is_border = (h0_face == hmesh_t::null_face() || h1_face == hmesh_t::null_face());
-            partial_cut_detected = (is_cs_edge && is_border);
-        }
+    if (!rec.empty() && !getenv("MCB200_CANONICAL_REGISTRY")) {
+        // registry in the reference's own order: by the rank of the edge (mcb200_reference_edge_rank), faces ascending — the
+        // records arrive sorted by (edge, face), so a stable sort on the rank is all it takes
+        const std::vector<uint32_t> rank = mcb200_hook_reference_edge_rank(ps, cand_faces.data(), n_cand, t_pool_threads);
+        std::stable_sort(rec.begin(), rec.end(), [&](const mcb200_record& a, const mcb200_record& b) { return rank[a.edge] < rank[b.edge]; });
     }
+    mcb200_hook_dump("device", 0, nullptr, nullptr, nullptr, nullptr, rec.data(), rec.size());
+    mcb200_hook_fill_registry(ps, sm_vtx_cnt, sm_face_count, rec.data(), rec.size(), m0, m0_ivtx_to_intersection_registry_entry,
+        cm_border_reentrant_ivtx_list, ps_intersecting_edges, cutpath_edge_creation_info, ps_iface_to_ivtx_list, partial_cut_detected);
     return MCB200_HOOK_OK;
 }

@@ -98,6 +98,20 @@ def soup_ids(nsv: int, src_off: np.ndarray, src_vtx: np.ndarray, cut_off: np.nda
     return fv, fe, ev[:2 * n].reshape(n, 2).copy(), ef[:2 * n].reshape(n, 2).copy()
 
 
+def reference_edge_rank(cand_faces: np.ndarray, face_off, face_edge: np.ndarray, ne: int, helper_threads: int = 0) -> np.ndarray:
+    """rank[e] = position of polygon-soup edge e in the order in which the reference registers intersection points
+    (mcb200_reference_edge_rank); the registry order is records sorted by (rank[edge], face)."""
+    cand = np.ascontiguousarray(cand_faces, dtype=np.uint32)
+    fe = np.ascontiguousarray(face_edge, dtype=np.uint32)
+    off = None if face_off is None else np.ascontiguousarray(face_off, dtype=np.uint32)
+    rank = np.zeros(max(ne, 1), dtype=np.uint32)
+    rc = _lib.lib().mcb200_reference_edge_rank(cand.size, _u32p(cand), _u32p(off) if off is not None else None, _u32p(fe), ne,
+                                               helper_threads, _u32p(rank))
+    if rc:
+        raise Mcb200Error(rc, "reference_edge_rank: invalid arguments")
+    return rank[:ne]
+
+
 class Context:
     """One device + one stream (what an MCUT context maps to)."""
 

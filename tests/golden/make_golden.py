@@ -372,6 +372,7 @@ def stage_fixture_from(src, cut, flags, td, name):
         if f"dispatch{k}_ipoints" in o:
             ip = o[f"dispatch{k}_ipoints"]
             fx[f"d{k}_ipoints_sorted"] = ip[np.lexsort((ip[:, 2], ip[:, 1], ip[:, 0]))] if len(ip) else ip
+            fx[f"d{k}_ipoints"] = ip  # in the reference's registry order (m0's intersection vertices as numbered)
     fx["cc_type"] = o["cc_type"]
     fx["cc_nv"] = o["cc_nv"]
     fx["cc_nf"] = o["cc_nf"]

@@ -242,30 +242,33 @@ def components_equivalent(a, b, tol):
 @needs_hooked
 @pytest.mark.parametrize("pair", CORPUS_CASES)
 def test_corpus_mcdispatch_with_device_narrowphase(tmp_path_factory, pair):
-    """Hooked dispatch() on the corpus.  The registry comes back in canonical (edge, face) order; the reference numbers its
-    intersection vertices in the iteration order of a std::unordered_map (kernel.cpp:1779), an accident of the STL.  Where
-    that numbering only names things the components are bit-identical as geometry (all 34 pairs without a repartition and
-    22 of the others).  Where the reference's
-    floating-polygon resolution runs (27 pairs) the numbering decides from which polygon edges the partition segment is
-    computed (preproc.cpp:1000-1126: midpoints of edge pairs, a priority queue with ties): the partition vertices then
-    agree to rounding (pairs 30, 34, 35, 58), or another equally valid segment is chosen (pair 47); the component
-    inventory (count per type and location/patch attributes) is the same in every case."""
+    """Hooked dispatch() on the corpus: broadphase AND narrowphase on the device inside a live mcDispatch.  The hook hands
+    the registry over in the reference's own order (it replays the insertion sequence of the reference's
+    std::unordered_map<ed_t, ...>, kernel.cpp:1781-1852, and the block order of its parallel_for, :2415-2868), so the
+    intersection vertices get the reference's numbers and EVERYTHING downstream — floating-polygon partition segments
+    included (27 of the pairs) — is bit-identical: every output array of every connected component, all 61 pairs."""
     fx, src, cut, flags = load_corpus(pair)
     a = _corpus_run(tmp_path_factory, "ref", pair)
     b = _corpus_run(tmp_path_factory, "hooked", pair)
     assert int(a["mcDispatch_result"][0]) == int(b["mcDispatch_result"][0]), b["_stderr"]
     assert a["cc_type"].size == b["cc_type"].size and a["cc_type"].size > 0
-    inventory = lambda o: sorted(zip(o["cc_type"].tolist(), map(tuple, np.asarray(o["cc_attrs"]).reshape(-1, 3).tolist())))  # noqa: E731
-    assert inventory(a) == inventory(b)
-    repartitioned = any(int(fx[f"d{k}_repartitioned"][0]) for k in range(int(fx["n_dispatch"][0])))
-    if not repartitioned:
-        assert components_equivalent(a, b, 0.0)
-    elif pair not in OTHER_PARTITION_SEGMENT:
-        assert components_equivalent(a, b, 1e-9)
+    for k in ("cc_type", "cc_attrs", "cc_nv", "cc_nf", "cc_vertices", "cc_faces", "cc_face_sizes"):
+        assert a[k].shape == b[k].shape and a[k].tobytes() == b[k].tobytes(), k
+    assert components_equivalent(a, b, 0.0)
 
 
-# repartition pairs where the hooked run picks another (equally valid) partition segment than the reference's numbering
-OTHER_PARTITION_SEGMENT = {47}
+@needs_hooked
+@pytest.mark.parametrize("helpers", [0, 3])
+def test_hooked_registry_order_follows_the_helper_count(tmp_path, helpers):
+    """Above 1024 candidate faces the reference's parallel_for cuts its maps into blocks, so its registry order depends on
+    the helper-thread count; the hook is told the count and reproduces either order bit for bit."""
+    src, cut, flags = cases.ALL["spheres_k64"]()
+    extra = ["--helpers", str(helpers)]
+    a = run_driver(str(tmp_path), "ref", src, cut, flags, [NODUMP], extra)
+    b = run_driver(str(tmp_path), "hooked", src, cut, flags, [NODUMP], extra, driver=HOOKED)
+    assert int(a["mcDispatch_result"][0]) == int(b["mcDispatch_result"][0]) == 0, b["_stderr"]
+    for k in ("cc_type", "cc_attrs", "cc_nv", "cc_nf", "cc_vertices", "cc_faces", "cc_face_sizes"):
+        assert a[k].shape == b[k].shape and a[k].tobytes() == b[k].tobytes(), k
 
 
 @needs_hooked
