@@ -66,7 +66,7 @@ typedef struct mcb200_soup mcb200_soup; /* device-resident polygon-soup topology
 typedef struct mcb200_result mcb200_result; /* device-resident outputs of traversal + narrowphase */
 
 /* The order in which the reference registers intersection points (= how it numbers the intersection vertices of m0):
- * the iteration order of its std::unordered_map<ed_t, ...> ps_edge_face_intersection_pairs (source/kernel.cpp:1779-1852) walked
+ * the iteration order of its hash map ps_edge_face_intersection_pairs (an unordered_map keyed by edge) (source/kernel.cpp:1779-1852) walked
  * in parallel_for blocks (include/mcut/internal/tpool.h:354-472; kernel.cpp:2415-2868).  cand_faces = the polygon-soup ids of
  * all faces that have a candidate partner, ASCENDING (the keys of ps_face_to_potentially_intersecting_others); face_off /
  * face_edge as in mcb200_soup_ids (face_off == NULL: triangles); helper_threads = the dispatch's thread-pool size.
@@ -264,6 +264,28 @@ typedef struct mcb200_host_soup {
 int mcb200_intersect_stage_host(mcb200_ctx* ctx, const mcb200_host_mesh* src, const mcb200_host_mesh* cut, const double com[3],
     const double shift[3], const double perturbation[3] /* or NULL */, double cut_eps, const mcb200_host_soup* soup,
     mcb200_result* res, uint32_t flags);
+/* Many independent dispatches in one call — the MultipleContextsInParallel pattern (tutorials/MultipleContextsInParallel/
+ * MultipleContextsInParallel.cpp:129-345: one MCUT context per task, tasks spread over threads) for dispatches that are too
+ * small to fill the machine one at a time.  `nctx` contexts of ONE device (each with its own result object) serve as
+ * lanes: item i is enqueued on lane i % nctx through mcb200_intersect_stage_host (for small meshes that is a handful of
+ * copies plus one replayed CUDA graph), a lane's previous item is collected (counts read, capacity retries done) right
+ * before the lane is reused, so up to nctx dispatches are in flight and ONE host thread feeds them.
+ * com == NULL in an item: the frame (mcb200_vertex_parameters) and the cut eps (mcb200_cut_bbox_eps with gp_constant,
+ * relative) are computed here, as the reference does per dispatch (preproc.cpp:2124-2290, :2518).  counts[i] receives the
+ * counts and status of item i.  Host arrays of ALL items must stay valid until the call returns.  Returns 0, or the first
+ * error (the remaining lanes are still drained). */
+typedef struct mcb200_batch_item {
+    mcb200_host_mesh src, cut;
+    const double* com; /* [3] or NULL: compute frame and eps here */
+    const double* shift; /* [3] */
+    const double* perturbation; /* [3] or NULL */
+    double cut_eps; /* used when com != NULL */
+    double gp_constant; /* used when com == NULL (the reference's default is 1e-4) */
+    uint32_t flags; /* MCB200_NARROW_* / MCB200_STAGE_* */
+} mcb200_batch_item;
+int mcb200_batch_intersect_host(mcb200_ctx** ctxs, mcb200_result** results, uint32_t nctx, const mcb200_batch_item* items, uint32_t n,
+    mcb200_counts* counts);
+
 /* The polygon-soup ids the last mcb200_intersect_stage_host call of this context worked with (uploaded or numbered on the
  * device): face_vtx[nh], face_edge[nh], edge_f[2*ne].  Any output may be NULL.  Synchronises. */
 int mcb200_staged_soup_read(mcb200_ctx* ctx, uint32_t* face_vtx, uint32_t* face_edge, uint32_t* edge_f, uint32_t capacity_edges,

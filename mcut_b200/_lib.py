@@ -30,6 +30,11 @@ class HostMesh(C.Structure):
                 ("nf", C.c_uint32)]
 
 
+class BatchItem(C.Structure):
+    _fields_ = [("src", HostMesh), ("cut", HostMesh), ("com", C.c_void_p), ("shift", C.c_void_p), ("perturbation", C.c_void_p),
+                ("cut_eps", C.c_double), ("gp_constant", C.c_double), ("flags", C.c_uint32)]
+
+
 class HostSoup(C.Structure):
     _fields_ = [("nh", C.c_uint32), ("ne", C.c_uint32), ("face_edge", C.c_void_p), ("edge_f", C.c_void_p)]
 
@@ -92,6 +97,8 @@ SYMBOLS = {
                                              C.POINTER(HostSoup), vp, C.c_uint32]),
     "mcb200_staged_soup_read": (C.c_int, [vp, c_u32p, c_u32p, c_u32p, C.c_uint32, c_u32p, c_u32p]),
     "mcb200_result_counts": (C.c_int, [vp, vp, C.POINTER(Counts)]),
+    "mcb200_batch_intersect_host": (C.c_int, [C.POINTER(vp), C.POINTER(vp), C.c_uint32, C.POINTER(BatchItem), C.c_uint32,
+                                              C.POINTER(Counts)]),
     "mcb200_result_read_pairs": (C.c_int, [vp, vp, c_u64p, C.c_size_t]),
     "mcb200_result_read_records": (C.c_int, [vp, vp, C.POINTER(Record), C.c_size_t]),
     "mcb200_result_read_tests": (C.c_int, [vp, vp, C.POINTER(Test), C.c_size_t]),

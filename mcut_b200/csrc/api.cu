@@ -100,6 +100,9 @@ int mcb200_ctx_create(int device, void* stream, mcb200_ctx** out)
         return (int)e;
     }
     if (const char* e = std::getenv("MCB200_PDL")) ctx->pdl = (e[0] != '0');
+    if (const char* e = std::getenv("MCB200_GRAPHS")) ctx->use_graphs = (e[0] != '0');
+    if (const char* e = std::getenv("MCB200_TWO_KERNEL_BOXES")) ctx->two_kernel_boxes = (e[0] != '0');
+    if (const char* e = std::getenv("MCB200_GRAPH_MAX_FACES")) ctx->graph_max_faces = (size_t)std::atoll(e);
     if (const char* e = std::getenv("MCB200_MORTON_SORT_BITS")) ctx->morton_sort_bits = (std::atoi(e) >= 30) ? 30 : 24;
     {
         // keep freed blocks in the stream-ordered pool instead of handing them back to the driver at every synchronisation:
@@ -168,6 +171,11 @@ void mcb200_ctx_destroy(mcb200_ctx* ctx)
     cudaEventDestroy(ctx->ev_join);
     cudaEventDestroy(ctx->ev_fork2);
     cudaEventDestroy(ctx->ev_join2);
+    for (mcb200_graph* g : ctx->graphs) {
+        if (g->exec) cudaGraphExecDestroy(g->exec);
+        delete g;
+    }
+    ctx->graphs.clear();
     if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
     for (auto& r : ctx->prof) {
         cudaEventDestroy(r.a);
@@ -503,6 +511,7 @@ int mcb200_bvh_build(mcb200_ctx* ctx, mcb200_mesh* m, double eps)
     if (!ctx || !m) return MCB200_ERR_INVALID;
     MCB_CUDA(ctx, cudaSetDevice(ctx->device));
     ctx->use_main();
+    MCB_TRY(mesh_sync_frames(ctx, m, eps));
     return lbvh_build(ctx, m, eps);
 }
 
@@ -561,7 +570,7 @@ void mcb200_result_free(mcb200_ctx* ctx, mcb200_result* r)
 {
     if (!ctx || !r) return;
     cudaSetDevice(ctx->device);
-    dbuf* all[] = { &r->counters, &r->pairs, &r->pairs_a, &r->pairs_b, &r->items, &r->cand_flag, &r->plane, &r->plane_mc, &r->exact_queue, &r->records, &r->rec_keys,
+    dbuf* all[] = { &r->counters, &r->pairs, &r->pairs_a, &r->pairs_b, &r->pair_cnt, &r->pair_off, &r->pair_tile, &r->cand_flag, &r->plane, &r->plane_mc, &r->exact_queue, &r->records, &r->rec_keys,
         &r->rec_idx, &r->records_sorted, &r->tests, &r->tests_sorted, &r->test_keys, &r->test_idx };
     for (dbuf* b : all) ctx->release(*b);
     delete r;
@@ -753,65 +762,67 @@ int mcb200_narrowphase(mcb200_ctx* ctx, const mcb200_soup* soup, const mcb200_me
     return narrowphase_run(ctx, soup, src, cut, res, flags);
 }
 
-// Issue the two builds' launches alternately: main lane <- src, aux lane <- cut.
-static int build_both_interleaved(mcb200_ctx* ctx, mcb200_mesh* src, mcb200_mesh* cut, double cut_eps)
+// ---------------------------------------------------------------------------------------------------------- the stage
+// One body for both stage entry points.  Everything is enqueued from ctx->stream outwards (aux / background lanes fork from
+// it by event and join it again before the body returns), so the body can be CAPTURED into a CUDA graph and replayed:
+//   * all allocations happen before it (stage_reserve), the frames live in device memory (mesh_sync_frames),
+//   * no host decision inside it depends on device data, every launch's arguments are functions of the signature below.
+// wait_uploads: the inputs are still travelling on ctx->copy (mcb200_intersect_stage_host without a graph): each lane waits
+// for the upload event of what it reads.  number_soup: 0 = the caller's soup as is, 1 = number the soup on the device,
+// 2 = the caller's edge ids, vertex lists derived on the device.
+static int stage_body(mcb200_ctx* ctx, mcb200_mesh* src, mcb200_mesh* cut, double cut_eps, mcb200_soup* soup, mcb200_result* res,
+    uint32_t flags, bool wait_uploads, int number_soup, bool interleave)
 {
-    std::vector<std::function<int()>> qa, qb;
     ctx->use_main();
-    ctx->recording = &qa;
-    int rc = lbvh_build(ctx, src, 0.0);
-    ctx->use_aux();
-    ctx->recording = &qb;
-    if (!rc) rc = lbvh_build(ctx, cut, cut_eps);
-    ctx->recording = nullptr;
-    ctx->use_main();
-    for (size_t i = 0; !rc && (i < qa.size() || i < qb.size()); ++i) {
-        if (i < qa.size()) rc = qa[i]();
-        if (!rc && i < qb.size()) rc = qb[i]();
-    }
-    return rc;
-}
-
-int mcb200_intersect_stage(mcb200_ctx* ctx, mcb200_mesh* src, mcb200_mesh* cut, double cut_eps, const mcb200_soup* soup,
-    mcb200_result* res, uint32_t flags)
-{
-    if (!ctx || !src || !cut || !soup || !res) return MCB200_ERR_INVALID;
-    MCB_CUDA(ctx, cudaSetDevice(ctx->device));
-    // The cut boxes always come from the UNPERTURBED cut frame (the reference builds the cut BVH on the first pass only,
-    // preproc.cpp:2676-2698); a perturbation only affects the narrowphase coordinates.
-    frame_t cut_frame = cut->frame;
-    if (cut_frame.has_pert) {
-        cut->frame.has_pert = 0;
-        for (int j = 0; j < 3; ++j) cut->frame.pert[j] = 0.0;
-    }
-    // ---- every allocation first, on the main lane (so the aux lane only ever sees memory that already exists) ----
-    ctx->use_main();
-    int rc = lbvh_reserve(ctx, src);
-    if (!rc) rc = traverse_reserve(ctx, src, cut, res);
-    if (!rc) rc = narrowphase_reserve(ctx, soup, res, flags);
-    ctx->use_aux();
-    if (!rc) rc = lbvh_reserve(ctx, cut);
-    if (!rc) rc = sort_pairs_reserve(ctx, src, cut, res);
-    ctx->use_main();
-    if (rc) {
-        cut->frame = cut_frame;
-        return rc;
-    }
     // resets that nothing before the traversal depends on: up front, not between the kernels of the critical path
-    rc = result_reset_counters(ctx, res);
-    res->counters_zeroed = (rc == 0);
-    if (!rc) rc = narrowphase_prezero(ctx, soup, res);
-    if (rc) {
-        cut->frame = cut_frame;
-        return rc;
-    }
-    // ---- the two LBVH builds side by side ----
+    MCB_TRY(result_reset_counters(ctx, res));
+    res->counters_zeroed = true;
+    MCB_TRY(narrowphase_prezero(ctx, soup, res));
     MCB_CUDA(ctx, cudaEventRecord(ctx->ev_fork, ctx->stream));
     MCB_CUDA(ctx, cudaStreamWaitEvent(ctx->aux, ctx->ev_fork, 0));
-    rc = build_both_interleaved(ctx, src, cut, cut_eps);
+    int rc = 0;
+    if (number_soup) {
+        // the polygon soup needs the face arrays only: it is numbered on the lowest-priority lane while the builds run (and,
+        // with uploads in flight, while the last coordinates still travel), and gives way to them whenever they have blocks to place
+        ctx->use_bg();
+        MCB_CUDA(ctx, cudaStreamWaitEvent(ctx->bg, ctx->ev_fork, 0));
+        if (wait_uploads) MCB_CUDA(ctx, cudaStreamWaitEvent(ctx->bg, ctx->ev_up[2], 0));
+        rc = number_soup == 1 ? soup_number_device(ctx, src, cut, soup, res->counters.as<result_counters_t>())
+                              : soup_face_vtx_device(ctx, src, cut, soup);
+        cudaEventRecord(ctx->ev_bg, ctx->bg);
+        ctx->use_main();
+        if (rc) return rc;
+    }
+    // ---- the two LBVH builds side by side: main lane <- src, aux lane <- cut ----
+    if (wait_uploads) {
+        MCB_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_up[0], 0));
+        MCB_CUDA(ctx, cudaStreamWaitEvent(ctx->aux, ctx->ev_up[1], 0));
+    }
+    if (interleave) {
+        // issue the two builds' launches alternately (the host needs ~5 us per launch: one lane's ten kernels before the
+        // other lane's first one would start that lane ~50 us late)
+        std::vector<std::function<int()>> qa, qb;
+        ctx->use_main();
+        ctx->recording = &qa;
+        rc = lbvh_build(ctx, src, 0.0);
+        ctx->use_aux();
+        ctx->recording = &qb;
+        if (!rc) rc = lbvh_build(ctx, cut, cut_eps);
+        ctx->recording = nullptr;
+        ctx->use_main();
+        for (size_t i = 0; !rc && (i < qa.size() || i < qb.size()); ++i) {
+            if (i < qa.size()) rc = qa[i]();
+            if (!rc && i < qb.size()) rc = qb[i]();
+        }
+    } else {
+        ctx->use_main();
+        rc = lbvh_build(ctx, src, 0.0);
+        ctx->use_aux();
+        if (!rc) rc = lbvh_build(ctx, cut, cut_eps);
+        ctx->use_main();
+    }
     cudaEventRecord(ctx->ev_join, ctx->aux);
     cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0);
-    cut->frame = cut_frame;
     if (rc) return rc;
     // ---- traversal, then the pair sort (aux lane) next to the narrowphase (main lane, reads the unsorted pairs) ----
     MCB_TRY(traverse_pairs(ctx, src, cut, res));
@@ -821,13 +832,158 @@ int mcb200_intersect_stage(mcb200_ctx* ctx, mcb200_mesh* src, mcb200_mesh* cut, 
     rc = sort_pairs(ctx, src, cut, res);
     cudaEventRecord(ctx->ev_join2, ctx->aux);
     ctx->use_main();
+    if (number_soup) cudaStreamWaitEvent(ctx->stream, ctx->ev_bg, 0);
+    if (wait_uploads && number_soup == 2) cudaStreamWaitEvent(ctx->stream, ctx->ev_up[3], 0);
     if (!rc) rc = narrowphase_run(ctx, soup, src, cut, res, flags);
     cudaStreamWaitEvent(ctx->stream, ctx->ev_join2, 0);
     return rc;
 }
 
-// Stage the host arrays of one mesh into the context-owned staging mesh `k` (0 source, 1 cut); copies go to ctx->copy.
-static int stage_mesh(mcb200_ctx* ctx, int k, const mcb200_host_mesh* hm, bool last, bool resident)
+// every allocation of a stage, on the main lane, before anything forks (the other lanes only ever see memory that exists)
+static int stage_reserve(mcb200_ctx* ctx, mcb200_mesh* src, mcb200_mesh* cut, const mcb200_soup* soup, mcb200_result* res, uint32_t flags)
+{
+    ctx->use_main();
+    int rc = lbvh_reserve(ctx, src);
+    if (!rc) rc = traverse_reserve(ctx, src, cut, res);
+    if (!rc) rc = narrowphase_reserve(ctx, soup, res, flags);
+    ctx->use_aux();
+    if (!rc) rc = lbvh_reserve(ctx, cut);
+    if (!rc) rc = sort_pairs_reserve(ctx, src, cut, res);
+    ctx->use_main();
+    return rc;
+}
+
+// ---- CUDA graphs ---------------------------------------------------------------------------------------------------------
+// A stage is ~40 launches on three lanes; for small dispatches (the MultipleContextsInParallel pattern: thousands of
+// 5k-triangle pairs) issuing them costs more than running them.  The body of a stage call is therefore captured the
+// SECOND time a signature is seen (the first run makes every allocation and per-function attribute call) and replayed from
+// then on: one cudaGraphLaunch per dispatch.  The signature names everything the captured launches depend on: array
+// addresses and sizes, capacities, flags, shard; the frames are not part of it (device memory).  Any buffer (re)allocation in
+// the context invalidates all graphs (alloc_epoch).  MCB200_GRAPHS=0 turns the mechanism off.
+static std::vector<uint64_t> stage_signature(const mcb200_ctx* ctx, const mcb200_mesh* src, const mcb200_mesh* cut, const mcb200_soup* soup,
+    const mcb200_result* res, uint32_t flags, int number_soup, double cut_eps_is_param)
+{
+    (void)cut_eps_is_param;
+    std::vector<uint64_t> g;
+    auto mesh = [&](const mcb200_mesh* m) {
+        g.push_back((uint64_t)(uintptr_t)m);
+        g.push_back((uint64_t)(uintptr_t)m->d_xyz);
+        g.push_back((uint64_t)(uintptr_t)m->d_face_vtx);
+        g.push_back((uint64_t)(uintptr_t)m->d_face_off);
+        g.push_back(((uint64_t)m->nv << 32) | m->nf);
+        g.push_back(((uint64_t)m->nh << 8) | (uint64_t)(m->is_float ? 1 : 0) | (uint64_t)(m->is_tri ? 2 : 0));
+    };
+    mesh(src);
+    mesh(cut);
+    g.push_back((uint64_t)(uintptr_t)soup);
+    g.push_back((uint64_t)(uintptr_t)soup->face_vtx.p);
+    g.push_back((uint64_t)(uintptr_t)soup->face_edge.p);
+    g.push_back((uint64_t)(uintptr_t)soup->edge_f.p);
+    g.push_back((uint64_t)(uintptr_t)soup->face_off.p);
+    g.push_back(((uint64_t)soup->nh << 32) | soup->ne);
+    g.push_back(((uint64_t)soup->nsf << 32) | soup->ncf);
+    g.push_back((uint64_t)(uintptr_t)res);
+    g.push_back((uint64_t)res->cap_pairs);
+    g.push_back(((uint64_t)res->shard_part << 40) | ((uint64_t)res->shard_nparts << 20) | res->shard_chunk);
+    g.push_back(((uint64_t)flags << 8) | (uint64_t)number_soup | ((uint64_t)ctx->morton_sort_bits << 40) | ((uint64_t)(ctx->pdl ? 1 : 0) << 48));
+    return g;
+}
+
+static void drop_stale_graphs(mcb200_ctx* ctx)
+{
+    for (size_t i = 0; i < ctx->graphs.size();) {
+        if (ctx->graphs[i]->epoch != ctx->alloc_epoch) {
+            if (ctx->graphs[i]->exec) cudaGraphExecDestroy(ctx->graphs[i]->exec);
+            delete ctx->graphs[i];
+            ctx->graphs.erase(ctx->graphs.begin() + (long)i);
+        } else {
+            ++i;
+        }
+    }
+}
+
+// runs the body of a stage: replayed from a graph when one exists, captured when the signature is seen for the second time
+static int stage_run(mcb200_ctx* ctx, mcb200_mesh* src, mcb200_mesh* cut, double cut_eps, mcb200_soup* soup, mcb200_result* res,
+    uint32_t flags, bool wait_uploads, int number_soup, bool interleave)
+{
+    const bool eligible = ctx->use_graphs && !ctx->profiling && !wait_uploads && src->n_prior == 0 && cut->n_prior == 0;
+    if (!eligible) return stage_body(ctx, src, cut, cut_eps, soup, res, flags, wait_uploads, number_soup, interleave);
+    drop_stale_graphs(ctx);
+    const std::vector<uint64_t> sig = stage_signature(ctx, src, cut, soup, res, flags, number_soup, cut_eps);
+    mcb200_graph* g = nullptr;
+    for (mcb200_graph* e : ctx->graphs)
+        if (e->sig == sig) g = e;
+    auto finish = [&](mcb200_graph* e) { // what a run of the body leaves behind on the host
+        const size_t cap_keep = res->cap_pairs;
+        *res = e->res_state;
+        res->cap_pairs = cap_keep;
+        res->h_valid = false;
+        src->built = cut->built = true;
+        src->groups_valid = cut->groups_valid = true;
+        src->eps = 0.0;
+        cut->eps = cut_eps;
+    };
+    if (g && g->exec) {
+        MCB_CUDA(ctx, cudaGraphLaunch(g->exec, ctx->stream));
+        ctx->launches += g->launches;
+        finish(g);
+        return 0;
+    }
+    if (!g) { // first sighting: a plain run (allocations, attribute calls), remember the signature
+        const int rc = stage_body(ctx, src, cut, cut_eps, soup, res, flags, false, number_soup, interleave);
+        if (rc) return rc;
+        if (ctx->graphs.size() < 64) {
+            g = new mcb200_graph();
+            // the run may have allocated: take the signature and the epoch as they are NOW
+            g->sig = stage_signature(ctx, src, cut, soup, res, flags, number_soup, cut_eps);
+            g->epoch = ctx->alloc_epoch;
+            ctx->graphs.push_back(g);
+        }
+        return 0;
+    }
+    if (g->refused) return stage_body(ctx, src, cut, cut_eps, soup, res, flags, false, number_soup, interleave);
+    // second sighting: capture
+    const uint64_t launches0 = ctx->launches;
+    cudaGraph_t graph = nullptr;
+    cudaError_t e = cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal);
+    int rc = 0;
+    if (e == cudaSuccess) {
+        rc = stage_body(ctx, src, cut, cut_eps, soup, res, flags, false, number_soup, false);
+        e = cudaStreamEndCapture(ctx->stream, &graph);
+    }
+    if (e == cudaSuccess && !rc && graph && g->epoch == ctx->alloc_epoch) e = cudaGraphInstantiate(&g->exec, graph, 0);
+    else if (e == cudaSuccess) e = cudaErrorUnknown;
+    if (graph) cudaGraphDestroy(graph);
+    if (e != cudaSuccess || !g->exec) {
+        cudaGetLastError(); // a failed capture leaves a sticky-looking error behind; the stream itself is fine
+        g->exec = nullptr;
+        g->refused = true;
+        if (rc) return rc;
+        return stage_body(ctx, src, cut, cut_eps, soup, res, flags, false, number_soup, interleave);
+    }
+    g->launches = ctx->launches - launches0;
+    g->res_state = *res;
+    ctx->launches = launches0;
+    MCB_CUDA(ctx, cudaGraphLaunch(g->exec, ctx->stream));
+    ctx->launches += g->launches;
+    finish(g);
+    return 0;
+}
+
+int mcb200_intersect_stage(mcb200_ctx* ctx, mcb200_mesh* src, mcb200_mesh* cut, double cut_eps, const mcb200_soup* soup,
+    mcb200_result* res, uint32_t flags)
+{
+    if (!ctx || !src || !cut || !soup || !res) return MCB200_ERR_INVALID;
+    MCB_CUDA(ctx, cudaSetDevice(ctx->device));
+    MCB_TRY(stage_reserve(ctx, src, cut, soup, res, flags));
+    // the frames into their device slots (the cut BVH is built from the UNPERTURBED cut frame: the reference builds it on the
+    // first pass only, preproc.cpp:2676-2698; a perturbation only moves the narrowphase coordinates)
+    MCB_TRY(mesh_sync_frames(ctx, src, 0.0, cut, cut_eps));
+    return stage_run(ctx, src, cut, cut_eps, const_cast<mcb200_soup*>(soup), res, flags, false, 0, true);
+}
+
+// Describe the host arrays of one mesh in the context-owned staging mesh `k` (0 source, 1 cut) and size its buffers.
+static int stage_mesh_describe(mcb200_ctx* ctx, int k, const mcb200_host_mesh* hm, bool resident, std::vector<uint32_t>& off)
 {
     if (!hm || !hm->xyz || !hm->face_vtx || hm->nv == 0 || hm->nf == 0) MCB_FAIL(ctx, MCB200_ERR_INVALID, "stage_host: empty mesh or NULL array");
     if (!ctx->st_mesh[k]) {
@@ -839,10 +995,6 @@ static int stage_mesh(mcb200_ctx* ctx, int k, const mcb200_host_mesh* hm, bool l
         // the caller vouches that this mesh's arrays are the ones of the previous call on this context: nothing travels
         if (!m->d_xyz || m->nv != hm->nv || m->nf != hm->nf || m->is_float != (hm->is_float ? 1 : 0))
             MCB_FAIL(ctx, MCB200_ERR_INVALID, "stage_host: *_RESIDENT flag, but the staged mesh has different counts (or none was staged)");
-        MCB_CUDA(ctx, cudaEventRecord(ctx->ev_fork, ctx->stream));
-        MCB_CUDA(ctx, cudaStreamWaitEvent(ctx->copy, ctx->ev_fork, 0));
-        if (last) MCB_CUDA(ctx, cudaEventRecord(ctx->ev_up[2], ctx->copy));
-        MCB_CUDA(ctx, cudaEventRecord(ctx->ev_up[k], ctx->copy));
         m->built = false;
         return 0;
     }
@@ -853,7 +1005,7 @@ static int stage_mesh(mcb200_ctx* ctx, int k, const mcb200_host_mesh* hm, bool l
     m->h_face_vtx.clear(); // host copies are only needed by mcb200_soup_from_meshes; the staged path never keeps them
     m->h_face_off.clear();
     uint32_t nh = 3u * hm->nf;
-    std::vector<uint32_t> off;
+    off.clear();
     if (hm->face_sizes) {
         off.resize((size_t)hm->nf + 1);
         uint32_t acc = 0;
@@ -871,27 +1023,37 @@ static int stage_mesh(mcb200_ctx* ctx, int k, const mcb200_host_mesh* hm, bool l
     MCB_TRY(ctx->reserve(ctx->st_xyz[k], vbytes));
     MCB_TRY(ctx->reserve(ctx->st_fv[k], sizeof(uint32_t) * (size_t)nh));
     if (!m->is_tri) MCB_TRY(ctx->reserve(ctx->st_fo[k], sizeof(uint32_t) * ((size_t)hm->nf + 1)));
-    // buffers come from the main stream's pool order: make the copy stream wait for that point
-    MCB_CUDA(ctx, cudaEventRecord(ctx->ev_fork, ctx->stream));
-    MCB_CUDA(ctx, cudaStreamWaitEvent(ctx->copy, ctx->ev_fork, 0));
-    // the mesh that travels last sends its faces first: with them the polygon soup can be numbered while the coordinates
-    // are still on their way
-    if (!last) MCB_CUDA(ctx, cudaMemcpyAsync(ctx->st_xyz[k].p, hm->xyz, vbytes, cudaMemcpyHostToDevice, ctx->copy));
-    MCB_CUDA(ctx, cudaMemcpyAsync(ctx->st_fv[k].p, hm->face_vtx, sizeof(uint32_t) * (size_t)nh, cudaMemcpyHostToDevice, ctx->copy));
-    if (!m->is_tri) {
-        // `off` is a local: this (small, polygon-only) copy must complete before it goes out of scope
-        MCB_CUDA(ctx, cudaMemcpyAsync(ctx->st_fo[k].p, off.data(), sizeof(uint32_t) * off.size(), cudaMemcpyHostToDevice, ctx->copy));
-        MCB_CUDA(ctx, cudaStreamSynchronize(ctx->copy));
-    }
-    if (last) {
-        MCB_CUDA(ctx, cudaEventRecord(ctx->ev_up[2], ctx->copy)); // all face arrays are on the device
-        MCB_CUDA(ctx, cudaMemcpyAsync(ctx->st_xyz[k].p, hm->xyz, vbytes, cudaMemcpyHostToDevice, ctx->copy));
-    }
-    MCB_CUDA(ctx, cudaEventRecord(ctx->ev_up[k], ctx->copy));
     m->d_xyz = ctx->st_xyz[k].p;
     m->d_face_vtx = ctx->st_fv[k].as<uint32_t>();
     m->d_face_off = m->is_tri ? nullptr : ctx->st_fo[k].as<uint32_t>();
     m->built = false;
+    return 0;
+}
+
+// The uploads of one mesh on stream `st`.  `last`: the mesh that travels last sends its faces first — with them the polygon
+// soup can be numbered while the coordinates are still on their way.  Records ev_up[k] (mesh landed) and, for the last mesh,
+// ev_up[2] (all face arrays landed).
+static int stage_mesh_upload(mcb200_ctx* ctx, cudaStream_t st, int k, const mcb200_host_mesh* hm, bool last, bool resident,
+    const std::vector<uint32_t>& off, bool events)
+{
+    mcb200_mesh* m = ctx->st_mesh[k];
+    if (!resident) {
+        const size_t vbytes = (size_t)hm->nv * 3 * (hm->is_float ? sizeof(float) : sizeof(double));
+        if (!last) MCB_CUDA(ctx, cudaMemcpyAsync(ctx->st_xyz[k].p, hm->xyz, vbytes, cudaMemcpyHostToDevice, st));
+        MCB_CUDA(ctx, cudaMemcpyAsync(ctx->st_fv[k].p, hm->face_vtx, sizeof(uint32_t) * (size_t)m->nh, cudaMemcpyHostToDevice, st));
+        if (!m->is_tri) {
+            // `off` is a local of the caller: this (small, polygon-only) copy must complete before it goes out of scope
+            MCB_CUDA(ctx, cudaMemcpyAsync(ctx->st_fo[k].p, off.data(), sizeof(uint32_t) * off.size(), cudaMemcpyHostToDevice, st));
+            MCB_CUDA(ctx, cudaStreamSynchronize(st));
+        }
+        if (last) {
+            if (events) MCB_CUDA(ctx, cudaEventRecord(ctx->ev_up[2], st)); // all face arrays are on the device
+            MCB_CUDA(ctx, cudaMemcpyAsync(ctx->st_xyz[k].p, hm->xyz, vbytes, cudaMemcpyHostToDevice, st));
+        }
+    } else if (last && events) {
+        MCB_CUDA(ctx, cudaEventRecord(ctx->ev_up[2], st));
+    }
+    if (events) MCB_CUDA(ctx, cudaEventRecord(ctx->ev_up[k], st));
     return 0;
 }
 
@@ -901,19 +1063,11 @@ int mcb200_intersect_stage_host(mcb200_ctx* ctx, const mcb200_host_mesh* hsrc, c
 {
     if (!ctx || !hsrc || !hcut || !res) return MCB200_ERR_INVALID;
     MCB_CUDA(ctx, cudaSetDevice(ctx->device));
-    // the previous call's kernels may still be reading the staging buffers
-    MCB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     ctx->use_main();
-    // ---- uploads, in the order the stage consumes them.  The tree-side mesh goes first: its build is the longer one
-    // (node records + climb); the query-side mesh (the one with more faces) travels last, its shorter build is the tail ----
     const bool src_res = (flags & MCB200_STAGE_SRC_RESIDENT) != 0, cut_res = (flags & MCB200_STAGE_CUT_RESIDENT) != 0;
-    if (hcut->nf > hsrc->nf) {
-        MCB_TRY(stage_mesh(ctx, 0, hsrc, false, src_res));
-        MCB_TRY(stage_mesh(ctx, 1, hcut, true, cut_res));
-    } else {
-        MCB_TRY(stage_mesh(ctx, 1, hcut, false, cut_res));
-        MCB_TRY(stage_mesh(ctx, 0, hsrc, true, src_res));
-    }
+    std::vector<uint32_t> off_s, off_c;
+    MCB_TRY(stage_mesh_describe(ctx, 0, hsrc, src_res, off_s));
+    MCB_TRY(stage_mesh_describe(ctx, 1, hcut, cut_res, off_c));
     mcb200_mesh* src = ctx->st_mesh[0];
     mcb200_mesh* cut = ctx->st_mesh[1];
     MCB_TRY(mcb200_mesh_set_frame(ctx, src, com, shift, nullptr));
@@ -937,62 +1091,100 @@ int mcb200_intersect_stage_host(mcb200_ctx* ctx, const mcb200_host_mesh* hsrc, c
         if (!soup->all_tri) MCB_TRY(ctx->reserve(soup->face_off, sizeof(uint32_t) * ((size_t)soup->nsf + soup->ncf + 1)));
     }
     // every other allocation of the stage, still before any lane forks
-    int rc = lbvh_reserve(ctx, src);
-    if (!rc) rc = traverse_reserve(ctx, src, cut, res);
-    if (!rc) rc = narrowphase_reserve(ctx, soup, res, flags);
-    ctx->use_aux();
-    if (!rc) rc = lbvh_reserve(ctx, cut);
-    if (!rc) rc = sort_pairs_reserve(ctx, src, cut, res);
-    ctx->use_main();
-    if (rc) return rc;
+    MCB_TRY(stage_reserve(ctx, src, cut, soup, res, flags));
+    const int number_soup = number_on_device ? 1 : 2;
+    // Small dispatches are bound by the cost of issuing ~45 launches, not by the uploads (a few hundred KB): everything
+    // travels on the main stream and the body is replayed from a graph.  Large ones keep the pipelined uploads on the copy
+    // stream (the builds start as each mesh lands), where the launches do not matter.
+    const bool small = ctx->use_graphs && !ctx->profiling && ((size_t)src->nf + cut->nf) <= ctx->graph_max_faces;
+    if (small) {
+        // uploads in the order of use on the main stream itself; the previous call's kernels are ahead of them in the stream
+        MCB_TRY(stage_mesh_upload(ctx, ctx->stream, 0, hsrc, false, src_res, off_s, false));
+        MCB_TRY(stage_mesh_upload(ctx, ctx->stream, 1, hcut, false, cut_res, off_c, false));
+        if (!number_on_device) {
+            MCB_CUDA(ctx, cudaMemcpyAsync(soup->face_edge.p, hsoup->face_edge, sizeof(uint32_t) * (size_t)soup->nh, cudaMemcpyHostToDevice, ctx->stream));
+            MCB_CUDA(ctx, cudaMemcpyAsync(soup->edge_f.p, hsoup->edge_f, sizeof(uint32_t) * 2 * (size_t)soup->ne, cudaMemcpyHostToDevice, ctx->stream));
+        }
+        MCB_TRY(mesh_sync_frames(ctx, src, 0.0, cut, cut_eps));
+        return stage_run(ctx, src, cut, cut_eps, soup, res, flags, false, number_soup, false);
+    }
+    // the previous call's kernels may still be reading the staging buffers
+    MCB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    // ---- uploads on the copy stream, in the order the stage consumes them: the mesh with more faces travels last ----
+    MCB_CUDA(ctx, cudaEventRecord(ctx->ev_fork, ctx->stream));
+    MCB_CUDA(ctx, cudaStreamWaitEvent(ctx->copy, ctx->ev_fork, 0));
+    if (hcut->nf > hsrc->nf) {
+        MCB_TRY(stage_mesh_upload(ctx, ctx->copy, 0, hsrc, false, src_res, off_s, true));
+        MCB_TRY(stage_mesh_upload(ctx, ctx->copy, 1, hcut, true, cut_res, off_c, true));
+    } else {
+        MCB_TRY(stage_mesh_upload(ctx, ctx->copy, 1, hcut, false, cut_res, off_c, true));
+        MCB_TRY(stage_mesh_upload(ctx, ctx->copy, 0, hsrc, true, src_res, off_s, true));
+    }
     if (!number_on_device) {
-        MCB_CUDA(ctx, cudaEventRecord(ctx->ev_fork, ctx->stream));
-        MCB_CUDA(ctx, cudaStreamWaitEvent(ctx->copy, ctx->ev_fork, 0));
         MCB_CUDA(ctx, cudaMemcpyAsync(soup->face_edge.p, hsoup->face_edge, sizeof(uint32_t) * (size_t)soup->nh, cudaMemcpyHostToDevice, ctx->copy));
         MCB_CUDA(ctx, cudaMemcpyAsync(soup->edge_f.p, hsoup->edge_f, sizeof(uint32_t) * 2 * (size_t)soup->ne, cudaMemcpyHostToDevice, ctx->copy));
         MCB_CUDA(ctx, cudaEventRecord(ctx->ev_up[3], ctx->copy));
     }
+    MCB_TRY(mesh_sync_frames(ctx, src, 0.0, cut, cut_eps));
+    return stage_body(ctx, src, cut, cut_eps, soup, res, flags, true, number_soup, false);
+}
 
-    // ---- builds: each lane starts when its mesh has landed ----
-    frame_t cut_frame = cut->frame;
-    cut->frame.has_pert = 0;
-    for (int j = 0; j < 3; ++j) cut->frame.pert[j] = 0.0;
-    // the counters are reset here, while the lanes still wait for the uploads (the soup numbering reports into them)
-    MCB_TRY(result_reset_counters(ctx, res));
-    res->counters_zeroed = true;
-    MCB_TRY(narrowphase_prezero(ctx, soup, res));
-    MCB_CUDA(ctx, cudaEventRecord(ctx->ev_fork, ctx->stream));
-    MCB_CUDA(ctx, cudaStreamWaitEvent(ctx->aux, ctx->ev_fork, 0));
-    MCB_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_up[0], 0));
-    rc = lbvh_build(ctx, src, 0.0);
-    // the polygon soup needs the face arrays only: it is numbered on the lowest-priority lane while the cut mesh's
-    // coordinates still travel, and gives way to the builds whenever they have blocks to place
-    ctx->use_bg();
-    MCB_CUDA(ctx, cudaStreamWaitEvent(ctx->bg, ctx->ev_fork, 0));
-    MCB_CUDA(ctx, cudaStreamWaitEvent(ctx->bg, ctx->ev_up[2], 0));
-    if (!rc) rc = number_on_device ? soup_number_device(ctx, src, cut, soup, res->counters.as<result_counters_t>())
-                                   : soup_face_vtx_device(ctx, src, cut, soup);
-    cudaEventRecord(ctx->ev_bg, ctx->bg);
-    ctx->use_aux();
-    cudaStreamWaitEvent(ctx->aux, ctx->ev_up[1], 0);
-    if (!rc) rc = lbvh_build(ctx, cut, cut_eps);
-    cudaEventRecord(ctx->ev_join, ctx->aux);
-    ctx->use_main();
-    cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0);
-    cut->frame = cut_frame;
-    if (rc) return rc;
-    MCB_TRY(traverse_pairs(ctx, src, cut, res));
-    MCB_CUDA(ctx, cudaEventRecord(ctx->ev_fork2, ctx->stream));
-    MCB_CUDA(ctx, cudaStreamWaitEvent(ctx->aux, ctx->ev_fork2, 0));
-    ctx->use_aux();
-    rc = sort_pairs(ctx, src, cut, res);
-    cudaEventRecord(ctx->ev_join2, ctx->aux);
-    ctx->use_main();
-    cudaStreamWaitEvent(ctx->stream, ctx->ev_bg, 0);
-    if (!number_on_device) cudaStreamWaitEvent(ctx->stream, ctx->ev_up[3], 0);
-    if (!rc) rc = narrowphase_run(ctx, soup, src, cut, res, flags);
-    cudaStreamWaitEvent(ctx->stream, ctx->ev_join2, 0);
-    return rc;
+int mcb200_batch_intersect_host(mcb200_ctx** ctxs, mcb200_result** results, uint32_t nctx, const mcb200_batch_item* items, uint32_t n,
+    mcb200_counts* counts)
+{
+    if (!ctxs || !results || nctx == 0 || (n && (!items || !counts))) return MCB200_ERR_INVALID;
+    for (uint32_t k = 0; k < nctx; ++k)
+        if (!ctxs[k] || !results[k]) return MCB200_ERR_INVALID;
+    struct frame_of_item {
+        double com[3], shift[3], eps;
+    };
+    std::vector<frame_of_item> fr(nctx); // the frame of the item a lane is working on
+    std::vector<uint32_t> in_flight(nctx, MCB200_NULL);
+    int first_error = 0;
+    auto enqueue = [&](uint32_t lane, uint32_t i) -> int {
+        const mcb200_batch_item& it = items[i];
+        frame_of_item& f = fr[lane];
+        const double *com = it.com, *shift = it.shift;
+        double eps = it.cut_eps;
+        if (!com) {
+            double sb[6], cb[6];
+            if (it.src.is_float != it.cut.is_float) return MCB200_ERR_INVALID;
+            mcb200_vertex_parameters(it.src.is_float, it.src.xyz, it.src.nv, it.cut.xyz, it.cut.nv, f.com, f.shift, sb, cb);
+            f.eps = mcb200_cut_bbox_eps(cb, it.gp_constant > 0.0 ? it.gp_constant : 1e-4, 0);
+            com = f.com;
+            shift = f.shift;
+            eps = f.eps;
+        }
+        return mcb200_intersect_stage_host(ctxs[lane], &it.src, &it.cut, com, shift, it.perturbation, eps, nullptr, results[lane], it.flags);
+    };
+    auto collect = [&](uint32_t lane) -> int {
+        const uint32_t i = in_flight[lane];
+        if (i == MCB200_NULL) return 0;
+        in_flight[lane] = MCB200_NULL;
+        int rc = mcb200_result_counts(ctxs[lane], results[lane], &counts[i]);
+        for (int attempt = 0; rc == MCB200_ERR_CAPACITY && attempt < 4; ++attempt) { // a buffer was too small: it has grown, run again
+            rc = enqueue(lane, i);
+            if (!rc) rc = mcb200_result_counts(ctxs[lane], results[lane], &counts[i]);
+        }
+        return rc;
+    };
+    for (uint32_t i = 0; i < n; ++i) {
+        const uint32_t lane = i % nctx;
+        int rc = collect(lane);
+        if (!rc) rc = enqueue(lane, i);
+        if (rc) {
+            if (!first_error) first_error = rc;
+            std::memset(&counts[i], 0, sizeof(mcb200_counts));
+            counts[i].status = -1;
+            continue;
+        }
+        in_flight[lane] = i;
+    }
+    for (uint32_t lane = 0; lane < nctx; ++lane) {
+        const int rc = collect(lane);
+        if (rc && !first_error) first_error = rc;
+    }
+    return first_error;
 }
 
 // Reads back the polygon-soup ids the last mcb200_intersect_stage_host call used (tests: device numbering == mcb200_soup_ids).

@@ -96,6 +96,12 @@ struct mcb200_ctx {
     int morton_sort_bits = 24; // the build sorts the leaves on the top 24 of the 30 Morton bits: 3 radix passes (MCB200_MORTON_SORT_BITS=30: all four)
     bool pdl = true; // programmatic dependent launch between in-stream kernels (MCB200_PDL=0 turns it off)
     bool sort_smem_opt_in[4] = { false, false, false, false }; // radix_sort.cuh: dynamic shared memory opt-in done
+    bool traverse_smem_opt_in = false;
+    bool two_kernel_boxes = false; // MCB200_TWO_KERNEL_BOXES=1: face boxes and Morton codes in two kernels (lbvh.cu)
+    // CUDA graphs of stage bodies (api.cu)
+    bool use_graphs = true;
+    size_t graph_max_faces = 400000; // mcb200_intersect_stage_host: above this the pipelined-upload path is used instead
+    std::vector<struct mcb200_graph*> graphs;
     void use_main() { cur = stream; sci = 0; }
     void use_aux() { cur = aux; sci = 1; }
     void use_bg() { cur = bg; sci = 0; } // kernels on this lane bring their own buffers, never the sort scratch
@@ -104,9 +110,11 @@ struct mcb200_ctx {
     {
         error = msg + " (" + file + ":" + std::to_string(line) + ")";
     }
+    uint64_t alloc_epoch = 0; // bumped whenever a device buffer moves: captured graphs hold raw pointers
     int reserve(dbuf& b, size_t bytes)
     {
         if (bytes <= b.cap) return 0;
+        ++alloc_epoch;
         // grow geometrically so repeated dispatches of growing size do not reallocate every time
         size_t want = bytes + bytes / 4 + 256;
         if (b.p) {
@@ -128,6 +136,7 @@ struct mcb200_ctx {
     }
     void release(dbuf& b)
     {
+        if (b.p) ++alloc_epoch;
         if (b.p) cudaFreeAsync(b.p, stream);
         b.p = nullptr;
         b.cap = 0;
@@ -158,7 +167,10 @@ struct frame_t {
     int has_frame; // 0: vertices already are internal coordinates
     int has_pert;
     int is_float;
+    int pad_;
+    double eps; // enlargement of the face boxes (the build's frame only)
 };
+static_assert(sizeof(frame_t) % 8 == 0, "frame_t is copied word by word");
 
 struct mcb200_mesh {
     uint32_t nv = 0, nf = 0, nh = 0;
@@ -169,6 +181,13 @@ struct mcb200_mesh {
     const uint32_t* d_face_vtx = nullptr; // [nh]
     const uint32_t* d_face_off = nullptr; // [nf+1] or nullptr for triangles
     frame_t frame;
+    // The kernels read the frame from DEVICE memory (so that a captured launch sequence can be replayed for another frame):
+    // d_frames[0] = the build's frame (perturbation stripped: the reference builds the cut BVH from the unperturbed mesh,
+    // preproc.cpp:2676-2698; eps = the face-box enlargement), d_frames[1] = the narrowphase's frame.  dev_frames = what is there.
+    dbuf d_frames;
+    frame_t dev_frames[2];
+    bool dev_frames_valid = false;
+    void* dev_frames_ptr = nullptr;
     // host copies of the face arrays (needed by mcb200_soup_from_meshes)
     std::vector<uint32_t> h_face_vtx, h_face_off;
     // build products
@@ -251,11 +270,12 @@ struct result_counters_t {
     unsigned int gp_violation;
     unsigned int bad_face; // min polygon-soup id of a degenerate candidate face, 0xFFFFFFFF if none
     unsigned int pair_overflow;
-    unsigned int work_counter; // number of traversal work items (k_group_top)
+    unsigned int work_counter; // ticket counter of the traversal: next query group to hand out
     unsigned int soup_error; // device-side soup numbering: an edge with three faces or two faces wound the same way
     unsigned int soup_ne; // number of polygon-soup edges it found
     unsigned long long n_queue; // tests the filter kernel handed to the second kernel (stage-A failures + crossings)
-    unsigned int pad[4];
+    unsigned int pair_seg_max; // most candidate pairs of one source face (decides how the pair list is put in order)
+    unsigned int pad[3];
 };
 static_assert(offsetof(result_counters_t, n_queue) % 8 == 0, "n_queue is atomically incremented as a 64-bit word");
 
@@ -263,8 +283,8 @@ struct mcb200_result {
     dbuf counters; // result_counters_t
     dbuf pairs; // u64 [cap_pairs], in the order the traversal emitted them (what the narrowphase consumes)
     dbuf pairs_a, pairs_b; // ping-pong buffers of the pair sort
-    dbuf items; // uint2 [cap_items]: (query group, node of the other tree's level S) pairs whose boxes overlap (traverse.cu: k_group_top)
-    size_t cap_items = 0;
+    dbuf pair_cnt, pair_off, pair_tile; // per source face: pair count / cursor, first slot in the ordered list; tile sums of the scan
+    void* pair_cnt_zeroed = nullptr; // the count array is all zero between runs (each run clears what it touched)
     unsigned long long* pairs_sorted = nullptr; // ascending (src << 32 | cut): points into pairs_a or pairs_b
     size_t cap_pairs = 0;
     bool cand_flag_fresh = false; // candidate flags already cleared for the coming narrowphase
@@ -291,6 +311,17 @@ struct mcb200_result {
     bool records_sorted_valid = false, tests_sorted_valid = false;
     result_counters_t h; // last host copy
     bool h_valid = false;
+};
+
+// a captured stage body (api.cu: stage_run)
+struct mcb200_graph {
+    std::vector<uint64_t> sig;
+    uint64_t epoch = 0;
+    cudaGraphExec_t exec = nullptr; // nullptr: seen once, not captured yet
+    bool refused = false; // capture failed once: do not try again
+    uint64_t launches = 0;
+    mcb200_result res_state; // host-side bookkeeping of the result after a run of the body
+    double src_eps = 0.0, cut_eps = 0.0;
 };
 
 // ------------------------------------------------------------------------------------------------------------
@@ -376,9 +407,9 @@ __device__ __forceinline__ void pdl_prologue()
 // Several small fills in ONE launch (a cudaMemsetAsync per counter block costs a stream operation each, and every one
 // of them breaks the programmatic launch chain between the kernels around it).
 struct fill_list_t {
-    unsigned* p[8];
-    unsigned words[8];
-    unsigned value[8];
+    unsigned* p[10];
+    unsigned words[10];
+    unsigned value[10];
     int n;
     void add(void* ptr, size_t nwords, unsigned v)
     {
@@ -393,6 +424,27 @@ static __global__ void __launch_bounds__(256) k_fill(fill_list_t L)
     pdl_prologue();
     for (int e = 0; e < L.n; ++e)
         for (unsigned i = blockIdx.x * 256u + threadIdx.x; i < L.words[e]; i += gridDim.x * 256u) L.p[e][i] = L.value[e];
+}
+
+// the frames of up to two meshes into their device slots (kernel parameters: no staging buffer, no synchronisation)
+struct frame_pack_t {
+    frame_t* dst[2];
+    frame_t f[2][2];
+    int n;
+};
+static __global__ void __launch_bounds__(128) k_set_frames(frame_pack_t p)
+{
+    pdl_prologue();
+    constexpr unsigned W = sizeof(frame_t) / 4;
+    for (int m = 0; m < p.n; ++m)
+        if (threadIdx.x < 2 * W) reinterpret_cast<unsigned*>(p.dst[m])[threadIdx.x] = reinterpret_cast<const unsigned*>(&p.f[m][0])[threadIdx.x];
+}
+
+// block-wide copy of a frame from device memory into shared memory (first statement group of the kernels that use frames)
+__device__ __forceinline__ void load_frame_shared(frame_t* s_dst, const frame_t* __restrict__ g_src)
+{
+    constexpr unsigned W = sizeof(frame_t) / 4;
+    if (threadIdx.x < W) reinterpret_cast<unsigned*>(s_dst)[threadIdx.x] = __ldg(reinterpret_cast<const unsigned*>(g_src) + threadIdx.x);
 }
 
 static inline unsigned div_up(size_t a, size_t b) { return (unsigned)((a + b - 1) / b); }

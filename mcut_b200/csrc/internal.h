@@ -4,6 +4,9 @@
 #include "common.cuh"
 
 // lbvh.cu
+// puts the frames of the given meshes (build frame with `eps`, narrowphase frame) into their device slots when they changed;
+// enqueued on ctx->cur — call it before forking lanes
+int mesh_sync_frames(mcb200_ctx* ctx, mcb200_mesh* a, double eps_a, mcb200_mesh* b = nullptr, double eps_b = 0.0);
 int lbvh_reserve(mcb200_ctx* ctx, mcb200_mesh* mesh);
 int lbvh_build(mcb200_ctx* ctx, mcb200_mesh* mesh, double eps);
 // traverse.cu

@@ -43,11 +43,16 @@ __device__ __forceinline__ unsigned morton3D(float x, float y, float z)
 // ---- K_aabb -----------------------------------------------------------------------------------------------------
 // One thread per face, grid-stride; the block's union goes to the mesh AABB through 6 ordered-integer atomics.
 template <bool TRI>
-__global__ void __launch_bounds__(BLOCK) k_face_bbox(const void* __restrict__ xyz, frame_t fr,
-    const uint32_t* __restrict__ face_vtx, const uint32_t* __restrict__ face_off, uint32_t nf, double eps,
+__global__ void __launch_bounds__(BLOCK) k_face_bbox(const void* __restrict__ xyz, const frame_t* __restrict__ frp,
+    const uint32_t* __restrict__ face_vtx, const uint32_t* __restrict__ face_off, uint32_t nf,
     double* __restrict__ face_bbox, unsigned long long* __restrict__ root_ordered, const double* __restrict__ prior, uint32_t n_prior)
 {
     pdl_prologue();
+    __shared__ frame_t s_fr;
+    load_frame_shared(&s_fr, frp);
+    __syncthreads();
+    const frame_t& fr = s_fr;
+    const double eps = s_fr.eps;
     double bmin[3] = { DBL_MAX, DBL_MAX, DBL_MAX }, bmax[3] = { -DBL_MAX, -DBL_MAX, -DBL_MAX };
     for (uint32_t f = blockIdx.x * BLOCK + threadIdx.x; f < nf; f += gridDim.x * BLOCK) {
         const uint32_t h0 = TRI ? 3u * f : face_off[f];
@@ -170,6 +175,170 @@ __global__ void __launch_bounds__(BLOCK) k_morton(const double* __restrict__ fac
     }
 }
 
+// ---- K_vertex_bbox + K_face_codes: the first two kernels in one ---------------------------------------------------------
+// The Morton code of a face needs the mesh AABB, which is the union of all face boxes — a grid-wide dependency that used to
+// cost a second kernel re-reading all 48-byte boxes.  But the union of the face boxes is the box of the VERTICES, enlarged
+// by eps (every vertex of a mesh the reference accepts belongs to a face — check_input_mesh, preproc.cpp:505-578, rejects
+// stray vertices — and x -> x -/+ eps is monotone, so min/max and the enlargement commute bit for bit).  A pass over the
+// vertices (a quarter of the bytes) yields it up front; one kernel then gathers each face once and writes box, code and sort
+// key together.  The mesh AABB that is RETURNED is still reduced from the face boxes themselves, so it is exact whatever
+// the input.  Meshes that carry prior boxes (the in/out vector after a repartition) take the two-kernel path.
+__global__ void __launch_bounds__(BLOCK) k_vertex_bbox(const void* __restrict__ xyz, const frame_t* __restrict__ frp, uint32_t nv,
+    unsigned long long* __restrict__ vroot_ordered)
+{
+    pdl_prologue();
+    __shared__ frame_t s_fr;
+    load_frame_shared(&s_fr, frp);
+    __syncthreads();
+    double bmin[3] = { DBL_MAX, DBL_MAX, DBL_MAX }, bmax[3] = { -DBL_MAX, -DBL_MAX, -DBL_MAX };
+    for (uint32_t v = blockIdx.x * BLOCK + threadIdx.x; v < nv; v += gridDim.x * BLOCK) {
+        double p[3];
+        load_vertex(xyz, s_fr, v, p);
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+            bmax[j] = ref_max(bmax[j], p[j]);
+            bmin[j] = ref_min(bmin[j], p[j]);
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            bmin[j] = fmin(bmin[j], __shfl_xor_sync(0xffffffffu, bmin[j], o));
+            bmax[j] = fmax(bmax[j], __shfl_xor_sync(0xffffffffu, bmax[j], o));
+        }
+    }
+    __shared__ double s_min[BLOCK / 32][3], s_max[BLOCK / 32][3];
+    const unsigned w = threadIdx.x >> 5;
+    if (lane_id() == 0) {
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+            s_min[w][j] = bmin[j];
+            s_max[w][j] = bmax[j];
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x < 6) {
+        const int j = threadIdx.x % 3;
+        if (threadIdx.x < 3) {
+            double v = s_min[0][j];
+            for (int i = 1; i < BLOCK / 32; ++i) v = fmin(v, s_min[i][j]);
+            if (v != DBL_MAX) atomicMin(vroot_ordered + j, dbl_to_ordered(v));
+        } else {
+            double v = s_max[0][j];
+            for (int i = 1; i < BLOCK / 32; ++i) v = fmax(v, s_max[i][j]);
+            if (v != -DBL_MAX) atomicMax(vroot_ordered + 3 + j, dbl_to_ordered(v));
+        }
+    }
+}
+
+template <bool TRI>
+__global__ void __launch_bounds__(BLOCK) k_face_codes(const void* __restrict__ xyz, const frame_t* __restrict__ frp,
+    const uint32_t* __restrict__ face_vtx, const uint32_t* __restrict__ face_off, uint32_t nf, double* __restrict__ face_bbox,
+    const unsigned long long* __restrict__ vroot_ordered, unsigned long long* __restrict__ root_ordered, uint32_t* __restrict__ codes,
+    uint32_t* __restrict__ sort_keys, unsigned* __restrict__ hist /* [4][256] */, unsigned* __restrict__ status, unsigned status_words,
+    unsigned key_shift, int npasses)
+{
+    pdl_prologue();
+    __shared__ frame_t s_fr;
+    __shared__ unsigned s_hist[4 * 256];
+    load_frame_shared(&s_fr, frp);
+    for (int i = threadIdx.x; i < 4 * 256; i += BLOCK) s_hist[i] = 0;
+    for (unsigned i = blockIdx.x * BLOCK + threadIdx.x; i < status_words; i += gridDim.x * BLOCK) status[i] = 0u;
+    __syncthreads();
+    const frame_t& fr = s_fr;
+    const double eps = s_fr.eps;
+    // the mesh AABB the codes are normalised with: vertex box enlarged like every face box is (bvh.cpp:262-272, :330-368)
+    double rmin[3], dims[3];
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+        double lo = ordered_to_dbl(vroot_ordered[j]), hi = ordered_to_dbl(vroot_ordered[3 + j]);
+        if (eps > 0.0) {
+            hi = __dadd_rn(hi, eps);
+            lo = __dsub_rn(lo, eps);
+        }
+        rmin[j] = lo;
+        dims[j] = __dsub_rn(hi, lo);
+    }
+    double bmin[3] = { DBL_MAX, DBL_MAX, DBL_MAX }, bmax[3] = { -DBL_MAX, -DBL_MAX, -DBL_MAX };
+    for (uint32_t f = blockIdx.x * BLOCK + threadIdx.x; f < nf; f += gridDim.x * BLOCK) {
+        const uint32_t h0 = TRI ? 3u * f : face_off[f];
+        const uint32_t h1 = TRI ? h0 + 3u : face_off[f + 1];
+        double mn[3] = { DBL_MAX, DBL_MAX, DBL_MAX }, mx[3] = { -DBL_MAX, -DBL_MAX, -DBL_MAX };
+        for (uint32_t h = h0; h < h1; ++h) {
+            double p[3];
+            load_vertex(xyz, fr, __ldg(face_vtx + h), p);
+#pragma unroll
+            for (int j = 0; j < 3; ++j) {
+                mx[j] = ref_max(mx[j], p[j]);
+                mn[j] = ref_min(mn[j], p[j]);
+            }
+        }
+        if (eps > 0.0) {
+#pragma unroll
+            for (int j = 0; j < 3; ++j) {
+                mx[j] = __dadd_rn(mx[j], eps);
+                mn[j] = __dsub_rn(mn[j], eps);
+            }
+        }
+        double* out = face_bbox + 6 * (size_t)f;
+        reinterpret_cast<double2*>(out)[0] = make_double2(mn[0], mn[1]);
+        reinterpret_cast<double2*>(out)[1] = make_double2(mn[2], mx[0]);
+        reinterpret_cast<double2*>(out)[2] = make_double2(mx[1], mx[2]);
+        float nrm[3];
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+            bmax[j] = ref_max(bmax[j], mx[j]);
+            bmin[j] = ref_min(bmin[j], mn[j]);
+            const double centre = __dadd_rn(mn[j], mx[j]) / 2; // bvh.cpp:275
+            const double off = __dsub_rn(centre, rmin[j]); // bvh.cpp:382
+            nrm[j] = (float)(off / dims[j]); // bvh.cpp:399-402
+        }
+        const uint32_t code = morton3D(nrm[0], nrm[1], nrm[2]);
+        codes[f] = code;
+        const uint32_t key = code >> key_shift;
+        sort_keys[f] = key;
+#pragma unroll
+        for (int p = 0; p < 4; ++p)
+            if (p < npasses) atomicAdd(&s_hist[p * 256 + ((key >> (8 * p)) & 255u)], 1u);
+    }
+    // the returned mesh AABB: reduced from the face boxes themselves
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            bmin[j] = fmin(bmin[j], __shfl_xor_sync(0xffffffffu, bmin[j], o));
+            bmax[j] = fmax(bmax[j], __shfl_xor_sync(0xffffffffu, bmax[j], o));
+        }
+    }
+    __shared__ double s_min[BLOCK / 32][3], s_max[BLOCK / 32][3];
+    const unsigned w = threadIdx.x >> 5;
+    if (lane_id() == 0) {
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+            s_min[w][j] = bmin[j];
+            s_max[w][j] = bmax[j];
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x < 6) {
+        const int j = threadIdx.x % 3;
+        if (threadIdx.x < 3) {
+            double v = s_min[0][j];
+            for (int i = 1; i < BLOCK / 32; ++i) v = fmin(v, s_min[i][j]);
+            if (v != DBL_MAX) atomicMin(root_ordered + j, dbl_to_ordered(v));
+        } else {
+            double v = s_max[0][j];
+            for (int i = 1; i < BLOCK / 32; ++i) v = fmax(v, s_max[i][j]);
+            if (v != -DBL_MAX) atomicMax(root_ordered + 3 + j, dbl_to_ordered(v));
+        }
+    }
+    for (int i = threadIdx.x; i < 4 * 256; i += BLOCK) {
+        const unsigned c = s_hist[i];
+        if (c) atomicAdd(&hist[i], c);
+    }
+}
+
 // 24 bytes, 8-byte aligned
 __device__ __forceinline__ void store_box(float* dst, const float* b) // 24 bytes, 8-byte aligned
 {
@@ -248,28 +417,23 @@ __device__ __forceinline__ void empty_box(float* b)
     b[3] = b[4] = b[5] = -FLT_MAX;
 }
 
-// Segmented scans of the 32 boxes of one chunk (lane = leaf), segments starting at the lanes whose bit is set in `heads`:
-//   pre[c] = union of the boxes from the start of the lane's segment (or of the chunk) up to the lane,
-//   suf[c] = union from the lane to the end of its segment (or of the chunk).
-__device__ __forceinline__ void segmented_unions(const float* box, unsigned heads, float* pre, float* suf)
+// Segmented SUFFIX union of the 32 boxes of one chunk (lane = leaf; a segment starts at every lane whose bit is set in
+// `heads`, the lanes below the first head form a segment of their own): suf = union of the boxes from the lane to the end of
+// its segment.  At a head lane that is its group's box (as far as this chunk goes); at lane 0, when it is no head, it is
+// the part of the previous chunk's last group that lies in this chunk.  (redux.sync per segment mask was tried: fewer
+// instructions, but slower than these five shuffle rounds.)
+__device__ __forceinline__ void segmented_suffix_union(const float* box, unsigned heads, float* suf)
 {
     const unsigned lane = lane_id();
 #pragma unroll
-    for (int c = 0; c < 6; ++c) pre[c] = suf[c] = box[c];
+    for (int c = 0; c < 6; ++c) suf[c] = box[c];
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
-        // lanes (lane - d, lane] hold no segment start: the value d lanes below belongs to the same segment
-        const bool up = lane >= (unsigned)d && ((heads >> (lane - d + 1u)) & ((1u << d) - 1u)) == 0u;
-        // lanes (lane, lane + d] hold no segment start
+        // lanes (lane, lane + d] hold no segment start: the value d lanes above belongs to the same segment
         const bool down = lane + d < 32u && ((heads >> (lane + 1u)) & ((1u << d) - 1u)) == 0u;
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
-            const float pu = __shfl_up_sync(0xffffffffu, pre[c], d), pU = __shfl_up_sync(0xffffffffu, pre[3 + c], d);
             const float sd = __shfl_down_sync(0xffffffffu, suf[c], d), sD = __shfl_down_sync(0xffffffffu, suf[3 + c], d);
-            if (up) {
-                pre[c] = fminf(pre[c], pu);
-                pre[3 + c] = fmaxf(pre[3 + c], pU);
-            }
             if (down) {
                 suf[c] = fminf(suf[c], sd);
                 suf[3 + c] = fmaxf(suf[3 + c], sD);
@@ -280,13 +444,15 @@ __device__ __forceinline__ void segmented_unions(const float* box, unsigned head
 
 __global__ void __launch_bounds__(LB_THREADS, 3) k_leaves(const uint32_t* __restrict__ codes, const double* __restrict__ face_bbox,
     const uint32_t* __restrict__ sorted_faces, uint32_t nf, float* __restrict__ wide, double* __restrict__ sorted_bbox, wide_levels_t lv,
-    uint2* __restrict__ groups, group_box_t* __restrict__ group_box, unsigned* __restrict__ n_groups, unsigned* __restrict__ done_ticket)
+    uint2* __restrict__ groups, group_box_t* __restrict__ group_box, unsigned* __restrict__ n_groups, unsigned* __restrict__ done_ticket,
+    const unsigned long long* __restrict__ root_ordered, double* __restrict__ root_decoded)
 {
     pdl_prologue();
+    if (blockIdx.x == 0 && threadIdx.x < 6) root_decoded[threadIdx.x] = ordered_to_dbl(root_ordered[threadIdx.x]); // the mesh AABB callers read
     __shared__ uint32_t s_code[LB_WIN];
     // s_lam[0]: delta + 1 of the boundary before window leaf k (0 at the ends of the array); s_lam[t]: minimum over 2^t boundaries
     __shared__ uint8_t s_lam[LB_LOG][LB_WIN];
-    __shared__ float s_pre[6][LB_BOXES]; // per chunk of 32 leaves: union from the start of the leaf's segment (or chunk) up to the leaf
+    __shared__ float s_pre[6][LB_BOXES / 32]; // per chunk of 32 leaves: union of the leaves BEFORE its first group start (the tail of a group of the previous chunk)
     __shared__ uint32_t s_flag[LB_BOXES / 32 + 2];
     __shared__ float s_l1[6][32];
     __shared__ unsigned s_warp[LB_THREADS / 32], s_base, s_ticket;
@@ -400,10 +566,13 @@ __global__ void __launch_bounds__(LB_THREADS, 3) k_leaves(const uint32_t* __rest
         } else {
             empty_box(fb);
         }
-        float pre[6], sf[6];
-        segmented_unions(fb, s_flag[q], pre, sf);
+        // union over the lane's own segment: for a head lane that is its group (as far as this chunk goes), for lane 0 — when
+        // it is no head — the part of the previous chunk's last group that lies in this chunk
+        float sf[6];
+        segmented_suffix_union(fb, s_flag[q], sf);
+        if (lane == 0)
 #pragma unroll
-        for (int c = 0; c < 6; ++c) s_pre[c][32u * q + lane] = pre[c];
+            for (int c = 0; c < 6; ++c) s_pre[c][q] = sf[c];
         if (i < LB_ITEMS) {
 #pragma unroll
             for (int c = 0; c < 6; ++c) suf[i][c] = sf[c];
@@ -436,11 +605,11 @@ __global__ void __launch_bounds__(LB_THREADS, 3) k_leaves(const uint32_t* __rest
                 } else {
                     const unsigned t = (unsigned)__ffs((int)s_flag[q + 1u]) - 1u; // leaves of the next chunk that still belong
                     cnt_of[i] = 32u - lane + t;
-                    if (t > 0u) {
+                    if (t > 0u) { // lane 0 of the next chunk is no head: its segment is the rest of this group
 #pragma unroll
                         for (int c = 0; c < 3; ++c) {
-                            suf[i][c] = fminf(suf[i][c], s_pre[c][(q + 1u) * 32u + t - 1u]);
-                            suf[i][3 + c] = fmaxf(suf[i][3 + c], s_pre[3 + c][(q + 1u) * 32u + t - 1u]);
+                            suf[i][c] = fminf(suf[i][c], s_pre[c][q + 1u]);
+                            suf[i][3 + c] = fmaxf(suf[i][3 + c], s_pre[3 + c][q + 1u]);
                         }
                     }
                 }
@@ -552,13 +721,14 @@ int lbvh_reserve(mcb200_ctx* ctx, mcb200_mesh* m)
     if (!m->lv) m->lv = new wide_levels_t();
     make_levels(nf, *m->lv);
     MCB_TRY(ctx->reserve(m->face_bbox, sizeof(double) * 6 * (size_t)nf));
-    MCB_TRY(ctx->reserve(m->root, sizeof(unsigned long long) * 6 + sizeof(double) * 6));
+    MCB_TRY(ctx->reserve(m->root, sizeof(unsigned long long) * 6 + sizeof(double) * 6 + sizeof(unsigned long long) * 6));
     MCB_TRY(ctx->reserve(m->codes, sizeof(uint32_t) * (size_t)nf));
     MCB_TRY(ctx->reserve(m->sorted_codes, sizeof(uint32_t) * (size_t)nf));
     MCB_TRY(ctx->reserve(m->sorted_faces, sizeof(uint32_t) * (size_t)nf));
     MCB_TRY(ctx->reserve(m->wide, sizeof(float) * MCB_WBLOCK_FLOATS * wide_blocks(*m->lv)));
     MCB_TRY(ctx->reserve(m->sorted_bbox, sizeof(double) * 6 * (size_t)nf));
     MCB_TRY(ctx->reserve(m->flags, sizeof(unsigned) * 4));
+    MCB_TRY(ctx->reserve(m->d_frames, sizeof(frame_t) * 2));
     MCB_TRY(ctx->reserve(m->groups, sizeof(uint2) * (size_t)nf + sizeof(unsigned) * 4));
     MCB_TRY(ctx->reserve(m->group_box, sizeof(group_box_t) * (size_t)nf));
     MCB_TRY((rsort::reserve_scratch<uint32_t>(ctx, nf, 4, true, true)));
@@ -567,6 +737,37 @@ int lbvh_reserve(mcb200_ctx* ctx, mcb200_mesh* m)
 }
 
 // Everything is enqueued on ctx->cur (the caller picks the lane); all allocations happen in lbvh_reserve.
+int mesh_sync_frames(mcb200_ctx* ctx, mcb200_mesh* a, double eps_a, mcb200_mesh* b, double eps_b)
+{
+    frame_pack_t pk;
+    std::memset(&pk, 0, sizeof(pk));
+    mcb200_mesh* ms[2] = { a, b };
+    const double eps[2] = { eps_a, eps_b };
+    for (int k = 0; k < 2; ++k) {
+        mcb200_mesh* m = ms[k];
+        if (!m) continue;
+        MCB_TRY(ctx->reserve(m->d_frames, sizeof(frame_t) * 2));
+        frame_t f[2];
+        f[0] = m->frame;
+        f[0].has_pert = 0;
+        f[0].pert[0] = f[0].pert[1] = f[0].pert[2] = 0.0;
+        f[0].eps = eps[k];
+        f[1] = m->frame;
+        f[1].eps = 0.0;
+        if (m->dev_frames_valid && m->dev_frames_ptr == m->d_frames.p && std::memcmp(f, m->dev_frames, sizeof(f)) == 0) continue;
+        std::memcpy(m->dev_frames, f, sizeof(f));
+        m->dev_frames_valid = true;
+        m->dev_frames_ptr = m->d_frames.p;
+        pk.dst[pk.n] = m->d_frames.as<frame_t>();
+        pk.f[pk.n][0] = f[0];
+        pk.f[pk.n][1] = f[1];
+        ++pk.n;
+    }
+    if (pk.n) MCB_LAUNCH(ctx, k_set_frames, 1, 128, 0, pk);
+    return 0;
+}
+
+// The build reads the mesh's frame and eps from its device slot: the caller has called mesh_sync_frames(ctx, m, eps).
 int lbvh_build(mcb200_ctx* ctx, mcb200_mesh* m, double eps)
 {
     MCB_TRY(lbvh_reserve(ctx, m));
@@ -582,6 +783,8 @@ int lbvh_build(mcb200_ctx* ctx, mcb200_mesh* m, double eps)
         fill_list_t fl {};
         fl.add(root_ord, 6, 0xFFFFFFFFu);
         fl.add(root_ord + 3, 6, 0u);
+        fl.add(root_ord + 12, 6, 0xFFFFFFFFu); // the same for the vertex box
+        fl.add(root_ord + 15, 6, 0u);
         fl.add(n_groups, 4, 0u);
         fl.add(m->flags.p, 4, 0u);
         fl.add(sc.hist.p, (size_t)rsort::MAX_PASSES * rsort::RADIX, 0u);
@@ -593,18 +796,12 @@ int lbvh_build(mcb200_ctx* ctx, mcb200_mesh* m, double eps)
     const unsigned grid = div_up(nf, BLOCK) < max_grid ? div_up(nf, BLOCK) : max_grid;
     const double* prior = m->n_prior ? m->prior_bbox.as<double>() : nullptr;
     const uint32_t n_prior = m->n_prior < nf ? m->n_prior : nf;
-    if (m->is_tri)
-        MCB_LAUNCH(ctx, k_face_bbox<true>, grid, BLOCK, 0, m->d_xyz, m->frame, m->d_face_vtx, m->d_face_off, nf, eps,
-            m->face_bbox.as<double>(), root_ord, prior, n_prior);
-    else
-        MCB_LAUNCH(ctx, k_face_bbox<false>, grid, BLOCK, 0, m->d_xyz, m->frame, m->d_face_vtx, m->d_face_off, nf, eps,
-            m->face_bbox.as<double>(), root_ord, prior, n_prior);
-    m->n_prior = 0; // consumed: the boxes are part of face_bbox now
     // (key, face) ascending by key (values implicit 0..nf-1), ping-pong scratch <-> mesh arrays; the histograms come out
-    // of k_morton.  The leaves are ordered by the top `morton_sort_bits` bits of their code.  Nothing that leaves this stage depends on the
-    // order (the pair SET is tree-independent and the groups hold up to 32 leaves anyway), so the default sorts 24 bits in
-    // three passes; codes that tie are told apart by their position, as equal codes always were.  With an odd number of
-    // passes the keys start in the scratch buffer so that the last pass lands in the mesh's own arrays.
+    // of the kernel that makes the keys.  The leaves are ordered by the top `morton_sort_bits` bits of their code.  Nothing
+    // that leaves this stage depends on the order (the pair SET is tree-independent and the groups hold up to 32 leaves
+    // anyway), so the default sorts 24 bits in three passes; codes that tie are told apart by their position, as equal codes
+    // always were.  With an odd number of passes the keys start in the scratch buffer so that the last pass lands in the
+    // mesh's own arrays.
     const int sort_bits = ctx->morton_sort_bits >= 30 ? 32 : 24;
     const unsigned key_shift = sort_bits == 32 ? 0u : 6u;
     const rsort::pass_desc pd = rsort::make_passes(0, sort_bits);
@@ -616,8 +813,29 @@ int lbvh_build(mcb200_ctx* ctx, mcb200_mesh* m, double eps)
     uint32_t* keys_b = odd ? sc.keys_alt.as<uint32_t>() : m->sorted_codes.as<uint32_t>();
     uint32_t* vals_a = odd ? m->sorted_faces.as<uint32_t>() : sc.vals_alt.as<uint32_t>();
     uint32_t* vals_b = odd ? sc.vals_alt.as<uint32_t>() : m->sorted_faces.as<uint32_t>();
-    MCB_LAUNCH(ctx, k_morton, grid, BLOCK, 0, m->face_bbox.as<double>(), nf, root_ord, root_dec, m->codes.as<uint32_t>(), keys_in,
-        sc.hist.as<unsigned>(), sc.status.as<unsigned>(), status_words, key_shift, pd.npasses);
+    if (n_prior == 0 && !ctx->two_kernel_boxes) {
+        unsigned long long* vroot = root_ord + 12; // vertex-box accumulators (cleared by the fill above)
+        const unsigned vgrid = div_up(m->nv, BLOCK) < max_grid ? div_up(m->nv, BLOCK) : max_grid;
+        MCB_LAUNCH(ctx, k_vertex_bbox, vgrid, BLOCK, 0, m->d_xyz, m->d_frames.as<frame_t>(), m->nv, vroot);
+        if (m->is_tri)
+            MCB_LAUNCH(ctx, k_face_codes<true>, grid, BLOCK, 0, m->d_xyz, m->d_frames.as<frame_t>(), m->d_face_vtx, m->d_face_off, nf,
+                m->face_bbox.as<double>(), vroot, root_ord, m->codes.as<uint32_t>(), keys_in, sc.hist.as<unsigned>(), sc.status.as<unsigned>(),
+                status_words, key_shift, pd.npasses);
+        else
+            MCB_LAUNCH(ctx, k_face_codes<false>, grid, BLOCK, 0, m->d_xyz, m->d_frames.as<frame_t>(), m->d_face_vtx, m->d_face_off, nf,
+                m->face_bbox.as<double>(), vroot, root_ord, m->codes.as<uint32_t>(), keys_in, sc.hist.as<unsigned>(), sc.status.as<unsigned>(),
+                status_words, key_shift, pd.npasses);
+    } else {
+        if (m->is_tri)
+            MCB_LAUNCH(ctx, k_face_bbox<true>, grid, BLOCK, 0, m->d_xyz, m->d_frames.as<frame_t>(), m->d_face_vtx, m->d_face_off, nf,
+                m->face_bbox.as<double>(), root_ord, prior, n_prior);
+        else
+            MCB_LAUNCH(ctx, k_face_bbox<false>, grid, BLOCK, 0, m->d_xyz, m->d_frames.as<frame_t>(), m->d_face_vtx, m->d_face_off, nf,
+                m->face_bbox.as<double>(), root_ord, prior, n_prior);
+        MCB_LAUNCH(ctx, k_morton, grid, BLOCK, 0, m->face_bbox.as<double>(), nf, root_ord, root_dec, m->codes.as<uint32_t>(), keys_in,
+            sc.hist.as<unsigned>(), sc.status.as<unsigned>(), status_words, key_shift, pd.npasses);
+    }
+    m->n_prior = 0; // consumed: the boxes are part of face_bbox now
     uint32_t *kout = nullptr, *vout = nullptr;
     MCB_TRY((rsort::sort_passes<uint32_t, uint32_t, true>(ctx, keys_in, keys_a, keys_b, nullptr, vals_a, vals_b, nullptr, nf, pd, &kout,
         &vout)));
@@ -627,7 +845,7 @@ int lbvh_build(mcb200_ctx* ctx, mcb200_mesh* m, double eps)
     }
     MCB_LAUNCH(ctx, k_leaves, div_up(nf, LB_LEAVES), LB_THREADS, 0, m->sorted_codes.as<uint32_t>(), m->face_bbox.as<double>(),
         m->sorted_faces.as<uint32_t>(), nf, m->wide.as<float>(), m->sorted_bbox.as<double>(), *m->lv, m->groups.as<uint2>(), m->group_box.as<group_box_t>(), n_groups,
-        m->flags.as<unsigned>());
+        m->flags.as<unsigned>(), root_ord, root_dec);
     m->built = true;
     m->groups_valid = true;
     m->eps = eps;

@@ -28,7 +28,8 @@ struct narrow_args_t {
     // geometry
     const void* src_xyz;
     const void* cut_xyz;
-    frame_t src_frame, cut_frame;
+    const frame_t* src_frame; // device slots (d_frames[1] of each mesh); the kernels repoint them at a shared-memory copy
+    const frame_t* cut_frame;
     uint32_t src_nv;
     const double* src_bbox; // [nsf][6]
     const double* cut_bbox; // [ncf][6] (enlarged, from the unperturbed build)
@@ -54,8 +55,8 @@ struct narrow_args_t {
 
 __device__ __forceinline__ void load_ps_vertex(const narrow_args_t& a, uint32_t v, double* out)
 {
-    if (v < a.src_nv) load_vertex(a.src_xyz, a.src_frame, v, out);
-    else load_vertex(a.cut_xyz, a.cut_frame, v - a.src_nv, out);
+    if (v < a.src_nv) load_vertex(a.src_xyz, *a.src_frame, v, out);
+    else load_vertex(a.cut_xyz, *a.cut_frame, v - a.src_nv, out);
 }
 
 __device__ __forceinline__ void load_box(const double* p, double* b)
@@ -366,9 +367,20 @@ __device__ __forceinline__ bool setup_test(const narrow_args_t& a, uint32_t s, u
 
 // Work items: the exact kernel takes queue entries (pair, slot); the filter takes pairs and walks the slots of its pair
 // in a loop (one thread per (pair, slot) was measured slower: 2.4x the instructions, the per-pair loads dominate).
-template <bool TRI, bool EXACT> __global__ void __launch_bounds__(NBLOCK) k_tests(narrow_args_t a)
+template <bool TRI, bool EXACT> __global__ void __launch_bounds__(NBLOCK) k_tests(narrow_args_t a_in)
 {
     pdl_prologue();
+    __shared__ frame_t s_fr[2];
+    load_frame_shared(&s_fr[0], a_in.src_frame);
+    if (threadIdx.x >= 64) { // second half of the block fetches the cut frame
+        constexpr unsigned W = sizeof(frame_t) / 4;
+        const unsigned t = threadIdx.x - 64u;
+        if (t < W) reinterpret_cast<unsigned*>(&s_fr[1])[t] = __ldg(reinterpret_cast<const unsigned*>(a_in.cut_frame) + t);
+    }
+    __syncthreads();
+    narrow_args_t a = a_in;
+    a.src_frame = &s_fr[0];
+    a.cut_frame = &s_fr[1];
     unsigned long long n_items;
     if (EXACT) {
         n_items = a.counters->n_queue < a.cap_exact ? a.counters->n_queue : a.cap_exact;
@@ -481,7 +493,17 @@ struct plane_args_t {
 template <bool TRI> __global__ void __launch_bounds__(NBLOCK) k_planes(plane_args_t pa)
 {
     pdl_prologue();
-    const narrow_args_t& a = pa.n;
+    __shared__ frame_t s_fr[2];
+    load_frame_shared(&s_fr[0], pa.n.src_frame);
+    if (threadIdx.x >= 64) {
+        constexpr unsigned W = sizeof(frame_t) / 4;
+        const unsigned t = threadIdx.x - 64u;
+        if (t < W) reinterpret_cast<unsigned*>(&s_fr[1])[t] = __ldg(reinterpret_cast<const unsigned*>(pa.n.cut_frame) + t);
+    }
+    __syncthreads();
+    narrow_args_t a = pa.n;
+    a.src_frame = &s_fr[0];
+    a.cut_frame = &s_fr[1];
     for (uint32_t f = blockIdx.x * NBLOCK + threadIdx.x; f < a.nf; f += gridDim.x * NBLOCK) {
         if (!a.cand_flag[f]) continue;
         const uint32_t h0 = TRI ? 3u * f : __ldg(a.face_off + f);
@@ -507,13 +529,9 @@ template <bool TRI> __global__ void __launch_bounds__(NBLOCK) k_planes(plane_arg
 }
 
 // ---- canonical ordering of records / logged tests -----------------------------------------------------------------------
-// Up to SMALL_SORT items (the usual case: an intersection curve crosses thousands of edges, not millions) are ordered by
-// counting: the rank of an item is the number of items with a smaller (edge, face) key — keys are unique — and the item is
-// written straight to its place.  16 items per block, 16 threads share one item's scan.  One launch instead of
-// key extraction + histogram + six radix passes + gather; those kernels return at once when n <= SMALL_SORT.
+// Up to SMALL_SORT items (the usual case: an intersection curve crosses thousands of edges, not millions) are ordered by a
+// single block (k_rank_sort_small); the radix path's kernels return at once when n <= SMALL_SORT.
 constexpr unsigned SMALL_SORT = 16384;
-constexpr int RANK_CHUNK = 4096; // keys staged per round (32 KB)
-constexpr int RANK_ITEMS = 16; // items per block: 16 threads share one item's scan
 
 template <typename T> __device__ __forceinline__ unsigned long long item_key(const T* item)
 {
@@ -521,6 +539,15 @@ template <typename T> __device__ __forceinline__ unsigned long long item_key(con
     const unsigned long long v = __ldg(reinterpret_cast<const unsigned long long*>(item));
     return (v << 32) | (v >> 32);
 }
+
+// Order by counting: the rank of an item is the number of items with a smaller (edge, face) key — keys are unique — and the
+// item is written straight to its place.  64 items per block, four threads share one item's scan of all keys (staged through
+// shared memory 4096 at a time, 32 KB static: no shared-memory carve-out change between this kernel and its neighbours,
+// which a 128 KB bucket table cost more than it saved).  One launch instead of key extraction + histogram + six radix
+// passes + gather; those kernels return at once when n <= SMALL_SORT.
+constexpr int RANK_CHUNK = 4096; // keys staged per round (32 KB)
+constexpr int RANK_ITEMS = 64; // items per block
+constexpr int RANK_SHARE = 256 / RANK_ITEMS; // threads per item
 
 template <typename T> __global__ void __launch_bounds__(256) k_rank_sort_small(const T* __restrict__ items,
     const unsigned long long* d_n, unsigned long long cap, T* __restrict__ out)
@@ -531,7 +558,7 @@ template <typename T> __global__ void __launch_bounds__(256) k_rank_sort_small(c
     const unsigned long long n64 = *d_n < cap ? *d_n : cap;
     if (n64 > SMALL_SORT || (unsigned long long)blockIdx.x * RANK_ITEMS >= n64) return;
     const unsigned n = (unsigned)n64;
-    const unsigned i = blockIdx.x * RANK_ITEMS + (threadIdx.x >> 4), sub = threadIdx.x & 15u;
+    const unsigned i = blockIdx.x * RANK_ITEMS + (threadIdx.x / RANK_SHARE), sub = threadIdx.x % RANK_SHARE;
     const bool live = i < n;
     const unsigned long long mine = live ? item_key(items + i) : ~0ull;
     unsigned rank = 0;
@@ -546,21 +573,19 @@ template <typename T> __global__ void __launch_bounds__(256) k_rank_sort_small(c
 #pragma unroll
         for (int k = 0; k < RANK_CHUNK / 256; ++k) s_keys[k * 256u + threadIdx.x] = tmp[k];
         __syncthreads();
-        // 16 consecutive keys per step and item; the 2 items of a warp read the same addresses (broadcast)
-        const unsigned steps = (cn + 15u) >> 4;
-#pragma unroll 4
-        for (unsigned st = 0; st < steps; ++st) rank += (s_keys[st * 16u + sub] < mine) ? 1u : 0u;
+        // RANK_SHARE consecutive keys per step and item; the 8 items of a warp read the same addresses (broadcast)
+        const unsigned steps = (cn + RANK_SHARE - 1u) / RANK_SHARE;
+#pragma unroll 8
+        for (unsigned st = 0; st < steps; ++st) rank += (s_keys[st * RANK_SHARE + sub] < mine) ? 1u : 0u;
         __syncthreads();
     }
-    rank += __shfl_xor_sync(0xffffffffu, rank, 1);
-    rank += __shfl_xor_sync(0xffffffffu, rank, 2);
-    rank += __shfl_xor_sync(0xffffffffu, rank, 4);
-    rank += __shfl_xor_sync(0xffffffffu, rank, 8);
+#pragma unroll
+    for (int o = 1; o < RANK_SHARE; o <<= 1) rank += __shfl_xor_sync(0xffffffffu, rank, o);
     if (live) {
         // the item is a few 8-byte words: the threads of the group copy it together
         const unsigned long long* src = reinterpret_cast<const unsigned long long*>(items + i);
         unsigned long long* dst = reinterpret_cast<unsigned long long*>(out + rank);
-        for (unsigned w = sub; w < sizeof(T) / 8; w += 16u) dst[w] = src[w];
+        for (unsigned w = sub; w < sizeof(T) / 8; w += RANK_SHARE) dst[w] = src[w];
     }
 }
 
@@ -694,8 +719,9 @@ int narrowphase_run(mcb200_ctx* ctx, const mcb200_soup* soup, const mcb200_mesh*
     narrow_args_t a;
     a.src_xyz = src->d_xyz;
     a.cut_xyz = cut->d_xyz;
-    a.src_frame = src->frame;
-    a.cut_frame = cut->frame;
+    MCB_TRY(mesh_sync_frames(ctx, const_cast<mcb200_mesh*>(src), src->eps, const_cast<mcb200_mesh*>(cut), cut->eps));
+    a.src_frame = src->d_frames.as<frame_t>() + 1;
+    a.cut_frame = cut->d_frames.as<frame_t>() + 1;
     a.src_nv = src->nv;
     a.src_bbox = src->face_bbox.as<double>();
     a.cut_bbox = cut->face_bbox.as<double>();

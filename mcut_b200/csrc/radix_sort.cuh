@@ -104,12 +104,13 @@ __device__ __forceinline__ size_t resolve_n(const unsigned long long* d_n, size_
 template <typename KeyT>
 __global__ void __launch_bounds__(THREADS) k_histogram(const KeyT* __restrict__ keys, const unsigned long long* d_n,
     size_t n_max, pass_desc pd, int tile_items, unsigned* __restrict__ hist /* [npasses][RADIX] */,
-    unsigned* __restrict__ status, size_t skip_le)
+    unsigned* __restrict__ status, size_t skip_le, const unsigned* d_flag, unsigned flag_le)
 {
     pdl_prologue();
     __shared__ unsigned s_hist[MAX_PASSES * RADIX];
     const size_t n = resolve_n(d_n, n_max);
     if (n <= skip_le) return; // a small-n kernel already produced the sorted output
+    if (d_flag && *d_flag <= flag_le) return; // another method took this input (decided on the device)
     for (int i = threadIdx.x; i < pd.npasses * RADIX; i += THREADS) s_hist[i] = 0;
     __syncthreads();
     {
@@ -187,7 +188,8 @@ template <typename KeyT, typename ValT, bool HAS_VALS, int ITEMS>
 __global__ void __launch_bounds__(THREADS, 3) k_onesweep_pass(const KeyT* __restrict__ keys_in, KeyT* __restrict__ keys_out,
     const ValT* __restrict__ vals_in, ValT* __restrict__ vals_out, const unsigned long long* d_n, size_t n_max,
     digit_desc dd, int pass_index, const unsigned* __restrict__ hist /* [RADIX] of this pass */,
-    unsigned* status_all /* [npasses][tiles(n)][RADIX] */, unsigned* tile_counter, size_t skip_le)
+    unsigned* status_all /* [npasses][tiles(n)][RADIX] */, unsigned* tile_counter, size_t skip_le, const unsigned* d_flag,
+    unsigned flag_le)
 {
     pdl_prologue();
     static_assert(THREADS == RADIX, "one thread per digit in the per-digit steps");
@@ -206,6 +208,7 @@ __global__ void __launch_bounds__(THREADS, 3) k_onesweep_pass(const KeyT* __rest
 
     const size_t n = resolve_n(d_n, n_max);
     if (n <= skip_le) return;
+    if (d_flag && *d_flag <= flag_le) return;
     const unsigned num_tiles = (unsigned)((n + TILE - 1) / TILE);
     unsigned* status = status_all + (size_t)pass_index * status_rows(num_tiles) * RADIX;
     unsigned* gstatus = status + (size_t)num_tiles * RADIX; // group rows
@@ -446,7 +449,8 @@ inline int sort_prepare(mcb200_ctx* ctx)
 // in.  vals_in == nullptr with HAS_VALS: the value of element i is i.
 template <typename KeyT, typename ValT, bool HAS_VALS>
 int sort_passes(mcb200_ctx* ctx, const KeyT* keys_in, KeyT* keys_a, KeyT* keys_b, const ValT* vals_in, ValT* vals_a, ValT* vals_b,
-    const unsigned long long* d_n, size_t n_max, const pass_desc& pd, KeyT** keys_out, ValT** vals_out, size_t skip_le = 0)
+    const unsigned long long* d_n, size_t n_max, const pass_desc& pd, KeyT** keys_out, ValT** vals_out, size_t skip_le = 0,
+    const unsigned* d_flag = nullptr, unsigned flag_le = 0)
 {
     constexpr int ITEMS = items_for<KeyT>::value;
     constexpr int TILE = THREADS * ITEMS;
@@ -471,7 +475,7 @@ int sort_passes(mcb200_ctx* ctx, const KeyT* keys_in, KeyT* keys_a, KeyT* keys_b
         KeyT* kout = (p & 1) ? keys_b : keys_a;
         ValT* vout = (p & 1) ? vals_b : vals_a;
         MCB_LAUNCH_NAMED(ctx, pname, (k_onesweep_pass<KeyT, ValT, HAS_VALS, ITEMS>), pgrid, THREADS, smem, kin, kout, vin, vout, d_n, n_max,
-            pd.d[p], p, sc.hist.as<unsigned>() + p * RADIX, sc.status.as<unsigned>(), sc.tilectr.as<unsigned>() + p, skip_le);
+            pd.d[p], p, sc.hist.as<unsigned>() + p * RADIX, sc.status.as<unsigned>(), sc.tilectr.as<unsigned>() + p, skip_le, d_flag, flag_le);
         kin = kout;
         vin = vout;
     }
@@ -482,7 +486,8 @@ int sort_passes(mcb200_ctx* ctx, const KeyT* keys_in, KeyT* keys_a, KeyT* keys_b
 
 template <typename KeyT, typename ValT, bool HAS_VALS>
 int sort(mcb200_ctx* ctx, const KeyT* keys_in, KeyT* keys_a, KeyT* keys_b, const ValT* vals_in, ValT* vals_a, ValT* vals_b,
-    const unsigned long long* d_n, size_t n_max, const pass_desc& pd, KeyT** keys_out, ValT** vals_out, size_t skip_le = 0)
+    const unsigned long long* d_n, size_t n_max, const pass_desc& pd, KeyT** keys_out, ValT** vals_out, size_t skip_le = 0,
+    const unsigned* d_flag = nullptr, unsigned flag_le = 0)
 {
     constexpr int TILE = THREADS * items_for<KeyT>::value;
     if (keys_out) *keys_out = const_cast<KeyT*>(keys_in);
@@ -495,9 +500,9 @@ int sort(mcb200_ctx* ctx, const KeyT* keys_in, KeyT* keys_a, KeyT* keys_b, const
     const unsigned hgrid = (unsigned)((tiles < (size_t)ctx->num_sms * 4) ? tiles : (size_t)ctx->num_sms * 4);
     const char* hname = sizeof(KeyT) == 4 ? "sort_histogram_u32" : "sort_histogram_u64";
     MCB_LAUNCH_NAMED(ctx, hname, (k_histogram<KeyT>), hgrid, THREADS, 0, keys_in, d_n, n_max, pd, TILE, sc.hist.as<unsigned>(),
-        sc.status.as<unsigned>(), skip_le);
+        sc.status.as<unsigned>(), skip_le, d_flag, flag_le);
     return sort_passes<KeyT, ValT, HAS_VALS>(ctx, keys_in, keys_a, keys_b, vals_in, vals_a, vals_b, d_n, n_max, pd, keys_out, vals_out,
-        skip_le);
+        skip_le, d_flag, flag_le);
 }
 
 } // namespace rsort
