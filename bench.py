@@ -1,25 +1,28 @@
 #!/usr/bin/env python
 """bench.py — the intersect stage of mcDispatch (BVH build + BVH x BVH traversal + exact edge/face narrowphase)
-on the BASELINE.json workload, one process per GPU.
+on the BASELINE.json workloads, one process per GPU.
 
-    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
-    python bench.py --impl reference --gpus N --steps K ...   # the reference's own CPU path (oracle/_ref)
+    python bench.py --gpus N --steps K --warmup W                 # this repo's CUDA path, BASELINE configs[1] (C2)
+    python bench.py --workload c5|c3|c4|c5dense|c3batch|c4batch    # the other configs
+    python bench.py --impl reference --gpus N --steps K ...        # the reference's own CPU path (oracle/_ref)
 
-A "step" is one whole intersect stage of one mcDispatch on configs[1] of BASELINE.json: CSG of two synthetic
-cube-spheres, 1,002,252 triangles each (SURVEY.md §8-d "C2").  One JSON line is printed by rank 0:
+A "step" is one whole intersect stage of one mcDispatch.  One JSON line is printed by rank 0:
 
   value        candidate face pairs ("tri-pairs") pushed through build + traversal + narrowphase per second, inputs
                resident in HBM, device time from CUDA events, max over ranks; ms_per_step = intersect-stage ms per
                dispatch (the other half of BASELINE.json's metric)
-  e2e          the same through the C-ABI with HOST buffers: every step uploads both meshes and the polygon-soup
-               topology from pinned memory and reads pairs, registry records and status back
+  e2e          the same through the C-ABI with HOST buffers: every step uploads both meshes from pinned memory and reads
+               pairs, registry records and status back
   roofline     the dominant kernel's algorithmic bytes / its CUDA-event duration vs the measured HBM peak
   cpu_baseline the reference's own CPU implementation of the same stage on this box's host cores
 
 N > 1 ("weak"): every rank runs its own dispatch of the same workload (the MultipleContextsInParallel pattern, one
 context per GPU, no data-path collective); value = all ranks' pairs / max-over-ranks time.  The sharded single-dispatch
-mode (leaf-range split + NCCL all-gather of the pair/record buffers) is measured in the same run and
-reported under "sharded".
+mode (leaf-range split + NCCL exchange inside the C-ABI, mcb200_intersect_stage_sharded) is measured in the same run — on
+the workload itself and on C5, where the stage is long enough for a split to pay — and reported under "sharded".
+
+Batch workloads (c3batch: 256 planar sections of one terrain; c4batch: many small CSG pairs): a step is still one
+dispatch; they are issued through mcb200_batch_intersect_host over several context lanes of the GPU.
 """
 from __future__ import annotations
 
@@ -43,6 +46,7 @@ from mcut_b200 import meshgen  # noqa: E402
 
 METRIC = "intersect_stage_tri_pairs_per_s"
 UNIT = "candidate face pairs/s (BVH build + traversal + exact narrowphase per mcDispatch)"
+DBL = meshgen.MC_DISPATCH_VERTEX_ARRAY_DOUBLE | meshgen.MC_DISPATCH_ENFORCE_GENERAL_POSITION
 
 
 def load_peaks():
@@ -53,24 +57,41 @@ def load_peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+WORKLOADS = {
+    "c2": "C2: CSG of two cube-spheres, 1,002,252 triangles / 501,128 vertices each, R=20",
+    "c2small": "C2-small: two cube-spheres, 101,568 triangles each (smoke size)",
+    "c5": "C5: dense overlap of two cube-spheres, 2,007,372 triangles each, with near-coplanar regions (1,037,662 tests need "
+          "the exact orient3d stages)",
+    "c5dense": "C5-dense: SURVEY's original recipe (dense overlap, no exact tests), 2,007,372 triangles each",
+    "c3": "C3 (one of its 256 dispatches): 3,998,792-triangle terrain cut by the section supertriangle of plane 0",
+    "c4": "C4 (one of its dispatches): two icospheres of 5,120 triangles",
+    "c3batch": "C3: planar sectioning of a 3,998,792-triangle terrain by 256 planes (mcEnqueueDispatchPlanarSection's supertriangle)",
+    "c4batch": "C4: independent small CSG pairs (two icospheres of 5,120 triangles each), MultipleContextsInParallel pattern",
+}
+
+
 def workload(name: str):
     if name == "c2":
-        return meshgen.c2_two_spheres(k=289), "C2: CSG of two cube-spheres, 1,002,252 triangles / 501,128 vertices each, R=20"
+        return meshgen.c2_two_spheres(k=289)
     if name == "c2small":
-        return meshgen.c2_two_spheres(k=92), "C2-small: two cube-spheres, 101,568 triangles each (smoke size)"
+        return meshgen.c2_two_spheres(k=92)
     if name == "c5":
-        return meshgen.c5_coplanar_regions(k=409), ("C5: dense overlap of two cube-spheres, 2,007,372 triangles each, with near-coplanar "
-                                                    "regions (1,037,662 tests need the exact orient3d stages)")
+        return meshgen.c5_coplanar_regions(k=409)
     if name == "c5dense":
-        return meshgen.c5_near_coplanar(k=409), "C5-dense: SURVEY's original recipe (dense overlap, no exact tests), 2,007,372 triangles each"
+        return meshgen.c5_near_coplanar(k=409)
     if name == "c3":
-        tri = np.array([[-900.0, -850.0, -4.1], [1400.0, -700.0, 3.3], [150.0, 1600.0, 1.7]])
-        cut = (tri, np.array([0, 1, 2], dtype=np.uint32), None)
-        flags = meshgen.MC_DISPATCH_VERTEX_ARRAY_DOUBLE | meshgen.MC_DISPATCH_ENFORCE_GENERAL_POSITION
-        return (meshgen.terrain(), cut, flags), "C3 (one of its 256 dispatches): 3,998,792-triangle terrain cut by one triangle"
+        ter = meshgen.terrain()
+        nrm, _ = meshgen.c3_plane(0)
+        return ter, meshgen.c3_supertriangle(ter[0], nrm), DBL
     if name == "c4":
-        return meshgen.c4_pair(0), "C4 (one of its 10,000 dispatches): two icospheres of 5,120 triangles"
+        return meshgen.c4_pair(0)
     raise SystemExit(f"unknown workload {name}")
+
+
+def base_config(name: str, world: int):
+    """the keys both arms (ours and --impl reference) print"""
+    return {"workload": WORKLOADS[name], "workload_id": name,
+            "parallelism": f"{world} independent dispatch stream(s)" if world > 1 else "1 dispatch stream"}
 
 
 # ----------------------------------------------------------------------------------------------------------------------
@@ -133,29 +154,8 @@ REF_STAGES = ["build_oibvh", "intersectOIBVHs", "Prepare edge-to-face pairs", "B
               "Calculate intersection points (edge-to-face)"]
 
 
-def reference_stage_once(in_path: str, out_path: str, helpers: int):
-    """One mcDispatch of the unmodified reference (profiling build) cut short right after its narrowphase.
-    Returns (stage_ms summed over the reference's own timers, n_pairs, n_points)."""
-    from mcut_b200.mcbio import read_mcb
-    exe = os.path.join(ROOT, "oracle", "_ref", "stage_harness_prof")
-    r = subprocess.run([exe, in_path, out_path, "--helpers", str(helpers), "--no-events", "--abort-after-narrowphase"],
-                       capture_output=True, text=True, cwd=os.path.dirname(out_path))
-    ms = 0.0
-    seen = {}
-    for line in r.stderr.splitlines():
-        m = re.search(r'\[MCUT\]\[PROF:\d+\]: "(.*)" \((\d+)ms\)', line)
-        if m and m.group(1) in REF_STAGES:
-            ms += float(m.group(2))
-            seen[m.group(1)] = seen.get(m.group(1), 0.0) + float(m.group(2))
-    o = read_mcb(out_path)
-    # sub-millisecond precision where the harness measured the call itself (build x2, traversal)
-    fine = o["timings_ms"]
-    fine_bt = float(fine[fine[:, 0] < 2, 1].sum())
-    coarse_bt = seen.get("build_oibvh", 0.0) + seen.get("intersectOIBVHs", 0.0)
-    ms = ms - coarse_bt + fine_bt
-    n_pairs = int(o["isect0_map_entries"].shape[0] // 2)
-    n_points = int(o["dispatch0_ipoints"].shape[0])
-    return ms, n_pairs, n_points, seen
+def have_reference_binary() -> bool:
+    return os.path.exists(os.path.join(ROOT, "oracle", "_ref", "stage_harness_prof"))
 
 
 def write_input(src, cut, flags, path):
@@ -168,6 +168,54 @@ def write_input(src, cut, flags, path):
     write_mcb(path, d)
 
 
+def reference_stage_start(in_path: str, out_path: str, helpers: int, extra=()):
+    exe = os.path.join(ROOT, "oracle", "_ref", "stage_harness_prof")
+    return subprocess.Popen([exe, in_path, out_path, "--helpers", str(helpers), "--no-events", "--abort-after-narrowphase", *extra],
+                            stdout=subprocess.DEVNULL, stderr=subprocess.PIPE, text=True, cwd=os.path.dirname(out_path))
+
+
+def reference_stage_finish(proc, out_path: str):
+    """(stage ms = sum of the reference's own timers, candidate pairs, intersection points) of one finished harness run"""
+    from mcut_b200.mcbio import read_mcb
+    _, err = proc.communicate()
+    ms = 0.0
+    seen = {}
+    for line in err.splitlines():
+        m = re.search(r'\[MCUT\]\[PROF:\d+\]: "(.*)" \((\d+)ms\)', line)
+        if m and m.group(1) in REF_STAGES:
+            ms += float(m.group(2))
+            seen[m.group(1)] = seen.get(m.group(1), 0.0) + float(m.group(2))
+    o = read_mcb(out_path)
+    # sub-millisecond precision where the harness measured the call itself (build x2, traversal)
+    fine = o["timings_ms"]
+    fine_bt = float(fine[fine[:, 0] < 2, 1].sum())
+    coarse_bt = seen.get("build_oibvh", 0.0) + seen.get("intersectOIBVHs", 0.0)
+    ms = ms - coarse_bt + fine_bt
+    n_pairs = int(o["isect0_map_entries"].shape[0] // 2) if "isect0_map_entries" in o else 0
+    n_points = int(o["dispatch0_ipoints"].shape[0]) if "dispatch0_ipoints" in o else 0
+    return ms, n_pairs, n_points
+
+
+def reference_streams(inputs, streams: int, cores: int, td: str, extra_of=None):
+    """Runs the harness on `inputs` (paths), `streams` processes at a time, each with cores/streams - 1 helper threads.
+    Returns (wall seconds, [stage ms], total pairs, helper threads per process)."""
+    helpers = max(cores // max(streams, 1) - 1, 0)
+    t0 = time.perf_counter()
+    stage_ms, pairs = [], 0
+    pending = list(enumerate(inputs))
+    running = []
+    while pending or running:
+        while pending and len(running) < streams:
+            i, ip = pending.pop(0)
+            op = os.path.join(td, f"out{i}.mcb")
+            running.append((reference_stage_start(ip, op, helpers, extra_of(i) if extra_of else ()), op))
+        proc, op = running.pop(0)
+        ms, npairs, _ = reference_stage_finish(proc, op)
+        stage_ms.append(ms)
+        pairs += npairs
+    return time.perf_counter() - t0, stage_ms, pairs, helpers
+
+
 def oracle_port_stage_once(src, cut, flags):
     from oracle import pyoracle
     t0 = time.perf_counter()
@@ -175,39 +223,77 @@ def oracle_port_stage_once(src, cut, flags):
     return (time.perf_counter() - t0) * 1e3, len(r["pairs"]), len(r["records"])
 
 
-def have_reference_binary() -> bool:
-    return os.path.exists(os.path.join(ROOT, "oracle", "_ref", "stage_harness_prof"))
+def c3_plane_extra(k):
+    nrm, off = meshgen.c3_plane(k)
+    return ["--planar", repr(float(nrm[0])), repr(float(nrm[1])), repr(float(nrm[2])), repr(float(off))]
 
 
 def run_reference_arm(args):
+    """The reference's own CPU path on the same workload.  At --gpus N it runs N dispatch streams side by side on the host
+    (N harness processes, cores/N - 1 helper threads each) so that the N-GPU figure is compared like for like."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    (src, cut, flags), desc = workload(args.workload)
     cores = os.cpu_count() or 1
-    helpers = max(cores - 1, 0)
-    times, n_pairs = [], 0
+    streams = max(args.gpus, 1)
+    name = args.workload
+    cfg = base_config(name, streams)
     with tempfile.TemporaryDirectory() as td:
         kind = "reference" if have_reference_binary() else "port"
-        if kind == "reference":
-            write_input(src, cut, flags, os.path.join(td, "in.mcb"))
-        for i in range(args.warmup + args.steps):
-            if kind == "reference":
-                ms, n_pairs, _, _ = reference_stage_once(os.path.join(td, "in.mcb"), os.path.join(td, "out.mcb"), helpers)
+        if name in ("c3batch", "c4batch"):
+            if kind != "reference":
+                print(json.dumps({"impl": "reference", "unavailable": "batch workloads need oracle/_ref (the reference harness)"}))
+                return
+            total = args.steps
+            inputs, extra_of = [], None
+            if name == "c4batch":
+                for j in range(args.warmup + total):
+                    s, c, f = meshgen.c4_pair(j)
+                    ip = os.path.join(td, f"in{j}.mcb")
+                    write_input(s, c, f, ip)
+                    inputs.append(ip)
+                streams_eff = min(cores, max(streams * 8, 8))  # the tutorial pattern: many contexts in flight, no helpers
             else:
-                ms, n_pairs, _ = oracle_port_stage_once(src, cut, flags)
-            if i >= args.warmup:
-                times.append(ms)
-    ms_per_step = float(np.mean(times))
-    value = n_pairs / (ms_per_step * 1e-3)
-    sample = (f"{args.steps} whole intersect stages of the full workload; each = one mcDispatch of the unmodified reference "
-              "cut short after its narrowphase, stage ms = sum of the reference's own timers (build_oibvh x2, intersectOIBVHs, "
-              "the five kernel.cpp:1781-3231 stages)") if kind == "reference" else \
-        f"{args.steps} runs of the oracle port (single thread)"
+                ter = meshgen.terrain()
+                dummy = (np.zeros((3, 3)), np.array([0, 1, 2], dtype=np.uint32), None)
+                ip = os.path.join(td, "in.mcb")
+                write_input(ter, dummy, DBL, ip)
+                inputs = [ip] * (args.warmup + total)
+                extra_of = c3_plane_extra
+                streams_eff = streams
+            if args.warmup:
+                reference_streams(inputs[:args.warmup], streams_eff, cores, td, extra_of)
+            wall, stage_ms, pairs, helpers = reference_streams(inputs[args.warmup:], streams_eff, cores, td,
+                                                               (lambda i: extra_of(i + args.warmup)) if extra_of else None)
+            ms_per_step = wall * 1e3 / total
+            value = pairs / wall
+            sample = (f"{total} dispatches, {streams_eff} harness processes in flight with {helpers} helper threads each; value = pairs / "
+                      "wall time of the batch (each process = one mcDispatch of the unmodified reference cut short after its narrowphase)")
+            cfg.update({"dispatches": total, "pairs_per_dispatch": pairs / max(total, 1)})
+        else:
+            src, cut, flags = workload(name)
+            times, n_pairs = [], 0
+            if kind == "reference":
+                write_input(src, cut, flags, os.path.join(td, "in.mcb"))
+            for i in range(args.warmup + args.steps):
+                if kind == "reference":
+                    wall, stage_ms, pairs, helpers = reference_streams([os.path.join(td, "in.mcb")] * streams, streams, cores, td)
+                    ms, n_pairs = max(stage_ms), pairs // streams
+                else:
+                    ms, n_pairs, _ = oracle_port_stage_once(src, cut, flags)
+                if i >= args.warmup:
+                    times.append(ms)
+            ms_per_step = float(np.mean(times))
+            value = streams * n_pairs / (ms_per_step * 1e-3) if kind == "reference" else n_pairs / (ms_per_step * 1e-3)
+            sample = (f"{args.steps} whole intersect stages of the full workload on {streams} stream(s); each = one mcDispatch of the unmodified "
+                      "reference cut short after its narrowphase, stage ms = sum of the reference's own timers (build_oibvh x2, "
+                      "intersectOIBVHs, the five kernel.cpp:1781-3231 stages), max over the streams") if kind == "reference" else \
+                f"{args.steps} runs of the oracle port (single thread)"
+            cfg.update({"pairs_per_dispatch": n_pairs})
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f64", "data": "synthetic", "config": {"workload": desc, "pairs_per_dispatch": n_pairs},
+        "dtype": "f64", "data": "synthetic", "config": cfg,
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores if kind == "reference" else 1, "kind": kind, "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
@@ -222,42 +308,36 @@ def pinned_copy(torch, a: np.ndarray):
     return t, t.numpy()
 
 
-def kernel_traffic(kname: str):
-    """dram__bytes_read.sum + dram__bytes_write.sum per launch of `kname` from the committed `ncu --set full` capture of
-    this same command (profiles/*_traffic.json, written by tools/ncu_to_profiles.py); None when no capture names it."""
-    import glob
-    best = None
-    for f in sorted(glob.glob(os.path.join(ROOT, "profiles", "*_traffic.json"))):
-        try:
-            d = json.load(open(f))
-        except Exception:
-            continue
-        if kname in d:
-            best = d[kname]["dram_bytes_per_launch"]
-    return best
+def profile_facts(workload_id: str):
+    """per-kernel facts from the committed ncu captures of THIS workload (profiles/r02_<workload>_kernels.json, written by
+    tools/ncu_to_profiles.py): DRAM bytes per launch, FP64-pipe utilisation; {} when the workload was not captured"""
+    p = os.path.join(ROOT, "profiles", f"r02_{workload_id}_kernels.json")
+    try:
+        return json.load(open(p))
+    except Exception:
+        return {}
 
 
 def algorithmic_bytes(kname: str, src_nv, src_nf, cut_nv, cut_nf, counts, vbytes=24):
-    """Algorithmic bytes per LAUNCH of a kernel (SURVEY.md §8-d figures).  Build kernels run once
-    per mesh, so their per-launch figure uses the mean mesh size."""
+    """Algorithmic bytes per LAUNCH of a kernel (SURVEY.md §8-d figures).  Build kernels run once per mesh, so
+    their per-launch figure uses the mean mesh size."""
     F = (src_nf + cut_nf) / 2.0
     V = (src_nv + cut_nv) / 2.0
     n_pairs, n_tests = counts["n_pairs"], counts["n_tests"]
     table = {
-        # coords gathered once per vertex + 12 B of indices per face in, 48 B box out
+        "k_vertex_bbox": vbytes * V,
+        # coords gathered once per vertex + 12 B of indices per face in; 48 B box + code + sort key out
+        "k_face_codes<true>": vbytes * V + 12 * F + 48 * F + 8 * F,
+        "k_face_codes<false>": vbytes * V + 12 * F + 48 * F + 8 * F,
         "k_face_bbox<true>": vbytes * V + 12 * F + 48 * F,
-        "k_face_bbox<false>": vbytes * V + 12 * F + 48 * F,
-        "k_morton": 48 * F + 8 * F,  # box in, code out twice (by face + sort key)
+        "k_morton": 48 * F + 8 * F,
         "onesweep_pass_u32_kv": 16 * F,  # one radix pass: key + value read once, written once
-        # codes + leaf boxes (gathered through the sorted order) in; every node inside the <=32-leaf treelets ((31/32)F of
-        # them) written once as a 64-byte record, topology of the rest, parent words, group list out
-        "k_tree<true>": 4 * F + 48 * F + 4 * F + 64 * F * 31 / 32 + 16 * F / 32 + 8 * F + 40 * F / 16,
-        # query-only build (the mesh that is only the traversal's query side): no node records, no parent words
-        "k_tree<false>": 4 * F + 48 * F + 4 * F + 40 * F / 16,
-        # the F/32 nodes above the treelets: group box in, node boxes out
-        "k_refit_climb": 32 * F / 16 + 48 * F / 32,
+        # sorted keys + face ids + exact boxes (gathered) in; exact boxes in leaf order, single-precision leaf boxes, the levels
+        # above (1/32 + 1/1024 ...), groups (about F/16 of 40 B) out
+        "k_leaves": 4 * F + 4 * F + 48 * F + 48 * F + 24 * F * (1 + 1 / 32 + 1 / 1024) + 40 * F / 16,
         "k_traverse": 24.0 * counts["n_node_tests"] + 8.0 * n_pairs,
-        "onesweep_pass_u64_k": 16.0 * n_pairs,
+        "k_pair_scatter": 16.0 * n_pairs,
+        "k_pair_segsort": 16.0 * n_pairs + 8.0 * src_nf,
         "k_tests_filter_tri": 8.0 * n_pairs + 128.0 * n_tests,
         "k_tests_filter_poly": 8.0 * n_pairs + 128.0 * n_tests,
     }
@@ -269,6 +349,7 @@ def run_ours(args):
     import torch.distributed as dist
 
     from mcut_b200 import stage
+    from mcut_b200._lib import BatchItem, Counts, HostMesh, HostSoup
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -281,71 +362,34 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local_rank}"))
     torch.cuda.set_device(local_rank)
     dev = torch.device(f"cuda:{local_rank}")
-
-    (src, cut, flags), desc = workload(args.workload)
-    sx, sf, ss = src
-    cx, cf, cs = cut
-    src_nv, src_nf = meshgen.mesh_counts(src)
-    cut_nv, cut_nf = meshgen.mesh_counts(cut)
-
     # torch's legacy default stream has handle 0, which the C-ABI reads as "make your own stream"; use an explicit
     # stream for everything so torch.cuda.Event (which sees torch's CURRENT stream only) brackets our kernels
     tstream = torch.cuda.Stream(device=dev)
     torch.cuda.set_stream(tstream)
-    stream = tstream.cuda_stream
-    assert stream != 0
-    ctx = stage.Context(local_rank, stream)
-
-    # ---- host-side inputs of the stage (what `hmesh`/`ps` are to the reference's stage): frame + polygon-soup ids ----
-    com, shift, sbb, cbb = stage.vertex_parameters(sx, cx)
-    eps = stage.cut_bbox_eps(cbb, 1e-4, False)
-    soff = np.arange(0, sf.size + 1, 3, dtype=np.uint32)
-    coff = np.arange(0, cf.size + 1, 3, dtype=np.uint32)
-    fv, fe, ev, ef = stage.soup_ids(src_nv, soff, sf, coff, cf)
-    ne = ev.shape[0]
-    nh = fv.size
-
-    # pinned host copies (the e2e leg uploads from these every step)
-    keep = []
-    host = {}
-    for name, arr in (("sx", sx), ("sf", sf), ("cx", cx), ("cf", cf), ("fv", fv), ("fe", fe), ("ef", ef)):
-        t, a = pinned_copy(torch, arr)
-        keep.append(t)
-        host[name] = a
+    ctx = stage.Context(local_rank, tstream.cuda_stream)
     L = ctx.L
     vp = ctypes.c_void_p
-
-    def make_mesh(xyz, faces, nv, nf):
-        h = vp()
-        ctx.check(L.mcb200_mesh_create(ctx.h, 0, xyz.ctypes.data, nv, faces.ctypes.data_as(stage.c_u32p), None, nf, ctypes.byref(h)))
-        return h
-
-    def set_frame(h):
-        ctx.check(L.mcb200_mesh_set_frame(ctx.h, h, com.ctypes.data_as(stage.c_dp), shift.ctypes.data_as(stage.c_dp), None))
-
-    def make_soup():
-        h = vp()
-        ctx.check(L.mcb200_soup_create(ctx.h, src_nf, cut_nf, nh, ne, host["fv"].ctypes.data_as(stage.c_u32p),
-                                       host["fe"].ctypes.data_as(stage.c_u32p), host["ef"].ctypes.data_as(stage.c_u32p), ctypes.byref(h)))
-        return h
-
-    # ---- resident inputs for the `value` leg ----
-    m_src = make_mesh(host["sx"], host["sf"], src_nv, src_nf)
-    m_cut = make_mesh(host["cx"], host["cf"], cut_nv, cut_nf)
-    set_frame(m_src)
-    set_frame(m_cut)
-    soup = make_soup()
-    res = stage.Result(ctx)
-
     flush_buf = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)  # > 126 MB L2
-
-    def step_resident():
-        ctx.check(L.mcb200_intersect_stage(ctx.h, m_src, m_cut, eps, soup, res.h, 0))
+    peak, peak_src = load_peaks()
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
+
+    def max_over_ranks(x: float) -> float:
+        if world > 1:
+            t = torch.tensor([x], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            return float(t.item())
+        return x
+
+    def sum_over_ranks(x: float) -> float:
+        if world > 1:
+            t = torch.tensor([x], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.SUM)
+            return float(t.item())
+        return x
 
     def timed_loop(fn, steps, warmup, flush=True):
         for _ in range(warmup):
@@ -363,17 +407,12 @@ def run_ours(args):
             b.record()
             evs.append((a, b))
         barrier()
-        total_ms = sum(a.elapsed_time(b) for a, b in evs)
-        if world > 1:
-            t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            total_ms = float(t.item())
-        return total_ms
+        return max_over_ranks(sum(a.elapsed_time(b) for a, b in evs))
 
     def settle_capacity(step, result):
         """One untimed run: a dispatch whose pair count exceeds the default buffer reports MCB200_ERR_CAPACITY from
         mcb200_result_counts, which also raises the capacity; the timed loops then run with buffers that fit."""
-        for _ in range(4):
+        for _ in range(5):
             try:
                 step()
                 result.counts()
@@ -383,14 +422,277 @@ def run_ours(args):
                     raise
         raise RuntimeError("pair buffer did not settle")
 
-    settle_capacity(step_resident, res)
+    def make_comm():
+        idbuf = ctypes.create_string_buffer(128)
+        if rank == 0:
+            ctx.check(L.mcb200_comm_unique_id(idbuf))
+        t = torch.frombuffer(bytearray(idbuf.raw), dtype=torch.uint8).to(dev)
+        dist.broadcast(t, 0)
+        raw = bytes(t.cpu().numpy().tobytes())
+        h = vp()
+        ctx.check(L.mcb200_comm_create(ctx.h, world, rank, raw, ctypes.byref(h)))
+        return h
+
+    class Resident:
+        """both meshes, their frame and the polygon soup resident on the device (the `value` leg's inputs)"""
+
+        def __init__(self, src, cut):
+            sx, sf, _ = src
+            cx, cf, _ = cut
+            self.src_nv, self.src_nf = meshgen.mesh_counts(src)
+            self.cut_nv, self.cut_nf = meshgen.mesh_counts(cut)
+            self.com, self.shift, sbb, cbb = stage.vertex_parameters(sx, cx)
+            self.eps = stage.cut_bbox_eps(cbb, 1e-4, False)
+            soff = np.arange(0, sf.size + 1, 3, dtype=np.uint32)
+            coff = np.arange(0, cf.size + 1, 3, dtype=np.uint32)
+            fv, fe, ev, ef = stage.soup_ids(self.src_nv, soff, sf, coff, cf)
+            self.ne, self.nh = ev.shape[0], fv.size
+            self.keep, self.host = [], {}
+            for nm, arr in (("sx", sx), ("sf", sf), ("cx", cx), ("cf", cf), ("fv", fv), ("fe", fe), ("ef", ef)):
+                t, a = pinned_copy(torch, arr)
+                self.keep.append(t)
+                self.host[nm] = a
+            h = self.host
+            self.m_src, self.m_cut, self.soup = vp(), vp(), vp()
+            ctx.check(L.mcb200_mesh_create(ctx.h, 0, h["sx"].ctypes.data, self.src_nv, h["sf"].ctypes.data_as(stage.c_u32p), None, self.src_nf,
+                                           ctypes.byref(self.m_src)))
+            ctx.check(L.mcb200_mesh_create(ctx.h, 0, h["cx"].ctypes.data, self.cut_nv, h["cf"].ctypes.data_as(stage.c_u32p), None, self.cut_nf,
+                                           ctypes.byref(self.m_cut)))
+            for m in (self.m_src, self.m_cut):
+                ctx.check(L.mcb200_mesh_set_frame(ctx.h, m, self.com.ctypes.data_as(stage.c_dp), self.shift.ctypes.data_as(stage.c_dp), None))
+            ctx.check(L.mcb200_soup_create(ctx.h, self.src_nf, self.cut_nf, self.nh, self.ne, h["fv"].ctypes.data_as(stage.c_u32p),
+                                           h["fe"].ctypes.data_as(stage.c_u32p), h["ef"].ctypes.data_as(stage.c_u32p), ctypes.byref(self.soup)))
+            self.hm_src = HostMesh(0, h["sx"].ctypes.data, self.src_nv, h["sf"].ctypes.data, None, self.src_nf)
+            self.hm_cut = HostMesh(0, h["cx"].ctypes.data, self.cut_nv, h["cf"].ctypes.data, None, self.cut_nf)
+            self.h_soup = HostSoup(self.nh, self.ne, h["fe"].ctypes.data, h["ef"].ctypes.data)
+
+        def stage(self, res):
+            ctx.check(L.mcb200_intersect_stage(ctx.h, self.m_src, self.m_cut, self.eps, self.soup, res.h, 0))
+
+        def stage_host(self, res, soup_arg=None):
+            ctx.check(L.mcb200_intersect_stage_host(ctx.h, ctypes.byref(self.hm_src), ctypes.byref(self.hm_cut),
+                                                    self.com.ctypes.data_as(stage.c_dp), self.shift.ctypes.data_as(stage.c_dp), None, self.eps,
+                                                    soup_arg, res.h, 0))
+
+        def free(self):
+            L.mcb200_soup_free(ctx.h, self.soup)
+            L.mcb200_mesh_free(ctx.h, self.m_src)
+            L.mcb200_mesh_free(ctx.h, self.m_cut)
+
+    def measure_sharded(R, comm, steps, warmup, reference_res):
+        """one dispatch split over all ranks; returns the section for the JSON line.  The merged pairs and records of every
+        rank are compared byte for byte with that rank's own single-GPU result."""
+        res3 = stage.Result(ctx)
+
+        def step():
+            for _ in range(5):
+                rc = L.mcb200_intersect_stage_sharded(ctx.h, comm, R.m_src, R.m_cut, R.eps, R.soup, res3.h, 0)
+                if rc != stage.ERR_CAPACITY:
+                    ctx.check(rc)
+                    return
+            raise RuntimeError("sharded stage: capacities did not settle")
+
+        step()
+        res3.counts()
+        total_ms = timed_loop(step, steps, warmup)
+        c3 = res3.counts()
+        same = None
+        if reference_res is not None:
+            c1 = reference_res.counts()
+            same = bool(c1.n_pairs == c3.n_pairs and c1.n_records == c3.n_records and c1.n_tests == c3.n_tests
+                        and reference_res.pairs().tobytes() == res3.pairs().tobytes()
+                        and reference_res.records().tobytes() == res3.records().tobytes())
+            same = bool(sum_over_ranks(1.0 if same else 0.0) == world)
+        out = {"ms_per_dispatch": total_ms / steps, "pairs": int(c3.n_pairs), "records": int(c3.n_records),
+               "pairs_per_s": int(c3.n_pairs) / (total_ms / steps * 1e-3),
+               "identical_to_single_gpu_result_on_every_rank": same,
+               "scheme": "replicated meshes + BVHs, 4096-leaf chunks of the Morton order dealt round-robin, exchange inside the C-ABI: "
+                         "ncclAllGather of the counter blocks, grouped ncclBroadcast of pairs and records, ncclAllReduce of per-face "
+                         "pair counts and candidate flags, canonical orders on every rank"}
+        res3.free()
+        return out
+
+    name = args.workload
+    cfg = base_config(name, world)
+
+    # ==================================================================================================================
+    # batch workloads
+    # ==================================================================================================================
+    if name in ("c3batch", "c4batch"):
+        nlanes = args.lanes if args.lanes > 0 else (8 if name == "c4batch" else 2)
+        n_items = args.batch if args.batch > 0 else (256 if name == "c3batch" else 2000)
+        my_items = list(range(rank, n_items, world))  # round-robin over the GPUs (SURVEY §8-e)
+        lanes = [ctx] + [stage.Context(local_rank) for _ in range(nlanes - 1)]
+        lane_res = [stage.Result(c) for c in lanes]
+        ctx_arr = (vp * nlanes)(*[c.h for c in lanes])
+        res_arr = (vp * nlanes)(*[r.h for r in lane_res])
+        keep = []
+        items = (BatchItem * len(my_items))()
+        h2d = 0
+        if name == "c4batch":
+            for k, j in enumerate(my_items):
+                s, c, f = meshgen.c4_pair(j)
+                ts, sx = pinned_copy(torch, s[0])
+                tc, cx = pinned_copy(torch, c[0])
+                if k == 0:
+                    tf, fa = pinned_copy(torch, s[1])
+                    keep.append(tf)
+                keep += [ts, tc]
+                nv, nf = sx.shape[0], fa.size // 3
+                items[k].src = HostMesh(0, sx.ctypes.data, nv, fa.ctypes.data, None, nf)
+                items[k].cut = HostMesh(0, cx.ctypes.data, nv, fa.ctypes.data, None, nf)
+                items[k].com = None
+                items[k].gp_constant = 1e-4
+                items[k].flags = 0
+                h2d = sx.nbytes + cx.nbytes + 2 * fa.nbytes
+            src_faces = cut_faces = nf
+            cut_nv = nv
+        else:
+            ter = meshgen.terrain()
+            tt, tx = pinned_copy(torch, ter[0])
+            tf, tfa = pinned_copy(torch, ter[1])
+            keep += [tt, tf]
+            nv, nf = tx.shape[0], tfa.size // 3
+            for k, j in enumerate(my_items):
+                nrm, _ = meshgen.c3_plane(j)
+                tri = meshgen.c3_supertriangle(ter[0], nrm)
+                tc, cx = pinned_copy(torch, tri[0])
+                tcf, cfa = pinned_copy(torch, tri[1])
+                keep += [tc, tcf]
+                items[k].src = HostMesh(0, tx.ctypes.data, nv, tfa.ctypes.data, None, nf)
+                items[k].cut = HostMesh(0, cx.ctypes.data, 3, cfa.ctypes.data, None, 1)
+                items[k].com = None
+                items[k].gp_constant = 1e-4
+                # the terrain arrays are the same in every dispatch: after a lane's first item only the plane travels
+                items[k].flags = stage.STAGE_SRC_RESIDENT if k >= nlanes else 0
+            src_faces, cut_faces, cut_nv = nf, 1, 3
+            h2d = 3 * 24 + 12  # per dispatch once the terrain is resident on the lane (first item of a lane: + 96 MB)
+        counts = (Counts * len(my_items))()
+
+        def run_batch(lo, hi):
+            n = hi - lo
+            if n <= 0:
+                return
+            sub = ctypes.cast(ctypes.addressof(items) + lo * ctypes.sizeof(BatchItem), ctypes.POINTER(BatchItem))
+            csub = ctypes.cast(ctypes.addressof(counts) + lo * ctypes.sizeof(Counts), ctypes.POINTER(Counts))
+            rc = L.mcb200_batch_intersect_host(ctx_arr, res_arr, nlanes, sub, n, csub)
+            if rc:
+                ctx.check(rc)
+
+        warm = min(max(args.warmup * nlanes, 2 * nlanes), len(my_items) // 2)
+        warm -= warm % nlanes  # the timed part starts on lane 0 again
+        run_batch(0, warm)  # allocations, graph capture, (c3batch) the terrain lands on every lane
+        torch.cuda.synchronize()
+        sampler = ClockSampler(local_rank)
+        if rank == 0:
+            sampler.start()
+        barrier()
+        launches0 = sum(c.launches for c in lanes)
+        t0 = time.perf_counter()
+        run_batch(warm, len(my_items))
+        torch.cuda.synchronize()
+        wall = time.perf_counter() - t0
+        launches = sum(c.launches for c in lanes) - launches0
+        barrier()
+        clocks = sampler.stop() if rank == 0 else None
+        timed = len(my_items) - warm
+        pairs = sum(int(counts[i].n_pairs) for i in range(warm, len(my_items)))
+        bad = sum(1 for i in range(len(my_items)) if counts[i].status not in (0, 1))
+        wall = max_over_ranks(wall)
+        pairs_all = sum_over_ranks(float(pairs))
+        timed_all = sum_over_ranks(float(timed))
+        e2e_value = pairs_all / wall
+        # per-kernel device times of a few dispatches (lane 0, profiling on: no graph) for the roofline entry
+        ctx.set_profiling(True)
+        prof_n = min(4, len(my_items))
+        sub_ctx = (vp * 1)(ctx.h)
+        sub_res = (vp * 1)(lane_res[0].h)
+        c_tmp = (Counts * prof_n)()
+        for it in range(prof_n):
+            items[it].flags = 0
+        L.mcb200_batch_intersect_host(sub_ctx, sub_res, 1, items, prof_n, c_tmp)
+        prof = ctx.profile_read()
+        ctx.set_profiling(False)
+        kern = {k: {"launches_per_step": cnt / prof_n, "ms_per_step": ms / prof_n, "ms_per_launch": ms / cnt} for k, (cnt, ms) in prof.items()}
+        top = max(kern, key=lambda k: kern[k]["ms_per_step"])
+        counts1 = {"n_pairs": int(c_tmp[0].n_pairs), "n_tests": int(c_tmp[0].n_tests), "n_node_tests": int(c_tmp[0].n_node_tests)}
+        roofline, rooflines = None, []
+        facts = profile_facts(name)
+        for kname in sorted(kern, key=lambda k: -kern[k]["ms_per_step"]):
+            ab = algorithmic_bytes(kname, nv, src_faces, cut_nv, cut_faces, counts1)
+            if ab is None:
+                continue
+            ach = ab / (kern[kname]["ms_per_launch"] * 1e-3) / 1e9
+            if ach / peak > 1.2:
+                continue  # the mean-size byte model does not describe this launch (e.g. a one-face mesh)
+            e = {"kernel": kname, "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                 "traffic": facts.get(kname, {}).get("dram_bytes_per_launch"), "peak_source": peak_src,
+                 "algorithmic_bytes_per_launch": ab, "ms_per_launch": kern[kname]["ms_per_launch"]}
+            rooflines.append(e)
+            roofline = roofline or e
+        cpu = None
+        if rank == 0 and world == 1 and not args.no_cpu_baseline and have_reference_binary():
+            cores = os.cpu_count() or 1
+            with tempfile.TemporaryDirectory() as td:
+                if name == "c4batch":
+                    sample_n = min(64, n_items)
+                    inputs = []
+                    for j in range(sample_n):
+                        s, c, f = meshgen.c4_pair(j)
+                        ip = os.path.join(td, f"in{j}.mcb")
+                        write_input(s, c, f, ip)
+                        inputs.append(ip)
+                    w, sms, prs, helpers = reference_streams(inputs, cores, cores, td)
+                    what = f"{sample_n} pairs, {cores} reference processes in flight with 0 helper threads (the tutorial's pattern)"
+                else:
+                    sample_n = 2
+                    ip = os.path.join(td, "in.mcb")
+                    write_input(ter, (np.zeros((3, 3)), np.array([0, 1, 2], dtype=np.uint32), None), DBL, ip)
+                    w, sms, prs, helpers = reference_streams([ip] * sample_n, 1, cores, td, c3_plane_extra)
+                    what = f"{sample_n} planar sections through mcEnqueueDispatchPlanarSection, one at a time with {helpers} helper threads"
+                cpu = {"value": prs / w, "unit": UNIT, "cores": cores, "kind": "reference", "dispatches_per_s": sample_n / w,
+                       "stage_ms_mean": float(np.mean(sms)),
+                       "sample": what + "; value = candidate pairs / wall time of the sample (process start-up and mesh conversion included: "
+                                        "the reference has no batched entry point)"}
+        if rank == 0:
+            cfg.update({"dispatches": int(timed_all), "lanes_per_gpu": nlanes, "src_faces": src_faces, "cut_faces": cut_faces,
+                        "pairs_per_dispatch": pairs_all / max(timed_all, 1), "dispatches_per_s": timed_all / wall,
+                        "failed_dispatches": bad,
+                        "timing": "host wall clock around mcb200_batch_intersect_host between device synchronisations (several "
+                                  "streams are in flight: no single stream's events bracket the batch); L2 is not flushed between "
+                                  "dispatches (every dispatch brings new inputs from the host)"})
+            line = {"metric": METRIC, "value": e2e_value, "unit": UNIT, "n_gpus": world, "steps": int(timed_all), "warmup": warm,
+                    "ms_per_step": wall * 1e3 / max(timed_all / world, 1), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                    "dtype": "f64", "data": "synthetic", "config": cfg, "clocks": clocks,
+                    "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": 56,
+                            "call": "mcb200_batch_intersect_host",
+                            "note": "value == e2e for batch workloads: the batch entry point takes host arrays by design; inputs come "
+                                    "from pinned host memory every dispatch, the counts/status of every dispatch are read back"},
+                    "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu, "rooflines": rooflines, "kernels": kern,
+                    "top_kernel": top}
+            sys.stdout.flush()
+            os.dup2(real_stdout, 1)
+            print(json.dumps(line), flush=True)
+            os.dup2(2, 1)
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
+        return
+
+    # ==================================================================================================================
+    # single-dispatch workloads
+    # ==================================================================================================================
+    src, cut, flags = workload(name)
+    R = Resident(src, cut)
+    res = stage.Result(ctx)
+    settle_capacity(lambda: R.stage(res), res)
 
     # ---- value: resident inputs ----
     launches0 = ctx.launches
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    total_ms = timed_loop(step_resident, args.steps, args.warmup)
+    total_ms = timed_loop(lambda: R.stage(res), args.steps, args.warmup)
     clocks = sampler.stop() if rank == 0 else None
     launches = (ctx.launches - launches0) // (args.steps + args.warmup) * args.steps
     c = res.counts()
@@ -402,42 +704,31 @@ def run_ours(args):
     # ---- e2e: host buffers through the C-ABI every step ----
     pairs_host_t = torch.empty(max(counts["n_pairs"] * 2, 1 << 16), dtype=torch.int64).pin_memory()
     rec_host_t = torch.empty(max(counts["n_records"] * 2, 1 << 12) * 4, dtype=torch.float64).pin_memory()
-    pairs_host = pairs_host_t.numpy()
-    rec_host = rec_host_t.numpy()
+    pairs_host, rec_host = pairs_host_t.numpy(), rec_host_t.numpy()
     res2 = stage.Result(ctx)
     d2h = {"bytes": 0}
-
-    from mcut_b200._lib import HostMesh, HostSoup
-    hm_src = HostMesh(0, host["sx"].ctypes.data, src_nv, host["sf"].ctypes.data, None, src_nf)
-    hm_cut = HostMesh(0, host["cx"].ctypes.data, cut_nv, host["cf"].ctypes.data, None, cut_nf)
-    h_soup = HostSoup(nh, ne, host["fe"].ctypes.data, host["ef"].ctypes.data)
 
     def step_e2e(soup_arg=None):
         # ONE reference-facing call with host arrays: uploads are pipelined with the builds inside it; soup == NULL: the
         # polygon soup is numbered on the device, only the two meshes travel
-        ctx.check(L.mcb200_intersect_stage_host(ctx.h, ctypes.byref(hm_src), ctypes.byref(hm_cut), com.ctypes.data_as(stage.c_dp),
-                                                shift.ctypes.data_as(stage.c_dp), None, eps, soup_arg, res2.h, 0))
+        R.stage_host(res2, soup_arg)
         cc = res2.counts()
         ctx.check(L.mcb200_result_read_pairs(ctx.h, res2.h, pairs_host.ctypes.data_as(stage.c_u64p), pairs_host.size))
         ctx.check(L.mcb200_result_read_records(ctx.h, res2.h, ctypes.cast(rec_host.ctypes.data, ctypes.POINTER(stage.Record)),
                                                rec_host.size // 4))
         d2h["bytes"] = int(cc.n_pairs) * 8 + int(cc.n_records) * 32 + 128
-        d2h["pairs"] = int(cc.n_pairs)
-        d2h["records"] = int(cc.n_records)
+        d2h["pairs"], d2h["records"] = int(cc.n_pairs), int(cc.n_records)
 
     settle_capacity(step_e2e, res2)
     e2e_steps = max(3, min(args.steps, 10))
-    e2e_total = timed_loop(step_e2e, e2e_steps, max(args.warmup, 3), flush=False)
-    e2e_ms = e2e_total / e2e_steps
+    e2e_ms = timed_loop(step_e2e, e2e_steps, max(args.warmup, 3), flush=False) / e2e_steps
     assert d2h["pairs"] == counts["n_pairs"] and d2h["records"] == counts["n_records"], "host-array path disagrees with the resident path"
-    h2d = sum(host[k].nbytes for k in ("sx", "sf", "cx", "cf"))
-    # variant: the caller brings its own `ps` edge ids (what the reference holds on the host) and they are uploaded too
-    e2e_hs_ms = timed_loop(lambda: step_e2e(ctypes.byref(h_soup)), e2e_steps, 3, flush=False) / e2e_steps
+    h2d = sum(R.host[k].nbytes for k in ("sx", "sf", "cx", "cf"))
+    e2e_hs_ms = timed_loop(lambda: step_e2e(ctypes.byref(R.h_soup)), e2e_steps, 3, flush=False) / e2e_steps
     e2e = {"value": world * counts["n_pairs"] / (e2e_ms * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms,
-           "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h["bytes"]),
-           "call": "mcb200_intersect_stage_host",
+           "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h["bytes"]), "call": "mcb200_intersect_stage_host",
            "ms_per_step_with_host_soup_ids": e2e_hs_ms,
-           "h2d_bytes_with_host_soup_ids": int(h2d + host["fe"].nbytes + host["ef"].nbytes),
+           "h2d_bytes_with_host_soup_ids": int(h2d + R.host["fe"].nbytes + R.host["ef"].nbytes),
            "note": "inputs = both meshes from pinned host memory (uploads pipelined with the builds on a copy stream, polygon soup "
                    "numbered on the device); outputs = sorted pairs, registry records, status"}
 
@@ -446,83 +737,82 @@ def run_ours(args):
     ctx.set_profiling(True)
     for _ in range(prof_steps):
         flush_buf.zero_()
-        step_resident()
+        R.stage(res)
     prof = ctx.profile_read()
     ctx.set_profiling(False)
-    peak, peak_src = load_peaks()
     kern = {}
-    for name, (cnt, ms) in prof.items():
-        kern[name] = {"launches_per_step": cnt / prof_steps, "ms_per_step": ms / prof_steps, "ms_per_launch": ms / cnt}
+    for kname, (cnt, ms) in prof.items():
+        kern[kname] = {"launches_per_step": cnt / prof_steps, "ms_per_step": ms / prof_steps, "ms_per_launch": ms / cnt}
     step_kernel_ms = sum(v["ms_per_step"] for v in kern.values())
     top = max(kern, key=lambda k: kern[k]["ms_per_step"])
+    facts = profile_facts(name)
     # `roofline` = the kernel with the largest share of the step (among those with an algorithmic-bytes model);
     # `rooflines` = the same figures for every modelled kernel, largest share first
-    roofline = None
-    rooflines = []
-    cands = sorted(kern, key=lambda k: -kern[k]["ms_per_step"])
-    for name in cands:
-        ab = algorithmic_bytes(name, src_nv, src_nf, cut_nv, cut_nf, counts)
+    roofline, rooflines = None, []
+    for kname in sorted(kern, key=lambda k: -kern[k]["ms_per_step"]):
+        ab = algorithmic_bytes(kname, R.src_nv, R.src_nf, R.cut_nv, R.cut_nf, counts)
+        fact = facts.get(kname, {})
+        if kname.startswith("k_tests_exact") and counts["n_exact"] > 0:
+            # the exact-expansion kernel is compute / local-memory bound: what is reported is the FP64 pipe's busy share from
+            # the committed ncu capture of this workload (sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active)
+            pct = fact.get("fp64_pipe_pct")
+            rooflines.append({"kernel": kname, "bound": "fp64", "achieved": pct, "peak": 100.0, "unit": "% of FP64 pipe cycles",
+                              "frac": (pct / 100.0) if pct is not None else None, "traffic": fact.get("dram_bytes_per_launch"),
+                              "peak_source": "ncu capture of this workload under profiles/" if pct is not None else "not captured",
+                              "tests_per_launch": counts["n_exact"], "ms_per_launch": kern[kname]["ms_per_launch"],
+                              "share_of_step": kern[kname]["ms_per_step"] / step_kernel_ms})
+            continue
         if ab is None:
             continue
-        achieved = ab / (kern[name]["ms_per_launch"] * 1e-3) / 1e9
-        entry = {"kernel": name, "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                 "traffic": kernel_traffic(name), "peak_source": peak_src, "algorithmic_bytes_per_launch": ab,
-                 "ms_per_launch": kern[name]["ms_per_launch"], "share_of_step": kern[name]["ms_per_step"] / step_kernel_ms}
+        achieved = ab / (kern[kname]["ms_per_launch"] * 1e-3) / 1e9
+        if achieved / peak > 1.2:
+            continue  # the mean-size byte model does not describe this launch (e.g. the one-face side of a planar section)
+        entry = {"kernel": kname, "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                 "traffic": fact.get("dram_bytes_per_launch"), "peak_source": peak_src, "algorithmic_bytes_per_launch": ab,
+                 "ms_per_launch": kern[kname]["ms_per_launch"], "share_of_step": kern[kname]["ms_per_step"] / step_kernel_ms,
+                 "fp64_pipe_pct": fact.get("fp64_pipe_pct")}
         rooflines.append(entry)
         if roofline is None:
             roofline = entry
-    # whole-build figure (B_build = 24V + 296F per mesh)
+    build_kernels = ("k_vertex_bbox", "k_face_codes", "k_face_bbox", "k_morton", "k_leaves")
     stage_ms = {
-        "build_ms": sum(kern[k]["ms_per_step"] for k in kern if k.startswith(("k_face_bbox", "k_morton", "k_tree", "k_refit"))
-                    or k == "onesweep_pass_u32_kv"),
-        "traverse_ms": sum(kern[k]["ms_per_step"] for k in kern if k in ("k_traverse", "k_group_filter")),
+        "build_ms": sum(kern[k]["ms_per_step"] for k in kern if k.startswith(build_kernels) or k == "onesweep_pass_u32_kv"),
+        "traverse_ms": sum(kern[k]["ms_per_step"] for k in kern if k == "k_traverse"),
         "narrowphase_ms": sum(kern[k]["ms_per_step"] for k in kern if "k_tests" in k or "k_planes" in k),
-        "pair_and_record_sort_ms": sum(kern[k]["ms_per_step"] for k in kern if "u64" in k),
-        "other_ms": sum(kern[k]["ms_per_step"] for k in kern if "k_make_keys" in k or "k_gather" in k or "k_rank_sort" in k),
+        "pair_and_record_order_ms": sum(kern[k]["ms_per_step"] for k in kern if "u64" in k or k.startswith("k_pair") or "k_rank_sort" in k
+                                        or "k_make_keys" in k or "k_gather" in k),
         "sum_of_kernels_ms": step_kernel_ms,
     }
+    # whole-stage and whole-build figures against the HBM roofline by SURVEY §8-d's byte model (B_build = 24V + 296F per mesh)
+    b_build = 24.0 * (R.src_nv + R.cut_nv) + 296.0 * (R.src_nf + R.cut_nf)
+    b_rest = 48.0 * counts["n_node_tests"] + 8.0 * counts["n_pairs"] + 8.0 * counts["n_pairs"] + 128.0 * counts["n_tests"]
+    stage_roofline = {"bytes_model": "SURVEY 8-d: build 24V+296F per mesh, traversal 48/test + 8/pair, cull+predicates 8/pair + 128/test",
+                      "build_frac_of_hbm_by_kernel_sum": b_build / (stage_ms["build_ms"] * 1e-3) / 1e9 / peak if stage_ms["build_ms"] else None,
+                      "stage_frac_of_hbm_by_step_time": (b_build + b_rest) / (ms_per_step * 1e-3) / 1e9 / peak}
 
-    # ---- sharded single dispatch (N > 1): leaf-range split + NCCL all-gather of pairs / records ----
+    # ---- sharded single dispatch (N > 1) ----
     sharded = None
     if world > 1:
-        res3 = stage.Result(ctx)
-        res3.set_shard(rank, world, 4096)
-
-        class _DevArr:
-            def __init__(self, ptr, n, typestr):
-                self.__cuda_array_interface__ = {"shape": (n,), "typestr": typestr, "data": (ptr, False), "version": 2}
-
-        max_pairs = torch.zeros(1, dtype=torch.int64, device=dev)
-
-        def step_sharded():
-            ctx.check(L.mcb200_intersect_stage(ctx.h, m_src, m_cut, eps, soup, res3.h, 0))
-            ptr, n = res3.device_ptr(0)
-            rptr, rn = res3.device_ptr(1)
-            cnt = torch.tensor([n, rn], dtype=torch.int64, device=dev)
-            allc = [torch.zeros(2, dtype=torch.int64, device=dev) for _ in range(world)]
-            dist.all_gather(allc, cnt)
-            allc_h = torch.stack(allc).cpu().numpy()
-            mp, mr = int(allc_h[:, 0].max()), int(allc_h[:, 1].max())
-            mine = torch.zeros(max(mp, 1), dtype=torch.int64, device=dev)
-            if n:
-                mine[:n] = torch.as_tensor(_DevArr(ptr, n, "<i8"), device=dev)
-            outs = [torch.empty_like(mine) for _ in range(world)]
-            dist.all_gather(outs, mine)
-            minr = torch.zeros(max(mr, 1) * 4, dtype=torch.float64, device=dev)
-            if rn:
-                minr[:rn * 4] = torch.as_tensor(_DevArr(rptr, rn * 4, "<f8"), device=dev)
-            outr = [torch.empty_like(minr) for _ in range(world)]
-            dist.all_gather(outr, minr)
-            max_pairs[0] = int(allc_h[:, 0].sum())
-
-        sh_total = timed_loop(step_sharded, max(3, min(args.steps, 10)), max(args.warmup, 3))
-        sh_ms = sh_total / max(3, min(args.steps, 10))
-        total_pairs = int(max_pairs.item())
-        sharded = {"ms_per_dispatch": sh_ms, "pairs": total_pairs, "pairs_per_s": total_pairs / (sh_ms * 1e-3),
-                   "matches_single_gpu_pair_count": total_pairs == counts["n_pairs"],
-                   "scheme": "replicated meshes+BVHs, 4096-leaf chunks of the Morton order dealt round-robin, "
-                             "NCCL all_gather of counts, pairs and records"}
-        res3.free()
+        comm = make_comm()
+        sh_steps = max(3, min(args.steps, 10))
+        sharded = {"this_workload": measure_sharded(R, comm, sh_steps, max(args.warmup, 3), res)}
+        sharded["this_workload"]["single_gpu_ms"] = ms_per_step
+        if name != "c5" and not args.no_sharded_c5:
+            # the split pays where traversal + narrowphase dominate: BASELINE config 5
+            res.free()
+            res2.free()
+            R.free()
+            s5, c5, f5 = workload("c5")
+            R5 = Resident(s5, c5)
+            r5 = stage.Result(ctx)
+            settle_capacity(lambda: R5.stage(r5), r5)
+            one = timed_loop(lambda: R5.stage(r5), 3, 3) / 3
+            sec = measure_sharded(R5, comm, 3, 3, r5)
+            sec["single_gpu_ms"] = one
+            sec["speedup_vs_single_gpu"] = one / sec["ms_per_dispatch"]
+            sec["workload"] = WORKLOADS["c5"]
+            sharded["c5"] = sec
+        L.mcb200_comm_destroy(comm)
 
     # ---- cpu baseline (rank 0, N == 1 only) ----
     cpu = None
@@ -531,14 +821,13 @@ def run_ours(args):
         with tempfile.TemporaryDirectory() as td:
             if have_reference_binary():
                 write_input(src, cut, flags, os.path.join(td, "in.mcb"))
-                runs = []
+                runs, npairs_ref = [], 0
                 for _ in range(2):
-                    ms, npairs_ref, npts, seen = reference_stage_once(os.path.join(td, "in.mcb"), os.path.join(td, "out.mcb"),
-                                                                      max(cores - 1, 0))
-                    runs.append(ms)
+                    w, sms, npairs_ref, helpers = reference_streams([os.path.join(td, "in.mcb")], 1, cores, td)
+                    runs.append(sms[0])
                 best = min(runs)
                 cpu = {"value": npairs_ref / (best * 1e-3), "unit": UNIT, "cores": cores, "kind": "reference",
-                       "ms_per_step": best, "pairs": npairs_ref, "intersection_points": npts,
+                       "ms_per_step": best, "pairs": npairs_ref,
                        "sample": "2 whole intersect stages of the full workload (best of 2): one mcDispatch of the unmodified "
                                  "reference each, cut short after its narrowphase; stage ms = the reference's own timers "
                                  "(build_oibvh x2, intersectOIBVHs, kernel.cpp:1781-3231), helper pool = cores-1 threads"}
@@ -548,14 +837,14 @@ def run_ours(args):
                        "pairs": npairs_ref, "sample": "1 run of the single-threaded oracle port on the full workload"}
 
     if rank == 0:
+        cfg.update({"pairs_per_dispatch": counts["n_pairs"], "src_faces": R.src_nf, "cut_faces": R.cut_nf,
+                    "l2": "256 MiB write between timed steps", **counts, "status": status})
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
-            "data": "synthetic",
-            "config": {"workload": desc, "src_faces": src_nf, "cut_faces": cut_nf, "l2": "256 MiB write between timed steps",
-                       "parallelism": f"{world} independent dispatch(es), one context per GPU", **counts, "status": status},
-            "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
-            "rooflines": rooflines, "stage_ms": stage_ms, "kernels": kern, "top_kernel": top,
+            "data": "synthetic", "config": cfg, "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
+            "cpu_baseline": cpu, "rooflines": rooflines, "stage_roofline": stage_roofline, "stage_ms": stage_ms, "kernels": kern,
+            "top_kernel": top,
         }
         if sharded:
             line["sharded"] = sharded
@@ -574,14 +863,15 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="c2")
+    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
+    ap.add_argument("--batch", type=int, default=0, help="batch workloads: number of dispatches (default 256 / 2000)")
+    ap.add_argument("--lanes", type=int, default=0, help="batch workloads: contexts in flight per GPU")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-sharded-c5", action="store_true")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3
     if args.impl == "reference":
-        if args.steps > 6:
-            pass  # each step is ~10 s of CPU work at full size; still run exactly K steps
         run_reference_arm(args)
     else:
         run_ours(args)

@@ -264,6 +264,25 @@ typedef struct mcb200_host_soup {
 int mcb200_intersect_stage_host(mcb200_ctx* ctx, const mcb200_host_mesh* src, const mcb200_host_mesh* cut, const double com[3],
     const double shift[3], const double perturbation[3] /* or NULL */, double cut_eps, const mcb200_host_soup* soup,
     mcb200_result* res, uint32_t flags);
+/* ---------------------------------------------------------------- one dispatch on several GPUs -------- */
+/* One process per GPU, one context each; NCCL (loaded at run time, libnccl.so.2) carries the exchange over NVLink.
+ * Rank 0 makes an id (mcb200_comm_unique_id), hands it to the other ranks by whatever means the application has (MPI,
+ * torch.distributed, a file), every rank calls mcb200_comm_create.
+ * mcb200_intersect_stage_sharded: every rank passes the SAME meshes and soup (replicated); rank r walks its slice of the
+ * query leaf range (4096-leaf chunks of the Morton order dealt round-robin) and runs the narrowphase on its pairs; pairs
+ * and registry records are then all-gathered (counts by ncclAllGather, payloads by grouped ncclBroadcast), merged and put in
+ * canonical order on every rank: afterwards `res` on every rank holds the complete result, byte for byte what one GPU
+ * produces.  Collective: all ranks must call it together.  MCB200_ERR_CAPACITY (on all ranks alike): run it again. */
+#define MCB200_COMM_ID_BYTES 128
+typedef struct mcb200_comm mcb200_comm;
+int mcb200_comm_unique_id(char id[MCB200_COMM_ID_BYTES]);
+int mcb200_comm_create(mcb200_ctx* ctx, int nranks, int rank, const char id[MCB200_COMM_ID_BYTES], mcb200_comm** comm);
+void mcb200_comm_destroy(mcb200_comm* comm);
+int mcb200_comm_rank(const mcb200_comm* comm);
+int mcb200_comm_size(const mcb200_comm* comm);
+int mcb200_intersect_stage_sharded(mcb200_ctx* ctx, mcb200_comm* comm, mcb200_mesh* src, mcb200_mesh* cut, double cut_eps,
+    const mcb200_soup* soup, mcb200_result* res, uint32_t flags);
+
 /* Many independent dispatches in one call — the MultipleContextsInParallel pattern (tutorials/MultipleContextsInParallel/
  * MultipleContextsInParallel.cpp:129-345: one MCUT context per task, tasks spread over threads) for dispatches that are too
  * small to fill the machine one at a time.  `nctx` contexts of ONE device (each with its own result object) serve as

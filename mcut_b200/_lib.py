@@ -97,6 +97,12 @@ SYMBOLS = {
                                              C.POINTER(HostSoup), vp, C.c_uint32]),
     "mcb200_staged_soup_read": (C.c_int, [vp, c_u32p, c_u32p, c_u32p, C.c_uint32, c_u32p, c_u32p]),
     "mcb200_result_counts": (C.c_int, [vp, vp, C.POINTER(Counts)]),
+    "mcb200_comm_unique_id": (C.c_int, [C.c_char_p]),
+    "mcb200_comm_create": (C.c_int, [vp, C.c_int, C.c_int, C.c_char_p, C.POINTER(vp)]),
+    "mcb200_comm_destroy": (None, [vp]),
+    "mcb200_comm_rank": (C.c_int, [vp]),
+    "mcb200_comm_size": (C.c_int, [vp]),
+    "mcb200_intersect_stage_sharded": (C.c_int, [vp, vp, vp, vp, C.c_double, vp, vp, C.c_uint32]),
     "mcb200_batch_intersect_host": (C.c_int, [C.POINTER(vp), C.POINTER(vp), C.c_uint32, C.POINTER(BatchItem), C.c_uint32,
                                               C.POINTER(Counts)]),
     "mcb200_result_read_pairs": (C.c_int, [vp, vp, c_u64p, C.c_size_t]),

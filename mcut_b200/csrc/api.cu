@@ -19,6 +19,7 @@ int fail(mcb200_ctx* ctx, int code, const char* msg, const char* file, int line)
 }
 #define MCB_FAIL(ctx, code, msg) return fail((ctx), (code), (msg), __FILE__, __LINE__)
 
+} // namespace
 int fetch_counters(mcb200_ctx* ctx, mcb200_result* res)
 {
     if (res->h_valid) return 0;
@@ -30,6 +31,7 @@ int fetch_counters(mcb200_ctx* ctx, mcb200_result* res)
     res->h_valid = true;
     return 0;
 }
+namespace {
 
 int upload(mcb200_ctx* ctx, dbuf& dst, const void* src, size_t bytes)
 {
@@ -762,6 +764,8 @@ int mcb200_narrowphase(mcb200_ctx* ctx, const mcb200_soup* soup, const mcb200_me
     return narrowphase_run(ctx, soup, src, cut, res, flags);
 }
 
+} // extern "C"
+
 // ---------------------------------------------------------------------------------------------------------- the stage
 // One body for both stage entry points.  Everything is enqueued from ctx->stream outwards (aux / background lanes fork from
 // it by event and join it again before the body returns), so the body can be CAPTURED into a CUDA graph and replayed:
@@ -770,8 +774,8 @@ int mcb200_narrowphase(mcb200_ctx* ctx, const mcb200_soup* soup, const mcb200_me
 // wait_uploads: the inputs are still travelling on ctx->copy (mcb200_intersect_stage_host without a graph): each lane waits
 // for the upload event of what it reads.  number_soup: 0 = the caller's soup as is, 1 = number the soup on the device,
 // 2 = the caller's edge ids, vertex lists derived on the device.
-static int stage_body(mcb200_ctx* ctx, mcb200_mesh* src, mcb200_mesh* cut, double cut_eps, mcb200_soup* soup, mcb200_result* res,
-    uint32_t flags, bool wait_uploads, int number_soup, bool interleave)
+int stage_body(mcb200_ctx* ctx, mcb200_mesh* src, mcb200_mesh* cut, double cut_eps, mcb200_soup* soup, mcb200_result* res,
+    uint32_t flags, bool wait_uploads, int number_soup, bool interleave, bool order)
 {
     ctx->use_main();
     // resets that nothing before the traversal depends on: up front, not between the kernels of the critical path
@@ -826,21 +830,23 @@ static int stage_body(mcb200_ctx* ctx, mcb200_mesh* src, mcb200_mesh* cut, doubl
     if (rc) return rc;
     // ---- traversal, then the pair sort (aux lane) next to the narrowphase (main lane, reads the unsorted pairs) ----
     MCB_TRY(traverse_pairs(ctx, src, cut, res));
-    MCB_CUDA(ctx, cudaEventRecord(ctx->ev_fork2, ctx->stream));
-    MCB_CUDA(ctx, cudaStreamWaitEvent(ctx->aux, ctx->ev_fork2, 0));
-    ctx->use_aux();
-    rc = sort_pairs(ctx, src, cut, res);
-    cudaEventRecord(ctx->ev_join2, ctx->aux);
-    ctx->use_main();
+    if (order) {
+        MCB_CUDA(ctx, cudaEventRecord(ctx->ev_fork2, ctx->stream));
+        MCB_CUDA(ctx, cudaStreamWaitEvent(ctx->aux, ctx->ev_fork2, 0));
+        ctx->use_aux();
+        rc = sort_pairs(ctx, src, cut, res);
+        cudaEventRecord(ctx->ev_join2, ctx->aux);
+        ctx->use_main();
+    }
     if (number_soup) cudaStreamWaitEvent(ctx->stream, ctx->ev_bg, 0);
     if (wait_uploads && number_soup == 2) cudaStreamWaitEvent(ctx->stream, ctx->ev_up[3], 0);
-    if (!rc) rc = narrowphase_run(ctx, soup, src, cut, res, flags);
-    cudaStreamWaitEvent(ctx->stream, ctx->ev_join2, 0);
+    if (!rc) rc = narrowphase_run(ctx, soup, src, cut, res, order ? flags : (flags | MCB200_NARROW_INTERNAL_PARTIAL));
+    if (order) cudaStreamWaitEvent(ctx->stream, ctx->ev_join2, 0);
     return rc;
 }
 
 // every allocation of a stage, on the main lane, before anything forks (the other lanes only ever see memory that exists)
-static int stage_reserve(mcb200_ctx* ctx, mcb200_mesh* src, mcb200_mesh* cut, const mcb200_soup* soup, mcb200_result* res, uint32_t flags)
+int stage_reserve(mcb200_ctx* ctx, mcb200_mesh* src, mcb200_mesh* cut, const mcb200_soup* soup, mcb200_result* res, uint32_t flags)
 {
     ctx->use_main();
     int rc = lbvh_reserve(ctx, src);
@@ -969,6 +975,8 @@ static int stage_run(mcb200_ctx* ctx, mcb200_mesh* src, mcb200_mesh* cut, double
     finish(g);
     return 0;
 }
+
+extern "C" {
 
 int mcb200_intersect_stage(mcb200_ctx* ctx, mcb200_mesh* src, mcb200_mesh* cut, double cut_eps, const mcb200_soup* soup,
     mcb200_result* res, uint32_t flags)

@@ -685,6 +685,53 @@ int narrowphase_reserve(mcb200_ctx* ctx, const mcb200_soup* soup, mcb200_result*
     return 0;
 }
 
+static int make_narrow_args(mcb200_ctx* ctx, const mcb200_soup* soup, const mcb200_mesh* src, const mcb200_mesh* cut, mcb200_result* res,
+    bool want_log, narrow_args_t& a)
+{
+    a.src_xyz = src->d_xyz;
+    a.cut_xyz = cut->d_xyz;
+    MCB_TRY(mesh_sync_frames(ctx, const_cast<mcb200_mesh*>(src), src->eps, const_cast<mcb200_mesh*>(cut), cut->eps));
+    a.src_frame = src->d_frames.as<frame_t>() + 1;
+    a.cut_frame = cut->d_frames.as<frame_t>() + 1;
+    a.src_nv = src->nv;
+    a.src_bbox = src->face_bbox.as<double>();
+    a.cut_bbox = cut->face_bbox.as<double>();
+    a.face_off = soup->face_off.as<uint32_t>();
+    a.face_vtx = soup->face_vtx.as<uint32_t>();
+    a.face_edge = soup->face_edge.as<uint32_t>();
+    a.edge_f = soup->edge_f.as<uint32_t>();
+    a.nsf = soup->nsf;
+    a.nf = soup->nsf + soup->ncf;
+    a.pairs = res->pairs.as<unsigned long long>();
+    a.cap_pairs = res->cap_pairs;
+    a.counters = res->counters.as<result_counters_t>();
+    a.cand_flag = res->cand_flag.as<uint8_t>();
+    a.records = res->records.as<mcb200_record>();
+    a.cap_records = res->cap_records;
+    a.exact_queue = res->exact_queue.as<unsigned long long>();
+    a.cap_exact = res->cap_exact;
+    a.tests = want_log ? res->tests.as<mcb200_test>() : nullptr;
+    a.cap_tests = res->cap_tests;
+    return 0;
+}
+
+// The plane data of the candidate faces (an OUTPUT, consumed downstream by the host; the tests compute the planes they need
+// themselves): one row per face flagged in res->cand_flag, on ctx->cur.
+int narrowphase_planes(mcb200_ctx* ctx, const mcb200_soup* soup, const mcb200_mesh* src, const mcb200_mesh* cut, mcb200_result* res)
+{
+    const uint32_t nf = soup->nsf + soup->ncf;
+    plane_args_t pa;
+    MCB_TRY(make_narrow_args(ctx, soup, src, cut, res, false, pa.n));
+    pa.plane = res->plane.as<double>();
+    pa.plane_mc = res->plane_mc.as<int32_t>();
+    pa.plane_face = reinterpret_cast<uint32_t*>(res->plane_mc.as<int32_t>() + nf);
+    const unsigned grid = (unsigned)ctx->num_sms * 8u;
+    const unsigned pgrid = div_up(nf, NBLOCK) < grid ? div_up(nf, NBLOCK) : grid;
+    if (soup->all_tri) MCB_LAUNCH(ctx, k_planes<true>, pgrid, NBLOCK, 0, pa);
+    else MCB_LAUNCH(ctx, k_planes<false>, pgrid, NBLOCK, 0, pa);
+    return 0;
+}
+
 int narrowphase_run(mcb200_ctx* ctx, const mcb200_soup* soup, const mcb200_mesh* src, const mcb200_mesh* cut,
     mcb200_result* res, uint32_t flags)
 {
@@ -699,8 +746,9 @@ int narrowphase_run(mcb200_ctx* ctx, const mcb200_soup* soup, const mcb200_mesh*
     const uint32_t nf = soup->nsf + soup->ncf;
     const bool tri = soup->all_tri != 0;
     const bool want_log = (flags & MCB200_NARROW_LOG_TESTS) != 0;
+    // a shard of a multi-GPU dispatch: the candidate-face rows and the canonical orders are made after the exchange (comm.cu)
+    const bool partial = (flags & MCB200_NARROW_INTERNAL_PARTIAL) != 0;
     MCB_TRY(narrowphase_reserve(ctx, soup, res, flags));
-    const size_t cap_rec = res->cap_records, cap_exact = res->cap_exact, cap_tests = res->cap_tests;
     if (!res->cand_flag_fresh) MCB_CUDA(ctx, cudaMemsetAsync(res->cand_flag.p, 0, (size_t)nf, ctx->cur));
     res->cand_flag_fresh = false;
 
@@ -717,54 +765,25 @@ int narrowphase_run(mcb200_ctx* ctx, const mcb200_soup* soup, const mcb200_mesh*
     res->narrow_counters_fresh = false;
 
     narrow_args_t a;
-    a.src_xyz = src->d_xyz;
-    a.cut_xyz = cut->d_xyz;
-    MCB_TRY(mesh_sync_frames(ctx, const_cast<mcb200_mesh*>(src), src->eps, const_cast<mcb200_mesh*>(cut), cut->eps));
-    a.src_frame = src->d_frames.as<frame_t>() + 1;
-    a.cut_frame = cut->d_frames.as<frame_t>() + 1;
-    a.src_nv = src->nv;
-    a.src_bbox = src->face_bbox.as<double>();
-    a.cut_bbox = cut->face_bbox.as<double>();
-    a.face_off = soup->face_off.as<uint32_t>();
-    a.face_vtx = soup->face_vtx.as<uint32_t>();
-    a.face_edge = soup->face_edge.as<uint32_t>();
-    a.edge_f = soup->edge_f.as<uint32_t>();
-    a.nsf = soup->nsf;
-    a.nf = nf;
-    a.pairs = res->pairs.as<unsigned long long>();
-    a.cap_pairs = res->cap_pairs;
-    a.counters = res->counters.as<result_counters_t>();
-    a.cand_flag = res->cand_flag.as<uint8_t>();
-    a.records = res->records.as<mcb200_record>();
-    a.cap_records = cap_rec;
-    a.exact_queue = res->exact_queue.as<unsigned long long>();
-    a.cap_exact = cap_exact;
-    a.tests = want_log ? res->tests.as<mcb200_test>() : nullptr;
-    a.cap_tests = cap_tests;
+    MCB_TRY(make_narrow_args(ctx, soup, src, cut, res, want_log, a));
 
     const unsigned grid = (unsigned)ctx->num_sms * 8u;
     if (tri) MCB_LAUNCH_NAMED(ctx, "k_tests_filter_tri", (k_tests<true, false>), grid, NBLOCK, 0, a);
     else MCB_LAUNCH_NAMED(ctx, "k_tests_filter_poly", (k_tests<false, false>), grid, NBLOCK, 0, a);
 
-    // The plane data of the candidate faces is an OUTPUT (consumed downstream by the host); the tests compute the planes
-    // they need themselves.  It only depends on the candidate flags the filter just wrote, so it runs beside the exact
-    // pass and the record sort on the background lane.
+    // The plane rows only depend on the candidate flags the filter just wrote, so they are made beside the exact pass and the
+    // record sort on the background lane.
     cudaStream_t lane = ctx->cur;
     const int lane_sci = ctx->sci;
-    MCB_CUDA(ctx, cudaEventRecord(ctx->ev_np, lane));
-    MCB_CUDA(ctx, cudaStreamWaitEvent(ctx->bg, ctx->ev_np, 0));
-    ctx->use_bg();
-
-    plane_args_t pa;
-    pa.n = a;
-    pa.plane = res->plane.as<double>();
-    pa.plane_mc = res->plane_mc.as<int32_t>();
-    pa.plane_face = reinterpret_cast<uint32_t*>(res->plane_mc.as<int32_t>() + nf);
-    const unsigned pgrid = div_up(nf, NBLOCK) < grid ? div_up(nf, NBLOCK) : grid;
-    if (tri) MCB_LAUNCH(ctx, k_planes<true>, pgrid, NBLOCK, 0, pa);
-    else MCB_LAUNCH(ctx, k_planes<false>, pgrid, NBLOCK, 0, pa);
-    ctx->cur = lane;
-    ctx->sci = lane_sci;
+    if (!partial) {
+        MCB_CUDA(ctx, cudaEventRecord(ctx->ev_np, lane));
+        MCB_CUDA(ctx, cudaStreamWaitEvent(ctx->bg, ctx->ev_np, 0));
+        ctx->use_bg();
+        const int rcp = narrowphase_planes(ctx, soup, src, cut, res);
+        ctx->cur = lane;
+        ctx->sci = lane_sci;
+        if (rcp) return rcp;
+    }
 
     // exact-expansion pass over the compacted filter failures (own kernel: its local-memory footprint and divergence
     // stay out of the filter kernel)
@@ -776,6 +795,7 @@ int narrowphase_run(mcb200_ctx* ctx, const mcb200_soup* soup, const mcb200_mesh*
     res->h_valid = false;
     res->records_sorted_valid = false;
     res->tests_sorted_valid = false;
+    if (partial) return 0;
     // Canonical order of the registry.  The small-n kernel stays on this lane; the radix path — nine launches that return
     // at once in the usual small case — goes to the background lane behind the plane kernel, so its launches are not paid
     // on the critical path.  (Scratch set 0 is free: this lane's last radix sort was the source mesh's Morton sort.)

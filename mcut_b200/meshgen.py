@@ -454,6 +454,30 @@ def c3_plane(k: int, count: int = 256) -> Tuple[np.ndarray, float]:
     return nrm, off
 
 
+def c3_supertriangle(xyz: np.ndarray, normal) -> Mesh:
+    """The cut mesh mcEnqueueDispatchPlanarSection builds for a section of `xyz` (frontend.cpp:722-899,
+    generate_supertriangle_from_mesh_vertices): one triangle of side ~4 bounding-box diagonals in the plane through the
+    vertex mean projected along the normal (the reference computes an offset centroid and then does not use it, :802)."""
+    n = np.asarray(normal, dtype=np.float64)
+    n = n / np.linalg.norm(n)
+    mean = xyz.mean(axis=0)
+    diag = float(np.linalg.norm(xyz.max(axis=0) - xyz.min(axis=0)))
+    k = int(np.argmax(np.abs(n)))
+    w = np.zeros(3)
+    w[k] = 1.0
+    if np.array_equal(w, n):
+        w[k] = 0.0
+        w[(k + 1) % 3] = 1.0
+    u = np.cross(n, w)
+    v = np.cross(n, u)
+    on_plane = mean - n * float(mean @ n)
+    uv_pos = (u + v) / np.linalg.norm(u + v)
+    uv_neg = (u - v) / np.linalg.norm(u - v)
+    third = (uv_pos + uv_neg) / np.linalg.norm(uv_pos + uv_neg)
+    tri = np.stack([on_plane + uv_pos * (2.0 * diag), on_plane + uv_neg * (2.0 * diag), on_plane - third * (2.0 * diag)])
+    return np.ascontiguousarray(tri), np.array([0, 1, 2], dtype=np.uint32), None
+
+
 # ----------------------------------------------------------------------------------------------
 # small shapes for unit tests
 # ----------------------------------------------------------------------------------------------
