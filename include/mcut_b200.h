@@ -74,6 +74,11 @@ typedef struct mcb200_result mcb200_result; /* device-resident outputs of traver
  * order = records sorted by (rank[edge], face). */
 int mcb200_reference_edge_rank(uint32_t n_cand_faces, const uint32_t* cand_faces, const uint32_t* face_off,
     const uint32_t* face_edge, uint32_t ne, uint32_t helper_threads, uint32_t* rank);
+/* The same order as a list, from compact arrays: slot_edge[slot_off[i] .. slot_off[i+1]) = the edges around the i-th candidate
+ * face (slot_off == NULL: three each).  order[0 .. *n_order) receives the distinct edges in registration order (capacity:
+ * the number of slots).  This is what the adapter calls inside a live dispatch: nothing here is sized by the mesh. */
+int mcb200_reference_edge_order(uint32_t n_cand_faces, const uint32_t* slot_off, const uint32_t* slot_edge,
+    uint32_t helper_threads, uint32_t* order, uint32_t* n_order);
 
 /* ---------------------------------------------------------------- context ---------------------------------- */
 int mcb200_device_count(void);
@@ -95,6 +100,11 @@ int mcb200_ctx_profile_read(mcb200_ctx* ctx, char* buf, size_t capacity);
 /* ---------------------------------------------------------------- host-side logic (no GPU) ----------------- */
 void mcb200_vertex_parameters(int is_float, const void* src_xyz, uint32_t nsv, const void* cut_xyz, uint32_t ncv,
     double com[3], double shift[3], double src_bbox[6], double cut_bbox[6]);
+/* the same in two steps: stats[9] = min xyz, max xyz, mean xyz of one mesh (the sequential pass), then the combination;
+ * lets a caller that cuts one source mesh many times (planar sections) scan it once */
+void mcb200_vertex_stats(int is_float, const void* xyz, uint32_t nv, double stats[9]);
+void mcb200_vertex_parameters_from_stats(const double src_stats[9], const double cut_stats[9], double com[3], double shift[3],
+    double src_bbox[6], double cut_bbox[6]);
 double mcb200_cut_bbox_eps(const double cut_bbox[6], double gp_constant, int absolute);
 /* Polygon-soup ids.  *_off are face offsets ([nf+1]); *_vtx the user's vertex lists.  Outputs (caller-allocated):
  *   face_vtx[nh], face_edge[nh]  (nh = src_off[nsf] + cut_off[ncf]) in ps.get_vertices_around_face order,
@@ -107,6 +117,12 @@ int mcb200_soup_ids(uint32_t nsv, const uint32_t* src_off, const uint32_t* src_v
 /* Uploads the user's arrays as they are (float or double vertices; face_sizes == NULL means triangles,
  * preproc.cpp:206).  No geometry is computed here. */
 int mcb200_mesh_create(mcb200_ctx* ctx, int is_float, const void* xyz, uint32_t nv, const uint32_t* face_vtx,
+    const uint32_t* face_sizes, uint32_t nf, mcb200_mesh** mesh);
+/* Same upload for a caller that has validated its indices already (the adapter inside a live mcDispatch, where
+ * client_input_arrays_to_hmesh has range-checked every index, preproc.cpp:271 / :417): no index check and no host copy of the
+ * face array.  Such a mesh cannot be handed to mcb200_soup_create, which reads that copy; number the soup on the device
+ * (mcb200_intersect_stage_host) or from the caller's own tables. */
+int mcb200_mesh_create_trusted(mcb200_ctx* ctx, int is_float, const void* xyz, uint32_t nv, const uint32_t* face_vtx,
     const uint32_t* face_sizes, uint32_t nf, mcb200_mesh** mesh);
 /* Same, from arrays that already live on this context's device (no copy is made of xyz/face_vtx; face_off may be
  * NULL for triangles).  Used when inputs are resident in HBM. */

@@ -63,11 +63,15 @@ SYMBOLS = {
     "mcb200_ctx_set_profiling": (C.c_int, [vp, C.c_int]),
     "mcb200_ctx_profile_read": (C.c_int, [vp, C.c_char_p, C.c_size_t]),
     "mcb200_vertex_parameters": (None, [C.c_int, vp, C.c_uint32, vp, C.c_uint32, c_dp, c_dp, c_dp, c_dp]),
+    "mcb200_vertex_stats": (None, [C.c_int, vp, C.c_uint32, c_dp]),
+    "mcb200_vertex_parameters_from_stats": (None, [c_dp, c_dp, c_dp, c_dp, c_dp, c_dp]),
     "mcb200_cut_bbox_eps": (C.c_double, [c_dp, C.c_double, C.c_int]),
     "mcb200_soup_ids": (C.c_int, [C.c_uint32, c_u32p, c_u32p, C.c_uint32, c_u32p, c_u32p, C.c_uint32, c_u32p, c_u32p, c_u32p,
                                   c_u32p, c_u32p]),
     "mcb200_reference_edge_rank": (C.c_int, [C.c_uint32, c_u32p, c_u32p, c_u32p, C.c_uint32, C.c_uint32, c_u32p]),
+    "mcb200_reference_edge_order": (C.c_int, [C.c_uint32, c_u32p, c_u32p, C.c_uint32, c_u32p, c_u32p]),
     "mcb200_mesh_create": (C.c_int, [vp, C.c_int, vp, C.c_uint32, c_u32p, c_u32p, C.c_uint32, C.POINTER(vp)]),
+    "mcb200_mesh_create_trusted": (C.c_int, [vp, C.c_int, vp, C.c_uint32, c_u32p, c_u32p, C.c_uint32, C.POINTER(vp)]),
     "mcb200_mesh_adopt_device": (C.c_int, [vp, C.c_int, vp, C.c_uint32, vp, vp, C.c_uint32, C.c_uint32, C.POINTER(vp)]),
     "mcb200_mesh_update_xyz": (C.c_int, [vp, vp, vp, C.c_uint32]),
     "mcb200_mesh_validate": (C.c_int, [vp, vp, C.POINTER(Validation)]),

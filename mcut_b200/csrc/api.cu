@@ -29,6 +29,7 @@ int fetch_counters(mcb200_ctx* ctx, mcb200_result* res)
     MCB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     std::memcpy(&res->h, ctx->h_pinned, sizeof(result_counters_t));
     res->h_valid = true;
+    if (res->pairs_order_unchecked) MCB_TRY(sort_pairs_fallback(ctx, res)); // a face with very many pairs: see traverse.cu
     return 0;
 }
 namespace {
@@ -256,8 +257,23 @@ static void identity_frame(frame_t& fr, int is_float)
     fr.is_float = is_float;
 }
 
+static int mesh_create_impl(mcb200_ctx* ctx, int is_float, const void* xyz, uint32_t nv, const uint32_t* face_vtx,
+    const uint32_t* face_sizes, uint32_t nf, mcb200_mesh** out, bool trusted);
+
 int mcb200_mesh_create(mcb200_ctx* ctx, int is_float, const void* xyz, uint32_t nv, const uint32_t* face_vtx,
     const uint32_t* face_sizes, uint32_t nf, mcb200_mesh** out)
+{
+    return mesh_create_impl(ctx, is_float, xyz, nv, face_vtx, face_sizes, nf, out, false);
+}
+
+int mcb200_mesh_create_trusted(mcb200_ctx* ctx, int is_float, const void* xyz, uint32_t nv, const uint32_t* face_vtx,
+    const uint32_t* face_sizes, uint32_t nf, mcb200_mesh** out)
+{
+    return mesh_create_impl(ctx, is_float, xyz, nv, face_vtx, face_sizes, nf, out, true);
+}
+
+static int mesh_create_impl(mcb200_ctx* ctx, int is_float, const void* xyz, uint32_t nv, const uint32_t* face_vtx,
+    const uint32_t* face_sizes, uint32_t nf, mcb200_mesh** out, bool trusted)
 {
     if (!ctx || !out) return MCB200_ERR_INVALID;
     *out = nullptr;
@@ -268,7 +284,7 @@ int mcb200_mesh_create(mcb200_ctx* ctx, int is_float, const void* xyz, uint32_t 
     m->nf = nf;
     m->is_float = is_float ? 1 : 0;
     m->is_tri = 1;
-    m->h_face_off.resize((size_t)nf + 1);
+    if (face_sizes || !trusted) m->h_face_off.resize((size_t)nf + 1);
     if (face_sizes) {
         uint32_t acc = 0;
         for (uint32_t f = 0; f < nf; ++f) {
@@ -281,16 +297,23 @@ int mcb200_mesh_create(mcb200_ctx* ctx, int is_float, const void* xyz, uint32_t 
             acc += face_sizes[f];
         }
         m->h_face_off[nf] = acc;
-    } else {
+    } else if (!trusted) {
         for (uint32_t f = 0; f <= nf; ++f) m->h_face_off[f] = 3u * f;
     }
-    m->nh = m->h_face_off[nf];
-    m->h_face_vtx.assign(face_vtx, face_vtx + m->nh);
-    for (uint32_t h = 0; h < m->nh; ++h)
-        if (face_vtx[h] >= nv) {
-            delete m;
-            MCB_FAIL(ctx, MCB200_ERR_INVALID, "mesh_create: face index out of range");
-        }
+    m->nh = face_sizes ? m->h_face_off[nf] : 3u * nf;
+    if (!trusted) {
+        // the host copy of the faces serves mcb200_soup_from_meshes; a caller that has validated its indices already and numbers
+        // the soup on the device (the adapter inside a live mcDispatch) skips both passes over the face array
+        m->h_face_vtx.assign(face_vtx, face_vtx + m->nh);
+        for (uint32_t h = 0; h < m->nh; ++h)
+            if (face_vtx[h] >= nv) {
+                delete m;
+                MCB_FAIL(ctx, MCB200_ERR_INVALID, "mesh_create: face index out of range");
+            }
+    } else if (m->is_tri) {
+        m->h_face_off.clear();
+        m->h_face_off.shrink_to_fit();
+    }
     identity_frame(m->frame, m->is_float);
     const size_t vbytes = (size_t)nv * 3 * (is_float ? sizeof(float) : sizeof(double));
     void* d_xyz = nullptr;
@@ -1149,15 +1172,25 @@ int mcb200_batch_intersect_host(mcb200_ctx** ctxs, mcb200_result** results, uint
     std::vector<frame_of_item> fr(nctx); // the frame of the item a lane is working on
     std::vector<uint32_t> in_flight(nctx, MCB200_NULL);
     int first_error = 0;
+    double src_stats[9];
+    const void* src_stats_of = nullptr;
+    uint32_t src_stats_nv = 0;
     auto enqueue = [&](uint32_t lane, uint32_t i) -> int {
         const mcb200_batch_item& it = items[i];
         frame_of_item& f = fr[lane];
         const double *com = it.com, *shift = it.shift;
         double eps = it.cut_eps;
         if (!com) {
-            double sb[6], cb[6];
+            double sb[6], cb[6], cs[9];
             if (it.src.is_float != it.cut.is_float) return MCB200_ERR_INVALID;
-            mcb200_vertex_parameters(it.src.is_float, it.src.xyz, it.src.nv, it.cut.xyz, it.cut.nv, f.com, f.shift, sb, cb);
+            // the source statistics are kept while the caller vouches (MCB200_STAGE_SRC_RESIDENT) that the arrays are unchanged
+            if (!((it.flags & MCB200_STAGE_SRC_RESIDENT) && src_stats_of == it.src.xyz && src_stats_nv == it.src.nv)) {
+                mcb200_vertex_stats(it.src.is_float, it.src.xyz, it.src.nv, src_stats);
+                src_stats_of = it.src.xyz;
+                src_stats_nv = it.src.nv;
+            }
+            mcb200_vertex_stats(it.cut.is_float, it.cut.xyz, it.cut.nv, cs);
+            mcb200_vertex_parameters_from_stats(src_stats, cs, f.com, f.shift, sb, cb);
             f.eps = mcb200_cut_bbox_eps(cb, it.gp_constant > 0.0 ? it.gp_constant : 1e-4, 0);
             com = f.com;
             shift = f.shift;

@@ -284,6 +284,8 @@ struct mcb200_result {
     dbuf pairs; // u64 [cap_pairs], in the order the traversal emitted them (what the narrowphase consumes)
     dbuf pairs_a, pairs_b; // ping-pong buffers of the pair sort
     dbuf pair_cnt, pair_off, pair_tile; // per source face: pair count / cursor, first slot in the ordered list; tile sums of the scan
+    const void* pairs_order_input = nullptr; // the unordered list the last sort_pairs took (fallback: sort_pairs_fallback)
+    bool pairs_order_unchecked = false; // pair_seg_max has not been looked at since the last sort_pairs
     void* pair_cnt_zeroed = nullptr; // the count array is all zero between runs (each run clears what it touched)
     unsigned long long* pairs_sorted = nullptr; // ascending (src << 32 | cut): points into pairs_a or pairs_b
     size_t cap_pairs = 0;

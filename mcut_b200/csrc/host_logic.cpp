@@ -64,17 +64,26 @@ inline uint64_t mix(uint64_t x)
 
 } // namespace
 
-extern "C" void mcb200_vertex_parameters(int is_float, const void* src_xyz, uint32_t nsv, const void* cut_xyz, uint32_t ncv,
-    double com[3], double shift[3], double src_bbox[6], double cut_bbox[6])
+// The frame in two steps: per-mesh statistics (a sequential pass over the vertices: min, max, mean), then their combination.
+// A caller that cuts the SAME source mesh again and again (planar sections: 256 planes through one terrain) keeps the
+// source's statistics and only scans the three vertices of each new cut mesh.
+extern "C" void mcb200_vertex_stats(int is_float, const void* xyz, uint32_t nv, double stats[9])
 {
-    const stats_t s = is_float ? scan_vertices(static_cast<const float*>(src_xyz), nsv)
-                               : scan_vertices(static_cast<const double*>(src_xyz), nsv);
-    const stats_t c = is_float ? scan_vertices(static_cast<const float*>(cut_xyz), ncv)
-                               : scan_vertices(static_cast<const double*>(cut_xyz), ncv);
+    const stats_t s = is_float ? scan_vertices(static_cast<const float*>(xyz), nv) : scan_vertices(static_cast<const double*>(xyz), nv);
+    for (int j = 0; j < 3; ++j) {
+        stats[j] = s.mn[j];
+        stats[3 + j] = s.mx[j];
+        stats[6 + j] = s.mean[j];
+    }
+}
+
+extern "C" void mcb200_vertex_parameters_from_stats(const double s[9], const double c[9], double com[3], double shift[3],
+    double src_bbox[6], double cut_bbox[6])
+{
     double to_positive[3];
     for (int j = 0; j < 3; ++j) {
-        com[j] = (s.mean[j] + c.mean[j]) / 2.0; // preproc.cpp:2215
-        const double lo = c.mn[j] < s.mn[j] ? c.mn[j] : s.mn[j];
+        com[j] = (s[6 + j] + c[6 + j]) / 2.0; // preproc.cpp:2215
+        const double lo = c[j] < s[j] ? c[j] : s[j];
         to_positive[j] = com[j] - lo; // :2221
     }
     double len2 = 0.0; // dot_product accumulates from 0.0 (math.h:634-642)
@@ -82,11 +91,20 @@ extern "C" void mcb200_vertex_parameters(int is_float, const void* src_xyz, uint
     const double len = std::sqrt(len2);
     for (int j = 0; j < 3; ++j) shift[j] = to_positive[j] + to_positive[j] / len; // :2222-2225
     for (int j = 0; j < 3; ++j) { // :2241-2246
-        src_bbox[j] = s.mn[j] + shift[j];
-        src_bbox[3 + j] = s.mx[j] + shift[j];
-        cut_bbox[j] = c.mn[j] + shift[j];
-        cut_bbox[3 + j] = c.mx[j] + shift[j];
+        src_bbox[j] = s[j] + shift[j];
+        src_bbox[3 + j] = s[3 + j] + shift[j];
+        cut_bbox[j] = c[j] + shift[j];
+        cut_bbox[3 + j] = c[3 + j] + shift[j];
     }
+}
+
+extern "C" void mcb200_vertex_parameters(int is_float, const void* src_xyz, uint32_t nsv, const void* cut_xyz, uint32_t ncv,
+    double com[3], double shift[3], double src_bbox[6], double cut_bbox[6])
+{
+    double s[9], c[9];
+    mcb200_vertex_stats(is_float, src_xyz, nsv, s);
+    mcb200_vertex_stats(is_float, cut_xyz, ncv, c);
+    mcb200_vertex_parameters_from_stats(s, c, com, shift, src_bbox, cut_bbox);
 }
 
 extern "C" double mcb200_cut_bbox_eps(const double cut_bbox[6], double gp_constant, int absolute)
@@ -174,6 +192,94 @@ extern "C" int mcb200_soup_ids(uint32_t nsv, const uint32_t* src_off, const uint
 #include <algorithm>
 #include <unordered_map>
 
+namespace {
+// node storage for the replayed maps: one arena, released at once (the iteration order does not depend on the allocator)
+struct arena_t {
+    std::vector<char*> blocks;
+    size_t left = 0;
+    char* cur = nullptr;
+    ~arena_t()
+    {
+        for (char* b : blocks) ::operator delete(b);
+    }
+    void* take(size_t bytes)
+    {
+        bytes = (bytes + 15u) & ~(size_t)15u;
+        if (bytes > left) {
+            const size_t block = std::max<size_t>(bytes, (size_t)1 << 20);
+            cur = static_cast<char*>(::operator new(block));
+            blocks.push_back(cur);
+            left = block;
+        }
+        void* p = cur;
+        cur += bytes;
+        left -= bytes;
+        return p;
+    }
+};
+template <typename T>
+struct arena_alloc {
+    typedef T value_type;
+    arena_t* a;
+    explicit arena_alloc(arena_t* a_) : a(a_) {}
+    template <typename U>
+    arena_alloc(const arena_alloc<U>& o) : a(o.a) {}
+    T* allocate(size_t n) { return static_cast<T*>(a->take(n * sizeof(T))); }
+    void deallocate(T*, size_t) {}
+    template <typename U>
+    bool operator==(const arena_alloc<U>& o) const { return a == o.a; }
+    template <typename U>
+    bool operator!=(const arena_alloc<U>& o) const { return a != o.a; }
+};
+}
+
+extern "C" int mcb200_reference_edge_order(uint32_t n_cand_faces, const uint32_t* slot_off, const uint32_t* slot_edge,
+    uint32_t helper_threads, uint32_t* order, uint32_t* n_order)
+{
+    if (!n_order || (n_cand_faces && (!slot_edge || !order))) return MCB200_ERR_INVALID;
+    *n_order = 0;
+    if (n_cand_faces == 0) return 0;
+    arena_t arena;
+    typedef std::unordered_map<uint32_t, char, std::hash<uint32_t>, std::equal_to<uint32_t>, arena_alloc<std::pair<const uint32_t, char>>> edge_set_t;
+    const arena_alloc<std::pair<const uint32_t, char>> alloc(&arena);
+    const uint32_t available = helper_threads + 1u;
+    auto schedule = [&](uint32_t length, uint32_t& nthreads, uint32_t& block_size) { // get_scheduling_parameters, tpool.h:354-392
+        const uint32_t max_threads = (length + 1023u) / 1024u;
+        nthreads = std::min(available, max_threads);
+        block_size = length / nthreads;
+    };
+    auto block = [&](edge_set_t& local, uint32_t a, uint32_t b) {
+        for (uint32_t i = a; i < b; ++i) {
+            const uint32_t h0 = slot_off ? slot_off[i] : 3u * i, h1 = slot_off ? slot_off[i + 1] : 3u * i + 3u;
+            for (uint32_t h = h0; h < h1; ++h) local[slot_edge[h]];
+        }
+    };
+    uint32_t nthreads = 1, block_size = 0;
+    schedule(n_cand_faces, nthreads, block_size);
+    std::vector<edge_set_t> futures;
+    futures.reserve(nthreads - 1);
+    uint32_t block_start = 0;
+    for (uint32_t i = 0; i + 1 < nthreads; ++i) {
+        futures.emplace_back(alloc); // as default-constructed: same bucket growth
+        block(futures.back(), block_start, block_start + block_size);
+        block_start += block_size;
+    }
+    edge_set_t all(alloc);
+    block(all, block_start, n_cand_faces);
+    for (const edge_set_t& f : futures)
+        for (edge_set_t::const_iterator i = f.cbegin(); i != f.cend(); ++i)
+            if (all.find(i->first) == all.cend()) all[i->first] = i->second;
+    const uint32_t n = (uint32_t)all.size();
+    schedule(n, nthreads, block_size);
+    const uint32_t master_first = (nthreads - 1) * block_size;
+    // the map's iteration order, rotated: the master's block (the last one) registers first
+    uint32_t k = 0;
+    for (edge_set_t::const_iterator i = all.cbegin(); i != all.cend(); ++i, ++k)
+        order[k >= master_first ? k - master_first : k + (n - master_first)] = i->first;
+    *n_order = n;
+    return 0;
+}
+
 extern "C" int mcb200_reference_edge_rank(uint32_t n_cand_faces, const uint32_t* cand_faces, const uint32_t* face_off,
     const uint32_t* face_edge, uint32_t ne, uint32_t helper_threads, uint32_t* rank)
 {
@@ -182,44 +288,20 @@ extern "C" int mcb200_reference_edge_rank(uint32_t n_cand_faces, const uint32_t*
     if (n_cand_faces == 0) return 0;
     for (uint32_t i = 1; i < n_cand_faces; ++i)
         if (cand_faces[i] <= cand_faces[i - 1]) return MCB200_ERR_INVALID; // keys of a std::map
-    typedef std::unordered_map<uint32_t, char> edge_set_t;
-    const uint32_t available = helper_threads + 1u;
-    auto schedule = [&](uint32_t length, uint32_t& nthreads, uint32_t& block_size) { // get_scheduling_parameters, tpool.h:354-392
-        const uint32_t max_threads = (length + 1023u) / 1024u;
-        nthreads = std::min(available, max_threads);
-        block_size = length / nthreads;
-    };
-    auto block = [&](uint32_t a, uint32_t b) {
-        edge_set_t local;
-        for (uint32_t i = a; i < b; ++i) {
-            const uint32_t f = cand_faces[i];
-            const uint32_t h0 = face_off ? face_off[f] : 3u * f, h1 = face_off ? face_off[f + 1] : 3u * f + 3u;
-            for (uint32_t h = h0; h < h1; ++h) local[face_edge[h]];
+    std::vector<uint32_t> off((size_t)n_cand_faces + 1, 0u), slots;
+    for (uint32_t i = 0; i < n_cand_faces; ++i) {
+        const uint32_t f = cand_faces[i];
+        const uint32_t h0 = face_off ? face_off[f] : 3u * f, h1 = face_off ? face_off[f + 1] : 3u * f + 3u;
+        for (uint32_t h = h0; h < h1; ++h) {
+            if (face_edge[h] >= ne) return MCB200_ERR_INVALID;
+            slots.push_back(face_edge[h]);
         }
-        return local;
-    };
-    uint32_t nthreads = 1, block_size = 0;
-    schedule(n_cand_faces, nthreads, block_size);
-    std::vector<edge_set_t> futures(nthreads - 1);
-    uint32_t block_start = 0;
-    for (uint32_t i = 0; i + 1 < nthreads; ++i) {
-        futures[i] = block(block_start, block_start + block_size);
-        block_start += block_size;
+        off[i + 1] = (uint32_t)slots.size();
     }
-    edge_set_t all = block(block_start, n_cand_faces);
-    for (const edge_set_t& f : futures)
-        for (edge_set_t::const_iterator i = f.cbegin(); i != f.cend(); ++i)
-            if (all.find(i->first) == all.cend()) all[i->first] = i->second;
-    std::vector<uint32_t> order;
-    order.reserve(all.size());
-    for (edge_set_t::const_iterator i = all.cbegin(); i != all.cend(); ++i) {
-        if (i->first >= ne) return MCB200_ERR_INVALID;
-        order.push_back(i->first);
-    }
-    schedule((uint32_t)order.size(), nthreads, block_size);
-    const size_t master_first = (size_t)(nthreads - 1) * block_size;
-    uint32_t next = 0;
-    for (size_t k = master_first; k < order.size(); ++k) rank[order[k]] = next++;
-    for (size_t k = 0; k < master_first; ++k) rank[order[k]] = next++;
+    std::vector<uint32_t> order(slots.size() ? slots.size() : 1u);
+    uint32_t n = 0;
+    const int rc = mcb200_reference_edge_order(n_cand_faces, off.data(), slots.data(), helper_threads, order.data(), &n);
+    if (rc) return rc;
+    for (uint32_t k = 0; k < n; ++k) rank[order[k]] = k;
     return 0;
 }

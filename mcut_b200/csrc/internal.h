@@ -15,6 +15,7 @@ int result_reset_counters(mcb200_ctx* ctx, mcb200_result* res);
 int traverse_pairs(mcb200_ctx* ctx, const mcb200_mesh* src, const mcb200_mesh* cut, mcb200_result* res);
 int sort_pairs_reserve(mcb200_ctx* ctx, const mcb200_mesh* src, const mcb200_mesh* cut, mcb200_result* res);
 int sort_pairs(mcb200_ctx* ctx, const mcb200_mesh* src, const mcb200_mesh* cut, mcb200_result* res);
+int sort_pairs_fallback(mcb200_ctx* ctx, mcb200_result* res);
 // narrowphase.cu
 int narrowphase_reserve(mcb200_ctx* ctx, const mcb200_soup* soup, mcb200_result* res, uint32_t flags);
 int narrowphase_run(mcb200_ctx* ctx, const mcb200_soup* soup, const mcb200_mesh* src, const mcb200_mesh* cut,

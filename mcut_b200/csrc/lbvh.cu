@@ -476,6 +476,17 @@ __global__ void __launch_bounds__(LB_THREADS, 3) k_leaves(const uint32_t* __rest
             if (k < LB_WIN) s_code[k] = creg[r];
         }
     }
+    // chunks q = 4 w + i (i < 4) belong to warp w (their face ids are requested now: one hop less when the boxes are gathered); warp 0 also fetches the 32 leaves after the block (i == 4, q = 32)
+    constexpr int NI = LB_ITEMS + 1;
+    uint32_t face[NI];
+    bool have[NI];
+#pragma unroll
+    for (int i = 0; i < NI; ++i) {
+        const unsigned q = (i < LB_ITEMS) ? w * LB_ITEMS + i : 32u;
+        const long long j = base + 32ll * q + lane;
+        have[i] = (i < LB_ITEMS || w == 0) && j < (long long)nf;
+        face[i] = have[i] ? __ldg(sorted_faces + j) : 0u;
+    }
     __syncthreads();
     // ---- delta of every boundary of the window, then its range minima ----
     for (int k = threadIdx.x; k < LB_WIN; k += LB_THREADS) {
@@ -524,17 +535,6 @@ __global__ void __launch_bounds__(LB_THREADS, 3) k_leaves(const uint32_t* __rest
         if (lane == 0 && word < LB_BOXES / 32 + 2) s_flag[word] = m;
     }
     __syncthreads();
-    // chunks q = 4 w + i (i < 4) belong to warp w; warp 0 also fetches the 32 leaves after the block (i == 4, q = 32)
-    constexpr int NI = LB_ITEMS + 1;
-    uint32_t face[NI];
-    bool have[NI];
-#pragma unroll
-    for (int i = 0; i < NI; ++i) {
-        const unsigned q = (i < LB_ITEMS) ? w * LB_ITEMS + i : 32u;
-        const long long j = base + 32ll * q + lane;
-        have[i] = (i < LB_ITEMS || w == 0) && j < (long long)nf;
-        face[i] = have[i] ? __ldg(sorted_faces + j) : 0u;
-    }
     double2 bx[NI][3];
 #pragma unroll
     for (int i = 0; i < NI; ++i) {

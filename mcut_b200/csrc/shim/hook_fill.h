@@ -4,10 +4,13 @@
 // container logic and the registry order are checked on every round, GPU or not.
 #pragma once
 
+#include <algorithm>
+#include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <map>
+#include <memory>
 #include <stdexcept>
 #include <unordered_map>
 #include <utility>
@@ -17,6 +20,20 @@
 #include "mcut/internal/hmesh.h"
 #include "mcut/internal/math.h"
 #include "mcut/internal/utils.h"
+
+// MCB200_SHIM_TIMING=1: wall time of a scope on stderr (the adapter's entries and the steps of the hook's host half)
+struct mcb200_scope_timer {
+    const char* what;
+    std::chrono::steady_clock::time_point t0;
+    explicit mcb200_scope_timer(const char* w) : what(w), t0(std::chrono::steady_clock::now()) {}
+    ~mcb200_scope_timer()
+    {
+        static const bool on = std::getenv("MCB200_SHIM_TIMING") != nullptr;
+        if (on)
+            std::fprintf(stderr, "[mcut_b200 shim] %s: %.3f ms\n", what,
+                std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count());
+    }
+};
 
 // MCB200_HOOK_DEBUG=2: what the hook hands over, bit patterns included (to diff the device hook against the CPU stand-in)
 static inline void mcb200_hook_dump(const char* who, size_t np, const uint32_t* faces, const double* normal, const double* d,
@@ -37,15 +54,21 @@ static inline void mcb200_hook_dump(const char* who, size_t np, const uint32_t* 
     }
 }
 
-// kernel.cpp:2184-2356: plane normal, d, largest component and vertex list of every candidate face
+// kernel.cpp:2184-2356: plane normal, d, largest component and vertex list of the candidate faces.  The reference fills these
+// maps for every candidate face, but the rest of dispatch() only ever looks up faces named by a registry entry — the tested
+// face and the faces incident to the tested edge (ps_get_ivtx_registry_entry_faces; kernel.cpp:3536-3567, :4187-4191,
+// :6637-6664, :6811-6814) — and never iterates them; `needed` restricts the rows to those faces.
 static inline void mcb200_hook_fill_planes(const hmesh_t& ps, size_t n, const uint32_t* faces, const double* normal, const double* d,
-    const int32_t* max_comp, std::unordered_map<fd_t, vec3>& ps_tested_face_to_plane_normal,
+    const int32_t* max_comp, const unsigned char* needed /* by face id, or NULL: every row */,
+    std::unordered_map<fd_t, vec3>& ps_tested_face_to_plane_normal,
     std::unordered_map<fd_t, scalar_t>& ps_tested_face_to_plane_normal_d_param,
     std::unordered_map<fd_t, int>& ps_tested_face_to_plane_normal_max_comp,
     std::unordered_map<fd_t, std::vector<vec3>>& ps_tested_face_to_vertices)
 {
+    mcb200_scope_timer timer("  hook: plane maps");
     std::vector<vd_t> tmp;
     for (size_t k = 0; k < n; ++k) {
+        if (needed && !needed[faces[k]]) continue;
         const fd_t f(faces[k]);
         ps_tested_face_to_plane_normal[f] = vec3(normal[3 * k], normal[3 * k + 1], normal[3 * k + 2]);
         ps_tested_face_to_plane_normal_d_param[f] = d[k];
@@ -57,41 +80,42 @@ static inline void mcb200_hook_fill_planes(const hmesh_t& ps, size_t n, const ui
     }
 }
 
-// The reference's registry order (mcb200_reference_edge_rank, host_logic.cpp): the candidate faces and the edge of every
-// halfedge slot of `ps` as flat arrays, then the library's replay of the reference's unordered_map.
-static inline std::vector<uint32_t> mcb200_hook_reference_edge_rank(const hmesh_t& ps, const uint32_t* cand_faces, size_t n_cand,
-    uint32_t pool_threads)
+// The reference's registry order (mcb200_reference_edge_order, host_logic.cpp): the edges around the candidate faces as flat
+// arrays, the library's replay of the reference's unordered_map, and the records sorted into that order.
+static inline void mcb200_hook_reference_order(const hmesh_t& ps, const uint32_t* cand_faces, size_t n_cand, uint32_t pool_threads,
+    std::vector<mcb200_record>& rec)
 {
     // cand_faces: every face with a candidate partner, ascending = the keys of the reference's
     // ps_face_to_potentially_intersecting_others (the hooked adapter does not fill that map on the host: the pairs stay
     // on the device; the plane rows name the same faces)
-    const uint32_t nf = (uint32_t)ps.number_of_faces(), ne = (uint32_t)ps.number_of_edges();
-    std::vector<uint32_t> faces(cand_faces, cand_faces + n_cand), off((size_t)nf + 1, 0u), fe;
-    std::vector<uint32_t> size_of(nf, 0u); // only the candidate faces' slots are read: the other faces get empty ranges
-    for (uint32_t f : faces) size_of[f] = (uint32_t)ps.get_halfedges_around_face(fd_t(f)).size();
-    for (uint32_t f = 0; f < nf; ++f) off[f + 1] = off[f] + size_of[f];
-    fe.resize(off[nf] ? off[nf] : 1u);
-    for (uint32_t f : faces) {
-        uint32_t h = off[f];
-        for (const hd_t& he : ps.get_halfedges_around_face(fd_t(f))) fe[h++] = (uint32_t)ps.edge(he);
+    mcb200_scope_timer timer("  hook: registry order replay");
+    const uint32_t ne = (uint32_t)ps.number_of_edges();
+    std::vector<uint32_t> off(n_cand + 1, 0u), slots;
+    slots.reserve(3 * n_cand);
+    for (size_t i = 0; i < n_cand; ++i) {
+        for (const hd_t& he : ps.get_halfedges_around_face(fd_t(cand_faces[i]))) slots.push_back((uint32_t)ps.edge(he));
+        off[i + 1] = (uint32_t)slots.size();
     }
-    std::vector<uint32_t> rank(ne ? ne : 1u);
-    if (mcb200_reference_edge_rank((uint32_t)faces.size(), faces.data(), off.data(), fe.data(), ne, pool_threads, rank.data()))
-        throw std::runtime_error("mcut_b200: mcb200_reference_edge_rank failed");
+    std::vector<uint32_t> order(slots.size() ? slots.size() : 1u);
+    uint32_t n = 0;
+    if (mcb200_reference_edge_order((uint32_t)n_cand, off.data(), slots.data(), pool_threads, order.data(), &n))
+        throw std::runtime_error("mcut_b200: mcb200_reference_edge_order failed");
     if (const char* e = getenv("MCB200_HOOK_DEBUG")) {
         if (e[0] == '2') {
-            fprintf(stderr, "[rank] threads=%u cand:", pool_threads);
-            for (uint32_t f : faces) {
-                fprintf(stderr, " %u(", f);
-                for (uint32_t h = off[f]; h < off[f + 1]; ++h) fprintf(stderr, "%u ", fe[h]);
-                fprintf(stderr, ")");
-            }
-            fprintf(stderr, " rank:");
-            for (uint32_t k = 0; k < ne; ++k) fprintf(stderr, " %d", (int)rank[k]);
+            fprintf(stderr, "[order] threads=%u:", pool_threads);
+            for (uint32_t k = 0; k < n; ++k) fprintf(stderr, " %u", order[k]);
             fprintf(stderr, "\n");
         }
     }
-    return rank;
+    // rank of the edges that matter (uninitialised elsewhere: every record's edge belongs to a candidate face)
+    std::unique_ptr<uint32_t[]> rank(new uint32_t[ne ? ne : 1u]);
+    for (const mcb200_record& r : rec) rank[r.edge] = MCB200_NULL;
+    for (uint32_t k = 0; k < n; ++k)
+        if (order[k] < ne) rank[order[k]] = k;
+    for (const mcb200_record& r : rec)
+        if (rank[r.edge] == MCB200_NULL) throw std::runtime_error("mcut_b200: a registry record names an edge of no candidate face");
+    // the records arrive sorted by (edge, face): a stable sort on the rank leaves each edge's faces ascending
+    std::stable_sort(rec.begin(), rec.end(), [&](const mcb200_record& a, const mcb200_record& b) { return rank[a.edge] < rank[b.edge]; });
 }
 
 // kernel.cpp:2601-2655 (merged form :2673-2868): one m0 vertex per record, in the order given, and everything keyed by it
@@ -100,6 +124,7 @@ static inline void mcb200_hook_fill_registry(const hmesh_t& ps, int sm_vtx_cnt, 
     std::unordered_map<ed_t, std::vector<vd_t>>& ps_intersecting_edges, std::map<pair<fd_t>, std::vector<vd_t>>& cutpath_edge_creation_info,
     std::unordered_map<fd_t, std::vector<vd_t>>& ps_iface_to_ivtx_list, bool& partial_cut_detected)
 {
+    mcb200_scope_timer timer("  hook: registry containers");
     m0_ivtx_to_intersection_registry_entry.reserve(n);
     for (size_t i = 0; i < n; ++i) {
         const mcb200_record& r = rec[i];
@@ -133,4 +158,41 @@ static inline void mcb200_hook_fill_registry(const hmesh_t& ps, int sm_vtx_cnt, 
             partial_cut_detected = (is_cs_edge && is_border);
         }
     }
+}
+
+// Everything after the narrowphase itself: plane rows -> maps (registry faces only), records -> the reference's own order ->
+// containers.  `rec` arrives sorted by (edge, face) and is reordered in place.
+static inline void mcb200_hook_finish(const hmesh_t& ps, int sm_vtx_cnt, int sm_face_count, const char* who, size_t n_cand,
+    const uint32_t* cand_faces, const double* normal, const double* d, const int32_t* max_comp, std::vector<mcb200_record>& rec,
+    uint32_t pool_threads, hmesh_t& m0, std::unordered_map<fd_t, vec3>& ps_tested_face_to_plane_normal,
+    std::unordered_map<fd_t, scalar_t>& ps_tested_face_to_plane_normal_d_param,
+    std::unordered_map<fd_t, int>& ps_tested_face_to_plane_normal_max_comp,
+    std::unordered_map<fd_t, std::vector<vec3>>& ps_tested_face_to_vertices,
+    std::vector<std::pair<ed_t, fd_t>>& m0_ivtx_to_intersection_registry_entry, std::vector<vd_t>& cm_border_reentrant_ivtx_list,
+    std::unordered_map<ed_t, std::vector<vd_t>>& ps_intersecting_edges, std::map<pair<fd_t>, std::vector<vd_t>>& cutpath_edge_creation_info,
+    std::unordered_map<fd_t, std::vector<vd_t>>& ps_iface_to_ivtx_list, bool& partial_cut_detected)
+{
+    mcb200_hook_dump(who, n_cand, cand_faces, normal, d, max_comp, nullptr, 0);
+    {
+        std::vector<unsigned char> needed;
+        if (!getenv("MCB200_HOOK_ALL_PLANES")) {
+            needed.assign((size_t)ps.number_of_faces(), 0);
+            for (const mcb200_record& r : rec) {
+                needed[r.face] = 1;
+                const fd_t f0 = ps.face(ps.halfedge(ed_t(r.edge), 0)), f1 = ps.face(ps.halfedge(ed_t(r.edge), 1));
+                if (f0 != hmesh_t::null_face()) needed[(uint32_t)f0] = 1;
+                if (f1 != hmesh_t::null_face()) needed[(uint32_t)f1] = 1;
+            }
+        }
+        mcb200_hook_fill_planes(ps, n_cand, cand_faces, normal, d, max_comp, needed.empty() ? nullptr : needed.data(),
+            ps_tested_face_to_plane_normal, ps_tested_face_to_plane_normal_d_param, ps_tested_face_to_plane_normal_max_comp,
+            ps_tested_face_to_vertices);
+    }
+    if (!rec.empty() && !getenv("MCB200_CANONICAL_REGISTRY")) {
+        // registry in the reference's own order (mcb200_reference_edge_order), an edge's faces ascending
+        mcb200_hook_reference_order(ps, cand_faces, n_cand, pool_threads, rec);
+    }
+    mcb200_hook_dump(who, 0, nullptr, nullptr, nullptr, nullptr, rec.data(), rec.size());
+    mcb200_hook_fill_registry(ps, sm_vtx_cnt, sm_face_count, rec.data(), rec.size(), m0, m0_ivtx_to_intersection_registry_entry,
+        cm_border_reentrant_ivtx_list, ps_intersecting_edges, cutpath_edge_creation_info, ps_iface_to_ivtx_list, partial_cut_detected);
 }

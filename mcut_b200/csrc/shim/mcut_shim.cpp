@@ -103,19 +103,7 @@ mcb200_ctx* thread_ctx()
     return ctx;
 }
 
-// MCB200_SHIM_TIMING=1: wall time of every adapter entry on stderr (what a live mcDispatch pays, host glue included)
-struct scope_timer {
-    const char* what;
-    std::chrono::steady_clock::time_point t0;
-    explicit scope_timer(const char* w) : what(w), t0(std::chrono::steady_clock::now()) {}
-    ~scope_timer()
-    {
-        static const bool on = std::getenv("MCB200_SHIM_TIMING") != nullptr;
-        if (on)
-            std::fprintf(stderr, "[mcut_b200 shim] %s: %.3f ms\n", what,
-                std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count());
-    }
-};
+typedef mcb200_scope_timer scope_timer; // MCB200_SHIM_TIMING=1 (hook_fill.h)
 
 void check(mcb200_ctx* ctx, int rc, const char* what)
 {
@@ -218,8 +206,10 @@ void build_oibvh(thread_pool& /*pool*/, const hmesh_t& mesh, std::vector<bbox_t>
     auto cap = t_captures.find(&mesh);
     if (cap != t_captures.end() && capture_matches(cap->second, mesh)) {
         // fast path: the device reads the user's own arrays and applies the frame itself — no walk over the half-edge mesh
+        // (the conversion itself has range-checked every index, preproc.cpp:271 / :417, and returned true)
         const capture_t& c = cap->second;
-        check(ctx, mcb200_mesh_create(ctx, c.is_float, c.xyz, c.nv, c.faces, c.sizes, c.nf, &t.mesh), "mesh_create");
+        scope_timer t2("  build_oibvh: upload of the user's arrays");
+        check(ctx, mcb200_mesh_create_trusted(ctx, c.is_float, c.xyz, c.nv, c.faces, c.sizes, c.nf, &t.mesh), "mesh_create");
         check(ctx, mcb200_mesh_set_frame(ctx, t.mesh, c.com, c.shift, c.has_pert ? c.pert : nullptr), "set_frame");
         t.from_arrays = true;
         t.cap = c;
@@ -425,6 +415,7 @@ int mcb200_hook_narrowphase(const hmesh_t& ps, int sm_vtx_cnt, int sm_face_count
     if (cut_arrays)
         check(ctx, mcb200_mesh_set_frame(ctx, t_last.cut, cut_now.com, cut_now.shift, cut_now.has_pert ? cut_now.pert : nullptr), "set_frame(cut)");
     if (fast) {
+        scope_timer t2("  hook: soup numbering (device)");
         if (!t_last.soup) check(ctx, mcb200_soup_number(ctx, t_last.src, t_last.cut, t_last.res, &t_last.soup), "soup_number");
         soup = t_last.soup; // the numbering does not depend on coordinates: one per broadphase, reused by every retry
         own_soup = false;
@@ -475,6 +466,7 @@ int mcb200_hook_narrowphase(const hmesh_t& ps, int sm_vtx_cnt, int sm_face_count
     }
 
     // ---- device narrowphase on the resident trees / pairs ----
+    scope_timer* t_dev = new scope_timer("  hook: device narrowphase + counters");
     int rc = mcb200_narrowphase(ctx, soup, t_last.src, t_last.cut, t_last.res, 0);
     mcb200_counts counts;
     int rc2 = rc ? rc : mcb200_result_counts(ctx, t_last.res, &counts);
@@ -485,6 +477,7 @@ int mcb200_hook_narrowphase(const hmesh_t& ps, int sm_vtx_cnt, int sm_face_count
         if (!rc) rc = mcb200_narrowphase(ctx, soup, t_last.src, t_last.cut, t_last.res, 0);
         rc2 = rc ? rc : mcb200_result_counts(ctx, t_last.res, &counts);
     }
+    delete t_dev;
     if (rc2) {
         if (own_soup) mcb200_soup_free(ctx, soup);
         check(ctx, rc2, "narrowphase");
@@ -503,30 +496,22 @@ int mcb200_hook_narrowphase(const hmesh_t& ps, int sm_vtx_cnt, int sm_face_count
         return MCB200_HOOK_GENERAL_POSITION_VIOLATION;
     }
 
-    // ---- plane data of the candidate faces (kernel.cpp:2184-2356), faces ascending ----
+    // ---- plane rows of the candidate faces (kernel.cpp:2184-2356, faces ascending) and the registry records
+    // (kernel.cpp:2601-2655, merged form :2673-2868; canonical (edge, face) order), then the host half (hook_fill.h) ----
     const size_t n_cand = (size_t)counts.n_cand_faces;
     std::vector<uint32_t> cand_faces(n_cand);
-    {
-        std::vector<double> normal(3 * n_cand), d(n_cand);
-        std::vector<int32_t> mc(n_cand);
-        check(ctx, mcb200_result_read_planes(ctx, t_last.res, cand_faces.data(), normal.data(), d.data(), mc.data(), n_cand), "read_planes");
-        mcb200_hook_dump("device", n_cand, cand_faces.data(), normal.data(), d.data(), mc.data(), nullptr, 0);
-        mcb200_hook_fill_planes(ps, n_cand, cand_faces.data(), normal.data(), d.data(), mc.data(), ps_tested_face_to_plane_normal,
-            ps_tested_face_to_plane_normal_d_param, ps_tested_face_to_plane_normal_max_comp, ps_tested_face_to_vertices);
-    }
-
-    // ---- the registry (kernel.cpp:2601-2655, merged form :2673-2868), records in canonical (edge, face) order ----
+    std::vector<double> normal(3 * n_cand), d(n_cand);
+    std::vector<int32_t> mc(n_cand);
     std::vector<mcb200_record> rec((size_t)counts.n_records);
-    check(ctx, mcb200_result_read_records(ctx, t_last.res, rec.data(), rec.size()), "read_records");
-    if (own_soup) mcb200_soup_free(ctx, soup);
-    if (!rec.empty() && !getenv("MCB200_CANONICAL_REGISTRY")) {
-        // registry in the reference's own order: by the rank of the edge (mcb200_reference_edge_rank), faces ascending — the
-        // records arrive sorted by (edge, face), so a stable sort on the rank is all it takes
-        const std::vector<uint32_t> rank = mcb200_hook_reference_edge_rank(ps, cand_faces.data(), n_cand, t_pool_threads);
-        std::stable_sort(rec.begin(), rec.end(), [&](const mcb200_record& a, const mcb200_record& b) { return rank[a.edge] < rank[b.edge]; });
+    {
+        mcb200_scope_timer t2("  hook: read planes + records");
+        check(ctx, mcb200_result_read_planes(ctx, t_last.res, cand_faces.data(), normal.data(), d.data(), mc.data(), n_cand), "read_planes");
+        check(ctx, mcb200_result_read_records(ctx, t_last.res, rec.data(), rec.size()), "read_records");
     }
-    mcb200_hook_dump("device", 0, nullptr, nullptr, nullptr, nullptr, rec.data(), rec.size());
-    mcb200_hook_fill_registry(ps, sm_vtx_cnt, sm_face_count, rec.data(), rec.size(), m0, m0_ivtx_to_intersection_registry_entry,
+    if (own_soup) mcb200_soup_free(ctx, soup);
+    mcb200_hook_finish(ps, sm_vtx_cnt, sm_face_count, "device", n_cand, cand_faces.data(), normal.data(), d.data(), mc.data(), rec,
+        t_pool_threads, m0, ps_tested_face_to_plane_normal, ps_tested_face_to_plane_normal_d_param,
+        ps_tested_face_to_plane_normal_max_comp, ps_tested_face_to_vertices, m0_ivtx_to_intersection_registry_entry,
         cm_border_reentrant_ivtx_list, ps_intersecting_edges, cutpath_edge_creation_info, ps_iface_to_ivtx_list, partial_cut_detected);
     return MCB200_HOOK_OK;
 }

@@ -324,7 +324,10 @@ __global__ void __launch_bounds__(TBLOCK, 3) k_traverse(traverse_args_t a)
 //   k_pair_scatter                    every pair into the range of its source face (cursor by atomicAdd)
 //   k_pair_segsort                    one thread per source face orders its handful of pairs by cut face
 // A face with more than SEG_LIMIT pairs (one huge face over a fine mesh) would make its thread crawl: the radix sort takes
-// such inputs instead; the choice is made on the device (pair_seg_max), both paths are enqueued, one returns at once.
+// such inputs instead.  Which case it is only the device knows (pair_seg_max), and enqueueing seven radix launches that
+// return at once in every ordinary dispatch costs more than the counting order itself; so the counting kernels simply stand
+// aside above the limit, and the host runs the radix sort when it next reads the counters and finds pair_seg_max above it
+// (sort_pairs_fallback, called from fetch_counters) — before anybody can see the ordered list.
 constexpr unsigned SEG_LIMIT = 256;
 constexpr int PS_THREADS = 256;
 constexpr int PS_TILE = PS_THREADS * 8;
@@ -367,10 +370,14 @@ __global__ void __launch_bounds__(PS_THREADS) k_pair_offsets(unsigned* __restric
     unsigned before = 0;
     for (unsigned i = threadIdx.x; i < blockIdx.x; i += PS_THREADS) before += __ldg(tile_sum + i);
     before = block_sum(before, s_warp);
+    // (the arrays are padded to a multiple of 8 entries: whole 16-byte accesses everywhere; entries past nsf hold zeros)
     const size_t base = (size_t)blockIdx.x * PS_TILE + threadIdx.x * 8u;
-    unsigned c[8];
-#pragma unroll
-    for (int k = 0; k < 8; ++k) c[k] = (base + k < nsf) ? cnt[base + k] : 0u;
+    unsigned c[8] = { 0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u };
+    const bool in_range = base < nsf;
+    if (in_range) {
+        const uint4 a = *reinterpret_cast<const uint4*>(cnt + base), b = *reinterpret_cast<const uint4*>(cnt + base + 4);
+        c[0] = a.x; c[1] = a.y; c[2] = a.z; c[3] = a.w; c[4] = b.x; c[5] = b.y; c[6] = b.z; c[7] = b.w;
+    }
     unsigned mine = 0, mx = 0;
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
@@ -392,14 +399,20 @@ __global__ void __launch_bounds__(PS_THREADS) k_pair_offsets(unsigned* __restric
     for (int i = 0; i < PS_THREADS / 32; ++i)
         if ((unsigned)i < w) wbase += s_warp[i];
     unsigned run = before + wbase + inc - mine;
+    if (in_range) {
+        unsigned o[8];
 #pragma unroll
-    for (int k = 0; k < 8; ++k) {
-        if (base + k < nsf) {
-            off[base + k] = run;
-            cnt[base + k] = 0u; // becomes the scatter's cursor
+        for (int k = 0; k < 8; ++k) {
+            o[k] = run;
+            run += c[k];
         }
-        run += c[k];
-        if (base + k + 1 == nsf) off[nsf] = run;
+        *reinterpret_cast<uint4*>(off + base) = make_uint4(o[0], o[1], o[2], o[3]);
+        *reinterpret_cast<uint4*>(off + base + 4) = make_uint4(o[4], o[5], o[6], o[7]);
+        if (mine) { // becomes the scatter's cursor
+            *reinterpret_cast<uint4*>(cnt + base) = make_uint4(0u, 0u, 0u, 0u);
+            *reinterpret_cast<uint4*>(cnt + base + 4) = make_uint4(0u, 0u, 0u, 0u);
+        }
+        if (base + 8 >= nsf) off[nsf] = run; // (entries past nsf are zero, so `run` is the total here)
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
@@ -428,20 +441,29 @@ __global__ void __launch_bounds__(256) k_pair_segsort(unsigned long long* __rest
 {
     pdl_prologue();
     const bool counting = counters->pair_seg_max <= SEG_LIMIT && !counters->pair_overflow;
-    for (uint32_t s = blockIdx.x * 256u + threadIdx.x; s < nsf; s += gridDim.x * 256u) {
-        const unsigned c = cursor[s];
-        if (c) cursor[s] = 0u; // all zero again for the next run
-        if (!counting || c < 2u) continue;
-        unsigned long long* seg = out + off[s];
-        // insertion sort of a handful of entries (same source face: the cut face decides)
-        for (unsigned i = 1; i < c; ++i) {
-            const unsigned long long x = seg[i];
-            unsigned j = i;
-            while (j > 0 && seg[j - 1] > x) {
-                seg[j] = seg[j - 1];
-                --j;
+    // four faces per thread and step (16-byte loads of the cursors; most faces have no pair at all)
+    const uint32_t n4 = (nsf + 3u) / 4u;
+    for (uint32_t q = blockIdx.x * 256u + threadIdx.x; q < n4; q += gridDim.x * 256u) {
+        const uint4 c4 = *reinterpret_cast<const uint4*>(cursor + 4u * q);
+        if ((c4.x | c4.y | c4.z | c4.w) == 0u) continue;
+        *reinterpret_cast<uint4*>(cursor + 4u * q) = make_uint4(0u, 0u, 0u, 0u); // all zero again for the next run
+        if (!counting) continue;
+        const unsigned cs[4] = { c4.x, c4.y, c4.z, c4.w };
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const unsigned c = cs[k];
+            if (c < 2u) continue;
+            unsigned long long* seg = out + off[4u * q + k];
+            // insertion sort of a handful of entries (same source face: the cut face decides)
+            for (unsigned i = 1; i < c; ++i) {
+                const unsigned long long x = seg[i];
+                unsigned j = i;
+                while (j > 0 && seg[j - 1] > x) {
+                    seg[j] = seg[j - 1];
+                    --j;
+                }
+                seg[j] = x;
             }
-            seg[j] = x;
         }
     }
 }
@@ -579,16 +601,31 @@ int sort_pairs(mcb200_ctx* ctx, const mcb200_mesh* src, const mcb200_mesh* cut, 
     MCB_LAUNCH(ctx, k_pair_offsets, tiles, PS_THREADS, 0, cnt, nsf, res->pair_tile.as<unsigned>(), off, c);
     const unsigned grid = (unsigned)ctx->num_sms * 8u;
     MCB_LAUNCH(ctx, k_pair_scatter, grid, 256, 0, res->pairs.as<unsigned long long>(), (unsigned long long)res->cap_pairs, off, cnt, dst, c);
-    const unsigned sgrid = div_up(nsf, 256) < grid ? div_up(nsf, 256) : grid;
+    const unsigned sgrid = div_up(div_up(nsf, 4), 256) < grid ? div_up(div_up(nsf, 4), 256) : grid;
     MCB_LAUNCH(ctx, k_pair_segsort, sgrid, 256, 0, dst, off, cnt, nsf, (unsigned long long)res->cap_pairs, c);
+    res->pairs_order_input = res->pairs.p;
+    res->pairs_order_unchecked = true; // fetch_counters looks at pair_seg_max once
+    res->pairs_sorted = dst;
+    return 0;
+}
+
+// The rare case: some source face has more pairs than the counting order handles per thread.  Radix sort of the same
+// input into the same buffer; called by fetch_counters right after it has read the counters (the stream is idle).
+int sort_pairs_fallback(mcb200_ctx* ctx, mcb200_result* res)
+{
+    res->pairs_order_unchecked = false;
+    if (res->h.pair_seg_max <= SEG_LIMIT || res->h.pair_overflow) return 0;
+    const uint32_t nsf = res->nsf, ncf = res->nf_ps - res->nsf;
+    const rsort::pass_desc pd = pair_passes(nsf, ncf);
+    ctx->use_main();
     unsigned long long* out = nullptr;
-    MCB_TRY((rsort::sort<unsigned long long, uint32_t, false>(ctx, res->pairs.as<unsigned long long>(),
-        res->pairs_a.as<unsigned long long>(), res->pairs_b.as<unsigned long long>(), nullptr, nullptr, nullptr, &c->n_pairs, res->cap_pairs,
-        pd, &out, nullptr, 0, &c->pair_seg_max, SEG_LIMIT)));
-    if (out != dst) {
+    MCB_TRY((rsort::sort<unsigned long long, uint32_t, false>(ctx, static_cast<const unsigned long long*>(res->pairs_order_input),
+        res->pairs_a.as<unsigned long long>(), res->pairs_b.as<unsigned long long>(), nullptr, nullptr, nullptr,
+        &res->counters.as<result_counters_t>()->n_pairs, res->cap_pairs, pd, &out, nullptr)));
+    if (out != res->pairs_sorted) {
         ctx->set_error("internal: the two pair orders do not end in the same buffer", __FILE__, __LINE__);
         return MCB200_ERR_INTERNAL;
     }
-    res->pairs_sorted = dst;
+    MCB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return 0;
 }

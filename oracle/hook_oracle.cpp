@@ -109,21 +109,15 @@ int mcb200_hook_narrowphase(const hmesh_t& ps, int sm_vtx_cnt, int sm_face_count
     } else if (out.status == MCO_GENERAL_POSITION_VIOLATION) {
         rc = MCB200_HOOK_GENERAL_POSITION_VIOLATION;
     } else {
-        mcb200_hook_fill_planes(ps, out.n_cand_faces, out.cand_faces, out.cand_normal, out.cand_d, out.cand_maxcomp,
-            ps_tested_face_to_plane_normal, ps_tested_face_to_plane_normal_d_param, ps_tested_face_to_plane_normal_max_comp,
-            ps_tested_face_to_vertices);
         std::vector<mcb200_record> rec(out.n_records);
         for (size_t i = 0; i < out.n_records; ++i) {
             rec[i].edge = out.records[i].edge;
             rec[i].face = out.records[i].face;
             for (int k = 0; k < 3; ++k) rec[i].point[k] = out.records[i].point[k];
         }
-        if (!rec.empty() && !getenv("MCB200_CANONICAL_REGISTRY")) {
-            const std::vector<uint32_t> rank = mcb200_hook_reference_edge_rank(ps, out.cand_faces, out.n_cand_faces, t_pool_threads);
-            std::stable_sort(rec.begin(), rec.end(), [&](const mcb200_record& a, const mcb200_record& b) { return rank[a.edge] < rank[b.edge]; });
-        }
-        mcb200_hook_dump("oracle", out.n_cand_faces, out.cand_faces, out.cand_normal, out.cand_d, out.cand_maxcomp, rec.data(), rec.size());
-        mcb200_hook_fill_registry(ps, sm_vtx_cnt, sm_face_count, rec.data(), rec.size(), m0, m0_ivtx_to_intersection_registry_entry,
+        mcb200_hook_finish(ps, sm_vtx_cnt, sm_face_count, "oracle", out.n_cand_faces, out.cand_faces, out.cand_normal, out.cand_d,
+            out.cand_maxcomp, rec, t_pool_threads, m0, ps_tested_face_to_plane_normal, ps_tested_face_to_plane_normal_d_param,
+            ps_tested_face_to_plane_normal_max_comp, ps_tested_face_to_vertices, m0_ivtx_to_intersection_registry_entry,
             cm_border_reentrant_ivtx_list, ps_intersecting_edges, cutpath_edge_creation_info, ps_iface_to_ivtx_list, partial_cut_detected);
     }
     mco_narrow_free(&out);
