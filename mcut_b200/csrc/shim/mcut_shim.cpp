@@ -78,29 +78,59 @@ struct last_intersect_t {
     capture_t src_cap, cut_cap;
 };
 thread_local last_intersect_t t_last;
-thread_local std::deque<const void*> t_recent; // keys of the trees this thread built, oldest first
 
 std::mutex g_mutex;
 std::unordered_map<const void*, device_tree_t> g_trees; // key: address of the caller's bvhAABBs vector
+std::vector<mcb200_ctx*> g_idle_ctx; // device contexts whose API thread has ended, warm buffers and all
 
 // One device context per API thread of the reference (every MCUT context owns its API thread, frontend.h:548-584), so
 // concurrently dispatching contexts never share a stream.  Device: MCB200_DEVICE, else threads are dealt round-robin.
+// When the API thread ends (mcReleaseContext) its device objects are released and the device context is parked for the next
+// API thread: a program that creates an MCUT context per dispatch keeps its reserved device buffers instead of mapping a few
+// hundred MB anew each time.
+struct thread_state_t {
+    mcb200_ctx* ctx = nullptr;
+    std::deque<const void*> recent; // keys of the trees this thread built, oldest first
+    ~thread_state_t()
+    {
+        if (!ctx) return;
+        if (t_last.res) mcb200_result_free(t_last.ctx, t_last.res);
+        if (t_last.soup) mcb200_soup_free(t_last.ctx, t_last.soup);
+        t_last = last_intersect_t();
+        std::lock_guard<std::mutex> lk(g_mutex);
+        for (const void* key : recent) {
+            auto it = g_trees.find(key);
+            if (it == g_trees.end() || it->second.ctx != ctx) continue;
+            mcb200_mesh_free(ctx, it->second.mesh);
+            g_trees.erase(it);
+        }
+        g_idle_ctx.push_back(ctx);
+    }
+};
+thread_local thread_state_t t_state;
+
 mcb200_ctx* thread_ctx()
 {
-    static thread_local mcb200_ctx* ctx = nullptr;
-    if (!ctx) {
+    if (!t_state.ctx) {
         static int next_device = 0;
-        int device = 0;
-        const int n = mcb200_device_count();
+        int device = -1;
         if (const char* e = std::getenv("MCB200_DEVICE")) device = std::atoi(e);
-        else if (n > 0) {
+        {
             std::lock_guard<std::mutex> lk(g_mutex);
-            device = next_device++ % n;
+            if (!g_idle_ctx.empty()) { // (with MCB200_DEVICE every context of the process is on that device)
+                t_state.ctx = g_idle_ctx.back();
+                g_idle_ctx.pop_back();
+                return t_state.ctx;
+            }
+            if (device < 0) {
+                const int n = mcb200_device_count();
+                device = n > 0 ? next_device++ % n : 0;
+            }
         }
-        const int rc = mcb200_ctx_create(device, nullptr, &ctx);
+        const int rc = mcb200_ctx_create(device, nullptr, &t_state.ctx);
         if (rc != 0) throw std::runtime_error(std::string("mcut_b200: ") + mcb200_last_error(nullptr));
     }
-    return ctx;
+    return t_state.ctx;
 }
 
 typedef mcb200_scope_timer scope_timer; // MCB200_SHIM_TIMING=1 (hook_fill.h)
@@ -278,10 +308,10 @@ void build_oibvh(thread_pool& /*pool*/, const hmesh_t& mesh, std::vector<bbox_t>
     g_trees[&bvhAABBs] = t;
     // A dispatch uses two trees.  The caller's vectors usually live at the same addresses from one dispatch to the next
     // (then the tree was released above); if they do not, trees of this thread beyond the four most recent are released.
-    t_recent.push_back(&bvhAABBs);
-    while (t_recent.size() > 4) {
-        const void* old = t_recent.front();
-        t_recent.pop_front();
+    t_state.recent.push_back(&bvhAABBs);
+    while (t_state.recent.size() > 4) {
+        const void* old = t_state.recent.front();
+        t_state.recent.pop_front();
         auto it = g_trees.find(old);
         if (it == g_trees.end() || old == static_cast<const void*>(&bvhAABBs)) continue;
         if (it->second.mesh == t_last.src || it->second.mesh == t_last.cut) continue; // still needed by the hook
