@@ -236,6 +236,11 @@ void mcb200_soup_free(mcb200_ctx* ctx, mcb200_soup* soup);
 int mcb200_soup_from_meshes(mcb200_ctx* ctx, const mcb200_mesh* src, const mcb200_mesh* cut, mcb200_soup** soup);
 
 #define MCB200_NARROW_LOG_TESTS 1u /* also keep one log entry per edge/face test (parity checks) */
+/* Triangle meshes dismiss most tests before the ownership / box culls are even looked at (both endpoints on one certified
+ * side of the tested plane: no output either way), and mcb200_counts.n_tests then counts only the tests that went
+ * further.  With this flag the dismissed tests are put through the culls as well, so that n_tests is the number of
+ * edge/face tests the reference runs (kernel.cpp:2483).  (MCB200_NARROW_LOG_TESTS implies it.) */
+#define MCB200_NARROW_COUNT_TESTS 8u
 /* mcb200_intersect_stage_host only: the caller vouches that the source (cut) mesh arrays are bit-for-bit the ones passed to
  * the previous call on this context, so their upload is skipped (C3: one 4M-triangle terrain against 256 planes; the BVH
  * is still rebuilt because the internal coordinates depend on both meshes through `com`).  The C API of the reference

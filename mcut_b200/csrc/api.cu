@@ -20,6 +20,14 @@ int fail(mcb200_ctx* ctx, int code, const char* msg, const char* file, int line)
 #define MCB_FAIL(ctx, code, msg) return fail((ctx), (code), (msg), __FILE__, __LINE__)
 
 } // namespace
+// did a queue between the narrowphase kernels run out of room?  (triangle meshes: the exact queue is split in halves, stage-A
+// failures / certified crossings; what neither settles is parked in the mid queue, one entry per pair of capacity)
+bool narrow_queue_overflow(const mcb200_result* res, const result_counters_t& h)
+{
+    if (!res->tri_queues) return h.n_queue > res->cap_exact;
+    return h.n_queue > res->cap_exact / 2 || h.n_cross > res->cap_exact / 2 || h.n_full > res->cap_pairs;
+}
+
 int fetch_counters(mcb200_ctx* ctx, mcb200_result* res)
 {
     if (res->h_valid) return 0;
@@ -29,6 +37,13 @@ int fetch_counters(mcb200_ctx* ctx, mcb200_result* res)
     MCB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     std::memcpy(&res->h, ctx->h_pinned, sizeof(result_counters_t));
     res->h_valid = true;
+    {
+        static const bool dbg = std::getenv("MCB200_DEBUG_COUNTERS") != nullptr; // how the narrowphase queues filled up
+        if (dbg)
+            std::fprintf(stderr, "[mcut_b200] pairs=%llu tests=%llu exact=%llu records=%llu | mid=%llu open=%llu cross=%llu full=%llu seg_max=%u\n",
+                res->h.n_pairs, res->h.n_tests, res->h.n_exact, res->h.n_records, res->h.n_mid, res->h.n_queue, res->h.n_cross, res->h.n_full,
+                res->h.pair_seg_max);
+    }
     if (res->pairs_order_unchecked) MCB_TRY(sort_pairs_fallback(ctx, res)); // a face with very many pairs: see traverse.cu
     return 0;
 }
@@ -595,7 +610,7 @@ void mcb200_result_free(mcb200_ctx* ctx, mcb200_result* r)
 {
     if (!ctx || !r) return;
     cudaSetDevice(ctx->device);
-    dbuf* all[] = { &r->counters, &r->pairs, &r->pairs_a, &r->pairs_b, &r->pair_cnt, &r->pair_off, &r->pair_tile, &r->cand_flag, &r->plane, &r->plane_mc, &r->exact_queue, &r->records, &r->rec_keys,
+    dbuf* all[] = { &r->counters, &r->pairs, &r->pairs_a, &r->pairs_b, &r->pair_cnt, &r->pair_off, &r->pair_tile, &r->cand_flag, &r->plane, &r->plane_mc, &r->exact_queue, &r->mid_queue, &r->records, &r->rec_keys,
         &r->rec_idx, &r->records_sorted, &r->tests, &r->tests_sorted, &r->test_keys, &r->test_idx };
     for (dbuf* b : all) ctx->release(*b);
     delete r;
@@ -1254,6 +1269,7 @@ int mcb200_staged_soup_read(mcb200_ctx* ctx, uint32_t* face_vtx, uint32_t* face_
 
 // ---------------------------------------------------------------------------------------------------------- reads
 
+
 int mcb200_result_counts(mcb200_ctx* ctx, mcb200_result* res, mcb200_counts* out)
 {
     if (!ctx || !res || !out) return MCB200_ERR_INVALID;
@@ -1276,12 +1292,12 @@ int mcb200_result_counts(mcb200_ctx* ctx, mcb200_result* res, mcb200_counts* out
         out->status = MCB200_STATUS_SUCCESS;
     if (h.soup_error)
         MCB_FAIL(ctx, MCB200_ERR_NON_MANIFOLD, "polygon-soup numbering: an edge is shared by three faces or by two faces wound the same way");
-    if (res->have_narrow && (h.n_records > res->cap_records || h.n_queue > res->cap_exact || (res->logged_tests && h.n_log > res->cap_tests))) {
+    if (res->have_narrow && (h.n_records > res->cap_records || narrow_queue_overflow(res, h) || (res->logged_tests && h.n_log > res->cap_tests))) {
         // The narrowphase buffers are sized from the pair capacity (2 records, 6 queue entries per pair); an input that
         // needs more gets a pair capacity that provides it, and the caller runs the stage again — nothing is dropped silently.
         size_t need = res->cap_pairs;
         if (h.n_records > res->cap_records) need = std::max(need, (size_t)h.n_records / 2 + 1024);
-        if (h.n_queue > res->cap_exact || (res->logged_tests && h.n_log > res->cap_tests)) need = std::max(need, res->cap_pairs * 2);
+        if (narrow_queue_overflow(res, h) || (res->logged_tests && h.n_log > res->cap_tests)) need = std::max(need, res->cap_pairs * 2);
         res->cap_pairs = need;
         res->h_valid = false;
         MCB_FAIL(ctx, MCB200_ERR_CAPACITY, "narrowphase buffer overflow: capacity has been raised, run the stage again");

@@ -188,7 +188,7 @@ int mcb200_intersect_stage_sharded(mcb200_ctx* ctx, mcb200_comm* comm, mcb200_me
     bool overflow = false;
     for (int r = 0; r < N; ++r) {
         overflow = overflow || hc[r].pair_overflow || hc[r].n_pairs > res->cap_pairs || hc[r].n_records > res->cap_records
-            || hc[r].n_queue > res->cap_exact;
+            || narrow_queue_overflow(res, hc[r]);
         npairs[(size_t)r] = std::min<unsigned long long>(hc[r].n_pairs, res->cap_pairs);
         nrec[(size_t)r] = std::min<unsigned long long>(hc[r].n_records, res->cap_records);
         tot.n_pairs += hc[r].n_pairs;
@@ -197,6 +197,8 @@ int mcb200_intersect_stage_sharded(mcb200_ctx* ctx, mcb200_comm* comm, mcb200_me
         tot.n_exact += hc[r].n_exact;
         tot.n_records += hc[r].n_records;
         tot.n_queue = std::max(tot.n_queue, hc[r].n_queue);
+        tot.n_cross = std::max(tot.n_cross, hc[r].n_cross);
+        tot.n_full = std::max(tot.n_full, hc[r].n_full);
         tot.gp_violation |= hc[r].gp_violation;
         tot.bad_face = std::min(tot.bad_face, hc[r].bad_face);
         tot.soup_error |= hc[r].soup_error;
@@ -208,7 +210,7 @@ int mcb200_intersect_stage_sharded(mcb200_ctx* ctx, mcb200_comm* comm, mcb200_me
         for (int r = 0; r < N; ++r) {
             need = std::max(need, (size_t)hc[r].n_pairs + (size_t)hc[r].n_pairs / 8 + 1024);
             need = std::max(need, (size_t)hc[r].n_records / 2 + 1024);
-            if (hc[r].n_queue > res->cap_exact) need = std::max(need, res->cap_pairs * 2);
+            if (narrow_queue_overflow(res, hc[r])) need = std::max(need, res->cap_pairs * 2);
         }
         res->cap_pairs = need;
         res->h_valid = false;

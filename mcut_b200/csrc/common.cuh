@@ -273,9 +273,12 @@ struct result_counters_t {
     unsigned int work_counter; // ticket counter of the traversal: next query group to hand out
     unsigned int soup_error; // device-side soup numbering: an edge with three faces or two faces wound the same way
     unsigned int soup_ne; // number of polygon-soup edges it found
-    unsigned long long n_queue; // tests the filter kernel handed to the second kernel (stage-A failures + crossings)
+    unsigned long long n_queue; // polygons: tests the filter kernel handed on; triangles: tests whose stage A failed
+    unsigned long long n_mid; // triangles: pairs the side prefilter could not dismiss
+    unsigned long long n_cross; // triangles: certified plane crossings (second half of the exact queue)
+    unsigned long long n_full; // triangles: tests with inexact differences, for the general exact kernel
     unsigned int pair_seg_max; // most candidate pairs of one source face (decides how the pair list is put in order)
-    unsigned int pad[3];
+    unsigned int pad[1];
 };
 static_assert(offsetof(result_counters_t, n_queue) % 8 == 0, "n_queue is atomically incremented as a 64-bit word");
 
@@ -296,7 +299,9 @@ struct mcb200_result {
     dbuf plane; // per ps face: normal[3], d  (4 doubles) ; maxcomp in separate int array
     dbuf plane_mc; // i32 per ps face
     dbuf exact_queue; // u64 test keys needing the exact stage
+    dbuf mid_queue; // u64 [cap_pairs], triangle meshes only (narrowphase.cu: k_tri_prefilter)
     size_t cap_exact = 0;
+    bool tri_queues = false; // the last narrowphase used the triangle pipeline (split exact queue + mid queue)
     dbuf records; // mcb200_record [cap_records]
     dbuf rec_keys; // u64
     dbuf rec_idx; // u32

@@ -32,6 +32,7 @@ int stage_reserve(mcb200_ctx* ctx, mcb200_mesh* src, mcb200_mesh* cut, const mcb
 int stage_body(mcb200_ctx* ctx, mcb200_mesh* src, mcb200_mesh* cut, double cut_eps, mcb200_soup* soup, mcb200_result* res, uint32_t flags,
     bool wait_uploads, int number_soup, bool interleave, bool order = true);
 int fetch_counters(mcb200_ctx* ctx, mcb200_result* res);
+bool narrow_queue_overflow(const mcb200_result* res, const result_counters_t& h);
 // soup_ids.cu
 int soup_number_reserve(mcb200_ctx* ctx, const mcb200_mesh* src, const mcb200_mesh* cut, mcb200_soup* soup);
 int soup_number_device(mcb200_ctx* ctx, const mcb200_mesh* src, const mcb200_mesh* cut, mcb200_soup* soup, result_counters_t* counters);

@@ -47,8 +47,15 @@ struct narrow_args_t {
     uint8_t* cand_flag;
     mcb200_record* records;
     unsigned long long cap_records;
-    unsigned long long* exact_queue; // (pair index << 8 | slot)
+    unsigned long long* exact_queue; // polygons: (pair index << 8 | slot); triangles: see k_tri_classify
     unsigned long long cap_exact;
+    unsigned long long* mid_queue; // triangles: pairs the side prefilter could not dismiss; reused for what k_tri_resolve hands on
+    unsigned long long cap_mid;
+    // what the general exact kernel (k_tests<*, true>) reads: (pair index << 8 | slot) entries and their count
+    const unsigned long long* exact_in;
+    const unsigned long long* exact_in_n;
+    unsigned long long exact_in_cap;
+    uint32_t tri_mode; // 0: prefilter on; 1: and the dismissed tests are still counted (n_tests as the reference runs them); 2: prefilter off (test log)
     mcb200_test* tests; // optional log
     unsigned long long cap_tests;
 };
@@ -188,6 +195,11 @@ __device__ __noinline__ bool best_triple(const face_view& G, const double* norma
     return found;
 }
 
+__device__ __forceinline__ void classify_signs(int sq, int sr, test_out_t& o);
+template <bool TRI>
+__device__ __forceinline__ void finish_touching(const face_view& G, const double (*gv)[3], const double* q, const double* r,
+    test_out_t& o, unsigned& gp_violation, bool have_plane, double* normal, double d, int mc);
+
 // One edge/face test (kernel.cpp:2483-2656).  With EXACT off it returns false unless the test is a CERTIFIED non-crossing
 // (both stage-A determinants pass the error-bound filter and have the same sign): the caller queues everything else for
 // the second kernel (`needs_exact` tells it whether a stage-A filter failed); with EXACT on it always fills `o`.
@@ -237,21 +249,35 @@ __device__ __forceinline__ bool eval_test(const face_view& G, const double (*gv)
         if (!cq) detq = pred::orient3d_adapt(A, B, C, q, permq);
         if (!cr) detr = pred::orient3d_adapt(A, B, C, r, permr);
     }
-    o.sq = (int8_t)sgn(detq);
-    o.sr = (int8_t)sgn(detr);
-    o.pip = 0;
-    o.p[0] = o.p[1] = o.p[2] = 0.0;
-    // math.cpp:416-426
-    if (detq == 0.0 && detr == 0.0) o.type = 'p';
-    else if (detq == 0.0) o.type = 'q';
-    else if (detr == 0.0) o.type = 'r';
-    else if ((detr < 0.0 && detq < 0.0) || (detr > 0.0 && detq > 0.0)) o.type = '0';
-    else o.type = '1';
+    classify_signs(sgn(detq), sgn(detr), o);
     if (o.type == '0') return true;
     // The filter kernel settles the certified non-crossings only (98 % of the tests of a dense overlap): an edge that does
     // cross the plane — plane point, point-in-polygon, registry record — is left to the second kernel, so that this
     // kernel's register budget is the two stage-A determinants and nothing else.
     if (!EXACT) return false;
+    finish_touching<TRI>(G, gv, q, r, o, gp_violation, have_plane, normal, d, mc);
+    return true;
+}
+
+// segment vs plane from the two orientation signs (math.cpp:416-426)
+__device__ __forceinline__ void classify_signs(int sq, int sr, test_out_t& o)
+{
+    o.sq = (int8_t)sq;
+    o.sr = (int8_t)sr;
+    o.pip = 0;
+    o.p[0] = o.p[1] = o.p[2] = 0.0;
+    if (sq == 0 && sr == 0) o.type = 'p';
+    else if (sq == 0) o.type = 'q';
+    else if (sr == 0) o.type = 'r';
+    else if (sq == sr) o.type = '0';
+    else o.type = '1';
+}
+
+// everything after the signs for a test that crosses or touches the plane (kernel.cpp:2518-2597)
+template <bool TRI>
+__device__ __forceinline__ void finish_touching(const face_view& G, const double (*gv)[3], const double* q, const double* r,
+    test_out_t& o, unsigned& gp_violation, bool have_plane, double* normal, double d, int mc)
+{
     if (!have_plane) mc = face_plane<TRI>(G, gv, normal, d);
     if (o.type == '1') {
         pred::segment_plane_point(o.p, normal, d, q, r); // kernel.cpp:2559-2564
@@ -270,7 +296,6 @@ __device__ __forceinline__ bool eval_test(const face_view& G, const double (*gv)
         }
         if (stop) gp_violation = 1u;
     }
-    return true;
 }
 
 __device__ __forceinline__ void emit(const narrow_args_t& a, uint32_t edge, uint32_t face, const test_out_t& o)
@@ -317,7 +342,7 @@ template <bool TRI>
 __device__ __forceinline__ bool setup_test(const narrow_args_t& a, uint32_t s, uint32_t c, uint32_t slot, uint32_t hs,
     uint32_t ns, uint32_t hc, uint32_t nc, const double (*sv)[3], const double (*cv)[3], const double* sbox,
     const double* cbox, uint32_t& edge, uint32_t& tested_face, bool& edge_from_src, double* q, double* r,
-    const uint32_t* pre_edge = nullptr, const uint2* pre_ef = nullptr)
+    const uint32_t* pre_edge = nullptr, const uint2* pre_ef = nullptr, bool* h0_out = nullptr)
 {
     edge_from_src = slot < ns;
     const uint32_t i = edge_from_src ? slot : slot - ns;
@@ -329,6 +354,7 @@ __device__ __forceinline__ bool setup_test(const narrow_args_t& a, uint32_t s, u
     edge = pre_edge ? pre_edge[slot] : __ldg(a.face_edge + hbase + i);
     const uint2 ef = pre_ef ? pre_ef[slot] : __ldg(reinterpret_cast<const uint2*>(a.edge_f) + edge);
     const bool is_h0 = (ef.x == own_face);
+    if (h0_out) *h0_out = is_h0;
     const double* tbox = edge_from_src ? cbox : sbox; // box of the tested face
     if (!is_h0 && ef.x != MCB200_NULL) { // (an edge whose h0 has no face — a border after a repartition — is owned by the h1 face)
         // the face of h0 owns this test whenever it is paired with the tested face too
@@ -383,7 +409,7 @@ template <bool TRI, bool EXACT> __global__ void __launch_bounds__(NBLOCK) k_test
     a.cut_frame = &s_fr[1];
     unsigned long long n_items;
     if (EXACT) {
-        n_items = a.counters->n_queue < a.cap_exact ? a.counters->n_queue : a.cap_exact;
+        n_items = *a.exact_in_n < a.exact_in_cap ? *a.exact_in_n : a.exact_in_cap;
     } else {
         n_items = a.counters->n_pairs < a.cap_pairs ? a.counters->n_pairs : a.cap_pairs;
     }
@@ -393,7 +419,7 @@ template <bool TRI, bool EXACT> __global__ void __launch_bounds__(NBLOCK) k_test
         unsigned long long pair_index = it;
         uint32_t only_slot = 0xFFFFFFFFu;
         if (EXACT) {
-            const unsigned long long e = a.exact_queue[it];
+            const unsigned long long e = a.exact_in[it];
             pair_index = e >> 8;
             only_slot = (uint32_t)(e & 0xFFu);
         }
@@ -480,6 +506,268 @@ template <bool TRI, bool EXACT> __global__ void __launch_bounds__(NBLOCK) k_test
         if (n_exact_local) atomicAdd(&a.counters->n_exact, (unsigned long long)n_exact_local);
         if (gp) atomicOr(&a.counters->gp_violation, 1u);
     }
+}
+
+// ---- triangle meshes: prefilter -> classify -> resolve -> (general exact kernel) ----------------------------------------
+// Nearly all candidate pairs of a dense overlap are two triangles that merely lie close to each other: every vertex of one
+// is clearly on one side of the other's plane, so none of the six edge/face tests can cross.  Three kernels, each with
+// dense warps of one kind of work and the registers that work needs:
+//   k_tri_prefilter  one thread per pair: side of each vertex w.r.t. the other triangle's plane with a bound that implies
+//                    orient3d's stage-A certificate (pred::orient3d_side_prefilter).  A test whose two endpoints are on the
+//                    same certified side is a certified non-crossing — it has no output in the reference either, whether
+//                    the ownership / box culls would have let it run or not — and is dropped here.  Pairs with anything
+//                    left go to the mid queue with the sides found so far.
+//   k_tri_classify   one thread per queued pair, the undecided slots only: ownership + box culls (kernel.cpp:2004-2115),
+//                    then the real stage A where a side is still open.  Outcomes: certified non-crossing (done), certified
+//                    crossing (second half of the exact queue), stage A failed (first half).
+//   k_tri_resolve    one thread per queued test, stage-A failures first: exact sign when the differences are exact
+//                    (pred::det3_sign_exact), plane point, point-in-triangle, registry record.  A test with inexact
+//                    differences is handed to the general kernel (k_tests<true, true>, Shewchuk's stages B-D).
+// Mid-queue entry:   pair index << 24 | sides << 12 | count-only slots << 6 | slots to test
+//                    (sides: 2 bits per vertex, source vertices 0-2 vs the cut plane then cut vertices vs the source plane;
+//                     0 open, 1 orient3d > 0, 2 orient3d < 0)
+// Exact-queue entry: pair index << 8 | sr>0 << 7 | sq>0 << 6 | r open << 5 | q open << 4 | is_h0 << 3 | slot
+constexpr int PF_THREADS = 256;
+
+__device__ __forceinline__ void load_tri(const narrow_args_t& a, uint32_t h, double (*v)[3])
+{
+    const uint32_t i0 = __ldg(a.face_vtx + h), i1 = __ldg(a.face_vtx + h + 1), i2 = __ldg(a.face_vtx + h + 2);
+    load_ps_vertex(a, i0, v[0]);
+    load_ps_vertex(a, i1, v[1]);
+    load_ps_vertex(a, i2, v[2]);
+}
+
+__device__ __forceinline__ void stage_frames(const narrow_args_t& a_in, frame_t* s_fr)
+{
+    load_frame_shared(&s_fr[0], a_in.src_frame);
+    if (threadIdx.x >= 64) { // second half of the block fetches the cut frame
+        constexpr unsigned W = sizeof(frame_t) / 4;
+        const unsigned t = threadIdx.x - 64u;
+        if (t < W) reinterpret_cast<unsigned*>(&s_fr[1])[t] = __ldg(reinterpret_cast<const unsigned*>(a_in.cut_frame) + t);
+    }
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(PF_THREADS, 4) k_tri_prefilter(narrow_args_t a_in)
+{
+    pdl_prologue();
+    __shared__ frame_t s_fr[2];
+    stage_frames(a_in, s_fr);
+    narrow_args_t a = a_in;
+    a.src_frame = &s_fr[0];
+    a.cut_frame = &s_fr[1];
+    const unsigned long long n_items = a.counters->n_pairs < a.cap_pairs ? a.counters->n_pairs : a.cap_pairs;
+    for (unsigned long long it = (unsigned long long)blockIdx.x * PF_THREADS + threadIdx.x; it < n_items;
+         it += (unsigned long long)gridDim.x * PF_THREADS) {
+        const unsigned long long pr = a.pairs[it];
+        const uint32_t s = (uint32_t)(pr >> 32), c = (uint32_t)(pr & 0xFFFFFFFFu);
+        a.cand_flag[s] = 1;
+        a.cand_flag[a.nsf + c] = 1;
+        unsigned sides = 0, todo = 63u;
+        if (a.tri_mode != 2u) {
+            double sv[3][3], cv[3][3], nrm[3];
+            load_tri(a, 3u * s, sv);
+            load_tri(a, 3u * (a.nsf + c), cv);
+            int sd[6];
+            double luv = pred::side_prefilter_plane(cv[0], cv[1], cv[2], nrm);
+#pragma unroll
+            for (int j = 0; j < 3; ++j) sd[j] = pred::orient3d_side_prefilter(nrm, luv, cv[0], sv[j]);
+            luv = pred::side_prefilter_plane(sv[0], sv[1], sv[2], nrm);
+#pragma unroll
+            for (int j = 0; j < 3; ++j) sd[3 + j] = pred::orient3d_side_prefilter(nrm, luv, sv[0], cv[j]);
+            todo = 0;
+#pragma unroll
+            for (int k = 0; k < 6; ++k) {
+                sides |= (sd[k] > 0 ? 1u : (sd[k] < 0 ? 2u : 0u)) << (2 * k);
+                // halfedge k of a face runs from its vertex k-1 to its vertex k
+                const int base = k < 3 ? 0 : 3, i = k - base, ip = (i + 2) % 3;
+                const bool same_side = sd[base + i] != 0 && sd[base + i] == sd[base + ip];
+                todo |= (same_side ? 0u : 1u) << k;
+            }
+        }
+        const unsigned count_only = a.tri_mode == 1u ? (~todo & 63u) : 0u;
+        if (todo | count_only) {
+            const unsigned long long slot = alloc_slot(&a.counters->n_mid);
+            if (slot < a.cap_mid) a.mid_queue[slot] = (it << 24) | ((unsigned long long)sides << 12) | (count_only << 6) | todo;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(NBLOCK) k_tri_classify(narrow_args_t a_in)
+{
+    pdl_prologue();
+    __shared__ frame_t s_fr[2];
+    stage_frames(a_in, s_fr);
+    narrow_args_t a = a_in;
+    a.src_frame = &s_fr[0];
+    a.cut_frame = &s_fr[1];
+    const unsigned long long n_items = a.counters->n_mid < a.cap_mid ? a.counters->n_mid : a.cap_mid;
+    const unsigned long long half = a.cap_exact / 2;
+    unsigned n_tests_local = 0, n_exact_local = 0;
+    for (unsigned long long it = (unsigned long long)blockIdx.x * NBLOCK + threadIdx.x; it < n_items;
+         it += (unsigned long long)gridDim.x * NBLOCK) {
+        const unsigned long long me = a.mid_queue[it];
+        const unsigned long long pair_index = me >> 24;
+        const unsigned sides = (unsigned)(me >> 12) & 0xFFFu, count_only = (unsigned)(me >> 6) & 63u, todo = (unsigned)me & 63u;
+        const unsigned long long pr = a.pairs[pair_index];
+        const uint32_t s = (uint32_t)(pr >> 32), c = (uint32_t)(pr & 0xFFFFFFFFu);
+        const uint32_t hs = 3u * s, hc = 3u * (a.nsf + c);
+        double sv[3][3], cv[3][3];
+        load_tri(a, hs, sv);
+        load_tri(a, hc, cv);
+        double sbox[6], cbox[6];
+        load_box(a.src_bbox + 6 * (size_t)s, sbox);
+        load_box(a.cut_bbox + 6 * (size_t)c, cbox);
+        uint32_t pre_edge[6];
+        uint2 pre_ef[6];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            pre_edge[k] = __ldg(a.face_edge + hs + k);
+            pre_edge[3 + k] = __ldg(a.face_edge + hc + k);
+        }
+#pragma unroll
+        for (int k = 0; k < 6; ++k) pre_ef[k] = __ldg(reinterpret_cast<const uint2*>(a.edge_f) + pre_edge[k]);
+        // six slots, unrolled: every vertex / edge-id selection below is a compile-time index (no local-memory arrays)
+#pragma unroll
+        for (uint32_t slot = 0; slot < 6u; ++slot) {
+            if (!(((todo | count_only) >> slot) & 1u)) continue;
+            uint32_t edge, tested_face;
+            bool from_src, is_h0;
+            double q[3], r[3];
+            if (!setup_test<true>(a, s, c, slot, hs, 3u, hc, 3u, sv, cv, sbox, cbox, edge, tested_face, from_src, q, r, pre_edge,
+                    pre_ef, &is_h0))
+                continue;
+            n_tests_local++;
+            if ((count_only >> slot) & 1u) continue;
+            // sides of the halfedge's two vertices as the prefilter left them: q = source(h0), r = target(h0)
+            const uint32_t i = slot < 3u ? slot : slot - 3u, ip = (i + 2u) % 3u, vb = slot < 3u ? 0u : 3u;
+            const unsigned s_from = (sides >> (2u * (vb + ip))) & 3u, s_to = (sides >> (2u * (vb + i))) & 3u;
+            unsigned side_q = is_h0 ? s_from : s_to, side_r = is_h0 ? s_to : s_from;
+            unsigned open_q = 0, open_r = 0;
+            if (side_q == 0u || side_r == 0u) {
+                const double(*gv)[3] = slot < 3u ? cv : sv; // (slot is a constant here: no pointer selection at run time)
+                bool cq, cr;
+                double permq, permr;
+                const double detq = pred::orient3d_stageA(gv[0], gv[1], gv[2], q, cq, permq);
+                const double detr = pred::orient3d_stageA(gv[0], gv[1], gv[2], r, cr, permr);
+                open_q = cq ? 0u : 1u;
+                open_r = cr ? 0u : 1u;
+                side_q = cq ? (detq > 0.0 ? 1u : 2u) : 0u;
+                side_r = cr ? (detr > 0.0 ? 1u : 2u) : 0u;
+                n_exact_local += (open_q | open_r);
+                if (!(open_q | open_r) && side_q == side_r) { // certified non-crossing
+                    if (a.tests) {
+                        test_out_t o;
+                        classify_signs(side_q == 1u ? 1 : -1, side_r == 1u ? 1 : -1, o);
+                        o.exact = 0;
+                        log_test(a, edge, tested_face, o);
+                    }
+                    continue;
+                }
+            }
+            const unsigned long long entry = (pair_index << 8) | ((side_r == 1u ? 1u : 0u) << 7) | ((side_q == 1u ? 1u : 0u) << 6)
+                | (open_r << 5) | (open_q << 4) | ((is_h0 ? 1u : 0u) << 3) | slot;
+            if (open_q | open_r) {
+                const unsigned long long qs = alloc_slot(&a.counters->n_queue);
+                if (qs < half) a.exact_queue[qs] = entry;
+            } else {
+                const unsigned long long qs = alloc_slot(&a.counters->n_cross);
+                if (qs < half) a.exact_queue[half + qs] = entry;
+            }
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        n_tests_local += __shfl_xor_sync(0xffffffffu, n_tests_local, o);
+        n_exact_local += __shfl_xor_sync(0xffffffffu, n_exact_local, o);
+    }
+    if (lane_id() == 0) {
+        if (n_tests_local) atomicAdd(&a.counters->n_tests, (unsigned long long)n_tests_local);
+        if (n_exact_local) atomicAdd(&a.counters->n_exact, (unsigned long long)n_exact_local);
+    }
+}
+
+__global__ void __launch_bounds__(NBLOCK) k_tri_resolve(narrow_args_t a_in)
+{
+    pdl_prologue();
+    __shared__ frame_t s_fr[2];
+    stage_frames(a_in, s_fr);
+    narrow_args_t a = a_in;
+    a.src_frame = &s_fr[0];
+    a.cut_frame = &s_fr[1];
+    const unsigned long long half = a.cap_exact / 2;
+    const unsigned long long n_open = a.counters->n_queue < half ? a.counters->n_queue : half;
+    const unsigned long long n_cross = a.counters->n_cross < half ? a.counters->n_cross : half;
+    unsigned gp = 0;
+    for (unsigned long long it = (unsigned long long)blockIdx.x * NBLOCK + threadIdx.x; it < n_open + n_cross;
+         it += (unsigned long long)gridDim.x * NBLOCK) {
+        const unsigned long long e = it < n_open ? a.exact_queue[it] : a.exact_queue[half + (it - n_open)];
+        const unsigned long long pair_index = e >> 8;
+        const uint32_t slot = (uint32_t)e & 7u;
+        const bool is_h0 = (e >> 3) & 1u, open_q = (e >> 4) & 1u, open_r = (e >> 5) & 1u;
+        const unsigned long long pr = a.pairs[pair_index];
+        const uint32_t s = (uint32_t)(pr >> 32), c = (uint32_t)(pr & 0xFFFFFFFFu);
+        const bool from_src = slot < 3u;
+        const uint32_t i = from_src ? slot : slot - 3u, ip = (i + 2u) % 3u;
+        const uint32_t h_own = from_src ? 3u * s : 3u * (a.nsf + c), h_tst = from_src ? 3u * (a.nsf + c) : 3u * s;
+        const uint32_t tested_face = from_src ? a.nsf + c : s;
+        double gv[3][3], from[3], to[3];
+        load_tri(a, h_tst, gv);
+        load_ps_vertex(a, __ldg(a.face_vtx + h_own + ip), from);
+        load_ps_vertex(a, __ldg(a.face_vtx + h_own + i), to);
+        const uint32_t edge = __ldg(a.face_edge + h_own + i);
+        double q[3], r[3];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            q[k] = is_h0 ? from[k] : to[k];
+            r[k] = is_h0 ? to[k] : from[k];
+        }
+        int sq = ((e >> 6) & 1u) ? 1 : -1, sr = ((e >> 7) & 1u) ? 1 : -1;
+        bool decided = true;
+        if (open_q | open_r) {
+            // orient3d(gv0, gv1, gv2, p): the rows of stage A are gv_k - p
+#pragma unroll
+            for (int which = 0; which < 2; ++which) {
+                if (!(which == 0 ? open_q : open_r) || !decided) continue;
+                const double* p = which == 0 ? q : r;
+                double dx[9];
+                bool exact_rows = true;
+#pragma unroll
+                for (int k = 0; k < 3; ++k) {
+#pragma unroll
+                    for (int j = 0; j < 3; ++j) {
+                        dx[3 * k + j] = pred::sub(gv[k][j], p[j]);
+                        exact_rows = exact_rows && pred::two_diff_tail(gv[k][j], p[j], dx[3 * k + j]) == 0.0;
+                    }
+                }
+                int sg = 0;
+                if (exact_rows && pred::det3_sign_exact(dx[0], dx[1], dx[2], dx[3], dx[4], dx[5], dx[6], dx[7], dx[8], sg)) {
+                    if (which == 0) sq = sg;
+                    else sr = sg;
+                } else {
+                    decided = false;
+                }
+            }
+        }
+        if (!decided) { // inexact differences: Shewchuk's adaptive stages, in the general kernel
+            const unsigned long long qs = alloc_slot(&a.counters->n_full);
+            if (qs < a.cap_mid) a.mid_queue[qs] = (pair_index << 8) | slot;
+            continue;
+        }
+        test_out_t o;
+        classify_signs(sq, sr, o);
+        o.exact = (uint8_t)((open_q ? 1 : 0) | (open_r ? 2 : 0));
+        if (o.type != '0') {
+            const face_view G { &a, h_tst, 3u };
+            double normal[3];
+            finish_touching<true>(G, gv, q, r, o, gp, false, normal, 0.0, 0);
+            emit(a, edge, tested_face, o);
+        }
+        log_test(a, edge, tested_face, o);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) gp |= __shfl_xor_sync(0xffffffffu, gp, o);
+    if (lane_id() == 0 && gp) atomicOr(&a.counters->gp_violation, 1u);
 }
 
 // ---- per-candidate-face plane data + degenerate-face rule (kernel.cpp:2184-2356) ----------------------------------------
@@ -662,6 +950,8 @@ int narrowphase_reserve(mcb200_ctx* ctx, const mcb200_soup* soup, mcb200_result*
     res->cap_records = cap_rec;
     MCB_TRY(ctx->reserve(res->exact_queue, sizeof(unsigned long long) * cap_exact));
     res->cap_exact = cap_exact;
+    if (tri) MCB_TRY(ctx->reserve(res->mid_queue, sizeof(unsigned long long) * res->cap_pairs));
+    res->tri_queues = tri;
     MCB_TRY(ctx->reserve(res->cand_flag, (size_t)nf));
     MCB_TRY(ctx->reserve(res->plane, sizeof(double) * 4 * (size_t)nf));
     MCB_TRY(ctx->reserve(res->plane_mc, sizeof(int32_t) * 2 * (size_t)nf));
@@ -710,6 +1000,18 @@ static int make_narrow_args(mcb200_ctx* ctx, const mcb200_soup* soup, const mcb2
     a.cap_records = res->cap_records;
     a.exact_queue = res->exact_queue.as<unsigned long long>();
     a.cap_exact = res->cap_exact;
+    a.mid_queue = res->mid_queue.as<unsigned long long>();
+    a.cap_mid = res->cap_pairs;
+    if (soup->all_tri) { // what k_tri_resolve could not settle, parked in the (by then idle) mid queue
+        a.exact_in = a.mid_queue;
+        a.exact_in_n = &a.counters->n_full;
+        a.exact_in_cap = a.cap_mid;
+    } else {
+        a.exact_in = a.exact_queue;
+        a.exact_in_n = &a.counters->n_queue;
+        a.exact_in_cap = a.cap_exact;
+    }
+    a.tri_mode = 0;
     a.tests = want_log ? res->tests.as<mcb200_test>() : nullptr;
     a.cap_tests = res->cap_tests;
     return 0;
@@ -757,7 +1059,7 @@ int narrowphase_run(mcb200_ctx* ctx, const mcb200_soup* soup, const mcb200_mesh*
         result_counters_t* c = res->counters.as<result_counters_t>();
         fill_list_t fl {};
         fl.add(&c->n_tests, 10, 0u); // n_tests .. n_log
-        fl.add(&c->n_queue, 2, 0u);
+        fl.add(&c->n_queue, 8, 0u); // n_queue, n_mid, n_cross, n_full
         fl.add(&c->gp_violation, 1, 0u);
         fl.add(&c->bad_face, 1, 0xFFFFFFFFu);
         MCB_LAUNCH(ctx, k_fill, 1, 256, 0, fl);
@@ -768,8 +1070,13 @@ int narrowphase_run(mcb200_ctx* ctx, const mcb200_soup* soup, const mcb200_mesh*
     MCB_TRY(make_narrow_args(ctx, soup, src, cut, res, want_log, a));
 
     const unsigned grid = (unsigned)ctx->num_sms * 8u;
-    if (tri) MCB_LAUNCH_NAMED(ctx, "k_tests_filter_tri", (k_tests<true, false>), grid, NBLOCK, 0, a);
-    else MCB_LAUNCH_NAMED(ctx, "k_tests_filter_poly", (k_tests<false, false>), grid, NBLOCK, 0, a);
+    if (tri) {
+        a.tri_mode = want_log ? 2u : ((flags & MCB200_NARROW_COUNT_TESTS) ? 1u : 0u);
+        MCB_LAUNCH(ctx, k_tri_prefilter, grid, PF_THREADS, 0, a);
+        MCB_LAUNCH(ctx, k_tri_classify, grid, NBLOCK, 0, a);
+    } else {
+        MCB_LAUNCH_NAMED(ctx, "k_tests_filter_poly", (k_tests<false, false>), grid, NBLOCK, 0, a);
+    }
 
     // The plane rows only depend on the candidate flags the filter just wrote, so they are made beside the exact pass and the
     // record sort on the background lane.
@@ -788,8 +1095,12 @@ int narrowphase_run(mcb200_ctx* ctx, const mcb200_soup* soup, const mcb200_mesh*
     // exact-expansion pass over the compacted filter failures (own kernel: its local-memory footprint and divergence
     // stay out of the filter kernel)
     const unsigned egrid = (unsigned)ctx->num_sms * 4u;
-    if (tri) MCB_LAUNCH_NAMED(ctx, "k_tests_exact_tri", (k_tests<true, true>), egrid, NBLOCK, 0, a);
-    else MCB_LAUNCH_NAMED(ctx, "k_tests_exact_poly", (k_tests<false, true>), egrid, NBLOCK, 0, a);
+    if (tri) {
+        MCB_LAUNCH(ctx, k_tri_resolve, grid, NBLOCK, 0, a);
+        MCB_LAUNCH_NAMED(ctx, "k_tests_exact_tri", (k_tests<true, true>), egrid, NBLOCK, 0, a); // returns at once unless n_full > 0
+    } else {
+        MCB_LAUNCH_NAMED(ctx, "k_tests_exact_poly", (k_tests<false, true>), egrid, NBLOCK, 0, a);
+    }
 
     res->have_narrow = true;
     res->h_valid = false;

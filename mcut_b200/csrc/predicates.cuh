@@ -400,6 +400,84 @@ __device__ __noinline__ double orient3d_adapt(const double* pa, const double* pb
 }
 
 // ---- plane of a polygon (math.cpp:130-239) ----------------------------------------------------------------------
+// ---- device-side shortcuts that reproduce orient3d's SIGN without following its arithmetic ---------------------------
+// The narrowphase consumes nothing of orient3d but the sign of its result (kernel.cpp:2483-2516 via math.cpp:416-426), and
+// that sign is by construction the sign of the exact determinant (Shewchuk 1997, sec. 4.4).  Two consequences used here.
+
+// (1) Side prefilter.  For a tested triangle T0 T1 T2 and a query point P, with u = T1-T0, v = T2-T0, w = P-T0 computed in
+// binary64, det' = (u x v) . w and L >= every |u_i|, |v_i|, |w_i|:
+//   |det' - D| <= 48 e L^3          (D the exact determinant, e = 2^-53: three roundings per difference, five per monomial)
+//   permanent_A <= 24 L^3 (1+10e)   (rows of stage A are T0-P, T1-P, T2-P: entries <= L, 2L, 2L)
+// so |det'| > 2^-43 L^3 = 1024 e L^3 implies |D| > 976 e L^3, hence stage A's own estimate exceeds
+// (976 - 168) e L^3 > o3derrboundA * permanent_A: stage A certifies the sign, and the sign is sign(D) = -sign(det').
+// Returns +1 / -1 = orient3d's certified sign, 0 = not decided here (the caller runs the real stage A).
+__device__ __forceinline__ int orient3d_side_prefilter(const double* nrm, double luv, const double* t0, const double* p)
+{
+    const double wx = p[0] - t0[0], wy = p[1] - t0[1], wz = p[2] - t0[2];
+    const double l = fmax(fmax(luv, fabs(wx)), fmax(fabs(wy), fabs(wz)));
+    const double det = nrm[0] * wx + nrm[1] * wy + nrm[2] * wz;
+    const double thr = l * l * l * 0x1p-43;
+    return det > thr ? -1 : (det < -thr ? 1 : 0); // (a NaN or an overflow compares false twice: undecided)
+}
+__device__ __forceinline__ double side_prefilter_plane(const double* t0, const double* t1, const double* t2, double* nrm)
+{
+    const double ux = t1[0] - t0[0], uy = t1[1] - t0[1], uz = t1[2] - t0[2];
+    const double vx = t2[0] - t0[0], vy = t2[1] - t0[1], vz = t2[2] - t0[2];
+    nrm[0] = uy * vz - uz * vy;
+    nrm[1] = uz * vx - ux * vz;
+    nrm[2] = ux * vy - uy * vx;
+    return fmax(fmax(fmax(fabs(ux), fabs(uy)), fmax(fabs(uz), fabs(vx))), fmax(fabs(vy), fabs(vz)));
+}
+
+// (2) Exact sign when the nine differences of stage A are exact (all tails zero: orient3dadapt then returns at stage B
+// with an estimate of the exact determinant of those differences, shewchuk.c:2041-2075).  The determinant is written as
+// 24 doubles whose sum is exact — each of the six triple products x*y*z as two_product(x,y) = (p,e), then two_product(p,z)
+// and two_product(e,z), with the fused multiply-add giving each error term in one instruction — and the sign of the sum
+// is found by error-free distillation passes (t[i], t[i-1] <- two_sum) until the leading term dominates what is left.
+// Everything is indexed statically: the 24 terms live in registers.  Returns false if five passes did not decide (the
+// caller falls back to orient3d_adapt); products that underflow are excluded by the caller's magnitude guard.
+__device__ __forceinline__ void exact_triple(double x, double y, double z, double* t)
+{
+    const double p = __dmul_rn(x, y), e = __fma_rn(x, y, -p);
+    t[0] = __dmul_rn(e, z);
+    t[1] = __fma_rn(e, z, -t[0]);
+    t[2] = __dmul_rn(p, z);
+    t[3] = __fma_rn(p, z, -t[2]);
+}
+__device__ __forceinline__ bool det3_sign_exact(double adx, double ady, double adz, double bdx, double bdy, double bdz, double cdx,
+    double cdy, double cdz, int& sign)
+{
+    double t[24];
+    exact_triple(bdx, cdy, adz, t);
+    exact_triple(-cdx, bdy, adz, t + 4);
+    exact_triple(cdx, ady, bdz, t + 8);
+    exact_triple(-adx, cdy, bdz, t + 12);
+    exact_triple(adx, bdy, cdz, t + 16);
+    exact_triple(-bdx, ady, cdz, t + 20);
+    // guard: a term below 2^-960 in magnitude may have lost bits to underflow in its error term
+    double mn = 1.0;
+#pragma unroll
+    for (int i = 2; i < 24; i += 4) mn = fmin(mn, t[i] == 0.0 ? 1.0 : fabs(t[i]));
+    if (mn < 0x1p-800) return false;
+#pragma unroll 1
+    for (int pass = 0; pass < 6; ++pass) {
+#pragma unroll
+        for (int i = 1; i < 24; ++i) {
+            const dd r = two_sum(t[i], t[i - 1]);
+            t[i] = r.hi;
+            t[i - 1] = r.lo;
+        }
+        double rest = 0.0;
+#pragma unroll
+        for (int i = 0; i < 23; ++i) rest += fabs(t[i]);
+        if (rest == 0.0 || fabs(t[23]) > 2.0 * rest) {
+            sign = (t[23] > 0.0) - (t[23] < 0.0);
+            return true;
+        }
+    }
+    return false;
+}
+
 __device__ __forceinline__ double dot3(const double* a, const double* b)
 {
     // math.h:634-642: accumulates from 0.0 in x, y, z order

@@ -436,34 +436,51 @@ __global__ void __launch_bounds__(256) k_pair_scatter(const unsigned long long* 
     }
 }
 
-__global__ void __launch_bounds__(256) k_pair_segsort(unsigned long long* __restrict__ out, const unsigned* __restrict__ off,
+// One block orders the segments of SS_FACES consecutive source faces.  Their pairs are contiguous in `out`: the span is
+// staged in shared memory with coalesced loads, every thread orders its own face's handful of entries there (insertion
+// sort: the same source face, so the cut face decides), and the span goes back coalesced.  In global memory the same sort is
+// a chain of dependent round trips — tens of microseconds for a 15-entry segment, whatever the size of the input.
+constexpr int SS_FACES = 128;
+constexpr unsigned SS_SPAN = 4096; // pairs staged per tile (32 KB); a denser tile is ordered in place
+
+__global__ void __launch_bounds__(SS_FACES) k_pair_segsort(unsigned long long* __restrict__ out, const unsigned* __restrict__ off,
     unsigned* __restrict__ cursor, uint32_t nsf, unsigned long long cap, const result_counters_t* counters)
 {
     pdl_prologue();
+    __shared__ unsigned long long sh[SS_SPAN];
     const bool counting = counters->pair_seg_max <= SEG_LIMIT && !counters->pair_overflow;
-    // four faces per thread and step (16-byte loads of the cursors; most faces have no pair at all)
-    const uint32_t n4 = (nsf + 3u) / 4u;
-    for (uint32_t q = blockIdx.x * 256u + threadIdx.x; q < n4; q += gridDim.x * 256u) {
-        const uint4 c4 = *reinterpret_cast<const uint4*>(cursor + 4u * q);
-        if ((c4.x | c4.y | c4.z | c4.w) == 0u) continue;
-        *reinterpret_cast<uint4*>(cursor + 4u * q) = make_uint4(0u, 0u, 0u, 0u); // all zero again for the next run
-        if (!counting) continue;
-        const unsigned cs[4] = { c4.x, c4.y, c4.z, c4.w };
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            const unsigned c = cs[k];
-            if (c < 2u) continue;
-            unsigned long long* seg = out + off[4u * q + k];
-            // insertion sort of a handful of entries (same source face: the cut face decides)
-            for (unsigned i = 1; i < c; ++i) {
-                const unsigned long long x = seg[i];
-                unsigned j = i;
-                while (j > 0 && seg[j - 1] > x) {
-                    seg[j] = seg[j - 1];
-                    --j;
-                }
-                seg[j] = x;
+    const uint32_t tiles = (nsf + SS_FACES - 1) / SS_FACES;
+    for (uint32_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+        const uint32_t f0 = tile * SS_FACES, f = f0 + threadIdx.x;
+        const uint32_t f1 = f0 + SS_FACES < nsf ? f0 + SS_FACES : nsf;
+        const unsigned lo = __ldg(off + f0), hi = __ldg(off + f1); // (written by k_pair_offsets, an earlier launch)
+        if (hi == lo) continue; // no pair in this tile: its cursors are zero already
+        unsigned c = 0, first = 0;
+        if (f < nsf) {
+            c = cursor[f];
+            if (c) cursor[f] = 0u; // all zero again for the next run
+            first = __ldg(off + f) - lo;
+        }
+        if (!counting || hi > cap) continue;
+        const unsigned span = hi - lo;
+        unsigned long long* seg = span <= SS_SPAN ? sh + first : out + lo + first;
+        if (span <= SS_SPAN) {
+            for (unsigned i = threadIdx.x; i < span; i += SS_FACES) sh[i] = out[lo + i];
+            __syncthreads();
+        }
+        for (unsigned i = 1; i < c; ++i) {
+            const unsigned long long x = seg[i];
+            unsigned j = i;
+            while (j > 0 && seg[j - 1] > x) {
+                seg[j] = seg[j - 1];
+                --j;
             }
+            seg[j] = x;
+        }
+        if (span <= SS_SPAN) {
+            __syncthreads();
+            for (unsigned i = threadIdx.x; i < span; i += SS_FACES) out[lo + i] = sh[i];
+            __syncthreads();
         }
     }
 }
@@ -601,8 +618,8 @@ int sort_pairs(mcb200_ctx* ctx, const mcb200_mesh* src, const mcb200_mesh* cut, 
     MCB_LAUNCH(ctx, k_pair_offsets, tiles, PS_THREADS, 0, cnt, nsf, res->pair_tile.as<unsigned>(), off, c);
     const unsigned grid = (unsigned)ctx->num_sms * 8u;
     MCB_LAUNCH(ctx, k_pair_scatter, grid, 256, 0, res->pairs.as<unsigned long long>(), (unsigned long long)res->cap_pairs, off, cnt, dst, c);
-    const unsigned sgrid = div_up(div_up(nsf, 4), 256) < grid ? div_up(div_up(nsf, 4), 256) : grid;
-    MCB_LAUNCH(ctx, k_pair_segsort, sgrid, 256, 0, dst, off, cnt, nsf, (unsigned long long)res->cap_pairs, c);
+    const unsigned sgrid = div_up(nsf, SS_FACES) < grid * 2u ? div_up(nsf, SS_FACES) : grid * 2u;
+    MCB_LAUNCH(ctx, k_pair_segsort, sgrid, SS_FACES, 0, dst, off, cnt, nsf, (unsigned long long)res->cap_pairs, c);
     res->pairs_order_input = res->pairs.p;
     res->pairs_order_unchecked = true; // fetch_counters looks at pair_seg_max once
     res->pairs_sorted = dst;

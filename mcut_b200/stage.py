@@ -32,6 +32,7 @@ MC_DISPATCH_ENFORCE_GENERAL_POSITION = 1 << 15
 MC_DISPATCH_ENFORCE_GENERAL_POSITION_ABSOLUTE = 1 << 16
 
 NARROW_LOG_TESTS = 1
+NARROW_COUNT_TESTS = 8  # n_tests as the reference counts them (the side prefilter's dismissals are put through the culls too)
 
 STATUS_SUCCESS = 0
 STATUS_GENERAL_POSITION_VIOLATION = 1
@@ -324,11 +325,15 @@ class Result:
 
 
 def intersect_stage(ctx: Context, src, cut, flags: int, gp_constant: float = 1e-4, perturbation=None, log_tests: bool = False,
-                    want_boxes: bool = True, params=None, prior_boxes=(None, None), soup_tables=None) -> Dict[str, object]:
+                    want_boxes: bool = True, params=None, prior_boxes=(None, None), soup_tables=None,
+                    count_tests: bool = False) -> Dict[str, object]:
     """One kernel invocation's intersect stage on user arrays, through the C-ABI with host buffers.
     `src`/`cut` = (xyz[V,3] float32|float64, faces_flat uint32, sizes uint32|None).
     `params` = (com, shift, eps) replaces the frame derived from the arrays (zeros: the arrays are internal coordinates);
-    `prior_boxes` = (src, cut) face boxes the two builds start from (see Mesh.build); `soup_tables`: see Soup."""
+    `prior_boxes` = (src, cut) face boxes the two builds start from (see Mesh.build); `soup_tables`: see Soup.
+    `count_tests`: after the run proper, the narrowphase is repeated with MCB200_NARROW_COUNT_TESTS on the same pairs and
+    its n_tests (= the number of edge/face tests the reference runs) is returned as "n_tests_reference"; the records of
+    that second run must equal the first run's."""
     sx, sf, ss = src
     cx, cf, cs = cut
     if params is None:
@@ -363,6 +368,14 @@ def intersect_stage(ctx: Context, src, cut, flags: int, gp_constant: float = 1e-
     out.update({"cand_faces": faces, "cand_normal": normal, "cand_d": d, "cand_maxcomp": mcmp})
     if log_tests:
         out["tests"] = res.tests()
+        out["n_tests_reference"] = out["n_tests"]
+    elif count_tests:
+        ctx.check(ctx.L.mcb200_narrowphase(ctx.h, soup.h, ms.h, mc.h, res.h, NARROW_COUNT_TESTS))
+        c2 = res.counts()
+        out["n_tests_reference"] = int(c2.n_tests)
+        if int(c2.n_records) != out["n_records"] or int(c2.n_exact) != out["n_exact"] or int(c2.status) != out["status"] \
+                or res.records().tobytes() != out["records"].tobytes():
+            raise Mcb200Error(-1, "the counting run of the narrowphase differs from the plain run")
     for o in (soup, res, ms, mc):
         o.free()
     return out

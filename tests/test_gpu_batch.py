@@ -30,7 +30,7 @@ def run_batch(pairs, nlanes, device=0):
         items[k].cut = HostMesh(0, cx.ctypes.data, cx.shape[0], cf.ctypes.data, None, cf.size // 3)
         items[k].com = None
         items[k].gp_constant = 1e-4
-        items[k].flags = 0
+        items[k].flags = 8  # MCB200_NARROW_COUNT_TESTS: n_tests as the reference counts them
     counts = (Counts * len(pairs))()
     rc = L.mcb200_batch_intersect_host(ctx_arr, res_arr, nlanes, items, len(pairs), counts)
     assert rc == 0, L.mcb200_last_error(lanes[0].h).decode()

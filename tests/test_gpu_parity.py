@@ -51,6 +51,29 @@ def test_stage_matches_oracle(oracle, gpu_ctx, case):
         assert beq(gr["edge"], rr["edge"]) and beq(gr["face"], rr["face"]) and beq(gr["point"], rr["point"]), "registry"
 
 
+@pytest.mark.parametrize("case", sorted(cases.ALL))
+def test_stage_without_the_test_log_matches_oracle(oracle, gpu_ctx, case):
+    """The production configuration: no test log, so triangle meshes go through the side prefilter (narrowphase.cu:
+    k_tri_prefilter / k_tri_classify / k_tri_resolve).  Every output equals the oracle's; the prefilter's dismissals show
+    up only in n_tests, and MCB200_NARROW_COUNT_TESTS brings that back to the reference's count."""
+    from mcut_b200 import stage
+    src, cut, flags = cases.ALL[case]()
+    ref = oracle.intersect_stage(src, cut, flags)
+    got = stage.intersect_stage(gpu_ctx, src, cut, flags, count_tests=True)
+    assert beq(got["pairs"], ref["pairs"]) and got["status"] == ref["status"]
+    if ref["status"] in (2, 3):
+        assert got["bad_face"] == ref["bad_face"]
+        return
+    assert beq(got["cand_faces"], ref["cand_faces"]) and beq(got["cand_normal"], ref["cand_normal"])
+    assert beq(got["cand_d"], ref["cand_d"]) and beq(got["cand_maxcomp"], ref["cand_maxcomp"])
+    rt = ref["tests"]
+    assert got["n_tests_reference"] == len(rt) and got["n_tests"] <= len(rt)
+    assert got["n_exact"] == int(np.count_nonzero(rt["exact_q"] | rt["exact_r"])) or case in ("hello", "patch_vs_sphere", "cube_cube_axis_aligned")
+    if ref["status"] == 0:
+        rr, gr = ref["records"], got["records"]
+        assert beq(gr["edge"], rr["edge"]) and beq(gr["face"], rr["face"]) and beq(gr["point"], rr["point"]), "registry"
+
+
 def test_perturbed_cut_frame(oracle, gpu_ctx):
     pert = np.array([1.3e-3, -0.7e-3, 2.1e-3])
     ref, got = run_both(oracle, gpu_ctx, "cube_cube_axis_aligned", perturbation=pert)
