@@ -331,6 +331,11 @@ int mcb200_batch_intersect_host(mcb200_ctx** ctxs, mcb200_result** results, uint
 int mcb200_staged_soup_read(mcb200_ctx* ctx, uint32_t* face_vtx, uint32_t* face_edge, uint32_t* edge_f, uint32_t capacity_edges,
     uint32_t* nh, uint32_t* ne);
 
+/* Diagnostics: how many items each narrowphase kernel worked on in the last run.  out[0] pairs that went past the side
+ * prefilter (triangle meshes; every pair otherwise), out[1] tests whose stage-A filter failed, out[2] certified plane
+ * crossings, out[3] tests that needed Shewchuk's adaptive stages B-D (inexact coordinate differences). */
+int mcb200_result_queue_counts(mcb200_ctx* ctx, mcb200_result* res, uint64_t out[4]);
+
 /* ---------------------------------------------------------------- reading results (D2H, synchronising) ----- */
 int mcb200_result_counts(mcb200_ctx* ctx, mcb200_result* res, mcb200_counts* out);
 int mcb200_result_read_pairs(mcb200_ctx* ctx, mcb200_result* res, uint64_t* pairs, size_t capacity);

@@ -109,6 +109,7 @@ SYMBOLS = {
     "mcb200_intersect_stage_sharded": (C.c_int, [vp, vp, vp, vp, C.c_double, vp, vp, C.c_uint32]),
     "mcb200_batch_intersect_host": (C.c_int, [C.POINTER(vp), C.POINTER(vp), C.c_uint32, C.POINTER(BatchItem), C.c_uint32,
                                               C.POINTER(Counts)]),
+    "mcb200_result_queue_counts": (C.c_int, [vp, vp, C.POINTER(C.c_uint64)]),
     "mcb200_result_read_pairs": (C.c_int, [vp, vp, c_u64p, C.c_size_t]),
     "mcb200_result_read_records": (C.c_int, [vp, vp, C.POINTER(Record), C.c_size_t]),
     "mcb200_result_read_tests": (C.c_int, [vp, vp, C.POINTER(Test), C.c_size_t]),

@@ -121,7 +121,7 @@ int mcb200_ctx_create(int device, void* stream, mcb200_ctx** out)
     if (const char* e = std::getenv("MCB200_GRAPHS")) ctx->use_graphs = (e[0] != '0');
     if (const char* e = std::getenv("MCB200_TWO_KERNEL_BOXES")) ctx->two_kernel_boxes = (e[0] != '0');
     if (const char* e = std::getenv("MCB200_GRAPH_MAX_FACES")) ctx->graph_max_faces = (size_t)std::atoll(e);
-    if (const char* e = std::getenv("MCB200_MORTON_SORT_BITS")) ctx->morton_sort_bits = (std::atoi(e) >= 30) ? 30 : 24;
+    if (const char* e = std::getenv("MCB200_MORTON_SORT_BITS")) ctx->morton_sort_bits = (std::atoi(e) >= 30) ? 30 : (std::atoi(e) <= 16 ? 16 : 24);
     {
         // keep freed blocks in the stream-ordered pool instead of handing them back to the driver at every synchronisation:
         // a dispatch allocates a few hundred MB of build products, and mapping that memory anew costs far more than the stage
@@ -1308,6 +1308,17 @@ int mcb200_result_counts(mcb200_ctx* ctx, mcb200_result* res, mcb200_counts* out
         res->h_valid = false;
         MCB_FAIL(ctx, MCB200_ERR_CAPACITY, "pair buffer overflow: capacity has been raised, run the stage again");
     }
+    return 0;
+}
+
+int mcb200_result_queue_counts(mcb200_ctx* ctx, mcb200_result* res, uint64_t out[4])
+{
+    if (!ctx || !res || !out) return MCB200_ERR_INVALID;
+    MCB_TRY(fetch_counters(ctx, res));
+    out[0] = res->tri_queues ? res->h.n_mid : res->h.n_pairs;
+    out[1] = res->h.n_queue;
+    out[2] = res->h.n_cross;
+    out[3] = res->h.n_full;
     return 0;
 }
 

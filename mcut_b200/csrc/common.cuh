@@ -95,7 +95,7 @@ struct mcb200_ctx {
     std::vector<std::function<int()>>* recording = nullptr; // MCB_LAUNCH queues here instead of launching (see the macro)
     int morton_sort_bits = 24; // the build sorts the leaves on the top 24 of the 30 Morton bits: 3 radix passes (MCB200_MORTON_SORT_BITS=30: all four)
     bool pdl = true; // programmatic dependent launch between in-stream kernels (MCB200_PDL=0 turns it off)
-    bool sort_smem_opt_in[4] = { false, false, false, false }; // radix_sort.cuh: dynamic shared memory opt-in done
+    bool sort_smem_opt_in[8] = { false, false, false, false, false, false, false, false }; // radix_sort.cuh: dynamic shared memory opt-in done
     bool traverse_smem_opt_in = false;
     bool two_kernel_boxes = false; // MCB200_TWO_KERNEL_BOXES=1: face boxes and Morton codes in two kernels (lbvh.cu)
     // CUDA graphs of stage bodies (api.cu)

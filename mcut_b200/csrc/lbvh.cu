@@ -802,10 +802,10 @@ int lbvh_build(mcb200_ctx* ctx, mcb200_mesh* m, double eps)
     // anyway), so the default sorts 24 bits in three passes; codes that tie are told apart by their position, as equal codes
     // always were.  With an odd number of passes the keys start in the scratch buffer so that the last pass lands in the
     // mesh's own arrays.
-    const int sort_bits = ctx->morton_sort_bits >= 30 ? 32 : 24;
-    const unsigned key_shift = sort_bits == 32 ? 0u : 6u;
+    const int sort_bits = ctx->morton_sort_bits >= 30 ? 32 : (ctx->morton_sort_bits <= 16 ? 16 : 24);
+    const unsigned key_shift = sort_bits == 32 ? 0u : (sort_bits == 16 ? 14u : 6u);
     const rsort::pass_desc pd = rsort::make_passes(0, sort_bits);
-    constexpr int SORT_TILE = rsort::THREADS * rsort::items_for<uint32_t>::value;
+    const int SORT_TILE = rsort::THREADS * rsort::items_rt<uint32_t>(nf);
     const unsigned status_words = (unsigned)rsort::status_rows(((size_t)nf + SORT_TILE - 1) / SORT_TILE) * rsort::RADIX * (unsigned)pd.npasses;
     const bool odd = (pd.npasses & 1) != 0;
     uint32_t* keys_in = odd ? sc.keys_alt.as<uint32_t>() : m->sorted_codes.as<uint32_t>();

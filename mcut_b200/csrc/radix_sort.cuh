@@ -417,11 +417,25 @@ __global__ void __launch_bounds__(THREADS, 3) k_onesweep_pass(const KeyT* __rest
 template <typename KeyT> struct items_for {
     static constexpr int value = sizeof(KeyT) == 4 ? 16 : 8;
 };
+// 32-bit keys: inputs of up to about a million keys are sorted in tiles of half the size.  A pass over so few keys is bound
+// by the latency of one tile's load -> rank -> look-back -> scatter chain, not by bandwidth: twice the blocks per SM hide it.
+inline size_t& small_tile_max()
+{
+    static size_t v = [] {
+        const char* e = std::getenv("MCB200_SORT_SMALL_TILE_MAX");
+        return e ? (size_t)std::atoll(e) : (size_t)0; // measured on C2 (1M keys): 0.331 ms with half tiles, 0.322 ms without - off by default
+    }();
+    return v;
+}
+template <typename KeyT> inline int items_rt(size_t n_max)
+{
+    return (sizeof(KeyT) == 4 && n_max <= small_tile_max()) ? 8 : items_for<KeyT>::value;
+}
 
 // scratch sizes a sort of n_max keys needs in the CURRENT scratch set (so callers can reserve before forking lanes)
 template <typename KeyT> int reserve_scratch(mcb200_ctx* ctx, size_t n_max, int npasses, bool need_alt_keys, bool need_alt_vals)
 {
-    constexpr int TILE = THREADS * items_for<KeyT>::value;
+    const int TILE = THREADS * items_rt<KeyT>(n_max);
     const size_t tiles = (n_max + TILE - 1) / TILE;
     mcb200_ctx::sort_scratch_t& sc = ctx->sc();
     MCB_TRY(ctx->reserve(sc.hist, sizeof(unsigned) * MAX_PASSES * RADIX));
@@ -450,9 +464,13 @@ inline int sort_prepare(mcb200_ctx* ctx)
 template <typename KeyT, typename ValT, bool HAS_VALS>
 int sort_passes(mcb200_ctx* ctx, const KeyT* keys_in, KeyT* keys_a, KeyT* keys_b, const ValT* vals_in, ValT* vals_a, ValT* vals_b,
     const unsigned long long* d_n, size_t n_max, const pass_desc& pd, KeyT** keys_out, ValT** vals_out, size_t skip_le = 0,
-    const unsigned* d_flag = nullptr, unsigned flag_le = 0)
+    const unsigned* d_flag = nullptr, unsigned flag_le = 0);
+
+template <typename KeyT, typename ValT, bool HAS_VALS, int ITEMS>
+int sort_passes_impl(mcb200_ctx* ctx, const KeyT* keys_in, KeyT* keys_a, KeyT* keys_b, const ValT* vals_in, ValT* vals_a, ValT* vals_b,
+    const unsigned long long* d_n, size_t n_max, const pass_desc& pd, KeyT** keys_out, ValT** vals_out, size_t skip_le,
+    const unsigned* d_flag, unsigned flag_le)
 {
-    constexpr int ITEMS = items_for<KeyT>::value;
     constexpr int TILE = THREADS * ITEMS;
     const size_t tiles = (n_max + TILE - 1) / TILE;
     mcb200_ctx::sort_scratch_t& sc = ctx->sc();
@@ -464,7 +482,7 @@ int sort_passes(mcb200_ctx* ctx, const KeyT* keys_in, KeyT* keys_a, KeyT* keys_b
     constexpr size_t smem = pass_smem_bytes<KeyT, ValT, HAS_VALS, ITEMS>();
     {
         // the opt-in is per function and per device; a context is bound to one device
-        const int which = (sizeof(KeyT) == 8 ? 2 : 0) + (HAS_VALS ? 1 : 0);
+        const int which = (sizeof(KeyT) == 8 ? 2 : 0) + (HAS_VALS ? 1 : 0) + (ITEMS != items_for<KeyT>::value ? 4 : 0);
         if (!ctx->sort_smem_opt_in[which]) {
             MCB_CUDA(ctx, cudaFuncSetAttribute(k_onesweep_pass<KeyT, ValT, HAS_VALS, ITEMS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                 (int)smem));
@@ -485,11 +503,23 @@ int sort_passes(mcb200_ctx* ctx, const KeyT* keys_in, KeyT* keys_a, KeyT* keys_b
 }
 
 template <typename KeyT, typename ValT, bool HAS_VALS>
+int sort_passes(mcb200_ctx* ctx, const KeyT* keys_in, KeyT* keys_a, KeyT* keys_b, const ValT* vals_in, ValT* vals_a, ValT* vals_b,
+    const unsigned long long* d_n, size_t n_max, const pass_desc& pd, KeyT** keys_out, ValT** vals_out, size_t skip_le,
+    const unsigned* d_flag, unsigned flag_le)
+{
+    if (sizeof(KeyT) == 4 && items_rt<KeyT>(n_max) == 8)
+        return sort_passes_impl<KeyT, ValT, HAS_VALS, 8>(ctx, keys_in, keys_a, keys_b, vals_in, vals_a, vals_b, d_n, n_max, pd, keys_out,
+            vals_out, skip_le, d_flag, flag_le);
+    return sort_passes_impl<KeyT, ValT, HAS_VALS, items_for<KeyT>::value>(ctx, keys_in, keys_a, keys_b, vals_in, vals_a, vals_b, d_n, n_max,
+        pd, keys_out, vals_out, skip_le, d_flag, flag_le);
+}
+
+template <typename KeyT, typename ValT, bool HAS_VALS>
 int sort(mcb200_ctx* ctx, const KeyT* keys_in, KeyT* keys_a, KeyT* keys_b, const ValT* vals_in, ValT* vals_a, ValT* vals_b,
     const unsigned long long* d_n, size_t n_max, const pass_desc& pd, KeyT** keys_out, ValT** vals_out, size_t skip_le = 0,
     const unsigned* d_flag = nullptr, unsigned flag_le = 0)
 {
-    constexpr int TILE = THREADS * items_for<KeyT>::value;
+    const int TILE = THREADS * items_rt<KeyT>(n_max);
     if (keys_out) *keys_out = const_cast<KeyT*>(keys_in);
     if (vals_out) *vals_out = const_cast<ValT*>(vals_in);
     if (n_max == 0 || pd.npasses == 0) return 0;

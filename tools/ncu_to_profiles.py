@@ -8,7 +8,8 @@ import csv, json, re, subprocess, sys, collections
 
 rep, out = sys.argv[1], sys.argv[2]
 exclude = sys.argv[3].split(",") if len(sys.argv) > 3 else []  # kernel-name prefixes kept out of the share column (other legs of bench.py)
-raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+# (a `--page raw --csv` export works as input too: the GPU box exports it, the report itself is too big to bring back)
+raw = open(rep).read() if rep.endswith(".csv") else subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(raw.splitlines()))
 hdr, units = rows[0], rows[1]
 ix = {h: i for i, h in enumerate(hdr)}
