@@ -343,7 +343,7 @@ def algorithmic_bytes(kname: str, src_nv, src_nf, cut_nv, cut_nf, counts, vbytes
         # boxes; per queued test the entry, the pair, five vertex ids + vertices, the edge id, 32 B per record
         "k_tri_prefilter": (8 + 24 + 6 * vbytes + 2) * n_pairs + 8.0 * counts.get("n_mid", 0),
         "k_tri_classify": (8 + 8 + 24 + 6 * vbytes + 96 + 24 + 48 + 144) * counts.get("n_mid", 0) + 8.0 * (counts.get("n_open", 0) + counts.get("n_cross", 0)),
-        "k_tri_resolve": (8 + 8 + 20 + 5 * vbytes + 4) * (counts.get("n_open", 0) + counts.get("n_cross", 0)) + 32.0 * counts["n_records"],
+        "k_tri_resolve": (8 + 8 + 20 + 5 * vbytes + 4) * (counts.get("n_open", 0) + counts.get("n_cross", 0)) + 32.0 * counts.get("n_records", 0),
         "k_tests_filter_poly": 8.0 * n_pairs + 128.0 * n_tests,
     }
     return table.get(kname)

@@ -93,7 +93,7 @@ struct mcb200_ctx {
     dbuf st_tab_keys, st_hfirst, st_bsum; // device-side polygon-soup numbering (soup_ids.cu)
     size_t st_tab_cap = 0;
     std::vector<std::function<int()>>* recording = nullptr; // MCB_LAUNCH queues here instead of launching (see the macro)
-    int morton_sort_bits = 24; // the build sorts the leaves on the top 24 of the 30 Morton bits: 3 radix passes (MCB200_MORTON_SORT_BITS=30: all four)
+    int morton_sort_bits = 16; // the build orders the leaves by the top 16 of the 30 Morton bits: 2 radix passes (MCB200_MORTON_SORT_BITS=24 / 30: three / four)
     bool pdl = true; // programmatic dependent launch between in-stream kernels (MCB200_PDL=0 turns it off)
     bool sort_smem_opt_in[8] = { false, false, false, false, false, false, false, false }; // radix_sort.cuh: dynamic shared memory opt-in done
     bool traverse_smem_opt_in = false;
