@@ -376,7 +376,7 @@ int mcb200_mesh_validate(mcb200_ctx* ctx, mcb200_mesh* mesh, mcb200_validation* 
     if (!ctx || !mesh || !out) return MCB200_ERR_INVALID;
     MCB_CUDA(ctx, cudaSetDevice(ctx->device));
     ctx->use_main();
-    MCB_TRY(mesh_validate_run(ctx, mesh));
+    if (!mesh->validated) MCB_TRY(mesh_validate_run(ctx, mesh)); // (a mesh's faces never change; asking twice costs one read-back)
     uint32_t info[4];
     MCB_CUDA(ctx, cudaMemcpyAsync(info, mesh->cc_info.p, sizeof(info), cudaMemcpyDeviceToHost, ctx->stream));
     MCB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));

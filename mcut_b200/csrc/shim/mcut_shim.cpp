@@ -88,12 +88,19 @@ std::vector<mcb200_ctx*> g_idle_ctx; // device contexts whose API thread has end
 // When the API thread ends (mcReleaseContext) its device objects are released and the device context is parked for the next
 // API thread: a program that creates an MCUT context per dispatch keeps its reserved device buffers instead of mapping a few
 // hundred MB anew each time.
+struct early_mesh_t { // a device mesh made for the input checks, before build_oibvh asked for one (adopted there)
+    mcb200_mesh* mesh = nullptr;
+    capture_t cap;
+};
 struct thread_state_t {
     mcb200_ctx* ctx = nullptr;
     std::deque<const void*> recent; // keys of the trees this thread built, oldest first
+    std::unordered_map<const hmesh_t*, early_mesh_t> early;
     ~thread_state_t()
     {
         if (!ctx) return;
+        for (auto& kv : early) mcb200_mesh_free(ctx, kv.second.mesh);
+        early.clear();
         if (t_last.res) mcb200_result_free(t_last.ctx, t_last.res);
         if (t_last.soup) mcb200_soup_free(t_last.ctx, t_last.soup);
         t_last = last_intersect_t();
@@ -173,6 +180,46 @@ bool capture_matches(const capture_t& c, const hmesh_t& mesh)
     return true;
 }
 
+bool same_capture(const capture_t& a, const capture_t& b)
+{
+    if (a.xyz != b.xyz || a.faces != b.faces || a.sizes != b.sizes || a.nv != b.nv || a.nf != b.nf || a.is_float != b.is_float
+        || a.has_pert != b.has_pert)
+        return false;
+    for (int j = 0; j < 3; ++j)
+        if (a.com[j] != b.com[j] || a.shift[j] != b.shift[j] || a.pert[j] != b.pert[j]) return false;
+    return true;
+}
+
+void drop_early_mesh(const hmesh_t* key)
+{
+    auto it = t_state.early.find(key);
+    if (it == t_state.early.end()) return;
+    mcb200_mesh_free(t_state.ctx, it->second.mesh);
+    t_state.early.erase(it);
+}
+
+// The device copy of a half-edge mesh that is still exactly what the user's arrays say (or nullptr): made on first use,
+// handed over to build_oibvh when the reference gets there.
+mcb200_mesh* early_device_mesh(const hmesh_t& mesh, const capture_t** cap_out)
+{
+    auto cap = t_captures.find(&mesh);
+    if (cap == t_captures.end() || !capture_matches(cap->second, mesh)) return nullptr;
+    const capture_t& c = cap->second;
+    if (cap_out) *cap_out = &c;
+    auto it = t_state.early.find(&mesh);
+    if (it != t_state.early.end()) {
+        if (same_capture(it->second.cap, c)) return it->second.mesh;
+        drop_early_mesh(&mesh);
+    }
+    mcb200_ctx* ctx = thread_ctx();
+    early_mesh_t e;
+    e.cap = c;
+    check(ctx, mcb200_mesh_create_trusted(ctx, c.is_float, c.xyz, c.nv, c.faces, c.sizes, c.nf, &e.mesh), "mesh_create");
+    check(ctx, mcb200_mesh_set_frame(ctx, e.mesh, c.com, c.shift, c.has_pert ? c.pert : nullptr), "set_frame");
+    t_state.early[&mesh] = e;
+    return e.mesh;
+}
+
 } // namespace
 
 // source/preproc.cpp:57-468: called through the PLT by preproc() for the source mesh (:2338) and for the cut mesh of every
@@ -204,9 +251,97 @@ bool client_input_arrays_to_hmesh(std::shared_ptr<context_t>& context_ptr, McFla
         }
         c.has_pert = perturbation != nullptr;
     }
+    if (t_state.ctx) drop_early_mesh(&halfedgeMesh); // whatever lived at this address before is gone
     t_captures[&halfedgeMesh] = c; // a failed conversion leaves an empty capture: generic path
     t_latest_capture = c;
     return ok;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Input validation, PLT-called by preproc(): answered from the device copy of the user's arrays.
+// MCB200_SHIM_HOST_CHECKS=1 leaves all three to the reference.
+// ---------------------------------------------------------------------------------------------------------------------
+static bool host_checks()
+{
+    static const bool v = std::getenv("MCB200_SHIM_HOST_CHECKS") != nullptr;
+    return v;
+}
+
+// source/preproc.cpp:505-578 (called at :2353, :2786, :2797).  Triangle meshes only: the coplanarity warning loop (:552-575)
+// has nothing to look at then; the vertex / face count checks and polygon meshes stay with the reference's function.
+bool check_input_mesh(std::shared_ptr<context_t>& context_ptr, const hmesh_t& m)
+{
+    typedef bool (*fn_t)(std::shared_ptr<context_t>&, const hmesh_t&);
+    static fn_t real = reinterpret_cast<fn_t>(dlsym(RTLD_NEXT, "_Z16check_input_meshRSt10shared_ptrI9context_tERK7hmesh_t"));
+    if (!real) throw std::runtime_error("mcut_b200: the reference's check_input_mesh was not found");
+    if (host_checks() || m.number_of_vertices() < 3 || m.number_of_faces() < 1) return real(context_ptr, m);
+    const capture_t* c = nullptr;
+    mcb200_mesh* dm = early_device_mesh(m, &c);
+    if (!dm || c->sizes != nullptr) return real(context_ptr, m);
+    scope_timer timer("check_input_mesh (device)");
+    mcb200_validation v;
+    if (mcb200_mesh_validate(t_state.ctx, dm, &v) != 0) return real(context_ptr, m);
+    if (v.n_components != 1) { // :541-550
+        context_ptr->dbg_cb(MC_DEBUG_SOURCE_API, MC_DEBUG_TYPE_ERROR, 0, MC_DEBUG_SEVERITY_HIGH,
+            "Detected multiple connected components in mesh (N=" + std::to_string(v.n_components) + ")");
+        return false;
+    }
+    return true;
+}
+
+// source/preproc.cpp:1957-1990 (called at :2805, :2814): no border edge
+bool mesh_is_closed(const hmesh_t& mesh)
+{
+    typedef bool (*fn_t)(const hmesh_t&);
+    static fn_t real = reinterpret_cast<fn_t>(dlsym(RTLD_NEXT, "_Z14mesh_is_closedRK7hmesh_t"));
+    if (!real) throw std::runtime_error("mcut_b200: the reference's mesh_is_closed was not found");
+    if (host_checks()) return real(mesh);
+    // only the copy check_input_mesh just made, or the tree build_oibvh holds, is consulted: no upload for this question alone
+    mcb200_mesh* dm = nullptr;
+    auto early = t_state.early.find(&mesh);
+    auto cap = t_captures.find(&mesh);
+    if (early != t_state.early.end() && cap != t_captures.end() && same_capture(early->second.cap, cap->second) && capture_matches(cap->second, mesh))
+        dm = early->second.mesh;
+    if (!dm && cap != t_captures.end() && capture_matches(cap->second, mesh)) {
+        std::lock_guard<std::mutex> lk(g_mutex);
+        for (const void* key : t_state.recent) {
+            auto it = g_trees.find(key);
+            if (it != g_trees.end() && it->second.from_arrays && it->second.ctx == t_state.ctx && same_capture(it->second.cap, cap->second))
+                dm = it->second.mesh;
+        }
+    }
+    if (!dm) return real(mesh);
+    scope_timer timer("mesh_is_closed (device)");
+    mcb200_validation v;
+    if (mcb200_mesh_validate(t_state.ctx, dm, &v) != 0) return real(mesh);
+    return v.is_closed != 0;
+}
+
+// source/preproc.cpp:1999-2122 (called at :2891 when the BVHs do not overlap and at :3716 when the surfaces do not cut each
+// other): the inside / outside verdict for MC_DISPATCH_INCLUDE_INTERSECTION_TYPE, from the two device trees of this dispatch.
+void check_and_store_input_mesh_intersection_type(std::shared_ptr<context_t>& context_ptr, const std::shared_ptr<hmesh_t>& source_hmesh,
+    const std::shared_ptr<hmesh_t>& cut_hmesh, const bool sm_is_watertight, const bool cm_is_watertight,
+    const bounding_box_t<vec3_<double>>& sm_aabb, const bounding_box_t<vec3_<double>>& cm_aabb, const double multiplier)
+{
+    typedef void (*fn_t)(std::shared_ptr<context_t>&, const std::shared_ptr<hmesh_t>&, const std::shared_ptr<hmesh_t>&, const bool,
+        const bool, const bounding_box_t<vec3_<double>>&, const bounding_box_t<vec3_<double>>&, const double);
+    static fn_t real = reinterpret_cast<fn_t>(dlsym(RTLD_NEXT,
+        "_Z44check_and_store_input_mesh_intersection_typeRSt10shared_ptrI9context_tERKS_I7hmesh_tES6_bbRK14bounding_box_tI5vec3_IdEESC_d"));
+    if (!real) throw std::runtime_error("mcut_b200: the reference's check_and_store_input_mesh_intersection_type was not found");
+    // the two trees the last intersectOIBVHs of this thread worked with are this dispatch's meshes as they are NOW (the cut
+    // mesh of the last general-position attempt); both must be the user's own arrays on the device
+    const bool usable = !host_checks() && t_last.ctx && t_last.src && t_last.cut && t_last.src_from_arrays && t_last.cut_from_arrays
+        && t_last.src_cap.nv == (uint32_t)source_hmesh->number_of_vertices() && t_last.src_cap.nf == (uint32_t)source_hmesh->number_of_faces()
+        && t_last.cut_cap.nv == (uint32_t)cut_hmesh->number_of_vertices() && t_last.cut_cap.nf == (uint32_t)cut_hmesh->number_of_faces();
+    if (usable) {
+        scope_timer timer("intersection type (device)");
+        uint32_t type = 0;
+        if (mcb200_intersection_type_without_cut(t_last.ctx, t_last.src, t_last.cut, &type) == 0) {
+            context_ptr->set_most_recent_dispatch_intersection_type((McDispatchIntersectionType)type);
+            return;
+        } // (faces with more than four vertices need the reference's CDT: the host function answers)
+    }
+    real(context_ptr, source_hmesh, cut_hmesh, sm_is_watertight, cm_is_watertight, sm_aabb, cm_aabb, multiplier);
 }
 
 void build_oibvh(thread_pool& /*pool*/, const hmesh_t& mesh, std::vector<bbox_t>& bvhAABBs, std::vector<fd_t>& bvhLeafNodeFaces,
@@ -238,9 +373,15 @@ void build_oibvh(thread_pool& /*pool*/, const hmesh_t& mesh, std::vector<bbox_t>
         // fast path: the device reads the user's own arrays and applies the frame itself — no walk over the half-edge mesh
         // (the conversion itself has range-checked every index, preproc.cpp:271 / :417, and returned true)
         const capture_t& c = cap->second;
-        scope_timer t2("  build_oibvh: upload of the user's arrays");
-        check(ctx, mcb200_mesh_create_trusted(ctx, c.is_float, c.xyz, c.nv, c.faces, c.sizes, c.nf, &t.mesh), "mesh_create");
-        check(ctx, mcb200_mesh_set_frame(ctx, t.mesh, c.com, c.shift, c.has_pert ? c.pert : nullptr), "set_frame");
+        auto early = t_state.early.find(&mesh);
+        if (early != t_state.early.end() && same_capture(early->second.cap, c)) {
+            t.mesh = early->second.mesh; // the input checks have uploaded it already (check_input_mesh below)
+            t_state.early.erase(early);
+        } else {
+            scope_timer t2("  build_oibvh: upload of the user's arrays");
+            check(ctx, mcb200_mesh_create_trusted(ctx, c.is_float, c.xyz, c.nv, c.faces, c.sizes, c.nf, &t.mesh), "mesh_create");
+            check(ctx, mcb200_mesh_set_frame(ctx, t.mesh, c.com, c.shift, c.has_pert ? c.pert : nullptr), "set_frame");
+        }
         t.from_arrays = true;
         t.cap = c;
     } else {

@@ -301,3 +301,70 @@ def test_contexts_in_parallel_through_the_drop_in(tmp_path, case):
     for k in ("cc_type", "cc_attrs", "cc_nv", "cc_nf", "cc_vertices", "cc_faces", "cc_face_sizes"):
         assert a[k].shape == b[k].shape and a[k].tobytes() == b[k].tobytes(), k
     assert components_equivalent(a, c, 0.0)
+
+
+# ---- input validation answered from the device (check_input_mesh, mesh_is_closed, the intersection-type
+# verdict are PLT-called by preproc() and interposed by the adapter) ----
+ITYPE_FLAG = 1 << 17  # MC_DISPATCH_INCLUDE_INTERSECTION_TYPE (mcut.h:440)
+
+
+def _two_spheres(k, r_src, r_cut, centre_cut):
+    from mcut_b200 import meshgen as mg
+    src = mg.cube_sphere(k, r_src)
+    cut = mg.cube_sphere(k, r_cut, rotation=mg.rot_z(0.2), centre=centre_cut)
+    return (src[0], src[1], None), (cut[0], cut[1], None)
+
+
+@needs_ref
+@pytest.mark.parametrize("name,geometry", [
+    ("cut_inside_src", (8, 10.0, 3.0, (0.5, 0.2, -0.3))),  # both watertight, no contact: INSIDE_SOURCEMESH, two winding numbers asked
+    ("src_inside_cut", (8, 3.0, 10.0, (0.5, 0.2, -0.3))),
+    ("apart", (8, 3.0, 3.0, (20.0, 1.0, 0.0))),  # the BVHs do not overlap: preproc.cpp:2891
+    ("boxes_overlap_surfaces_apart", (8, 3.0, 0.3, (2.6, 2.6, 2.6))),  # inside the source's AABB, outside the sphere
+    ("crossing", (8, 3.0, 3.0, (2.0, 0.5, 0.0))),  # STANDARD
+])
+def test_input_checks_and_intersection_type_from_the_device(tmp_path, name, geometry):
+    from mcut_b200 import meshgen as mg
+    src, cut = _two_spheres(*geometry)
+    flags = mg.MC_DISPATCH_VERTEX_ARRAY_DOUBLE | mg.MC_DISPATCH_ENFORCE_GENERAL_POSITION | ITYPE_FLAG
+    a = run_driver(str(tmp_path), "ref", src, cut, flags, [NODUMP])
+    os.environ["MCB200_SHIM_TIMING"] = "1"
+    try:
+        b = run_driver(str(tmp_path), "b200", src, cut, flags, [SHIM, NODUMP])
+        os.environ["MCB200_SHIM_HOST_CHECKS"] = "1"
+        c = run_driver(str(tmp_path), "b200_host_checks", src, cut, flags, [SHIM, NODUMP])
+    finally:
+        os.environ.pop("MCB200_SHIM_TIMING", None)
+        os.environ.pop("MCB200_SHIM_HOST_CHECKS", None)
+    for got in (b, c):
+        assert int(a["mcDispatch_result"][0]) == int(got["mcDispatch_result"][0]) == 0
+        assert int(a["intersection_type"][0]) == int(got["intersection_type"][0]), name
+        for k in ("cc_type", "cc_attrs", "cc_nv", "cc_nf", "cc_vertices", "cc_faces", "cc_face_sizes"):
+            assert a[k].shape == got[k].shape and a[k].tobytes() == got[k].tobytes(), k
+    # the device really answered: the adapter's timers name the three interposed functions
+    err = b["_stderr"]
+    assert "check_input_mesh (device)" in err and "mesh_is_closed (device)" in err
+    if name != "crossing":
+        assert "intersection type (device)" in err
+    assert "(device)" not in c["_stderr"]
+
+
+@needs_ref
+def test_two_components_are_rejected_by_the_device_check(tmp_path):
+    """check_input_mesh: "Detected multiple connected components in mesh" (preproc.cpp:541-550) -> mcDispatch fails the same way
+    with the component count coming from the device."""
+    from mcut_b200 import meshgen as mg
+    s1 = mg.cube_sphere(6, 2.0)
+    s2 = mg.cube_sphere(6, 2.0, centre=(10.0, 0.0, 0.0))
+    src = (np.concatenate([s1[0], s2[0]]), np.concatenate([s1[1], s2[1] + np.uint32(s1[0].shape[0])]).astype(np.uint32), None)
+    c = mg.cube_sphere(6, 2.0, centre=(1.0, 0.5, 0.0))
+    cut = (c[0], c[1], None)
+    flags = mg.MC_DISPATCH_VERTEX_ARRAY_DOUBLE
+    a = run_driver(str(tmp_path), "ref", src, cut, flags, [NODUMP])
+    os.environ["MCB200_SHIM_TIMING"] = "1"
+    try:
+        b = run_driver(str(tmp_path), "b200", src, cut, flags, [SHIM, NODUMP])
+    finally:
+        os.environ.pop("MCB200_SHIM_TIMING", None)
+    assert int(a["mcDispatch_result"][0]) == int(b["mcDispatch_result"][0]) != 0
+    assert "check_input_mesh (device)" in b["_stderr"]
