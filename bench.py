@@ -850,6 +850,11 @@ def run_ours(args):
                 cpu = {"value": npairs_ref / (ms * 1e-3), "unit": UNIT, "cores": 1, "kind": "port", "ms_per_step": ms,
                        "pairs": npairs_ref, "sample": "1 run of the single-threaded oracle port on the full workload"}
 
+    # ---- e2e_dropin (--dropin): what a LIVE mcDispatch pays for the stage through the adapter + hooked kernel ----
+    dropin = None
+    if rank == 0 and args.dropin:
+        dropin = measure_dropin(src, cut, flags)
+
     if rank == 0:
         cfg.update({"pairs_per_dispatch": counts["n_pairs"], "src_faces": R.src_nf, "cut_faces": R.cut_nf,
                     "l2": "256 MiB write between timed steps", **counts, "status": status})
@@ -862,6 +867,8 @@ def run_ours(args):
         }
         if sharded:
             line["sharded"] = sharded
+        if dropin:
+            line["e2e_dropin"] = dropin
         sys.stdout.flush()
         os.dup2(real_stdout, 1)
         print(json.dumps(line), flush=True)
@@ -869,6 +876,40 @@ def run_ours(args):
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def measure_dropin(src, cut, flags):
+    """Two whole mcDispatch calls of the workload through the public C API of the HOOKED reference build
+    (oracle/_ref/api_driver_hooked: unmodified objects + kernel.cpp with its narrowphase region replaced by one call) with
+    the adapter loaded; the adapter's own wall-clock timers (MCB200_SHIM_TIMING) of the SECOND dispatch are summed.  The
+    rest of mcDispatch is the reference's host code and takes tens of seconds at BASELINE sizes, hence opt-in."""
+    drv = os.path.join(ROOT, "oracle", "_ref", "api_driver_hooked")
+    nodump = os.path.join(ROOT, "oracle", "_ref", "libnodump.so")
+    if not (os.path.exists(drv) and os.path.exists(nodump)):
+        return {"unavailable": "oracle/_ref/api_driver_hooked is not built (needs /root/reference at build time)"}
+    with tempfile.TemporaryDirectory() as td:
+        write_input(src, cut, flags, os.path.join(td, "in.mcb"))
+        env = dict(os.environ, LD_PRELOAD=nodump, MCB200_SHIM_TIMING="1")
+        t0 = time.perf_counter()
+        r = subprocess.run([drv, os.path.join(td, "in.mcb"), os.path.join(td, "out.mcb"), "--repeat", "2"], capture_output=True, text=True,
+                           cwd=td, env=env)
+        wall = time.perf_counter() - t0
+        if r.returncode != 0:
+            return {"unavailable": "api_driver_hooked failed: " + r.stderr[-300:]}
+    entries = []  # (name, ms) of the top-level adapter entries (sub-steps are indented in the log)
+    for ln in r.stderr.splitlines():
+        if ln.startswith("[mcut_b200 shim] ") and not ln.startswith("[mcut_b200 shim]   "):
+            name, _, ms = ln[len("[mcut_b200 shim] "):].rpartition(": ")
+            entries.append((name, float(ms.split()[0])))
+    half = len(entries) // 2
+    second = entries[half:]
+    by_name = {}
+    for name, ms in second:
+        by_name[name] = by_name.get(name, 0.0) + ms
+    return {"stage_ms_per_mcdispatch": sum(ms for _, ms in second), "adapter_entries_ms": by_name,
+            "first_dispatch_stage_ms": sum(ms for _, ms in entries[:half]), "process_wall_s_for_2_dispatches": wall,
+            "call": "mcDispatch (public C API) -> hooked libmcut -> libmcut_b200_shim -> C-ABI",
+            "note": "user arrays are pageable host memory; includes uploads, device work, read-backs and filling the reference's own containers"}
 
 
 def main():
@@ -882,6 +923,7 @@ def main():
     ap.add_argument("--lanes", type=int, default=0, help="batch workloads: contexts in flight per GPU")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-sharded-c5", action="store_true")
+    ap.add_argument("--dropin", action="store_true", help="also time a live mcDispatch through the adapter (adds about a minute)")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3

@@ -331,6 +331,22 @@ int mcb200_batch_intersect_host(mcb200_ctx** ctxs, mcb200_result** results, uint
 int mcb200_staged_soup_read(mcb200_ctx* ctx, uint32_t* face_vtx, uint32_t* face_edge, uint32_t* edge_f, uint32_t capacity_edges,
     uint32_t* nh, uint32_t* ne);
 
+/* ---------------------------------------------------------------- cut-path segment table ------ */
+/* The first consumer of the registry, "Create edges with intersection points" (source/kernel.cpp:3332-3617), works from
+ * cutpath_edge_creation_info: the intersection points grouped by {source-mesh face, cut-mesh face} (kernel.cpp:2603-2633).
+ * mcb200_cutpath_segments makes that table on the device from the last narrowphase's registry (canonical order: vertex i =
+ * record i): groups in ascending (sm face, cm face) order like the reference's ordered map, a group's points in registry
+ * order, groups of more than two points in order along their line (linear_projection_sort, kernel.cpp:1496-1531).  A
+ * group of two points is one cut-path edge; n_single_point_groups > 0 is the reference's late general-position violation
+ * (:3366-3440).  mcb200_cutpath_read: keys[g] = sm face << 32 | cm face (polygon-soup ids), offsets[n_groups + 1],
+ * vertices[n_entries] = registry indices.  The m0 bookkeeping that follows stays host code. */
+typedef struct mcb200_cutpath_counts {
+    uint64_t n_groups, n_entries, n_single_point_groups;
+} mcb200_cutpath_counts;
+int mcb200_cutpath_segments(mcb200_ctx* ctx, const mcb200_soup* soup, mcb200_result* res, mcb200_cutpath_counts* out);
+int mcb200_cutpath_read(mcb200_ctx* ctx, mcb200_result* res, uint64_t* keys, uint32_t* offsets, uint32_t* vertices, size_t cap_groups,
+    size_t cap_entries);
+
 /* Diagnostics: how many items each narrowphase kernel worked on in the last run.  out[0] pairs that went past the side
  * prefilter (triangle meshes; every pair otherwise), out[1] tests whose stage-A filter failed, out[2] certified plane
  * crossings, out[3] tests that needed Shewchuk's adaptive stages B-D (inexact coordinate differences). */

@@ -15,6 +15,11 @@ CSRC = os.path.join(_HERE, "csrc")
 
 c_dp = C.POINTER(C.c_double)
 c_u32p = C.POINTER(C.c_uint32)
+
+
+class CutpathCounts(C.Structure):
+    _fields_ = [("n_groups", C.c_uint64), ("n_entries", C.c_uint64), ("n_single_point_groups", C.c_uint64)]
+
 c_u64p = C.POINTER(C.c_uint64)
 c_i32p = C.POINTER(C.c_int32)
 vp = C.c_void_p
@@ -110,6 +115,8 @@ SYMBOLS = {
     "mcb200_batch_intersect_host": (C.c_int, [C.POINTER(vp), C.POINTER(vp), C.c_uint32, C.POINTER(BatchItem), C.c_uint32,
                                               C.POINTER(Counts)]),
     "mcb200_result_queue_counts": (C.c_int, [vp, vp, C.POINTER(C.c_uint64)]),
+    "mcb200_cutpath_segments": (C.c_int, [vp, vp, vp, C.POINTER(CutpathCounts)]),
+    "mcb200_cutpath_read": (C.c_int, [vp, vp, C.POINTER(C.c_uint64), c_u32p, c_u32p, C.c_size_t, C.c_size_t]),
     "mcb200_result_read_pairs": (C.c_int, [vp, vp, c_u64p, C.c_size_t]),
     "mcb200_result_read_records": (C.c_int, [vp, vp, C.POINTER(Record), C.c_size_t]),
     "mcb200_result_read_tests": (C.c_int, [vp, vp, C.POINTER(Test), C.c_size_t]),

@@ -610,7 +610,7 @@ void mcb200_result_free(mcb200_ctx* ctx, mcb200_result* r)
 {
     if (!ctx || !r) return;
     cudaSetDevice(ctx->device);
-    dbuf* all[] = { &r->counters, &r->pairs, &r->pairs_a, &r->pairs_b, &r->pair_cnt, &r->pair_off, &r->pair_tile, &r->cand_flag, &r->plane, &r->plane_mc, &r->exact_queue, &r->mid_queue, &r->records, &r->rec_keys,
+    dbuf* all[] = { &r->counters, &r->pairs, &r->pairs_a, &r->pairs_b, &r->pair_cnt, &r->pair_off, &r->pair_tile, &r->cand_flag, &r->plane, &r->plane_mc, &r->exact_queue, &r->mid_queue, &r->cp_keys, &r->cp_idx, &r->cp_head, &r->cp_rank, &r->cp_tile, &r->cp_seg_key, &r->cp_seg_off, &r->cp_seg_vtx, &r->cp_info, &r->records, &r->rec_keys,
         &r->rec_idx, &r->records_sorted, &r->tests, &r->tests_sorted, &r->test_keys, &r->test_idx };
     for (dbuf* b : all) ctx->release(*b);
     delete r;

@@ -300,6 +300,10 @@ struct mcb200_result {
     dbuf plane_mc; // i32 per ps face
     dbuf exact_queue; // u64 test keys needing the exact stage
     dbuf mid_queue; // u64 [cap_pairs], triangle meshes only (narrowphase.cu: k_tri_prefilter)
+    // cut-path segment table (cutpath.cu)
+    dbuf cp_keys, cp_idx, cp_head, cp_rank, cp_tile, cp_seg_key, cp_seg_off, cp_seg_vtx, cp_info;
+    size_t cp_groups = 0, cp_entries = 0;
+    bool cp_valid = false;
     size_t cap_exact = 0;
     bool tri_queues = false; // the last narrowphase used the triangle pipeline (split exact queue + mid queue)
     dbuf records; // mcb200_record [cap_records]

@@ -33,6 +33,9 @@ int stage_body(mcb200_ctx* ctx, mcb200_mesh* src, mcb200_mesh* cut, double cut_e
     bool wait_uploads, int number_soup, bool interleave, bool order = true);
 int fetch_counters(mcb200_ctx* ctx, mcb200_result* res);
 bool narrow_queue_overflow(const mcb200_result* res, const result_counters_t& h);
+// traverse.cu: off[i] = cnt[0] + ... + cnt[i-1], off[n] = total; both arrays padded to a multiple of 8 entries (+8) with zeros behind
+// n; `tile` needs n / 2048 + 2 words.  cnt is zeroed on the way (it is the pair order's scatter cursor).
+int exclusive_scan_u32(mcb200_ctx* ctx, unsigned* cnt, uint32_t n, unsigned* tile, unsigned* off, result_counters_t* counters);
 // soup_ids.cu
 int soup_number_reserve(mcb200_ctx* ctx, const mcb200_mesh* src, const mcb200_mesh* cut, mcb200_soup* soup);
 int soup_number_device(mcb200_ctx* ctx, const mcb200_mesh* src, const mcb200_mesh* cut, mcb200_soup* soup, result_counters_t* counters);

@@ -195,4 +195,26 @@ static inline void mcb200_hook_finish(const hmesh_t& ps, int sm_vtx_cnt, int sm_
     mcb200_hook_dump(who, 0, nullptr, nullptr, nullptr, nullptr, rec.data(), rec.size());
     mcb200_hook_fill_registry(ps, sm_vtx_cnt, sm_face_count, rec.data(), rec.size(), m0, m0_ivtx_to_intersection_registry_entry,
         cm_border_reentrant_ivtx_list, ps_intersecting_edges, cutpath_edge_creation_info, ps_iface_to_ivtx_list, partial_cut_detected);
+    if (const char* path = getenv("MCB200_HOOK_DUMP_CUTPATH")) {
+        // what "Create edges with intersection points" (kernel.cpp:3332-3617) is about to consume, for tests/test_oracle_cutpath.py:
+        // the registry in its final order (+ the faces of every tested edge) and cutpath_edge_creation_info as the live dispatch holds it
+        if (FILE* fp = fopen(path, "w")) {
+            const uint32_t base = (uint32_t)m0.number_of_vertices() - (uint32_t)rec.size();
+            fprintf(fp, "R %zu %d\n", rec.size(), sm_face_count);
+            for (const mcb200_record& r : rec) {
+                const fd_t f0 = ps.face(ps.halfedge(ed_t(r.edge), 0)), f1 = ps.face(ps.halfedge(ed_t(r.edge), 1));
+                unsigned long long b[3];
+                memcpy(b, r.point, 24);
+                fprintf(fp, "%u %u %u %u %016llx %016llx %016llx\n", r.edge, r.face, f0 == hmesh_t::null_face() ? 0xFFFFFFFFu : (uint32_t)f0,
+                    f1 == hmesh_t::null_face() ? 0xFFFFFFFFu : (uint32_t)f1, b[0], b[1], b[2]);
+            }
+            fprintf(fp, "G %zu\n", cutpath_edge_creation_info.size());
+            for (const auto& kv : cutpath_edge_creation_info) {
+                fprintf(fp, "%u %u %zu", (uint32_t)kv.first.first, (uint32_t)kv.first.second, kv.second.size());
+                for (const vd_t& v : kv.second) fprintf(fp, " %u", (uint32_t)v - base);
+                fprintf(fp, "\n");
+            }
+            fclose(fp);
+        }
+    }
 }

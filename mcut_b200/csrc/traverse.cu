@@ -590,6 +590,14 @@ int traverse_pairs(mcb200_ctx* ctx, const mcb200_mesh* src, const mcb200_mesh* c
     return 0;
 }
 
+int exclusive_scan_u32(mcb200_ctx* ctx, unsigned* cnt, uint32_t n, unsigned* tile, unsigned* off, result_counters_t* counters)
+{
+    const unsigned tiles = div_up(n, PS_TILE);
+    MCB_LAUNCH(ctx, k_pair_tilesum, tiles, PS_THREADS, 0, cnt, n, tile);
+    MCB_LAUNCH(ctx, k_pair_offsets, tiles, PS_THREADS, 0, cnt, n, tile, off, counters);
+    return 0;
+}
+
 int sort_pairs_reserve(mcb200_ctx* ctx, const mcb200_mesh* src, const mcb200_mesh* cut, mcb200_result* res)
 {
     const rsort::pass_desc pd = pair_passes(src->nf, cut->nf);

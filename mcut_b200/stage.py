@@ -289,6 +289,16 @@ class Result:
         self.ctx.check(self.ctx.L.mcb200_result_read_records(self.ctx.h, self.h, out.ctypes.data_as(C.POINTER(Record)), n))
         return out
 
+    def cutpath(self, soup) -> Dict[str, object]:
+        """Cut-path segment table of the registry (mcb200_cutpath_segments + mcb200_cutpath_read)."""
+        cc = _lib.CutpathCounts()
+        self.ctx.check(self.ctx.L.mcb200_cutpath_segments(self.ctx.h, soup.h, self.h, C.byref(cc)))
+        g, m = int(cc.n_groups), int(cc.n_entries)
+        keys, off, vtx = np.zeros(g, dtype=np.uint64), np.zeros(g + 1, dtype=np.uint32), np.zeros(m, dtype=np.uint32)
+        self.ctx.check(self.ctx.L.mcb200_cutpath_read(self.ctx.h, self.h, keys.ctypes.data_as(C.POINTER(C.c_uint64)), _u32p(off),
+                                                      _u32p(vtx) if m else None, g, m))
+        return {"keys": keys, "off": off, "vtx": vtx, "n_single": int(cc.n_single_point_groups)}
+
     def tests(self) -> np.ndarray:
         # the log count is not part of mcb200_counts; ask with a generous capacity = n_tests
         n = int(self.counts().n_tests)
@@ -326,7 +336,7 @@ class Result:
 
 def intersect_stage(ctx: Context, src, cut, flags: int, gp_constant: float = 1e-4, perturbation=None, log_tests: bool = False,
                     want_boxes: bool = True, params=None, prior_boxes=(None, None), soup_tables=None,
-                    count_tests: bool = False) -> Dict[str, object]:
+                    count_tests: bool = False, want_cutpath: bool = False) -> Dict[str, object]:
     """One kernel invocation's intersect stage on user arrays, through the C-ABI with host buffers.
     `src`/`cut` = (xyz[V,3] float32|float64, faces_flat uint32, sizes uint32|None).
     `params` = (com, shift, eps) replaces the frame derived from the arrays (zeros: the arrays are internal coordinates);
@@ -366,6 +376,8 @@ def intersect_stage(ctx: Context, src, cut, flags: int, gp_constant: float = 1e-
         out["cut_bboxes"], out["cut_root"] = mc.read_bvh()
     faces, normal, d, mcmp = res.planes()
     out.update({"cand_faces": faces, "cand_normal": normal, "cand_d": d, "cand_maxcomp": mcmp})
+    if want_cutpath and int(c.status) == 0:
+        out["cutpath"] = res.cutpath(soup)
     if log_tests:
         out["tests"] = res.tests()
         out["n_tests_reference"] = out["n_tests"]

@@ -1567,3 +1567,106 @@ double mco_winding_number(const double* xyz, const uint32_t* face_off, const uin
     }
     return wn;
 }
+
+
+/* ---- cut-path segment table ------------------------------------------------------------------------------ */
+typedef struct {
+    uint64_t key;
+    uint32_t v;
+} cp_entry_t;
+
+static int cp_entry_cmp(const void* a, const void* b)
+{
+    const cp_entry_t *x = (const cp_entry_t*)a, *y = (const cp_entry_t*)b;
+    if (x->key != y->key) return x->key < y->key ? -1 : 1;
+    return x->v < y->v ? -1 : (x->v > y->v ? 1 : 0);
+}
+
+/* source/kernel.cpp:1496-1531 with the arithmetic of math.h:635-642 (dot product accumulated from 0.0 in x, y, z order),
+ * :718-721 (normalize = v / sqrt(dot(v, v))); std::sort on a handful of elements is an insertion sort */
+static void cp_linear_projection_sort(const mco_record_t* rec, uint32_t* v, uint32_t n)
+{
+    const double* o = rec[v[0]].point;
+    const double* d = rec[v[1]].point;
+    double dir[3], len2 = 0.0;
+    for (int k = 0; k < 3; ++k) dir[k] = o[k] - d[k];
+    for (int k = 0; k < 3; ++k) len2 += dir[k] * dir[k];
+    const double len = sqrt(len2);
+    for (int k = 0; k < 3; ++k) dir[k] = dir[k] / len;
+    double* proj = (double*)malloc(sizeof(double) * n);
+    for (uint32_t i = 0; i < n; ++i) {
+        const double* p = rec[v[i]].point;
+        double acc = 0.0;
+        for (int k = 0; k < 3; ++k) acc += (o[k] - p[k]) * dir[k];
+        proj[i] = acc;
+    }
+    for (uint32_t i = 1; i < n; ++i) { /* stable insertion sort, ascending projection */
+        const double x = proj[i];
+        const uint32_t xv = v[i];
+        uint32_t j = i;
+        while (j > 0 && x < proj[j - 1]) {
+            proj[j] = proj[j - 1];
+            v[j] = v[j - 1];
+            --j;
+        }
+        proj[j] = x;
+        v[j] = xv;
+    }
+    free(proj);
+}
+
+int mco_cutpath_segments(const uint32_t* edge_f, uint32_t src_nf, const mco_record_t* rec, size_t n, mco_cutpath_t* out)
+{
+    memset(out, 0, sizeof(*out));
+    cp_entry_t* e = (cp_entry_t*)malloc(sizeof(cp_entry_t) * (2 * n + 1));
+    size_t m = 0;
+    for (size_t i = 0; i < n; ++i) {
+        /* kernel.cpp:2610-2640: the tested edge's faces; the face of h0 unless h0 is a border halfedge */
+        const uint32_t h0f = edge_f[2 * (size_t)rec[i].edge], h1f = edge_f[2 * (size_t)rec[i].edge + 1];
+        const uint32_t tested = rec[i].face;
+        const uint32_t own = h0f != MCO_NULL ? h0f : h1f;
+        const uint32_t other = own == h0f ? h1f : MCO_NULL; /* (an edge whose h0 has no face has no second face to add) */
+        if (own == MCO_NULL) {
+            free(e);
+            return -1;
+        }
+        const int edge_is_cut = own >= src_nf;
+        /* key = {source-mesh face, cut-mesh face} */
+        e[m].key = edge_is_cut ? ((uint64_t)tested << 32 | own) : ((uint64_t)own << 32 | tested);
+        e[m++].v = (uint32_t)i;
+        if (other != MCO_NULL) {
+            e[m].key = edge_is_cut ? ((uint64_t)tested << 32 | other) : ((uint64_t)other << 32 | tested);
+            e[m++].v = (uint32_t)i;
+        }
+    }
+    qsort(e, m, sizeof(cp_entry_t), cp_entry_cmp);
+    out->key = (uint64_t*)malloc(sizeof(uint64_t) * (m + 1));
+    out->off = (uint32_t*)malloc(sizeof(uint32_t) * (m + 2));
+    out->vtx = (uint32_t*)malloc(sizeof(uint32_t) * (m + 1));
+    size_t g = 0;
+    for (size_t i = 0; i < m; ++i) {
+        if (i == 0 || e[i].key != e[i - 1].key) {
+            out->key[g] = e[i].key;
+            out->off[g++] = (uint32_t)i;
+        }
+        out->vtx[i] = e[i].v;
+    }
+    out->off[g] = (uint32_t)m;
+    out->n_groups = g;
+    out->n_entries = m;
+    for (size_t k = 0; k < g; ++k) {
+        const uint32_t c = out->off[k + 1] - out->off[k];
+        if (c == 1) out->n_single++;
+        if (c > 2) cp_linear_projection_sort(rec, out->vtx + out->off[k], c);
+    }
+    free(e);
+    return 0;
+}
+
+void mco_cutpath_free(mco_cutpath_t* o)
+{
+    free(o->key);
+    free(o->off);
+    free(o->vtx);
+    memset(o, 0, sizeof(*o));
+}

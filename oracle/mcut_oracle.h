@@ -157,6 +157,23 @@ double mco_solid_angle_tri(const double a[3], const double b[3], const double c[
 double mco_solid_angle_quad(const double a[3], const double b[3], const double c[3], const double d[3], const double q[3]);
 double mco_winding_number(const double* xyz, const uint32_t* face_off, const uint32_t* face_vtx, uint32_t nf, const double q[3]);
 
+/* ---- cut-path segment table (the first consumer of the registry) -------------------------------------------- */
+/* What "Create edges with intersection points" (source/kernel.cpp:3332-3617) works from: cutpath_edge_creation_info, the
+ * registry's intersection points grouped by {source-mesh face, cut-mesh face} (filled at kernel.cpp:2601-2655: the tested
+ * face against each face incident to the tested edge; a std::map, so groups come in ascending (sm, cm) order and a group's
+ * points in registry order), with groups of more than two points put in order along their common line by
+ * linear_projection_sort (:1496-1531: projection of origin - p on normalize(origin - second point), std::sort ascending).
+ * A group of two points is one cut-path edge; a group of one point is the reference's late general-position violation
+ * (:3366-3440).  rec[i] is registry entry i (m0 vertex ps_vtx_cnt + i). */
+typedef struct mco_cutpath {
+    size_t n_groups, n_entries, n_single;
+    uint64_t* key; /* [n_groups] sm face << 32 | cm face (polygon-soup ids), ascending */
+    uint32_t* off; /* [n_groups + 1] */
+    uint32_t* vtx; /* [n_entries] registry indices */
+} mco_cutpath_t;
+int mco_cutpath_segments(const uint32_t* edge_f /* [ne*2] */, uint32_t src_nf, const mco_record_t* rec, size_t n, mco_cutpath_t* out);
+void mco_cutpath_free(mco_cutpath_t* o);
+
 #ifdef __cplusplus
 }
 #endif

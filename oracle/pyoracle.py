@@ -50,6 +50,11 @@ class NarrowOut(C.Structure):
 TEST_DTYPE = np.dtype([("edge", "<u4"), ("face", "<u4"), ("type", "S1"), ("pip", "S1"), ("sign_q", "i1"),
                        ("sign_r", "i1"), ("exact_q", "u1"), ("exact_r", "u1"), ("pad", "u1", (2,)),
                        ("point", "<f8", (3,))])
+class CutPath(C.Structure):
+    _fields_ = [("n_groups", C.c_size_t), ("n_entries", C.c_size_t), ("n_single", C.c_size_t),
+                ("key", c_u64p), ("off", c_u32p), ("vtx", c_u32p)]
+
+
 RECORD_DTYPE = np.dtype([("edge", "<u4"), ("face", "<u4"), ("point", "<f8", (3,))])
 
 
@@ -113,6 +118,10 @@ def lib() -> C.CDLL:
         L.mco_narrowphase.restype = C.c_int
         L.mco_narrow_free.argtypes = [C.POINTER(NarrowOut)]
         L.mco_narrow_free.restype = None
+        L.mco_cutpath_segments.argtypes = [c_u32p, C.c_uint32, C.POINTER(Record), C.c_size_t, C.POINTER(CutPath)]
+        L.mco_cutpath_segments.restype = C.c_int
+        L.mco_cutpath_free.argtypes = [C.POINTER(CutPath)]
+        L.mco_cutpath_free.restype = None
         _LIB = L
     return _LIB
 
@@ -363,6 +372,23 @@ def narrowphase(soup, pairs: np.ndarray, src_bb: np.ndarray, cut_bb: np.ndarray,
         res["cand_d"] = np.zeros(0)
         res["cand_maxcomp"] = np.zeros(0, dtype=np.int32)
     lib().mco_narrow_free(C.byref(out))
+    return res
+
+
+def cutpath_segments(edge_f: np.ndarray, src_nf: int, records: np.ndarray) -> Dict[str, object]:
+    """The cut-path segment table of a registry (mco_cutpath_segments): records[i] is registry entry i."""
+    rec = np.ascontiguousarray(records, dtype=RECORD_DTYPE)
+    ef = np.ascontiguousarray(edge_f, dtype=np.uint32)
+    out = CutPath()
+    rc = lib().mco_cutpath_segments(u32p(ef), int(src_nf), rec.ctypes.data_as(C.POINTER(Record)), rec.size, C.byref(out))
+    if rc != 0:
+        raise ValueError("cutpath_segments: a record names an edge without faces")
+    g, m = out.n_groups, out.n_entries
+    res = {"keys": np.ctypeslib.as_array(out.key, shape=(g,)).copy() if g else np.zeros(0, dtype=np.uint64),
+           "off": np.ctypeslib.as_array(out.off, shape=(g + 1,)).copy() if g else np.zeros(1, dtype=np.uint32),
+           "vtx": np.ctypeslib.as_array(out.vtx, shape=(m,)).copy() if m else np.zeros(0, dtype=np.uint32),
+           "n_single": int(out.n_single)}
+    lib().mco_cutpath_free(C.byref(out))
     return res
 
 

@@ -55,6 +55,24 @@ def check_cuda_against_fixture(gpu_ctx, fx, src, cut, flags):
             assert beq(pts, fx[f"d{k}_ipoints_sorted"]), "intersection points = the reference's m0 vertices"
 
 
+@pytest.mark.parametrize("pair", CORPUS_CASES)
+def test_cutpath_segment_table_on_reference_regression_corpus(oracle, gpu_ctx, pair):
+    """SURVEY §8-f4 on the corpus (polygon faces: face pairs with more than two intersection points occur): the device's
+    segment table of the last kernel invocation of every pair equals the oracle's."""
+    from mcut_b200 import stage
+    fx, src, cut, flags = load_corpus(pair)
+    k = int(fx["n_dispatch"][0]) - 1
+    kw = replay_inputs(fx, k, src, cut)
+    ref = oracle.intersect_stage(flags=flags, **kw)
+    if ref["status"] != 0:
+        pytest.skip("the last invocation of this pair has no registry")
+    got = stage.intersect_stage(gpu_ctx, flags=flags, want_boxes=False, want_cutpath=True, **kw)
+    want = oracle.cutpath_segments(ref["soup"].edge_f, ref["soup"].src_nf, ref["records"])
+    cp = got["cutpath"]
+    assert beq(cp["keys"], want["keys"]) and beq(cp["off"], want["off"]) and beq(cp["vtx"], want["vtx"])
+    assert cp["n_single"] == want["n_single"]
+
+
 def test_degenerate_candidate_face_reports_invalid_mesh(oracle, gpu_ctx):
     from mcut_b200 import stage
     from test_oracle_stage import degenerate_case

@@ -74,6 +74,23 @@ def test_stage_without_the_test_log_matches_oracle(oracle, gpu_ctx, case):
         assert beq(gr["edge"], rr["edge"]) and beq(gr["face"], rr["face"]) and beq(gr["point"], rr["point"]), "registry"
 
 
+@pytest.mark.parametrize("case", sorted(cases.ALL))
+def test_cutpath_segment_table_matches_oracle(oracle, gpu_ctx, case):
+    """SURVEY §8-f4: the registry grouped by {source face, cut face} (what kernel.cpp:3332-3617 consumes), groups in std::map
+    order, points in registry order, groups of more than two points along their line — device sort vs the oracle's table
+    (which tests/test_oracle_cutpath.py pins against the container of a live reference dispatch)."""
+    from mcut_b200 import stage
+    src, cut, flags = cases.ALL[case]()
+    ref = oracle.intersect_stage(src, cut, flags)
+    if ref["status"] != 0:
+        pytest.skip("no registry: the stage reports a general-position violation or an invalid mesh")
+    got = stage.intersect_stage(gpu_ctx, src, cut, flags, want_boxes=False, want_cutpath=True)
+    want = oracle.cutpath_segments(ref["soup"].edge_f, ref["soup"].src_nf, ref["records"])
+    cp = got["cutpath"]
+    assert beq(cp["keys"], want["keys"]) and beq(cp["off"], want["off"]) and beq(cp["vtx"], want["vtx"])
+    assert cp["n_single"] == want["n_single"]
+
+
 def test_perturbed_cut_frame(oracle, gpu_ctx):
     pert = np.array([1.3e-3, -0.7e-3, 2.1e-3])
     ref, got = run_both(oracle, gpu_ctx, "cube_cube_axis_aligned", perturbation=pert)

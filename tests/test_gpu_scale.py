@@ -35,6 +35,18 @@ def test_c2_two_spheres_1m(oracle, gpu_ctx):
     assert got["n_pairs"] == 34464 and got["n_records"] == 5100  # == the reference's own run (harness)
 
 
+def test_c2_cutpath_segment_table(oracle, gpu_ctx):
+    """f4 at BASELINE size: 5,100 registry records -> 5,100 face pairs of two points each (one closed intersection curve)."""
+    from mcut_b200 import stage
+    src, cut, flags = mg.c2_two_spheres(k=289)
+    ref = oracle.intersect_stage(src, cut, flags)
+    got = stage.intersect_stage(gpu_ctx, src, cut, flags, want_boxes=False, want_cutpath=True)
+    want = oracle.cutpath_segments(ref["soup"].edge_f, ref["soup"].src_nf, ref["records"])
+    cp = got["cutpath"]
+    assert beq(cp["keys"], want["keys"]) and beq(cp["off"], want["off"]) and beq(cp["vtx"], want["vtx"])
+    assert cp["keys"].size == 5100 and cp["n_single"] == 0 and np.all(np.diff(cp["off"]) == 2)
+
+
 def test_c3_terrain_4m_one_plane(oracle, gpu_ctx):
     """One of C3's 256 dispatches: 3,998,792-triangle terrain vs a single huge triangle (a one-leaf cut BVH)."""
     ter = mg.terrain()
