@@ -45,6 +45,7 @@ int fetch_counters(mcb200_ctx* ctx, mcb200_result* res)
                 res->h.pair_seg_max);
     }
     if (res->pairs_order_unchecked) MCB_TRY(sort_pairs_fallback(ctx, res)); // a face with very many pairs: see traverse.cu
+    if (res->record_radix_pending) MCB_TRY(narrowphase_finish_record_order(ctx, res));
     return 0;
 }
 namespace {
@@ -1110,6 +1111,7 @@ int mcb200_intersect_stage_host(mcb200_ctx* ctx, const mcb200_host_mesh* hsrc, c
     if (!ctx || !hsrc || !hcut || !res) return MCB200_ERR_INVALID;
     MCB_CUDA(ctx, cudaSetDevice(ctx->device));
     ctx->use_main();
+    flags |= MCB200_NARROW_INTERNAL_LAZY_RADIX; // (results of this call are only reachable through mcb200_result_counts)
     const bool src_res = (flags & MCB200_STAGE_SRC_RESIDENT) != 0, cut_res = (flags & MCB200_STAGE_CUT_RESIDENT) != 0;
     std::vector<uint32_t> off_s, off_c;
     MCB_TRY(stage_mesh_describe(ctx, 0, hsrc, src_res, off_s));

@@ -305,6 +305,7 @@ struct mcb200_result {
     size_t cp_groups = 0, cp_entries = 0;
     bool cp_valid = false;
     size_t cap_exact = 0;
+    bool record_radix_pending = false; // the registry's radix order was deferred to the next read of the counters
     bool tri_queues = false; // the last narrowphase used the triangle pipeline (split exact queue + mid queue)
     dbuf records; // mcb200_record [cap_records]
     dbuf rec_keys; // u64

@@ -22,11 +22,16 @@ int narrowphase_run(mcb200_ctx* ctx, const mcb200_soup* soup, const mcb200_mesh*
     mcb200_result* res, uint32_t flags);
 // internal flag (never set by callers of the C-ABI): this run is one shard of a multi-GPU dispatch — no plane rows, no orders
 #define MCB200_NARROW_INTERNAL_PARTIAL 0x40000000u
+// The radix path of the registry order (ten launches that return at once unless there are more than 16384 records) is not
+// enqueued; fetch_counters runs it when the count calls for it.  Set by the host-array entry points, whose callers cannot
+// look at a record before they have asked for the counts.
+#define MCB200_NARROW_INTERNAL_LAZY_RADIX 0x20000000u
 int narrowphase_planes(mcb200_ctx* ctx, const mcb200_soup* soup, const mcb200_mesh* src, const mcb200_mesh* cut, mcb200_result* res);
 int narrowphase_prezero(mcb200_ctx* ctx, const mcb200_soup* soup, mcb200_result* res);
 int soup_face_vtx_device(mcb200_ctx* ctx, const mcb200_mesh* src, const mcb200_mesh* cut, mcb200_soup* soup);
 int narrowphase_sort_records(mcb200_ctx* ctx, mcb200_result* res, int part = 3);
 int narrowphase_sort_tests(mcb200_ctx* ctx, mcb200_result* res, int part = 3);
+int narrowphase_finish_record_order(mcb200_ctx* ctx, mcb200_result* res); // the deferred radix path, if the count needs it
 // api.cu: the stage body shared by the stage entry points (order = false: a shard — pairs and records stay unordered)
 int stage_reserve(mcb200_ctx* ctx, mcb200_mesh* src, mcb200_mesh* cut, const mcb200_soup* soup, mcb200_result* res, uint32_t flags);
 int stage_body(mcb200_ctx* ctx, mcb200_mesh* src, mcb200_mesh* cut, double cut_eps, mcb200_soup* soup, mcb200_result* res, uint32_t flags,

@@ -1113,7 +1113,9 @@ int narrowphase_run(mcb200_ctx* ctx, const mcb200_soup* soup, const mcb200_mesh*
     MCB_CUDA(ctx, cudaEventRecord(ctx->ev_np3, lane));
     MCB_CUDA(ctx, cudaStreamWaitEvent(ctx->bg, ctx->ev_np3, 0));
     ctx->use_bg();
-    int rc = narrowphase_sort_records(ctx, res, 2);
+    const bool lazy_radix = (flags & MCB200_NARROW_INTERNAL_LAZY_RADIX) != 0 && !want_log;
+    res->record_radix_pending = lazy_radix;
+    int rc = lazy_radix ? 0 : narrowphase_sort_records(ctx, res, 2);
     if (!rc && want_log) rc = narrowphase_sort_tests(ctx, res, 2);
     cudaEventRecord(ctx->ev_np2, ctx->bg);
     ctx->cur = lane;
@@ -1173,6 +1175,19 @@ int narrowphase_sort_records(mcb200_ctx* ctx, mcb200_result* res, int part)
     MCB_TRY(sort_items<mcb200_record>(ctx, res, res->records.as<mcb200_record>(), res->records_sorted.as<mcb200_record>(),
         res->rec_keys, res->rec_idx, &c->n_records, res->cap_records, res->nf_ps, res->ne_ps, part));
     if (part & 1) res->records_sorted_valid = true; // narrowphase_run issues part 2 first, part 1 last
+    return 0;
+}
+
+// fetch_counters has just read the counters of a run whose radix path was deferred (the stream is idle)
+int narrowphase_finish_record_order(mcb200_ctx* ctx, mcb200_result* res)
+{
+    res->record_radix_pending = false;
+    if (res->h.n_records <= SMALL_SORT || res->h.n_records > res->cap_records) return 0;
+    ctx->use_main();
+    result_counters_t* c = res->counters.as<result_counters_t>();
+    MCB_TRY(sort_items<mcb200_record>(ctx, res, res->records.as<mcb200_record>(), res->records_sorted.as<mcb200_record>(), res->rec_keys,
+        res->rec_idx, &c->n_records, res->cap_records, res->nf_ps, res->ne_ps, 2));
+    MCB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return 0;
 }
 
