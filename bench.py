@@ -88,6 +88,23 @@ def workload(name: str):
     raise SystemExit(f"unknown workload {name}")
 
 
+# The reference's own stage is QUADRATIC in the number of faces one face overlaps: on C3's section (one supertriangle over the
+# whole terrain) it takes 94 s at 250,632 triangles and 372 s at 500,000 (measured, 8 cores), i.e. hours at the workload's
+# 3,998,792.  The CPU legs of C3 therefore run a bounded sample — the same terrain recipe at 63,368 triangles — and say so.
+C3_CPU_SAMPLE_N = 179
+C3_CPU_SAMPLE_NOTE = ("BOUNDED SAMPLE: the same terrain recipe at 63,368 triangles (n = 179), because the reference's stage is quadratic "
+                      "here (94 s at 250,632 triangles, 372 s at 500,000: hours at the workload's 3,998,792); ")
+
+
+def cpu_workload(name: str):
+    """what the CPU legs (cpu_baseline, --impl reference) run: the workload itself, or a bounded sample of it + a note"""
+    if name == "c3":
+        ter = meshgen.terrain(n=C3_CPU_SAMPLE_N)
+        nrm, _ = meshgen.c3_plane(0)
+        return (ter, meshgen.c3_supertriangle(ter[0], nrm), DBL), C3_CPU_SAMPLE_NOTE
+    return workload(name), ""
+
+
 def base_config(name: str, world: int):
     """the keys both arms (ours and --impl reference) print"""
     return {"workload": WORKLOADS[name], "workload_id": name,
@@ -254,7 +271,7 @@ def run_reference_arm(args):
                     inputs.append(ip)
                 streams_eff = min(cores, max(streams * 8, 8))  # the tutorial pattern: many contexts in flight, no helpers
             else:
-                ter = meshgen.terrain()
+                ter = meshgen.terrain(n=C3_CPU_SAMPLE_N)  # (see C3_CPU_SAMPLE_NOTE)
                 dummy = (np.zeros((3, 3)), np.array([0, 1, 2], dtype=np.uint32), None)
                 ip = os.path.join(td, "in.mcb")
                 write_input(ter, dummy, DBL, ip)
@@ -267,11 +284,11 @@ def run_reference_arm(args):
                                                                (lambda i: extra_of(i + args.warmup)) if extra_of else None)
             ms_per_step = wall * 1e3 / total
             value = pairs / wall
-            sample = (f"{total} dispatches, {streams_eff} harness processes in flight with {helpers} helper threads each; value = pairs / "
+            sample = (C3_CPU_SAMPLE_NOTE if name == "c3batch" else "") + (f"{total} dispatches, {streams_eff} harness processes in flight with {helpers} helper threads each; value = pairs / "
                       "wall time of the batch (each process = one mcDispatch of the unmodified reference cut short after its narrowphase)")
             cfg.update({"dispatches": total, "pairs_per_dispatch": pairs / max(total, 1)})
         else:
-            src, cut, flags = workload(name)
+            (src, cut, flags), sample_note = cpu_workload(name)
             times, n_pairs = [], 0
             if kind == "reference":
                 write_input(src, cut, flags, os.path.join(td, "in.mcb"))
@@ -285,7 +302,7 @@ def run_reference_arm(args):
                     times.append(ms)
             ms_per_step = float(np.mean(times))
             value = streams * n_pairs / (ms_per_step * 1e-3) if kind == "reference" else n_pairs / (ms_per_step * 1e-3)
-            sample = (f"{args.steps} whole intersect stages of the full workload on {streams} stream(s); each = one mcDispatch of the unmodified "
+            sample = sample_note + (f"{args.steps} whole intersect stages of the {'sample' if sample_note else 'full workload'} on {streams} stream(s); each = one mcDispatch of the unmodified "
                       "reference cut short after its narrowphase, stage ms = sum of the reference's own timers (build_oibvh x2, "
                       "intersectOIBVHs, the five kernel.cpp:1781-3231 stages), max over the streams") if kind == "reference" else \
                 f"{args.steps} runs of the oracle port (single thread)"
@@ -833,8 +850,9 @@ def run_ours(args):
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cores = os.cpu_count() or 1
         with tempfile.TemporaryDirectory() as td:
+            (csrc, ccut, cflags), sample_note = cpu_workload(name)
             if have_reference_binary():
-                write_input(src, cut, flags, os.path.join(td, "in.mcb"))
+                write_input(csrc, ccut, cflags, os.path.join(td, "in.mcb"))
                 runs, npairs_ref = [], 0
                 for _ in range(2):
                     w, sms, npairs_ref, helpers = reference_streams([os.path.join(td, "in.mcb")], 1, cores, td)
@@ -842,13 +860,13 @@ def run_ours(args):
                 best = min(runs)
                 cpu = {"value": npairs_ref / (best * 1e-3), "unit": UNIT, "cores": cores, "kind": "reference",
                        "ms_per_step": best, "pairs": npairs_ref,
-                       "sample": "2 whole intersect stages of the full workload (best of 2): one mcDispatch of the unmodified "
+                       "sample": sample_note + "2 whole intersect stages (best of 2): one mcDispatch of the unmodified "
                                  "reference each, cut short after its narrowphase; stage ms = the reference's own timers "
                                  "(build_oibvh x2, intersectOIBVHs, kernel.cpp:1781-3231), helper pool = cores-1 threads"}
             else:
-                ms, npairs_ref, nrec = oracle_port_stage_once(src, cut, flags)
+                ms, npairs_ref, nrec = oracle_port_stage_once(csrc, ccut, cflags)
                 cpu = {"value": npairs_ref / (ms * 1e-3), "unit": UNIT, "cores": 1, "kind": "port", "ms_per_step": ms,
-                       "pairs": npairs_ref, "sample": "1 run of the single-threaded oracle port on the full workload"}
+                       "pairs": npairs_ref, "sample": sample_note + "1 run of the single-threaded oracle port"}
 
     # ---- e2e_dropin (--dropin): what a LIVE mcDispatch pays for the stage through the adapter + hooked kernel ----
     dropin = None
