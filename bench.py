@@ -793,6 +793,15 @@ def run_ours(args):
                               "tests_per_launch": counts["n_exact"], "ms_per_launch": kern[kname]["ms_per_launch"],
                               "share_of_step": kern[kname]["ms_per_step"] / step_kernel_ms})
             continue
+        if kname == "k_tri_resolve" and counts["n_exact"] > 0:
+            # the kernel that settles the stage-A failures (exact sign from a 24-term error-free sum, in registers): besides its
+            # byte model below, the FP64 pipe's busy share from the committed ncu capture of this workload
+            pct = fact.get("fp64_pipe_pct")
+            rooflines.append({"kernel": kname, "bound": "fp64", "achieved": pct, "peak": 100.0, "unit": "% of FP64 pipe cycles",
+                              "frac": (pct / 100.0) if pct is not None else None, "traffic": fact.get("dram_bytes_per_launch"),
+                              "peak_source": "ncu capture of this workload under profiles/" if pct is not None else "not captured",
+                              "tests_per_launch": counts["n_exact"], "ms_per_launch": kern[kname]["ms_per_launch"],
+                              "share_of_step": kern[kname]["ms_per_step"] / step_kernel_ms})
         if ab is None:
             continue
         achieved = ab / (kern[kname]["ms_per_launch"] * 1e-3) / 1e9
