@@ -64,3 +64,34 @@ def test_absolute_eps(stage):
     bb = np.array([1.0, 2.0, 3.0, 4.0, 6.0, 15.0])
     assert stage.cut_bbox_eps(bb, 1e-4, True) == 1e-4
     assert stage.cut_bbox_eps(bb, 1e-4, False) == np.sqrt(0.0 + 9.0 + 16.0 + 144.0) * 1e-4
+
+
+def test_reference_edge_order_and_rank_agree(stage, oracle):
+    """mcb200_reference_edge_order (compact arrays: what the adapter calls inside a live dispatch) and mcb200_reference_edge_rank
+    (arrays indexed by face id) replay the same hash map: order[rank[e]] == e for every edge of a candidate face, edges of no
+    candidate face have no rank, and the helper-thread count changes the order only above 1024 candidate faces / edges
+    (tpool.h:354-392).  The order itself is pinned by tests/test_hook_cpu.py against the unmodified reference."""
+    import ctypes as C
+    from mcut_b200 import _lib
+    src, cut, flags = cases.ALL["spheres_k64"]()
+    ref = oracle.intersect_stage(src, cut, flags)
+    soup = ref["soup"]
+    cand = np.ascontiguousarray(ref["cand_faces"], dtype=np.uint32)
+    assert cand.size > 1024
+    p = lambda a: a.ctypes.data_as(C.POINTER(C.c_uint32))  # noqa: E731
+    orders = {}
+    for helpers in (0, 3):
+        rank = stage.reference_edge_rank(cand, soup.face_off, soup.face_edge, soup.ne, helpers)
+        slots = np.ascontiguousarray(np.concatenate([soup.face_edge[soup.face_off[f]:soup.face_off[f + 1]] for f in cand]), dtype=np.uint32)
+        off = np.ascontiguousarray(np.concatenate([[0], np.cumsum([soup.face_off[f + 1] - soup.face_off[f] for f in cand])]), dtype=np.uint32)
+        order = np.zeros(slots.size, dtype=np.uint32)
+        n = C.c_uint32(0)
+        rc = _lib.lib().mcb200_reference_edge_order(cand.size, p(off), p(slots), helpers, p(order), C.byref(n))
+        assert rc == 0
+        order = order[:n.value]
+        assert np.array_equal(np.sort(order), np.unique(slots)), "every edge of a candidate face exactly once"
+        assert np.array_equal(rank[order], np.arange(order.size, dtype=np.uint32))
+        no_rank = np.setdiff1d(np.arange(soup.ne, dtype=np.uint32), order)
+        assert np.all(rank[no_rank] == 0xFFFFFFFF)
+        orders[helpers] = order
+    assert not np.array_equal(orders[0], orders[3]), "more than 1024 candidate faces: the block layout depends on the helper count"
