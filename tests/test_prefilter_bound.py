@@ -100,3 +100,71 @@ def test_prefilter_sign_against_exact_arithmetic():
         exact = (r[0][0] * (r[1][1] * r[2][2] - r[1][2] * r[2][1]) - r[0][1] * (r[1][0] * r[2][2] - r[1][2] * r[2][0])
                  + r[0][2] * (r[1][0] * r[2][1] - r[1][1] * r[2][0]))
         assert exact != 0 and (1 if exact > 0 else -1) == side[i], i
+
+
+# ---- the in-register exact sign (predicates.cuh: det3_sign_exact), restated in Python floats -----------------------------
+def _two_sum(a, b):
+    x = a + b
+    bv = x - a
+    av = x - bv
+    return x, (a - av) + (b - bv)
+
+
+def _two_product(a, b):  # Dekker / Veltkamp: the same (product, error) pair an FMA gives
+    p = a * b
+    def split(x):
+        c = 134217729.0 * x
+        hi = c - (c - x)
+        return hi, x - hi
+    ah, al = split(a)
+    bh, bl = split(b)
+    return p, al * bl - (((p - ah * bh) - al * bh) - ah * bl)
+
+
+def _det3_sign_exact(r):
+    """r = rows a, b, c (exact differences).  Returns (decided, sign, passes)."""
+    (ax, ay, az), (bx, by, bz), (cx, cy, cz) = r
+    t = []
+    for x, y, z in ((bx, cy, az), (-cx, by, az), (cx, ay, bz), (-ax, cy, bz), (ax, by, cz), (-bx, ay, cz)):
+        p, e = _two_product(x, y)
+        lo = _two_product(e, z)
+        hi = _two_product(p, z)
+        t += [lo[0], lo[1], hi[0], hi[1]]
+    for n_pass in range(1, 7):
+        for i in range(1, 24):
+            t[i], t[i - 1] = _two_sum(t[i], t[i - 1])
+        rest = sum(abs(x) for x in t[:23])
+        if rest == 0.0 or abs(t[23]) > 2.0 * rest:
+            return True, (t[23] > 0) - (t[23] < 0), n_pass
+    return False, 0, 6
+
+
+def test_exact_sign_by_distillation_matches_integer_determinants():
+    """rows on a lattice (integers * 2^-20), many of them nearly dependent: the determinant is tiny against its terms or
+    exactly zero — the regime the device kernel k_tri_resolve is there for"""
+    rng = np.random.default_rng(17)
+    undecided, zeros, passes = 0, 0, [0] * 7
+    for k in range(20000):
+        a = rng.integers(-2 ** 30, 2 ** 30, size=3)
+        b = rng.integers(-2 ** 30, 2 ** 30, size=3)
+        mode = k % 4
+        if mode == 0:
+            c = rng.integers(-2 ** 30, 2 ** 30, size=3)
+        else:  # c = i*a + j*b (+ a tiny lattice step or nothing): |det| is a few units against terms of 2^90
+            i, j = rng.integers(-3, 4, size=2)
+            c = i * a + j * b
+            if mode != 3:
+                c = c + rng.integers(-2, 3, size=3)
+        rows_int = [[int(v) for v in r] for r in (a, b, c)]
+        rows = [[v * 2.0 ** -20 for v in r] for r in rows_int]
+        assert all(float(int(v * 2 ** 20)) == v * 2 ** 20 for r in rows for v in r)
+        (ax, ay, az), (bx, by, bz), (cx, cy, cz) = rows_int
+        exact = az * (bx * cy - cx * by) + bz * (cx * ay - ax * cy) + cz * (ax * by - bx * ay)
+        ok, sg, n_pass = _det3_sign_exact(rows)
+        if not ok:
+            undecided += 1
+            continue
+        passes[n_pass] += 1
+        zeros += exact == 0
+        assert sg == (exact > 0) - (exact < 0), (k, exact)
+    assert undecided == 0 and zeros > 1000 and sum(passes[2:]) > 3000  # cancellation really happened, and was resolved
